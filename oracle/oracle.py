@@ -1,0 +1,247 @@
+"""ctypes front-end to the CPU oracle (oracle/libpadeops_oracle.so).
+
+TEST INFRASTRUCTURE ONLY.  Import this from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs — never from padeops_b200/.
+
+Arrays follow the reference's Fortran layout: a field f(n1,n2,n3) is a numpy array of shape
+(n3, n2, n1), C-contiguous, so that the first Fortran index is the fastest one in memory.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libpadeops_oracle.so")
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, s) for s in ("padeops_oracle.c", "decomp_oracle.c", "spectral_oracle.c")]
+    if (not force) and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
+        return _SO
+    subprocess.check_call(["make", "-C", _HERE, "-s", "all"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+    return _lib
+
+
+def _p(a):
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(_dp)
+
+
+# ---------------------------------------------------------------- LU tables
+def penta_lu(n, e, a, d, c, f):
+    LU = np.zeros((9, n))
+    lib().pdo_oracle_penta_lu(C.c_int(n), C.c_double(e), C.c_double(a), C.c_double(d), C.c_double(c), C.c_double(f), _p(LU))
+    return LU
+
+
+def tri_lu(n, b, d, a):
+    LU = np.zeros((5, n))
+    lib().pdo_oracle_tri_lu(C.c_int(n), C.c_double(b), C.c_double(d), C.c_double(a), _p(LU))
+    return LU
+
+
+def cd10_lu(n, which):
+    LU = np.zeros((9, n))
+    ierr = lib().pdo_oracle_cd10_lu(C.c_int(n), C.c_int(which), _p(LU))
+    return ierr, LU
+
+
+def cd06_lu(n):
+    LU = np.zeros((5, n))
+    ierr = lib().pdo_oracle_cd06_lu(C.c_int(n), _p(LU))
+    return ierr, LU
+
+
+def cf90_lu(n):
+    LU = np.zeros((9, n))
+    ierr = lib().pdo_oracle_cf90_lu(C.c_int(n), _p(LU))
+    return ierr, LU
+
+
+def stagg_lu(n, which):
+    LU = np.zeros((5, n))
+    ierr = lib().pdo_oracle_stagg_lu(C.c_int(n), C.c_int(which), _p(LU))
+    return ierr, LU
+
+
+# ---------------------------------------------------------------- operators
+def _na_nb(f, axis):
+    n3, n2, n1 = f.shape
+    if axis == 0:
+        return n1, n2, n3
+    if axis == 1:
+        return n2, n1, n3
+    return n3, n1, n2
+
+
+def cd10(f, dx, axis, which=1):
+    """cd10%dd1/dd2/dd3 (which=1) or d2d1/d2d2/d2d3 (which=2) along `axis` (0=x fastest)."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    n, na, nb = _na_nb(f, axis)
+    ierr, LU = cd10_lu(n, which)
+    assert ierr == 0
+    out = np.empty_like(f)
+    lib().pdo_oracle_cd10(_p(LU), C.c_int(n), C.c_double(dx), C.c_int(which), C.c_int(axis), _p(f), _p(out),
+                          C.c_int64(na), C.c_int64(nb))
+    return out
+
+
+def cd06(f, dx, axis):
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    n, na, nb = _na_nb(f, axis)
+    ierr, LU = cd06_lu(n)
+    assert ierr == 0
+    out = np.empty_like(f)
+    lib().pdo_oracle_cd06(_p(LU), C.c_int(n), C.c_double(dx), C.c_int(axis), _p(f), _p(out), C.c_int64(na), C.c_int64(nb))
+    return out
+
+
+def cf90(f, axis):
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    n, na, nb = _na_nb(f, axis)
+    ierr, LU = cf90_lu(n)
+    assert ierr == 0
+    out = np.empty_like(f)
+    lib().pdo_oracle_cf90(_p(LU), C.c_int(n), C.c_int(axis), _p(f), _p(out), C.c_int64(na), C.c_int64(nb))
+    return out
+
+
+def gaussian(f, axis):
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    n, na, nb = _na_nb(f, axis)
+    out = np.empty_like(f)
+    lib().pdo_oracle_gaussian(C.c_int(n), C.c_int(axis), _p(f), _p(out), C.c_int64(na), C.c_int64(nb))
+    return out
+
+
+STAGG_OPS = ("ddz_E2C", "ddz_C2E", "interp_E2C", "interp_C2E", "d2dz2_C2C", "d2dz2_E2E")
+_STAGG_LU = (0, 0, 2, 2, 1, 1)
+_STAGG_IN_E = (True, False, True, False, False, True)
+_STAGG_OUT_E = (False, True, False, True, False, True)
+
+
+def stagg(op, f, n, dz):
+    """Periodic cd06stagg op along z.  f: (nz_in, n2, n1) real or complex; n = number of cells."""
+    if isinstance(op, str):
+        op = STAGG_OPS.index(op)
+    cplx = np.iscomplexobj(f)
+    f = np.ascontiguousarray(f, dtype=np.complex128 if cplx else np.float64)
+    nin = n + 1 if _STAGG_IN_E[op] else n
+    nout = n + 1 if _STAGG_OUT_E[op] else n
+    assert f.shape[0] == nin, (f.shape, nin)
+    out = np.zeros((nout,) + f.shape[1:], dtype=f.dtype)
+    m = f.shape[1] * f.shape[2] * (2 if cplx else 1)
+    ierr, LU = stagg_lu(n, _STAGG_LU[op])
+    assert ierr == 0
+    lib().pdo_oracle_stagg(_p(LU), C.c_int(n), C.c_double(dz), C.c_int(op), _p(f.view(np.float64)), _p(out.view(np.float64)),
+                           C.c_int64(m))
+    return out
+
+
+# ---------------------------------------------------------------- decomposition / transposes
+class _Decomp(C.Structure):
+    _fields_ = [(nm, C.c_int * 3) for nm in ("xst", "xen", "xsz", "yst", "yen", "ysz", "zst", "zen", "zsz")]
+
+
+def distribute(n, p):
+    st = (C.c_int * p)()
+    en = (C.c_int * p)()
+    sz = (C.c_int * p)()
+    lib().pdo_oracle_distribute(C.c_int(n), C.c_int(p), st, en, sz)
+    return list(st), list(en), list(sz)
+
+
+def decomp_info(nx, ny, nz, p_row, p_col, rank):
+    d = _Decomp()
+    lib().pdo_oracle_decomp_info(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(p_row), C.c_int(p_col), C.c_int(rank), C.byref(d))
+    return {nm: tuple(getattr(d, nm)) for nm, _ in _Decomp._fields_}
+
+
+_PEN_OF_DIR = {0: ("x", "y"), 1: ("y", "x"), 2: ("y", "z"), 3: ("z", "y")}
+
+
+def transpose(direction, nx, ny, nz, p_row, p_col, src_list):
+    """Run the reference's pack → ALLTOALLV → unpack with all ranks simulated.
+
+    direction: 0 x→y, 1 y→x, 2 y→z, 3 z→y (or the strings 'x2y','y2x','y2z','z2y').
+    src_list[r]: rank r's pencil, shape (s3, s2, s1), float64 or complex128.  Returns dst_list.
+    """
+    if isinstance(direction, str):
+        direction = ("x2y", "y2x", "y2z", "z2y").index(direction)
+    P = p_row * p_col
+    cplx = np.iscomplexobj(src_list[0])
+    dt = np.complex128 if cplx else np.float64
+    w = 2 if cplx else 1
+    infos = [decomp_info(nx, ny, nz, p_row, p_col, r) for r in range(P)]
+    sp, dp_ = _PEN_OF_DIR[direction]
+    for r in range(P):
+        assert tuple(src_list[r].shape) == tuple(reversed(infos[r][sp + "sz"])), (src_list[r].shape, infos[r][sp + "sz"])
+    src_all = np.concatenate([np.ascontiguousarray(s, dtype=dt).ravel() for s in src_list])
+    dsz = [infos[r][dp_ + "sz"] for r in range(P)]
+    tot = sum(int(np.prod(s)) for s in dsz)
+    dst_all = np.zeros(tot, dtype=dt)
+    lib().pdo_oracle_transpose(C.c_int(direction), C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(p_row), C.c_int(p_col),
+                               C.c_int(w), _p(src_all.view(np.float64)), _p(dst_all.view(np.float64)))
+    out, off = [], 0
+    for r in range(P):
+        cnt = int(np.prod(dsz[r]))
+        out.append(dst_all[off:off + cnt].reshape(tuple(reversed(dsz[r]))).copy())
+        off += cnt
+    return out
+
+
+def scatter_global(g, nx, ny, nz, p_row, p_col, pencil):
+    """Cut a global array g (nz, ny, nx) into the per-rank pencils 2DECOMP would hold."""
+    out = []
+    for r in range(p_row * p_col):
+        d = decomp_info(nx, ny, nz, p_row, p_col, r)
+        st, en = d[pencil + "st"], d[pencil + "en"]
+        out.append(np.ascontiguousarray(g[st[2] - 1:en[2], st[1] - 1:en[1], st[0] - 1:en[0]]))
+    return out
+
+
+# ---------------------------------------------------------------- spectral
+def wavenums(n, dx):
+    k = np.zeros(n)
+    lib().pdo_oracle_wavenums(C.c_int(n), C.c_double(dx), _p(k))
+    return k
+
+
+def poisson_multiply(rhs_hat, kx, ky, kz, have_zero=True):
+    a = np.ascontiguousarray(rhs_hat, dtype=np.complex128).copy()
+    nzh, nyh, nxh = a.shape
+    lib().pdo_oracle_poisson_multiply(_p(a.view(np.float64)), C.c_int64(nxh), C.c_int64(nyh), C.c_int64(nzh),
+                                      _p(np.ascontiguousarray(kx)), _p(np.ascontiguousarray(ky)), _p(np.ascontiguousarray(kz)),
+                                      C.c_int(1 if have_zero else 0))
+    return a
+
+
+def poisson_solve(rhs, dx, dy, dz):
+    """PoissonPeriodic%poisson_solve on one rank (dir_id=1): fft3_x2z → multiply → ifft3_z2x
+    (utilities/PoissonPeriodic.F90:62-74; fft_3d.F90:588-613, 670-696).  rhs: (nz, ny, nx) real.
+    FFT arithmetic: numpy pocketfft standing in for FFTW (unnormalised forward, 1/(nx ny nz) on inverse)."""
+    nz, ny, nx = rhs.shape
+    h = np.fft.rfft(rhs, axis=2)
+    h = np.fft.fft(h, axis=1)
+    h = np.fft.fft(h, axis=0)
+    kx = wavenums(nx, dx)[: nx // 2 + 1]
+    ky = wavenums(ny, dy)
+    kz = wavenums(nz, dz)
+    h = poisson_multiply(h, kx, ky, kz, True)
+    h = np.fft.ifft(h, axis=0) * nz  # FFTW backward is unnormalised
+    h = np.fft.ifft(h, axis=1) * ny
+    f = np.fft.irfft(h, n=nx, axis=2) * nx
+    return f * (1.0 / (float(nx) * float(ny) * float(nz)))
