@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the PadeOps operator hot path on B200.
+
+Metric (BASELINE.json): Gpoints/s per compact derivative, with the HBM-roofline fraction.
+Workload at N=1: CD10 ddx + ddy + ddz on a 1024^3 double-precision periodic field (the north_star target
+config; one "step" = the three derivative calls, 3 * 2^30 points).  At N>1 (torchrun, one rank per GPU)
+the global field is 1024 x 1024 x (1024 N), decomposed 1 x N like 2DECOMP would: every rank owns 2^30
+points (weak scaling); ddx / ddy are pencil-local, ddz goes y->z transpose, derivative, z->y transpose
+over NCCL, exactly the choreography of tests/test_derivatives_parallel.F90:94-126.
+
+`value`       device-resident throughput (inputs already in HBM), CUDA-event timed, max over ranks.
+`e2e`         same metric through the C ABI with HOST (pinned) buffers: H2D + kernel + D2H per call.
+`roofline`    dominant kernel: 16 B/pt algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json.
+`cpu_baseline` the oracle port (flat-MPI emulation: one worker per host core, each owning a pencil),
+              timed on a bounded 512^3 sample.  `--impl reference` prints that arm alone.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Gpoints/s per CD10 derivative (ddx+ddy+ddz), double precision"
+UNIT = "Gpoints/s"
+BYTES_PER_POINT = 16.0  # read f once + write df once
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement run the way the reference runs — flat MPI, one worker per core,
+# each worker owning the pencil a 2DECOMP rank would own (transposes between pencils are not timed,
+# which favours the CPU).
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(n_global, steps, warmup, cores=None):
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    O.build()
+    cores = cores or os.cpu_count() or 1
+    n = n_global
+    d = 2 * np.pi / n
+    # 1 x C slabs: each worker owns (n, n, n/C) of the x/y-pencil and (n, n/C, n) of the z-pencil
+    nloc = [n // cores + (1 if i >= cores - n % cores else 0) for i in range(cores)]
+    rng = np.random.default_rng(20240607)
+    fxy = [rng.standard_normal((max(1, nl), n, n)) for nl in nloc]     # f(n, n, nl): x- and y-pencil
+    fz = [rng.standard_normal((n, max(1, nl), n)) for nl in nloc]      # f(n, nl, n): z-pencil
+    O.cd10(fxy[0][:1], d, 0, 1)  # builds LU once (untimed, like init)
+
+    def work(i):
+        O.cd10(fxy[i], d, 0, 1)
+        O.cd10(fxy[i], d, 1, 1)
+        O.cd10(fz[i], d, 2, 1)
+
+    pts = 3.0 * n ** 3
+    times = []
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            list(ex.map(work, range(cores)))
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    t = sum(times) / len(times)
+    return {"value": pts / t / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"CD10 ddx+ddy+ddz on a {n}^3 field split 1x{cores} (one worker per core, own pencil each); "
+                      f"{len(times)} passes, {t*1e3:.1f} ms/pass; oracle/padeops_oracle.c compiled -O3 -march=native"}, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    cb, t = cpu_arm(512, steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cd10 ddx+ddy+ddz, periodic, 512^3 sample of the 1024^3 workload (CPU arm)", "n": 512},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, dev):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(dev), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import padeops_b200 as pdo
+    from padeops_b200 import decomp as dc
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = pdo.lib()
+    n = args.n
+    # global field: N * n^3 points, as cubic as the grid allows; 2DECOMP grid p_row x p_col
+    grids = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
+    mult = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}
+    assert world in grids, "bench.py supports 1, 2, 4 or 8 GPUs"
+    p_row, p_col = grids[world]
+    nx, ny, nz = (n * m for m in mult[world])
+    dx, dy, dz = 2 * np.pi / nx, 2 * np.pi / ny, 2 * np.pi / nz
+    gp = pdo.decomp_2d.init(nx, ny, nz, p_row, p_col)
+    npts_rank = gp.ysz[0] * gp.ysz[1] * gp.ysz[2]
+    der = pdo.derivatives()
+    der.init(gp, dx, dy, dz, True, True, True, "cd10", "cd10", "cd10")
+
+    def pencil(sz):
+        return torch.empty(tuple(reversed(sz)), dtype=torch.float64, device="cuda")
+
+    g = torch.Generator(device="cuda").manual_seed(20240607 + rank)
+    f = torch.rand(tuple(reversed(gp.ysz)), dtype=torch.float64, device="cuda", generator=g)   # the field lives in the y-pencil
+    df = torch.empty_like(f)
+    tin = pencil(gp.xsz) if world > 1 else None      # transposed copy of f (x- or z-pencil; same volume)
+    tout = pencil(gp.xsz) if world > 1 else None
+    st = torch.cuda.current_stream()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+
+    def step(i=None):
+        # tests/test_derivatives_parallel.F90:94-126: transpose to the pencil where the axis is local, differentiate, transpose back
+        e = ev[i] if i is not None else None
+        if e: e[0].record(st)
+        if p_row > 1:
+            a, b = tin.view(tuple(reversed(gp.xsz))), tout.view(tuple(reversed(gp.xsz)))
+            dc.transpose_y_to_x(f, a, gp)
+            der.ddx(a, b)
+            dc.transpose_x_to_y(b, df, gp)
+        else:
+            der.ddx(f, df)            # one rank in the row communicator: x- and y-pencils coincide
+        if e: e[1].record(st)
+        der.ddy(f, df)
+        if e: e[2].record(st)
+        if p_col > 1:
+            a, b = tin.view(tuple(reversed(gp.zsz))), tout.view(tuple(reversed(gp.zsz)))
+            dc.transpose_y_to_z(f, a, gp)
+            der.ddz(a, b)
+            dc.transpose_z_to_y(b, df, gp)
+        else:
+            der.ddz(f, df)
+        if e: e[3].record(st)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = L.pdo_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(st)
+    for i in range(args.steps):
+        step(i)
+    t1.record(st)
+    barrier()
+    launches = L.pdo_launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    ms = t0.elapsed_time(t1)
+    per = [sum(e[j].elapsed_time(e[j + 1]) for e in ev) / args.steps for j in range(3)]  # ddx, ddy, ddz(+transposes)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    ms_step = ms / args.steps
+    pts_step_rank = 3.0 * npts_rank
+    value = pts_step_rank * world / (ms_step * 1e-3) / 1e9
+
+    # ---- e2e: the C-ABI call with HOST buffers (H2D + kernel + D2H inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        ne = args.e2e_n or n
+        fh = torch.rand((ne, ne, ne), dtype=torch.float64).pin_memory()
+        oh = torch.empty_like(fh).pin_memory()
+        ce = pdo.cd10()
+        assert ce.init(ne, 2 * np.pi / ne) == 0
+        def e2e_step():
+            ce.dd1(fh, oh); ce.dd2(fh, oh); ce.dd3(fh, oh)
+        e2e_step()
+        barrier()
+        k = max(1, min(args.steps, 3))
+        tt = time.perf_counter()
+        for _ in range(k):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - tt) / k
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = t.item()
+        e2e = {"value": 3.0 * ne ** 3 * world / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 3 * 8 * ne ** 3,
+               "d2h_bytes_per_step": 3 * 8 * ne ** 3, "n": ne, "ms_per_step": dt * 1e3,
+               "note": "pdo_cd10_dd1/dd2/dd3 called with pinned HOST pointers; the library stages H2D/D2H"}
+        del fh, oh
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    names = ["cd10 ddx (chunk_x_kernel)", "cd10 ddy (chunk_strided_kernel)", "cd10 ddz (chunk_strided_kernel)"]
+    per_k = {}
+    for nm, t in zip(names, per):
+        per_k[nm] = {"ms": t, "GBps": BYTES_PER_POINT * npts_rank / (t * 1e-3) / 1e9}
+    kern_only = [t for j, t in enumerate(per) if (j == 1) or (j == 0 and p_row == 1) or (j == 2 and p_col == 1)]
+    kidx = [j for j in range(3) if (j == 1) or (j == 0 and p_row == 1) or (j == 2 and p_col == 1)]
+    dom = kidx[max(range(len(kern_only)), key=lambda j: kern_only[j])]
+    ach = BYTES_PER_POINT * npts_rank / (per[dom] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_POINT * npts_rank, "per_kernel": per_k}
+    tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get(names[dom].split("(")[1].rstrip(")"))
+        except Exception:
+            pass
+    cb = None
+    if not args.no_cpu:
+        cb, _ = cpu_arm(512, 1, 1)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"cd10 ddx+ddy+ddz, periodic, {nx}x{ny}x{nz} field, 2DECOMP grid {p_row}x{p_col}, "
+                                   f"{npts_rank} points per GPU" + ("; off-pencil axes include their NCCL transposes" if world > 1 else ""),
+                       "n": n, "global": [nx, ny, nz], "grid": [p_row, p_col],
+                       "l2": "inputs (8 GiB per field at n=1024) larger than the 126 MB L2, no flush needed"},
+            "roofline": roof, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1024, help="points per direction per GPU")
+    ap.add_argument("--e2e-n", type=int, default=0, dest="e2e_n", help="field size of the host-pointer (e2e) leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+"""ctypes loader for libpadeops_b200.so — prototypes mirror include/padeops_b200.h one to one."""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "lib", "libpadeops_b200.so")
+_lib = None
+
+c_dp = C.c_void_p  # field pointers travel as raw addresses (host or device)
+
+
+class PadeOpsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"padeops_b200 error {code}: {msg}")
+        self.code = code
+
+
+class DecompInfo(C.Structure):
+    _fields_ = [(nm, C.c_int * 3) for nm in ("xst", "xen", "xsz", "yst", "yen", "ysz", "zst", "zen", "zsz")]
+
+
+def library_path():
+    return _SO
+
+
+def build_library(force=False):
+    """Compile every CUDA source for sm_100a into lib/libpadeops_b200.so (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-s", "clean"])
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-s", "-j8", "all"])
+    return _SO
+
+
+_OPS7 = [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+_PROTOS = {
+    "pdo_last_error": (C.c_char_p, []),
+    "pdo_version": (C.c_int, []),
+    "pdo_launch_count": (C.c_int64, []),
+    "pdo_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "pdo_free": (C.c_int, [C.c_void_p]),
+    "pdo_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "pdo_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "pdo_stream_sync": (C.c_int, [C.c_void_p]),
+    "pdo_cd10_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]),
+    "pdo_cd10_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_cd10_getsize": (C.c_int, [C.c_void_p]),
+    "pdo_cd06_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]),
+    "pdo_cd06_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_cd06_getsize": (C.c_int, [C.c_void_p]),
+    "pdo_cf90_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
+    "pdo_cf90_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_gaussian_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
+    "pdo_gaussian_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_cd06stagg_init_periodic": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_double]),
+    "pdo_cd06stagg_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_derivatives_init": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                       C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p,
+                                       C.c_char_p]),
+    "pdo_derivatives_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_filters_init": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
+                                   C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p]),
+    "pdo_filters_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "pdo_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p]),
+    "pdo_comm_finalize": (C.c_int, []),
+    "pdo_comm_rank": (C.c_int, []),
+    "pdo_comm_size": (C.c_int, []),
+    "pdo_decomp_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "pdo_decomp_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_decomp_get_info": (C.c_int, [C.c_void_p, C.POINTER(DecompInfo)]),
+    "pdo_decomp_info_for": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DecompInfo)]),
+    "pdo_p_maxval": (C.c_int, [C.c_double, C.POINTER(C.c_double)]),
+    "pdo_p_sum": (C.c_int, [C.c_double, C.POINTER(C.c_double)]),
+    "pdo_fft3d_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                 C.c_int]),
+    "pdo_fft3d_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_fft3d_get_complex_output_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "pdo_fft3d_get_spectral_info": (C.c_int, [C.c_void_p, C.POINTER(DecompInfo)]),
+    "pdo_fft3d_get_physical_info": (C.c_int, [C.c_void_p, C.POINTER(DecompInfo)]),
+    "pdo_fft3d_fft3_x2z": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
+    "pdo_fft3d_ifft3_z2x": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
+    "pdo_fft3d_fft2_x2y": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
+    "pdo_fft3d_ifft2_y2x": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_void_p]),
+    "pdo_poisson_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdo_poisson_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_poisson_solve": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
+}
+for _t, _fns in (("cd10", ("dd1", "dd2", "dd3", "d2d1", "d2d2", "d2d3")), ("cd06", ("dd1", "dd2", "dd3")),
+                 ("cf90", ("filter1", "filter2", "filter3")), ("gaussian", ("filter1", "filter2", "filter3"))):
+    for _f in _fns:
+        _PROTOS[f"pdo_{_t}_{_f}"] = (C.c_int, _OPS7)
+for _f in ("ddz_E2C", "ddz_C2E", "interpz_E2C", "interpz_C2E", "d2dz2_C2C", "d2dz2_E2E"):
+    _PROTOS[f"pdo_cd06stagg_{_f}"] = (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_void_p])
+for _f in ("ddx", "ddy", "ddz", "d2dx2", "d2dy2", "d2dz2"):
+    _PROTOS[f"pdo_derivatives_{_f}"] = (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_void_p])
+for _f in ("filterx", "filtery", "filterz"):
+    _PROTOS[f"pdo_filters_{_f}"] = (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_void_p])
+for _f in ("x_to_y", "y_to_x", "y_to_z", "z_to_y"):
+    _PROTOS[f"pdo_transpose_{_f}"] = (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_void_p])
+_PROTOS["pdo_debug_cd10_generic"] = (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.c_int, C.c_void_p])
+
+EXPORTED = sorted(k for k in _PROTOS if not k.startswith("pdo_debug"))
+
+
+def lib():
+    """Load the CUDA library.  Fails loudly if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise PadeOpsError(-1, f"{_SO} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                   "(padeops_b200 has no CPU fallback)")
+        # Map torch's CUDA libraries first when torch is around: libnccl.so.2 / libcufft.so.11 are resolved by
+        # SONAME, and torch refuses to import after an older system NCCL has been mapped under that name.
+        try:
+            import torch  # noqa: F401
+        except ImportError:
+            pass
+        L = C.CDLL(_SO)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PadeOpsError(rc, lib().pdo_last_error().decode("utf-8", "replace"))
+
+
+def ptr(a):
+    """Raw address of a torch tensor (device or host) or a numpy array."""
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+def stream_ptr(stream=None):
+    if stream is None:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        except Exception:
+            pass
+        return C.c_void_p(0)
+    if hasattr(stream, "cuda_stream"):
+        return C.c_void_p(stream.cuda_stream)
+    return C.c_void_p(int(stream))

@@ -1,0 +1,493 @@
+// banded.cu — hand-written sm_100a kernels for the periodic compact line operators.
+//
+// Replaces, per call, the reference's three sweeps (RHS stencil, forward elimination with running
+// corner sums, back substitution):
+//   CD10 d1/d2  derivatives/cd10.F90:1098-1142, 1265-1308, 1428-1468, 1587-1635 (RHS) + 712-1013 (Solve*LU*)
+//   CD06 d1     derivatives/cd06.F90:515-550, 596-630, 674-704 (RHS) + 345-429 (Solve*LU1)
+//   CF90        filters/cf90.F90:610-669 (+ CF90_files/ComputeZRHS_common.F90) + 421-530
+//   Gaussian    filters/gaussian.F90:137-187 (explicit stencil, no solve)
+//   CD06 stagg  derivatives/cd06stagg.F90:301-629 (RHS) + 248-299 (SolveZLU_*)
+// with ONE fused pass: every grid point is read from HBM once and written once (16 B/pt).
+//
+// Two kernel families share one register-resident "chunk engine" (see tables.h for the algebra):
+//   chunk_strided_kernel : solve axis is y or z.  A CTA owns XT contiguous x-columns x the whole line;
+//                          thread (xi,p) owns chunk p (M consecutive points along the line) of column xi,
+//                          so every global access is a coalesced row segment of XT doubles.
+//   chunk_x_kernel       : solve axis is x (contiguous).  A CTA stages L whole lines in shared memory with
+//                          coalesced 16-byte accesses (one padding double per chunk → conflict-free), thread
+//                          (line,p) pulls its chunk into registers, solves, and the tile goes back the same way.
+// LU factors / spike tables arrive as a __grid_constant__ struct, i.e. in the constant bank.
+// Generic any-n kernels (one thread per line, tables in global memory) cover line lengths that are not a
+// multiple of 8.  There is no CPU path.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "banded.cuh"
+
+namespace pdo {
+
+// ------------------------------------------------------------------------------------------------
+// RHS stencils
+// ------------------------------------------------------------------------------------------------
+template <int RK> struct Halo;
+template <> struct Halo<RK_D1_7> { static constexpr int L = 3, R = 3; };
+template <> struct Halo<RK_D2_7> { static constexpr int L = 3, R = 3; };
+template <> struct Halo<RK_D1_5> { static constexpr int L = 2, R = 2; };
+template <> struct Halo<RK_SYM_9> { static constexpr int L = 4, R = 4; };
+template <> struct Halo<RK_D2_5> { static constexpr int L = 2, R = 2; };
+template <> struct Halo<RK_STAG_E2C> { static constexpr int L = 1, R = 2; };
+template <> struct Halo<RK_STAG_C2E> { static constexpr int L = 2, R = 1; };
+
+// w points at the centre value; operand order follows the Fortran expressions.
+template <int RK>
+__device__ __forceinline__ double rhs_eval(const double* w, const OpParams& op) {
+    if (RK == RK_D1_7) {
+        return op.co[0] * (w[1] - w[-1]) + op.co[1] * (w[2] - w[-2]) + op.co[2] * (w[3] - w[-3]);
+    } else if (RK == RK_D2_7) {
+        return op.co[0] * (w[1] - 2.0 * w[0] + w[-1]) + op.co[1] * (w[2] - 2.0 * w[0] + w[-2]) +
+               op.co[2] * (w[3] - 2.0 * w[0] + w[-3]);
+    } else if (RK == RK_D1_5) {
+        return op.co[0] * (w[1] - w[-1]) + op.co[1] * (w[2] - w[-2]);
+    } else if (RK == RK_SYM_9) {
+        return op.co[0] * (w[0]) + op.co[1] * (w[1] + w[-1]) + op.co[2] * (w[2] + w[-2]) + op.co[3] * (w[3] + w[-3]) +
+               op.co[4] * (w[4] + w[-4]);
+    } else if (RK == RK_D2_5) {
+        return op.co[0] * (w[1] - 2.0 * w[0] + w[-1]) + op.co[1] * (w[2] - 2.0 * w[0] + w[-2]);
+    } else if (RK == RK_STAG_E2C) {
+        return op.co[0] * (w[1] + op.co[2] * w[0]) + op.co[1] * (w[2] + op.co[2] * w[-1]);
+    } else {  // RK_STAG_C2E
+        return op.co[0] * (w[0] + op.co[2] * w[-1]) + op.co[1] * (w[1] + op.co[2] * w[-2]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Chunk engine: r[0..M) (RHS of this thread's chunk, in registers) → x[0..M) in place.
+// smem: gA[BW][nchunk_slots], gB[BW][..], s[BW][..]; `slot(q)` maps chunk q of MY line to its slot.
+// Two __syncthreads; every thread of the CTA must call this.
+// ------------------------------------------------------------------------------------------------
+template <int BW, int M, class SlotFn>
+__device__ __forceinline__ void chunk_solve(double (&r)[M], const ChunkTables& t, double* __restrict__ sm_g,
+                                            int slots, int p, SlotFn slot) {
+    constexpr int mi = M - BW;
+    // forward elimination on the interior block
+    r[1] = r[1] - t.l1[1] * r[0];
+#pragma unroll
+    for (int i = 2; i < mi; ++i) {
+        if (BW == 2) r[i] = r[i] - t.l1[i] * r[i - 1] - t.l2[i] * r[i - 2];
+        else r[i] = r[i] - t.l1[i] * r[i - 1];
+    }
+    // back substitution
+    r[mi - 1] = r[mi - 1] * t.ginv[mi - 1];
+    if (BW == 2) {
+        r[mi - 2] = (r[mi - 2] - t.u1[mi - 2] * r[mi - 1]) * t.ginv[mi - 2];
+#pragma unroll
+        for (int i = mi - 3; i >= 0; --i) r[i] = (r[i] - t.u1[i] * r[i + 1] - t.b2 * r[i + 2]) * t.ginv[i];
+    } else {
+#pragma unroll
+        for (int i = mi - 2; i >= 0; --i) r[i] = (r[i] - t.u1[i] * r[i + 1]) * t.ginv[i];
+    }
+    // reduced right-hand side pieces: gA from my chunk's tail rows, gB = what my head rows contribute to the
+    // separator rows of the PREVIOUS chunk.
+    double* gA = sm_g;
+    double* gB = sm_g + BW * slots;
+    double* sS = sm_g + 2 * BW * slots;
+    const int me = slot(p);
+    if (BW == 2) {
+        gA[me] = r[M - 2] - t.b2 * r[mi - 2] - t.b1 * r[mi - 1];
+        gA[slots + me] = r[M - 1] - t.b2 * r[mi - 1];
+        gB[me] = -t.b2 * r[0];
+        gB[slots + me] = -t.b1 * r[0] - t.b2 * r[1];
+    } else {
+        gA[me] = r[M - 1] - t.b1 * r[mi - 1];
+        gB[me] = -t.b1 * r[0];
+    }
+    __syncthreads();
+    // separator solve: s_p = sum_d G[d] (gA_{p+d} + gB_{p+d+1})
+    const int P = t.P, W = t.W;
+    double s0 = 0.0, s1 = 0.0;
+    int q = p - W;
+    q %= P;
+    if (q < 0) q += P;
+    for (int d = 0; d <= 2 * W; ++d) {
+        int q1 = q + 1;
+        if (q1 == P) q1 = 0;
+        const int a = slot(q), b = slot(q1);
+        if (BW == 2) {
+            const double h0 = gA[a] + gB[b];
+            const double h1 = gA[slots + a] + gB[slots + b];
+            s0 += t.G[d][0] * h0 + t.G[d][1] * h1;
+            s1 += t.G[d][2] * h0 + t.G[d][3] * h1;
+        } else {
+            s0 += t.G[d][0] * (gA[a] + gB[b]);
+        }
+        q = q1;
+    }
+    sS[me] = s0;
+    if (BW == 2) sS[slots + me] = s1;
+    __syncthreads();
+    const int pm = slot(p == 0 ? P - 1 : p - 1);
+    const double sp0 = sS[pm];
+    const double sp1 = (BW == 2) ? sS[slots + pm] : 0.0;
+    // spikes
+#pragma unroll
+    for (int i = 0; i < mi; ++i) {
+        if (BW == 2) r[i] = r[i] - t.V[i][0] * sp0 - t.V[i][1] * sp1 - t.U[i][0] * s0 - t.U[i][1] * s1;
+        else r[i] = r[i] - t.V[i][0] * sp0 - t.U[i][0] * s0;
+    }
+    r[mi] = s0;
+    if (BW == 2) r[mi + 1] = s1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strided (y / z) kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kStridedThreads = 512;
+
+template <int RK, int BW, int M>
+__global__ void __launch_bounds__(kStridedThreads, 1)
+chunk_strided_kernel(const double* __restrict__ f, double* __restrict__ out, long long n1, int n, long long in_slab,
+                     long long out_slab, int tiles_x, int XT, const __grid_constant__ ChunkTables tab,
+                     const __grid_constant__ OpParams op) {
+    constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
+    extern __shared__ double sm_g[];
+    const int tid = threadIdx.x;
+    const int xi = tid % XT, p = tid / XT;
+    const int P = n / M;
+    const long long tile = blockIdx.x;
+    const long long k = tile / tiles_x;
+    const long long x = (tile - k * tiles_x) * XT + xi;
+    const bool active = x < n1;
+    const double* fin = f + k * in_slab + (active ? x : 0);
+    double* fo = out + k * out_slab + (active ? x : 0);
+
+    double v[M + HL + HR];
+    const int nwrap = op.edge_in ? n + 1 : n;  // first logical position that wraps back by n
+#pragma unroll
+    for (int j = 0; j < M + HL + HR; ++j) {
+        int q = p * M - HL + j;
+        if (j < HL) { if (q < 0) q += n; }
+        if (j >= M + HL) { if (q >= nwrap) q -= n; }
+        v[j] = __ldg(fin + (long long)q * n1);
+    }
+    double r[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) r[i] = rhs_eval<RK>(&v[i + HL], op);
+
+    if constexpr (BW > 0) {
+        const int slots = P * XT;
+        chunk_solve<BW, M>(r, tab, sm_g, slots, p, [&](int q) { return q * XT + xi; });
+    }
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) fo[(long long)(p * M + i) * n1] = r[i];
+        if (op.edge_out && p == 0) fo[(long long)n * n1] = r[0];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Contiguous (x) kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kXThreads = 256;
+
+template <int RK, int BW, int M>
+__global__ void __launch_bounds__(kXThreads, 2)
+chunk_x_kernel(const double* __restrict__ f, double* __restrict__ out, long long nlines, int n, int L,
+               const __grid_constant__ ChunkTables tab, const __grid_constant__ OpParams op) {
+    constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
+    extern __shared__ double sm[];
+    const int P = n / M;
+    const int pitch = n + P;  // one padding double per chunk: chunk p starts at p*(M+1)
+    double* tile = sm;
+    double* sm_g = sm + (size_t)L * pitch;
+    const int tid = threadIdx.x;
+    const long long line0 = (long long)blockIdx.x * L;
+    const int nl = (int)min((long long)L, nlines - line0);  // lines present in this tile
+    const double* fbase = f + line0 * n;
+    double* obase = out + line0 * n;
+
+    // ---- coalesced tile load (16-byte when aligned) ----
+    const long long tot = (long long)nl * n;
+    if ((reinterpret_cast<uintptr_t>(fbase) & 15) == 0) {
+        const double2* f2 = reinterpret_cast<const double2*>(fbase);
+        int ln = 0, j0 = 2 * tid;
+        while (j0 >= n) { j0 -= n; ++ln; }
+        for (long long e = tid; 2 * e < tot; e += kXThreads) {
+            const double2 val = __ldg(f2 + e);
+            const int pos = ln * pitch + j0 + j0 / M;
+            tile[pos] = val.x;
+            tile[pos + 1] = val.y;
+            j0 += 2 * kXThreads;
+            while (j0 >= n) { j0 -= n; ++ln; }
+        }
+    } else {
+        int ln = 0, j0 = tid;
+        while (j0 >= n) { j0 -= n; ++ln; }
+        for (long long e = tid; e < tot; e += kXThreads) {
+            tile[ln * pitch + j0 + j0 / M] = __ldg(fbase + e);
+            j0 += kXThreads;
+            while (j0 >= n) { j0 -= n; ++ln; }
+        }
+    }
+    __syncthreads();
+
+    const int p = tid % P, ln = tid / P;
+    const bool active = (tid < L * P) && (ln < nl);
+    const double* row = tile + (active ? ln : 0) * pitch;
+    double v[M + HL + HR];
+    {
+        const int pl = (p == 0 ? P - 1 : p - 1) * (M + 1) + M - HL;  // left halo lives at the tail of chunk p-1
+        const int pr = (p == P - 1 ? 0 : p + 1) * (M + 1);           // right halo at the head of chunk p+1
+        const int pc = p * (M + 1);
+#pragma unroll
+        for (int j = 0; j < HL; ++j) v[j] = row[pl + j];
+#pragma unroll
+        for (int j = 0; j < M; ++j) v[HL + j] = row[pc + j];
+#pragma unroll
+        for (int j = 0; j < HR; ++j) v[HL + M + j] = row[pr + j];
+    }
+    double r[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) r[i] = rhs_eval<RK>(&v[i + HL], op);
+
+    if constexpr (BW > 0) {
+        chunk_solve<BW, M>(r, tab, sm_g, kXThreads, p, [&](int q) { return tid - p + q; });
+    } else {
+        __syncthreads();  // everyone has read the tile
+    }
+    // (chunk_solve's barriers also guarantee every thread finished reading `tile`)
+    if (active) {
+        double* wrow = tile + ln * pitch + p * (M + 1);
+#pragma unroll
+        for (int i = 0; i < M; ++i) wrow[i] = r[i];
+    }
+    __syncthreads();
+    // ---- coalesced tile store ----
+    if ((reinterpret_cast<uintptr_t>(obase) & 15) == 0) {
+        double2* o2 = reinterpret_cast<double2*>(obase);
+        int l2 = 0, j0 = 2 * tid;
+        while (j0 >= n) { j0 -= n; ++l2; }
+        for (long long e = tid; 2 * e < tot; e += kXThreads) {
+            const int pos = l2 * pitch + j0 + j0 / M;
+            o2[e] = make_double2(tile[pos], tile[pos + 1]);
+            j0 += 2 * kXThreads;
+            while (j0 >= n) { j0 -= n; ++l2; }
+        }
+    } else {
+        int l2 = 0, j0 = tid;
+        while (j0 >= n) { j0 -= n; ++l2; }
+        for (long long e = tid; e < tot; e += kXThreads) {
+            obase[e] = tile[l2 * pitch + j0 + j0 / M];
+            j0 += kXThreads;
+            while (j0 >= n) { j0 -= n; ++l2; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic any-n kernels (tables in global memory).  f(n1, n, n3): es = n1 is the element stride along
+// the line.  Pass 1: pointwise RHS.  Pass 2: one thread per line, in place on `out`.
+// ------------------------------------------------------------------------------------------------
+template <int RK>
+__global__ void rhs_generic_kernel(const double* __restrict__ f, double* __restrict__ out, long long n1, int n,
+                                   long long n3, long long in_slab, long long out_slab, OpParams op) {
+    constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
+    const long long tot = n1 * n * n3;
+    const int nwrap = op.edge_in ? n + 1 : n;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long i = idx % n1;
+        const long long t = idx / n1;
+        const int j = (int)(t % n);
+        const long long k = t / n;
+        const double* base = f + k * in_slab + i;
+        double w[HL + HR + 1];
+#pragma unroll
+        for (int o = -HL; o <= HR; ++o) {
+            int q = j + o;
+            if (q < 0) q += n;
+            else if (q >= nwrap) q -= n;
+            w[o + HL] = base[(long long)q * n1];
+        }
+        out[k * out_slab + (long long)j * n1 + i] = rhs_eval<RK>(&w[HL], op);
+    }
+}
+
+template <int BW>
+__global__ void line_solve_generic_kernel(double* __restrict__ y, long long n1, int n, long long n3, long long slab,
+                                          const double* __restrict__ T, int edge_out) {
+    const long long nlines = n1 * n3;
+    const long long ln = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (ln >= nlines) return;
+    const long long i = ln % n1, k = ln / n1;
+    double* Y = y + k * slab + i;
+    const long long es = n1;
+    const int mi = n - BW;
+    const double *l1 = T, *l2 = T + n, *ginv = T + 2 * n, *u1 = T + 3 * n, *VU = T + 4 * n, *G0 = T + 6 * (long long)n;
+    // forward
+    double ym1 = Y[0], ym2 = 0.0;
+    for (int r = 1; r < mi; ++r) {
+        double v = Y[r * es] - l1[r] * ym1;
+        if (BW == 2 && r >= 2) v -= l2[r] * ym2;
+        Y[r * es] = v;
+        ym2 = ym1;
+        ym1 = v;
+    }
+    // backward
+    const double B2 = VU[2 * (long long)n - 1];  // b2 stashed in the last VU slot by the host (see create)
+    const double B1 = VU[2 * (long long)n - 2];
+    double zp1 = 0.0, zp2 = 0.0;
+    for (int r = mi - 1; r >= 0; --r) {
+        double v = Y[r * es];
+        if (r + 1 < mi) v -= u1[r] * zp1;
+        if (BW == 2 && r + 2 < mi) v -= B2 * zp2;
+        v *= ginv[r];
+        Y[r * es] = v;
+        zp2 = zp1;
+        zp1 = v;
+    }
+    // separator values (one chunk: previous == own)
+    double s0, s1 = 0.0;
+    if (BW == 2) {
+        const double z0 = Y[0], z1 = Y[es], za = Y[(mi - 2) * es], zb = Y[(mi - 1) * es];
+        const double g0 = Y[(n - 2) * es] - B2 * za - B1 * zb - B2 * z0;
+        const double g1 = Y[(n - 1) * es] - B2 * zb - B1 * z0 - B2 * z1;
+        s0 = G0[0] * g0 + G0[1] * g1;
+        s1 = G0[2] * g0 + G0[3] * g1;
+    } else {
+        const double g0 = Y[(n - 1) * es] - B1 * Y[(mi - 1) * es] - B1 * Y[0];
+        s0 = G0[0] * g0;
+    }
+    for (int r = 0; r < mi; ++r) {
+        double v = Y[r * es] - VU[2 * r] * s0;
+        if (BW == 2) v -= VU[2 * r + 1] * s1;
+        Y[r * es] = v;
+    }
+    Y[mi * es] = s0;
+    if (BW == 2) Y[(mi + 1) * es] = s1;
+    if (edge_out) Y[(long long)n * es] = Y[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+cudaError_t banded_op_create(BandedOp* h, int n, int rk, int bw, double b1, double b2, const OpParams& op) {
+    h->n = n; h->rk = rk; h->bw = bw; h->op = op; h->M = 0; h->d_line = nullptr;
+    if (n <= 1) return cudaSuccess;
+    const int cands[3] = {32, 16, 8};
+    for (int c = 0; c < 3; ++c) {
+        const int M = cands[c];
+        if (n % M != 0) continue;
+        const int P = n / M;
+        if (P > 128) continue;
+        if (bw == 0) {
+            std::memset(&h->tab, 0, sizeof(h->tab));
+            h->tab.n = n; h->tab.M = M; h->tab.P = P;
+            h->M = M;
+            break;
+        }
+        if (build_chunk_tables(n, M, bw, b1, b2, &h->tab) == 0) { h->M = M; break; }
+    }
+    if (bw > 0) {
+        LineTablesHost lt{};
+        if (build_line_tables(n, bw, b1, b2, &lt) != 0) return cudaErrorInvalidValue;
+        lt.data[6 * (size_t)n - 2] = b1;  // VU rows >= n-BW are unused: stash the off-diagonals there
+        lt.data[6 * (size_t)n - 1] = (bw == 2) ? b2 : 0.0;
+        cudaError_t e = cudaMalloc(&h->d_line, sizeof(double) * (6 * (size_t)n + 4));
+        if (e != cudaSuccess) { std::free(lt.data); return e; }
+        e = cudaMemcpy(h->d_line, lt.data, sizeof(double) * (6 * (size_t)n + 4), cudaMemcpyHostToDevice);
+        std::free(lt.data);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+void banded_op_destroy(BandedOp* h) {
+    if (h->d_line) cudaFree(h->d_line);
+    h->d_line = nullptr;
+}
+
+namespace {
+
+template <int RK, int BW, int M>
+cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3,
+                         long long in_slab, long long out_slab, cudaStream_t st) {
+    const int n = h->n, P = n / M;
+    if (axis == 0) {
+        static bool attr_done = false;
+        const int L = kXThreads / P > 0 ? kXThreads / P : 1;
+        const size_t smem = sizeof(double) * ((size_t)L * (n + P) + 3 * (BW > 0 ? BW : 1) * kXThreads);
+        auto kern = chunk_x_kernel<RK, BW, M>;
+        if (!attr_done) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        if (smem > 100 * 1024 || P > kXThreads) return cudaErrorInvalidConfiguration;
+        const long long nlines = n3;
+        const long long grid = (nlines + L - 1) / L;
+        kern<<<(unsigned)grid, kXThreads, smem, st>>>(f, out, nlines, n, L, h->tab, h->op);
+    } else {
+        int XT = 1;
+        while (XT * 2 * P <= kStridedThreads) XT *= 2;
+        while (XT > 1 && XT / 2 >= n1) XT /= 2;
+        if (XT * P > kStridedThreads) return cudaErrorInvalidConfiguration;
+        const int tiles_x = (int)((n1 + XT - 1) / XT);
+        const long long grid = (long long)tiles_x * n3;
+        const size_t smem = sizeof(double) * 3 * (BW > 0 ? BW : 1) * (size_t)P * XT;
+        chunk_strided_kernel<RK, BW, M><<<(unsigned)grid, XT * P, smem, st>>>(f, out, n1, n, in_slab, out_slab, tiles_x,
+                                                                             XT, h->tab, h->op);
+    }
+    return cudaGetLastError();
+}
+
+template <int RK, int BW>
+cudaError_t launch_any(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3,
+                       long long in_slab, long long out_slab, cudaStream_t st, int force_generic) {
+    if (h->M == 32 && !force_generic) return launch_chunk<RK, BW, 32>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
+    if (h->M == 16 && !force_generic) return launch_chunk<RK, BW, 16>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
+    if (h->M == 8 && !force_generic) return launch_chunk<RK, BW, 8>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
+    // generic
+    const int n = h->n;
+    const long long tot = n1 * n * n3;
+    const int thr = 256;
+    long long blocks = (tot + thr - 1) / thr;
+    if (blocks > 148LL * 64) blocks = 148LL * 64;
+    rhs_generic_kernel<RK><<<(unsigned)blocks, thr, 0, st>>>(f, out, n1, n, n3, in_slab, out_slab, h->op);
+    if constexpr (BW > 0) {
+        const long long nlines = n1 * n3;
+        line_solve_generic_kernel<BW><<<(unsigned)((nlines + 127) / 128), 128, 0, st>>>(
+            out, n1, n, n3, out_slab, h->d_line, h->op.edge_out);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t banded_op_apply(const BandedOp* h, int axis, const double* f, double* out, long long na, long long nb,
+                            cudaStream_t st, int force_generic) {
+    const int n = h->n;
+    long long n1, n3;
+    if (axis == 0) { n1 = 1; n3 = na * nb; }
+    else if (axis == 1) { n1 = na; n3 = nb; }
+    else if (axis == 2) { n1 = na * nb; n3 = 1; }
+    else return cudaErrorInvalidValue;
+    if (n1 * n3 == 0) return cudaSuccess;
+    const long long in_slab = n1 * (n + (h->op.edge_in || (h->op.edge_out && h->rk == RK_D2_5) ? 1 : 0));
+    const long long out_slab = n1 * (n + (h->op.edge_out ? 1 : 0));
+    const int key = h->rk * 10 + h->bw;
+    switch (key) {
+        case RK_D1_7 * 10 + 2: return launch_any<RK_D1_7, 2>(h, axis, f, out, n1, n3, in_slab, out_slab, st, force_generic);
+        case RK_D2_7 * 10 + 2: return launch_any<RK_D2_7, 2>(h, axis, f, out, n1, n3, in_slab, out_slab, st, force_generic);
+        case RK_D1_5 * 10 + 1: return launch_any<RK_D1_5, 1>(h, axis, f, out, n1, n3, in_slab, out_slab, st, force_generic);
+        case RK_SYM_9 * 10 + 2: return launch_any<RK_SYM_9, 2>(h, axis, f, out, n1, n3, in_slab, out_slab, st, force_generic);
+        case RK_SYM_9 * 10 + 0: return launch_any<RK_SYM_9, 0>(h, axis, f, out, n1, n3, in_slab, out_slab, st, force_generic);
+        case RK_D2_5 * 10 + 1: return launch_any<RK_D2_5, 1>(h, axis, f, out, n1, n3, in_slab, out_slab, st, force_generic);
+        case RK_STAG_E2C * 10 + 1: return launch_any<RK_STAG_E2C, 1>(h, axis, f, out, n1, n3, in_slab, out_slab, st, force_generic);
+        case RK_STAG_C2E * 10 + 1: return launch_any<RK_STAG_C2E, 1>(h, axis, f, out, n1, n3, in_slab, out_slab, st, force_generic);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace pdo

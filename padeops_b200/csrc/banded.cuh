@@ -1,0 +1,46 @@
+// banded.cuh — host-side handle + launch interface of the compact (banded) line operators.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "tables.h"
+
+namespace pdo {
+
+// Right-hand-side stencil families (one per reference RHS loop nest; file:line in banded.cu).
+enum RhsKind {
+    RK_D1_7 = 0,      // a(f+1 - f-1) + b(f+2 - f-2) + c(f+3 - f-3)                  CD10 first derivative
+    RK_D2_7 = 1,      // a(f+1 - 2f + f-1) + b(f+2 - 2f + f-2) + c(f+3 - 2f + f-3)    CD10 second derivative
+    RK_D1_5 = 2,      // a(f+1 - f-1) + b(f+2 - f-2)                                  CD06 first derivative
+    RK_SYM_9 = 3,     // a f + b(f+1 + f-1) + ... + e(f+4 + f-4)                      CF90 / Gaussian
+    RK_D2_5 = 4,      // a(f+1 - 2f + f-1) + b(f+2 - 2f + f-2)                        staggered d2 (C2C / E2E)
+    RK_STAG_E2C = 5,  // a(f[k+1] ± f[k]) + b(f[k+2] ± f[k-1])                        edge → cell (ddz / interp)
+    RK_STAG_C2E = 6,  // a(f[k] ± f[k-1]) + b(f[k+1] ± f[k-2])                        cell → edge (ddz / interp)
+};
+
+struct OpParams {
+    double co[5];  // stencil coefficients with the grid spacing folded in exactly as the reference does
+    int edge_in;   // input has n+1 planes and plane n (0-based) is read un-wrapped (E2C quirk)
+    int edge_out;  // output has n+1 planes; plane n := plane 0 after the solve (C2E / E2E)
+};
+
+struct BandedOp {
+    int n = 0;
+    int rk = 0;
+    int bw = 0;  // 0 explicit stencil, 1 cyclic tridiagonal, 2 cyclic pentadiagonal
+    OpParams op{};
+    int M = 0;   // chunk length of the fast path; 0 → generic any-n kernels
+    ChunkTables tab{};
+    double* d_line = nullptr;  // generic path tables (device)
+};
+
+// Builds tables (host) and uploads what the generic path needs.  LHS = circ[b2 b1 1 b1 b2].
+cudaError_t banded_op_create(BandedOp* h, int n, int rk, int bw, double b1, double b2, const OpParams& op);
+void banded_op_destroy(BandedOp* h);
+
+// Applies the operator along `axis` of a column-major field: axis 0: f(n,na,nb); 1: f(na,n,nb); 2: f(na,nb,n).
+// Device pointers; f and out must not alias.  For edge_in / edge_out ops the solve axis has n+1 planes on
+// that side.  force_generic != 0 routes through the any-n kernels (used by tests to cross-check).
+cudaError_t banded_op_apply(const BandedOp* h, int axis, const double* f, double* out, long long na, long long nb,
+                            cudaStream_t stream, int force_generic = 0);
+
+}  // namespace pdo

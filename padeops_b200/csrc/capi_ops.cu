@@ -1,0 +1,468 @@
+// capi_ops.cu — C ABI for the 1-D line operators and their dispatch types (include/padeops_b200.h).
+// Host-side mirror of cd10stuff / cd06stuff / cf90stuff / gaussianstuff / cd06staggstuff /
+// DerivativesMod / FiltersMod: same constructor arguments, same error codes, same degenerate cases.
+#include <cstring>
+#include <new>
+
+#include "banded.cuh"
+#include "common.cuh"
+
+namespace pdo {
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+StagePool& stage_pool() {
+    static thread_local StagePool p;
+    return p;
+}
+}  // namespace pdo
+
+using namespace pdo;
+
+namespace {
+
+// coefficients: derivatives/cd10.F90:16-27, cd06.F90:14-16, cd06stagg.F90:174-176,307,411,532,
+// filters/cf90.F90:16-22, gaussian.F90:16-20
+constexpr double alpha10d1 = 1.0 / 2.0, beta10d1 = 1.0 / 20.0;
+constexpr double a10d1 = (17.0 / 12.0) / 2.0, b10d1 = (101.0 / 150.0) / 4.0, c10d1 = (1.0 / 100.0) / 6.0;
+constexpr double alpha10d2 = 334.0 / 899.0, beta10d2 = 43.0 / 1798.0;
+constexpr double a10d2 = (1065.0 / 1798.0) / 1.0, b10d2 = (1038.0 / 899.0) / 4.0, c10d2 = (79.0 / 1798.0) / 9.0;
+constexpr double alpha06d1 = 1.0 / 3.0, a06d1 = (14.0 / 9.0) / 2.0, b06d1 = (1.0 / 9.0) / 4.0;
+constexpr double alpha90 = 6.6624e-1, beta90 = 1.6688e-1;
+constexpr double a90 = 9.9965e-1, b90 = 6.6652e-1, c90 = 1.6674e-1, d90 = 4.0e-5, e90 = -5.0e-6;
+constexpr double agf = 3565.0 / 10368.0, bgf = 3091.0 / 12960.0, cgf = 1997.0 / 25920.0, dgf = 149.0 / 12960.0,
+                 egf = 107.0 / 103680.0;
+
+int check_bc(int bc1, int bcn) {
+    if ((bc1 != 0 && bc1 != 1 && bc1 != -1) || (bcn != 0 && bcn != 1 && bcn != -1))
+        return fail(324, "Incorrect boundary specification for bc1/bcn (should be 0, 1 or -1)");  // cd10.F90:2044-2046
+    return 0;
+}
+
+int ensure_device() {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PDO_E_NODEVICE, "no CUDA device available: padeops_b200 has no CPU fallback");
+    }
+    return 0;
+}
+
+// n == 1: derivative = 0, filter = copy (cd10.F90:2037-2040, cf90.F90:1028-1031)
+int degenerate(bool is_filter, const double* f, double* out, size_t count, cudaStream_t st) {
+    const size_t bytes = count * sizeof(double);
+    return with_device_views(f, bytes, out, bytes, st, [&](const void* din, void* dout) -> int {
+        if (is_filter) PDO_CUDA(cudaMemcpyAsync(dout, din, bytes, cudaMemcpyDeviceToDevice, st));
+        else PDO_CUDA(cudaMemsetAsync(dout, 0, bytes, st));
+        return 0;
+    });
+}
+
+int apply(const BandedOp& op, bool is_filter, int axis, const double* f, double* out, long long na, long long nb,
+          void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!f || !out) return fail(PDO_E_BADARG, "null field pointer");
+    if (na < 0 || nb < 0) return fail(PDO_E_BADARG, "negative extent");
+    const size_t in_count = (size_t)(op.n + (op.op.edge_in || (op.op.edge_out && op.rk == RK_D2_5) ? 1 : 0)) * na * nb;
+    const size_t out_count = (size_t)(op.n + (op.op.edge_out ? 1 : 0)) * na * nb;
+    if (op.n == 1) return degenerate(is_filter, f, out, out_count, st);
+    return with_device_views(f, in_count * sizeof(double), out, out_count * sizeof(double), st,
+                             [&](const void* din, void* dout) -> int {
+                                 PDO_CUDA(banded_op_apply(&op, axis, (const double*)din, (double*)dout, na, nb, st, 0));
+                                 g_launches += (op.M ? 1 : (op.bw ? 2 : 1));
+                                 return 0;
+                             });
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct pdo_cd10_s { int n; BandedOp d1, d2; };
+struct pdo_cd06_s { int n; BandedOp d1; };
+struct pdo_cf90_s { int n; BandedOp op; };
+struct pdo_gaussian_s { int n; BandedOp op; };
+struct pdo_cd06stagg_s { int n; BandedOp ops[6]; };
+
+extern "C" {
+
+const char* pdo_last_error(void) { return g_last_error.c_str(); }
+int pdo_version(void) { return 100; }
+int64_t pdo_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int pdo_malloc(void** dptr, size_t bytes) {
+    if (int rc = ensure_device()) return rc;
+    PDO_CUDA(cudaMalloc(dptr, bytes));
+    return 0;
+}
+int pdo_free(void* dptr) {
+    PDO_CUDA(cudaFree(dptr));
+    return 0;
+}
+int pdo_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+    PDO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return 0;
+}
+int pdo_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+    PDO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
+int pdo_stream_sync(void* stream) {
+    PDO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+// ---------------- cd10 ----------------
+int pdo_cd10_init(pdo_cd10_t* h, int n, double dx, int periodic, int bc1, int bcn) {
+    (void)bc1; (void)bcn;
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    *h = nullptr;
+    if (n < 1) return fail(PDO_E_BADARG, "n < 1");
+    if (!periodic) return fail(PDO_E_UNSUPPORTED, "cd10: non-periodic closures are out of scope (SURVEY.md 8f rank 2)");
+    if (n != 1 && n < 8) return fail(2, "cd10: periodic n must be 1 or >= 8");  // cd10.F90:219-226
+    if (int rc = ensure_device()) return rc;
+    pdo_cd10_s* o = new (std::nothrow) pdo_cd10_s();
+    if (!o) return fail(PDO_E_BADARG, "out of memory");
+    o->n = n;
+    const double onebydx = 1.0 / dx, onebydx2 = onebydx / dx;  // cd10.F90:206-207
+    OpParams p1{}, p2{};
+    p1.co[0] = a10d1 * onebydx; p1.co[1] = b10d1 * onebydx; p1.co[2] = c10d1 * onebydx;     // :1115-1117
+    p2.co[0] = a10d2 * onebydx2; p2.co[1] = b10d2 * onebydx2; p2.co[2] = c10d2 * onebydx2;  // :1601-1603
+    cudaError_t e = banded_op_create(&o->d1, n, RK_D1_7, 2, alpha10d1, beta10d1, p1);
+    if (e == cudaSuccess) e = banded_op_create(&o->d2, n, RK_D2_7, 2, alpha10d2, beta10d2, p2);
+    if (e != cudaSuccess) {
+        delete o;
+        return fail(PDO_E_CUDA, "cd10 init: %s", cudaGetErrorString(e));
+    }
+    *h = o;
+    return 0;
+}
+int pdo_cd10_destroy(pdo_cd10_t h) {
+    if (!h) return 0;
+    banded_op_destroy(&h->d1);
+    banded_op_destroy(&h->d2);
+    delete h;
+    return 0;
+}
+int pdo_cd10_getsize(pdo_cd10_t h) { return h ? h->n : -1; }
+
+#define PDO_CD10_FN(name, member, axis)                                                                   \
+    int name(pdo_cd10_t h, const double* f, double* df, int na, int nb, int bc1, int bcn, void* stream) { \
+        if (!h) return fail(PDO_E_BADARG, "null handle");                                                 \
+        if (int rc = check_bc(bc1, bcn)) return rc;                                                       \
+        return apply(h->member, false, axis, f, df, na, nb, stream);                                      \
+    }
+PDO_CD10_FN(pdo_cd10_dd1, d1, 0)
+PDO_CD10_FN(pdo_cd10_dd2, d1, 1)
+PDO_CD10_FN(pdo_cd10_dd3, d1, 2)
+PDO_CD10_FN(pdo_cd10_d2d1, d2, 0)
+PDO_CD10_FN(pdo_cd10_d2d2, d2, 1)
+PDO_CD10_FN(pdo_cd10_d2d3, d2, 2)
+
+// ---------------- cd06 ----------------
+int pdo_cd06_init(pdo_cd06_t* h, int n, double dx, int periodic, int bc1, int bcn) {
+    (void)bc1; (void)bcn;
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    *h = nullptr;
+    if (n < 1) return fail(PDO_E_BADARG, "n < 1");
+    if (!periodic) return fail(PDO_E_UNSUPPORTED, "cd06: non-periodic closures are out of scope (SURVEY.md 8f rank 2)");
+    if (n != 1 && n < 6) return fail(3, "cd06: periodic n must be 1 or >= 6");  // cd06.F90:151-160
+    if (int rc = ensure_device()) return rc;
+    pdo_cd06_s* o = new (std::nothrow) pdo_cd06_s();
+    if (!o) return fail(PDO_E_BADARG, "out of memory");
+    o->n = n;
+    const double onebydx = 1.0 / dx;
+    OpParams p{};
+    p.co[0] = a06d1 * onebydx; p.co[1] = b06d1 * onebydx;  // cd06.F90:530-531
+    cudaError_t e = banded_op_create(&o->d1, n, RK_D1_5, 1, alpha06d1, 0.0, p);
+    if (e != cudaSuccess) {
+        delete o;
+        return fail(PDO_E_CUDA, "cd06 init: %s", cudaGetErrorString(e));
+    }
+    *h = o;
+    return 0;
+}
+int pdo_cd06_destroy(pdo_cd06_t h) {
+    if (!h) return 0;
+    banded_op_destroy(&h->d1);
+    delete h;
+    return 0;
+}
+int pdo_cd06_getsize(pdo_cd06_t h) { return h ? h->n : -1; }
+#define PDO_CD06_FN(name, axis)                                                                           \
+    int name(pdo_cd06_t h, const double* f, double* df, int na, int nb, int bc1, int bcn, void* stream) { \
+        if (!h) return fail(PDO_E_BADARG, "null handle");                                                 \
+        if (int rc = check_bc(bc1, bcn)) return rc;                                                       \
+        return apply(h->d1, false, axis, f, df, na, nb, stream);                                          \
+    }
+PDO_CD06_FN(pdo_cd06_dd1, 0)
+PDO_CD06_FN(pdo_cd06_dd2, 1)
+PDO_CD06_FN(pdo_cd06_dd3, 2)
+
+// ---------------- cf90 ----------------
+int pdo_cf90_init(pdo_cf90_t* h, int n, int periodic) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    *h = nullptr;
+    if (n < 1) return fail(PDO_E_BADARG, "n < 1");
+    if (!periodic) return fail(PDO_E_UNSUPPORTED, "cf90: non-periodic closures are out of scope (SURVEY.md 8f rank 2)");
+    if (n != 1 && n < 10) return fail(7, "cf90: periodic n must be 1 or >= 10");  // cf90.F90:121-129
+    if (int rc = ensure_device()) return rc;
+    pdo_cf90_s* o = new (std::nothrow) pdo_cf90_s();
+    if (!o) return fail(PDO_E_BADARG, "out of memory");
+    o->n = n;
+    OpParams p{};
+    p.co[0] = a90; p.co[1] = b90; p.co[2] = c90; p.co[3] = d90; p.co[4] = e90;
+    cudaError_t e = banded_op_create(&o->op, n, RK_SYM_9, 2, alpha90, beta90, p);
+    if (e != cudaSuccess) {
+        delete o;
+        return fail(PDO_E_CUDA, "cf90 init: %s", cudaGetErrorString(e));
+    }
+    *h = o;
+    return 0;
+}
+int pdo_cf90_destroy(pdo_cf90_t h) {
+    if (!h) return 0;
+    banded_op_destroy(&h->op);
+    delete h;
+    return 0;
+}
+#define PDO_FIL_FN(T, name, axis)                                                                 \
+    int name(T h, const double* f, double* fil, int na, int nb, int bc1, int bcn, void* stream) { \
+        if (!h) return fail(PDO_E_BADARG, "null handle");                                         \
+        if (int rc = check_bc(bc1, bcn)) return rc;                                               \
+        return apply(h->op, true, axis, f, fil, na, nb, stream);                                  \
+    }
+PDO_FIL_FN(pdo_cf90_t, pdo_cf90_filter1, 0)
+PDO_FIL_FN(pdo_cf90_t, pdo_cf90_filter2, 1)
+PDO_FIL_FN(pdo_cf90_t, pdo_cf90_filter3, 2)
+
+// ---------------- gaussian ----------------
+int pdo_gaussian_init(pdo_gaussian_t* h, int n, int periodic) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    *h = nullptr;
+    if (n < 1) return fail(PDO_E_BADARG, "n < 1");
+    if (!periodic) return fail(PDO_E_UNSUPPORTED, "gaussian: non-periodic closures are out of scope (SURVEY.md 8f rank 2)");
+    if (n != 1 && n < 9) return fail(PDO_E_BADARG, "gaussian: periodic 9-point stencil needs n >= 9");
+    if (int rc = ensure_device()) return rc;
+    pdo_gaussian_s* o = new (std::nothrow) pdo_gaussian_s();
+    if (!o) return fail(PDO_E_BADARG, "out of memory");
+    o->n = n;
+    OpParams p{};
+    p.co[0] = agf; p.co[1] = bgf; p.co[2] = cgf; p.co[3] = dgf; p.co[4] = egf;
+    cudaError_t e = banded_op_create(&o->op, n, RK_SYM_9, 0, 0.0, 0.0, p);
+    if (e != cudaSuccess) {
+        delete o;
+        return fail(PDO_E_CUDA, "gaussian init: %s", cudaGetErrorString(e));
+    }
+    *h = o;
+    return 0;
+}
+int pdo_gaussian_destroy(pdo_gaussian_t h) {
+    if (!h) return 0;
+    banded_op_destroy(&h->op);
+    delete h;
+    return 0;
+}
+PDO_FIL_FN(pdo_gaussian_t, pdo_gaussian_filter1, 0)
+PDO_FIL_FN(pdo_gaussian_t, pdo_gaussian_filter2, 1)
+PDO_FIL_FN(pdo_gaussian_t, pdo_gaussian_filter3, 2)
+
+// ---------------- cd06stagg (periodic) ----------------
+int pdo_cd06stagg_init_periodic(pdo_cd06stagg_t* h, int n, double dx) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    *h = nullptr;
+    if (n <= 4) return fail(21, "CD06_stagg requires at least 4 points");  // cd06stagg.F90:182-184
+    if (int rc = ensure_device()) return rc;
+    pdo_cd06stagg_s* o = new (std::nothrow) pdo_cd06stagg_s();
+    if (!o) return fail(PDO_E_BADARG, "out of memory");
+    o->n = n;
+    const double onebydx = 1.0 / dx;
+    const double aD1 = 9.0 / 62.0, aD2 = 2.0 / 11.0, aI = 3.0 / 10.0;  // :174-176
+    OpParams d1{}, in{}, d2{};
+    d1.co[0] = (63.0 / 62.0) * onebydx; d1.co[1] = ((17.0 / 62.0) / 3.0) * onebydx;                       // :307-311
+    in.co[0] = (3.0 / 2.0) * (1.0 / 2.0); in.co[1] = (1.0 / 10.0) * (1.0 / 2.0);                           // :532-536
+    d2.co[0] = (12.0 / 11.0) * (onebydx * onebydx); d2.co[1] = ((3.0 / 11.0) / 4.0) * (onebydx * onebydx);  // :411-415
+    cudaError_t e = cudaSuccess;
+    auto mk = [&](int idx, int rk, double al, OpParams p, double sg, int ein, int eout) {
+        p.co[2] = sg; p.edge_in = ein; p.edge_out = eout;
+        if (e == cudaSuccess) e = banded_op_create(&o->ops[idx], n, rk, 1, al, 0.0, p);
+    };
+    mk(0, RK_STAG_E2C, aD1, d1, -1.0, 1, 0);  // ddz_E2C
+    mk(1, RK_STAG_C2E, aD1, d1, -1.0, 0, 1);  // ddz_C2E
+    mk(2, RK_STAG_E2C, aI, in, +1.0, 1, 0);   // InterpZ_E2C
+    mk(3, RK_STAG_C2E, aI, in, +1.0, 0, 1);   // InterpZ_C2E
+    mk(4, RK_D2_5, aD2, d2, 0.0, 0, 0);       // d2dz2_C2C
+    mk(5, RK_D2_5, aD2, d2, 0.0, 0, 1);       // d2dz2_E2E
+    if (e != cudaSuccess) {
+        pdo_cd06stagg_destroy(o);
+        return fail(PDO_E_CUDA, "cd06stagg init: %s", cudaGetErrorString(e));
+    }
+    *h = o;
+    return 0;
+}
+int pdo_cd06stagg_destroy(pdo_cd06stagg_t h) {
+    if (!h) return 0;
+    for (int i = 0; i < 6; ++i) banded_op_destroy(&h->ops[i]);
+    delete h;
+    return 0;
+}
+#define PDO_STAGG_FN(name, idx)                                                                                \
+    int name(pdo_cd06stagg_t h, const double* in, double* out, int n1, int n2, int is_complex, void* stream) { \
+        if (!h) return fail(PDO_E_BADARG, "null handle");                                                      \
+        /* complex data, real LU: re/im are independent lines -> a real field with 2*n1 points in x */         \
+        return apply(h->ops[idx], false, 2, in, out, (long long)n1 * (is_complex ? 2 : 1), n2, stream);        \
+    }
+PDO_STAGG_FN(pdo_cd06stagg_ddz_E2C, 0)
+PDO_STAGG_FN(pdo_cd06stagg_ddz_C2E, 1)
+PDO_STAGG_FN(pdo_cd06stagg_interpz_E2C, 2)
+PDO_STAGG_FN(pdo_cd06stagg_interpz_C2E, 3)
+PDO_STAGG_FN(pdo_cd06stagg_d2dz2_C2C, 4)
+PDO_STAGG_FN(pdo_cd06stagg_d2dz2_E2E, 5)
+
+}  // extern "C"
+
+// ---------------- DerivativesMod::derivatives / FiltersMod::filters ----------------
+struct pdo_derivatives_s {
+    int xsz[3], ysz[3], zsz[3];
+    int method[3];  // 0 cd10, 1 cd06
+    pdo_cd10_t c10[3];
+    pdo_cd06_t c06[3];
+};
+struct pdo_filters_s {
+    int xsz[3], ysz[3], zsz[3];
+    int method[3];  // 0 cf90, 1 gaussian
+    pdo_cf90_t cf[3];
+    pdo_gaussian_t ga[3];
+};
+
+extern "C" {
+
+int pdo_derivatives_init(pdo_derivatives_t* h, const int xsz[3], const int ysz[3], const int zsz[3], double dx, double dy,
+                         double dz, int px, int py, int pz, const char* mx, const char* my, const char* mz) {
+    if (!h || !xsz || !ysz || !zsz || !mx || !my || !mz) return fail(PDO_E_BADARG, "null argument");
+    *h = nullptr;
+    pdo_derivatives_s* o = new (std::nothrow) pdo_derivatives_s();
+    if (!o) return fail(PDO_E_BADARG, "out of memory");
+    std::memcpy(o->xsz, xsz, sizeof(o->xsz));
+    std::memcpy(o->ysz, ysz, sizeof(o->ysz));
+    std::memcpy(o->zsz, zsz, sizeof(o->zsz));
+    const int n[3] = {xsz[0], ysz[1], zsz[2]};  // derivatives.F90:288, 322, 356
+    const double d[3] = {dx, dy, dz};
+    const int per[3] = {px, py, pz};
+    const char* m[3] = {mx, my, mz};
+    for (int a = 0; a < 3; ++a) { o->c10[a] = nullptr; o->c06[a] = nullptr; }
+    for (int a = 0; a < 3; ++a) {
+        int rc;
+        if (std::strncmp(m[a], "cd10", 4) == 0) {
+            o->method[a] = 0;
+            rc = pdo_cd10_init(&o->c10[a], n[a], d[a], per[a], 0, 0);
+        } else if (std::strncmp(m[a], "cd06", 4) == 0) {
+            o->method[a] = 1;
+            rc = pdo_cd06_init(&o->c06[a], n[a], d[a], per[a], 0, 0);
+        } else {
+            rc = fail(PDO_E_UNSUPPORTED, "derivatives: method '%s' is out of scope (cd10, cd06 only; SURVEY.md 2.1 #5-6)", m[a]);
+        }
+        if (rc) {
+            pdo_derivatives_destroy(o);
+            return rc;
+        }
+    }
+    *h = o;
+    return 0;
+}
+int pdo_derivatives_destroy(pdo_derivatives_t h) {
+    if (!h) return 0;
+    for (int a = 0; a < 3; ++a) { pdo_cd10_destroy(h->c10[a]); pdo_cd06_destroy(h->c06[a]); }
+    delete h;
+    return 0;
+}
+static int der_apply(pdo_derivatives_t h, int axis, int order, const double* f, double* out, int bc1, int bcn, void* st) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    const int* sz = axis == 0 ? h->xsz : axis == 1 ? h->ysz : h->zsz;
+    int na, nb;
+    if (axis == 0) { na = sz[1]; nb = sz[2]; }
+    else if (axis == 1) { na = sz[0]; nb = sz[2]; }
+    else { na = sz[0]; nb = sz[1]; }
+    if (h->method[axis] == 0) {
+        typedef int (*fn_t)(pdo_cd10_t, const double*, double*, int, int, int, int, void*);
+        static const fn_t fns[2][3] = {{pdo_cd10_dd1, pdo_cd10_dd2, pdo_cd10_dd3}, {pdo_cd10_d2d1, pdo_cd10_d2d2, pdo_cd10_d2d3}};
+        return fns[order - 1][axis](h->c10[axis], f, out, na, nb, bc1, bcn, st);
+    }
+    if (order == 2) return fail(PDO_E_UNSUPPORTED, "CD06 is incomplete right now");  // derivatives.F90:525
+    typedef int (*fn6_t)(pdo_cd06_t, const double*, double*, int, int, int, int, void*);
+    static const fn6_t f6[3] = {pdo_cd06_dd1, pdo_cd06_dd2, pdo_cd06_dd3};
+    return f6[axis](h->c06[axis], f, out, na, nb, bc1, bcn, st);
+}
+int pdo_derivatives_ddx(pdo_derivatives_t h, const double* f, double* o, int b1, int bn, void* s) { return der_apply(h, 0, 1, f, o, b1, bn, s); }
+int pdo_derivatives_ddy(pdo_derivatives_t h, const double* f, double* o, int b1, int bn, void* s) { return der_apply(h, 1, 1, f, o, b1, bn, s); }
+int pdo_derivatives_ddz(pdo_derivatives_t h, const double* f, double* o, int b1, int bn, void* s) { return der_apply(h, 2, 1, f, o, b1, bn, s); }
+int pdo_derivatives_d2dx2(pdo_derivatives_t h, const double* f, double* o, int b1, int bn, void* s) { return der_apply(h, 0, 2, f, o, b1, bn, s); }
+int pdo_derivatives_d2dy2(pdo_derivatives_t h, const double* f, double* o, int b1, int bn, void* s) { return der_apply(h, 1, 2, f, o, b1, bn, s); }
+int pdo_derivatives_d2dz2(pdo_derivatives_t h, const double* f, double* o, int b1, int bn, void* s) { return der_apply(h, 2, 2, f, o, b1, bn, s); }
+
+int pdo_filters_init(pdo_filters_t* h, const int xsz[3], const int ysz[3], const int zsz[3], int px, int py, int pz,
+                     const char* mx, const char* my, const char* mz) {
+    if (!h || !xsz || !ysz || !zsz || !mx || !my || !mz) return fail(PDO_E_BADARG, "null argument");
+    *h = nullptr;
+    pdo_filters_s* o = new (std::nothrow) pdo_filters_s();
+    if (!o) return fail(PDO_E_BADARG, "out of memory");
+    std::memcpy(o->xsz, xsz, sizeof(o->xsz));
+    std::memcpy(o->ysz, ysz, sizeof(o->ysz));
+    std::memcpy(o->zsz, zsz, sizeof(o->zsz));
+    const int n[3] = {xsz[0], ysz[1], zsz[2]};
+    const int per[3] = {px, py, pz};
+    const char* m[3] = {mx, my, mz};
+    for (int a = 0; a < 3; ++a) { o->cf[a] = nullptr; o->ga[a] = nullptr; }
+    for (int a = 0; a < 3; ++a) {
+        int rc;
+        if (std::strncmp(m[a], "cf90", 4) == 0) {
+            o->method[a] = 0;
+            rc = pdo_cf90_init(&o->cf[a], n[a], per[a]);
+        } else if (std::strncmp(m[a], "gaussian", 8) == 0) {
+            o->method[a] = 1;
+            rc = pdo_gaussian_init(&o->ga[a], n[a], per[a]);
+        } else {
+            rc = fail(PDO_E_UNSUPPORTED, "filters: method '%s' is out of scope (cf90, gaussian only; SURVEY.md 2.1 #9)", m[a]);
+        }
+        if (rc) {
+            pdo_filters_destroy(o);
+            return rc;
+        }
+    }
+    *h = o;
+    return 0;
+}
+int pdo_filters_destroy(pdo_filters_t h) {
+    if (!h) return 0;
+    for (int a = 0; a < 3; ++a) { pdo_cf90_destroy(h->cf[a]); pdo_gaussian_destroy(h->ga[a]); }
+    delete h;
+    return 0;
+}
+static int fil_apply(pdo_filters_t h, int axis, const double* f, double* out, int bc1, int bcn, void* st) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    const int* sz = axis == 0 ? h->xsz : axis == 1 ? h->ysz : h->zsz;
+    int na, nb;
+    if (axis == 0) { na = sz[1]; nb = sz[2]; }
+    else if (axis == 1) { na = sz[0]; nb = sz[2]; }
+    else { na = sz[0]; nb = sz[1]; }
+    if (h->method[axis] == 0) {
+        typedef int (*fn_t)(pdo_cf90_t, const double*, double*, int, int, int, int, void*);
+        static const fn_t fns[3] = {pdo_cf90_filter1, pdo_cf90_filter2, pdo_cf90_filter3};
+        return fns[axis](h->cf[axis], f, out, na, nb, bc1, bcn, st);
+    }
+    typedef int (*fng_t)(pdo_gaussian_t, const double*, double*, int, int, int, int, void*);
+    static const fng_t fg[3] = {pdo_gaussian_filter1, pdo_gaussian_filter2, pdo_gaussian_filter3};
+    return fg[axis](h->ga[axis], f, out, na, nb, bc1, bcn, st);
+}
+int pdo_filters_filterx(pdo_filters_t h, const double* f, double* o, int b1, int bn, void* s) { return fil_apply(h, 0, f, o, b1, bn, s); }
+int pdo_filters_filtery(pdo_filters_t h, const double* f, double* o, int b1, int bn, void* s) { return fil_apply(h, 1, f, o, b1, bn, s); }
+int pdo_filters_filterz(pdo_filters_t h, const double* f, double* o, int b1, int bn, void* s) { return fil_apply(h, 2, f, o, b1, bn, s); }
+
+// test hook (not in the public header): run the any-n kernels even when a chunked path exists
+int pdo_debug_cd10_generic(pdo_cd10_t h, int which, int axis, const double* f, double* df, int na, int nb, void* stream) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    PDO_CUDA(banded_op_apply(which == 1 ? &h->d1 : &h->d2, axis, f, df, na, nb, (cudaStream_t)stream, 1));
+    g_launches += 2;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,344 @@
+// decomp.cu — 2DECOMP pencil decomposition arithmetic and the four pencil transposes on NCCL.
+//
+// Replaces (2D» = dependencies/2decomp_fft-1.5.847.tar.gz » 2decomp_fft/src):
+//   decomp_2d_init / decomp_info_init / partition / distribute / prepare_buffer   2D» decomp_2d.f90:297-455, 498-580, 622-794
+//   transpose_x_to_y / y_to_x / y_to_z / z_to_y (real + complex)                  2D» transpose_*.f90
+//   p_maxval / p_sum                                                              utilities/reductions.F90:29-225
+// Process model: one process per GPU; rank r sits at (r / p_col, r % p_col) like MPI_CART_CREATE without
+// reorder.  The reference's MPI_ALLTOALLV on the COL / ROW sub-communicators becomes one grouped
+// ncclSend/ncclRecv exchange addressed by world rank (no communicator split needed), bracketed by a
+// single batched pack kernel and a single batched unpack kernel; the block a rank keeps for itself never
+// touches NCCL.  With one rank in the sub-communicator the two pencils have the same layout and the
+// transpose is a device copy.  Work buffers belong to the decomp handle (the reference's are module
+// globals, which is what makes its transposes non-re-entrant).
+#include <nccl.h>
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace pdo;
+
+namespace {
+
+struct Comm {
+    bool inited = false;
+    int rank = 0, nproc = 1;
+    ncclComm_t comm = nullptr;
+    double* d_scalar = nullptr;
+};
+Comm g_comm;
+
+#define PDO_NCCL(expr)                                                                                          \
+    do {                                                                                                        \
+        ncclResult_t _r = (expr);                                                                               \
+        if (_r != ncclSuccess) return fail(PDO_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, ncclGetErrorString(_r)); \
+    } while (0)
+
+// distribute (2D» decomp_2d.f90:676-708) in closed form: the last `rem` ranks get one extra point.
+inline int dist_size(int n, int p, int i) { const int base = n / p, rem = n % p; return base + (i >= p - rem ? 1 : 0); }
+inline int dist_start0(int n, int p, int i) {  // 0-based start
+    const int base = n / p, rem = n % p;
+    const int extra = i - (p - rem);
+    return i * base + (extra > 0 ? extra : 0);
+}
+
+void fill_info(int nx, int ny, int nz, int p_row, int p_col, int rank, pdo_decomp_info* d) {
+    const int c1 = rank / p_col, c2 = rank % p_col;
+    auto set = [](int* st, int* en, int* sz, int i, int n, int p, int c) {
+        if (p < 0) { st[i] = 1; en[i] = n; sz[i] = n; }
+        else { st[i] = dist_start0(n, p, c) + 1; sz[i] = dist_size(n, p, c); en[i] = st[i] + sz[i] - 1; }
+    };
+    // x-pencil: (nx, ny/p_row, nz/p_col); y-pencil: (nx/p_row, ny, nz/p_col); z-pencil: (nx/p_row, ny/p_col, nz)
+    set(d->xst, d->xen, d->xsz, 0, nx, -1, 0); set(d->xst, d->xen, d->xsz, 1, ny, p_row, c1); set(d->xst, d->xen, d->xsz, 2, nz, p_col, c2);
+    set(d->yst, d->yen, d->ysz, 0, nx, p_row, c1); set(d->yst, d->yen, d->ysz, 1, ny, -1, 0); set(d->yst, d->yen, d->ysz, 2, nz, p_col, c2);
+    set(d->zst, d->zen, d->zsz, 0, nx, p_row, c1); set(d->zst, d->zen, d->zsz, 1, ny, p_col, c2); set(d->zst, d->zen, d->zsz, 2, nz, -1, 0);
+}
+
+// ---- batched 3-D box copy: the pack (mem_split_*) and unpack (mem_merge_*) loops of every peer in ONE launch ----
+constexpr int kMaxPeers = 16;
+struct BoxCopy {
+    long long src_off, dst_off;       // element (double) offsets
+    long long s_ld2, s_ld3, d_ld2, d_ld3;  // strides of index 2 and 3 on each side (index 1 is contiguous)
+    int b1, b2, b3;                   // box extents (b1 in doubles)
+};
+struct BoxBatch { int count; BoxCopy c[kMaxPeers]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) box_copy_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                                       const __grid_constant__ BoxBatch batch) {
+    const BoxCopy& c = batch.c[blockIdx.y];
+    constexpr int V = sizeof(T) / sizeof(double);
+    const int b1v = c.b1 / V;
+    const long long rows = (long long)c.b2 * c.b3;
+    const T* s = reinterpret_cast<const T*>(src + c.src_off);
+    T* d = reinterpret_cast<T*>(dst + c.dst_off);
+    for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows; row += (long long)gridDim.x * blockDim.y) {
+        const long long k = row / c.b2;
+        const int j = (int)(row - k * c.b2);
+        const T* sr = s + (j * c.s_ld2 + k * c.s_ld3) / V;
+        T* dr = d + (j * c.d_ld2 + k * c.d_ld3) / V;
+        for (int i = threadIdx.x; i < b1v; i += blockDim.x) dr[i] = sr[i];
+    }
+}
+
+int launch_box_copy(const double* src, double* dst, const BoxBatch& b, cudaStream_t st) {
+    if (b.count == 0) return 0;
+    bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    long long max_rows = 0;
+    int min_b1 = 1 << 30;
+    for (int i = 0; i < b.count; ++i) {
+        const BoxCopy& c = b.c[i];
+        if ((c.b1 | c.src_off | c.dst_off | c.s_ld2 | c.s_ld3 | c.d_ld2 | c.d_ld3) & 1) vec = false;
+        const long long rows = (long long)c.b2 * c.b3;
+        if (rows > max_rows) max_rows = rows;
+        if (c.b1 < min_b1) min_b1 = c.b1;
+    }
+    if (max_rows == 0 || min_b1 <= 0) return 0;
+    const int tx = (min_b1 / (vec ? 2 : 1)) >= 128 ? 128 : ((min_b1 / (vec ? 2 : 1)) >= 64 ? 64 : 32);
+    dim3 block(tx, 256 / tx);
+    long long gx = (max_rows + block.y - 1) / block.y;
+    const long long cap = 148LL * 16;
+    if (gx > cap) gx = cap;
+    dim3 grid((unsigned)gx, (unsigned)b.count);
+    if (vec) box_copy_kernel<double2><<<grid, block, 0, st>>>(src, dst, b);
+    else box_copy_kernel<double><<<grid, block, 0, st>>>(src, dst, b);
+    PDO_CUDA(cudaGetLastError());
+    g_launches += 1;
+    return 0;
+}
+
+}  // namespace
+
+struct pdo_decomp_s {
+    int nx, ny, nz, p_row, p_col, c1, c2;
+    pdo_decomp_info info;
+    std::vector<int> x1dist, y1dist, y2dist, z2dist;
+    double* work_send = nullptr;
+    double* work_recv = nullptr;
+    size_t work_cap = 0;  // doubles
+};
+
+namespace {
+
+int ensure_work(pdo_decomp_s* d, size_t doubles) {
+    if (d->work_cap >= doubles) return 0;
+    if (d->work_send) cudaFree(d->work_send);
+    if (d->work_recv) cudaFree(d->work_recv);
+    d->work_send = d->work_recv = nullptr;
+    d->work_cap = 0;
+    PDO_CUDA(cudaMalloc(&d->work_send, doubles * sizeof(double)));
+    PDO_CUDA(cudaMalloc(&d->work_recv, doubles * sizeof(double)));
+    d->work_cap = doubles;
+    return 0;
+}
+
+inline long long vol3(const int* s) { return (long long)s[0] * s[1] * s[2]; }
+
+// dir: 0 x→y, 1 y→x, 2 y→z, 3 z→y.  Device pointers.  w = doubles per element.
+int transpose_device(pdo_decomp_s* d, int dir, const double* src, double* dst, int w, cudaStream_t st) {
+    const bool col = (dir == 0 || dir == 1);
+    const int np = col ? d->p_row : d->p_col;
+    const int me = col ? d->c1 : d->c2;
+    const int* ssz = (dir == 0) ? d->info.xsz : (dir == 3) ? d->info.zsz : d->info.ysz;
+    const int* dsz = (dir == 1) ? d->info.xsz : (dir == 2) ? d->info.zsz : d->info.ysz;
+    const long long s1 = (long long)ssz[0] * w, s2 = ssz[1], s3 = ssz[2];
+    const long long d1 = (long long)dsz[0] * w, d2 = dsz[1], d3 = dsz[2];
+    if (np == 1) {  // same layout on both sides
+        PDO_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * s1 * s2 * s3, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    if (np > kMaxPeers) return fail(PDO_E_UNSUPPORTED, "more than %d ranks in one sub-communicator", kMaxPeers);
+    const std::vector<int>& sdist = (dir == 0) ? d->x1dist : (dir == 3) ? d->z2dist : (dir == 1) ? d->y1dist : d->y2dist;
+    const std::vector<int>& rdist = (dir == 0) ? d->y1dist : (dir == 3) ? d->y2dist : (dir == 1) ? d->x1dist : d->z2dist;
+    // send block to peer m = a range of SRC index (1 for x→y, 2 for y→x / y→z, 3 for z→y);
+    // recv block from peer m = a range of DST index (2 for x→y / z→y, 1 for y→x, 3 for y→z).
+    std::vector<long long> scnt(np), sdisp(np), rcnt(np), rdisp(np), sst(np), rst(np);
+    long long sacc = 0, racc = 0, sa = 0, ra = 0;
+    for (int m = 0; m < np; ++m) {
+        sst[m] = sa; rst[m] = ra;
+        scnt[m] = (dir == 0) ? (long long)sdist[m] * w * s2 * s3 : (dir == 3) ? s1 * s2 * sdist[m] : s1 * sdist[m] * s3;
+        rcnt[m] = (dir == 1) ? (long long)rdist[m] * w * d2 * d3 : (dir == 2) ? d1 * d2 * rdist[m] : d1 * rdist[m] * d3;
+        sdisp[m] = sacc; rdisp[m] = racc;
+        sacc += scnt[m]; racc += rcnt[m];
+        sa += sdist[m]; ra += rdist[m];
+    }
+    const bool need_pack = (dir != 3), need_unpack = (dir != 2);
+    if (int rc = ensure_work(d, (size_t)((sacc > racc ? sacc : racc) + 2))) return rc;
+
+    auto src_box = [&](int m, BoxCopy& c) {  // where peer m's block lives in src
+        c.s_ld2 = s1; c.s_ld3 = s1 * s2;
+        if (dir == 0) { c.src_off = sst[m] * w; c.b1 = sdist[m] * w; c.b2 = (int)s2; c.b3 = (int)s3; }
+        else if (dir == 3) { c.src_off = sst[m] * s1 * s2; c.b1 = (int)s1; c.b2 = (int)s2; c.b3 = sdist[m]; }
+        else { c.src_off = sst[m] * s1; c.b1 = (int)s1; c.b2 = sdist[m]; c.b3 = (int)s3; }
+    };
+    auto dst_box = [&](int m, BoxCopy& c) {  // where the block from peer m lands in dst
+        c.d_ld2 = d1; c.d_ld3 = d1 * d2;
+        if (dir == 1) { c.dst_off = rst[m] * w; c.b1 = rdist[m] * w; c.b2 = (int)d2; c.b3 = (int)d3; }
+        else if (dir == 2) { c.dst_off = rst[m] * d1 * d2; c.b1 = (int)d1; c.b2 = (int)d2; c.b3 = rdist[m]; }
+        else { c.dst_off = rst[m] * d1; c.b1 = (int)d1; c.b2 = rdist[m]; c.b3 = (int)d3; }
+    };
+    // 1) my own block: src box → dst box directly
+    {
+        BoxBatch b{};
+        b.count = 1;
+        src_box(me, b.c[0]);
+        const int sb1 = b.c[0].b1, sb2 = b.c[0].b2, sb3 = b.c[0].b3;
+        dst_box(me, b.c[0]);
+        if (sb1 != b.c[0].b1 || sb2 != b.c[0].b2 || sb3 != b.c[0].b3) return fail(PDO_E_BADARG, "transpose: self block mismatch");
+        if (int rc = launch_box_copy(src, dst, b, st)) return rc;
+    }
+    // 2) pack the other peers' blocks (contiguous, in peer order, at the ALLTOALLV displacements)
+    if (need_pack) {
+        BoxBatch b{};
+        for (int m = 0; m < np; ++m) {
+            if (m == me) continue;
+            BoxCopy& c = b.c[b.count++];
+            src_box(m, c);
+            c.dst_off = sdisp[m]; c.d_ld2 = c.b1; c.d_ld3 = (long long)c.b1 * c.b2;
+        }
+        if (int rc = launch_box_copy(src, d->work_send, b, st)) return rc;
+    }
+    // 3) the exchange
+    PDO_NCCL(ncclGroupStart());
+    for (int m = 0; m < np; ++m) {
+        if (m == me) continue;
+        const int peer = col ? (m * d->p_col + d->c2) : (d->c1 * d->p_col + m);
+        const double* sp = need_pack ? d->work_send + sdisp[m] : src + sst[m] * s1 * s2;
+        double* rp = need_unpack ? d->work_recv + rdisp[m] : dst + rst[m] * d1 * d2;
+        PDO_NCCL(ncclSend(sp, (size_t)scnt[m], ncclDouble, peer, g_comm.comm, st));
+        PDO_NCCL(ncclRecv(rp, (size_t)rcnt[m], ncclDouble, peer, g_comm.comm, st));
+    }
+    PDO_NCCL(ncclGroupEnd());
+    g_launches += 1;
+    // 4) unpack
+    if (need_unpack) {
+        BoxBatch b{};
+        for (int m = 0; m < np; ++m) {
+            if (m == me) continue;
+            BoxCopy& c = b.c[b.count++];
+            dst_box(m, c);
+            c.src_off = rdisp[m]; c.s_ld2 = c.b1; c.s_ld3 = (long long)c.b1 * c.b2;
+        }
+        if (int rc = launch_box_copy(d->work_recv, dst, b, st)) return rc;
+    }
+    return 0;
+}
+
+int transpose_any(pdo_decomp_t h, int dir, const double* src, double* dst, int w, void* stream) {
+    if (!h || !src || !dst) return fail(PDO_E_BADARG, "null argument");
+    if (w != 1 && w != 2) return fail(PDO_E_BADARG, "elem_doubles must be 1 (real) or 2 (complex)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int* ssz = (dir == 0) ? h->info.xsz : (dir == 3) ? h->info.zsz : h->info.ysz;
+    const int* dsz = (dir == 1) ? h->info.xsz : (dir == 2) ? h->info.zsz : h->info.ysz;
+    return with_device_views(src, sizeof(double) * vol3(ssz) * w, dst, sizeof(double) * vol3(dsz) * w, st,
+                             [&](const void* ds, void* dd) { return transpose_device(h, dir, (const double*)ds, (double*)dd, w, st); });
+}
+
+}  // namespace
+
+namespace pdo {
+// used by spectral.cu: transposes on device pointers without the host-pointer probe
+int decomp_transpose_device(pdo_decomp_t h, int dir, const double* src, double* dst, int w, cudaStream_t st) {
+    return transpose_device(h, dir, src, dst, w, st);
+}
+}  // namespace pdo
+
+extern "C" {
+
+int pdo_comm_unique_id(char id[128]) {
+    ncclUniqueId uid;
+    static_assert(sizeof(uid) == 128, "ncclUniqueId is 128 bytes");
+    PDO_NCCL(ncclGetUniqueId(&uid));
+    std::memcpy(id, &uid, 128);
+    return 0;
+}
+
+int pdo_comm_init(int rank, int nproc, const char unique_id[128]) {
+    if (g_comm.inited) return fail(PDO_E_BADARG, "communicator already initialised");
+    if (nproc < 1 || rank < 0 || rank >= nproc) return fail(PDO_E_BADARG, "bad rank/nproc");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PDO_E_NODEVICE, "no CUDA device available: padeops_b200 has no CPU fallback");
+    }
+    g_comm.rank = rank; g_comm.nproc = nproc;
+    if (nproc > 1) {
+        if (!unique_id) return fail(PDO_E_BADARG, "unique_id required for nproc > 1");
+        ncclUniqueId uid;
+        std::memcpy(&uid, unique_id, 128);
+        PDO_NCCL(ncclCommInitRank(&g_comm.comm, nproc, uid, rank));
+        PDO_CUDA(cudaMalloc(&g_comm.d_scalar, 2 * sizeof(double)));
+    }
+    g_comm.inited = true;
+    return 0;
+}
+
+int pdo_comm_finalize(void) {
+    if (g_comm.comm) { ncclCommDestroy(g_comm.comm); g_comm.comm = nullptr; }
+    if (g_comm.d_scalar) { cudaFree(g_comm.d_scalar); g_comm.d_scalar = nullptr; }
+    g_comm = Comm();
+    return 0;
+}
+int pdo_comm_rank(void) { return g_comm.rank; }
+int pdo_comm_size(void) { return g_comm.nproc; }
+
+int pdo_decomp_info_for(int nx, int ny, int nz, int p_row, int p_col, int rank, pdo_decomp_info* info) {
+    if (!info || p_row < 1 || p_col < 1 || rank < 0 || rank >= p_row * p_col) return fail(PDO_E_BADARG, "bad argument");
+    // decomp_info_init's check (2D» decomp_2d.f90:507-514), error code 6
+    if (nx < p_row || ny < p_row || ny < p_col || nz < p_col)
+        return fail(6, "Invalid 2D processor grid. Make sure that min(nx,ny) >= p_row and min(ny,nz) >= p_col");
+    fill_info(nx, ny, nz, p_row, p_col, rank, info);
+    return 0;
+}
+
+int pdo_decomp_init(pdo_decomp_t* h, int nx, int ny, int nz, int p_row, int p_col) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    *h = nullptr;
+    const int nproc = g_comm.nproc;
+    if (p_row == 0 && p_col == 0) { p_row = 1; p_col = nproc; }
+    if (p_row * p_col != nproc) return fail(1, "Invalid 2D processor grid - nproc /= p_row*p_col");  // 2D» decomp_2d.f90:331-334
+    pdo_decomp_info info;
+    if (int rc = pdo_decomp_info_for(nx, ny, nz, p_row, p_col, g_comm.rank, &info)) return rc;
+    pdo_decomp_s* d = new (std::nothrow) pdo_decomp_s();
+    if (!d) return fail(PDO_E_BADARG, "out of memory");
+    d->nx = nx; d->ny = ny; d->nz = nz; d->p_row = p_row; d->p_col = p_col;
+    d->c1 = g_comm.rank / p_col; d->c2 = g_comm.rank % p_col;
+    d->info = info;
+    for (int i = 0; i < p_row; ++i) { d->x1dist.push_back(dist_size(nx, p_row, i)); d->y1dist.push_back(dist_size(ny, p_row, i)); }
+    for (int i = 0; i < p_col; ++i) { d->y2dist.push_back(dist_size(ny, p_col, i)); d->z2dist.push_back(dist_size(nz, p_col, i)); }
+    *h = d;
+    return 0;
+}
+int pdo_decomp_destroy(pdo_decomp_t h) {
+    if (!h) return 0;
+    if (h->work_send) cudaFree(h->work_send);
+    if (h->work_recv) cudaFree(h->work_recv);
+    delete h;
+    return 0;
+}
+int pdo_decomp_get_info(pdo_decomp_t h, pdo_decomp_info* info) {
+    if (!h || !info) return fail(PDO_E_BADARG, "null argument");
+    *info = h->info;
+    return 0;
+}
+
+int pdo_transpose_x_to_y(pdo_decomp_t h, const double* s, double* d, int w, void* st) { return transpose_any(h, 0, s, d, w, st); }
+int pdo_transpose_y_to_x(pdo_decomp_t h, const double* s, double* d, int w, void* st) { return transpose_any(h, 1, s, d, w, st); }
+int pdo_transpose_y_to_z(pdo_decomp_t h, const double* s, double* d, int w, void* st) { return transpose_any(h, 2, s, d, w, st); }
+int pdo_transpose_z_to_y(pdo_decomp_t h, const double* s, double* d, int w, void* st) { return transpose_any(h, 3, s, d, w, st); }
+
+static int allreduce1(double local, double* global, ncclRedOp_t op) {
+    if (!global) return fail(PDO_E_BADARG, "null argument");
+    if (g_comm.nproc == 1) { *global = local; return 0; }
+    PDO_CUDA(cudaMemcpy(g_comm.d_scalar, &local, sizeof(double), cudaMemcpyHostToDevice));
+    PDO_NCCL(ncclAllReduce(g_comm.d_scalar, g_comm.d_scalar + 1, 1, ncclDouble, op, g_comm.comm, 0));
+    PDO_CUDA(cudaMemcpy(global, g_comm.d_scalar + 1, sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int pdo_p_maxval(double local, double* global) { return allreduce1(local, global, ncclMax); }
+int pdo_p_sum(double local, double* global) { return allreduce1(local, global, ncclSum); }
+
+}  // extern "C"
