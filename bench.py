@@ -83,11 +83,12 @@ def run_reference(args):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 3))
-    cb, t = cpu_arm(512, steps, min(args.warmup, 1))
+    ncpu = int(os.environ.get("PDO_BENCH_CPU_N", "512"))
+    cb, t = cpu_arm(ncpu, steps, min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cd10 ddx+ddy+ddz, periodic, 512^3 sample of the 1024^3 workload (CPU arm)", "n": 512},
+            "config": {"workload": f"cd10 ddx+ddy+ddz, periodic, {ncpu}^3 sample of the 1024^3 workload (CPU arm)", "n": ncpu},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)

@@ -64,29 +64,32 @@ __device__ __forceinline__ double rhs_eval(const double* w, const OpParams& op) 
 
 // ------------------------------------------------------------------------------------------------
 // Chunk engine: r[0..M) (RHS of this thread's chunk, in registers) → x[0..M) in place.
-// smem: gA[BW][nchunk_slots], gB[BW][..], s[BW][..]; `slot(q)` maps chunk q of MY line to its slot.
+// smem: gA[BW][slots], gB[BW][slots], s[BW][slots]; `slot(q)` maps chunk q of MY line to its slot.
 // Two __syncthreads; every thread of the CTA must call this.
+// The sweeps are written so that the loop-carried dependency is ONE fma per row: the term that does not
+// depend on the previous row is folded in first, and 1/g is pre-multiplied into the factors.
 // ------------------------------------------------------------------------------------------------
 template <int BW, int M, class SlotFn>
 __device__ __forceinline__ void chunk_solve(double (&r)[M], const ChunkTables& t, double* __restrict__ sm_g,
                                             int slots, int p, SlotFn slot) {
     constexpr int mi = M - BW;
-    // forward elimination on the interior block
-    r[1] = r[1] - t.l1[1] * r[0];
+    // forward elimination on the interior block: y_i = (r_i - l2_i y_{i-2}) - l1_i y_{i-1}
+    r[1] = __fma_rn(-t.l1[1], r[0], r[1]);
 #pragma unroll
     for (int i = 2; i < mi; ++i) {
-        if (BW == 2) r[i] = r[i] - t.l1[i] * r[i - 1] - t.l2[i] * r[i - 2];
-        else r[i] = r[i] - t.l1[i] * r[i - 1];
+        if (BW == 2) r[i] = __fma_rn(-t.l1[i], r[i - 1], __fma_rn(-t.l2[i], r[i - 2], r[i]));
+        else r[i] = __fma_rn(-t.l1[i], r[i - 1], r[i]);
     }
-    // back substitution
+    // back substitution: z_i = (y_i ginv_i - bg_i z_{i+2}) - ug_i z_{i+1}
     r[mi - 1] = r[mi - 1] * t.ginv[mi - 1];
     if (BW == 2) {
-        r[mi - 2] = (r[mi - 2] - t.u1[mi - 2] * r[mi - 1]) * t.ginv[mi - 2];
+        r[mi - 2] = __fma_rn(-t.ug[mi - 2], r[mi - 1], r[mi - 2] * t.ginv[mi - 2]);
 #pragma unroll
-        for (int i = mi - 3; i >= 0; --i) r[i] = (r[i] - t.u1[i] * r[i + 1] - t.b2 * r[i + 2]) * t.ginv[i];
+        for (int i = mi - 3; i >= 0; --i)
+            r[i] = __fma_rn(-t.ug[i], r[i + 1], __fma_rn(-t.bg[i], r[i + 2], r[i] * t.ginv[i]));
     } else {
 #pragma unroll
-        for (int i = mi - 2; i >= 0; --i) r[i] = (r[i] - t.u1[i] * r[i + 1]) * t.ginv[i];
+        for (int i = mi - 2; i >= 0; --i) r[i] = __fma_rn(-t.ug[i], r[i + 1], r[i] * t.ginv[i]);
     }
     // reduced right-hand side pieces: gA from my chunk's tail rows, gB = what my head rows contribute to the
     // separator rows of the PREVIOUS chunk.
@@ -141,17 +144,18 @@ __device__ __forceinline__ void chunk_solve(double (&r)[M], const ChunkTables& t
 }
 
 // ------------------------------------------------------------------------------------------------
-// Strided (y / z) kernel
+// Strided (y / z) kernels.  THREADS = XT * P threads per CTA (XT contiguous columns x P chunks).
+//   chunk_strided_kernel       one tile per CTA, loads straight into registers (halo rows re-read via L1/L2)
+//   chunk_strided_pipe_kernel  persistent CTAs; the NEXT tile streams into shared memory with cp.async while
+//                              the current one is being solved out of registers; halo rows come from the tile
 // ------------------------------------------------------------------------------------------------
-constexpr int kStridedThreads = 512;
-
-template <int RK, int BW, int M>
-__global__ void __launch_bounds__(kStridedThreads, 1)
+template <int RK, int BW, int M, int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
 chunk_strided_kernel(const double* __restrict__ f, double* __restrict__ out, long long n1, int n, long long in_slab,
                      long long out_slab, int tiles_x, int XT, const __grid_constant__ ChunkTables tab,
                      const __grid_constant__ OpParams op) {
     constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
-    extern __shared__ double sm_g[];
+    extern __shared__ __align__(16) double sm_g[];
     const int tid = threadIdx.x;
     const int xi = tid % XT, p = tid / XT;
     const int P = n / M;
@@ -186,40 +190,140 @@ chunk_strided_kernel(const double* __restrict__ f, double* __restrict__ out, lon
     }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Stream tile `tile` (rows_in rows of XT doubles starting at column x0 of slab k) into smem `buf[row][XT]`.
+template <int THREADS>
+__device__ __forceinline__ void pipe_issue_tile(double* buf, const double* __restrict__ f, long long tile, int tiles_x,
+                                                int XT, int rows_in, long long n1, long long in_slab, bool vec16) {
+    const long long k = tile / tiles_x;
+    const long long x0 = (tile - k * tiles_x) * XT;
+    const double* base = f + k * in_slab + x0;
+    const int tid = threadIdx.x;
+    if (vec16) {
+        const int upr = XT >> 1;  // 16-byte units per row
+        const int units = rows_in * upr;
+        for (int u = tid; u < units; u += blockDim.x) {
+            const int row = u / upr, c = (u - row * upr) * 2;
+            if (x0 + c < n1) cp_async16(buf + row * XT + c, base + (long long)row * n1 + c);
+        }
+    } else {
+        const int units = rows_in * XT;
+        for (int u = tid; u < units; u += blockDim.x) {
+            const int row = u / XT, c = u - row * XT;
+            if (x0 + c < n1) cp_async8(buf + row * XT + c, base + (long long)row * n1 + c);
+        }
+    }
+    cp_async_commit();
+}
+
+template <int RK, int BW, int M, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+chunk_strided_pipe_kernel(const double* __restrict__ f, double* __restrict__ out, long long n1, int n, long long in_slab,
+                          long long out_slab, int tiles_x, int XT, long long ntiles, int vec16,
+                          const __grid_constant__ ChunkTables tab, const __grid_constant__ OpParams op) {
+    constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
+    extern __shared__ __align__(16) double sm[];
+    const int P = n / M;
+    const int rows_in = op.edge_in ? n + 1 : n;
+    double* buf = sm;                                   // [rows_in][XT]
+    double* sm_g = sm + (((size_t)rows_in * XT + 1) & ~(size_t)1);
+    const int tid = threadIdx.x;
+    const int xi = tid % XT, p = tid / XT;
+    const int nwrap = rows_in;
+
+    long long tile = blockIdx.x;
+    if (tile < ntiles) pipe_issue_tile<THREADS>(buf, f, tile, tiles_x, XT, rows_in, n1, in_slab, vec16 != 0);
+    for (; tile < ntiles; tile += gridDim.x) {
+        cp_async_wait_all();
+        __syncthreads();
+        double v[M + HL + HR];
+#pragma unroll
+        for (int j = 0; j < M + HL + HR; ++j) {
+            int q = p * M - HL + j;
+            if (j < HL) { if (q < 0) q += n; }
+            if (j >= M + HL) { if (q >= nwrap) q -= n; }
+            v[j] = buf[q * XT + xi];
+        }
+        __syncthreads();  // everyone holds its rows in registers: the buffer may be refilled
+        const long long next = tile + gridDim.x;
+        if (next < ntiles) pipe_issue_tile<THREADS>(buf, f, next, tiles_x, XT, rows_in, n1, in_slab, vec16 != 0);
+
+        double r[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) r[i] = rhs_eval<RK>(&v[i + HL], op);
+        if constexpr (BW > 0) {
+            const int slots = P * XT;
+            chunk_solve<BW, M>(r, tab, sm_g, slots, p, [&](int q) { return q * XT + xi; });
+        }
+        const long long k = tile / tiles_x;
+        const long long x = (tile - k * tiles_x) * XT + xi;
+        if (x < n1) {
+            double* fo = out + k * out_slab + x;
+#pragma unroll
+            for (int i = 0; i < M; ++i) fo[(long long)(p * M + i) * n1] = r[i];
+            if (op.edge_out && p == 0) fo[(long long)n * n1] = r[0];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Contiguous (x) kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kXThreads = 256;
+constexpr int kXPairsPerThread = 16;  // a full tile is L*n = 8192 doubles = 16 double2 per thread
 
 template <int RK, int BW, int M>
 __global__ void __launch_bounds__(kXThreads, 2)
 chunk_x_kernel(const double* __restrict__ f, double* __restrict__ out, long long nlines, int n, int L,
                const __grid_constant__ ChunkTables tab, const __grid_constant__ OpParams op) {
     constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     const int P = n / M;
     const int pitch = n + P;  // one padding double per chunk: chunk p starts at p*(M+1)
     double* tile = sm;
     double* sm_g = sm + (size_t)L * pitch;
+    const int slots = kXThreads + P;  // threads beyond L*P own no line but still index slot(q) in chunk_solve
     const int tid = threadIdx.x;
     const long long line0 = (long long)blockIdx.x * L;
     const int nl = (int)min((long long)L, nlines - line0);  // lines present in this tile
     const double* fbase = f + line0 * n;
     double* obase = out + line0 * n;
 
-    // ---- coalesced tile load (16-byte when aligned) ----
+    // ---- coalesced tile load: all global loads of a thread are issued before the first shared store ----
     const long long tot = (long long)nl * n;
-    if ((reinterpret_cast<uintptr_t>(fbase) & 15) == 0) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(fbase) | reinterpret_cast<uintptr_t>(obase)) & 15) == 0;
+    if (vec) {
         const double2* f2 = reinterpret_cast<const double2*>(fbase);
-        int ln = 0, j0 = 2 * tid;
-        while (j0 >= n) { j0 -= n; ++ln; }
-        for (long long e = tid; 2 * e < tot; e += kXThreads) {
-            const double2 val = __ldg(f2 + e);
-            const int pos = ln * pitch + j0 + j0 / M;
-            tile[pos] = val.x;
-            tile[pos + 1] = val.y;
-            j0 += 2 * kXThreads;
-            while (j0 >= n) { j0 -= n; ++ln; }
+        for (long long e0 = 0; 2 * e0 < tot; e0 += (long long)kXThreads * kXPairsPerThread) {
+            double2 val[kXPairsPerThread];
+#pragma unroll
+            for (int u = 0; u < kXPairsPerThread; ++u) {
+                const long long e = e0 + tid + (long long)u * kXThreads;
+                if (2 * e < tot) val[u] = __ldg(f2 + e);
+            }
+            long long e = e0 + tid;
+            int ln = (int)((2 * e) / n), j0 = (int)((2 * e) - (long long)ln * n);
+#pragma unroll
+            for (int u = 0; u < kXPairsPerThread; ++u) {
+                if (2 * e < tot) {
+                    const int pos = ln * pitch + j0 + j0 / M;
+                    tile[pos] = val[u].x;
+                    tile[pos + 1] = val[u].y;
+                }
+                e += kXThreads;
+                j0 += 2 * kXThreads;
+                while (j0 >= n) { j0 -= n; ++ln; }
+            }
         }
     } else {
         int ln = 0, j0 = tid;
@@ -252,7 +356,7 @@ chunk_x_kernel(const double* __restrict__ f, double* __restrict__ out, long long
     for (int i = 0; i < M; ++i) r[i] = rhs_eval<RK>(&v[i + HL], op);
 
     if constexpr (BW > 0) {
-        chunk_solve<BW, M>(r, tab, sm_g, kXThreads, p, [&](int q) { return tid - p + q; });
+        chunk_solve<BW, M>(r, tab, sm_g, slots, p, [&](int q) { return tid - p + q; });
     } else {
         __syncthreads();  // everyone has read the tile
     }
@@ -264,7 +368,7 @@ chunk_x_kernel(const double* __restrict__ f, double* __restrict__ out, long long
     }
     __syncthreads();
     // ---- coalesced tile store ----
-    if ((reinterpret_cast<uintptr_t>(obase) & 15) == 0) {
+    if (vec) {
         double2* o2 = reinterpret_cast<double2*>(obase);
         int l2 = 0, j0 = 2 * tid;
         while (j0 >= n) { j0 -= n; ++l2; }
@@ -410,6 +514,18 @@ void banded_op_destroy(BandedOp* h) {
 
 namespace {
 
+// PDO_STRIDED_MODE = pipe | t512 | t256 selects the strided kernel variant (default: pipe where it applies)
+int strided_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = std::getenv("PDO_STRIDED_MODE");
+        mode = 0;
+        if (e && std::strcmp(e, "t512") == 0) mode = 1;
+        if (e && std::strcmp(e, "t256") == 0) mode = 2;
+    }
+    return mode;
+}
+
 template <int RK, int BW, int M>
 cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3,
                          long long in_slab, long long out_slab, cudaStream_t st) {
@@ -417,7 +533,7 @@ cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* o
     if (axis == 0) {
         static bool attr_done = false;
         const int L = kXThreads / P > 0 ? kXThreads / P : 1;
-        const size_t smem = sizeof(double) * ((size_t)L * (n + P) + 3 * (BW > 0 ? BW : 1) * kXThreads);
+        const size_t smem = sizeof(double) * ((size_t)L * (n + P) + 3 * (BW > 0 ? BW : 1) * (size_t)(kXThreads + P));
         auto kern = chunk_x_kernel<RK, BW, M>;
         if (!attr_done) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -428,16 +544,36 @@ cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* o
         const long long nlines = n3;
         const long long grid = (nlines + L - 1) / L;
         kern<<<(unsigned)grid, kXThreads, smem, st>>>(f, out, nlines, n, L, h->tab, h->op);
+        return cudaGetLastError();
+    }
+    const int mode = strided_mode();
+    const int threads = (mode == 2) ? 256 : 512;
+    int XT = 1;
+    while (XT * 2 * P <= threads) XT *= 2;
+    while (XT > 1 && XT / 2 >= n1) XT /= 2;
+    if (XT * P > threads) return cudaErrorInvalidConfiguration;
+    const int tiles_x = (int)((n1 + XT - 1) / XT);
+    const long long ntiles = (long long)tiles_x * n3;
+    const size_t smem_g = sizeof(double) * 3 * (BW > 0 ? BW : 1) * (size_t)P * XT;
+    const int rows_in = n + (h->op.edge_in ? 1 : 0);
+    const size_t smem_pipe = sizeof(double) * (((size_t)rows_in * XT + 1) & ~(size_t)1) + smem_g;
+    if (mode == 0 && smem_pipe <= 200 * 1024 && ntiles >= 148) {
+        static bool attr_done = false;
+        auto kern = chunk_strided_pipe_kernel<RK, BW, M, 512>;
+        if (!attr_done) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        const int vec16 = (XT % 2 == 0) && (n1 % 2 == 0) && (in_slab % 2 == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0);
+        const long long grid = ntiles < 148 ? ntiles : 148;
+        kern<<<(unsigned)grid, XT * P, smem_pipe, st>>>(f, out, n1, n, in_slab, out_slab, tiles_x, XT, ntiles, vec16, h->tab, h->op);
+    } else if (threads == 256) {
+        chunk_strided_kernel<RK, BW, M, 256><<<(unsigned)ntiles, XT * P, smem_g, st>>>(f, out, n1, n, in_slab, out_slab, tiles_x,
+                                                                                       XT, h->tab, h->op);
     } else {
-        int XT = 1;
-        while (XT * 2 * P <= kStridedThreads) XT *= 2;
-        while (XT > 1 && XT / 2 >= n1) XT /= 2;
-        if (XT * P > kStridedThreads) return cudaErrorInvalidConfiguration;
-        const int tiles_x = (int)((n1 + XT - 1) / XT);
-        const long long grid = (long long)tiles_x * n3;
-        const size_t smem = sizeof(double) * 3 * (BW > 0 ? BW : 1) * (size_t)P * XT;
-        chunk_strided_kernel<RK, BW, M><<<(unsigned)grid, XT * P, smem, st>>>(f, out, n1, n, in_slab, out_slab, tiles_x,
-                                                                             XT, h->tab, h->op);
+        chunk_strided_kernel<RK, BW, M, 512><<<(unsigned)ntiles, XT * P, smem_g, st>>>(f, out, n1, n, in_slab, out_slab, tiles_x,
+                                                                                       XT, h->tab, h->op);
     }
     return cudaGetLastError();
 }

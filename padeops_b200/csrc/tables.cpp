@@ -123,7 +123,8 @@ int build_chunk_tables(int n, int M, int BW, double b1d, double b2d, ChunkTables
         out->l1[i] = (double)T.l1[i];
         out->l2[i] = (double)T.l2[i];
         out->ginv[i] = (double)((ld)1 / T.g[i]);
-        out->u1[i] = (double)T.u1[i];
+        out->ug[i] = (double)(T.u1[i] / T.g[i]);
+        out->bg[i] = (double)(b2 / T.g[i]);
     }
     // Left spike: interior rows 0..BW-1 see the previous chunk's separators (sa = its local M-2, sb = M-1 for
     // penta; the single separator for tri).  Row 0: b2*sa + b1*sb ; row 1: b2*sb.   V(:,q) = T^{-1} E_L(:,q).

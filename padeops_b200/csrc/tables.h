@@ -29,8 +29,9 @@ constexpr int kMaxW = 16;      // |d| <= W neighbour chunks in the separator sol
 struct ChunkTables {
     double l1[kMaxChunk];    // forward:  y_i = r_i - l1_i y_{i-1} - l2_i y_{i-2}
     double l2[kMaxChunk];
-    double ginv[kMaxChunk];  // backward: z_i = (y_i - u1_i z_{i+1} - b2 z_{i+2}) * ginv_i
-    double u1[kMaxChunk];
+    double ginv[kMaxChunk];  // backward: z_i = y_i ginv_i - ug_i z_{i+1} - bg_i z_{i+2}   (ug = u1 ginv, bg = b2 ginv:
+    double ug[kMaxChunk];    //           the 1/g scaling is folded into the factors so the dependent chain is
+    double bg[kMaxChunk];    //           one FMA per row)
     double V[kMaxChunk][2];  // x_i -= V[i][0]*sprev[0] + V[i][1]*sprev[1]   (left spike)
     double U[kMaxChunk][2];  // x_i -= U[i][0]*sown[0]  + U[i][1]*sown[1]    (right spike)
     double G[2 * kMaxW + 1][4];  // separator inverse blocks, G[d+W] row-major BWxBW

@@ -1,0 +1,115 @@
+"""Worker for the multi-GPU tests (launched by torchrun; one rank per GPU).  Checks, per rank, bit-exact
+transposes (real + complex, even + uneven sizes) against the oracle's simulated-rank ALLTOALLV, the
+distributed CD10 derivative choreography, and the pencil-decomposed FFT / Poisson solve."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import padeops_b200 as pdo
+    from padeops_b200 import decomp as dc
+    from oracle import oracle as O
+    pdo.decomp_2d.comm_init()
+    grids = [(1, world), (world, 1)] + ([(2, world // 2)] if world >= 4 else [])
+    nfail = 0
+
+    def ok(cond, what):
+        nonlocal nfail
+        if not cond:
+            nfail += 1
+            print(f"[rank {rank}] FAIL {what}", flush=True)
+
+    for (pr, pc) in grids:
+        for (nx, ny, nz) in [(16, 12, 8), (17, 9, 11), (33, 16, 10)]:
+            if min(nx, ny) < pr or min(ny, nz) < pc:
+                continue
+            gp = pdo.decomp_info(nx, ny, nz, pr, pc)
+            for cplx in (False, True):
+                rng = np.random.default_rng(5)
+                G = rng.standard_normal((nz, ny, nx))
+                if cplx:
+                    G = G + 1j * rng.standard_normal((nz, ny, nx))
+                pens = {p: O.scatter_global(G, nx, ny, nz, pr, pc, p) for p in "xyz"}
+                for d, (s, t, fn) in enumerate((("x", "y", dc.transpose_x_to_y), ("y", "x", dc.transpose_y_to_x),
+                                                ("y", "z", dc.transpose_y_to_z), ("z", "y", dc.transpose_z_to_y))):
+                    ref = O.transpose(d, nx, ny, nz, pr, pc, pens[s])[rank]
+                    got = fn(torch.from_numpy(pens[s][rank]).cuda(), None, gp).cpu().numpy()
+                    ok(got.shape == ref.shape and np.array_equal(got, ref), f"transpose {s}->{t} grid {pr}x{pc} {nx}x{ny}x{nz} cplx={cplx}")
+                    ok(np.array_equal(ref, pens[t][rank]), "oracle self-consistency")
+    # distributed derivative choreography (tests/test_derivatives_parallel.F90:94-126) on 64^3
+    n = 64
+    d = 2 * np.pi / n
+    pr, pc = (1, world)
+    gp = pdo.decomp_info(n, n, n, pr, pc)
+    der = pdo.derivatives()
+    der.init(gp, d, d, d, True, True, True, "cd10", "cd10", "cd10")
+    x = np.arange(n) * d
+    G = np.sin(x)[None, None, :] * np.sin(x)[None, :, None] * np.cos(x)[:, None, None] + 0.1 * np.random.default_rng(1).standard_normal((n, n, n))
+    fy = torch.from_numpy(O.scatter_global(G, n, n, n, pr, pc, "y")[rank]).cuda()
+    for ax, (to, back, pen) in enumerate(((dc.transpose_y_to_x, dc.transpose_x_to_y, "x"), (None, None, "y"), (dc.transpose_y_to_z, dc.transpose_z_to_y, "z"))):
+        ref = O.scatter_global(O.cd10(G, d, ax, 1), n, n, n, pr, pc, "y")[rank]
+        if to is None:
+            got = der.ddy(fy)
+        else:
+            a = to(fy, None, gp)
+            b = (der.ddx, None, der.ddz)[ax](a)
+            got = back(b, None, gp)
+        err = np.abs(got.cpu().numpy() - ref).max() / np.abs(ref).max()
+        ok(err < 1e-12, f"distributed cd10 axis {ax}: rel err {err:.2e}")
+    # pencil-decomposed FFT and Poisson
+    for (pr, pc) in grids:
+        for (nx, ny, nz) in [(32, 16, 24), (18, 12, 10)]:
+            if min(nx // 2 + 1, ny) < pr or min(ny, nz) < pc:
+                continue
+            dx, dy, dz = 2 * np.pi / nx, 2 * np.pi / ny, 2 * np.pi / nz
+            rng = np.random.default_rng(9)
+            G = rng.standard_normal((nz, ny, nx))
+            ft = pdo.fft_3d()
+            rc = ft.init(nx, ny, nz, "x", dx, dy, dz, p_row=pr, p_col=pc)
+            ok(rc == 0, "fft init")
+            fx = torch.from_numpy(O.scatter_global(G, nx, ny, nz, pr, pc, "x")[rank]).cuda()
+            H = np.fft.fft(np.fft.fft(np.fft.rfft(G, axis=2), axis=1), axis=0)
+            refz = O.scatter_global(H, nx // 2 + 1, ny, nz, pr, pc, "z")[rank]
+            got = ft.fft3_x2z(fx)
+            ok(np.abs(got.cpu().numpy() - refz).max() < 1e-12 * np.abs(H).max(), f"fft3_x2z grid {pr}x{pc} {nx}x{ny}x{nz}")
+            back = ft.ifft3_z2x(got)
+            ok(np.abs(back.cpu().numpy() - fx.cpu().numpy()).max() < 1e-12 * np.abs(G).max(), f"ifft3_z2x grid {pr}x{pc}")
+            H2 = np.fft.fft(np.fft.rfft(G, axis=2), axis=1)
+            refy = O.scatter_global(H2, nx // 2 + 1, ny, nz, pr, pc, "y")[rank]
+            got2 = ft.fft2_x2y(fx)
+            ok(np.abs(got2.cpu().numpy() - refy).max() < 1e-12 * np.abs(H2).max(), f"fft2_x2y grid {pr}x{pc}")
+            ok(np.abs(ft.ifft2_y2x(got2).cpu().numpy() - fx.cpu().numpy()).max() < 1e-12 * np.abs(G).max(), f"ifft2_y2x grid {pr}x{pc}")
+            ref = O.poisson_solve(G, dx, dy, dz)
+            for dir_id, pen in ((1, "x"), (2, "y")):
+                po = pdo.PoissonPeriodic()
+                po.init(dx, dy, dz, (nx, ny, nz), dir_id, p_row=pr, p_col=pc)
+                rin = torch.from_numpy(O.scatter_global(G, nx, ny, nz, pr, pc, pen)[rank]).cuda()
+                out = torch.empty_like(rin)
+                po.poisson_solve(rin, out)
+                rr = O.scatter_global(ref, nx, ny, nz, pr, pc, pen)[rank]
+                ok(np.abs(out.cpu().numpy() - rr).max() < 1e-12 * np.abs(ref).max(), f"poisson dir {dir_id} grid {pr}x{pc} {nx}x{ny}x{nz}")
+    # reductions (utilities/reductions.F90)
+    ok(pdo.decomp_2d.p_maxval(float(rank)) == float(world - 1), "p_maxval")
+    ok(pdo.decomp_2d.p_sum(1.0) == float(world), "p_sum")
+    t = torch.tensor([nfail], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print("MP_WORKER_RESULT", "PASS" if t.item() == 0 else f"FAIL({t.item()})", flush=True)
+    dist.barrier()
+    pdo.decomp_2d.finalize()
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,64 @@
+"""CPU, world_size 2 over gloo: the host-side rendezvous logic of the N>1 path (NCCL-id broadcast, per-rank
+decomposition arithmetic tiling the global domain, bench.py's reference arm under torchrun)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+import padeops_b200 as pdo
+from padeops_b200 import _lib
+# 1) per-rank pencils from the product's decomposition arithmetic must tile the global box exactly once
+nx, ny, nz, pr, pc = 17, 10, 9, 1, world
+info = pdo.decomp_info.for_rank(nx, ny, nz, pr, pc, rank)
+infos = [None] * world
+dist.all_gather_object(infos, info)
+for pen in "xyz":
+    cover = np.zeros((nz, ny, nx), dtype=int)
+    for d in infos:
+        st, en = d[pen + "st"], d[pen + "en"]
+        cover[st[2]-1:en[2], st[1]-1:en[1], st[0]-1:en[0]] += 1
+    assert (cover == 1).all(), pen
+# 2) the NCCL-id broadcast reaches pdo_comm_init on every rank; without a GPU it must refuse (no CPU fallback)
+try:
+    pdo.decomp_2d.comm_init()
+    outcome = "inited"
+except pdo.PadeOpsError as e:
+    outcome = "err%%d" %% e.code
+outs = [None] * world
+dist.all_gather_object(outs, outcome)
+if rank == 0:
+    print("GLOO_WORKER", outs, flush=True)
+dist.barrier()
+dist.destroy_process_group()
+''' % ROOT
+
+
+def test_world2_gloo_host_logic(tmp_path):
+    w = tmp_path / "worker.py"
+    w.write_text(WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(w)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    import torch
+    want = "inited" if torch.cuda.is_available() else "err1004"
+    assert f"GLOO_WORKER ['{want}', '{want}']" in r.stdout, r.stdout[-2000:]
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"]
+    env = dict(os.environ, PDO_BENCH_CPU_N="128")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and lines[0]["impl"] == "reference" and lines[0]["cpu_baseline"]["kind"] == "port"
+    assert lines[0]["value"] > 0 and lines[0]["e2e"]["h2d_bytes_per_step"] == 0
