@@ -52,3 +52,15 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in txt.replace("no oracle", ""), f"{fn} mentions the oracle"
+
+
+def test_fortran_shims_bind_declared_symbols(pdo):
+    """Every bind(C, name=...) / macro-instantiated name in fortran/*.F90 must be an exported, declared symbol."""
+    declared = set(_declared_symbols())
+    names = set()
+    for fn in os.listdir(os.path.join(ROOT, "fortran")):
+        txt = open(os.path.join(ROOT, "fortran", fn)).read()
+        names |= set(re.findall(r'name="(pdo_[A-Za-z0-9_]+)"', txt))
+        names |= set(re.findall(r"PDO_[A-Z]+_FN\((pdo_[A-Za-z0-9_]+)\)", txt))
+    assert len(names) >= 50
+    assert names <= declared, names - declared
