@@ -168,12 +168,23 @@ chunk_strided_kernel(const double* __restrict__ f, double* __restrict__ out, lon
 
     double v[M + HL + HR];
     const int nwrap = op.edge_in ? n + 1 : n;  // first logical position that wraps back by n
+    {
+        // running pointers: one 64-bit add per row instead of a 64-bit multiply
+        const double* pr = fin + (long long)(p * M) * n1;
 #pragma unroll
-    for (int j = 0; j < M + HL + HR; ++j) {
-        int q = p * M - HL + j;
-        if (j < HL) { if (q < 0) q += n; }
-        if (j >= M + HL) { if (q >= nwrap) q -= n; }
-        v[j] = __ldg(fin + (long long)q * n1);
+        for (int j = 0; j < M; ++j) { v[HL + j] = __ldg(pr); pr += n1; }
+#pragma unroll
+        for (int j = 0; j < HL; ++j) {
+            int q = p * M - HL + j;
+            if (q < 0) q += n;
+            v[j] = __ldg(fin + (long long)q * n1);
+        }
+#pragma unroll
+        for (int j = 0; j < HR; ++j) {
+            int q = (p + 1) * M + j;
+            if (q >= nwrap) q -= n;
+            v[HL + M + j] = __ldg(fin + (long long)q * n1);
+        }
     }
     double r[M];
 #pragma unroll
@@ -184,8 +195,9 @@ chunk_strided_kernel(const double* __restrict__ f, double* __restrict__ out, lon
         chunk_solve<BW, M>(r, tab, sm_g, slots, p, [&](int q) { return q * XT + xi; });
     }
     if (active) {
+        double* po = fo + (long long)(p * M) * n1;
 #pragma unroll
-        for (int i = 0; i < M; ++i) fo[(long long)(p * M + i) * n1] = r[i];
+        for (int i = 0; i < M; ++i) { *po = r[i]; po += n1; }
         if (op.edge_out && p == 0) fo[(long long)n * n1] = r[0];
     }
 }
@@ -202,25 +214,36 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // Stream tile `tile` (rows_in rows of XT doubles starting at column x0 of slab k) into smem `buf[row][XT]`.
-template <int THREADS>
+// XT is a power of two and blockDim.x = XT*P, so a thread keeps ONE column and walks rows with pointer increments.
 __device__ __forceinline__ void pipe_issue_tile(double* buf, const double* __restrict__ f, long long tile, int tiles_x,
-                                                int XT, int rows_in, long long n1, long long in_slab, bool vec16) {
+                                                int XT, int xt_shift, int rows_in, long long n1, long long in_slab,
+                                                bool vec16) {
     const long long k = tile / tiles_x;
     const long long x0 = (tile - k * tiles_x) * XT;
     const double* base = f + k * in_slab + x0;
     const int tid = threadIdx.x;
     if (vec16) {
-        const int upr = XT >> 1;  // 16-byte units per row
-        const int units = rows_in * upr;
-        for (int u = tid; u < units; u += blockDim.x) {
-            const int row = u / upr, c = (u - row * upr) * 2;
-            if (x0 + c < n1) cp_async16(buf + row * XT + c, base + (long long)row * n1 + c);
+        const int sh = xt_shift - 1;                 // log2(16-byte units per row)
+        const int c = (tid & ((1 << sh) - 1)) * 2;
+        int row = tid >> sh;
+        const int rstep = blockDim.x >> sh;
+        if (x0 + c < n1) {
+            const double* src = base + (long long)row * n1 + c;
+            double* dst = buf + row * XT + c;
+            const long long sstep = (long long)rstep * n1;
+            const int dstep = rstep * XT;
+            for (; row < rows_in; row += rstep) { cp_async16(dst, src); src += sstep; dst += dstep; }
         }
     } else {
-        const int units = rows_in * XT;
-        for (int u = tid; u < units; u += blockDim.x) {
-            const int row = u / XT, c = u - row * XT;
-            if (x0 + c < n1) cp_async8(buf + row * XT + c, base + (long long)row * n1 + c);
+        const int c = tid & (XT - 1);
+        int row = tid >> xt_shift;
+        const int rstep = blockDim.x >> xt_shift;
+        if (x0 + c < n1) {
+            const double* src = base + (long long)row * n1 + c;
+            double* dst = buf + row * XT + c;
+            const long long sstep = (long long)rstep * n1;
+            const int dstep = rstep * XT;
+            for (; row < rows_in; row += rstep) { cp_async8(dst, src); src += sstep; dst += dstep; }
         }
     }
     cp_async_commit();
@@ -238,25 +261,36 @@ chunk_strided_pipe_kernel(const double* __restrict__ f, double* __restrict__ out
     double* buf = sm;                                   // [rows_in][XT]
     double* sm_g = sm + (((size_t)rows_in * XT + 1) & ~(size_t)1);
     const int tid = threadIdx.x;
-    const int xi = tid % XT, p = tid / XT;
+    const int xt_shift = __ffs(XT) - 1;
+    const int xi = tid & (XT - 1), p = tid >> xt_shift;
     const int nwrap = rows_in;
 
     long long tile = blockIdx.x;
-    if (tile < ntiles) pipe_issue_tile<THREADS>(buf, f, tile, tiles_x, XT, rows_in, n1, in_slab, vec16 != 0);
+    if (tile < ntiles) pipe_issue_tile(buf, f, tile, tiles_x, XT, xt_shift, rows_in, n1, in_slab, vec16 != 0);
     for (; tile < ntiles; tile += gridDim.x) {
         cp_async_wait_all();
         __syncthreads();
         double v[M + HL + HR];
+        {
+            const double* b = buf + (p * M) * XT + xi;
 #pragma unroll
-        for (int j = 0; j < M + HL + HR; ++j) {
-            int q = p * M - HL + j;
-            if (j < HL) { if (q < 0) q += n; }
-            if (j >= M + HL) { if (q >= nwrap) q -= n; }
-            v[j] = buf[q * XT + xi];
+            for (int j = 0; j < M; ++j) { v[HL + j] = *b; b += XT; }
+#pragma unroll
+            for (int j = 0; j < HL; ++j) {
+                int q = p * M - HL + j;
+                if (q < 0) q += n;
+                v[j] = buf[q * XT + xi];
+            }
+#pragma unroll
+            for (int j = 0; j < HR; ++j) {
+                int q = (p + 1) * M + j;
+                if (q >= nwrap) q -= n;
+                v[HL + M + j] = buf[q * XT + xi];
+            }
         }
         __syncthreads();  // everyone holds its rows in registers: the buffer may be refilled
         const long long next = tile + gridDim.x;
-        if (next < ntiles) pipe_issue_tile<THREADS>(buf, f, next, tiles_x, XT, rows_in, n1, in_slab, vec16 != 0);
+        if (next < ntiles) pipe_issue_tile(buf, f, next, tiles_x, XT, xt_shift, rows_in, n1, in_slab, vec16 != 0);
 
         double r[M];
 #pragma unroll
@@ -269,8 +303,9 @@ chunk_strided_pipe_kernel(const double* __restrict__ f, double* __restrict__ out
         const long long x = (tile - k * tiles_x) * XT + xi;
         if (x < n1) {
             double* fo = out + k * out_slab + x;
+            double* po = fo + (long long)(p * M) * n1;
 #pragma unroll
-            for (int i = 0; i < M; ++i) fo[(long long)(p * M + i) * n1] = r[i];
+            for (int i = 0; i < M; ++i) { *po = r[i]; po += n1; }
             if (op.edge_out && p == 0) fo[(long long)n * n1] = r[0];
         }
     }
