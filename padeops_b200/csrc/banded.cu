@@ -69,9 +69,9 @@ __device__ __forceinline__ double rhs_eval(const double* w, const OpParams& op) 
 // The sweeps are written so that the loop-carried dependency is ONE fma per row: the term that does not
 // depend on the previous row is folded in first, and 1/g is pre-multiplied into the factors.
 // ------------------------------------------------------------------------------------------------
-template <int BW, int M, class SlotFn>
-__device__ __forceinline__ void chunk_solve(double (&r)[M], const ChunkTables& t, double* __restrict__ sm_g,
-                                            int slots, int p, SlotFn slot) {
+// step 1: interior sweeps (register-only).  Leaves z in r[0..mi) and returns the reduced-RHS pieces.
+template <int BW, int M>
+__device__ __forceinline__ void chunk_interior(double (&r)[M], const ChunkTables& t, double (&gA)[2], double (&gB)[2]) {
     constexpr int mi = M - BW;
     // forward elimination on the interior block: y_i = (r_i - l2_i y_{i-2}) - l1_i y_{i-1}
     r[1] = __fma_rn(-t.l1[1], r[0], r[1]);
@@ -93,19 +93,45 @@ __device__ __forceinline__ void chunk_solve(double (&r)[M], const ChunkTables& t
     }
     // reduced right-hand side pieces: gA from my chunk's tail rows, gB = what my head rows contribute to the
     // separator rows of the PREVIOUS chunk.
+    if (BW == 2) {
+        gA[0] = r[M - 2] - t.b2 * r[mi - 2] - t.b1 * r[mi - 1];
+        gA[1] = r[M - 1] - t.b2 * r[mi - 1];
+        gB[0] = -t.b2 * r[0];
+        gB[1] = -t.b1 * r[0] - t.b2 * r[1];
+    } else {
+        gA[0] = r[M - 1] - t.b1 * r[mi - 1];
+        gB[0] = -t.b1 * r[0];
+        gA[1] = gB[1] = 0.0;
+    }
+}
+
+// step 3: spikes.  s = own separator values, sp = previous chunk's.
+template <int BW, int M>
+__device__ __forceinline__ void chunk_finish(double (&r)[M], const ChunkTables& t, double s0, double s1, double sp0,
+                                             double sp1) {
+    constexpr int mi = M - BW;
+#pragma unroll
+    for (int i = 0; i < mi; ++i) {
+        if (BW == 2) r[i] = r[i] - t.V[i][0] * sp0 - t.V[i][1] * sp1 - t.U[i][0] * s0 - t.U[i][1] * s1;
+        else r[i] = r[i] - t.V[i][0] * sp0 - t.U[i][0] * s0;
+    }
+    r[mi] = s0;
+    if (BW == 2) r[mi + 1] = s1;
+}
+
+// steps 1-3 with the separator exchange (step 2) through this CTA's shared memory.
+template <int BW, int M, class SlotFn>
+__device__ __forceinline__ void chunk_solve(double (&r)[M], const ChunkTables& t, double* __restrict__ sm_g,
+                                            int slots, int p, SlotFn slot) {
+    double a_[2], b_[2];
+    chunk_interior<BW, M>(r, t, a_, b_);
     double* gA = sm_g;
     double* gB = sm_g + BW * slots;
     double* sS = sm_g + 2 * BW * slots;
     const int me = slot(p);
-    if (BW == 2) {
-        gA[me] = r[M - 2] - t.b2 * r[mi - 2] - t.b1 * r[mi - 1];
-        gA[slots + me] = r[M - 1] - t.b2 * r[mi - 1];
-        gB[me] = -t.b2 * r[0];
-        gB[slots + me] = -t.b1 * r[0] - t.b2 * r[1];
-    } else {
-        gA[me] = r[M - 1] - t.b1 * r[mi - 1];
-        gB[me] = -t.b1 * r[0];
-    }
+    gA[me] = a_[0];
+    gB[me] = b_[0];
+    if (BW == 2) { gA[slots + me] = a_[1]; gB[slots + me] = b_[1]; }
     __syncthreads();
     // separator solve: s_p = sum_d G[d] (gA_{p+d} + gB_{p+d+1})
     const int P = t.P, W = t.W;
@@ -133,14 +159,7 @@ __device__ __forceinline__ void chunk_solve(double (&r)[M], const ChunkTables& t
     const int pm = slot(p == 0 ? P - 1 : p - 1);
     const double sp0 = sS[pm];
     const double sp1 = (BW == 2) ? sS[slots + pm] : 0.0;
-    // spikes
-#pragma unroll
-    for (int i = 0; i < mi; ++i) {
-        if (BW == 2) r[i] = r[i] - t.V[i][0] * sp0 - t.V[i][1] * sp1 - t.U[i][0] * s0 - t.U[i][1] * s1;
-        else r[i] = r[i] - t.V[i][0] * sp0 - t.U[i][0] * s0;
-    }
-    r[mi] = s0;
-    if (BW == 2) r[mi + 1] = s1;
+    chunk_finish<BW, M>(r, t, s0, s1, sp0, sp1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -308,6 +327,129 @@ chunk_strided_pipe_kernel(const double* __restrict__ f, double* __restrict__ out
             for (int i = 0; i < M; ++i) { *po = r[i]; po += n1; }
             if (op.edge_out && p == 0) fo[(long long)n * n1] = r[0];
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cluster variant of the strided kernel: a line is split over the C CTAs of a thread-block cluster.
+// CTA = 256 threads = PC (8) chunks x 32 columns, so every warp moves whole 256-byte row segments and two
+// CTAs fit on an SM (their load / solve / store phases overlap).  The only coupling between the chunks of a
+// line is the separator exchange, which goes through distributed shared memory (each CTA publishes its
+// gA/gB/s, neighbours read them with mapa'd pointers) between cluster barriers.
+// ------------------------------------------------------------------------------------------------
+constexpr int kClThreads = 256;  // = PC chunks x XT columns; PC in {8, 4} -> XT in {32, 64}
+
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// generic address of `smem_ptr` in CTA `rank` of this cluster
+__device__ __forceinline__ const double* cluster_map(const double* smem_ptr, unsigned rank) {
+    unsigned long long in = (unsigned long long)smem_ptr, out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(in), "r"(rank));
+    return (const double*)out;
+}
+
+template <int RK, int BW, int M, int PC>
+__global__ void __launch_bounds__(kClThreads, 2)
+chunk_strided_cluster_kernel(const double* __restrict__ f, double* __restrict__ out, long long n1, int n, long long in_slab,
+                             long long out_slab, int tiles_x, int C, const __grid_constant__ ChunkTables tab,
+                             const __grid_constant__ OpParams op) {
+    constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
+    constexpr int XT = kClThreads / PC, SL = PC * XT;  // SL slots per array
+    constexpr int PSH = (PC == 8) ? 3 : 2, XSH = (PC == 8) ? 5 : 6;
+    __shared__ __align__(16) double sm_g[3 * (BW > 0 ? BW : 1) * SL];
+    const int tid = threadIdx.x;
+    const int xi = tid & (XT - 1), pl = tid >> XSH;
+    const unsigned rank = (C > 1) ? cluster_ctarank() : 0u;
+    const int p = (int)rank * PC + pl;
+    const int P = n / M;
+    const long long cl = blockIdx.x / C;
+    const long long k = cl / tiles_x;
+    const long long x = (cl - k * tiles_x) * XT + xi;
+    const bool active = x < n1;
+    const double* fin = f + k * in_slab + (active ? x : 0);
+    double* fo = out + k * out_slab + (active ? x : 0);
+
+    double v[M + HL + HR];
+    const int nwrap = op.edge_in ? n + 1 : n;
+    {
+        const double* pr = fin + (long long)(p * M) * n1;
+#pragma unroll
+        for (int j = 0; j < M; ++j) { v[HL + j] = __ldg(pr); pr += n1; }
+#pragma unroll
+        for (int j = 0; j < HL; ++j) {
+            int q = p * M - HL + j;
+            if (q < 0) q += n;
+            v[j] = __ldg(fin + (long long)q * n1);
+        }
+#pragma unroll
+        for (int j = 0; j < HR; ++j) {
+            int q = (p + 1) * M + j;
+            if (q >= nwrap) q -= n;
+            v[HL + M + j] = __ldg(fin + (long long)q * n1);
+        }
+    }
+    double r[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) r[i] = rhs_eval<RK>(&v[i + HL], op);
+
+    if constexpr (BW > 0) {
+        double a_[2], b_[2];
+        chunk_interior<BW, M>(r, tab, a_, b_);
+        double* gA = sm_g;
+        double* gB = sm_g + BW * SL;
+        double* sS = sm_g + 2 * BW * SL;
+        const int me = pl * XT + xi;
+        gA[me] = a_[0];
+        gB[me] = b_[0];
+        if (BW == 2) { gA[SL + me] = a_[1]; gB[SL + me] = b_[1]; }
+        if (C > 1) cluster_sync_all(); else __syncthreads();
+        const int W = tab.W;
+        double s0 = 0.0, s1 = 0.0;
+        int q = p - W;
+        q %= P;
+        if (q < 0) q += P;
+        for (int d = 0; d <= 2 * W; ++d) {
+            int q1 = q + 1;
+            if (q1 == P) q1 = 0;
+            const unsigned ra = (unsigned)(q >> PSH), rb = (unsigned)(q1 >> PSH);
+            const int ia = (q & (PC - 1)) * XT + xi, ib = (q1 & (PC - 1)) * XT + xi;
+            const double* A = (C > 1 && ra != rank) ? cluster_map(gA, ra) : gA;
+            const double* B = (C > 1 && rb != rank) ? cluster_map(gB, rb) : gB;
+            if (BW == 2) {
+                const double h0 = A[ia] + B[ib];
+                const double h1 = A[SL + ia] + B[SL + ib];
+                s0 += tab.G[d][0] * h0 + tab.G[d][1] * h1;
+                s1 += tab.G[d][2] * h0 + tab.G[d][3] * h1;
+            } else {
+                s0 += tab.G[d][0] * (A[ia] + B[ib]);
+            }
+            q = q1;
+        }
+        sS[me] = s0;
+        if (BW == 2) sS[SL + me] = s1;
+        if (C > 1) cluster_sync_all(); else __syncthreads();
+        const int qm = (p == 0 ? P - 1 : p - 1);
+        const unsigned rm = (unsigned)(qm >> PSH);
+        const int im = (qm & (PC - 1)) * XT + xi;
+        const double* S = (C > 1 && rm != rank) ? cluster_map(sS, rm) : sS;
+        const double sp0 = S[im];
+        const double sp1 = (BW == 2) ? S[SL + im] : 0.0;
+        chunk_finish<BW, M>(r, tab, s0, s1, sp0, sp1);
+        if (C > 1) {  // nobody may leave (and free its shared memory) while a neighbour can still read it
+            asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        }
+    }
+    if (active) {
+        double* po = fo + (long long)(p * M) * n1;
+#pragma unroll
+        for (int i = 0; i < M; ++i) { *po = r[i]; po += n1; }
+        if (op.edge_out && p == 0) fo[(long long)n * n1] = r[0];
+    }
+    if constexpr (BW > 0) {
+        if (C > 1) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     }
 }
 
@@ -557,6 +699,8 @@ int strided_mode() {
         mode = 0;
         if (e && std::strcmp(e, "t512") == 0) mode = 1;
         if (e && std::strcmp(e, "t256") == 0) mode = 2;
+        if (e && std::strcmp(e, "cluster") == 0) mode = 3;
+        if (e && std::strcmp(e, "cluster4") == 0) mode = 4;
     }
     return mode;
 }
@@ -582,6 +726,32 @@ cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* o
         return cudaGetLastError();
     }
     const int mode = strided_mode();
+    if constexpr (M == 32) {
+        // cluster kernel: P chunks split over C = P/PC CTAs (portable cluster sizes only); mode 3: PC=8, mode 4: PC=4
+        const int PC = (mode == 4) ? 4 : 8;
+        const int C = P / PC, XTc = kClThreads / PC;
+        if ((mode == 3 || mode == 4) && P % PC == 0 && (C == 1 || C == 2 || C == 4 || C == 8) && n1 >= XTc / 2) {
+            const int tiles_x = (int)((n1 + XTc - 1) / XTc);
+            const long long nblocks = (long long)tiles_x * n3 * C;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)nblocks);
+            cfg.blockDim = dim3(kClThreads);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)C;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            if (PC == 8)
+                return cudaLaunchKernelEx(&cfg, chunk_strided_cluster_kernel<RK, BW, M, 8>, f, out, n1, n, in_slab, out_slab, tiles_x,
+                                          C, h->tab, h->op);
+            return cudaLaunchKernelEx(&cfg, chunk_strided_cluster_kernel<RK, BW, M, 4>, f, out, n1, n, in_slab, out_slab, tiles_x, C,
+                                      h->tab, h->op);
+        }
+    }
     const int threads = (mode == 2) ? 256 : 512;
     int XT = 1;
     while (XT * 2 * P <= threads) XT *= 2;
