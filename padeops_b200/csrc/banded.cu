@@ -351,19 +351,28 @@ __device__ __forceinline__ const double* cluster_map(const double* smem_ptr, uns
     return (const double*)out;
 }
 
+constexpr int kClMaxHW = 8;  // halo chunks gathered from each neighbour CTA (needs W + 1 <= 8)
+
 template <int RK, int BW, int M, int PC>
 __global__ void __launch_bounds__(kClThreads, 2)
 chunk_strided_cluster_kernel(const double* __restrict__ f, double* __restrict__ out, long long n1, int n, long long in_slab,
                              long long out_slab, int tiles_x, int C, const __grid_constant__ ChunkTables tab,
                              const __grid_constant__ OpParams op) {
     constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
-    constexpr int XT = kClThreads / PC, SL = PC * XT;  // SL slots per array
+    constexpr int XT = kClThreads / PC;
     constexpr int PSH = (PC == 8) ? 3 : 2, XSH = (PC == 8) ? 5 : 6;
-    __shared__ __align__(16) double sm_g[3 * (BW > 0 ? BW : 1) * SL];
+    constexpr int BWc = (BW > 0 ? BW : 1);
+    constexpr int EC = PC + 2 * kClMaxHW;  // extended chunk slots: [halo left | own PC chunks | halo right]
+    constexpr int ESL = EC * XT;
+    // eA/eB[comp][extended chunk][column]; sS[comp][own chunk][column]
+    __shared__ __align__(16) double eA[BWc * ESL];
+    __shared__ __align__(16) double eB[BWc * ESL];
+    __shared__ __align__(16) double sS[BWc * PC * XT];
     const int tid = threadIdx.x;
     const int xi = tid & (XT - 1), pl = tid >> XSH;
     const unsigned rank = (C > 1) ? cluster_ctarank() : 0u;
-    const int p = (int)rank * PC + pl;
+    const int p0 = (int)rank * PC;
+    const int p = p0 + pl;
     const int P = n / M;
     const long long cl = blockIdx.x / C;
     const long long k = cl / tiles_x;
@@ -398,49 +407,71 @@ chunk_strided_cluster_kernel(const double* __restrict__ f, double* __restrict__ 
     if constexpr (BW > 0) {
         double a_[2], b_[2];
         chunk_interior<BW, M>(r, tab, a_, b_);
-        double* gA = sm_g;
-        double* gB = sm_g + BW * SL;
-        double* sS = sm_g + 2 * BW * SL;
-        const int me = pl * XT + xi;
-        gA[me] = a_[0];
-        gB[me] = b_[0];
-        if (BW == 2) { gA[SL + me] = a_[1]; gB[SL + me] = b_[1]; }
+        const int W = tab.W, HW = W + 1;
+        // publish into the middle region of the extended arrays (this is what neighbours read)
+        const int me = (kClMaxHW + pl) * XT + xi;
+        eA[me] = a_[0];
+        eB[me] = b_[0];
+        if (BW == 2) { eA[ESL + me] = a_[1]; eB[ESL + me] = b_[1]; }
         if (C > 1) cluster_sync_all(); else __syncthreads();
-        const int W = tab.W;
-        double s0 = 0.0, s1 = 0.0;
-        int q = p - W;
-        q %= P;
-        if (q < 0) q += P;
-        for (int d = 0; d <= 2 * W; ++d) {
-            int q1 = q + 1;
-            if (q1 == P) q1 = 0;
-            const unsigned ra = (unsigned)(q >> PSH), rb = (unsigned)(q1 >> PSH);
-            const int ia = (q & (PC - 1)) * XT + xi, ib = (q1 & (PC - 1)) * XT + xi;
-            const double* A = (C > 1 && ra != rank) ? cluster_map(gA, ra) : gA;
-            const double* B = (C > 1 && rb != rank) ? cluster_map(gB, rb) : gB;
-            if (BW == 2) {
-                const double h0 = A[ia] + B[ib];
-                const double h1 = A[SL + ia] + B[SL + ib];
-                s0 += tab.G[d][0] * h0 + tab.G[d][1] * h1;
-                s1 += tab.G[d][2] * h0 + tab.G[d][3] * h1;
-            } else {
-                s0 += tab.G[d][0] * (A[ia] + B[ib]);
+        // gather the HW halo chunks on each side from whoever owns them (DSMEM; all loads independent)
+        for (int idx = tid; idx < 2 * HW * XT; idx += kClThreads) {
+            const int hc = idx >> XSH, xc = idx & (XT - 1);
+            const int e = (hc < HW) ? (kClMaxHW - HW + hc) : (kClMaxHW + PC + (hc - HW));  // my extended slot
+            int q = p0 + (e - kClMaxHW);                                                  // global chunk
+            q %= P;
+            if (q < 0) q += P;
+            const unsigned rq = (unsigned)(q >> PSH);
+            const int src = (kClMaxHW + (q & (PC - 1))) * XT + xc;
+            const double* A = (C > 1 && rq != rank) ? cluster_map(eA, rq) : eA;
+            const double* B = (C > 1 && rq != rank) ? cluster_map(eB, rq) : eB;
+            const double a0 = A[src], b0 = B[src];
+            double a1 = 0.0, b1 = 0.0;
+            if (BW == 2) { a1 = A[ESL + src]; b1 = B[ESL + src]; }
+            eA[e * XT + xc] = a0;
+            eB[e * XT + xc] = b0;
+            if (BW == 2) { eA[ESL + e * XT + xc] = a1; eB[ESL + e * XT + xc] = b1; }
+        }
+        // my remote reads are done once this arrive executes; nobody leaves before everyone has arrived (wait below)
+        if (C > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        __syncthreads();
+        // separator solve from local shared memory: s_p = sum_d G[d] (gA_{p+d} + gB_{p+d+1})
+        double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+        {
+            int e = (kClMaxHW + pl - W) * XT + xi;
+            for (int d = 0; d <= 2 * W; ++d) {
+                if (BW == 2) {
+                    const double h0 = eA[e] + eB[e + XT];
+                    const double h1 = eA[ESL + e] + eB[ESL + e + XT];
+                    s0 += tab.G[d][0] * h0 + tab.G[d][1] * h1;
+                    s1 += tab.G[d][2] * h0 + tab.G[d][3] * h1;
+                } else {
+                    s0 += tab.G[d][0] * (eA[e] + eB[e + XT]);
+                }
+                e += XT;
             }
-            q = q1;
         }
-        sS[me] = s0;
-        if (BW == 2) sS[SL + me] = s1;
-        if (C > 1) cluster_sync_all(); else __syncthreads();
-        const int qm = (p == 0 ? P - 1 : p - 1);
-        const unsigned rm = (unsigned)(qm >> PSH);
-        const int im = (qm & (PC - 1)) * XT + xi;
-        const double* S = (C > 1 && rm != rank) ? cluster_map(sS, rm) : sS;
-        const double sp0 = S[im];
-        const double sp1 = (BW == 2) ? S[SL + im] : 0.0;
+        double sp0, sp1 = 0.0;
+        if (pl == 0) {  // previous chunk lives in another CTA: recompute its separator values from the halo
+            int e = (kClMaxHW - 1 - W) * XT + xi;
+            for (int d = 0; d <= 2 * W; ++d) {
+                if (BW == 2) {
+                    const double h0 = eA[e] + eB[e + XT];
+                    const double h1 = eA[ESL + e] + eB[ESL + e + XT];
+                    t0 += tab.G[d][0] * h0 + tab.G[d][1] * h1;
+                    t1 += tab.G[d][2] * h0 + tab.G[d][3] * h1;
+                } else {
+                    t0 += tab.G[d][0] * (eA[e] + eB[e + XT]);
+                }
+                e += XT;
+            }
+        }
+        sS[pl * XT + xi] = s0;
+        if (BW == 2) sS[PC * XT + pl * XT + xi] = s1;
+        __syncthreads();
+        if (pl == 0) { sp0 = t0; sp1 = t1; }
+        else { sp0 = sS[(pl - 1) * XT + xi]; if (BW == 2) sp1 = sS[PC * XT + (pl - 1) * XT + xi]; }
         chunk_finish<BW, M>(r, tab, s0, s1, sp0, sp1);
-        if (C > 1) {  // nobody may leave (and free its shared memory) while a neighbour can still read it
-            asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-        }
     }
     if (active) {
         double* po = fo + (long long)(p * M) * n1;
@@ -476,40 +507,33 @@ chunk_x_kernel(const double* __restrict__ f, double* __restrict__ out, long long
     const double* fbase = f + line0 * n;
     double* obase = out + line0 * n;
 
-    // ---- coalesced tile load: all global loads of a thread are issued before the first shared store ----
+    // ---- coalesced tile load: all global loads of a thread are issued before the first shared store.
+    // The padded layout puts one pad after every M doubles and lines are multiples of M long, so the shared
+    // position of flat tile element g is simply g + g/M — no line bookkeeping.
     const long long tot = (long long)nl * n;
     const bool vec = ((reinterpret_cast<uintptr_t>(fbase) | reinterpret_cast<uintptr_t>(obase)) & 15) == 0;
+    constexpr int MSH = (M == 32) ? 5 : (M == 16) ? 4 : 3;
     if (vec) {
         const double2* f2 = reinterpret_cast<const double2*>(fbase);
-        for (long long e0 = 0; 2 * e0 < tot; e0 += (long long)kXThreads * kXPairsPerThread) {
+        for (int g0 = 0; g0 < tot; g0 += 2 * kXThreads * kXPairsPerThread) {
             double2 val[kXPairsPerThread];
 #pragma unroll
             for (int u = 0; u < kXPairsPerThread; ++u) {
-                const long long e = e0 + tid + (long long)u * kXThreads;
-                if (2 * e < tot) val[u] = __ldg(f2 + e);
+                const int g = g0 + 2 * (tid + u * kXThreads);
+                if (g < tot) val[u] = __ldg(f2 + (g >> 1));
             }
-            long long e = e0 + tid;
-            int ln = (int)((2 * e) / n), j0 = (int)((2 * e) - (long long)ln * n);
 #pragma unroll
             for (int u = 0; u < kXPairsPerThread; ++u) {
-                if (2 * e < tot) {
-                    const int pos = ln * pitch + j0 + j0 / M;
+                const int g = g0 + 2 * (tid + u * kXThreads);
+                if (g < tot) {
+                    const int pos = g + (g >> MSH);
                     tile[pos] = val[u].x;
                     tile[pos + 1] = val[u].y;
                 }
-                e += kXThreads;
-                j0 += 2 * kXThreads;
-                while (j0 >= n) { j0 -= n; ++ln; }
             }
         }
     } else {
-        int ln = 0, j0 = tid;
-        while (j0 >= n) { j0 -= n; ++ln; }
-        for (long long e = tid; e < tot; e += kXThreads) {
-            tile[ln * pitch + j0 + j0 / M] = __ldg(fbase + e);
-            j0 += kXThreads;
-            while (j0 >= n) { j0 -= n; ++ln; }
-        }
+        for (int g = tid; g < tot; g += kXThreads) tile[g + (g >> MSH)] = __ldg(fbase + g);
     }
     __syncthreads();
 
@@ -547,22 +571,12 @@ chunk_x_kernel(const double* __restrict__ f, double* __restrict__ out, long long
     // ---- coalesced tile store ----
     if (vec) {
         double2* o2 = reinterpret_cast<double2*>(obase);
-        int l2 = 0, j0 = 2 * tid;
-        while (j0 >= n) { j0 -= n; ++l2; }
-        for (long long e = tid; 2 * e < tot; e += kXThreads) {
-            const int pos = l2 * pitch + j0 + j0 / M;
-            o2[e] = make_double2(tile[pos], tile[pos + 1]);
-            j0 += 2 * kXThreads;
-            while (j0 >= n) { j0 -= n; ++l2; }
+        for (int g = 2 * tid; g < tot; g += 2 * kXThreads) {
+            const int pos = g + (g >> MSH);
+            o2[g >> 1] = make_double2(tile[pos], tile[pos + 1]);
         }
     } else {
-        int l2 = 0, j0 = tid;
-        while (j0 >= n) { j0 -= n; ++l2; }
-        for (long long e = tid; e < tot; e += kXThreads) {
-            obase[e] = tile[l2 * pitch + j0 + j0 / M];
-            j0 += kXThreads;
-            while (j0 >= n) { j0 -= n; ++l2; }
-        }
+        for (int g = tid; g < tot; g += kXThreads) obase[g] = tile[g + (g >> MSH)];
     }
 }
 
@@ -730,7 +744,8 @@ cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* o
         // cluster kernel: P chunks split over C = P/PC CTAs (portable cluster sizes only); mode 3: PC=8, mode 4: PC=4
         const int PC = (mode == 4) ? 4 : 8;
         const int C = P / PC, XTc = kClThreads / PC;
-        if ((mode == 3 || mode == 4) && P % PC == 0 && (C == 1 || C == 2 || C == 4 || C == 8) && n1 >= XTc / 2) {
+        if ((mode == 3 || mode == 4) && P % PC == 0 && (C == 1 || C == 2 || C == 4 || C == 8) && n1 >= XTc / 2 &&
+            (BW == 0 || h->tab.W + 1 <= kClMaxHW)) {
             const int tiles_x = (int)((n1 + XTc - 1) / XTc);
             const long long nblocks = (long long)tiles_x * n3 * C;
             cudaLaunchConfig_t cfg = {};
