@@ -203,8 +203,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    VAR = {128: "chunk_x_kernel<128 thr>", 256: "chunk_x_kernel<256 thr>", 1: "chunk_strided_kernel<512>", 2: "chunk_strided_kernel<256>",
+           3: "chunk_strided_cluster_kernel", 5: "chunk_strided_cpipe_kernel", 6: "chunk_strided_pipe_kernel"}
     for _ in range(max(3, args.warmup)):
         step()
+    barrier()
+    kern_of = []   # which kernel variant the planner settled on, per axis
+    for fn in (der.ddx, der.ddy, der.ddz):
+        if (fn is der.ddx and p_row > 1) or (fn is der.ddz and p_col > 1):
+            kern_of.append("(see transposes)")
+            continue
+        fn(f, df)
+        kern_of.append(VAR.get(L.pdo_debug_last_variant(), "?"))
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = L.pdo_launch_count()
@@ -258,7 +268,7 @@ def run_ours(args):
     if rank != 0:
         return
     peak, peak_src = peaks()
-    names = ["cd10 ddx (chunk_x_kernel)", "cd10 ddy (chunk_strided_kernel)", "cd10 ddz (chunk_strided_kernel)"]
+    names = [f"cd10 dd{a} ({k})" for a, k in zip("xyz", kern_of)]
     per_k = {}
     for nm, t in zip(names, per):
         per_k[nm] = {"ms": t, "GBps": BYTES_PER_POINT * npts_rank / (t * 1e-3) / 1e9}
@@ -271,7 +281,7 @@ def run_ours(args):
     tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tr):
         try:
-            roof["traffic"] = json.load(open(tr)).get(names[dom].split("(")[1].rstrip(")"))
+            roof["traffic"] = json.load(open(tr)).get(names[dom].split("(")[1].rstrip(")").split("<")[0])
         except Exception:
             pass
     cb = None

@@ -101,6 +101,9 @@ for _f in ("x_to_y", "y_to_x", "y_to_z", "z_to_y"):
     _PROTOS[f"pdo_transpose_{_f}"] = (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_void_p])
 _PROTOS["pdo_debug_cd10_generic"] = (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.c_int, C.c_void_p])
 
+_PROTOS["pdo_debug_set_variant"] = (C.c_int, [C.c_int, C.c_int])
+_PROTOS["pdo_debug_last_variant"] = (C.c_int, [])
+
 EXPORTED = sorted(k for k in _PROTOS if not k.startswith("pdo_debug"))
 
 

@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "banded.cuh"
 
@@ -307,13 +308,13 @@ chunk_strided_pipe_kernel(const double* __restrict__ f, double* __restrict__ out
                 v[HL + M + j] = buf[q * XT + xi];
             }
         }
-        __syncthreads();  // everyone holds its rows in registers: the buffer may be refilled
-        const long long next = tile + gridDim.x;
-        if (next < ntiles) pipe_issue_tile(buf, f, next, tiles_x, XT, xt_shift, rows_in, n1, in_slab, vec16 != 0);
-
+        // the stencil is evaluated before the buffer is released: its FP64 work overlaps the shared loads above
         double r[M];
 #pragma unroll
         for (int i = 0; i < M; ++i) r[i] = rhs_eval<RK>(&v[i + HL], op);
+        __syncthreads();  // everyone has consumed its rows: the buffer may be refilled
+        const long long next = tile + gridDim.x;
+        if (next < ntiles) pipe_issue_tile(buf, f, next, tiles_x, XT, xt_shift, rows_in, n1, in_slab, vec16 != 0);
         if constexpr (BW > 0) {
             const int slots = P * XT;
             chunk_solve<BW, M>(r, tab, sm_g, slots, p, [&](int q) { return q * XT + xi; });
@@ -370,8 +371,8 @@ chunk_strided_cluster_kernel(const double* __restrict__ f, double* __restrict__ 
     __shared__ __align__(16) double sS[BWc * PC * XT];
     const int tid = threadIdx.x;
     const int xi = tid & (XT - 1), pl = tid >> XSH;
-    const unsigned rank = (C > 1) ? cluster_ctarank() : 0u;
-    const int p0 = (int)rank * PC;
+    const unsigned rank = (unsigned)(blockIdx.x % C);  // == %cluster_ctarank for the 1-D clusters launched here; explicit
+    const int p0 = (int)rank * PC;                      // stencils (BW == 0) need no exchange and are launched unclustered
     const int p = p0 + pl;
     const int P = n / M;
     const long long cl = blockIdx.x / C;
@@ -485,13 +486,243 @@ chunk_strided_cluster_kernel(const double* __restrict__ f, double* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Contiguous (x) kernel
+// Cluster + pipeline variant ("cpipe"): the persistent cp.async pipeline of chunk_strided_pipe_kernel with the
+// line split over the C CTAs of a cluster as in chunk_strided_cluster_kernel.  A CTA owns PC = 16 chunks
+// (512 rows at M = 32) of XT = 32 columns, so every row segment it touches is 256 contiguous bytes whatever
+// the line length (the single-CTA pipeline shrinks to 128 B at n = 1024 and 64 B at n = 2048): half the
+// TLB / DRAM-page visits per byte when the row stride is megabytes (solve axis outermost, ddz).  The RHS
+// halo rows of the neighbouring CTA are fetched with the tile (HL + HR extra rows, ~1 % extra L2 reads);
+// the only cross-CTA traffic is the separator exchange through distributed shared memory.
 // ------------------------------------------------------------------------------------------------
-constexpr int kXThreads = 256;
-constexpr int kXPairsPerThread = 16;  // a full tile is L*n = 8192 doubles = 16 double2 per thread
+constexpr int kCpXT = 32;
+constexpr int kCpPC = 16;
+constexpr int kCpMaxHW = 8;
+
+// --- distributed-shared-memory push with transaction barriers (no fences, no cluster barrier per tile) ---
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned cluster_map_u32(unsigned saddr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(mbar), "r"(parity) : "memory");
+}
+// 8-byte store into a peer CTA's shared memory that signals `remote_mbar` (in the same peer) with 8 transaction bytes
+__device__ __forceinline__ void st_async_f64(unsigned remote_addr, double v, unsigned remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "l"(__double_as_longlong(v)), "r"(remote_mbar) : "memory");
+}
 
 template <int RK, int BW, int M>
-__global__ void __launch_bounds__(kXThreads, 2)
+__global__ void __launch_bounds__(kCpPC * kCpXT, 1)
+chunk_strided_cpipe_kernel(const double* __restrict__ f, double* __restrict__ out, long long n1, int n, long long in_slab,
+                           long long out_slab, int tiles_x, long long ntiles, int C, int vec16,
+                           const __grid_constant__ ChunkTables tab, const __grid_constant__ OpParams op) {
+    constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
+    constexpr int XT = kCpXT, PC = kCpPC, THREADS = PC * XT;
+    constexpr int RC = PC * M;            // rows this CTA solves
+    constexpr int RB = RC + HL + HR;      // rows it buffers (own rows + stencil halo)
+    constexpr int BWc = (BW > 0 ? BW : 1);
+    constexpr int EC = PC + 2 * kCpMaxHW;  // extended chunk slots: [halo left | own PC chunks | halo right]
+    constexpr int ESL = EC * XT;
+    extern __shared__ __align__(16) double sm[];
+    double* buf = sm;                     // [RB][XT]
+    double* ex = sm + RB * XT;            // 2 x { eA[BWc][EC][XT], eB[BWc][EC][XT] }: ping-pong per tile (a neighbour may run
+    double* sS = ex + 4 * BWc * ESL;      // one tile ahead and push into the other half); sS[BWc][PC][XT]
+    __shared__ __align__(8) unsigned long long full_bar[2];  // transaction barriers: "halo of parity b has landed"
+    const int tid = threadIdx.x;
+    const int xi = tid & (XT - 1), pl = tid >> 5;
+    const unsigned rank = (C > 1) ? cluster_ctarank() : 0u;
+    const int p0 = (int)rank * PC;
+    const int nwrap = op.edge_in ? n + 1 : n;
+    const long long ncl = gridDim.x / C;
+    long long tile = blockIdx.x / C;
+
+    auto issue = [&](long long t) {
+        const long long k = t / tiles_x;
+        const long long x0 = (t - k * tiles_x) * XT;
+        const double* base = f + k * in_slab + x0;
+        const int q0 = p0 * M - HL;  // logical row of buffer row 0
+        if (vec16) {
+            const int c = (tid & 15) * 2;
+            if (x0 + c < n1) {
+                for (int l = tid >> 4; l < RB; l += THREADS / 16) {
+                    int q = q0 + l;
+                    q = q < 0 ? q + n : (q >= nwrap ? q - n : q);
+                    cp_async16(buf + l * XT + c, base + (long long)q * n1 + c);
+                }
+            }
+        } else {
+            if (x0 + xi < n1) {
+                for (int l = pl; l < RB; l += PC) {
+                    int q = q0 + l;
+                    q = q < 0 ? q + n : (q >= nwrap ? q - n : q);
+                    cp_async8(buf + l * XT + xi, base + (long long)q * n1 + xi);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    if constexpr (BW > 0) {
+        if (C > 1) {
+            if (tid == 0) {
+                mbar_init(smem_u32(&full_bar[0]), 1);
+                mbar_init(smem_u32(&full_bar[1]), 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            cluster_sync_all();  // peers' barriers exist before anyone pushes
+        }
+    }
+    if (tile < ntiles) issue(tile);
+    int par = 0;
+    unsigned it = 0;
+    for (; tile < ntiles; tile += ncl, par ^= 1, ++it) {
+        cp_async_wait_all();
+        __syncthreads();
+        double v[M + HL + HR];
+        {
+            const double* b = buf + (pl * M) * XT + xi;
+#pragma unroll
+            for (int j = 0; j < M + HL + HR; ++j) v[j] = b[j * XT];
+        }
+        // the stencil is evaluated before the buffer is released: its FP64 work overlaps the shared loads above and
+        // the window v[] is dead by the time the solve needs registers
+        double r[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) r[i] = rhs_eval<RK>(&v[i + HL], op);
+        __syncthreads();  // everyone has consumed its rows: the buffer may be refilled
+        const long long next = tile + ncl;
+        if (next < ntiles) issue(next);
+
+        if constexpr (BW > 0) {
+            double a_[2], b_[2];
+            chunk_interior<BW, M>(r, tab, a_, b_);
+            const int W = tab.W, HW = W + 1;
+            double* eA = ex + par * (2 * BWc * ESL);  // [BWc][EC][XT]
+            double* eB = eA + BWc * ESL;
+            const int me = (kCpMaxHW + pl) * XT + xi;
+            eA[me] = a_[0];
+            eB[me] = b_[0];
+            if (BW == 2) { eA[ESL + me] = a_[1]; eB[ESL + me] = b_[1]; }
+            // Push model: the chunks within HW of a CTA edge are what the neighbouring CTA needs as halo; their owner
+            // stores them straight into the neighbour's extended slots (st.async, completion counted on the neighbour's
+            // transaction barrier).  No cluster barrier and no fence sit on the per-tile path, so the prefetch issued
+            // above and the previous tile's stores stay in flight.
+            {
+                const bool to_right = pl >= PC - HW;  // my tail chunks are the right neighbour's left halo
+                const bool to_left = pl < HW;         // my head chunks are the left neighbour's right halo
+                const int er = (kCpMaxHW + pl - PC) * XT + xi;
+                const int el = (kCpMaxHW + PC + pl) * XT + xi;
+                if (C > 1) {
+                    const unsigned bar = smem_u32(&full_bar[par]);
+                    if (tid == 0) mbar_arrive_expect_tx(bar, (unsigned)(2 * HW * XT * 2 * BW * sizeof(double)));
+                    const unsigned aA = smem_u32(eA), aB = smem_u32(eB);
+                    if (to_right) {
+                        const unsigned rr = rank + 1 == (unsigned)C ? 0u : rank + 1;
+                        const unsigned rb = cluster_map_u32(bar, rr);
+                        const unsigned rA = cluster_map_u32(aA + er * 8, rr), rB = cluster_map_u32(aB + er * 8, rr);
+                        st_async_f64(rA, a_[0], rb);
+                        st_async_f64(rB, b_[0], rb);
+                        if (BW == 2) { st_async_f64(rA + ESL * 8, a_[1], rb); st_async_f64(rB + ESL * 8, b_[1], rb); }
+                    }
+                    if (to_left) {
+                        const unsigned rl = rank == 0 ? (unsigned)C - 1 : rank - 1;
+                        const unsigned rb = cluster_map_u32(bar, rl);
+                        const unsigned rA = cluster_map_u32(aA + el * 8, rl), rB = cluster_map_u32(aB + el * 8, rl);
+                        st_async_f64(rA, a_[0], rb);
+                        st_async_f64(rB, b_[0], rb);
+                        if (BW == 2) { st_async_f64(rA + ESL * 8, a_[1], rb); st_async_f64(rB + ESL * 8, b_[1], rb); }
+                    }
+                } else {  // the line lives in this CTA: the halo is a periodic copy of my own edge chunks
+                    if (to_right) {
+                        eA[er] = a_[0]; eB[er] = b_[0];
+                        if (BW == 2) { eA[ESL + er] = a_[1]; eB[ESL + er] = b_[1]; }
+                    }
+                    if (to_left) {
+                        eA[el] = a_[0]; eB[el] = b_[0];
+                        if (BW == 2) { eA[ESL + el] = a_[1]; eB[ESL + el] = b_[1]; }
+                    }
+                }
+            }
+            __syncthreads();
+            if (C > 1) mbar_wait(smem_u32(&full_bar[par]), (it >> 1) & 1u);
+            // separator solve from local shared memory: s_p = sum_d G[d] (gA_{p+d} + gB_{p+d+1})
+            double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+            {
+                int e = (kCpMaxHW + pl - W) * XT + xi;
+                for (int d = 0; d <= 2 * W; ++d) {
+                    if (BW == 2) {
+                        const double h0 = eA[e] + eB[e + XT];
+                        const double h1 = eA[ESL + e] + eB[ESL + e + XT];
+                        s0 += tab.G[d][0] * h0 + tab.G[d][1] * h1;
+                        s1 += tab.G[d][2] * h0 + tab.G[d][3] * h1;
+                    } else {
+                        s0 += tab.G[d][0] * (eA[e] + eB[e + XT]);
+                    }
+                    e += XT;
+                }
+            }
+            double sp0, sp1 = 0.0;
+            if (pl == 0) {  // previous chunk lives in another CTA: recompute its separator values from the halo
+                int e = (kCpMaxHW - 1 - W) * XT + xi;
+                for (int d = 0; d <= 2 * W; ++d) {
+                    if (BW == 2) {
+                        const double h0 = eA[e] + eB[e + XT];
+                        const double h1 = eA[ESL + e] + eB[ESL + e + XT];
+                        t0 += tab.G[d][0] * h0 + tab.G[d][1] * h1;
+                        t1 += tab.G[d][2] * h0 + tab.G[d][3] * h1;
+                    } else {
+                        t0 += tab.G[d][0] * (eA[e] + eB[e + XT]);
+                    }
+                    e += XT;
+                }
+            }
+            sS[pl * XT + xi] = s0;
+            if (BW == 2) sS[PC * XT + pl * XT + xi] = s1;
+            __syncthreads();
+            if (pl == 0) { sp0 = t0; sp1 = t1; }
+            else { sp0 = sS[(pl - 1) * XT + xi]; if (BW == 2) sp1 = sS[PC * XT + (pl - 1) * XT + xi]; }
+            chunk_finish<BW, M>(r, tab, s0, s1, sp0, sp1);
+        }
+        const long long k = tile / tiles_x;
+        const long long x = (tile - k * tiles_x) * XT + xi;
+        if (x < n1) {
+            double* fo = out + k * out_slab + x;
+            double* po = fo + (long long)((p0 + pl) * M) * n1;
+#pragma unroll
+            for (int i = 0; i < M; ++i) { *po = r[i]; po += n1; }
+            if (op.edge_out && p0 + pl == 0) fo[(long long)n * n1] = r[0];
+        }
+    }
+    // Exit is safe without a barrier: nobody reads a peer's shared memory, and every push aimed at this CTA was
+    // awaited by its last mbar_wait.
+}
+
+// ------------------------------------------------------------------------------------------------
+// Contiguous (x) kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kXPairsPerThread = 16;  // a full tile is L*n = 32 doubles per thread = 16 double2 per thread
+
+// kXThreads threads per CTA, 512 / kXThreads CTAs per SM: smaller CTAs put more independent load / solve / store
+// phases in flight on an SM.
+template <int RK, int BW, int M, int kXThreads>
+__global__ void __launch_bounds__(kXThreads, 512 / kXThreads)
 chunk_x_kernel(const double* __restrict__ f, double* __restrict__ out, long long nlines, int n, int L,
                const __grid_constant__ ChunkTables tab, const __grid_constant__ OpParams op) {
     constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
@@ -705,47 +936,84 @@ void banded_op_destroy(BandedOp* h) {
 
 namespace {
 
-// PDO_STRIDED_MODE = pipe | t512 | t256 selects the strided kernel variant (default: pipe where it applies)
+// PDO_STRIDED_MODE = auto | t512 | t256 | cluster | cluster4 | cpipe | pipe1 selects the strided kernel variant
+// (default auto: cpipe for megabyte row strides and lines of more than 32 chunks, the single-CTA pipeline otherwise)
+int g_strided_mode = -1;
 int strided_mode() {
-    static int mode = -1;
-    if (mode < 0) {
+    if (g_strided_mode < 0) {
         const char* e = std::getenv("PDO_STRIDED_MODE");
-        mode = 0;
+        int mode = 0;
         if (e && std::strcmp(e, "t512") == 0) mode = 1;
         if (e && std::strcmp(e, "t256") == 0) mode = 2;
         if (e && std::strcmp(e, "cluster") == 0) mode = 3;
         if (e && std::strcmp(e, "cluster4") == 0) mode = 4;
+        if (e && std::strcmp(e, "cpipe") == 0) mode = 5;
+        if (e && std::strcmp(e, "pipe1") == 0) mode = 6;  // single-CTA pipeline even where cpipe is the default
+        g_strided_mode = mode;
     }
-    return mode;
+    return g_strided_mode;
+}
+
+// PDO_X_THREADS = 256 | 128: CTA size of the contiguous-axis kernel
+int g_x_threads = -1;
+int x_threads() {  // 0 = auto
+    int& v = g_x_threads;
+    if (v < 0) {
+        const char* e = std::getenv("PDO_X_THREADS");
+        v = e ? (std::atoi(e) == 256 ? 256 : 128) : 0;
+    }
+    return v;
+}
+
+// PDO_TUNE=0 disables the first-call planner (heuristic dispatch only)
+bool tuning_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("PDO_TUNE");
+        v = (e && std::atoi(e) == 0) ? 0 : 1;
+    }
+    return v != 0;
+}
+std::mutex g_plan_mutex;
+int g_last_variant = 0;  // what the most recent chunked launch ran: 128/256 (x kernel) or 1 t512, 2 t256, 3 cluster, 5 cpipe, 6 pipe
+
+template <int RK, int BW, int M, int XTH>
+cudaError_t launch_x(const BandedOp* h, const double* f, double* out, long long nlines, cudaStream_t st) {
+    static bool attr_done = false;
+    const int n = h->n, P = n / M;
+    const int L = XTH / P > 0 ? XTH / P : 1;
+    const size_t smem = sizeof(double) * ((size_t)L * (n + P) + 3 * (BW > 0 ? BW : 1) * (size_t)(XTH + P));
+    auto kern = chunk_x_kernel<RK, BW, M, XTH>;
+    const size_t cap = (size_t)(200 * 1024) / (512 / XTH);
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    if (smem > cap || P > XTH) return cudaErrorInvalidConfiguration;
+    const long long grid = (nlines + L - 1) / L;
+    kern<<<(unsigned)grid, XTH, smem, st>>>(f, out, nlines, n, L, h->tab, h->op);
+    return cudaGetLastError();
 }
 
 template <int RK, int BW, int M>
 cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3,
-                         long long in_slab, long long out_slab, cudaStream_t st) {
+                         long long in_slab, long long out_slab, cudaStream_t st, int mode, int xth) {
     const int n = h->n, P = n / M;
     if (axis == 0) {
-        static bool attr_done = false;
-        const int L = kXThreads / P > 0 ? kXThreads / P : 1;
-        const size_t smem = sizeof(double) * ((size_t)L * (n + P) + 3 * (BW > 0 ? BW : 1) * (size_t)(kXThreads + P));
-        auto kern = chunk_x_kernel<RK, BW, M>;
-        if (!attr_done) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            if (e != cudaSuccess) return e;
-            attr_done = true;
-        }
-        if (smem > 100 * 1024 || P > kXThreads) return cudaErrorInvalidConfiguration;
-        const long long nlines = n3;
-        const long long grid = (nlines + L - 1) / L;
-        kern<<<(unsigned)grid, kXThreads, smem, st>>>(f, out, nlines, n, L, h->tab, h->op);
-        return cudaGetLastError();
+        if (xth != 256 && P <= 128) { g_last_variant = 128; return launch_x<RK, BW, M, 128>(h, f, out, n3, st); }
+        g_last_variant = 256;
+        return launch_x<RK, BW, M, 256>(h, f, out, n3, st);
     }
-    const int mode = strided_mode();
     if constexpr (M == 32) {
         // cluster kernel: P chunks split over C = P/PC CTAs (portable cluster sizes only); mode 3: PC=8, mode 4: PC=4
         const int PC = (mode == 4) ? 4 : 8;
         const int C = P / PC, XTc = kClThreads / PC;
-        if ((mode == 3 || mode == 4) && P % PC == 0 && (C == 1 || C == 2 || C == 4 || C == 8) && n1 >= XTc / 2 &&
-            (BW == 0 || h->tab.W + 1 <= kClMaxHW)) {
+        // explicit stencils (Gaussian) have no compute phase worth pipelining: the plain streaming form of this kernel
+        // (no shared staging, two CTAs per SM) runs at the copy rate, so it is their default
+        const bool stencil_default = (BW == 0) && (mode == 0) && n1 >= XTc;
+        if ((mode == 3 || mode == 4 || stencil_default) && P % PC == 0 && (BW == 0 || C == 1 || C == 2 || C == 4 || C == 8) &&
+            n1 >= XTc / 2 && (BW == 0 || h->tab.W + 1 <= kClMaxHW)) {
             const int tiles_x = (int)((n1 + XTc - 1) / XTc);
             const long long nblocks = (long long)tiles_x * n3 * C;
             cudaLaunchConfig_t cfg = {};
@@ -755,16 +1023,60 @@ cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* o
             cfg.stream = st;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = (unsigned)C;
+            at[0].val.clusterDim.x = (unsigned)(BW > 0 ? C : 1);
             at[0].val.clusterDim.y = 1;
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
+            g_last_variant = 3;
             if (PC == 8)
                 return cudaLaunchKernelEx(&cfg, chunk_strided_cluster_kernel<RK, BW, M, 8>, f, out, n1, n, in_slab, out_slab, tiles_x,
                                           C, h->tab, h->op);
             return cudaLaunchKernelEx(&cfg, chunk_strided_cluster_kernel<RK, BW, M, 4>, f, out, n1, n, in_slab, out_slab, tiles_x, C,
                                       h->tab, h->op);
+        }
+    }
+    if constexpr (M == 32) {
+        // cpipe: persistent clusters of C = P/16 CTAs, 256-byte row segments.  Default for the outermost axis
+        // (row stride n1 of megabytes) and for lines the single-CTA pipeline can only tile 8 columns wide.
+        const int C = P / kCpPC;
+        const bool fits = (P % kCpPC == 0) && (C == 1 || C == 2 || C == 4 || C == 8) && n1 >= kCpXT &&
+                          (BW == 0 || (!h->tab.dense && h->tab.W + 1 <= kCpMaxHW));
+        const bool want = (mode == 5) || (mode == 0 && (n1 * (long long)sizeof(double) >= (1 << 20) || P > 32));
+        if (fits && want) {
+            constexpr int HLR = Halo<RK>::L + Halo<RK>::R;
+            constexpr int BWc = (BW > 0 ? BW : 1);
+            const size_t smem = sizeof(double) * ((size_t)(kCpPC * M + HLR) * kCpXT + 4 * BWc * (size_t)(kCpPC + 2 * kCpMaxHW) * kCpXT +
+                                                  BWc * (size_t)kCpPC * kCpXT);
+            auto kern = chunk_strided_cpipe_kernel<RK, BW, M>;
+            static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            const int tiles_x = (int)((n1 + kCpXT - 1) / kCpXT);
+            const long long ntiles = (long long)tiles_x * n3;
+            cudaLaunchConfig_t cfg = {};
+            cfg.blockDim = dim3(kCpPC * kCpXT);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)C;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            if (max_clusters[C] == 0) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                cfg.gridDim = dim3((unsigned)(148 / C * C));
+                int nc = 0;
+                e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+                if (e != cudaSuccess) return e;
+                max_clusters[C] = nc > 0 ? nc : 1;
+            }
+            g_last_variant = 5;
+            const long long ncl = ntiles < max_clusters[C] ? ntiles : max_clusters[C];
+            cfg.gridDim = dim3((unsigned)(ncl * C));
+            const int vec16 = (n1 % 2 == 0) && (in_slab % 2 == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0);
+            return cudaLaunchKernelEx(&cfg, kern, f, out, n1, n, in_slab, out_slab, tiles_x, ntiles, C, vec16, h->tab, h->op);
         }
     }
     const int threads = (mode == 2) ? 256 : 512;
@@ -777,7 +1089,7 @@ cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* o
     const size_t smem_g = sizeof(double) * 3 * (BW > 0 ? BW : 1) * (size_t)P * XT;
     const int rows_in = n + (h->op.edge_in ? 1 : 0);
     const size_t smem_pipe = sizeof(double) * (((size_t)rows_in * XT + 1) & ~(size_t)1) + smem_g;
-    if (mode == 0 && smem_pipe <= 200 * 1024 && ntiles >= 148) {
+    if ((mode == 0 || mode == 6) && smem_pipe <= 200 * 1024 && ntiles >= 148) {
         static bool attr_done = false;
         auto kern = chunk_strided_pipe_kernel<RK, BW, M, 512>;
         if (!attr_done) {
@@ -787,23 +1099,92 @@ cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* o
         }
         const int vec16 = (XT % 2 == 0) && (n1 % 2 == 0) && (in_slab % 2 == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0);
         const long long grid = ntiles < 148 ? ntiles : 148;
+        g_last_variant = 6;
         kern<<<(unsigned)grid, XT * P, smem_pipe, st>>>(f, out, n1, n, in_slab, out_slab, tiles_x, XT, ntiles, vec16, h->tab, h->op);
     } else if (threads == 256) {
+        g_last_variant = 2;
         chunk_strided_kernel<RK, BW, M, 256><<<(unsigned)ntiles, XT * P, smem_g, st>>>(f, out, n1, n, in_slab, out_slab, tiles_x,
                                                                                        XT, h->tab, h->op);
     } else {
+        g_last_variant = 1;
         chunk_strided_kernel<RK, BW, M, 512><<<(unsigned)ntiles, XT * P, smem_g, st>>>(f, out, n1, n, in_slab, out_slab, tiles_x,
                                                                                        XT, h->tab, h->op);
     }
     return cudaGetLastError();
 }
 
+// Planner.  Which kernel variant wins depends on the operator (how much FP64 work sits between the load and the
+// store), the line length and the row stride, and the differences are tens of percent.  Like FFTW's planner and
+// 2DECOMP's best_2d_grid (both timing-based in the reference), the first large call of an operator on a given
+// (axis, shape) times the candidates on the caller's own arrays (out-of-place operators: re-running is harmless)
+// and remembers the winner in the handle.  All candidates produce bit-identical results (same per-chunk
+// arithmetic), so the choice never changes the answer.  Small problems and captured streams use the heuristic.
+template <int RK, int BW, int M>
+cudaError_t launch_planned(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3,
+                           long long in_slab, long long out_slab, cudaStream_t st) {
+    const int forced_mode = strided_mode(), forced_x = x_threads();
+    const bool forced = (axis == 0) ? forced_x != 0 : forced_mode != 0;
+    const long long pts = n1 * h->n * n3;
+    if (forced || !tuning_enabled() || pts < (1LL << 24))
+        return launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, forced_mode, forced_x);
+    {
+        std::lock_guard<std::mutex> lk(g_plan_mutex);
+        for (int i = 0; i < h->nplans; ++i)
+            if (h->plans[i].axis == axis && h->plans[i].n1 == n1 && h->plans[i].n3 == n3)
+                return launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, h->plans[i].choice, h->plans[i].choice);
+    }
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, 0, 0);
+    }
+    const int cand_x[2] = {128, 256};
+    const int cand_s[4] = {6, 5, 3, 1};  // pipe1, cpipe, cluster / streaming, t512
+    const int* cand = axis == 0 ? cand_x : cand_s;
+    const int ncand = axis == 0 ? 2 : 4;
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+        cudaGetLastError();
+        return launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, 0, 0);
+    }
+    int best = 0;
+    float best_ms = 1e30f;
+    for (int c = 0; c < ncand; ++c) {
+        float ms_c = 1e30f;
+        bool ok = true;
+        for (int rep = 0; rep < 3 && ok; ++rep) {  // rep 0 warms up (function attributes, instruction cache)
+            cudaEventRecord(e0, st);
+            ok = launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, cand[c], cand[c]) == cudaSuccess;
+            cudaEventRecord(e1, st);
+            if (cudaEventSynchronize(e1) != cudaSuccess) ok = false;
+            float ms = 0.f;
+            if (ok && rep > 0 && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess && ms < ms_c) ms_c = ms;
+        }
+        if (!ok) { cudaGetLastError(); continue; }
+        if (ms_c < best_ms) { best_ms = ms_c; best = cand[c]; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    {
+        std::lock_guard<std::mutex> lk(g_plan_mutex);
+        if (h->nplans < BandedOp::kMaxPlans) {
+            h->plans[h->nplans].axis = axis; h->plans[h->nplans].n1 = n1; h->plans[h->nplans].n3 = n3;
+            h->plans[h->nplans].choice = best;
+            h->nplans++;
+        }
+    }
+    if (std::getenv("PDO_TUNE_VERBOSE"))
+        std::fprintf(stderr, "[padeops_b200] plan rk=%d bw=%d n=%d axis=%d n1=%lld n3=%lld -> variant %d (%.3f ms)\n", RK, BW, h->n, axis,
+                     n1, n3, best, best_ms);
+    return cudaSuccess;  // the timed runs already produced `out`
+}
+
 template <int RK, int BW>
 cudaError_t launch_any(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3,
                        long long in_slab, long long out_slab, cudaStream_t st, int force_generic) {
-    if (h->M == 32 && !force_generic) return launch_chunk<RK, BW, 32>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
-    if (h->M == 16 && !force_generic) return launch_chunk<RK, BW, 16>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
-    if (h->M == 8 && !force_generic) return launch_chunk<RK, BW, 8>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
+    if (h->M == 32 && !force_generic) return launch_planned<RK, BW, 32>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
+    if (h->M == 16 && !force_generic) return launch_planned<RK, BW, 16>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
+    if (h->M == 8 && !force_generic) return launch_planned<RK, BW, 8>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
     // generic
     const int n = h->n;
     const long long tot = n1 * n * n3;
@@ -820,6 +1201,13 @@ cudaError_t launch_any(const BandedOp* h, int axis, const double* f, double* out
 }
 
 }  // namespace
+
+int banded_debug_last_variant() { return g_last_variant; }
+
+void banded_debug_set_variant(int strided_mode, int x_threads) {
+    g_strided_mode = strided_mode;
+    g_x_threads = x_threads;
+}
 
 cudaError_t banded_op_apply(const BandedOp* h, int axis, const double* f, double* out, long long na, long long nb,
                             cudaStream_t st, int force_generic) {

@@ -31,6 +31,11 @@ struct BandedOp {
     int M = 0;   // chunk length of the fast path; 0 → generic any-n kernels
     ChunkTables tab{};
     double* d_line = nullptr;  // generic path tables (device)
+    // planner memory: winning kernel variant per (axis, n1, n3), filled by the first large call (banded.cu: launch_planned)
+    static constexpr int kMaxPlans = 8;
+    struct Plan { int axis; long long n1, n3; int choice; };
+    mutable Plan plans[kMaxPlans];
+    mutable int nplans = 0;
 };
 
 // Builds tables (host) and uploads what the generic path needs.  LHS = circ[b2 b1 1 b1 b2].
@@ -42,5 +47,10 @@ void banded_op_destroy(BandedOp* h);
 // that side.  force_generic != 0 routes through the any-n kernels (used by tests to cross-check).
 cudaError_t banded_op_apply(const BandedOp* h, int axis, const double* f, double* out, long long na, long long nb,
                             cudaStream_t stream, int force_generic = 0);
+
+// Test hook: force a kernel variant (strided_mode: -1 env/auto, 0 auto, 1 t512, 2 t256, 3 cluster, 4 cluster4,
+// 5 cpipe, 6 pipe1; x_threads: -1 env/default, 128, 256).
+void banded_debug_set_variant(int strided_mode, int x_threads);
+int banded_debug_last_variant();
 
 }  // namespace pdo

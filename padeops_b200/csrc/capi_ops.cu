@@ -465,4 +465,11 @@ int pdo_debug_cd10_generic(pdo_cd10_t h, int which, int axis, const double* f, d
     return 0;
 }
 
+// test hook (not in the public header): force a kernel variant, see banded.cuh
+int pdo_debug_last_variant(void) { return banded_debug_last_variant(); }
+int pdo_debug_set_variant(int strided_mode, int x_threads) {
+    banded_debug_set_variant(strided_mode, x_threads);
+    return 0;
+}
+
 }  // extern "C"

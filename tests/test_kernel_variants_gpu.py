@@ -1,0 +1,91 @@
+"""Every strided / contiguous kernel variant against the CPU oracle at the BASELINE line lengths (512, 1024,
+2048 → clusters of 1, 2, 4 CTAs), including ragged x-extents (partial tiles, odd n1 → 8-byte cp.async path)
+and the staggered edge planes.  The default dispatch picks one variant per shape; here each is forced."""
+import numpy as np
+import pytest
+
+from conftest import broadband
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+MODES = {"auto": 0, "t512": 1, "t256": 2, "cluster": 3, "cluster4": 4, "cpipe": 5, "pipe1": 6}
+
+
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _relerr(got, ref):
+    return np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+@pytest.fixture
+def variant(pdo):
+    L = pdo.lib()
+    yield lambda mode, xth=-1: L.pdo_debug_set_variant(MODES[mode], xth)
+    L.pdo_debug_set_variant(-1, -1)
+
+
+@pytest.mark.parametrize("mode", ["cpipe", "pipe1", "cluster", "t512"])
+@pytest.mark.parametrize("n,n1", [(512, 96), (512, 33), (1024, 64), (1024, 45), (2048, 40)])
+def test_strided_variants_cd10_cf90(pdo, oracle, variant, mode, n, n1):
+    """axis 1 (f(n1, n, n3)) and axis 2 (f(na, nb, n)) with the forced variant; enough tiles (>= 148) for the persistent ones."""
+    variant(mode)
+    d = 2 * np.pi / n
+    c10, cf, c06 = pdo.cd10(), pdo.cf90(), pdo.cd06()
+    assert c10.init(n, d) == 0 and cf.init(n) == 0 and c06.init(n, d) == 0
+    n3 = 160 if n1 < 64 else 80
+    f = broadband((n3, n, n1), seed=n + n1)
+    fd = _dev(f)
+    assert _relerr(c10.dd2(fd).cpu().numpy(), oracle.cd10(f, d, 1, 1)) < TOL
+    assert _relerr(c10.d2d2(fd).cpu().numpy(), oracle.cd10(f, d, 1, 2)) < TOL
+    assert _relerr(cf.filter2(fd).cpu().numpy(), oracle.cf90(f, 1)) < TOL
+    assert _relerr(c06.dd2(fd).cpu().numpy(), oracle.cd06(f, d, 1)) < TOL
+    # axis 2: same memory seen as f(na, nb, n) with na*nb = n1*n3'
+    g = broadband((n, 48 if n < 2048 else 24, 100), seed=n)
+    gd = _dev(g)
+    assert _relerr(c10.dd3(gd).cpu().numpy(), oracle.cd10(g, d, 2, 1)) < TOL
+    assert _relerr(cf.filter3(gd).cpu().numpy(), oracle.cf90(g, 2)) < TOL
+    ga = pdo.gaussian()
+    assert ga.init(n) == 0
+    assert _relerr(ga.filter3(gd).cpu().numpy(), oracle.gaussian(g, 2)) < TOL
+
+
+@pytest.mark.parametrize("mode", ["cpipe", "pipe1"])
+@pytest.mark.parametrize("n", [512, 1024])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_staggered_edge_planes_variants(pdo, oracle, variant, mode, n, cplx):
+    variant(mode)
+    dz = 2 * np.pi / n
+    st = pdo.cd06stagg()
+    st.init(n, dz)
+    n2, n1 = 70, 77  # odd n1: the real case takes the 8-byte cp.async path, the complex one the 16-byte path
+
+    def field(planes):
+        a = broadband((planes, n2, n1), seed=planes)
+        if cplx:
+            a = a + 1j * broadband((planes, n2, n1), seed=planes + 1)
+        return a
+    fC, fE = field(n), field(n + 1)
+    for name, fn, fin in [("ddz_E2C", st.ddz_E2C, fE), ("ddz_C2E", st.ddz_C2E, fC), ("interp_E2C", st.InterpZ_E2C, fE),
+                          ("interp_C2E", st.InterpZ_C2E, fC), ("d2dz2_C2C", st.d2dz2_C2C, fC), ("d2dz2_E2E", st.d2dz2_E2E, fE)]:
+        got = fn(_dev(fin)).cpu().numpy()
+        ref = oracle.stagg(name, fin, n, dz)
+        assert got.shape == ref.shape
+        assert _relerr(got, ref) < TOL, (name, n, cplx, mode, _relerr(got, ref))
+
+
+@pytest.mark.parametrize("xth", [128, 256])
+@pytest.mark.parametrize("n", [512, 1024, 2048, 96])
+def test_contiguous_variants(pdo, oracle, variant, xth, n):
+    variant("auto", xth)
+    d = 2 * np.pi / n
+    c10, cf = pdo.cd10(), pdo.cf90()
+    assert c10.init(n, d) == 0 and cf.init(n) == 0
+    f = broadband((7, 31, n), seed=n)  # 217 lines: ragged last tile
+    fd = _dev(f)
+    assert _relerr(c10.dd1(fd).cpu().numpy(), oracle.cd10(f, d, 0, 1)) < TOL
+    assert _relerr(c10.d2d1(fd).cpu().numpy(), oracle.cd10(f, d, 0, 2)) < TOL
+    assert _relerr(cf.filter1(fd).cpu().numpy(), oracle.cf90(f, 0)) < TOL
