@@ -1,6 +1,7 @@
 // capi_ops.cu — C ABI for the 1-D line operators and their dispatch types (include/padeops_b200.h).
 // Host-side mirror of cd10stuff / cd06stuff / cf90stuff / gaussianstuff / cd06staggstuff /
 // DerivativesMod / FiltersMod: same constructor arguments, same error codes, same degenerate cases.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -58,14 +59,133 @@ int degenerate(bool is_filter, const double* f, double* out, size_t count, cudaS
     });
 }
 
+// ------------------------------------------------------------------------------------------------
+// Host-pointer (drop-in) path for large fields: the field is cut into ~64 MB pieces along an index that is
+// NOT the solve axis (whole lines stay together), and piece i+1 travels host->device while piece i is solved
+// and piece i-1 travels device->host — PCIe is full duplex, so the call costs about one direction's transfer
+// time instead of H2D + kernel + D2H back to back.  Three internal streams, rings of three device buffers.
+// ------------------------------------------------------------------------------------------------
+struct HostPipe {
+    static constexpr int R = 3;
+    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[R] = {}, ev_cmp[R] = {}, ev_out[R] = {};
+    void* din[R] = {};
+    void* dout[R] = {};
+    size_t cap_in = 0, cap_out = 0;
+    bool ready = false;
+    int init() {
+        if (ready) return 0;
+        PDO_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        PDO_CUDA(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
+        PDO_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < R; ++i) {
+            PDO_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            PDO_CUDA(cudaEventCreateWithFlags(&ev_cmp[i], cudaEventDisableTiming));
+            PDO_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+        }
+        ready = true;
+        return 0;
+    }
+    int reserve(size_t bin, size_t bout) {
+        if (cap_in < bin) {
+            for (int i = 0; i < R; ++i) { if (din[i]) cudaFree(din[i]); din[i] = nullptr; }
+            cap_in = 0;
+            for (int i = 0; i < R; ++i) PDO_CUDA(cudaMalloc(&din[i], bin));
+            cap_in = bin;
+        }
+        if (cap_out < bout) {
+            for (int i = 0; i < R; ++i) { if (dout[i]) cudaFree(dout[i]); dout[i] = nullptr; }
+            cap_out = 0;
+            for (int i = 0; i < R; ++i) PDO_CUDA(cudaMalloc(&dout[i], bout));
+            cap_out = bout;
+        }
+        return 0;
+    }
+};
+HostPipe& host_pipe() {
+    static thread_local HostPipe p;
+    return p;
+}
+
+// PDO_PIPE_CHUNK_MB / PDO_PIPE_MIN_MB override the piece size (64 MB) and the field size from which the pipelined
+// path is used (256 MB; smaller fields take the plain staged path).  Tests shrink both to cover it on small fields.
+size_t env_mb(const char* name, size_t dflt_mb) {
+    const char* e = std::getenv(name);
+    const double v = e ? std::atof(e) : 0.0;
+    return (size_t)((v > 0.0 ? v : (double)dflt_mb) * 1048576.0);
+}
+size_t pipe_chunk_bytes() { return env_mb("PDO_PIPE_CHUNK_MB", 64); }
+size_t pipe_min_bytes() { return env_mb("PDO_PIPE_MIN_MB", 256); }
+
+// f, out: HOST pointers.  in_rows / out_rows: planes along the solve axis on each side (n or n+1).
+int apply_host_pipelined(const BandedOp& op, int axis, const double* f, double* out, long long na, long long nb,
+                         int in_rows, int out_rows, cudaStream_t st) {
+    HostPipe& hp = host_pipe();
+    if (int rc = hp.init()) return rc;
+    PDO_CUDA(cudaStreamSynchronize(st));  // host-pointer calls are synchronous with respect to the caller's stream
+    // View the field as f(n1, rows, n3), solve along `rows` (axis 0: n1 = 1 and the pieces are groups of lines).
+    const long long n1 = axis == 0 ? 1 : (axis == 1 ? na : na * nb);
+    const long long n3 = axis == 0 ? na * nb : (axis == 1 ? nb : 1);
+    const size_t e = sizeof(double);
+    const bool split3 = (axis == 0) || (n3 >= 4);  // cut along the outer index (contiguous pieces), else along n1 (2-D copies)
+    const long long mrows = in_rows > out_rows ? in_rows : out_rows;
+    const long long unit = split3 ? n1 * mrows : mrows * n3;  // doubles per outer slab / per column
+    long long per = (long long)(pipe_chunk_bytes() / e) / (unit > 0 ? unit : 1);  // outer slabs (split3) or columns (else) per piece
+    if (per < 1) per = 1;
+    if (!split3) { per &= ~1LL; if (per < 2) per = 2; }  // even column counts keep the 16-byte paths
+    const long long total = split3 ? n3 : n1;
+    const long long npieces = (total + per - 1) / per;
+    if (int rc = hp.reserve((size_t)per * unit * e, (size_t)per * unit * e)) return rc;
+    for (long long i = 0; i < npieces; ++i) {
+        const int slot = (int)(i % HostPipe::R);
+        const long long o0 = i * per, cnt = (o0 + per <= total) ? per : total - o0;
+        if (i >= HostPipe::R) {
+            PDO_CUDA(cudaStreamWaitEvent(hp.s_in, hp.ev_cmp[slot], 0));   // din[slot] was read by the solve of piece i-R
+            PDO_CUDA(cudaStreamWaitEvent(hp.s_cmp, hp.ev_out[slot], 0));  // dout[slot] was read by the D2H of piece i-R
+        }
+        double* di = (double*)hp.din[slot];
+        double* d_o = (double*)hp.dout[slot];
+        if (split3) {
+            PDO_CUDA(cudaMemcpyAsync(di, f + o0 * n1 * in_rows, (size_t)cnt * n1 * in_rows * e, cudaMemcpyHostToDevice, hp.s_in));
+        } else {
+            PDO_CUDA(cudaMemcpy2DAsync(di, (size_t)cnt * e, f + o0, (size_t)n1 * e, (size_t)cnt * e, (size_t)in_rows * n3,
+                                       cudaMemcpyHostToDevice, hp.s_in));
+        }
+        PDO_CUDA(cudaEventRecord(hp.ev_in[slot], hp.s_in));
+        PDO_CUDA(cudaStreamWaitEvent(hp.s_cmp, hp.ev_in[slot], 0));
+        // the piece is itself a field of the same kind: f(n, cnt, 1) / f(na, n, cnt) / f(cnt, 1, n)
+        const long long pa = axis == 0 ? cnt : (axis == 1 ? (split3 ? na : cnt) : cnt);
+        const long long pb = axis == 0 ? 1 : (axis == 1 ? (split3 ? cnt : nb) : 1);
+        PDO_CUDA(banded_op_apply(&op, axis, di, d_o, pa, pb, hp.s_cmp, 0));
+        g_launches += (op.M ? 1 : (op.bw ? 2 : 1));
+        PDO_CUDA(cudaEventRecord(hp.ev_cmp[slot], hp.s_cmp));
+        PDO_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_cmp[slot], 0));
+        if (split3) {
+            PDO_CUDA(cudaMemcpyAsync(out + o0 * n1 * out_rows, d_o, (size_t)cnt * n1 * out_rows * e, cudaMemcpyDeviceToHost, hp.s_out));
+        } else {
+            PDO_CUDA(cudaMemcpy2DAsync(out + o0, (size_t)n1 * e, d_o, (size_t)cnt * e, (size_t)cnt * e, (size_t)out_rows * n3,
+                                       cudaMemcpyDeviceToHost, hp.s_out));
+        }
+        PDO_CUDA(cudaEventRecord(hp.ev_out[slot], hp.s_out));
+    }
+    PDO_CUDA(cudaStreamSynchronize(hp.s_out));
+    PDO_CUDA(cudaStreamSynchronize(hp.s_cmp));
+    PDO_CUDA(cudaStreamSynchronize(hp.s_in));
+    return 0;
+}
+
 int apply(const BandedOp& op, bool is_filter, int axis, const double* f, double* out, long long na, long long nb,
           void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!f || !out) return fail(PDO_E_BADARG, "null field pointer");
     if (na < 0 || nb < 0) return fail(PDO_E_BADARG, "negative extent");
-    const size_t in_count = (size_t)(op.n + (op.op.edge_in || (op.op.edge_out && op.rk == RK_D2_5) ? 1 : 0)) * na * nb;
-    const size_t out_count = (size_t)(op.n + (op.op.edge_out ? 1 : 0)) * na * nb;
+    const int in_rows = op.n + (op.op.edge_in || (op.op.edge_out && op.rk == RK_D2_5) ? 1 : 0);
+    const int out_rows = op.n + (op.op.edge_out ? 1 : 0);
+    const size_t in_count = (size_t)in_rows * na * nb;
+    const size_t out_count = (size_t)out_rows * na * nb;
     if (op.n == 1) return degenerate(is_filter, f, out, out_count, st);
+    if (in_count * sizeof(double) >= pipe_min_bytes() && axis >= 0 && axis <= 2 && !is_device_ptr(f) && !is_device_ptr(out))
+        return apply_host_pipelined(op, axis, f, out, na, nb, in_rows, out_rows, st);
     return with_device_views(f, in_count * sizeof(double), out, out_count * sizeof(double), st,
                              [&](const void* din, void* dout) -> int {
                                  PDO_CUDA(banded_op_apply(&op, axis, (const double*)din, (double*)dout, na, nb, st, 0));

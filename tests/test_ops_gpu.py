@@ -208,3 +208,31 @@ def test_full_size_lines_single_mode_identity(pdo, n):
         assert (got + kp * fs).abs().max().item() < 1e-12 * kp
         got = (cf.filter1, cf.filter2, cf.filter3)[ax](fc)
         assert (got - T * fc).abs().max().item() < 1e-12
+
+
+def test_host_pointer_pipelined_path(pdo, oracle, monkeypatch):
+    """The chunked full-duplex host path (capi_ops.cu: apply_host_pipelined) on every axis, with ragged last pieces,
+    edge planes (staggered ops) and both split directions; thresholds shrunk so small fields take it."""
+    monkeypatch.setenv("PDO_PIPE_MIN_MB", "0.001")
+    monkeypatch.setenv("PDO_PIPE_CHUNK_MB", "0.05")
+    n = 64
+    d = 0.1
+    op, cf = pdo.cd10(), pdo.cf90()
+    assert op.init(n, d) == 0 and cf.init(n) == 0
+    for axis, shape in [(0, (7, 33, n)), (1, (9, n, 40)), (1, (2, n, 300)), (2, (n, 13, 29))]:
+        f = broadband(shape, seed=axis)
+        out = np.empty_like(f)
+        (op.dd1, op.dd2, op.dd3)[axis](f, out)
+        assert _relerr(out, oracle.cd10(f, d, axis, 1)) < TOL, (axis, shape)
+        (cf.filter1, cf.filter2, cf.filter3)[axis](f, out)
+        assert _relerr(out, oracle.cf90(f, axis)) < TOL, (axis, shape)
+    st = pdo.cd06stagg()
+    st.init(n, d)
+    fE = broadband((n + 1, 11, 37), seed=5) + 1j * broadband((n + 1, 11, 37), seed=6)
+    fC = fE[:n].copy()
+    got = np.empty((n, 11, 37), dtype=np.complex128)
+    st.ddz_E2C(fE, got)
+    assert _relerr(got, oracle.stagg("ddz_E2C", fE, n, d)) < TOL
+    got = np.empty((n + 1, 11, 37), dtype=np.complex128)
+    st.InterpZ_C2E(fC, got)
+    assert _relerr(got, oracle.stagg("interp_C2E", fC, n, d)) < TOL
