@@ -1,0 +1,390 @@
+"""CPU restatement of the igrid periodic substep and the spectral / projection pieces it is made of.
+
+TEST INFRASTRUCTURE ONLY (see oracle.py header): imported by tests/, __graft_entry__.smoke() and bench.py's CPU legs.
+
+Follows (paths relative to /root/reference/src/incompressible):
+  spectral.F90:235-341     mTimes_ik1/ik2 (ip, oop)
+  spectral.F90:314-363     dealias (init_periodicInZ branch), dealias_edgeField
+  spectral.F90:755-865     init_periodic_inZ_procedures (3-D dealias mask with `>=`, k3 tables, normfactZ)
+  spectral.F90:933-1200    initializeEverything, TwoPeriodic branch (Nyquist sign flip :1030-1032, kabs_sq = k1^2+k2^2,
+                           2-D mask with strict `<` and a hard-wired 2/3 :1147-1159, fixOddball :1189-)
+  spectral.F90:1413-1509   fft / ifft / take_fftz / take_ifftz / take_(i)fft1d_z2z_ip
+  PadeDerOps.F90:57-88, 997-1053   Pade6stagg periodic dispatch (scheme cd06) and getmodCD06stagg
+  PadePoisson.F90:76-128, 386-432, 716-750, 900-949, 1165-1244   periodic Poisson init, PeriodicProjection,
+                           Periodic_getPressure(AndUpdateRHS), DivergenceCheck (with the fixDiv re-projection)
+  igrid.F90:1020-1037 dealiasFields, :1105-1173 TVD_RK3, :1176-1299 SSP_RK45, :1423-1447 interp_PrimitiveVars,
+  :1572-1679 addNonLinearTerm_skewSymm, :1914-1941 addViscousTerm, :1961-1990 project_and_prep,
+  :2553-2683 compute_duidxj, :625-655 the initial fft / dealias / projection sequence of igrid%init.
+
+Everything is written for ONE rank holding the global arrays: 2DECOMP transposes are pure relabelings of the
+same global array, so results do not depend on the processor grid.  Arrays follow the
+reference's Fortran layout: f(nx,ny,nz) is a numpy array of shape (nz, ny, nx); spectral arrays are
+(nz, ny, nx/2+1) complex128.  FFT arithmetic: numpy's pocketfft standing in for FFTW 3.3.5 (unnormalised forward,
+normalisation applied on the inverse as the reference does).
+"""
+import numpy as np
+
+from . import oracle as O
+
+imi = 1j
+
+
+def _wavenums(n, d, flip_nyquist):
+    k = O.wavenums(n, d)
+    if flip_nyquist:
+        k = k.copy()
+        k[n // 2] = -k[n // 2]  # spectral.F90:1030-1032 (1-based n/2+1)
+    return k
+
+
+class Spectral:
+    """spectralMod::spectral with pencil "x", dimTransform = 2 (igrid.F90:487-495)."""
+
+    def __init__(self, nx, ny, nz, dx, dy, dz, init_periodicInZ=False, dealiasF=2.0 / 3.0, fixOddball=False):
+        self.nx, self.ny, self.nz = nx, ny, nz
+        self.nxh = nx // 2 + 1
+        self.dx, self.dy, self.dz = dx, dy, dz
+        k1 = _wavenums(nx, dx, True)[: self.nxh].copy()
+        k2 = _wavenums(ny, dy, True).copy()
+        if fixOddball:  # spectral.F90:1189-1199 (TwoPeriodic branch)
+            k2[ny // 2] = 0.0
+            k1[nx // 2] = 0.0
+        self.k1_1d, self.k2_1d = k1, k2
+        self.k1 = np.broadcast_to(k1[None, None, :], (nz, ny, self.nxh))
+        self.k2 = np.broadcast_to(k2[None, :, None], (nz, ny, self.nxh))
+        self.kabs_sq = np.ascontiguousarray(self.k1 ** 2 + self.k2 ** 2)
+        kdx, kdy = ((2.0 / 3.0) * np.pi / dx), ((2.0 / 3.0) * np.pi / dy)
+        self.Gdealias = ((np.abs(self.k1) < kdx) & (np.abs(self.k2) < kdy)).astype(np.float64)
+        self.normfact2d = 1.0 / (float(nx) * float(ny))
+        self.init_periodicInZ = init_periodicInZ
+        if init_periodicInZ:
+            assert nz % 2 == 0
+            k3 = _wavenums(nz, dz, True)
+            f = dealiasF
+            cut = (np.abs(self.k1) >= f * np.pi / dx) | (np.abs(self.k2) >= f * np.pi / dy) | \
+                  (np.abs(k3)[:, None, None] >= f * np.pi / dz)
+            self.Gdealias = np.where(cut, 0.0, 1.0)
+            self.normfactz = 1.0 / float(nz)
+            k3_1d = O.wavenums(nz, dz)  # GetWaveNums, no sign flip (spectral.F90:845)
+            self.k3inZ = k3
+            self.mk3sq = -(k3_1d ** 2)
+            self.k3_C2Eshift = imi * k3_1d * np.exp(-imi * k3_1d * dz / 2.0)
+            self.k3_E2Cshift = imi * k3_1d * np.exp(imi * k3_1d * dz / 2.0)
+            self.k3_C2Cder = imi * k3_1d
+            self.C2Eshift = np.exp(-imi * k3_1d * dz / 2.0)
+            self.E2Cshift = np.exp(imi * k3_1d * dz / 2.0)
+
+    # fft_3d%fft2_x2y / ifft2_y2x (utilities/fft_3d.F90:645-663, 616-643)
+    def fft(self, a):
+        return np.fft.fft(np.fft.rfft(a, axis=2), axis=1)
+
+    def ifft(self, ahat, setOddball=False):
+        a = np.array(ahat, dtype=np.complex128, copy=True)
+        if setOddball:
+            a[:, :, self.nx // 2] = 0.0
+        a = np.fft.ifft(a, axis=1) * self.ny
+        r = np.fft.irfft(a, n=self.nx, axis=2) * self.nx
+        return r * self.normfact2d
+
+    def mTimes_ik1(self, f):
+        return (-self.k1 * f.imag) + 1j * (self.k1 * f.real)
+
+    def mTimes_ik2(self, f):
+        return (-self.k2 * f.imag) + 1j * (self.k2 * f.real)
+
+    def dealias(self, fhat):
+        if self.init_periodicInZ:
+            c = np.fft.fft(fhat, axis=0)
+            c = c * self.Gdealias
+            c = np.fft.ifft(c, axis=0) * self.nz  # FFTW backward is unnormalised ...
+            return self.normfactz * c             # ... take_ifftz scales by normfactz
+        return fhat * self.Gdealias
+
+    def dealias_edgeField(self, fhatE):
+        """fhatE: z-pencil edge field with nz+1 planes; spectC's (periodic) tables (spectral.F90:343-363)."""
+        nz = self.nz
+        out = np.array(fhatE, dtype=np.complex128, copy=True)
+        c = np.fft.fft(out[:nz], axis=0) * self.Gdealias
+        c = np.fft.ifft(c, axis=0) * nz
+        out[:nz] = self.normfactz * c
+        out[nz] = out[0]
+        return out
+
+    def take_fft1d_z2z(self, a):
+        return np.fft.fft(a, axis=0)
+
+    def take_ifft1d_z2z(self, a):
+        return self.normfactz * (np.fft.ifft(a, axis=0) * self.nz)
+
+
+def getmodCD06stagg(k, dx):
+    """PadeDerOps.F90:1034-1053."""
+    alpha, beta, a, b, c = 9.0 / 62.0, 0.0, 63.0 / 62.0, 17.0 / 62.0, 0.0
+    omega = k * dx
+    kp = (2.0 * a * np.sin(omega / 2.0) + (2.0 / 3.0) * b * np.sin(3.0 * omega / 2.0) + (2.0 / 5.0) * c * np.sin(5.0 * omega / 2.0)) / \
+         (1.0 + 2.0 * alpha * np.cos(omega) + 2.0 * beta * np.cos(2.0 * omega))
+    return kp / dx
+
+
+class Pade6stagg:
+    """PadeDerOps::Pade6stagg, isPeriodic = .true., scheme = cd06 (BC integers are ignored on this branch)."""
+
+    def __init__(self, nz, dz):
+        self.nz, self.dz = nz, dz
+
+    def ddz_E2C(self, fE): return O.stagg("ddz_E2C", fE, self.nz, self.dz)
+    def ddz_C2E(self, fC): return O.stagg("ddz_C2E", fC, self.nz, self.dz)
+    def interpz_E2C(self, fE): return O.stagg("interp_E2C", fE, self.nz, self.dz)
+    def interpz_C2E(self, fC): return O.stagg("interp_C2E", fC, self.nz, self.dz)
+    def d2dz2_C2C(self, fC): return O.stagg("d2dz2_C2C", fC, self.nz, self.dz)
+    def d2dz2_E2E(self, fE): return O.stagg("d2dz2_E2E", fE, self.nz, self.dz)
+
+    def getModifiedWavenumbers(self, k):
+        return getmodCD06stagg(k, self.dz)
+
+
+class PadePoisson:
+    """PadePoissonMod::padepoisson with PeriodicInZ = .true."""
+
+    def __init__(self, dx, dy, dz, spC, spE, derivZ):
+        self.sp, self.spE, self.derivZ = spC, spE, derivZ
+        nx, ny, nz = spC.nx, spC.ny, spC.nz
+        k1 = O.wavenums(nx, dx)[: spC.nxh]
+        k2 = O.wavenums(ny, dy)
+        k3mod = derivZ.getModifiedWavenumbers(O.wavenums(nz, dz))
+        kradsq = k1[None, None, :] ** 2 + k2[None, :, None] ** 2 + k3mod[:, None, None] ** 2
+        with np.errstate(divide="ignore"):
+            self.kradsq_inv = np.where(kradsq <= 1e-14, 0.0, 1.0 / kradsq)
+        self.mfact = 1.0 / float(nz)
+
+    def _solve(self, uhat, vhat, what):
+        sp = self.sp
+        f2dy = sp.k1 * uhat
+        f2dy = f2dy + sp.k2 * vhat
+        f2dy = -f2dy.imag + 1j * f2dy.real
+        w2 = what                                   # transpose_y_to_z: same global array
+        f2d = self.derivZ.ddz_E2C(w2)
+        f2d = f2d + f2dy
+        f2d = np.fft.fft(f2d, axis=0)
+        f2d = -self.kradsq_inv * f2d
+        f2d = np.fft.ifft(f2d, axis=0) * sp.nz
+        f2d = f2d * self.mfact
+        return f2d, w2
+
+    def PressureProjection(self, uhat, vhat, what):
+        sp = self.sp
+        f2d, w2 = self._solve(uhat, vhat, what)
+        dwdz = self.derivZ.ddz_C2E(f2d)
+        what_new = w2 - dwdz
+        uhat_new = uhat - imi * sp.k1 * f2d
+        vhat_new = vhat - imi * sp.k2 * f2d
+        return uhat_new, vhat_new, what_new
+
+    def getPressure(self, uhat, vhat, what):
+        f2d, _ = self._solve(uhat, vhat, what)
+        return self.sp.ifft(f2d)
+
+    def getPressureAndUpdateRHS(self, uhat, vhat, what):
+        sp = self.sp
+        f2d, w2 = self._solve(uhat, vhat, what)
+        dwdz = self.derivZ.ddz_C2E(f2d)
+        return uhat - imi * sp.k1 * f2d, vhat - imi * sp.k2 * f2d, w2 - dwdz, sp.ifft(f2d)
+
+    def divergence(self, uhat, vhat, what):
+        sp = self.sp
+        f2dy = self.derivZ.ddz_E2C(what)
+        f2dy = f2dy + imi * sp.k1 * uhat + imi * sp.k2 * vhat
+        return sp.ifft(f2dy)
+
+    def DivergenceCheck(self, uhat, vhat, what, fixDiv=False):
+        """Returns (uhat, vhat, what, divergence); re-projects like PadePoisson.F90:1203-1241 when fixDiv."""
+        div = self.divergence(uhat, vhat, what)
+        if fixDiv and div.max() > 1e-13:
+            uhat, vhat, what = self.PressureProjection(uhat, vhat, what)
+            div = self.divergence(uhat, vhat, what)
+            if div.max() > 1e-10:
+                uhat, vhat, what = self.PressureProjection(uhat, vhat, what)
+        return uhat, vhat, what, div
+
+
+class IGrid:
+    """igrid, periodic in x, y, z; NumericalSchemeVert = 1 (CD06), AdvectionTerm = 1 (skew-symmetric), no SGS / forcing /
+    Coriolis / stratification; viscous unless isInviscid.  u, v: (nz, ny, nx); w: (nz+1, ny, nx) with plane nz == plane 0."""
+
+    def __init__(self, nx, ny, nz, Lx, Ly, Lz, Re, u, v, w, isInviscid=False, dealiasFact=2.0 / 3.0, t_DivergenceCheck=10,
+                 TimeSteppingScheme=1, use_d2dz2_C2C=True):
+        self.nx, self.ny, self.nz = nx, ny, nz
+        self.dx, self.dy, self.dz = Lx / nx, Ly / ny, Lz / nz
+        self.Re, self.isInviscid = Re, isInviscid
+        self.t_DivergenceCheck, self.scheme = t_DivergenceCheck, TimeSteppingScheme
+        self.use_d2dz2_C2C = use_d2dz2_C2C
+        self.spectC = Spectral(nx, ny, nz, self.dx, self.dy, self.dz, True, dealiasFact, False)
+        self.spectE = Spectral(nx, ny, nz + 1, self.dx, self.dy, self.dz, False, dealiasFact, False)
+        self.ops = Pade6stagg(nz, self.dz)
+        self.poiss = PadePoisson(self.dx, self.dy, self.dz, self.spectC, self.spectE, self.ops)
+        self.step, self.tsim = 0, 0.0
+        # igrid.F90:625-655
+        self.uhat = self.spectC.fft(u)
+        self.vhat = self.spectC.fft(v)
+        self.what = self.spectE.fft(w)
+        self.dealiasFields()
+        _, _, _, self.divergence = self.poiss.DivergenceCheck(self.uhat, self.vhat, self.what)
+        self.uhat, self.vhat, self.what = self.poiss.PressureProjection(self.uhat, self.vhat, self.what)
+        self._to_physical()
+        self.interp_PrimitiveVars()
+        self.compute_duidxj()
+
+    # ---- igrid.F90:1020-1037
+    def dealiasFields(self):
+        self.uhat = self.spectC.dealias(self.uhat)
+        self.vhat = self.spectC.dealias(self.vhat)
+        self.what = self.spectC.dealias_edgeField(self.what)
+
+    def _to_physical(self):
+        self.u = self.spectC.ifft(self.uhat)
+        self.v = self.spectC.ifft(self.vhat)
+        self.w = self.spectE.ifft(self.what)
+
+    # ---- igrid.F90:1423-1447
+    def interp_PrimitiveVars(self):
+        self.whatC = self.ops.interpz_E2C(self.what)
+        self.wC = self.spectC.ifft(self.whatC)
+        self.uEhat = self.ops.interpz_C2E(self.uhat)
+        self.uE = self.spectE.ifft(self.uEhat)
+        self.vEhat = self.ops.interpz_C2E(self.vhat)
+        self.vE = self.spectE.ifft(self.vEhat)
+
+    # ---- igrid.F90:2553-2683
+    def compute_duidxj(self):
+        C, E, ops = self.spectC, self.spectE, self.ops
+        d = {}
+        d["dudx"] = C.ifft(C.mTimes_ik1(self.uhat)); d["dudxE"] = E.ifft(E.mTimes_ik1(self.uEhat))
+        d["dudy"] = C.ifft(C.mTimes_ik2(self.uhat)); d["dudyE"] = E.ifft(E.mTimes_ik2(self.uEhat))
+        d["dvdx"] = C.ifft(C.mTimes_ik1(self.vhat)); d["dvdxE"] = E.ifft(E.mTimes_ik1(self.vEhat))
+        d["dvdy"] = C.ifft(C.mTimes_ik2(self.vhat)); d["dvdyE"] = E.ifft(E.mTimes_ik2(self.vEhat))
+        d["dwdxC"] = C.ifft(C.mTimes_ik1(self.whatC)); d["dwdx"] = E.ifft(E.mTimes_ik1(self.what))
+        d["dwdyC"] = C.ifft(C.mTimes_ik2(self.whatC)); d["dwdy"] = E.ifft(E.mTimes_ik2(self.what))
+        dwdzH = ops.ddz_E2C(self.what)
+        d["dwdz"] = C.ifft(dwdzH)
+        d["dwdzE"] = E.ifft(ops.interpz_C2E(dwdzH))
+        if not self.isInviscid:
+            self.d2wdz2hatE = ops.d2dz2_E2E(self.what)
+        for nm, fhat in (("u", self.uhat), ("v", self.vhat)):
+            dEH = ops.ddz_C2E(fhat)
+            d["d%sdz" % nm] = E.ifft(dEH)
+            if not self.isInviscid:
+                d2 = ops.d2dz2_C2C(fhat) if self.use_d2dz2_C2C else ops.ddz_E2C(ops.ddz_C2E(fhat))
+                setattr(self, "d2%sdz2hatC" % nm, d2)
+            d["d%sdzC" % nm] = C.ifft(ops.interpz_E2C(dEH))
+        self.duidxj = d
+
+    # ---- igrid.F90:1572-1679
+    def addNonLinearTerm_skewSymm(self):
+        C, E, ops, d = self.spectC, self.spectE, self.ops, self.duidxj
+        u, v, w, wC, uE, vE = self.u, self.v, self.w, self.wC, self.uE, self.vE
+        T1C = d["dudx"] * u; T2C = d["dudy"] * v; T1C = T1C + T2C
+        T1E = d["dudz"] * w
+        fT1C = C.fft(T1C); fT1E = E.fft(T1E)
+        u_rhs = ops.interpz_E2C(fT1E) + fT1C
+        T1C = d["dvdx"] * u; T2C = d["dvdy"] * v; T1C = T1C + T2C
+        T1E = d["dvdz"] * w
+        fT1C = C.fft(T1C); fT1E = E.fft(T1E)
+        v_rhs = ops.interpz_E2C(fT1E) + fT1C
+        T1E = d["dwdx"] * uE; T2E = d["dwdy"] * vE; T2E = T1E + T2E
+        fT2E = E.fft(T2E)
+        T1C = d["dwdz"] * wC
+        fT1C = C.fft(T1C)
+        w_rhs = ops.interpz_C2E(fT1C) + fT2E
+        fT1C = C.mTimes_ik1(C.fft(u * u)); u_rhs = u_rhs + fT1C
+        fT1C = C.mTimes_ik2(C.fft(v * v)); v_rhs = v_rhs + fT1C
+        fT1C = C.fft(wC * wC)
+        w_rhs = w_rhs + ops.ddz_C2E(fT1C)
+        fT1C = C.fft(u * v)
+        u_rhs = u_rhs + C.mTimes_ik2(fT1C)
+        v_rhs = v_rhs + C.mTimes_ik1(fT1C)
+        fT1E = E.fft(uE * w)
+        u_rhs = u_rhs + ops.ddz_E2C(fT1E)
+        w_rhs = w_rhs + E.mTimes_ik1(fT1E)
+        fT1E = E.fft(vE * w)
+        v_rhs = v_rhs + ops.ddz_E2C(fT1E)
+        w_rhs = w_rhs + E.mTimes_ik2(fT1E)
+        return -0.5 * u_rhs, -0.5 * v_rhs, -0.5 * w_rhs
+
+    # ---- igrid.F90:1793-1912 (branches in scope) + 1914-1941
+    def populate_rhs(self):
+        u_rhs, v_rhs, w_rhs = self.addNonLinearTerm_skewSymm()
+        if not self.isInviscid:
+            oneByRe = 1.0 / self.Re
+            u_rhs = u_rhs + oneByRe * (-self.spectC.kabs_sq * self.uhat + self.d2udz2hatC)
+            v_rhs = v_rhs + oneByRe * (-self.spectC.kabs_sq * self.vhat + self.d2vdz2hatC)
+            w_rhs = w_rhs + oneByRe * (-self.spectE.kabs_sq * self.what + self.d2wdz2hatE)
+        return u_rhs, v_rhs, w_rhs
+
+    # ---- igrid.F90:1961-1990
+    def project_and_prep(self, AlreadyProjected=False):
+        self.dealiasFields()
+        if not AlreadyProjected:
+            self.uhat, self.vhat, self.what = self.poiss.PressureProjection(self.uhat, self.vhat, self.what)
+            if self.step % self.t_DivergenceCheck == 0:
+                self.uhat, self.vhat, self.what, self.divergence = self.poiss.DivergenceCheck(self.uhat, self.vhat, self.what, True)
+        self._to_physical()
+        self.interp_PrimitiveVars()
+        self.compute_duidxj()
+
+    def timeAdvance(self, dt):
+        self.dt = dt
+        (self.TVD_RK3 if self.scheme == 1 else self.SSP_RK45)(dt)
+        self.step += 1       # wrapup_timestep
+        self.tsim += dt
+
+    # ---- igrid.F90:1105-1173
+    def TVD_RK3(self, dt):
+        u0, v0, w0 = self.uhat, self.vhat, self.what
+        ur, vr, wr = self.populate_rhs()
+        u1, v1, w1 = u0 + dt * ur, v0 + dt * vr, w0 + dt * wr
+        self.uhat, self.vhat, self.what = u1, v1, w1
+        self.project_and_prep()
+        u1, v1, w1 = self.uhat, self.vhat, self.what   # uhat1 aliases the projected stage array
+        ur, vr, wr = self.populate_rhs()
+        u1 = (3.0 / 4.0) * u0 + (1.0 / 4.0) * u1 + (1.0 / 4.0) * dt * ur
+        v1 = (3.0 / 4.0) * v0 + (1.0 / 4.0) * v1 + (1.0 / 4.0) * dt * vr
+        w1 = (3.0 / 4.0) * w0 + (1.0 / 4.0) * w1 + (1.0 / 4.0) * dt * wr
+        self.uhat, self.vhat, self.what = u1, v1, w1
+        self.project_and_prep()
+        u1, v1, w1 = self.uhat, self.vhat, self.what
+        ur, vr, wr = self.populate_rhs()
+        self.uhat = (1.0 / 3.0) * u0 + (2.0 / 3.0) * u1 + (2.0 / 3.0) * dt * ur
+        self.vhat = (1.0 / 3.0) * v0 + (2.0 / 3.0) * v1 + (2.0 / 3.0) * dt * vr
+        self.what = (1.0 / 3.0) * w0 + (2.0 / 3.0) * w1 + (2.0 / 3.0) * dt * wr
+        self.project_and_prep()
+
+    # ---- igrid.F90:1176-1299
+    def SSP_RK45(self, dt):
+        b01, b12, b23, b34 = 0.39175222657189, 0.368410593050371, 0.25189177427169, 0.54497475022852
+        b35, b45 = 0.06369246866629, 0.22600748323690
+        a20, a21 = 0.444370493651235, 0.555629506348765
+        a30, a32 = 0.620101851488403, 0.379898148511597
+        a40, a43 = 0.17807995439313, 0.821920045606868
+        a52, a53, a54 = 0.517231671970585, 0.096059710526147, 0.386708617503269
+        S0 = (self.uhat, self.vhat, self.what)
+        R = self.populate_rhs()
+        self.uhat, self.vhat, self.what = (s + b01 * dt * r for s, r in zip(S0, R))
+        self.project_and_prep()
+        S1 = (self.uhat, self.vhat, self.what)
+        R = self.populate_rhs()
+        self.uhat, self.vhat, self.what = (a20 * s0 + a21 * s1 + b12 * dt * r for s0, s1, r in zip(S0, S1, R))
+        self.project_and_prep()
+        S2 = (self.uhat, self.vhat, self.what)
+        R = self.populate_rhs()
+        self.uhat, self.vhat, self.what = (a30 * s0 + a32 * s2 + b23 * dt * r for s0, s2, r in zip(S0, S2, R))
+        self.project_and_prep()
+        S3 = (self.uhat, self.vhat, self.what)
+        R3 = self.populate_rhs()
+        # stage 4 overwrites the base arrays (uhat4 => uhat)
+        self.uhat, self.vhat, self.what = (a40 * s0 + a43 * s3 + b34 * dt * r for s0, s3, r in zip(S0, S3, R3))
+        self.project_and_prep()
+        S4 = (self.uhat, self.vhat, self.what)
+        R4 = self.populate_rhs()
+        self.uhat, self.vhat, self.what = (a52 * s2 + a53 * s3 + b35 * dt * r3 + a54 * s4 + b45 * dt * r4
+                                           for s2, s3, r3, s4, r4 in zip(S2, S3, R3, S4, R4))
+        self.project_and_prep()
