@@ -183,6 +183,102 @@ int pdo_poisson_destroy(pdo_poisson_t h);
 /* poisson_solve(rhs, f): out-of-place (:62-87); f == rhs → in-place specific (:37-60) */
 int pdo_poisson_solve(pdo_poisson_t h, const double* rhs, double* f, void* stream);
 
+
+/* ---- spectralMod::spectral, pencil "x", dimTransform = 2  (incompressible/spectral.F90) --------
+   The igrid flavour: 2-D FFTs in (x, y) per z-plane; real fields live in x-pencils of (nx,ny,nz), transforms in
+   y-pencils of the spectral decomposition (nx/2+1, ny, nz).  init_periodicInZ adds the z-periodic procedures
+   (3-D dealiasing through c2c-z, edge-field dealiasing, z FFTs).  For an edge-grid type pass nz+1 as nz and
+   init_periodicInZ = 0, as igrid does for spectE (igrid.F90:487-495). */
+typedef struct pdo_spectral_s* pdo_spectral_t;
+/* spectral%init("x", nx,ny,nz, dx,dy,dz, "four", filt, 2, fixOddball, ..., init_periodicInZ, dealiasF)   spectral.F90:867-930 */
+int pdo_spectral_init(pdo_spectral_t* h, int nx, int ny, int nz, double dx, double dy, double dz, int p_row, int p_col,
+                      int fix_oddball, int init_periodic_in_z, double dealias_fact);
+int pdo_spectral_destroy(pdo_spectral_t h);
+int pdo_spectral_get_physical_info(pdo_spectral_t h, pdo_decomp_info* info);   /* physdecomp  */
+int pdo_spectral_get_spectral_info(pdo_spectral_t h, pdo_decomp_info* info);   /* spectdecomp */
+int pdo_spectral_fft(pdo_spectral_t h, const double* in_real_x, double* out_cplx_y, void* stream);                   /* :1413-1429 */
+int pdo_spectral_ifft(pdo_spectral_t h, const double* in_cplx_y, double* out_real_x, int set_oddball, void* stream);  /* :1431-1453 */
+int pdo_spectral_mtimes_ik1_oop(pdo_spectral_t h, const double* fin, double* fout, void* stream);   /* :235-253 */
+int pdo_spectral_mtimes_ik2_oop(pdo_spectral_t h, const double* fin, double* fout, void* stream);   /* :255-273 */
+int pdo_spectral_mtimes_ik1_ip(pdo_spectral_t h, double* f, void* stream);                          /* :276-293 */
+int pdo_spectral_mtimes_ik2_ip(pdo_spectral_t h, double* f, void* stream);                          /* :295-312 */
+int pdo_spectral_dealias(pdo_spectral_t h, double* fhat_cplx_y, void* stream);                      /* :314-341 */
+/* z-pencil edge field with nz+1 planes, dealiased with this (cell, periodic) type's tables          :343-363 */
+int pdo_spectral_dealias_edgefield(pdo_spectral_t h, double* fhatE_cplx_z, void* stream);
+int pdo_spectral_take_fft1d_z2z_ip(pdo_spectral_t h, double* a_cplx_z, void* stream);               /* :1483-1487 */
+int pdo_spectral_take_ifft1d_z2z_ip(pdo_spectral_t h, double* a_cplx_z, void* stream);              /* :1489-1494 */
+/* the 1-D tables behind k1 / k2 / kabs_sq / Gdealias: full global length (nx/2+1, ny, nz); NULL entries are skipped */
+int pdo_spectral_get_tables(pdo_spectral_t h, double* k1, double* k2, double* gdealias_x, double* gdealias_y, double* gdealias_z);
+
+/* ---- PadeDerOps::Pade6stagg, isPeriodic = .true.  (incompressible/PadeDerOps.F90) ------------- */
+typedef struct pdo_pade6stagg_s* pdo_pade6stagg_t;
+#define PDO_SCHEME_FD02 0
+#define PDO_SCHEME_CD06 1
+#define PDO_SCHEME_FOURIER 2
+/* Pade6stagg%init(gpC, sp_gpC, gpE, sp_gpE, dz, scheme, isPeriodic, spectC)                        PadeDerOps.F90:57-88
+   gp_zsz / sp_zsz: z-pencil sizes of the physical / spectral CELL decompositions.  scheme: cd06 only (fourierColl
+   and fd02 return PDO_E_UNSUPPORTED this round). */
+int pdo_pade6stagg_init(pdo_pade6stagg_t* h, const int gp_zsz[3], const int sp_zsz[3], double dz, int scheme, int is_periodic);
+int pdo_pade6stagg_destroy(pdo_pade6stagg_t h);
+/* generic over real (is_complex = 0, sizes from gp) / complex (is_complex = 1, sizes from sp_gp); bot/top BC integers
+   are accepted and ignored, as on the reference's periodic branch (:146-160, 404-418, 572-585, 689-702, 879-892) */
+int pdo_pade6stagg_ddz_C2E(pdo_pade6stagg_t h, const double* in, double* out, int is_complex, int bot, int top, void* stream);
+int pdo_pade6stagg_ddz_E2C(pdo_pade6stagg_t h, const double* in, double* out, int is_complex, int bot, int top, void* stream);
+int pdo_pade6stagg_interpz_C2E(pdo_pade6stagg_t h, const double* in, double* out, int is_complex, int bot, int top, void* stream);
+int pdo_pade6stagg_interpz_E2C(pdo_pade6stagg_t h, const double* in, double* out, int is_complex, int bot, int top, void* stream);
+int pdo_pade6stagg_d2dz2_C2C(pdo_pade6stagg_t h, const double* in, double* out, int is_complex, int bot, int top, void* stream);
+int pdo_pade6stagg_d2dz2_E2E(pdo_pade6stagg_t h, const double* in, double* out, int is_complex, int bot, int top, void* stream);
+int pdo_pade6stagg_get_modified_wavenumbers(pdo_pade6stagg_t h, const double* k, double* kp, int n);   /* :997-1053 */
+
+/* ---- PadePoissonMod::padepoisson, PeriodicInZ = .true.  (incompressible/PadePoisson.F90) ------ */
+typedef struct pdo_padepoisson_s* pdo_padepoisson_t;
+/* padepoisson%init(dx,dy,dz, sp, spE, computeStokesPressure=F, Lz, storePressure, gpC, derivZ, PeriodicInZ=T)   :130-180, 76-128 */
+int pdo_padepoisson_init(pdo_padepoisson_t* h, double dx, double dy, double dz, pdo_spectral_t sp, pdo_spectral_t spE,
+                         pdo_pade6stagg_t derivZ);
+int pdo_padepoisson_destroy(pdo_padepoisson_t h);
+/* uhat, vhat: complex y-pencils of sp; what: complex y-pencil of spE (nz+1 planes); all updated in place   :386-432 */
+int pdo_padepoisson_pressure_projection(pdo_padepoisson_t h, double* uhat, double* vhat, double* what, void* stream);
+int pdo_padepoisson_get_pressure(pdo_padepoisson_t h, const double* uhat, const double* vhat, const double* what,
+                                 double* pressure_real_x, void* stream);                                     /* :716-750 */
+int pdo_padepoisson_get_pressure_and_update_rhs(pdo_padepoisson_t h, double* uhat, double* vhat, double* what,
+                                                double* pressure_real_x, void* stream);                      /* :900-949 */
+/* divergence: real x-pencil out; fix_div != 0 re-projects as the reference does when max(div) > 1e-13 / 1e-10;
+   max_div (optional) receives p_maxval(maxval(divergence)) of the last evaluation                          :1165-1244 */
+int pdo_padepoisson_divergence_check(pdo_padepoisson_t h, double* uhat, double* vhat, double* what, double* divergence_real_x,
+                                     int fix_div, double* max_div, void* stream);
+
+/* ---- IncompressibleGrid::igrid, the periodic substep  (incompressible/igrid.F90) ---------------
+   Scope: PeriodicInZ, NumericalSchemeVert = 1 (CD06), AdvectionTerm = 1 (skew-symmetric), TimeSteppingScheme 1
+   (TVD-RK3) or 2 (SSP-RK45), viscous or inviscid, no SGS / forcing / Coriolis / stratification / turbines.
+   The namelist file of igrid%init is replaced by this struct. */
+typedef struct pdo_igrid_s* pdo_igrid_t;
+typedef struct {
+    int nx, ny, nz;
+    double Lx, Ly, Lz;
+    double Re;
+    int is_inviscid;
+    double dealias_fact;          /* dealiasFact, reference default 2/3 */
+    int t_divergence_check;       /* t_DivergenceCheck, reference default 10 */
+    int time_stepping_scheme;     /* 1 TVD-RK3, 2 SSP-RK45 */
+    int p_row, p_col;             /* 0,0 = 1 x nproc */
+    int use_d2dz2_c2c;            /* 1: d2dz2_C2C for the viscous z term (slip/periodic BC codes), 0: ddz_E2C(ddz_C2E) (igrid.F90:2642-2660) */
+    int compute_all_gradients;    /* 1: all 18 duidxjC/E fields like the reference; 0: only the 9 the substep reads */
+} pdo_igrid_params;
+/* igrid%init: u, v on the cell grid, w on the edge grid (nz+1 planes, plane nz+1 == plane 1), x-pencil local blocks,
+   host or device pointers (initfields_wallM is the caller's job).  Runs the fft / dealias / projection / gradient
+   sequence of igrid.F90:625-655. */
+int pdo_igrid_init(pdo_igrid_t* h, const pdo_igrid_params* p, const double* u, const double* v, const double* w);
+int pdo_igrid_destroy(pdo_igrid_t h);
+int pdo_igrid_time_advance(pdo_igrid_t h, double dt, void* stream);        /* timeAdvance(dtforced)  :1057-1299 */
+/* physical fields (x-pencils): 0 u, 1 v, 2 w (edge), 3 wC, 4 uE, 5 vE, 6 divergence;  spectral (y-pencils, complex):
+   10 uhat, 11 vhat, 12 what (edge).  Copies into `out` (host or device). */
+int pdo_igrid_get_field(pdo_igrid_t h, int which, double* out, void* stream);
+int pdo_igrid_get_decomp_info(pdo_igrid_t h, int which /*0 gpC, 1 gpE, 2 sp_gpC, 3 sp_gpE*/, pdo_decomp_info* info);
+int pdo_igrid_get_state(pdo_igrid_t h, int* step, double* tsim);
+/* compute_deltaT with useCFL (igrid.F90:1372-1396) */
+int pdo_igrid_compute_delta_t(pdo_igrid_t h, double cfl, double* dt, void* stream);
+int pdo_igrid_max_divergence(pdo_igrid_t h, double* max_div, void* stream);   /* printDivergence + p_maxval(|div|) */
+
 #ifdef __cplusplus
 }
 #endif

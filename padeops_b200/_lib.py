@@ -99,6 +99,51 @@ for _f in ("filterx", "filtery", "filterz"):
     _PROTOS[f"pdo_filters_{_f}"] = (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_void_p])
 for _f in ("x_to_y", "y_to_x", "y_to_z", "z_to_y"):
     _PROTOS[f"pdo_transpose_{_f}"] = (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_void_p])
+
+class IgridParams(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("Lx", C.c_double), ("Ly", C.c_double), ("Lz", C.c_double),
+                ("Re", C.c_double), ("is_inviscid", C.c_int), ("dealias_fact", C.c_double), ("t_divergence_check", C.c_int),
+                ("time_stepping_scheme", C.c_int), ("p_row", C.c_int), ("p_col", C.c_int), ("use_d2dz2_c2c", C.c_int),
+                ("compute_all_gradients", C.c_int)]
+
+
+_PROTOS.update({
+    "pdo_spectral_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, C.c_double]),
+    "pdo_spectral_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_spectral_get_physical_info": (C.c_int, [C.c_void_p, C.POINTER(DecompInfo)]),
+    "pdo_spectral_get_spectral_info": (C.c_int, [C.c_void_p, C.POINTER(DecompInfo)]),
+    "pdo_spectral_fft": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
+    "pdo_spectral_ifft": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_void_p]),
+    "pdo_spectral_mtimes_ik1_oop": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
+    "pdo_spectral_mtimes_ik2_oop": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
+    "pdo_spectral_mtimes_ik1_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
+    "pdo_spectral_mtimes_ik2_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
+    "pdo_spectral_dealias": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
+    "pdo_spectral_dealias_edgefield": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
+    "pdo_spectral_take_fft1d_z2z_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
+    "pdo_spectral_take_ifft1d_z2z_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
+    "pdo_spectral_get_tables": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "pdo_pade6stagg_init": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_double, C.c_int, C.c_int]),
+    "pdo_pade6stagg_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_pade6stagg_get_modified_wavenumbers": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int]),
+    "pdo_padepoisson_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdo_padepoisson_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_padepoisson_pressure_projection": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, C.c_void_p]),
+    "pdo_padepoisson_get_pressure": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
+    "pdo_padepoisson_get_pressure_and_update_rhs": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
+    "pdo_padepoisson_divergence_check": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
+    "pdo_igrid_init": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(IgridParams), c_dp, c_dp, c_dp]),
+    "pdo_igrid_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_igrid_time_advance": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
+    "pdo_igrid_get_field": (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_void_p]),
+    "pdo_igrid_get_decomp_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DecompInfo)]),
+    "pdo_igrid_get_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "pdo_igrid_compute_delta_t": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_void_p]),
+    "pdo_igrid_max_divergence": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
+})
+for _f in ("ddz_C2E", "ddz_E2C", "interpz_C2E", "interpz_E2C", "d2dz2_C2C", "d2dz2_E2E"):
+    _PROTOS[f"pdo_pade6stagg_{_f}"] = (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_void_p])
 _PROTOS["pdo_debug_cd10_generic"] = (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.c_int, C.c_void_p])
 
 _PROTOS["pdo_debug_set_variant"] = (C.c_int, [C.c_int, C.c_int])

@@ -22,9 +22,7 @@
 
 using namespace pdo;
 
-namespace pdo {
-int decomp_transpose_device(pdo_decomp_t h, int dir, const double* src, double* dst, int w, cudaStream_t st);
-}
+#include "spectral_internal.cuh"
 
 namespace {
 
@@ -182,6 +180,37 @@ int ifft3_z2x_dev(pdo_fft3d_s* f, const double2* in, double* out, bool do_scale,
 
 }  // namespace
 
+namespace pdo {
+// Device-pointer entry points shared with igrid.cu (declared in spectral_internal.cuh).
+int fft3d_forward_xy(pdo_fft3d_t f, const double* in_real_x, double2* out_cplx_y, cudaStream_t st) {
+    return forward_xy(f, in_real_x, out_cplx_y, st);
+}
+// ifft2_y2x: the input is intent(in) — it is staged into bufY, folding in 1/(nx ny) and the oddball zeroing
+// (fft_3d.F90:633-641; zeroing the x-Nyquist column commutes with the y pass).
+int fft3d_backward_yx(pdo_fft3d_t f, const double2* in_cplx_y, double* out_real_x, bool set_oddball, cudaStream_t st) {
+    const long long n = cvol(f->si.ysz);
+    int inyq = -1;
+    if (set_oddball) {
+        const int g = f->nx / 2;  // 0-based global index of mode nx/2+1
+        if (g >= f->si.yst[0] - 1 && g <= f->si.yen[0] - 1) inyq = g - (f->si.yst[0] - 1);
+    }
+    copy_scale_oddball_kernel<<<grid_for(n, 256), 256, 0, st>>>(in_cplx_y, f->bufY, n, f->si.ysz[0], inyq, f->normfactor2d);
+    PDO_CUDA(cudaGetLastError());
+    g_launches += 1;
+    return backward_yx(f, f->bufY, out_real_x, st);
+}
+// c2c along z, in place, on a z-pencil array of the spectral decomposition (or on the first nz planes of an edge
+// field, which has the same zsz(1:2)); dir = -1 forward, +1 backward, unnormalised like FFTW.
+int fft3d_z_inplace(pdo_fft3d_t f, double2* a_cplx_z, int dir, cudaStream_t st) {
+    PDO_CUFFT(cufftSetStream(f->planz, st));
+    PDO_CUFFT(cufftExecZ2Z(f->planz, (cufftDoubleComplex*)a_cplx_z, (cufftDoubleComplex*)a_cplx_z, dir < 0 ? CUFFT_FORWARD : CUFFT_INVERSE));
+    g_launches += 1;
+    return 0;
+}
+pdo_decomp_t fft3d_phys_decomp(pdo_fft3d_t f) { return f->phys; }
+pdo_decomp_t fft3d_spec_decomp(pdo_fft3d_t f) { return f->spec; }
+}  // namespace pdo
+
 struct pdo_poisson_s {
     pdo_fft3d_t ft = nullptr;
     int dir_id = 1;
@@ -305,19 +334,7 @@ int pdo_fft3d_ifft2_y2x(pdo_fft3d_t f, const double* in, double* out, int set_od
     cudaStream_t st = (cudaStream_t)stream;
     return with_device_views(in, sizeof(double2) * cvol(f->si.ysz), out, sizeof(double) * cvol(f->pi.xsz), st,
                              [&](const void* di, void* d_o) -> int {
-                                 // input is intent(in): stage it into bufY, folding in 1/(nx ny) and the oddball zeroing
-                                 // (fft_3d.F90:633-641; zeroing the x-Nyquist column commutes with the y pass).
-                                 const long long n = cvol(f->si.ysz);
-                                 int inyq = -1;
-                                 if (set_oddball) {
-                                     const int g = f->nx / 2;  // 0-based global index of mode nx/2+1
-                                     if (g >= f->si.yst[0] - 1 && g <= f->si.yen[0] - 1) inyq = g - (f->si.yst[0] - 1);
-                                 }
-                                 copy_scale_oddball_kernel<<<grid_for(n, 256), 256, 0, st>>>((const double2*)di, f->bufY, n, f->si.ysz[0],
-                                                                                             inyq, f->normfactor2d);
-                                 PDO_CUDA(cudaGetLastError());
-                                 g_launches += 1;
-                                 return backward_yx(f, f->bufY, (double*)d_o, st);
+                                 return pdo::fft3d_backward_yx(f, (const double2*)di, (double*)d_o, set_oddball != 0, st);
                              });
 }
 

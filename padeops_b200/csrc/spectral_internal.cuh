@@ -1,0 +1,15 @@
+// spectral_internal.cuh — device-pointer entry points of decomp.cu / spectral.cu used by the other translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/padeops_b200.h"
+
+namespace pdo {
+// dir: 0 x->y, 1 y->x, 2 y->z, 3 z->y; w = doubles per element (1 real, 2 complex)
+int decomp_transpose_device(pdo_decomp_t h, int dir, const double* src, double* dst, int w, cudaStream_t st);
+int fft3d_forward_xy(pdo_fft3d_t f, const double* in_real_x, double2* out_cplx_y, cudaStream_t st);
+int fft3d_backward_yx(pdo_fft3d_t f, const double2* in_cplx_y, double* out_real_x, bool set_oddball, cudaStream_t st);
+int fft3d_z_inplace(pdo_fft3d_t f, double2* a_cplx_z, int dir, cudaStream_t st);
+pdo_decomp_t fft3d_phys_decomp(pdo_fft3d_t f);
+pdo_decomp_t fft3d_spec_decomp(pdo_fft3d_t f);
+}  // namespace pdo

@@ -1,0 +1,191 @@
+"""GPU parity: spectral ops, periodic pressure projection and the igrid RK substep (through the C ABI) against the
+CPU oracle on the same seeded inputs.  Bar: 1e-12 relative to max|ref| (north_star)."""
+import numpy as np
+import pytest
+
+from conftest import broadband
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _rel(got, ref):
+    return np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+def _cplx(shape, seed):
+    return broadband(shape, seed) + 1j * broadband(shape, seed + 100)
+
+
+@pytest.fixture(scope="module")
+def IG(oracle):
+    from oracle import igrid_oracle
+    return igrid_oracle
+
+
+SHAPES = [(32, 24, 16), (16, 16, 32)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_spectral_ops_match_oracle(pdo, IG, shape):
+    nx, ny, nz = shape
+    d = [2 * np.pi / n for n in shape]
+    sp = pdo.spectral()
+    sp.init("x", nx, ny, nz, *d, "four", "2/3rd", 2, fixOddball=False, init_periodicInZ=True)
+    ref = IG.Spectral(nx, ny, nz, *d, True, 2.0 / 3.0, False)
+    t = sp.tables()
+    assert np.array_equal(t["k1"], ref.k1_1d) and np.array_equal(t["k2"], ref.k2_1d)
+    G = t["gz"][:, None, None] * t["gy"][None, :, None] * t["gx"][None, None, :]
+    assert np.array_equal(G, ref.Gdealias)
+    f = broadband((nz, ny, nx), seed=1)
+    fh = sp.fft(_dev(f))
+    assert _rel(fh.cpu().numpy(), ref.fft(f)) < TOL
+    assert _rel(sp.ifft(fh).cpu().numpy(), f) < TOL
+    fh_np = ref.fft(f)
+    assert _rel(sp.mTimes_ik1_oop(fh).cpu().numpy(), ref.mTimes_ik1(fh_np)) < TOL
+    assert _rel(sp.mTimes_ik2_oop(fh).cpu().numpy(), ref.mTimes_ik2(fh_np)) < TOL
+    g = fh.clone()
+    sp.mTimes_ik1_ip(g)
+    assert _rel(g.cpu().numpy(), ref.mTimes_ik1(fh_np)) < TOL
+    c = _cplx((nz, ny, nx // 2 + 1), 3)
+    got = sp.dealias(_dev(c)).cpu().numpy()
+    assert _rel(got, ref.dealias(c)) < TOL
+    cE = _cplx((nz + 1, ny, nx // 2 + 1), 5)
+    got = sp.dealias_edgeField(_dev(cE)).cpu().numpy()
+    assert _rel(got, ref.dealias_edgeField(cE)) < TOL
+    got = sp.take_ifft1d_z2z_ip(sp.take_fft1d_z2z_ip(_dev(c))).cpu().numpy()
+    assert _rel(got, c) < TOL
+    # setOddball zeroes the x-Nyquist column before the inverse
+    assert _rel(sp.ifft(fh, setOddball=True).cpu().numpy(), ref.ifft(fh_np, True)) < TOL
+    # the edge-grid type (nz+1 planes, not periodic in z): 2-D mask with the strict inequality
+    spE = pdo.spectral()
+    spE.init("x", nx, ny, nz + 1, *d, "four", "2/3rd", 2, fixOddball=False, init_periodicInZ=False)
+    refE = IG.Spectral(nx, ny, nz + 1, *d, False)
+    assert _rel(spE.dealias(_dev(cE)).cpu().numpy(), refE.dealias(cE)) < TOL
+    # host pointers in, host pointers out
+    out = np.empty((nz, ny, nx // 2 + 1), dtype=np.complex128)
+    sp.fft(f, out)
+    assert _rel(out, fh_np) < TOL
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_pade6stagg_and_projection_match_oracle(pdo, IG, shape):
+    nx, ny, nz = shape
+    d = [2 * np.pi / n for n in shape]
+    spC, spE = pdo.spectral(), pdo.spectral()
+    spC.init("x", nx, ny, nz, *d, fixOddball=False, init_periodicInZ=True)
+    spE.init("x", nx, ny, nz + 1, *d, fixOddball=False, init_periodicInZ=False)
+    der = pdo.Pade6stagg()
+    der.init(spC.physdecomp, spC.spectdecomp, dz=d[2], scheme=1, isPeriodic=True)
+    po = pdo.padepoisson()
+    po.init(*d, spC, spE, derivZ=der)
+    rC, rE = IG.Spectral(nx, ny, nz, *d, True), IG.Spectral(nx, ny, nz + 1, *d, False)
+    rops = IG.Pade6stagg(nz, d[2])
+    rpo = IG.PadePoisson(*d, rC, rE, rops)
+    k = np.linspace(-3.0, 3.0, 7)
+    assert np.allclose(der.getModifiedWavenumbers(k), rops.getModifiedWavenumbers(k), rtol=1e-15, atol=0)
+    nxh = nx // 2 + 1
+    uh, vh, wh = _cplx((nz, ny, nxh), 1), _cplx((nz, ny, nxh), 2), _cplx((nz + 1, ny, nxh), 3)
+    wh[nz] = wh[0]
+    # real and complex staggered ops through the dispatcher
+    fr = broadband((nz, ny, nx), 9)
+    assert _rel(der.ddz_C2E(_dev(fr)).cpu().numpy(), rops.ddz_C2E(fr)) < TOL
+    assert _rel(der.interpz_E2C(_dev(wh)).cpu().numpy(), rops.interpz_E2C(wh)) < TOL
+    assert _rel(der.d2dz2_E2E(_dev(wh)).cpu().numpy(), rops.d2dz2_E2E(wh)) < TOL
+    # divergence, projection, pressure
+    div, md = po.DivergenceCheck(_dev(uh), _dev(vh), _dev(wh))
+    rdiv = rpo.divergence(uh, vh, wh)
+    assert _rel(div.cpu().numpy(), rdiv) < TOL and abs(md - rdiv.max()) < TOL * np.abs(rdiv).max()
+    ud, vd, wd = _dev(uh), _dev(vh), _dev(wh)
+    po.PressureProjection(ud, vd, wd)
+    ru, rv, rw = rpo.PressureProjection(uh, vh, wh)
+    scale = max(np.abs(ru).max(), np.abs(rw).max())
+    for got, ref in ((ud, ru), (vd, rv), (wd, rw)):
+        assert np.abs(got.cpu().numpy() - ref).max() < TOL * scale
+    div2, md2 = po.DivergenceCheck(ud, vd, wd)
+    assert np.abs(div2.cpu().numpy()).max() < 1e-12 * np.abs(rdiv).max()
+    p = po.getPressure(_dev(uh), _dev(vh), _dev(wh)).cpu().numpy()
+    assert _rel(p, rpo.getPressure(uh, vh, wh)) < TOL
+    ud, vd, wd = _dev(uh), _dev(vh), _dev(wh)
+    p2 = po.getPressureAndUpdateRHS(ud, vd, wd).cpu().numpy()
+    assert _rel(p2, p) < TOL and np.abs(ud.cpu().numpy() - ru).max() < TOL * scale
+    # host arrays: updated in place
+    uh2, vh2, wh2 = uh.copy(), vh.copy(), wh.copy()
+    po.PressureProjection(uh2, vh2, wh2)
+    assert np.abs(uh2 - ru).max() < TOL * scale and np.abs(wh2 - rw).max() < TOL * scale
+
+
+def _tg_fields(n, direction):
+    d = 2 * np.pi / n
+    x = np.arange(n) * d
+    zC, zE = (np.arange(n) + 0.5) * d, np.arange(n + 1) * d
+    X, Y, ZC, ZE = x[None, None, :], x[None, :, None], zC[:, None, None], zE[:, None, None]
+    if direction == 1:
+        return (np.sin(X) * np.cos(Y) * np.ones((n, 1, 1)), -np.cos(X) * np.sin(Y) * np.ones((n, 1, 1)), np.zeros((n + 1, n, n)))
+    return (np.sin(X) * np.cos(ZC) * np.ones((1, n, 1)), np.zeros((n, n, n)), -np.cos(X) * np.sin(ZE) * np.ones((1, n, 1)))
+
+
+@pytest.mark.parametrize("scheme", [1, 2])
+@pytest.mark.parametrize("inviscid", [False, True])
+def test_igrid_substep_matches_oracle_broadband(pdo, IG, scheme, inviscid):
+    """Two full time steps (6 / 10 RK substeps) from a broadband, non-solenoidal start: every branch of the substep
+    (dealiasing, projection with the divergence re-check, interpolation, gradients, skew-symmetric advection, viscous term)."""
+    nx, ny, nz = 24, 16, 32
+    L = (2 * np.pi, 2 * np.pi, 2 * np.pi)
+    u, v = broadband((nz, ny, nx), 1), broadband((nz, ny, nx), 2)
+    w = broadband((nz + 1, ny, nx), 3)
+    w[nz] = w[0]
+    Re = 50.0
+    ref = IG.IGrid(nx, ny, nz, *L, Re, u, v, w, isInviscid=inviscid, TimeSteppingScheme=scheme)
+    g = pdo.igrid()
+    g.init(nx, ny, nz, *L, Re, u, v, w, isInviscid=inviscid, TimeSteppingScheme=scheme)
+    scale = max(np.abs(ref.u).max(), np.abs(ref.w).max())
+    for nm in ("u", "v", "w", "wC", "uE", "vE"):
+        assert np.abs(g.get(nm) - getattr(ref, nm)).max() < TOL * scale, ("init", nm)
+    dt = 0.01
+    for it in range(2):
+        ref.timeAdvance(dt)
+        g.timeAdvance(dt)
+        for nm in ("u", "v", "w", "wC", "uhat", "vhat", "what"):
+            r = getattr(ref, nm)
+            assert np.abs(g.get(nm) - r).max() < 5 * TOL * np.abs(r).max(), (it, nm, np.abs(g.get(nm) - r).max() / np.abs(r).max())
+    assert g.step == 2 and abs(g.tsim - 2 * dt) < 1e-15
+    assert g.maxDivergence() < 1e-11 * scale
+
+
+@pytest.mark.parametrize("direction", [1, 2])
+def test_igrid_taylor_green_decay_on_gpu(pdo, IG, direction):
+    """problems/incompressible/TaylorGreenPeriodic: 32^3, Re = 100 — analytic decay exp(-2t/Re)."""
+    n, Re = 32, 100.0
+    u, v, w = _tg_fields(n, direction)
+    g = pdo.igrid()
+    g.init(n, n, n, 2 * np.pi, 2 * np.pi, 2 * np.pi, Re, u, v, w, TimeSteppingScheme=2)
+    dt = 0.25 * (2 * np.pi / n)
+    for _ in range(4):
+        g.timeAdvance(dt)
+    decay = np.exp(-2.0 * g.tsim / Re)
+    tol = 1e-9 if direction == 1 else 5e-7
+    assert np.abs(g.get("u") - u * decay).max() < tol
+    assert np.abs(g.get("w") - w * decay).max() < tol
+    cfl_dt = g.compute_deltaT(0.4)
+    umax = (np.abs(g.get("u")) / (2 * np.pi / n) + np.abs(g.get("v")) / (2 * np.pi / n) + np.abs(g.get("wC")) / (2 * np.pi / n)).max()
+    assert abs(cfl_dt - min(0.4 / umax, 0.4 * Re * (2 * np.pi / n) ** 2)) < 1e-12 * cfl_dt
+
+
+def test_igrid_all_gradients_flag_does_not_change_the_solution(pdo):
+    n = 16
+    u, v = broadband((n, n, n), 1), broadband((n, n, n), 2)
+    w = broadband((n + 1, n, n), 3)
+    w[n] = w[0]
+    outs = []
+    for flag in (False, True):
+        g = pdo.igrid()
+        g.init(n, n, n, 2 * np.pi, 2 * np.pi, 2 * np.pi, 100.0, u, v, w, computeAllGradients=flag)
+        g.timeAdvance(0.01)
+        outs.append((g.get("u"), g.get("w")))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
