@@ -138,6 +138,15 @@ typedef struct {
 int pdo_comm_unique_id(char id[128]);
 int pdo_comm_init(int rank, int nproc, const char unique_id[128]);
 int pdo_comm_finalize(void);
+/* Collective over all ranks, same order everywhere: registers a device buffer (CUDA IPC) so that transposes whose
+   DESTINATION lies inside it run as one fused pack + NVLink store + unpack kernel instead of pack / NCCL / unpack.
+   The destination pointer must be the registered base pointer itself.  Unregistered
+   destinations (and PDO_P2P=0) use the NCCL path; results are bit-identical either way. */
+int pdo_comm_register_buffer(void* dev_ptr, size_t bytes);
+/* Local: forget a registered buffer.  MUST be called before the buffer is freed (a later allocation at the same address
+   would otherwise be mistaken for it on this rank only, and the ranks would disagree on the path). */
+int pdo_comm_deregister_buffer(void* dev_ptr);
+int pdo_comm_p2p_enabled(void);
 int pdo_comm_rank(void);   /* nrank */
 int pdo_comm_size(void);   /* nproc */
 /* decomp_info_init(nx,ny,nz,decomp) on a p_row x p_col grid (decomp_2d_init's grid; p_row*p_col must equal

@@ -64,6 +64,9 @@ _PROTOS = {
     "pdo_comm_unique_id": (C.c_int, [C.c_char_p]),
     "pdo_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p]),
     "pdo_comm_finalize": (C.c_int, []),
+    "pdo_comm_register_buffer": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "pdo_comm_deregister_buffer": (C.c_int, [C.c_void_p]),
+    "pdo_comm_p2p_enabled": (C.c_int, []),
     "pdo_comm_rank": (C.c_int, []),
     "pdo_comm_size": (C.c_int, []),
     "pdo_decomp_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

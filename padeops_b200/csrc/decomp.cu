@@ -11,8 +11,10 @@
 // touches NCCL.  With one rank in the sub-communicator the two pencils have the same layout and the
 // transpose is a device copy.  Work buffers belong to the decomp handle (the reference's are module
 // globals, which is what makes its transposes non-re-entrant).
+#include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -23,11 +25,28 @@ using namespace pdo;
 
 namespace {
 
+// A device buffer every rank registered collectively (same order on all ranks): peer[r] is rank r's copy of it,
+// mapped into this process with CUDA IPC.  Registered buffers can be written by peer GPUs over NVLink.
+struct SymBuf {
+    char* base = nullptr;
+    size_t bytes = 0;
+    std::vector<char*> peer;
+};
+struct IpcMapping { cudaIpcMemHandle_t h; char* mapped; };
+
 struct Comm {
     bool inited = false;
     int rank = 0, nproc = 1;
     ncclComm_t comm = nullptr;
     double* d_scalar = nullptr;
+    // P2P transposes
+    bool p2p = false;
+    std::vector<SymBuf> sym;
+    std::vector<IpcMapping> maps;
+    unsigned long long* flags = nullptr;               // [2][nproc]: entry / exit epochs written by peers
+    std::vector<unsigned long long*> peer_flags;       // mapped flags of every rank
+    unsigned long long epoch = 0;
+    char* d_xchg = nullptr;                            // all-gather staging for registration
 };
 Comm g_comm;
 
@@ -110,10 +129,146 @@ int launch_box_copy(const double* src, double* dst, const BoxBatch& b, cudaStrea
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Symmetric buffers (CUDA IPC) and the fused pack + transfer + unpack transposes that use them.
+// ------------------------------------------------------------------------------------------------
+struct XchgRec { cudaIpcMemHandle_t h; unsigned long long offset; unsigned long long bytes; };
+
+typedef int (*cuMemGetAddressRange_t)(unsigned long long*, size_t*, unsigned long long);
+cuMemGetAddressRange_t get_range_fn() {
+    static cuMemGetAddressRange_t fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        if (void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL)) fn = (cuMemGetAddressRange_t)dlsym(lib, "cuMemGetAddressRange_v2");
+    }
+    return fn;
+}
+
+// Collective over all ranks.  Returns the registry index, or -1 with p2p left usable for other buffers.
+int sym_register(void* ptr, size_t bytes) {
+    if (!g_comm.p2p || g_comm.nproc == 1 || !ptr) return -1;
+    const int np = g_comm.nproc;
+    XchgRec mine;
+    std::memset(&mine, 0, sizeof(mine));
+    bool ok = true;
+    unsigned long long base = 0;
+    size_t asz = 0;
+    cuMemGetAddressRange_t fn = get_range_fn();
+    if (!fn || fn(&base, &asz, (unsigned long long)(uintptr_t)ptr) != 0) ok = false;
+    if (ok && cudaIpcGetMemHandle(&mine.h, (void*)(uintptr_t)base) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    mine.offset = ok ? (unsigned long long)(uintptr_t)ptr - base : ~0ull;
+    mine.bytes = bytes;
+    std::vector<XchgRec> all(np);
+    if (cudaMemcpy(g_comm.d_xchg, &mine, sizeof(mine), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    if (ncclAllGather(g_comm.d_xchg, g_comm.d_xchg + sizeof(XchgRec), sizeof(XchgRec), ncclChar, g_comm.comm, 0) != ncclSuccess) return -1;
+    if (cudaMemcpy(all.data(), g_comm.d_xchg + sizeof(XchgRec), sizeof(XchgRec) * np, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (int r = 0; r < np; ++r) if (all[r].offset == ~0ull) ok = false;  // somebody could not export: nobody uses this buffer
+    SymBuf sb;
+    sb.base = (char*)ptr; sb.bytes = bytes; sb.peer.assign(np, nullptr);
+    for (int r = 0; r < np && ok; ++r) {
+        if (r == g_comm.rank) { sb.peer[r] = (char*)ptr; continue; }
+        char* mapped = nullptr;
+        for (auto& m : g_comm.maps) if (std::memcmp(&m.h, &all[r].h, sizeof(cudaIpcMemHandle_t)) == 0) mapped = m.mapped;
+        if (!mapped) {
+            void* q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+            mapped = (char*)q;
+            g_comm.maps.push_back({all[r].h, mapped});
+        }
+        sb.peer[r] = mapped + all[r].offset;
+    }
+    // agree on the outcome (an open can fail on one rank only)
+    int flag = ok ? 1 : 0, *d = (int*)g_comm.d_xchg;
+    cudaMemcpy(d, &flag, sizeof(int), cudaMemcpyHostToDevice);
+    ncclAllReduce(d, d + 1, 1, ncclInt, ncclMin, g_comm.comm, 0);
+    cudaMemcpy(&flag, d + 1, sizeof(int), cudaMemcpyDeviceToHost);
+    if (!flag) return -1;
+    g_comm.sym.push_back(sb);
+    return (int)g_comm.sym.size() - 1;
+}
+
+const SymBuf* sym_find(const void* p, size_t bytes) {
+    const char* c = (const char*)p;
+    for (const auto& sb : g_comm.sym)
+        if (c == sb.base && bytes <= sb.bytes) return &sb;  // exact base: the symmetric-offset rule is then trivially met
+    return nullptr;
+}
+
+struct PushBatch {
+    int count;                  // boxes (one per peer, self included)
+    BoxCopy c[kMaxPeers];
+    double* dst[kMaxPeers];     // absolute destination base per box (peer memory for the others)
+    int npeers;                 // peers to synchronise with (self excluded)
+    unsigned long long* peer_flags[kMaxPeers];
+    int peer_rank[kMaxPeers];
+    unsigned long long* my_flags;
+    unsigned int* counter;
+    unsigned long long epoch;
+    int me, nproc;
+};
+
+__device__ __forceinline__ void flag_store(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long flag_load(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Pack + transfer + unpack in one kernel: every box of `src` is copied to where it belongs in its owner's `dst`
+// (peer memory over NVLink, 16-byte stores).  Entry handshake: a rank's dst may be overwritten once that rank's stream
+// has reached this call (it announces itself to its peers; everybody waits for everybody in the group).  Exit: the
+// last CTA to finish publishes the epoch to the peers after a system-scope fence; box_wait_kernel (next in the stream)
+// holds the consumer until every peer has published.
+template <typename T>
+__global__ void __launch_bounds__(256) box_push_kernel(const double* __restrict__ src, const __grid_constant__ PushBatch b) {
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid < b.npeers) flag_store(b.peer_flags[tid] + b.me, b.epoch);
+    if (tid < b.npeers) {
+        const unsigned long long* f = b.my_flags + b.peer_rank[tid];
+        while (flag_load(f) < b.epoch) { }
+    }
+    __syncthreads();
+    const BoxCopy& c = b.c[blockIdx.y];
+    constexpr int V = sizeof(T) / sizeof(double);
+    const int b1v = c.b1 / V;
+    const long long rows = (long long)c.b2 * c.b3;
+    const T* s = reinterpret_cast<const T*>(src + c.src_off);
+    T* d = reinterpret_cast<T*>(b.dst[blockIdx.y] + c.dst_off);
+    for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows; row += (long long)gridDim.x * blockDim.y) {
+        const long long k = row / c.b2;
+        const int j = (int)(row - k * c.b2);
+        const T* sr = s + (j * c.s_ld2 + k * c.s_ld3) / V;
+        T* dr = d + (j * c.d_ld2 + k * c.d_ld3) / V;
+        for (int i = threadIdx.x; i < b1v; i += blockDim.x) dr[i] = sr[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int total = gridDim.x * gridDim.y;
+        if (atomicAdd(b.counter, 1u) == total - 1) {
+            *b.counter = 0;
+            __threadfence_system();
+            for (int t = 0; t < b.npeers; ++t) flag_store(b.peer_flags[t] + b.nproc + b.me, b.epoch);
+        }
+    }
+}
+
+__global__ void box_wait_kernel(const __grid_constant__ PushBatch b) {
+    const int tid = threadIdx.x;
+    if (tid < b.npeers) {
+        const unsigned long long* f = b.my_flags + b.nproc + b.peer_rank[tid];
+        while (flag_load(f) < b.epoch) { }
+    }
+}
+
 }  // namespace
 
 struct pdo_decomp_s {
     int nx, ny, nz, p_row, p_col, c1, c2;
+    unsigned int* push_counter = nullptr;
     pdo_decomp_info info;
     std::vector<int> x1dist, y1dist, y2dist, z2dist;
     double* work_send = nullptr;
@@ -164,6 +319,62 @@ int transpose_device(pdo_decomp_s* d, int dir, const double* src, double* dst, i
         sdisp[m] = sacc; rdisp[m] = racc;
         sacc += scnt[m]; racc += rcnt[m];
         sa += sdist[m]; ra += rdist[m];
+    }
+    // Fused path: dst is a registered (IPC-shared) buffer on every rank of the group -> each rank stores its blocks
+    // straight into their final place in the owners' dst over NVLink.  No pack buffer, no unpack pass, no NCCL.
+    if (g_comm.p2p) {
+        if (const SymBuf* sb = sym_find(dst, sizeof(double) * (size_t)(d1 * d2 * d3))) {
+            if (!d->push_counter) {
+                PDO_CUDA(cudaMalloc(&d->push_counter, sizeof(unsigned int)));
+                PDO_CUDA(cudaMemset(d->push_counter, 0, sizeof(unsigned int)));
+            }
+            PushBatch b;
+            std::memset(&b, 0, sizeof(b));
+            b.count = np; b.npeers = 0; b.me = g_comm.rank; b.nproc = g_comm.nproc;
+            b.my_flags = g_comm.flags; b.counter = d->push_counter; b.epoch = ++g_comm.epoch;
+            const size_t off = (const char*)dst - sb->base;
+            bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+            long long max_rows = 0;
+            int min_b1 = 1 << 30;
+            for (int m = 0; m < np; ++m) {
+                const int pw = col ? (m * d->p_col + d->c2) : (d->c1 * d->p_col + m);
+                BoxCopy& c = b.c[m];
+                c.s_ld2 = s1; c.s_ld3 = s1 * s2;
+                if (dir == 0) { c.src_off = sst[m] * w; c.b1 = sdist[m] * w; c.b2 = (int)s2; c.b3 = (int)s3; }
+                else if (dir == 3) { c.src_off = sst[m] * s1 * s2; c.b1 = (int)s1; c.b2 = (int)s2; c.b3 = sdist[m]; }
+                else { c.src_off = sst[m] * s1; c.b1 = (int)s1; c.b2 = sdist[m]; c.b3 = (int)s3; }
+                // where my block lands in rank m's dst (m's pencil extents differ from mine along the split index)
+                if (dir == 0) { c.d_ld2 = (long long)sdist[m] * w; c.d_ld3 = c.d_ld2 * d->ny; c.dst_off = rst[me] * c.d_ld2; }
+                else if (dir == 1) { c.d_ld2 = (long long)d->nx * w; c.d_ld3 = c.d_ld2 * sdist[m]; c.dst_off = rst[me] * w; }
+                else if (dir == 2) { c.d_ld2 = s1; c.d_ld3 = s1 * sdist[m]; c.dst_off = rst[me] * c.d_ld3; }
+                else { c.d_ld2 = s1; c.d_ld3 = s1 * d->ny; c.dst_off = rst[me] * s1; }
+                b.dst[m] = (double*)(sb->peer[pw] + off);
+                if ((c.b1 | c.src_off | c.dst_off | c.s_ld2 | c.s_ld3 | c.d_ld2 | c.d_ld3) & 1) vec = false;
+                if (reinterpret_cast<uintptr_t>(b.dst[m]) & 15) vec = false;
+                const long long rows = (long long)c.b2 * c.b3;
+                if (rows > max_rows) max_rows = rows;
+                if (c.b1 < min_b1) min_b1 = c.b1;
+                if (m != me) {
+                    b.peer_flags[b.npeers] = g_comm.peer_flags[pw];
+                    b.peer_rank[b.npeers] = pw;
+                    b.npeers++;
+                }
+            }
+            const int tx = (min_b1 / (vec ? 2 : 1)) >= 128 ? 128 : ((min_b1 / (vec ? 2 : 1)) >= 64 ? 64 : 32);
+            dim3 block(tx, 256 / tx);
+            long long gx = (max_rows + block.y - 1) / block.y;
+            const long long cap = (148LL * 8 + np - 1) / np;
+            if (gx > cap) gx = cap;
+            if (gx < 1) gx = 1;
+            dim3 grid((unsigned)gx, (unsigned)np);
+            if (vec) box_push_kernel<double2><<<grid, block, 0, st>>>(src, b);
+            else box_push_kernel<double><<<grid, block, 0, st>>>(src, b);
+            PDO_CUDA(cudaGetLastError());
+            box_wait_kernel<<<1, 32, 0, st>>>(b);
+            PDO_CUDA(cudaGetLastError());
+            g_launches += 2;
+            return 0;
+        }
     }
     const bool need_pack = (dir != 3), need_unpack = (dir != 2);
     if (int rc = ensure_work(d, (size_t)((sacc > racc ? sacc : racc) + 2))) return rc;
@@ -240,6 +451,8 @@ int transpose_any(pdo_decomp_t h, int dir, const double* src, double* dst, int w
 }  // namespace
 
 namespace pdo {
+void comm_deregister_buffer(void* p) { if (p) pdo_comm_deregister_buffer(p); }
+void comm_register_buffer_quiet(void* p, size_t bytes) { if (g_comm.inited && g_comm.nproc > 1 && g_comm.p2p) sym_register(p, bytes); }
 // used by spectral.cu: transposes on device pointers without the host-pointer probe
 int decomp_transpose_device(pdo_decomp_t h, int dir, const double* src, double* dst, int w, cudaStream_t st) {
     return transpose_device(h, dir, src, dst, w, st);
@@ -271,14 +484,51 @@ int pdo_comm_init(int rank, int nproc, const char unique_id[128]) {
         std::memcpy(&uid, unique_id, 128);
         PDO_NCCL(ncclCommInitRank(&g_comm.comm, nproc, uid, rank));
         PDO_CUDA(cudaMalloc(&g_comm.d_scalar, 2 * sizeof(double)));
+        // P2P transposes (PDO_P2P=0 keeps everything on NCCL): epoch flags every peer can write, shared through CUDA IPC
+        const char* e = std::getenv("PDO_P2P");
+        g_comm.p2p = !(e && std::atoi(e) == 0);
+        if (g_comm.p2p) {
+            PDO_CUDA(cudaMalloc(&g_comm.d_xchg, sizeof(XchgRec) * (size_t)(nproc + 1)));
+            PDO_CUDA(cudaMalloc(&g_comm.flags, sizeof(unsigned long long) * 2 * (size_t)nproc));
+            PDO_CUDA(cudaMemset(g_comm.flags, 0, sizeof(unsigned long long) * 2 * (size_t)nproc));
+            PDO_CUDA(cudaDeviceSynchronize());
+            const int id = sym_register(g_comm.flags, sizeof(unsigned long long) * 2 * (size_t)nproc);
+            if (id < 0) {
+                g_comm.p2p = false;  // no peer access between these GPUs: NCCL path everywhere
+            } else {
+                g_comm.peer_flags.resize(nproc);
+                for (int r = 0; r < nproc; ++r) g_comm.peer_flags[r] = (unsigned long long*)g_comm.sym[id].peer[r];
+            }
+        }
     }
     g_comm.inited = true;
     return 0;
 }
 
+int pdo_comm_register_buffer(void* dev_ptr, size_t bytes) {
+    if (!g_comm.inited) return fail(PDO_E_BADARG, "communicator not initialised");
+    if (g_comm.nproc == 1 || !g_comm.p2p) return 0;
+    sym_register(dev_ptr, bytes);  // a buffer that cannot be shared simply keeps the NCCL path
+    return 0;
+}
+// Local: forget a registered buffer (call before freeing it; peers' mappings stay open until pdo_comm_finalize).  A
+// freed-but-still-registered buffer is a hazard: a later allocation at the same address would be taken for it.
+int pdo_comm_deregister_buffer(void* dev_ptr) {
+    for (size_t i = 0; i < g_comm.sym.size();) {
+        if (g_comm.sym[i].base == (char*)dev_ptr && (void*)g_comm.flags != dev_ptr) g_comm.sym.erase(g_comm.sym.begin() + i);
+        else ++i;
+    }
+    return 0;
+}
+int pdo_comm_p2p_enabled(void) { return g_comm.p2p ? 1 : 0; }
+
 int pdo_comm_finalize(void) {
     if (g_comm.comm) { ncclCommDestroy(g_comm.comm); g_comm.comm = nullptr; }
     if (g_comm.d_scalar) { cudaFree(g_comm.d_scalar); g_comm.d_scalar = nullptr; }
+    cudaDeviceSynchronize();
+    for (auto& m : g_comm.maps) cudaIpcCloseMemHandle(m.mapped);
+    if (g_comm.flags) cudaFree(g_comm.flags);
+    if (g_comm.d_xchg) cudaFree(g_comm.d_xchg);
     g_comm = Comm();
     return 0;
 }
@@ -316,6 +566,7 @@ int pdo_decomp_destroy(pdo_decomp_t h) {
     if (!h) return 0;
     if (h->work_send) cudaFree(h->work_send);
     if (h->work_recv) cudaFree(h->work_recv);
+    if (h->push_counter) cudaFree(h->push_counter);
     delete h;
     return 0;
 }

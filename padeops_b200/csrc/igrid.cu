@@ -222,6 +222,7 @@ int pdo_spectral_init(pdo_spectral_t* h, int nx, int ny, int nz, double dx, doub
     if (!rc && s->periodicInZ && p_col > 1) {
         cudaError_t e = cudaMalloc(&s->ctmpz, sizeof(double2) * (size_t)vol(s->si.zsz));
         if (e != cudaSuccess) rc = fail(PDO_E_CUDA, "spectral ctmpz: %s", cudaGetErrorString(e));
+        else comm_register_buffer_quiet(s->ctmpz, sizeof(double2) * (size_t)vol(s->si.zsz));
     }
     if (!rc) {
         cudaError_t e = cudaMalloc(&s->partial, sizeof(double) * 2048);
@@ -236,7 +237,7 @@ int pdo_spectral_destroy(pdo_spectral_t s) {
     if (!s) return 0;
     double* ptrs[] = {s->k1y, s->k2, s->gx, s->gy, s->gyz, s->gz, s->partial};
     for (double* p : ptrs) if (p) cudaFree(p);
-    if (s->ctmpz) cudaFree(s->ctmpz);
+    if (s->ctmpz) { comm_deregister_buffer(s->ctmpz); cudaFree(s->ctmpz); }
     pdo_fft3d_destroy(s->ft);
     delete s;
     return 0;
@@ -549,6 +550,11 @@ int pdo_padepoisson_init(pdo_padepoisson_t* h, double dx, double dy, double dz, 
         if (e == cudaSuccess) e = cudaMalloc(&p->dwdz, sizeof(double2) * (size_t)vol(p->sE.zsz));
         if (e == cudaSuccess) e = cudaMalloc(&p->div_tmp, sizeof(double) * (size_t)vol(sp->pi.xsz));
         if (e != cudaSuccess) rc = fail(PDO_E_CUDA, "padepoisson buffers: %s", cudaGetErrorString(e));
+        if (!rc) {  // transpose destinations (collective, same order on every rank)
+            comm_register_buffer_quiet(p->uhatInZ, sizeof(double2) * (size_t)vol(p->sC.zsz));
+            comm_register_buffer_quiet(p->w2, sizeof(double2) * (size_t)vol(p->sE.zsz));
+            comm_register_buffer_quiet(p->f2dy, sizeof(double2) * (size_t)vol(p->sC.ysz));
+        }
     }
     if (rc) { pdo_padepoisson_destroy(p); return rc; }
     *h = p;
@@ -558,7 +564,7 @@ int pdo_padepoisson_init(pdo_padepoisson_t* h, double dx, double dy, double dz, 
 int pdo_padepoisson_destroy(pdo_padepoisson_t p) {
     if (!p) return 0;
     void* ptrs[] = {p->k1sq, p->k2sq, p->k3sq, p->f2d, p->f2dy, p->w2, p->uhatInZ, p->dwdz, p->div_tmp};
-    for (void* q : ptrs) if (q) cudaFree(q);
+    for (void* q : ptrs) if (q) { comm_deregister_buffer(q); cudaFree(q); }
     delete p;
     return 0;
 }
@@ -680,7 +686,12 @@ int ig_alloc(pdo_igrid_s* g, void** p, size_t bytes) {
     return 0;
 }
 template <class T>
-int ig_alloc_n(pdo_igrid_s* g, T** p, long long count) { return ig_alloc(g, (void**)p, sizeof(T) * (size_t)count); }
+int ig_alloc_n(pdo_igrid_s* g, T** p, long long count) {
+    if (int rc = ig_alloc(g, (void**)p, sizeof(T) * (size_t)count)) return rc;
+    // every spectral (complex) array can be the destination of a y<->z transpose: make it peer-writable
+    if (sizeof(T) == sizeof(double2)) comm_register_buffer_quiet(*p, sizeof(T) * (size_t)count);
+    return 0;
+}
 
 inline int fftC(pdo_igrid_s* g, const double* in, double2* out, cudaStream_t st) { return fft3d_forward_xy(g->spC->ft, in, out, st); }
 inline int fftE(pdo_igrid_s* g, const double* in, double2* out, cudaStream_t st) { return fft3d_forward_xy(g->spE->ft, in, out, st); }
@@ -988,7 +999,7 @@ extern "C" {
 
 int pdo_igrid_destroy(pdo_igrid_t g) {
     if (!g) return 0;
-    for (void* p : g->allocs) cudaFree(p);
+    for (void* p : g->allocs) { comm_deregister_buffer(p); cudaFree(p); }
     pdo_padepoisson_destroy(g->poiss);
     pdo_pade6stagg_destroy(g->ops);
     pdo_spectral_destroy(g->spE);

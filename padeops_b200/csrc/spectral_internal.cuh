@@ -7,6 +7,10 @@
 namespace pdo {
 // dir: 0 x->y, 1 y->x, 2 y->z, 3 z->y; w = doubles per element (1 real, 2 complex)
 int decomp_transpose_device(pdo_decomp_t h, int dir, const double* src, double* dst, int w, cudaStream_t st);
+// Collective (all ranks, same order): makes a device buffer writable by peer GPUs so that transposes INTO it take the
+// fused NVLink path.  No-op on one rank or when peer access is unavailable.
+void comm_register_buffer_quiet(void* p, size_t bytes);
+void comm_deregister_buffer(void* p);  // local; call before freeing a registered buffer
 int fft3d_forward_xy(pdo_fft3d_t f, const double* in_real_x, double2* out_cplx_y, cudaStream_t st);
 int fft3d_backward_yx(pdo_fft3d_t f, const double2* in_cplx_y, double* out_real_x, bool set_oddball, cudaStream_t st);
 int fft3d_z_inplace(pdo_fft3d_t f, double2* a_cplx_z, int dir, cudaStream_t st);

@@ -86,6 +86,17 @@ class decomp_2d:
         cls.main = None
 
     @staticmethod
+    def register(t):
+        """Collective: make tensor `t` (device) a legal destination of the fused NVLink transposes."""
+        check(lib().pdo_comm_register_buffer(C.c_void_p(t.data_ptr()), t.numel() * t.element_size()))
+        return t
+
+    @staticmethod
+    def deregister(t):
+        """Local: must be called before a registered tensor is freed."""
+        check(lib().pdo_comm_deregister_buffer(C.c_void_p(t.data_ptr())))
+
+    @staticmethod
     def p_maxval(x):
         out = C.c_double(0.0)
         check(lib().pdo_p_maxval(float(x), C.byref(out)))

@@ -46,6 +46,31 @@ def main():
                     got = fn(torch.from_numpy(pens[s][rank]).cuda(), None, gp).cpu().numpy()
                     ok(got.shape == ref.shape and np.array_equal(got, ref), f"transpose {s}->{t} grid {pr}x{pc} {nx}x{ny}x{nz} cplx={cplx}")
                     ok(np.array_equal(ref, pens[t][rank]), "oracle self-consistency")
+    # the same transposes into REGISTERED destinations: fused pack + NVLink store + unpack path (decomp.cu: box_push_kernel)
+    p2p = bool(pdo.lib().pdo_comm_p2p_enabled())
+    print(f"[rank {rank}] p2p enabled: {p2p}", flush=True)
+    for (pr, pc) in grids:
+        for (nx, ny, nz) in [(16, 12, 8), (17, 9, 11), (33, 16, 10), (128, 96, 80)]:
+            if min(nx, ny) < pr or min(ny, nz) < pc:
+                continue
+            gp = pdo.decomp_info(nx, ny, nz, pr, pc)
+            for cplx in (False, True):
+                rng = np.random.default_rng(7)
+                G = rng.standard_normal((nz, ny, nx))
+                if cplx:
+                    G = G + 1j * rng.standard_normal((nz, ny, nx))
+                pens = {p: O.scatter_global(G, nx, ny, nz, pr, pc, p) for p in "xyz"}
+                dt = torch.complex128 if cplx else torch.float64
+                dsts = {p: pdo.decomp_2d.register(torch.zeros(tuple(reversed(getattr(gp, p + "sz"))), dtype=dt, device="cuda")) for p in "xyz"}
+                for rep in range(2):  # twice: epochs / flag reuse
+                    for s_, t_, fn in (("x", "y", dc.transpose_x_to_y), ("y", "x", dc.transpose_y_to_x), ("y", "z", dc.transpose_y_to_z),
+                                       ("z", "y", dc.transpose_z_to_y)):
+                        dsts[t_].zero_()
+                        fn(torch.from_numpy(pens[s_][rank]).cuda(), dsts[t_], gp)
+                        ok(np.array_equal(dsts[t_].cpu().numpy(), pens[t_][rank]), f"p2p transpose {s_}->{t_} grid {pr}x{pc} {nx}x{ny}x{nz} cplx={cplx}")
+                for t_ in dsts.values():
+                    pdo.decomp_2d.deregister(t_)  # before the tensors are freed
+            gp.destroy()
     # distributed derivative choreography (tests/test_derivatives_parallel.F90:94-126) on 64^3
     n = 64
     d = 2 * np.pi / n
@@ -98,6 +123,29 @@ def main():
                 po.poisson_solve(rin, out)
                 rr = O.scatter_global(ref, nx, ny, nz, pr, pc, pen)[rank]
                 ok(np.abs(out.cpu().numpy() - rr).max() < 1e-12 * np.abs(ref).max(), f"poisson dir {dir_id} grid {pr}x{pc} {nx}x{ny}x{nz}")
+    # igrid periodic substep on decomposed fields: one TVD-RK3 step against the single-rank oracle
+    from oracle import igrid_oracle as IG
+    nx, ny, nz = 16, 16, 16
+    rng = np.random.default_rng(11)
+    U, V = rng.standard_normal((nz, ny, nx)), rng.standard_normal((nz, ny, nx))
+    W = rng.standard_normal((nz + 1, ny, nx))
+    W[nz] = W[0]
+    Lbox = (2 * np.pi,) * 3
+    ref = IG.IGrid(nx, ny, nz, *Lbox, 80.0, U, V, W, TimeSteppingScheme=1)
+    ref.timeAdvance(0.01)
+    for (pr, pc) in grids:
+        if min(nx // 2 + 1, ny) < pr or min(ny, nz) < pc:
+            continue
+        loc = [O.scatter_global(A, nx, ny, n3, pr, pc, "x")[rank] for A, n3 in ((U, nz), (V, nz), (W, nz + 1))]
+        g = pdo.igrid()
+        g.init(nx, ny, nz, *Lbox, 80.0, *loc, TimeSteppingScheme=1, prow=pr, pcol=pc)
+        g.timeAdvance(0.01)
+        for nm, n3 in (("u", nz), ("v", nz), ("w", nz + 1), ("wC", nz)):
+            rr = O.scatter_global(getattr(ref, nm), nx, ny, n3, pr, pc, "x")[rank]
+            got = g.get(nm)
+            ok(got.shape == rr.shape and np.abs(got - rr).max() < 5e-12 * np.abs(getattr(ref, nm)).max(), f"igrid {nm} grid {pr}x{pc}")
+        ok(g.maxDivergence() < 1e-11, f"igrid divergence grid {pr}x{pc}")
+        g.destroy()
     # reductions (utilities/reductions.F90)
     ok(pdo.decomp_2d.p_maxval(float(rank)) == float(world - 1), "p_maxval")
     ok(pdo.decomp_2d.p_sum(1.0) == float(world), "p_sum")
