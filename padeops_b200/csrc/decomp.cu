@@ -242,7 +242,12 @@ __global__ void __launch_bounds__(256) box_push_kernel(const double* __restrict_
         const int j = (int)(row - k * c.b2);
         const T* sr = s + (j * c.s_ld2 + k * c.s_ld3) / V;
         T* dr = d + (j * c.d_ld2 + k * c.d_ld3) / V;
-        for (int i = threadIdx.x; i < b1v; i += blockDim.x) dr[i] = sr[i];
+        int i = threadIdx.x;
+        for (; i + 3 * (int)blockDim.x < b1v; i += 4 * blockDim.x) {  // four independent loads in flight per thread
+            const T v0 = sr[i], v1 = sr[i + blockDim.x], v2 = sr[i + 2 * blockDim.x], v3 = sr[i + 3 * blockDim.x];
+            dr[i] = v0; dr[i + blockDim.x] = v1; dr[i + 2 * blockDim.x] = v2; dr[i + 3 * blockDim.x] = v3;
+        }
+        for (; i < b1v; i += blockDim.x) dr[i] = sr[i];
     }
     __threadfence_system();
     __syncthreads();
@@ -253,6 +258,25 @@ __global__ void __launch_bounds__(256) box_push_kernel(const double* __restrict_
             __threadfence_system();
             for (int t = 0; t < b.npeers; ++t) flag_store(b.peer_flags[t] + b.nproc + b.me, b.epoch);
         }
+    }
+}
+
+// copy-engine variant: the data moves with cudaMemcpy2D/3DAsync; these two kernels are the handshakes around it
+__global__ void box_entry_kernel(const __grid_constant__ PushBatch b) {
+    const int tid = threadIdx.x;
+    if (tid < b.npeers) {
+        flag_store(b.peer_flags[tid] + b.me, b.epoch);
+        const unsigned long long* f = b.my_flags + b.peer_rank[tid];
+        while (flag_load(f) < b.epoch) { }
+    }
+}
+__global__ void box_exit_kernel(const __grid_constant__ PushBatch b) {
+    const int tid = threadIdx.x;
+    if (tid < b.npeers) {
+        __threadfence_system();
+        flag_store(b.peer_flags[tid] + b.nproc + b.me, b.epoch);
+        const unsigned long long* f = b.my_flags + b.nproc + b.peer_rank[tid];
+        while (flag_load(f) < b.epoch) { }
     }
 }
 
@@ -269,6 +293,9 @@ __global__ void box_wait_kernel(const __grid_constant__ PushBatch b) {
 struct pdo_decomp_s {
     int nx, ny, nz, p_row, p_col, c1, c2;
     unsigned int* push_counter = nullptr;
+    cudaStream_t ce_stream[kMaxPeers] = {};   // copy-engine variant of the fused path: one stream per peer
+    cudaEvent_t ce_fork = nullptr, ce_join[kMaxPeers] = {};
+    bool ce_ready = false;
     pdo_decomp_info info;
     std::vector<int> x1dist, y1dist, y2dist, z2dist;
     double* work_send = nullptr;
@@ -359,6 +386,53 @@ int transpose_device(pdo_decomp_s* d, int dir, const double* src, double* dst, i
                     b.peer_rank[b.npeers] = pw;
                     b.npeers++;
                 }
+            }
+            static int p2p_mode = -1;  // PDO_P2P_MODE = sm (store kernel) | ce (copy engines, SMs stay free); default ce for large blocks
+            if (p2p_mode < 0) {
+                const char* e = std::getenv("PDO_P2P_MODE");
+                p2p_mode = (e && std::strcmp(e, "sm") == 0) ? 1 : ((e && std::strcmp(e, "ce") == 0) ? 2 : 0);
+            }
+            const long long box_bytes = (long long)b.c[me == 0 ? np - 1 : 0].b1 * b.c[me == 0 ? np - 1 : 0].b2 * b.c[me == 0 ? np - 1 : 0].b3 * 8;
+            const bool use_ce = (p2p_mode == 2) || (p2p_mode == 0 && box_bytes >= (4LL << 20));
+            if (use_ce) {
+                if (!d->ce_ready) {
+                    for (int m = 0; m < kMaxPeers; ++m) {
+                        PDO_CUDA(cudaStreamCreateWithFlags(&d->ce_stream[m], cudaStreamNonBlocking));
+                        PDO_CUDA(cudaEventCreateWithFlags(&d->ce_join[m], cudaEventDisableTiming));
+                    }
+                    PDO_CUDA(cudaEventCreateWithFlags(&d->ce_fork, cudaEventDisableTiming));
+                    d->ce_ready = true;
+                }
+                box_entry_kernel<<<1, 32, 0, st>>>(b);
+                PDO_CUDA(cudaGetLastError());
+                PDO_CUDA(cudaEventRecord(d->ce_fork, st));
+                for (int q = 0; q < np; ++q) {
+                    const int m = (me + 1 + q) % np;  // start with my right neighbour: spreads the ingress over the destinations
+                    const BoxCopy& c = b.c[m];
+                    if (c.b1 <= 0 || c.b2 <= 0 || c.b3 <= 0) continue;
+                    cudaStream_t cs = d->ce_stream[m];
+                    PDO_CUDA(cudaStreamWaitEvent(cs, d->ce_fork, 0));
+                    const double* sp = src + c.src_off;
+                    double* dp = b.dst[m] + c.dst_off;
+                    if (c.b1 == c.s_ld2 && c.b1 == c.d_ld2) {  // rows are contiguous on both sides: (i, j) collapse into wide rows
+                        PDO_CUDA(cudaMemcpy2DAsync(dp, (size_t)c.d_ld3 * 8, sp, (size_t)c.s_ld3 * 8, (size_t)c.b1 * c.b2 * 8, (size_t)c.b3,
+                                                   cudaMemcpyDeviceToDevice, cs));
+                    } else {
+                        cudaMemcpy3DParms pr;
+                        std::memset(&pr, 0, sizeof(pr));
+                        pr.srcPtr = make_cudaPitchedPtr((void*)sp, (size_t)c.s_ld2 * 8, (size_t)c.s_ld2, (size_t)(c.s_ld3 / c.s_ld2));
+                        pr.dstPtr = make_cudaPitchedPtr((void*)dp, (size_t)c.d_ld2 * 8, (size_t)c.d_ld2, (size_t)(c.d_ld3 / c.d_ld2));
+                        pr.extent = make_cudaExtent((size_t)c.b1 * 8, (size_t)c.b2, (size_t)c.b3);
+                        pr.kind = cudaMemcpyDeviceToDevice;
+                        PDO_CUDA(cudaMemcpy3DAsync(&pr, cs));
+                    }
+                    PDO_CUDA(cudaEventRecord(d->ce_join[m], cs));
+                    PDO_CUDA(cudaStreamWaitEvent(st, d->ce_join[m], 0));
+                }
+                box_exit_kernel<<<1, 32, 0, st>>>(b);
+                PDO_CUDA(cudaGetLastError());
+                g_launches += 2;
+                return 0;
             }
             const int tx = (min_b1 / (vec ? 2 : 1)) >= 128 ? 128 : ((min_b1 / (vec ? 2 : 1)) >= 64 ? 64 : 32);
             dim3 block(tx, 256 / tx);
@@ -567,6 +641,10 @@ int pdo_decomp_destroy(pdo_decomp_t h) {
     if (h->work_send) cudaFree(h->work_send);
     if (h->work_recv) cudaFree(h->work_recv);
     if (h->push_counter) cudaFree(h->push_counter);
+    if (h->ce_ready) {
+        for (int m = 0; m < kMaxPeers; ++m) { cudaStreamDestroy(h->ce_stream[m]); cudaEventDestroy(h->ce_join[m]); }
+        cudaEventDestroy(h->ce_fork);
+    }
     delete h;
     return 0;
 }
