@@ -103,18 +103,19 @@ struct pdo_spectral_s {
 
 namespace {
 
-int spectral_mtimes(pdo_spectral_s* s, int which, const double2* fin, double2* fout, cudaStream_t st) {
+// fout = i k fin (* scale: lets a caller fold the inverse transform's 1/(nx ny) into this pass)
+int spectral_mtimes(pdo_spectral_s* s, int which, const double2* fin, double2* fout, cudaStream_t st, double scale = 1.0) {
     const int n1 = s->si.ysz[0], n2 = s->si.ysz[1];
     const long long n = vol(s->si.ysz);
     const double* k = which == 1 ? s->k1y : s->k2;
     if (which == 1)
         return launch_ew(n, st, [=] __device__(long long i) {
-            const double kv = k[(int)(i % n1)];
+            const double kv = k[(int)(i % n1)] * scale;
             const double2 v = fin[i];
             fout[i] = make_double2(-kv * v.y, kv * v.x);
         });
     return launch_ew(n, st, [=] __device__(long long i) {
-        const double kv = k[(int)((i / n1) % n2)];
+        const double kv = k[(int)((i / n1) % n2)] * scale;
         const double2 v = fin[i];
         fout[i] = make_double2(-kv * v.y, kv * v.x);
     });
@@ -393,6 +394,8 @@ struct pdo_padepoisson_s {
     double mfact = 1.0;
     double2 *f2d = nullptr, *f2dy = nullptr, *w2 = nullptr, *uhatInZ = nullptr, *dwdz = nullptr;
     double* div_tmp = nullptr;  // real x-pencil, used when the caller passes no divergence array
+    bool alias = false;         // one rank in the column communicator: y- and z-pencil layouts coincide, transposes are skipped
+    const double2* phat_y = nullptr;  // where the last projection left the pressure (y-pencil layout)
 };
 
 namespace {
@@ -413,12 +416,15 @@ int poiss_div_xy(pdo_padepoisson_s* p, const double2* u, const double2* v, doubl
 // steps shared by PeriodicProjection / Periodic_getPressure*: leaves phat in f2d (z-pencil) and what in w2 (z-pencil)
 int poiss_solve(pdo_padepoisson_s* p, const double2* uhat, const double2* vhat, const double2* what, cudaStream_t st) {
     if (int rc = poiss_div_xy(p, uhat, vhat, p->f2dy, st)) return rc;
-    if (int rc = decomp_transpose_device(p->dC, 2, (const double*)p->f2dy, (double*)p->uhatInZ, 2, st)) return rc;
-    if (int rc = decomp_transpose_device(p->dE, 2, (const double*)what, (double*)p->w2, 2, st)) return rc;
-    if (int rc = pdo_pade6stagg_ddz_E2C(p->derivZ, (const double*)p->w2, (double*)p->f2d, 1, 0, 0, st)) return rc;
+    const double2 *uz = p->f2dy, *wz = what;
+    if (!p->alias) {
+        if (int rc = decomp_transpose_device(p->dC, 2, (const double*)p->f2dy, (double*)p->uhatInZ, 2, st)) return rc;
+        if (int rc = decomp_transpose_device(p->dE, 2, (const double*)what, (double*)p->w2, 2, st)) return rc;
+        uz = p->uhatInZ; wz = p->w2;
+    }
+    if (int rc = pdo_pade6stagg_ddz_E2C(p->derivZ, (const double*)wz, (double*)p->f2d, 1, 0, 0, st)) return rc;
     const long long n = vol(p->sC.zsz);
     double2* f2d = p->f2d;
-    const double2* uz = p->uhatInZ;
     if (int rc = launch_ew(n, st, [=] __device__(long long i) { double2 a = f2d[i]; const double2 b = uz[i]; a.x += b.x; a.y += b.y; f2d[i] = a; })) return rc;
     if (int rc = fft3d_z_inplace(p->sp->ft, f2d, -1, st)) return rc;
     const int n1 = p->sC.zsz[0], n2 = p->sC.zsz[1];
@@ -440,15 +446,19 @@ int poiss_solve(pdo_padepoisson_s* p, const double2* uhat, const double2* vhat, 
 // w2 -= ddz_C2E(f2d); what <- w2; f2dy <- f2d; u -= i k1 p, v -= i k2 p   (:417-431)
 int poiss_correct(pdo_padepoisson_s* p, double2* uhat, double2* vhat, double2* what, cudaStream_t st) {
     if (int rc = pdo_pade6stagg_ddz_C2E(p->derivZ, (const double*)p->f2d, (double*)p->dwdz, 1, 0, 0, st)) return rc;
-    double2* w2 = p->w2;
+    double2* w2 = p->alias ? what : p->w2;
     const double2* dw = p->dwdz;
     if (int rc = launch_ew(vol(p->sE.zsz), st, [=] __device__(long long i) { double2 a = w2[i]; const double2 b = dw[i]; a.x -= b.x; a.y -= b.y; w2[i] = a; })) return rc;
-    if (int rc = decomp_transpose_device(p->dE, 3, (const double*)p->w2, (double*)what, 2, st)) return rc;
-    if (int rc = decomp_transpose_device(p->dC, 3, (const double*)p->f2d, (double*)p->f2dy, 2, st)) return rc;
+    const double2* ph = p->f2d;
+    if (!p->alias) {
+        if (int rc = decomp_transpose_device(p->dE, 3, (const double*)p->w2, (double*)what, 2, st)) return rc;
+        if (int rc = decomp_transpose_device(p->dC, 3, (const double*)p->f2d, (double*)p->f2dy, 2, st)) return rc;
+        ph = p->f2dy;
+    }
+    p->phat_y = ph;
     const pdo_spectral_s* s = p->sp;
     const int n1 = s->si.ysz[0], n2 = s->si.ysz[1];
     const double *k1 = s->k1y, *k2 = s->k2;
-    const double2* ph = p->f2dy;
     return launch_ew(vol(s->si.ysz), st, [=] __device__(long long i) {
         const double a = k1[(int)(i % n1)], b = k2[(int)((i / n1) % n2)];
         const double2 q = ph[i];
@@ -460,13 +470,20 @@ int poiss_correct(pdo_padepoisson_s* p, double2* uhat, double2* vhat, double2* w
 }
 
 int poiss_divergence(pdo_padepoisson_s* p, const double2* uhat, const double2* vhat, const double2* what, double* div, cudaStream_t st) {
-    if (int rc = decomp_transpose_device(p->dE, 2, (const double*)what, (double*)p->w2, 2, st)) return rc;
-    if (int rc = pdo_pade6stagg_ddz_E2C(p->derivZ, (const double*)p->w2, (double*)p->f2d, 1, -1, -1, st)) return rc;
-    if (int rc = decomp_transpose_device(p->dC, 3, (const double*)p->f2d, (double*)p->f2dy, 2, st)) return rc;
+    const double2* wz = what;
+    if (!p->alias) {
+        if (int rc = decomp_transpose_device(p->dE, 2, (const double*)what, (double*)p->w2, 2, st)) return rc;
+        wz = p->w2;
+    }
+    if (int rc = pdo_pade6stagg_ddz_E2C(p->derivZ, (const double*)wz, (double*)p->f2d, 1, -1, -1, st)) return rc;
+    double2* f = p->f2d;
+    if (!p->alias) {
+        if (int rc = decomp_transpose_device(p->dC, 3, (const double*)p->f2d, (double*)p->f2dy, 2, st)) return rc;
+        f = p->f2dy;
+    }
     const pdo_spectral_s* s = p->sp;
     const int n1 = s->si.ysz[0], n2 = s->si.ysz[1];
     const double *k1 = s->k1y, *k2 = s->k2;
-    double2* f = p->f2dy;
     if (int rc = launch_ew(vol(s->si.ysz), st, [=] __device__(long long i) {  // + i k1 u + i k2 v  (:1191-1200)
             const double a = k1[(int)(i % n1)], b = k2[(int)((i / n1) % n2)];
             const double2 uu = uhat[i], vv = vhat[i];
@@ -475,7 +492,7 @@ int poiss_divergence(pdo_padepoisson_s* p, const double2* uhat, const double2* v
             q.y += a * uu.x + b * vv.x;
             f[i] = q;
         })) return rc;
-    return fft3d_backward_yx(s->ft, p->f2dy, div, false, st);
+    return fft3d_backward_yx(s->ft, f, div, false, st);
 }
 
 // p_maxval(maxval(a)) (use_abs = 0, as DivergenceCheck does) or of |a|
@@ -541,6 +558,7 @@ int pdo_padepoisson_init(pdo_padepoisson_t* h, double dx, double dy, double dz, 
     if (!rc) rc = upload(&p->k2sq, k2, p->sC.zst[1] - 1, p->sC.zsz[1]);
     if (!rc) rc = upload(&p->k3sq, k3m, 0, nz);
     p->mfact = 1.0 / (double)nz;
+    p->alias = (sp->p_col == 1);
     cudaError_t e = cudaSuccess;
     if (!rc) {
         e = cudaMalloc(&p->f2d, sizeof(double2) * (size_t)vol(p->sC.zsz));
@@ -616,10 +634,14 @@ int pdo_padepoisson_get_pressure(pdo_padepoisson_t p, const double* uhat, const 
     cudaStream_t st = (cudaStream_t)stream;
     return with_uvw(p, uhat, vhat, what, false, st, [&](double2* u, double2* v, double2* w) -> int {
         if (int rc = poiss_solve(p, u, v, w, st)) return rc;
-        if (int rc = decomp_transpose_device(p->dC, 3, (const double*)p->f2d, (double*)p->f2dy, 2, st)) return rc;
+        const double2* ph = p->f2d;
+        if (!p->alias) {
+            if (int rc = decomp_transpose_device(p->dC, 3, (const double*)p->f2d, (double*)p->f2dy, 2, st)) return rc;
+            ph = p->f2dy;
+        }
         const size_t bytes = sizeof(double) * (size_t)vol(p->sp->pi.xsz);
         return with_device_views(pressure, 0, pressure, bytes, st, [&](const void*, void* d_o) {
-            return fft3d_backward_yx(p->sp->ft, p->f2dy, (double*)d_o, false, st);
+            return fft3d_backward_yx(p->sp->ft, ph, (double*)d_o, false, st);
         });
     });
 }
@@ -629,10 +651,10 @@ int pdo_padepoisson_get_pressure_and_update_rhs(pdo_padepoisson_t p, double* uha
     if (!p || !uhat || !vhat || !what || !pressure) return fail(PDO_E_BADARG, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     return with_uvw(p, uhat, vhat, what, true, st, [&](double2* u, double2* v, double2* w) -> int {
-        if (int rc = poiss_projection(p, u, v, w, st)) return rc;  // leaves phat in f2dy
+        if (int rc = poiss_projection(p, u, v, w, st)) return rc;  // leaves phat at phat_y
         const size_t bytes = sizeof(double) * (size_t)vol(p->sp->pi.xsz);
         return with_device_views(pressure, 0, pressure, bytes, st, [&](const void*, void* d_o) {
-            return fft3d_backward_yx(p->sp->ft, p->f2dy, (double*)d_o, false, st);
+            return fft3d_backward_yx(p->sp->ft, p->phat_y, (double*)d_o, false, st);
         });
     });
 }
@@ -666,6 +688,7 @@ struct pdo_igrid_s {
     long long nRC, nRE, nYC, nYE, nZC, nZE;   // element counts: real x-pencils, complex y- and z-pencils
     int step = 0;
     double tsim = 0.0, dt = 0.0;
+    bool alias = false;  // p_col == 1: y- and z-pencil layouts coincide
     std::vector<void*> allocs;
     // physical fields
     double *u, *v, *wC, *w, *uE, *vE, *divergence;
@@ -697,10 +720,27 @@ inline int fftC(pdo_igrid_s* g, const double* in, double2* out, cudaStream_t st)
 inline int fftE(pdo_igrid_s* g, const double* in, double2* out, cudaStream_t st) { return fft3d_forward_xy(g->spE->ft, in, out, st); }
 inline int ifftC(pdo_igrid_s* g, const double2* in, double* out, cudaStream_t st) { return fft3d_backward_yx(g->spC->ft, in, out, false, st); }
 inline int ifftE(pdo_igrid_s* g, const double2* in, double* out, cudaStream_t st) { return fft3d_backward_yx(g->spE->ft, in, out, false, st); }
+// When the column communicator has one rank the y- and z-pencils of a spectral array are the same memory layout, so a
+// "transpose" is the identity: z-operators then read the y-pencil array directly (zview*) and write straight into the
+// y-pencil destination (ztarget* / zcommit*) instead of paying two device copies per visit to z.
 inline int y2zC(pdo_igrid_s* g, const double2* s, double2* d, cudaStream_t st) { return decomp_transpose_device(g->dC, 2, (const double*)s, (double*)d, 2, st); }
 inline int z2yC(pdo_igrid_s* g, const double2* s, double2* d, cudaStream_t st) { return decomp_transpose_device(g->dC, 3, (const double*)s, (double*)d, 2, st); }
 inline int y2zE(pdo_igrid_s* g, const double2* s, double2* d, cudaStream_t st) { return decomp_transpose_device(g->dE, 2, (const double*)s, (double*)d, 2, st); }
 inline int z2yE(pdo_igrid_s* g, const double2* s, double2* d, cudaStream_t st) { return decomp_transpose_device(g->dE, 3, (const double*)s, (double*)d, 2, st); }
+
+inline int zviewC(pdo_igrid_s* g, const double2* s, double2* buf, const double2** out, cudaStream_t st) {
+    if (g->alias) { *out = s; return 0; }
+    *out = buf;
+    return y2zC(g, s, buf, st);
+}
+inline int zviewE(pdo_igrid_s* g, const double2* s, double2* buf, const double2** out, cudaStream_t st) {
+    if (g->alias) { *out = s; return 0; }
+    *out = buf;
+    return y2zE(g, s, buf, st);
+}
+inline double2* ztarget(pdo_igrid_s* g, double2* ydst, double2* buf) { return g->alias ? ydst : buf; }
+inline int zcommitC(pdo_igrid_s* g, const double2* z, double2* ydst, cudaStream_t st) { return g->alias ? 0 : z2yC(g, z, ydst, st); }
+inline int zcommitE(pdo_igrid_s* g, const double2* z, double2* ydst, cudaStream_t st) { return g->alias ? 0 : z2yE(g, z, ydst, st); }
 
 #define IG(expr) do { if (int _rc = (expr)) return _rc; } while (0)
 #define ZOP(fn, in, out) IG(fn(g->ops, (const double*)(in), (double*)(out), 1, 0, 0, st))
@@ -745,40 +785,47 @@ int lincomb(double2* out, const Lin5& L, long long ncplx, cudaStream_t st) {
 int ig_dealias_fields(pdo_igrid_s* g, cudaStream_t st) {
     IG(spectral_dealias(g->spC, g->cur[0], st));
     IG(spectral_dealias(g->spC, g->cur[1], st));
-    IG(y2zE(g, g->cur[2], g->zE[0], st));
-    IG(spectral_dealias_edge(g->spC, g->zE[0], st));
-    return z2yE(g, g->zE[0], g->cur[2], st);
+    double2* we = ztarget(g, g->cur[2], g->zE[0]);
+    if (!g->alias) IG(y2zE(g, g->cur[2], we, st));
+    IG(spectral_dealias_edge(g->spC, we, st));
+    return zcommitE(g, we, g->cur[2], st);
 }
 
 // ---- igrid.F90:1423-1447
 int ig_interp_primitive(pdo_igrid_s* g, cudaStream_t st) {
-    IG(y2zE(g, g->cur[2], g->zE[0], st));
-    ZOP(pdo_pade6stagg_interpz_E2C, g->zE[0], g->zC[0]);
-    IG(z2yC(g, g->zC[0], g->whatC, st));
+    const double2* z = nullptr;
+    IG(zviewE(g, g->cur[2], g->zE[0], &z, st));
+    double2* t = ztarget(g, g->whatC, g->zC[0]);
+    ZOP(pdo_pade6stagg_interpz_E2C, z, t);
+    IG(zcommitC(g, t, g->whatC, st));
     IG(ifftC(g, g->whatC, g->wC, st));
-    IG(y2zC(g, g->cur[0], g->zC[0], st));
-    ZOP(pdo_pade6stagg_interpz_C2E, g->zC[0], g->zE[0]);
-    IG(z2yE(g, g->zE[0], g->uEhat, st));
-    IG(ifftE(g, g->uEhat, g->uE, st));
-    IG(y2zC(g, g->cur[1], g->zC[0], st));
-    ZOP(pdo_pade6stagg_interpz_C2E, g->zC[0], g->zE[0]);
-    IG(z2yE(g, g->zE[0], g->vEhat, st));
-    return ifftE(g, g->vEhat, g->vE, st);
+    for (int c = 0; c < 2; ++c) {
+        double2* eh = c == 0 ? g->uEhat : g->vEhat;
+        IG(zviewC(g, g->cur[c], g->zC[0], &z, st));
+        t = ztarget(g, eh, g->zE[0]);
+        ZOP(pdo_pade6stagg_interpz_C2E, z, t);
+        IG(zcommitE(g, t, eh, st));
+        IG(ifftE(g, eh, c == 0 ? g->uE : g->vE, st));
+    }
+    return 0;
 }
 
 // ---- igrid.F90:2553-2683.  Slots: 0 dudx 1 dudy 2 dudz 3 dvdx 4 dvdy 5 dvdz 6 dwdx 7 dwdy 8 dwdz (C: cell values, E: edge values)
 int ig_compute_duidxj(pdo_igrid_s* g, cudaStream_t st) {
     pdo_spectral_s *C = g->spC, *E = g->spE;
     const bool visc = !g->prm.is_inviscid;
+    // i k f goes into a scratch array that nobody reads again: the 1/(nx ny) of the inverse is folded into that pass and
+    // the inverse transform consumes the scratch directly (no intent(in) staging copy)
+    const double nf2 = 1.0 / ((double)g->prm.nx * (double)g->prm.ny);
     auto dC = [&](int which, const double2* fhat, double* out) -> int {
         if (!out) return 0;
-        IG(spectral_mtimes(C, which, fhat, g->yC[0], st));
-        return ifftC(g, g->yC[0], out, st);
+        IG(spectral_mtimes(C, which, fhat, g->yC[0], st, nf2));
+        return fft3d_backward_yx_scratch(C->ft, g->yC[0], out, st);
     };
     auto dE = [&](int which, const double2* fhat, double* out) -> int {
         if (!out) return 0;
-        IG(spectral_mtimes(E, which, fhat, g->yE[0], st));
-        return ifftE(g, g->yE[0], out, st);
+        IG(spectral_mtimes(E, which, fhat, g->yE[0], st, nf2));
+        return fft3d_backward_yx_scratch(E->ft, g->yE[0], out, st);
     };
     IG(dC(1, g->cur[0], g->gradC[0])); IG(dE(1, g->uEhat, g->gradE[0]));
     IG(dC(2, g->cur[0], g->gradC[1])); IG(dE(2, g->uEhat, g->gradE[1]));
@@ -787,37 +834,46 @@ int ig_compute_duidxj(pdo_igrid_s* g, cudaStream_t st) {
     IG(dC(1, g->whatC, g->gradC[6])); IG(dE(1, g->cur[2], g->gradE[6]));
     IG(dC(2, g->whatC, g->gradC[7])); IG(dE(2, g->cur[2], g->gradE[7]));
     // dwdz (and its edge interpolant), d2wdz2
-    IG(y2zE(g, g->cur[2], g->zE[0], st));
-    ZOP(pdo_pade6stagg_ddz_E2C, g->zE[0], g->zC[0]);
-    IG(z2yC(g, g->zC[0], g->yC[0], st));
+    const double2* wz = nullptr;
+    IG(zviewE(g, g->cur[2], g->zE[0], &wz, st));
+    double2* dwz = ztarget(g, g->yC[0], g->zC[0]);
+    ZOP(pdo_pade6stagg_ddz_E2C, wz, dwz);
+    IG(zcommitC(g, dwz, g->yC[0], st));
     IG(ifftC(g, g->yC[0], g->gradC[8], st));
     if (g->gradE[8]) {
-        ZOP(pdo_pade6stagg_interpz_C2E, g->zC[0], g->zE[1]);
-        IG(z2yE(g, g->zE[1], g->yE[0], st));
+        double2* t = ztarget(g, g->yE[0], g->zE[1]);
+        ZOP(pdo_pade6stagg_interpz_C2E, dwz, t);
+        IG(zcommitE(g, t, g->yE[0], st));
         IG(ifftE(g, g->yE[0], g->gradE[8], st));
     }
     if (visc) {
-        ZOP(pdo_pade6stagg_d2dz2_E2E, g->zE[0], g->zE[1]);
-        IG(z2yE(g, g->zE[1], g->d2w, st));
+        double2* t = ztarget(g, g->d2w, g->zE[1]);
+        ZOP(pdo_pade6stagg_d2dz2_E2E, wz, t);
+        IG(zcommitE(g, t, g->d2w, st));
     }
     // dudz / dvdz on edges, their cell interpolants, and the viscous second derivatives
     for (int c = 0; c < 2; ++c) {
-        IG(y2zC(g, g->cur[c], g->zC[0], st));
-        ZOP(pdo_pade6stagg_ddz_C2E, g->zC[0], g->zE[0]);
-        IG(z2yE(g, g->zE[0], g->yE[0], st));
+        const double2* fz = nullptr;
+        IG(zviewC(g, g->cur[c], g->zC[0], &fz, st));
+        double2* te = ztarget(g, g->yE[0], g->zE[0]);
+        ZOP(pdo_pade6stagg_ddz_C2E, fz, te);
+        IG(zcommitE(g, te, g->yE[0], st));
         IG(ifftE(g, g->yE[0], g->gradE[2 + 3 * c], st));
         if (visc) {
+            double2* d2 = c == 0 ? g->d2u : g->d2v;
+            double2* td = ztarget(g, d2, g->zC[1]);
             if (g->prm.use_d2dz2_c2c) {
-                ZOP(pdo_pade6stagg_d2dz2_C2C, g->zC[0], g->zC[1]);
+                ZOP(pdo_pade6stagg_d2dz2_C2C, fz, td);
             } else {
-                ZOP(pdo_pade6stagg_ddz_C2E, g->zC[0], g->zE[1]);
-                ZOP(pdo_pade6stagg_ddz_E2C, g->zE[1], g->zC[1]);
+                ZOP(pdo_pade6stagg_ddz_C2E, fz, g->zE[1]);
+                ZOP(pdo_pade6stagg_ddz_E2C, g->zE[1], td);
             }
-            IG(z2yC(g, g->zC[1], c == 0 ? g->d2u : g->d2v, st));
+            IG(zcommitC(g, td, d2, st));
         }
         if (g->gradC[2 + 3 * c]) {
-            ZOP(pdo_pade6stagg_interpz_E2C, g->zE[0], g->zC[0]);
-            IG(z2yC(g, g->zC[0], g->yC[0], st));
+            double2* tc = ztarget(g, g->yC[0], g->zC[0]);
+            ZOP(pdo_pade6stagg_interpz_E2C, te, tc);
+            IG(zcommitC(g, tc, g->yC[0], st));
             IG(ifftC(g, g->yC[0], g->gradC[2 + 3 * c], st));
         }
     }
@@ -828,8 +884,10 @@ int ig_compute_duidxj(pdo_igrid_s* g, cudaStream_t st) {
 int ig_nonlinear_skew(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStream_t st) {
     pdo_spectral_s *C = g->spC, *E = g->spE;
     double *T1C = g->rbC[0], *T1E = g->rbE[0];
-    double2 *fT1C = g->yC[0], *fT1E = g->yE[0], *fT2E = g->yE[1], *tzC = g->zC[0], *tzE = g->zE[0];
+    double2 *fT1C = g->yC[0], *fT1E = g->yE[0], *fT2E = g->yE[1];
     double **GC = g->gradC, **GE = g->gradE;
+    const double2* z = nullptr;
+    double2* t = nullptr;
     // u_rhs = interp_E2C(fft(dudz w)) + fft(dudx u + dudy v); same for v
     for (int c = 0; c < 2; ++c) {
         double2* r = c == 0 ? ru : rv;
@@ -837,9 +895,10 @@ int ig_nonlinear_skew(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cud
         IG(mul2(T1E, GE[3 * c + 2], g->w, nullptr, nullptr, g->nRE, st));
         IG(fftC(g, T1C, fT1C, st));
         IG(fftE(g, T1E, fT1E, st));
-        IG(y2zE(g, fT1E, tzE, st));
-        ZOP(pdo_pade6stagg_interpz_E2C, tzE, tzC);
-        IG(z2yC(g, tzC, r, st));
+        IG(zviewE(g, fT1E, g->zE[0], &z, st));
+        t = ztarget(g, r, g->zC[0]);
+        ZOP(pdo_pade6stagg_interpz_E2C, z, t);
+        IG(zcommitC(g, t, r, st));
         IG(cadd(r, fT1C, g->nYC, st));
     }
     // w_rhs = interp_C2E(fft(dwdz wC)) + fft(dwdx uE + dwdy vE)
@@ -847,9 +906,10 @@ int ig_nonlinear_skew(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cud
     IG(fftE(g, T1E, fT2E, st));
     IG(mul2(T1C, GC[8], g->wC, nullptr, nullptr, g->nRC, st));
     IG(fftC(g, T1C, fT1C, st));
-    IG(y2zC(g, fT1C, tzC, st));
-    ZOP(pdo_pade6stagg_interpz_C2E, tzC, tzE);
-    IG(z2yE(g, tzE, rw, st));
+    IG(zviewC(g, fT1C, g->zC[0], &z, st));
+    t = ztarget(g, rw, g->zE[0]);
+    ZOP(pdo_pade6stagg_interpz_C2E, z, t);
+    IG(zcommitE(g, t, rw, st));
     IG(cadd(rw, fT2E, g->nYE, st));
     // conservative half: d(uu)/dx, d(vv)/dy, d(wC wC)/dz, d(uv)/dy & /dx, d(uE w)/dz & /dx, d(vE w)/dz & /dy
     IG(mul2(T1C, g->u, g->u, nullptr, nullptr, g->nRC, st));
@@ -860,9 +920,10 @@ int ig_nonlinear_skew(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cud
     IG(cadd_ik(C, 2, rv, fT1C, st));
     IG(mul2(T1C, g->wC, g->wC, nullptr, nullptr, g->nRC, st));
     IG(fftC(g, T1C, fT1C, st));
-    IG(y2zC(g, fT1C, tzC, st));
-    ZOP(pdo_pade6stagg_ddz_C2E, tzC, tzE);
-    IG(z2yE(g, tzE, fT1E, st));
+    IG(zviewC(g, fT1C, g->zC[0], &z, st));
+    t = ztarget(g, fT1E, g->zE[0]);
+    ZOP(pdo_pade6stagg_ddz_C2E, z, t);
+    IG(zcommitE(g, t, fT1E, st));
     IG(cadd(rw, fT1E, g->nYE, st));
     IG(mul2(T1C, g->u, g->v, nullptr, nullptr, g->nRC, st));
     IG(fftC(g, T1C, fT1C, st));
@@ -871,9 +932,10 @@ int ig_nonlinear_skew(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cud
     for (int c = 0; c < 2; ++c) {
         IG(mul2(T1E, c == 0 ? g->uE : g->vE, g->w, nullptr, nullptr, g->nRE, st));
         IG(fftE(g, T1E, fT1E, st));
-        IG(y2zE(g, fT1E, tzE, st));
-        ZOP(pdo_pade6stagg_ddz_E2C, tzE, tzC);
-        IG(z2yC(g, tzC, fT1C, st));
+        IG(zviewE(g, fT1E, g->zE[0], &z, st));
+        t = ztarget(g, fT1C, g->zC[0]);
+        ZOP(pdo_pade6stagg_ddz_E2C, z, t);
+        IG(zcommitC(g, t, fT1C, st));
         IG(cadd(c == 0 ? ru : rv, fT1C, g->nYC, st));
         IG(cadd_ik(E, c == 0 ? 1 : 2, rw, fT1E, st));
     }
@@ -1032,6 +1094,7 @@ int pdo_igrid_init(pdo_igrid_t* h, const pdo_igrid_params* p, const double* u, c
     if (!rc) rc = pdo_padepoisson_init(&g->poiss, g->dx, g->dy, g->dz, g->spC, g->spE, g->ops);
     if (rc) { pdo_igrid_destroy(g); return rc; }
     g->dC = fft3d_spec_decomp(g->spC->ft); g->dE = fft3d_spec_decomp(g->spE->ft);
+    g->alias = (g->spC->p_col == 1);
     g->nRC = vol(g->gC.xsz); g->nRE = vol(g->gE.xsz);
     g->nYC = vol(g->sC.ysz); g->nYE = vol(g->sE.ysz);
     g->nZC = vol(g->sC.zsz); g->nZE = vol(g->sE.zsz);

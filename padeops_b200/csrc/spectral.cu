@@ -199,6 +199,11 @@ int fft3d_backward_yx(pdo_fft3d_t f, const double2* in_cplx_y, double* out_real_
     g_launches += 1;
     return backward_yx(f, f->bufY, out_real_x, st);
 }
+// Same inverse for a caller-owned scratch array that already carries the 1/(nx ny) factor: it is consumed in place
+// (no staging copy).
+int fft3d_backward_yx_scratch(pdo_fft3d_t f, double2* scratch_cplx_y, double* out_real_x, cudaStream_t st) {
+    return backward_yx(f, scratch_cplx_y, out_real_x, st);
+}
 // c2c along z, in place, on a z-pencil array of the spectral decomposition (or on the first nz planes of an edge
 // field, which has the same zsz(1:2)); dir = -1 forward, +1 backward, unnormalised like FFTW.
 int fft3d_z_inplace(pdo_fft3d_t f, double2* a_cplx_z, int dir, cudaStream_t st) {

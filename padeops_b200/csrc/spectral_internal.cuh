@@ -13,6 +13,7 @@ void comm_register_buffer_quiet(void* p, size_t bytes);
 void comm_deregister_buffer(void* p);  // local; call before freeing a registered buffer
 int fft3d_forward_xy(pdo_fft3d_t f, const double* in_real_x, double2* out_cplx_y, cudaStream_t st);
 int fft3d_backward_yx(pdo_fft3d_t f, const double2* in_cplx_y, double* out_real_x, bool set_oddball, cudaStream_t st);
+int fft3d_backward_yx_scratch(pdo_fft3d_t f, double2* prescaled_scratch_cplx_y, double* out_real_x, cudaStream_t st);
 int fft3d_z_inplace(pdo_fft3d_t f, double2* a_cplx_z, int dir, cudaStream_t st);
 pdo_decomp_t fft3d_phys_decomp(pdo_fft3d_t f);
 pdo_decomp_t fft3d_spec_decomp(pdo_fft3d_t f);

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""ms per igrid time step / RK substep (BASELINE.json metric iii) on synthetic Taylor-Green + broadband fields.
+Usage: python tools/substep_bench.py [n] [scheme] [steps]   (torchrun for multi-GPU; grid 1 x N)"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import padeops_b200 as pdo
+
+
+def main():
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    scheme = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+    pdo.decomp_2d.comm_init()
+    info = pdo.decomp_info.for_rank(n, n, n, 1, world, rank)
+    infoE = pdo.decomp_info.for_rank(n, n, n + 1, 1, world, rank)
+    d = 2 * np.pi / n
+    x = torch.arange(n, device="cuda", dtype=torch.float64) * d
+    def zc(inf, edge):
+        k = torch.arange(inf["xst"][2] - 1, inf["xen"][2], device="cuda", dtype=torch.float64)
+        return (k * d) if edge else ((k + 0.5) * d)
+    X, Y = x[None, None, :], x[None, :, None]
+    ZC, ZE = zc(info, False)[:, None, None], zc(infoE, True)[:, None, None]
+    u = (torch.sin(X) * torch.cos(Y) * torch.cos(ZC)).contiguous()
+    v = (-torch.cos(X) * torch.sin(Y) * torch.cos(ZC)).contiguous()
+    w = (0.1 * torch.sin(2 * X) * torch.sin(Y) * torch.sin(ZE)).contiguous()
+    g = pdo.igrid()
+    g.init(n, n, n, 2 * np.pi, 2 * np.pi, 2 * np.pi, 1600.0, u, v, w, TimeSteppingScheme=scheme, prow=1, pcol=world)
+    dt = 0.2 * d
+    g.timeAdvance(dt)
+    torch.cuda.synchronize()
+    L = pdo.lib()
+    l0 = L.pdo_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        g.timeAdvance(dt)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    nsub = 3 if scheme == 1 else 5
+    if rank == 0:
+        print(json.dumps({"workload": f"igrid periodic {n}^3, skew-symmetric, CD06 z, viscous, {'TVD-RK3' if scheme == 1 else 'SSP-RK45'}",
+                          "n_gpus": world, "ms_per_step": round(ms, 3), "ms_per_substep": round(ms / nsub, 3),
+                          "launches_per_substep": (L.pdo_launch_count() - l0) // (steps * nsub),
+                          "Mpoints_per_s_per_substep": round(n ** 3 / (ms / nsub) / 1e3, 1), "max_div": g.maxDivergence()}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
