@@ -96,44 +96,46 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Polls NVML (SM clock + clock-event reasons) every ~2 ms from a thread while the timed region runs."""
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, dev):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.sm, self.mask, self.mx, self.err = [], 0, None, None
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(dev), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.p = None
+            import pynvml as nv
+            nv.nvmlInit()
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; map through it when set
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[dev]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else dev
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception as e:  # noqa
+            self.err = f"nvml unavailable: {e}"
+            self.t = None
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception as e:  # noqa
+                self.err = str(e)
+                return
+            time.sleep(0.002)
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.f.read().splitlines():
-            c = [x.strip() for x in ln.split(",")]
-            if len(c) < 7:
-                continue
-            try:
-                sm.append(float(c[0])); mx.append(float(c[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, c[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(self.f.name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err]}
+        self._stop.set()
+        self.t.join(timeout=2)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(v for k, v in self.BAD.items() if self.mask & k), "samples": len(sm)}
 
 
 def run_ours(args):
@@ -224,11 +226,15 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = L.pdo_launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profile_region:   # ncu --profile-from-start off: capture exactly the timed launches
+        torch.cuda.cudart().cudaProfilerStart()
     t0.record(st)
     for i in range(args.steps):
         step(i)
     t1.record(st)
     barrier()
+    if args.profile_region:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = L.pdo_launch_count() - l0
     clocks = sampler.stop() if sampler else None
     ms = t0.elapsed_time(t1)
@@ -313,6 +319,8 @@ def main():
     ap.add_argument("--e2e-n", type=int, default=0, dest="e2e_n", help="field size of the host-pointer (e2e) leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile-region", action="store_true", dest="profile_region",
+                    help="cudaProfilerStart/Stop around the timed region (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -812,6 +812,150 @@ chunk_x_kernel(const double* __restrict__ f, double* __restrict__ out, long long
 }
 
 // ------------------------------------------------------------------------------------------------
+// Contiguous (x) kernel, TMA-staged persistent pipeline ("xtma")
+//
+// One persistent CTA per SM walks tiles of L whole lines.  Every line moves HBM -> shared and shared -> HBM as ONE
+// 1-D bulk copy (cp.async.bulk, SASS UBLKCP) issued by a lane of warp 0: no thread stages data through registers.
+// Three tile buffers rotate through the states {landing, being solved, draining}; a transaction mbarrier per buffer
+// says when a tile has landed, a bulk group per issuing lane says when a drain has finished reading its buffer.
+// Lines sit in shared memory with a pitch of n+2 doubles (rows stay 16-byte aligned) and lanes of a quarter-warp
+// own the SAME chunk of 8 DIFFERENT lines (ln = tid % L), so every 128-bit shared access of a quarter-warp hits 8
+// distinct 16-byte bank groups ((n+2)/2 is odd): conflict-free without per-chunk padding, which a bulk copy could
+// not produce.  The solved chunk goes back in place (all reads of the tile precede chunk_solve's first barrier).
+// ------------------------------------------------------------------------------------------------
+constexpr int kXtBuf = 3;
+constexpr int kXTma = 1000, kXTma16 = 1016;  // x-kernel variant codes next to the CTA sizes 128 / 256
+
+__device__ __forceinline__ void mbar_wait_or_trap(unsigned mbar, unsigned parity) {
+    // bounded spin: a protocol error traps (the launch fails loudly) instead of hanging the device
+    for (unsigned spin = 0; spin < (1u << 20); ++spin) {
+        unsigned ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}" : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void* gsrc, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, unsigned smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int RK, int BW, int M, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+chunk_x_tma_kernel(const double* __restrict__ f, double* __restrict__ out, long long nlines, int n, int L, long long ntiles,
+                   const __grid_constant__ ChunkTables tab, const __grid_constant__ OpParams op) {
+    constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
+    static_assert(HL <= 4 && HR <= 4 && M % 2 == 0, "halo window is 4 doubles each side");
+    extern __shared__ __align__(16) double sm[];
+    __shared__ __align__(8) unsigned long long full_bar[kXtBuf];
+    const int P = n / M;
+    const int pitch = n + 2;
+    const size_t tile_elems = (size_t)L * pitch;
+    double* sm_g = sm + kXtBuf * tile_elems;
+    const int tid = threadIdx.x;
+    const int ln = tid % L;
+    const int pq = tid / L;
+    const bool active = pq < P;
+    const int p = active ? pq : 0;
+    const int slots = THREADS;
+    const unsigned line_bytes = (unsigned)n * (unsigned)sizeof(double);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < kXtBuf; ++b) mbar_init(smem_u32(&full_bar[b]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // warp 0 is the copy issuer: lane i moves lines i, i+32, ... of a tile
+    auto issue_load = [&](long long tile, int b) {
+        const long long line0 = tile * L;
+        const int nl = (int)min((long long)L, nlines - line0);
+        const unsigned bar = smem_u32(&full_bar[b]);
+        if (tid == 0) mbar_arrive_expect_tx(bar, (unsigned)nl * line_bytes);
+        __syncwarp();
+        for (int i = tid; i < nl; i += 32)
+            bulk_g2s(smem_u32(sm + b * tile_elems + (size_t)i * pitch), f + (line0 + i) * n, line_bytes, bar);
+    };
+
+    const long long t0 = blockIdx.x;
+    if (tid < 32) {
+        if (t0 < ntiles) issue_load(t0, 0);
+        if (t0 + gridDim.x < ntiles) issue_load(t0 + gridDim.x, 1);
+    }
+
+    int it = 0;
+    for (long long tile = t0; tile < ntiles; tile += gridDim.x, ++it) {
+        const int b = it % kXtBuf;
+        const long long line0 = tile * L;
+        const int nl = (int)min((long long)L, nlines - line0);
+        double* tb = sm + b * tile_elems;
+        mbar_wait_or_trap(smem_u32(&full_bar[b]), (unsigned)(it / kXtBuf) & 1u);
+
+        // ---- my chunk plus a 4-double window on each side, 128-bit shared loads ----
+        const double* row = tb + (size_t)ln * pitch;
+        double w[M + 8];
+        {
+            const int c0 = p * M;
+            const int cl = (p == 0) ? n - 4 : c0 - 4;
+            const int cr = (p == P - 1) ? 0 : c0 + M;
+            const double2 a0 = *reinterpret_cast<const double2*>(row + cl);
+            const double2 a1 = *reinterpret_cast<const double2*>(row + cl + 2);
+            w[0] = a0.x; w[1] = a0.y; w[2] = a1.x; w[3] = a1.y;
+#pragma unroll
+            for (int j = 0; j < M; j += 2) {
+                const double2 c = *reinterpret_cast<const double2*>(row + c0 + j);
+                w[4 + j] = c.x; w[5 + j] = c.y;
+            }
+            const double2 b0 = *reinterpret_cast<const double2*>(row + cr);
+            const double2 b1 = *reinterpret_cast<const double2*>(row + cr + 2);
+            w[M + 4] = b0.x; w[M + 5] = b0.y; w[M + 6] = b1.x; w[M + 7] = b1.y;
+        }
+        double r[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) r[i] = rhs_eval<RK>(&w[4 + i], op);
+
+        if constexpr (BW > 0) {
+            chunk_solve<BW, M>(r, tab, sm_g, slots, p, [&](int q) { return active ? q * L + ln : tid; });
+        } else {
+            __syncthreads();  // everyone has read the tile
+        }
+        if (active) {
+            double* wrow = tb + (size_t)ln * pitch + p * M;
+#pragma unroll
+            for (int j = 0; j < M; j += 2) *reinterpret_cast<double2*>(wrow + j) = make_double2(r[j], r[j + 1]);
+        }
+        fence_proxy_async_smem();  // my generic-proxy writes become visible to the bulk-copy (async) proxy
+        __syncthreads();
+        if (tid < 32) {
+            for (int i = tid; i < nl; i += 32)
+                bulk_s2g(out + (line0 + i) * n, smem_u32(tb + (size_t)i * pitch), line_bytes);
+            bulk_commit();
+            // buffer (it+2)%3 was drained by the group committed one iteration ago: wait until that one has read its
+            // shared source (the group just committed may stay in flight), then refill it with tile it+2
+            bulk_wait_read<1>();
+            __syncwarp();
+            const long long nxt = tile + 2LL * gridDim.x;
+            if (nxt < ntiles) issue_load(nxt, (it + 2) % kXtBuf);
+        }
+    }
+    if (tid < 32) bulk_wait_read<0>();  // shared memory must outlive the last drains
+}
+
+// ------------------------------------------------------------------------------------------------
 // Generic any-n kernels (tables in global memory).  f(n1, n, n3): es = n1 is the element stride along
 // the line.  Pass 1: pointwise RHS.  Pass 2: one thread per line, in place on `out`.
 // ------------------------------------------------------------------------------------------------
@@ -915,6 +1059,16 @@ cudaError_t banded_op_create(BandedOp* h, int n, int rk, int bw, double b1, doub
         }
         if (build_chunk_tables(n, M, bw, b1, b2, &h->tab) == 0) { h->M = M; break; }
     }
+    h->has_tab16 = 0;
+    if (h->M == 32 && n % 16 == 0 && n / 16 <= 512) {
+        if (bw == 0) {
+            std::memset(&h->tab16, 0, sizeof(h->tab16));
+            h->tab16.n = n; h->tab16.M = 16; h->tab16.P = n / 16;
+            h->has_tab16 = 1;
+        } else if (build_chunk_tables(n, 16, bw, b1, b2, &h->tab16) == 0) {
+            h->has_tab16 = 1;
+        }
+    }
     if (bw > 0) {
         LineTablesHost lt{};
         if (build_line_tables(n, bw, b1, b2, &lt) != 0) return cudaErrorInvalidValue;
@@ -954,13 +1108,14 @@ int strided_mode() {
     return g_strided_mode;
 }
 
-// PDO_X_THREADS = 256 | 128: CTA size of the contiguous-axis kernel
+// PDO_X_THREADS = 256 | 128: CTA size of the contiguous-axis kernel; 1000 | 1016: the TMA pipeline (own M | M=16)
 int g_x_threads = -1;
 int x_threads() {  // 0 = auto
     int& v = g_x_threads;
     if (v < 0) {
         const char* e = std::getenv("PDO_X_THREADS");
-        v = e ? (std::atoi(e) == 256 ? 256 : 128) : 0;
+        const int a = e ? std::atoi(e) : 0;
+        v = e ? ((a == 256 || a == kXTma || a == kXTma16) ? a : 128) : 0;
     }
     return v;
 }
@@ -970,6 +1125,15 @@ bool tuning_enabled() {
     static int v = -1;
     if (v < 0) {
         const char* e = std::getenv("PDO_TUNE");
+        v = (e && std::atoi(e) == 0) ? 0 : 1;
+    }
+    return v != 0;
+}
+// PDO_XTMA=0 keeps the TMA x kernels out of the planner's candidate list
+bool xtma_in_planner() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("PDO_XTMA");
         v = (e && std::atoi(e) == 0) ? 0 : 1;
     }
     return v != 0;
@@ -996,11 +1160,43 @@ cudaError_t launch_x(const BandedOp* h, const double* f, double* out, long long 
     return cudaGetLastError();
 }
 
+// TMA-staged persistent x kernel.  `tab` is the chunk table for this M (the operator's own, or its M=16 alternate).
+template <int RK, int BW, int M, int THREADS>
+cudaError_t launch_xtma(const BandedOp* h, const ChunkTables& tab, const double* f, double* out, long long nlines, cudaStream_t st) {
+    static bool attr_done = false;
+    const int n = h->n, P = n / M;
+    if (n % M != 0 || P < 1 || P > THREADS) return cudaErrorInvalidConfiguration;
+    if (((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return cudaErrorInvalidConfiguration;
+    const int L = THREADS / P;
+    const size_t smem = sizeof(double) * ((size_t)kXtBuf * L * (n + 2) + 3 * (BW > 0 ? BW : 1) * (size_t)THREADS);
+    constexpr size_t cap = 227 * 1024 - 64;
+    if (smem > cap) return cudaErrorInvalidConfiguration;
+    auto kern = chunk_x_tma_kernel<RK, BW, M, THREADS>;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const long long ntiles = (nlines + L - 1) / L;
+    const long long grid = ntiles < 148 ? ntiles : 148;
+    kern<<<(unsigned)grid, THREADS, smem, st>>>(f, out, nlines, n, L, ntiles, tab, h->op);
+    return cudaGetLastError();
+}
+
 template <int RK, int BW, int M>
 cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3,
                          long long in_slab, long long out_slab, cudaStream_t st, int mode, int xth) {
     const int n = h->n, P = n / M;
     if (axis == 0) {
+        if (xth == kXTma) {  // TMA pipeline on the operator's own chunk length
+            if constexpr (M == 32) { g_last_variant = kXTma; return launch_xtma<RK, BW, 32, 256>(h, h->tab, f, out, n3, st); }
+            else if constexpr (M == 16) { g_last_variant = kXTma; return launch_xtma<RK, BW, 16, 512>(h, h->tab, f, out, n3, st); }
+            else return cudaErrorInvalidConfiguration;
+        }
+        if (xth == kXTma16) {  // TMA pipeline on 16-point chunks (twice the threads per tile byte)
+            if (M == 32 && h->has_tab16) { g_last_variant = kXTma16; return launch_xtma<RK, BW, 16, 512>(h, h->tab16, f, out, n3, st); }
+            return cudaErrorInvalidConfiguration;
+        }
         if (xth != 256 && P <= 128) { g_last_variant = 128; return launch_x<RK, BW, M, 128>(h, f, out, n3, st); }
         g_last_variant = 256;
         return launch_x<RK, BW, M, 256>(h, f, out, n3, st);
@@ -1138,10 +1334,10 @@ cudaError_t launch_planned(const BandedOp* h, int axis, const double* f, double*
         cudaGetLastError();
         return launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, 0, 0);
     }
-    const int cand_x[2] = {128, 256};
+    const int cand_x[4] = {128, 256, kXTma, kXTma16};
     const int cand_s[4] = {6, 5, 3, 1};  // pipe1, cpipe, cluster / streaming, t512
     const int* cand = axis == 0 ? cand_x : cand_s;
-    const int ncand = axis == 0 ? 2 : 4;
+    const int ncand = axis == 0 ? (xtma_in_planner() ? 4 : 2) : 4;
     cudaEvent_t e0, e1;
     if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
         cudaGetLastError();

@@ -30,6 +30,8 @@ struct BandedOp {
     OpParams op{};
     int M = 0;   // chunk length of the fast path; 0 → generic any-n kernels
     ChunkTables tab{};
+    ChunkTables tab16{};  // the same matrix cut into 16-point chunks, for the TMA x kernel (valid when has_tab16)
+    int has_tab16 = 0;
     double* d_line = nullptr;  // generic path tables (device)
     // planner memory: winning kernel variant per (axis, n1, n3), filled by the first large call (banded.cu: launch_planned)
     static constexpr int kMaxPlans = 8;

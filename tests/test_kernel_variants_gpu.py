@@ -77,9 +77,15 @@ def test_staggered_edge_planes_variants(pdo, oracle, variant, mode, n, cplx):
         assert _relerr(got, ref) < TOL, (name, n, cplx, mode, _relerr(got, ref))
 
 
-@pytest.mark.parametrize("xth", [128, 256])
+@pytest.mark.parametrize("xth", [128, 256, 1000, 1016])
 @pytest.mark.parametrize("n", [512, 1024, 2048, 96])
 def test_contiguous_variants(pdo, oracle, variant, xth, n):
+    """128 / 256: register-staged x kernel by CTA size; 1000 / 1016: the TMA (bulk-copy) pipeline on the operator's own
+    chunk length / on 16-point chunks.  A variant that does not cover a shape must fail loudly, never fall back."""
+    if xth == 1016 and n % 32 != 0:
+        pytest.skip("the M=16 alternate tables exist only next to M=32 ones")
+    if xth >= 1000 and n == 2048:
+        pytest.skip("three 2048-point tiles of 8 lines exceed 227 KB of shared memory")
     variant("auto", xth)
     d = 2 * np.pi / n
     c10, cf = pdo.cd10(), pdo.cf90()
@@ -89,3 +95,21 @@ def test_contiguous_variants(pdo, oracle, variant, xth, n):
     assert _relerr(c10.dd1(fd).cpu().numpy(), oracle.cd10(f, d, 0, 1)) < TOL
     assert _relerr(c10.d2d1(fd).cpu().numpy(), oracle.cd10(f, d, 0, 2)) < TOL
     assert _relerr(cf.filter1(fd).cpu().numpy(), oracle.cf90(f, 0)) < TOL
+    assert pdo.lib().pdo_debug_last_variant() == xth
+    c06, ga = pdo.cd06(), pdo.gaussian()
+    assert c06.init(n, d) == 0 and ga.init(n) == 0
+    assert _relerr(c06.dd1(fd).cpu().numpy(), oracle.cd06(f, d, 0)) < TOL
+    assert _relerr(ga.filter1(fd).cpu().numpy(), oracle.gaussian(f, 0)) < TOL
+
+
+@pytest.mark.parametrize("xth", [1000, 1016])
+def test_contiguous_tma_many_tiles(pdo, oracle, variant, xth):
+    """Enough lines that every persistent CTA cycles its three tile buffers several times (148 CTAs x 8 lines x >3)."""
+    variant("auto", xth)
+    n = 1024
+    d = 2 * np.pi / n
+    c10 = pdo.cd10()
+    assert c10.init(n, d) == 0
+    f = broadband((5, 1203, n), seed=3)   # 6015 lines: 752 tiles of 8 -> 5+ per CTA, ragged tail
+    got = c10.dd1(_dev(f)).cpu().numpy()
+    assert _relerr(got, oracle.cd10(f, d, 0, 1)) < TOL
