@@ -210,8 +210,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    VAR = {128: "chunk_x_kernel<128 thr>", 256: "chunk_x_kernel<256 thr>", 1: "chunk_strided_kernel<512>", 2: "chunk_strided_kernel<256>",
-           3: "chunk_strided_cluster_kernel", 5: "chunk_strided_cpipe_kernel", 6: "chunk_strided_pipe_kernel"}
+    VAR = {128: "chunk_x_kernel<128 thr>", 256: "chunk_x_kernel<256 thr>", 1000: "chunk_x_tma_kernel<M=32, 256 thr>",
+           1016: "chunk_x_tma_kernel<M=16, 512 thr>", 1: "chunk_strided_kernel<512>", 2: "chunk_strided_kernel<256>",
+           3: "chunk_strided_cluster_kernel", 5: "chunk_strided_cpipe_kernel", 6: "chunk_strided_pipe_kernel",
+           7: "chunk_strided_tma_kernel", 8: "chunk_strided_ctma_kernel<XT=64>", 9: "chunk_strided_ctma_kernel<XT=32>",
+           10: "chunk_strided_ctma_kernel<XT=32, 2 CTA/SM>", 11: "chunk_strided_cpipe_kernel<tma loads>"}
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
@@ -289,10 +292,15 @@ def run_ours(args):
     ach = BYTES_PER_POINT * npts_rank / (per[dom] * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_POINT * npts_rank, "per_kernel": per_k}
-    tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tr):
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (tools/ncu_summary.py)
+    import glob
+    base = names[dom].split("(")[1].rstrip(")").split("<")[0]
+    for tr in sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json"))):
         try:
-            roof["traffic"] = json.load(open(tr)).get(names[dom].split("(")[1].rstrip(")").split("<")[0])
+            v = json.load(open(tr)).get(base)
+            if v is not None:
+                roof["traffic"] = v
+                roof["traffic_source"] = os.path.relpath(tr, ROOT)
         except Exception:
             pass
     cb = None

@@ -19,6 +19,8 @@
 // LU factors / spike tables arrive as a __grid_constant__ struct, i.e. in the constant bank.
 // Generic any-n kernels (one thread per line, tables in global memory) cover line lengths that are not a
 // multiple of 8.  There is no CPU path.
+#include <cuda.h>
+
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -496,6 +498,7 @@ chunk_strided_cluster_kernel(const double* __restrict__ f, double* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 constexpr int kCpXT = 32;
 constexpr int kCpPC = 16;
+constexpr int kCpBoxRows = 256;
 constexpr int kCpMaxHW = 8;
 
 // --- distributed-shared-memory push with transaction barriers (no fences, no cluster barrier per tile) ---
@@ -528,10 +531,52 @@ __device__ __forceinline__ void st_async_f64(unsigned remote_addr, double v, uns
                  "l"(__double_as_longlong(v)), "r"(remote_mbar) : "memory");
 }
 
+// --- bulk-copy (TMA) and transaction-barrier helpers shared by the TMA-staged kernels ---
+constexpr int kXtBuf = 3;
+constexpr int kXTma = 1000, kXTma16 = 1016;  // x-kernel variant codes next to the CTA sizes 128 / 256
+
+__device__ __forceinline__ void mbar_wait_or_trap(unsigned mbar, unsigned parity) {
+    // bounded spin: a protocol error traps (the launch fails loudly) instead of hanging the device
+    for (unsigned spin = 0; spin < (1u << 20); ++spin) {
+        unsigned ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}" : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void* gsrc, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, unsigned smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(unsigned smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, unsigned mbar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int c1, int c2, unsigned smem_src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_src) : "memory");
+}
+
+
 template <int RK, int BW, int M>
 __global__ void __launch_bounds__(kCpPC * kCpXT, 1)
 chunk_strided_cpipe_kernel(const double* __restrict__ f, double* __restrict__ out, long long n1, int n, long long in_slab,
-                           long long out_slab, int tiles_x, long long ntiles, int C, int vec16,
+                           long long out_slab, int tiles_x, long long ntiles, int C, int vec16, int tma_in,
+                           const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_halo,
                            const __grid_constant__ ChunkTables tab, const __grid_constant__ OpParams op) {
     constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
     constexpr int XT = kCpXT, PC = kCpPC, THREADS = PC * XT;
@@ -540,11 +585,13 @@ chunk_strided_cpipe_kernel(const double* __restrict__ f, double* __restrict__ ou
     constexpr int BWc = (BW > 0 ? BW : 1);
     constexpr int EC = PC + 2 * kCpMaxHW;  // extended chunk slots: [halo left | own PC chunks | halo right]
     constexpr int ESL = EC * XT;
-    extern __shared__ __align__(16) double sm[];
+    extern __shared__ __align__(128) double smt[];
+    double* sm = smt;
     double* buf = sm;                     // [RB][XT]
     double* ex = sm + RB * XT;            // 2 x { eA[BWc][EC][XT], eB[BWc][EC][XT] }: ping-pong per tile (a neighbour may run
     double* sS = ex + 4 * BWc * ESL;      // one tile ahead and push into the other half); sS[BWc][PC][XT]
     __shared__ __align__(8) unsigned long long full_bar[2];  // transaction barriers: "halo of parity b has landed"
+    __shared__ __align__(8) unsigned long long in_bar;       // tma_in: "the tile has landed" (one phase per tile)
     const int tid = threadIdx.x;
     const int xi = tid & (XT - 1), pl = tid >> 5;
     const unsigned rank = (C > 1) ? cluster_ctarank() : 0u;
@@ -556,6 +603,20 @@ chunk_strided_cpipe_kernel(const double* __restrict__ f, double* __restrict__ ou
     auto issue = [&](long long t) {
         const long long k = t / tiles_x;
         const long long x0 = (t - k * tiles_x) * XT;
+        if (tma_in) {  // three tensor-map boxes issued by one thread: halo above, own rows, halo below (HL == HR here)
+            if (tid == 0) {
+                const unsigned bar = smem_u32(&in_bar);
+                mbar_arrive_expect_tx(bar, (unsigned)(RB * XT * sizeof(double)));
+                const int rw0 = p0 * M;
+                const int rl = rw0 == 0 ? n - HL : rw0 - HL;
+                const int rr = rw0 + RC == n ? 0 : rw0 + RC;
+                tma_load_3d(smem_u32(buf), &tm_halo, (int)x0, rl, (int)k, bar);
+                for (int r = 0; r < RC; r += kCpBoxRows)   // a tensor-map box is at most 256 rows
+                    tma_load_3d(smem_u32(buf + (HL + r) * XT), &tm_in, (int)x0, rw0 + r, (int)k, bar);
+                tma_load_3d(smem_u32(buf + (HL + RC) * XT), &tm_halo, (int)x0, rr, (int)k, bar);
+            }
+            return;
+        }
         const double* base = f + k * in_slab + x0;
         const int q0 = p0 * M - HL;  // logical row of buffer row 0
         if (vec16) {
@@ -579,6 +640,13 @@ chunk_strided_cpipe_kernel(const double* __restrict__ f, double* __restrict__ ou
         cp_async_commit();
     };
 
+    if (tma_in) {
+        if (tid == 0) {
+            mbar_init(smem_u32(&in_bar), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     if constexpr (BW > 0) {
         if (C > 1) {
             if (tid == 0) {
@@ -593,8 +661,12 @@ chunk_strided_cpipe_kernel(const double* __restrict__ f, double* __restrict__ ou
     int par = 0;
     unsigned it = 0;
     for (; tile < ntiles; tile += ncl, par ^= 1, ++it) {
-        cp_async_wait_all();
-        __syncthreads();
+        if (tma_in) {
+            mbar_wait_or_trap(smem_u32(&in_bar), it & 1u);
+        } else {
+            cp_async_wait_all();
+            __syncthreads();
+        }
         double v[M + HL + HR];
         {
             const double* b = buf + (pl * M) * XT + xi;
@@ -823,36 +895,6 @@ chunk_x_kernel(const double* __restrict__ f, double* __restrict__ out, long long
 // distinct 16-byte bank groups ((n+2)/2 is odd): conflict-free without per-chunk padding, which a bulk copy could
 // not produce.  The solved chunk goes back in place (all reads of the tile precede chunk_solve's first barrier).
 // ------------------------------------------------------------------------------------------------
-constexpr int kXtBuf = 3;
-constexpr int kXTma = 1000, kXTma16 = 1016;  // x-kernel variant codes next to the CTA sizes 128 / 256
-
-__device__ __forceinline__ void mbar_wait_or_trap(unsigned mbar, unsigned parity) {
-    // bounded spin: a protocol error traps (the launch fails loudly) instead of hanging the device
-    for (unsigned spin = 0; spin < (1u << 20); ++spin) {
-        unsigned ok;
-        asm volatile(
-            "{\n"
-            ".reg .pred P1;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, P1;\n"
-            "}" : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
-        if (ok) return;
-    }
-    __trap();
-}
-__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void* gsrc, unsigned bytes, unsigned mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
-                 "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* gdst, unsigned smem_src, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 template <int RK, int BW, int M, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 chunk_x_tma_kernel(const double* __restrict__ f, double* __restrict__ out, long long nlines, int n, int L, long long ntiles,
@@ -953,6 +995,313 @@ chunk_x_tma_kernel(const double* __restrict__ f, double* __restrict__ out, long 
         }
     }
     if (tid < 32) bulk_wait_read<0>();  // shared memory must outlive the last drains
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strided (y / z) kernel, TMA-staged persistent pipeline ("stma")
+//
+// Same rotation of three tile buffers as chunk_x_tma_kernel, but a tile is XT contiguous x-columns x the whole line
+// and moves as a few 3-D tensor-map boxes {XT, BR, 1} (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG): the TMA unit
+// walks the n1-strided rows, zero-fills / clips columns past n1, and no thread issues a per-row copy or store (the
+// register-staged pipelines spend most of their stall cycles in the LSU queue doing exactly that).  Thread (xi, p)
+// owns chunk p of column xi: a half-warp reads XT >= 8 adjacent doubles of one row, conflict-free.
+// ------------------------------------------------------------------------------------------------
+template <int RK, int BW, int M>
+__global__ void __launch_bounds__(512, 1)
+chunk_strided_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, int n, int XT,
+                         int BR, int nbox_in, int nbox_out, int tiles_x, long long ntiles,
+                         const __grid_constant__ ChunkTables tab, const __grid_constant__ OpParams op) {
+    constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
+    extern __shared__ __align__(128) double smt[];
+    __shared__ __align__(8) unsigned long long full_bar[kXtBuf];
+    const int P = n / M;
+    const int rows_in = op.edge_in ? n + 1 : n;
+    const int nbox_max = nbox_in > nbox_out ? nbox_in : nbox_out;
+    const size_t tile_elems = (size_t)nbox_max * BR * XT;
+    const unsigned box_bytes = (unsigned)(BR * XT) * (unsigned)sizeof(double);
+    double* sm_g = smt + kXtBuf * tile_elems;
+    const int tid = threadIdx.x;
+    const int xt_shift = __ffs(XT) - 1;
+    const int xi = tid & (XT - 1), p = tid >> xt_shift;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < kXtBuf; ++b) mbar_init(smem_u32(&full_bar[b]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue_load = [&](long long tile, int b) {  // thread 0 only
+        const int k = (int)(tile / tiles_x);
+        const int x0 = (int)(tile - (long long)k * tiles_x) * XT;
+        const unsigned bar = smem_u32(&full_bar[b]);
+        mbar_arrive_expect_tx(bar, box_bytes * (unsigned)nbox_in);
+        for (int i = 0; i < nbox_in; ++i)
+            tma_load_3d(smem_u32(smt + b * tile_elems + (size_t)i * BR * XT), &tm_in, x0, i * BR, k, bar);
+    };
+
+    const long long t0 = blockIdx.x;
+    if (tid == 0) {
+        if (t0 < ntiles) issue_load(t0, 0);
+        if (t0 + gridDim.x < ntiles) issue_load(t0 + gridDim.x, 1);
+    }
+
+    int it = 0;
+    for (long long tile = t0; tile < ntiles; tile += gridDim.x, ++it) {
+        const int b = it % kXtBuf;
+        double* buf = smt + b * tile_elems;
+        mbar_wait_or_trap(smem_u32(&full_bar[b]), (unsigned)(it / kXtBuf) & 1u);
+
+        double v[M + HL + HR];
+        {
+            const double* c = buf + (p * M) * XT + xi;
+#pragma unroll
+            for (int j = 0; j < M; ++j) { v[HL + j] = *c; c += XT; }
+#pragma unroll
+            for (int j = 0; j < HL; ++j) {
+                int q = p * M - HL + j;
+                if (q < 0) q += n;
+                v[j] = buf[q * XT + xi];
+            }
+#pragma unroll
+            for (int j = 0; j < HR; ++j) {
+                int q = (p + 1) * M + j;
+                if (q >= rows_in) q -= n;  // the staggered edge plane n is read un-wrapped
+                v[HL + M + j] = buf[q * XT + xi];
+            }
+        }
+        double r[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) r[i] = rhs_eval<RK>(&v[i + HL], op);
+
+        if constexpr (BW > 0) {
+            chunk_solve<BW, M>(r, tab, sm_g, P * XT, p, [&](int q) { return q * XT + xi; });
+        } else {
+            __syncthreads();  // everyone has read the tile
+        }
+        {
+            double* c = buf + (p * M) * XT + xi;
+#pragma unroll
+            for (int i = 0; i < M; ++i) { *c = r[i]; c += XT; }
+            if (op.edge_out && p == 0) buf[n * XT + xi] = r[0];
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            const int k = (int)(tile / tiles_x);
+            const int x0 = (int)(tile - (long long)k * tiles_x) * XT;
+            for (int i = 0; i < nbox_out; ++i) tma_store_3d(&tm_out, x0, i * BR, k, smem_u32(buf + (size_t)i * BR * XT));
+            bulk_commit();
+            bulk_wait_read<1>();
+            const long long nxt = tile + 2LL * gridDim.x;
+            if (nxt < ntiles) issue_load(nxt, (it + 2) % kXtBuf);
+        }
+    }
+    if (tid == 0) bulk_wait_read<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strided (y / z) kernel, cluster + TMA ("ctma"): for row strides of megabytes (solve axis outermost) what decides the
+// rate is how many bytes every visited row contributes, so the tile must be WIDE (XT = 32 / 64 columns = 256 / 512
+// byte row segments) and a whole line of such a tile no longer fits in one CTA.  A thread-block cluster of C CTAs
+// shares the line: CTA `rank` owns PC = P/C consecutive chunks (RPC = PC*M rows) of the tile.  Per tile and CTA:
+//   TMA in   one box {XT, RPC} plus two halo boxes of HB rows (periodic wrap resolved in the box coordinates)
+//   solve    interior sweeps in registers; gA/gB go into the CTA's own extended array and the chunks within W+1 of
+//            a CTA edge are PUSHED into the neighbour's halo slots (st.async, counted on the neighbour's transaction
+//            barrier), so the separator solve reads local shared memory only; the chunk before a CTA's first one is
+//            recomputed from the same window instead of being exchanged a second time.  The extended array is single
+//            buffered: a split-phase cluster barrier (arrive after my gather, wait before my next push) keeps a
+//            neighbour from overwriting slots I am still reading, and its wait lands after a whole tile's worth of
+//            independent work
+//   TMA out  one box {XT, RPC}, written in place of the input rows
+// with the same three-buffer rotation as the other TMA kernels.
+// ------------------------------------------------------------------------------------------------
+template <int RK, int BW, int M>
+__global__ void __launch_bounds__(512, 1)
+chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_halo,
+                          const __grid_constant__ CUtensorMap tm_out, int n, int XT, int C, int PC, int tiles_x, long long ntiles,
+                          const __grid_constant__ ChunkTables tab, const __grid_constant__ OpParams op) {
+    constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
+    constexpr int HB = HL > HR ? HL : HR;           // rows of a halo box
+    constexpr int BWc = BW > 0 ? BW : 1;
+    extern __shared__ __align__(128) double smt[];
+    __shared__ __align__(8) unsigned long long full_bar[kXtBuf];
+    __shared__ __align__(8) unsigned long long ex_bar;
+    const int RPC = PC * M;
+    const size_t tile_elems = (size_t)(RPC + 2 * HB) * XT;
+    const int W = tab.W, HW = W + 1;
+    const int EC = PC + 2 * HW;                     // extended chunk slots: [HW left halo][PC own][HW right halo]
+    const int ESL = EC * XT;
+    double* eA = smt + kXtBuf * tile_elems;         // [BWc][EC][XT]
+    double* eB = eA + BWc * ESL;
+    double* sS = eB + BWc * ESL;                    // [BWc][PC][XT]
+    const int tid = threadIdx.x;
+    const int xt_shift = __ffs(XT) - 1;
+    const int xi = tid & (XT - 1), pl = tid >> xt_shift;
+    const unsigned rank = (C > 1) ? cluster_ctarank() : 0u;
+    const int p0 = (int)rank * PC;
+    const int r0 = p0 * M;                          // first row of this CTA
+    const long long ncl = gridDim.x / C;
+    const unsigned load_bytes = (unsigned)tile_elems * (unsigned)sizeof(double);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < kXtBuf; ++b) mbar_init(smem_u32(&full_bar[b]), 1);
+        mbar_init(smem_u32(&ex_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (BW > 0 && C > 1) cluster_sync_all();        // peers' barriers exist before anyone pushes
+    else __syncthreads();
+
+    auto issue_load = [&](long long tile, int b) {  // thread 0 only
+        const int k = (int)(tile / tiles_x);
+        const int x0 = (int)(tile - (long long)k * tiles_x) * XT;
+        const unsigned bar = smem_u32(&full_bar[b]);
+        double* buf = smt + b * tile_elems;
+        mbar_arrive_expect_tx(bar, load_bytes);
+        const int rl = r0 == 0 ? n - HB : r0 - HB;  // periodic wrap: whole halo boxes wrap, never straddle
+        const int rr = r0 + RPC == n ? 0 : r0 + RPC;
+        tma_load_3d(smem_u32(buf), &tm_halo, x0, rl, k, bar);
+        tma_load_3d(smem_u32(buf + (size_t)HB * XT), &tm_in, x0, r0, k, bar);
+        tma_load_3d(smem_u32(buf + (size_t)(HB + RPC) * XT), &tm_halo, x0, rr, k, bar);
+    };
+
+    const long long t0 = blockIdx.x / C;
+    if (tid == 0) {
+        if (t0 < ntiles) issue_load(t0, 0);
+        if (t0 + ncl < ntiles) issue_load(t0 + ncl, 1);
+    }
+
+    int it = 0;
+    for (long long tile = t0; tile < ntiles; tile += ncl, ++it) {
+        const int b = it % kXtBuf;
+        double* buf = smt + b * tile_elems;
+        mbar_wait_or_trap(smem_u32(&full_bar[b]), (unsigned)(it / kXtBuf) & 1u);
+
+        double v[M + HL + HR];
+        {
+            const double* c = buf + (size_t)(HB + pl * M - HL) * XT + xi;
+#pragma unroll
+            for (int j = 0; j < M + HL + HR; ++j) v[j] = c[j * XT];
+        }
+        double r[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) r[i] = rhs_eval<RK>(&v[i + HL], op);
+
+        if constexpr (BW > 0) {
+            double a_[2], b_[2];
+            chunk_interior<BW, M>(r, tab, a_, b_);
+            // everyone in the cluster has finished reading the previous tile's extended arrays
+            if (C > 1 && it > 0) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+            const int me = (HW + pl) * XT + xi;
+            eA[me] = a_[0];
+            eB[me] = b_[0];
+            if (BW == 2) { eA[ESL + me] = a_[1]; eB[ESL + me] = b_[1]; }
+            {
+                const bool to_right = pl >= PC - HW;  // my tail chunks are the right neighbour's left halo
+                const bool to_left = pl < HW;         // my head chunks are the left neighbour's right halo
+                const int er = (HW + pl - PC) * XT + xi;
+                const int el = (HW + PC + pl) * XT + xi;
+                if (C > 1) {
+                    const unsigned bar = smem_u32(&ex_bar);
+                    if (tid == 0) mbar_arrive_expect_tx(bar, (unsigned)(2 * HW * XT * 2 * BW * sizeof(double)));
+                    const unsigned aA = smem_u32(eA), aB = smem_u32(eB);
+                    if (to_right) {
+                        const unsigned rr = rank + 1 == (unsigned)C ? 0u : rank + 1;
+                        const unsigned rb = cluster_map_u32(bar, rr);
+                        const unsigned rA = cluster_map_u32(aA + er * 8, rr), rB = cluster_map_u32(aB + er * 8, rr);
+                        st_async_f64(rA, a_[0], rb);
+                        st_async_f64(rB, b_[0], rb);
+                        if (BW == 2) { st_async_f64(rA + ESL * 8, a_[1], rb); st_async_f64(rB + ESL * 8, b_[1], rb); }
+                    }
+                    if (to_left) {
+                        const unsigned rl = rank == 0 ? (unsigned)C - 1 : rank - 1;
+                        const unsigned rb = cluster_map_u32(bar, rl);
+                        const unsigned rA = cluster_map_u32(aA + el * 8, rl), rB = cluster_map_u32(aB + el * 8, rl);
+                        st_async_f64(rA, a_[0], rb);
+                        st_async_f64(rB, b_[0], rb);
+                        if (BW == 2) { st_async_f64(rA + ESL * 8, a_[1], rb); st_async_f64(rB + ESL * 8, b_[1], rb); }
+                    }
+                } else {  // the line lives in this CTA: the halo is a periodic copy of my own edge chunks
+                    if (to_right) {
+                        eA[er] = a_[0]; eB[er] = b_[0];
+                        if (BW == 2) { eA[ESL + er] = a_[1]; eB[ESL + er] = b_[1]; }
+                    }
+                    if (to_left) {
+                        eA[el] = a_[0]; eB[el] = b_[0];
+                        if (BW == 2) { eA[ESL + el] = a_[1]; eB[ESL + el] = b_[1]; }
+                    }
+                }
+            }
+            __syncthreads();
+            if (C > 1) mbar_wait_or_trap(smem_u32(&ex_bar), (unsigned)it & 1u);
+            // separator solve from local shared memory: s_p = sum_d G[d] (gA_{p+d} + gB_{p+d+1})
+            double s0 = 0.0, s1 = 0.0, t0_ = 0.0, t1_ = 0.0;
+            {
+                int e = (HW + pl - W) * XT + xi;
+                for (int d = 0; d <= 2 * W; ++d) {
+                    if (BW == 2) {
+                        const double h0 = eA[e] + eB[e + XT];
+                        const double h1 = eA[ESL + e] + eB[ESL + e + XT];
+                        s0 += tab.G[d][0] * h0 + tab.G[d][1] * h1;
+                        s1 += tab.G[d][2] * h0 + tab.G[d][3] * h1;
+                    } else {
+                        s0 += tab.G[d][0] * (eA[e] + eB[e + XT]);
+                    }
+                    e += XT;
+                }
+            }
+            if (pl == 0) {  // previous chunk lives in another CTA: recompute its separator values from the halo
+                int e = (HW - 1 - W) * XT + xi;
+                for (int d = 0; d <= 2 * W; ++d) {
+                    if (BW == 2) {
+                        const double h0 = eA[e] + eB[e + XT];
+                        const double h1 = eA[ESL + e] + eB[ESL + e + XT];
+                        t0_ += tab.G[d][0] * h0 + tab.G[d][1] * h1;
+                        t1_ += tab.G[d][2] * h0 + tab.G[d][3] * h1;
+                    } else {
+                        t0_ += tab.G[d][0] * (eA[e] + eB[e + XT]);
+                    }
+                    e += XT;
+                }
+            }
+            sS[pl * XT + xi] = s0;
+            if (BW == 2) sS[PC * XT + pl * XT + xi] = s1;
+            __syncthreads();
+            double sp0, sp1 = 0.0;
+            if (pl == 0) { sp0 = t0_; sp1 = t1_; }
+            else { sp0 = sS[(pl - 1) * XT + xi]; if (BW == 2) sp1 = sS[PC * XT + (pl - 1) * XT + xi]; }
+            chunk_finish<BW, M>(r, tab, s0, s1, sp0, sp1);
+            // My reads of the extended arrays are done (their values have been consumed above): neighbours may push the
+            // next tile's values once every CTA has said so.  Nothing is published through this barrier, it only orders
+            // my completed shared-memory reads before the peers' later pushes, so the arrive is .relaxed: a .release
+            // arrive costs a MEMBAR.ALL.GPU + ERRBAR per tile (28 % of all stall samples in the first ncu capture).
+            if (C > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n" ::: "memory");
+        } else {
+            __syncthreads();  // everyone has read the tile (neighbours' halo rows overlap my rows)
+        }
+        {
+            double* c = buf + (size_t)(HB + pl * M) * XT + xi;
+#pragma unroll
+            for (int i = 0; i < M; ++i) { *c = r[i]; c += XT; }
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            const int k = (int)(tile / tiles_x);
+            const int x0 = (int)(tile - (long long)k * tiles_x) * XT;
+            tma_store_3d(&tm_out, x0, r0, k, smem_u32(buf + (size_t)HB * XT));
+            bulk_commit();
+            bulk_wait_read<1>();
+            const long long nxt = tile + 2 * ncl;
+            if (nxt < ntiles) issue_load(nxt, (it + 2) % kXtBuf);
+        }
+    }
+    if (tid == 0) bulk_wait_read<0>();
+    if constexpr (BW > 0) {
+        // pair the last arrive; also keeps every CTA resident until no peer can still push into it
+        if (C > 1 && it > 0) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1102,7 +1451,12 @@ int strided_mode() {
         if (e && std::strcmp(e, "cluster") == 0) mode = 3;
         if (e && std::strcmp(e, "cluster4") == 0) mode = 4;
         if (e && std::strcmp(e, "cpipe") == 0) mode = 5;
-        if (e && std::strcmp(e, "pipe1") == 0) mode = 6;  // single-CTA pipeline even where cpipe is the default
+        if (e && std::strcmp(e, "pipe1") == 0) mode = 6;
+        if (e && std::strcmp(e, "stma") == 0) mode = 7;   // TMA tensor-map pipeline
+        if (e && std::strcmp(e, "ctma64") == 0) mode = 8; // cluster + TMA, 64-column tiles
+        if (e && std::strcmp(e, "ctma32") == 0) mode = 9; // cluster + TMA, 32-column tiles
+        if (e && std::strcmp(e, "ctma32s") == 0) mode = 10; // same, 4 chunks per CTA, two CTAs per SM
+        if (e && std::strcmp(e, "cpipe_t") == 0) mode = 11; // cpipe with tensor-map tile loads  // single-CTA pipeline even where cpipe is the default
         g_strided_mode = mode;
     }
     return g_strided_mode;
@@ -1169,7 +1523,7 @@ cudaError_t launch_xtma(const BandedOp* h, const ChunkTables& tab, const double*
     if (((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return cudaErrorInvalidConfiguration;
     const int L = THREADS / P;
     const size_t smem = sizeof(double) * ((size_t)kXtBuf * L * (n + 2) + 3 * (BW > 0 ? BW : 1) * (size_t)THREADS);
-    constexpr size_t cap = 227 * 1024 - 64;
+    constexpr size_t cap = 227 * 1024 - 256;  // static mbarriers + padding up to the 128-byte aligned dynamic base
     if (smem > cap) return cudaErrorInvalidConfiguration;
     auto kern = chunk_x_tma_kernel<RK, BW, M, THREADS>;
     if (!attr_done) {
@@ -1181,6 +1535,152 @@ cudaError_t launch_xtma(const BandedOp* h, const ChunkTables& tab, const double*
     const long long grid = ntiles < 148 ? ntiles : 148;
     kern<<<(unsigned)grid, THREADS, smem, st>>>(f, out, nlines, n, L, ntiles, tab, h->op);
     return cudaGetLastError();
+}
+
+// Driver entry point for tensor-map encoding, resolved through the runtime (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// f64 field f(n1, rows, n3) as a 3-D tensor, box {XT, BR, 1}, no swizzle (rows land densely as [row][XT]).
+bool encode_field_map(CUtensorMap* tm, const double* base, long long n1, long long rows, long long n3, int XT, int BR) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)n1, (cuuint64_t)rows, (cuuint64_t)n3};
+    const cuuint64_t strides[2] = {(cuuint64_t)n1 * sizeof(double), (cuuint64_t)n1 * (cuuint64_t)rows * sizeof(double)};
+    const cuuint32_t box[3] = {(cuuint32_t)XT, (cuuint32_t)BR, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+constexpr int kSTma = 7;     // strided-mode code of the TMA pipeline
+constexpr int kCpipeT = 11;  // cpipe with tensor-map tile loads
+
+template <int RK, int BW, int M>
+cudaError_t launch_stma(const BandedOp* h, const double* f, double* out, long long n1, long long n3, long long in_slab,
+                        long long out_slab, cudaStream_t st) {
+    static bool attr_done = false;
+    const int n = h->n, P = n / M;
+    if (n % M != 0 || (n1 & 1) || n1 >= (1LL << 31) || n3 >= (1LL << 31)) return cudaErrorInvalidConfiguration;
+    if (((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return cudaErrorInvalidConfiguration;
+    const int rows_in = n + (h->op.edge_in ? 1 : 0), rows_out = n + (h->op.edge_out ? 1 : 0);
+    const int rows_max = rows_in > rows_out ? rows_in : rows_out;
+    constexpr size_t cap = 227 * 1024 - 256;  // static mbarriers + padding up to the 128-byte aligned dynamic base
+    // widest power-of-two column count whose three tiles fit: XT * P threads (<= 512), XT >= 8 (64-byte row segments)
+    for (int XT = 64; XT >= 8; XT >>= 1) {
+        if (XT * P > 512 || XT * P < 64) continue;
+        if (XT / 2 >= n1 && XT > 8) continue;
+        const int nbox = (rows_max + 255) / 256;
+        int BR = (rows_max + nbox - 1) / nbox;
+        const int ralign = (128 / (XT * 8)) > 1 ? 128 / (XT * 8) : 1;  // boxes start 128-byte aligned in shared memory
+        BR = (BR + ralign - 1) / ralign * ralign;
+        if (BR > 256) continue;
+        const int nbox_in = (rows_in + BR - 1) / BR, nbox_out = (rows_out + BR - 1) / BR;
+        const int nbox_max = nbox_in > nbox_out ? nbox_in : nbox_out;
+        const size_t smem = sizeof(double) * ((size_t)kXtBuf * nbox_max * BR * XT + 3 * (BW > 0 ? BW : 1) * (size_t)(XT * P));
+        if (smem > cap) continue;
+        CUtensorMap tm_in, tm_out;
+        if (!encode_field_map(&tm_in, f, n1, in_slab / n1, n3, XT, BR) || !encode_field_map(&tm_out, out, n1, out_slab / n1, n3, XT, BR))
+            return cudaErrorInvalidConfiguration;
+        auto kern = chunk_strided_tma_kernel<RK, BW, M>;
+        if (!attr_done) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        const int tiles_x = (int)((n1 + XT - 1) / XT);
+        const long long ntiles = (long long)tiles_x * n3;
+        const long long grid = ntiles < 148 ? ntiles : 148;
+        g_last_variant = kSTma;
+        kern<<<(unsigned)grid, XT * P, smem, st>>>(tm_in, tm_out, n, XT, BR, nbox_in, nbox_out, tiles_x, ntiles, h->tab, h->op);
+        return cudaGetLastError();
+    }
+    return cudaErrorInvalidConfiguration;
+}
+
+constexpr int kCTma64 = 8, kCTma32 = 9, kCTma32s = 10;  // strided-mode codes of the cluster + TMA kernel (512- / 256-byte row segments)
+
+template <int RK, int BW, int M>
+cudaError_t launch_ctma(const BandedOp* h, const double* f, double* out, long long n1, long long n3, long long in_slab,
+                        long long out_slab, cudaStream_t st, int XT, int pc_max = 16) {
+    const int n = h->n, P = n / M;
+    constexpr int BWc = BW > 0 ? BW : 1;
+    if (n % M != 0 || (n1 & 1) || n1 >= (1LL << 31) || n3 >= (1LL << 31) || n1 < XT / 2) return cudaErrorInvalidConfiguration;
+    if (h->op.edge_in || h->op.edge_out || in_slab != n1 * n || out_slab != n1 * n) return cudaErrorInvalidConfiguration;
+    if (BW > 0 && (h->tab.dense || 2 * h->tab.W + 2 > P)) return cudaErrorInvalidConfiguration;
+    constexpr int HB = Halo<RK>::L > Halo<RK>::R ? Halo<RK>::L : Halo<RK>::R;
+    const int HW = (BW > 0 ? h->tab.W : 0) + 1;
+    if (((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return cudaErrorInvalidConfiguration;
+    constexpr size_t cap = 227 * 1024 - 256;
+    int PC = 0;
+    size_t smem = 0;
+    for (int pc = pc_max; pc >= 1; pc >>= 1) {
+        if (P % pc != 0) continue;
+        const int c = P / pc;
+        if (!(c == 1 || c == 2 || c == 4 || c == 8)) continue;
+        if (XT * pc > 512 || XT * pc < 64 || pc * M > 256 || (BW > 0 && HW > pc)) continue;
+        const size_t need = sizeof(double) * ((size_t)kXtBuf * (pc * M + 2 * HB) * XT + 2 * BWc * (size_t)(pc + 2 * HW) * XT +
+                                              BWc * (size_t)pc * XT);
+        if (need > cap) continue;
+        PC = pc; smem = need;
+        break;
+    }
+    if (PC == 0) return cudaErrorInvalidConfiguration;
+    const int C = P / PC;
+    CUtensorMap tm_in, tm_halo, tm_out;
+    if (!encode_field_map(&tm_in, f, n1, n, n3, XT, PC * M) || !encode_field_map(&tm_halo, f, n1, n, n3, XT, HB) ||
+        !encode_field_map(&tm_out, out, n1, n, n3, XT, PC * M))
+        return cudaErrorInvalidConfiguration;
+    auto kern = chunk_strided_ctma_kernel<RK, BW, M>;
+    static bool attr_done = false;
+    static int max_clusters[9][3] = {};
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int tiles_x = (int)((n1 + XT - 1) / XT);
+    const long long ntiles = (long long)tiles_x * n3;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(XT * PC);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)C;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int& mc = max_clusters[C][pc_max < 16 ? 2 : (XT == 64 ? 1 : 0)];
+    if (mc == 0) {
+        cfg.gridDim = dim3((unsigned)(148 / C * C));
+        int nc = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+        if (e != cudaSuccess) return e;
+        mc = nc > 0 ? nc : 1;
+    }
+    const long long ncl = ntiles < mc ? ntiles : mc;
+    cfg.gridDim = dim3((unsigned)(ncl * C));
+    g_last_variant = pc_max < 16 ? kCTma32s : (XT == 64 ? kCTma64 : kCTma32);
+    return cudaLaunchKernelEx(&cfg, kern, tm_in, tm_halo, tm_out, n, XT, C, PC, tiles_x, ntiles, h->tab, h->op);
 }
 
 template <int RK, int BW, int M>
@@ -1197,10 +1697,21 @@ cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* o
             if (M == 32 && h->has_tab16) { g_last_variant = kXTma16; return launch_xtma<RK, BW, 16, 512>(h, h->tab16, f, out, n3, st); }
             return cudaErrorInvalidConfiguration;
         }
+        if (xth == 0 && xtma_in_planner() && n3 >= 148 * 8) {  // heuristic path (small problems, captured streams): TMA pipeline if it fits
+            cudaError_t e = cudaErrorInvalidConfiguration;
+            if constexpr (M == 32) e = launch_xtma<RK, BW, 32, 256>(h, h->tab, f, out, n3, st);
+            else if constexpr (M == 16) e = launch_xtma<RK, BW, 16, 512>(h, h->tab, f, out, n3, st);
+            if (e == cudaSuccess) { g_last_variant = kXTma; return e; }
+            cudaGetLastError();
+        }
         if (xth != 256 && P <= 128) { g_last_variant = 128; return launch_x<RK, BW, M, 128>(h, f, out, n3, st); }
         g_last_variant = 256;
         return launch_x<RK, BW, M, 256>(h, f, out, n3, st);
     }
+    if (mode == kSTma) return launch_stma<RK, BW, M>(h, f, out, n1, n3, in_slab, out_slab, st);
+    if (mode == kCTma64) return launch_ctma<RK, BW, M>(h, f, out, n1, n3, in_slab, out_slab, st, 64);
+    if (mode == kCTma32) return launch_ctma<RK, BW, M>(h, f, out, n1, n3, in_slab, out_slab, st, 32);
+    if (mode == kCTma32s) return launch_ctma<RK, BW, M>(h, f, out, n1, n3, in_slab, out_slab, st, 32, 4);  // two CTAs per SM
     if constexpr (M == 32) {
         // cluster kernel: P chunks split over C = P/PC CTAs (portable cluster sizes only); mode 3: PC=8, mode 4: PC=4
         const int PC = (mode == 4) ? 4 : 8;
@@ -1238,7 +1749,8 @@ cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* o
         const int C = P / kCpPC;
         const bool fits = (P % kCpPC == 0) && (C == 1 || C == 2 || C == 4 || C == 8) && n1 >= kCpXT &&
                           (BW == 0 || (!h->tab.dense && h->tab.W + 1 <= kCpMaxHW));
-        const bool want = (mode == 5) || (mode == 0 && (n1 * (long long)sizeof(double) >= (1 << 20) || P > 32));
+        const bool want = (mode == 5) || (mode == kCpipeT) || (mode == 0 && (n1 * (long long)sizeof(double) >= (1 << 20) || P > 32));
+        if (mode == kCpipeT && !fits) return cudaErrorInvalidConfiguration;
         if (fits && want) {
             constexpr int HLR = Halo<RK>::L + Halo<RK>::R;
             constexpr int BWc = (BW > 0 ? BW : 1);
@@ -1272,7 +1784,20 @@ cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* o
             const long long ncl = ntiles < max_clusters[C] ? ntiles : max_clusters[C];
             cfg.gridDim = dim3((unsigned)(ncl * C));
             const int vec16 = (n1 % 2 == 0) && (in_slab % 2 == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0);
-            return cudaLaunchKernelEx(&cfg, kern, f, out, n1, n, in_slab, out_slab, tiles_x, ntiles, C, vec16, h->tab, h->op);
+            CUtensorMap tm_in, tm_halo;
+            std::memset(&tm_in, 0, sizeof(tm_in));
+            std::memset(&tm_halo, 0, sizeof(tm_halo));
+            int tma_in = 0;
+            if (mode == kCpipeT) {  // tile loads through tensor maps instead of per-thread cp.async
+                if (Halo<RK>::L != Halo<RK>::R || h->op.edge_in || !vec16 || n1 >= (1LL << 31) || n3 >= (1LL << 31) ||
+                    !encode_field_map(&tm_in, f, n1, in_slab / n1, n3, kCpXT, kCpBoxRows) || (kCpPC * M) % kCpBoxRows != 0 ||
+                    !encode_field_map(&tm_halo, f, n1, in_slab / n1, n3, kCpXT, Halo<RK>::L))
+                    return cudaErrorInvalidConfiguration;
+                tma_in = 1;
+                g_last_variant = kCpipeT;
+            }
+            return cudaLaunchKernelEx(&cfg, kern, f, out, n1, n, in_slab, out_slab, tiles_x, ntiles, C, vec16, tma_in, tm_in, tm_halo,
+                                      h->tab, h->op);
         }
     }
     const int threads = (mode == 2) ? 256 : 512;
@@ -1334,10 +1859,12 @@ cudaError_t launch_planned(const BandedOp* h, int axis, const double* f, double*
         cudaGetLastError();
         return launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, 0, 0);
     }
-    const int cand_x[4] = {128, 256, kXTma, kXTma16};
-    const int cand_s[4] = {6, 5, 3, 1};  // pipe1, cpipe, cluster / streaming, t512
+    const int cand_x[3] = {128, 256, kXTma};  // kXTma16 regroups the arithmetic (not bit-identical): opt-in only
+    // pipe1, cpipe, cluster / streaming, t512, then the TMA-staged ones: single-CTA pipeline, cluster kernel (two small CTAs
+    // per SM / one large), cpipe with tensor-map loads
+    const int cand_s[8] = {6, 5, 3, 1, kSTma, kCTma32s, kCTma32, kCpipeT};
     const int* cand = axis == 0 ? cand_x : cand_s;
-    const int ncand = axis == 0 ? (xtma_in_planner() ? 4 : 2) : 4;
+    const int ncand = axis == 0 ? (xtma_in_planner() ? 3 : 2) : (xtma_in_planner() ? 8 : 4);
     cudaEvent_t e0, e1;
     if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
         cudaGetLastError();
@@ -1405,6 +1932,9 @@ void banded_debug_set_variant(int strided_mode, int x_threads) {
     g_x_threads = x_threads;
 }
 
+cudaError_t banded_dispatch(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3,
+                            long long in_slab, long long out_slab, cudaStream_t st, int force_generic);
+
 cudaError_t banded_op_apply(const BandedOp* h, int axis, const double* f, double* out, long long na, long long nb,
                             cudaStream_t st, int force_generic) {
     const int n = h->n;
@@ -1416,6 +1946,13 @@ cudaError_t banded_op_apply(const BandedOp* h, int axis, const double* f, double
     if (n1 * n3 == 0) return cudaSuccess;
     const long long in_slab = n1 * (n + (h->op.edge_in || (h->op.edge_out && h->rk == RK_D2_5) ? 1 : 0));
     const long long out_slab = n1 * (n + (h->op.edge_out ? 1 : 0));
+    const cudaError_t e = banded_dispatch(h, axis, f, out, n1, n3, in_slab, out_slab, st, force_generic);
+    if (e != cudaSuccess) cudaGetLastError();  // do not leave a stale error for the next launch check to trip over
+    return e;
+}
+
+cudaError_t banded_dispatch(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3,
+                            long long in_slab, long long out_slab, cudaStream_t st, int force_generic) {
     const int key = h->rk * 10 + h->bw;
     switch (key) {
         case RK_D1_7 * 10 + 2: return launch_any<RK_D1_7, 2>(h, axis, f, out, n1, n3, in_slab, out_slab, st, force_generic);
