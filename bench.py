@@ -138,6 +138,57 @@ class ClockSampler:
                 "reasons": sorted(v for k, v in self.BAD.items() if self.mask & k), "samples": len(sm)}
 
 
+def substep_leg(n, world, rank, steps=2):
+    """BASELINE.json metric (iii): ms per igrid RK substep.  Periodic box n^3 (strong scaling: the SAME global grid at every
+    N, slabs 1 x N), Taylor-Green + a z-dependent perturbation, skew-symmetric advection, CD06 staggered z operators, viscous,
+    TVD-RK3, fixed dt (the configuration of tests/test_igrid_gpu.py, which pins it against the oracle)."""
+    import numpy as np
+    import torch
+    import padeops_b200 as pdo
+    info = pdo.decomp_info.for_rank(n, n, n, 1, world, rank)
+    infoE = pdo.decomp_info.for_rank(n, n, n + 1, 1, world, rank)
+    d = 2 * np.pi / n
+    x = torch.arange(n, device="cuda", dtype=torch.float64) * d
+
+    def zc(inf, edge):
+        k = torch.arange(inf["xst"][2] - 1, inf["xen"][2], device="cuda", dtype=torch.float64)
+        return (k * d) if edge else ((k + 0.5) * d)
+    X, Y = x[None, None, :], x[None, :, None]
+    ZC, ZE = zc(info, False)[:, None, None], zc(infoE, True)[:, None, None]
+    u = (torch.sin(X) * torch.cos(Y) * torch.cos(ZC)).contiguous()
+    v = (-torch.cos(X) * torch.sin(Y) * torch.cos(ZC)).contiguous()
+    w = (0.1 * torch.sin(2 * X) * torch.sin(Y) * torch.sin(ZE)).contiguous()
+    g = pdo.igrid()
+    g.init(n, n, n, 2 * np.pi, 2 * np.pi, 2 * np.pi, 1600.0, u, v, w, TimeSteppingScheme=1, prow=1, pcol=world)
+    dt = 0.2 * d
+    g.timeAdvance(dt)
+    torch.cuda.synchronize()
+    L = pdo.lib()
+    l0 = L.pdo_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        g.timeAdvance(dt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    out = {"workload": f"igrid periodic {n}^3 (global, strong scaling), grid 1x{world}, skew-symmetric, CD06 z, viscous, TVD-RK3",
+           "ms_per_substep": ms / 3.0, "ms_per_step": ms, "unit": "ms", "scaling": "strong",
+           "launches_per_substep": int((L.pdo_launch_count() - l0) // (steps * 3)),
+           "Mpoints_per_s": n ** 3 / (ms / 3.0) / 1e3, "max_divergence": float(g.maxDivergence())}
+    g.destroy() if hasattr(g, "destroy") else None
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -173,17 +224,32 @@ def run_ours(args):
     g = torch.Generator(device="cuda").manual_seed(20240607 + rank)
     f = torch.rand(tuple(reversed(gp.ysz)), dtype=torch.float64, device="cuda", generator=g)   # the field lives in the y-pencil
     df = torch.empty_like(f)
-    tin = pencil(gp.xsz) if world > 1 else None      # transposed copy of f (x- or z-pencil; same volume)
-    tout = pencil(gp.xsz) if world > 1 else None
-    if world > 1:   # transpose destinations: peer-writable, so the fused NVLink path is taken (collective, same order on all ranks)
-        for t in (tin, tout, df):
-            pdo.decomp_2d.register(t)
+    tin = tout = None
+    if world > 1:   # transpose destination: peer-writable, so the fused NVLink path is taken (collective, same order on all ranks)
+        pdo.decomp_2d.register(df)
     st = torch.cuda.current_stream()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
 
+    # N > 1: the field lives in the y-pencil and the three derivatives go through the operators.F90-level entry points
+    # (pdo_operators_ddx/ddy/ddz, what operators.F90:gradient does per axis).  Along z the library distributes the compact
+    # solve over the z-group (halo planes + reduced-system edge pieces over NVLink) instead of transposing the field;
+    # --transposes forces the reference's choreography (transpose, differentiate, transpose back) for comparison.
+    ops = None
+    if world > 1:
+        ops = pdo.vector_ops()
+        ops.init(gp, dx, dy, dz, "cd10", allow_zslab=not args.transposes)
+
+    gx = gy = None
+    if ops is not None:
+        gx, gy = torch.empty_like(f), torch.empty_like(f)
+
     def step(i=None):
-        # tests/test_derivatives_parallel.F90:94-126: transpose to the pencil where the axis is local, differentiate, transpose back
         e = ev[i] if i is not None else None
+        if ops is not None:
+            # one gradient call = ddx + ddy + ddz of the field into three outputs; the z exchange overlaps the x / y kernels
+            ops.gradient(f, gx, gy, df)
+            return
+        # tests/test_derivatives_parallel.F90:94-126: transpose to the pencil where the axis is local, differentiate, transpose back
         if e: e[0].record(st)
         if p_row > 1:
             a, b = tin.view(tuple(reversed(gp.xsz))), tout.view(tuple(reversed(gp.xsz)))
@@ -219,9 +285,10 @@ def run_ours(args):
         step()
     barrier()
     kern_of = []   # which kernel variant the planner settled on, per axis
-    for fn in (der.ddx, der.ddy, der.ddz):
-        if (fn is der.ddx and p_row > 1) or (fn is der.ddz and p_col > 1):
-            kern_of.append("(see transposes)")
+    for ax, fn in enumerate((der.ddx, der.ddy, der.ddz)):
+        if (ax == 0 and p_row > 1) or (ax == 2 and p_col > 1):
+            kern_of.append("z-slab distributed solve: halo push + edge pass + chunk_strided_ctma_kernel" if (ops is not None and ops.zmode == 1)
+                           else "transposes + kernel")
             continue
         fn(f, df)
         kern_of.append(VAR.get(L.pdo_debug_last_variant(), "?"))
@@ -241,7 +308,19 @@ def run_ours(args):
     launches = L.pdo_launch_count() - l0
     clocks = sampler.stop() if sampler else None
     ms = t0.elapsed_time(t1)
-    per = [sum(e[j].elapsed_time(e[j + 1]) for e in ev) / args.steps for j in range(3)]  # ddx, ddy, ddz(+transposes)
+    if ops is None:
+        per = [sum(e[j].elapsed_time(e[j + 1]) for e in ev) / args.steps for j in range(3)]  # ddx, ddy, ddz
+    else:   # per-axis times measured one call at a time, outside the timed region (inside it they overlap)
+        per = []
+        for fn in (ops.ddx, ops.ddy, ops.ddz):
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            for _ in range(5):
+                fn(f, df)
+            b.record(st)
+            barrier()
+            per.append(a.elapsed_time(b) / 5)
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -279,7 +358,31 @@ def run_ours(args):
                "note": "pdo_cd10_dd1/dd2/dd3 called with pinned HOST pointers; the library stages H2D/D2H"}
         del fh, oh
 
+    # ---- igrid RK substep (metric iii), guarded: a failure or a stall here must not cost the headline line ----
+    sub = None
+    sub_holder = {}
+    if not args.no_substep:
+        torch.cuda.synchronize()
+        if world > 1:
+            pdo.decomp_2d.deregister(df)
+        if ops is not None:
+            ops.destroy()
+        del f, df, tin, tout, gx, gy
+        torch.cuda.empty_cache()
+
+        def _run_sub():
+            try:
+                torch.cuda.set_device(local)   # the current device is per thread
+                sub_holder["v"] = substep_leg(args.substep_n, world, rank)
+            except Exception as ex:  # noqa
+                sub_holder["v"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+        th = threading.Thread(target=_run_sub, daemon=True)
+        th.start()
+        th.join(timeout=float(args.substep_timeout))
+        sub = sub_holder.get("v", {"error": f"substep leg did not finish within {args.substep_timeout} s"})
     if rank != 0:
+        if not args.no_substep and "v" not in sub_holder:
+            os._exit(0)
         return
     peak, peak_src = peaks()
     names = [f"cd10 dd{a} ({k})" for a, k in zip("xyz", kern_of)]
@@ -310,11 +413,15 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"cd10 ddx+ddy+ddz, periodic, {nx}x{ny}x{nz} field, 2DECOMP grid {p_row}x{p_col}, "
-                                   f"{npts_rank} points per GPU" + ("; off-pencil axes include their NCCL transposes" if world > 1 else ""),
+                                   f"{npts_rank} points per GPU" + ("" if world == 1 else (
+                                       "; y-pencil field through pdo_operators_gradient (operators.F90:gradient), z via the distributed z-slab solve (no transposes), its exchange overlapped with the x / y kernels"
+                                       if ops.zmode == 1 else "; y-pencil field through pdo_operators_gradient, off-pencil axes by transposes")),
                        "n": n, "global": [nx, ny, nz], "grid": [p_row, p_col],
                        "l2": "inputs (8 GiB per field at n=1024) larger than the 126 MB L2, no flush needed"},
-            "roofline": roof, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+            "roofline": roof, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "substep": sub}
     print(json.dumps(line), flush=True)
+    if not args.no_substep and "v" not in sub_holder:
+        os._exit(0)   # the guarded leg is still stuck in a collective: leave without joining it
 
 
 def main():
@@ -327,6 +434,10 @@ def main():
     ap.add_argument("--e2e-n", type=int, default=0, dest="e2e_n", help="field size of the host-pointer (e2e) leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--transposes", action="store_true", help="N > 1: force the reference's transpose choreography along z")
+    ap.add_argument("--no-substep", action="store_true", dest="no_substep")
+    ap.add_argument("--substep-n", type=int, default=512, dest="substep_n", help="global grid of the igrid substep leg")
+    ap.add_argument("--substep-timeout", type=int, default=150, dest="substep_timeout")
     ap.add_argument("--profile-region", action="store_true", dest="profile_region",
                     help="cudaProfilerStart/Stop around the timed region (for ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -167,6 +167,24 @@ int pdo_transpose_z_to_y(pdo_decomp_t h, const double* src, double* dst, int ele
 int pdo_p_maxval(double local, double* global);
 int pdo_p_sum(double local, double* global);
 
+/* ---- operators  (utilities/operators.F90:17-151): vector calculus on y-pencil fields ----------
+ * gradient(decomp, der, f, dfdx, dfdy, dfdz), curl(decomp, der, u, v, w, curlu), divergence(decomp, der, u, v, w, div):
+ * every argument is a y-pencil array of `gp`; periodic, method "cd10" | "cd06" on all three axes.  Where the reference
+ * transposes to the pencil of the axis and back (operators.F90:43-51), this library does the same on its own
+ * transposes EXCEPT along z when the z-slabs are even multiples of 32 planes and the GPUs have peer access: then the
+ * compact solve itself is distributed (neighbours exchange a few halo planes and the edge pieces of the reduced system
+ * over NVLink; no transpose).  allow_zslab = 0 forces the reference's choreography.  Collective over all ranks. */
+typedef struct pdo_operators_s* pdo_operators_t;
+int pdo_operators_init(pdo_operators_t* h, pdo_decomp_t gp, double dx, double dy, double dz, const char* method, int allow_zslab);
+int pdo_operators_destroy(pdo_operators_t h);
+int pdo_operators_zmode(pdo_operators_t h);  /* 0: z local on this grid, 1: distributed z-slab solve, 2: transposes */
+int pdo_operators_ddx(pdo_operators_t h, const double* f, double* dfdx, void* stream);
+int pdo_operators_ddy(pdo_operators_t h, const double* f, double* dfdy, void* stream);
+int pdo_operators_ddz(pdo_operators_t h, const double* f, double* dfdz, void* stream);
+int pdo_operators_gradient(pdo_operators_t h, const double* f, double* dfdx, double* dfdy, double* dfdz, void* stream);      /* :17-53 */
+int pdo_operators_curl(pdo_operators_t h, const double* u, const double* v, const double* w, double* curlu, void* stream);   /* :55-116 */
+int pdo_operators_divergence(pdo_operators_t h, const double* u, const double* v, const double* w, double* div, void* stream); /* :118-151 */
+
 /* ---- fft_3d_stuff::fft_3d, "x" base pencil  (utilities/fft_3d.F90) ---------------------------- */
 typedef struct pdo_fft3d_s* pdo_fft3d_t;
 /* fft_3d%init(nx,ny,nz,"x",dx,dy,dz,...) on the communicator's grid       fft_3d.F90:109-468 */

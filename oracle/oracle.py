@@ -245,3 +245,29 @@ def poisson_solve(rhs, dx, dy, dz):
     h = np.fft.ifft(h, axis=1) * ny
     f = np.fft.irfft(h, n=nx, axis=2) * nx
     return f * (1.0 / (float(nx) * float(ny) * float(nz)))
+
+
+# ---- utilities/operators.F90: vector calculus on the GLOBAL field (the distributed results are its pencil slices) ----
+def _dd(f, d, axis, method):
+    return cd10(f, d, axis, 1) if method == "cd10" else cd06(f, d, axis)
+
+
+def gradient(f, dx, dy, dz, method="cd10"):
+    """operators.F90:17-53 (periodic): ddy, then ddx, then ddz of the same field."""
+    return _dd(f, dx, 0, method), _dd(f, dy, 1, method), _dd(f, dz, 2, method)
+
+
+def divergence(u, v, w, dx, dy, dz, method="cd10"):
+    """operators.F90:118-151: div = dv/dy; div = div + du/dx; div = div + dw/dz (this order of additions)."""
+    div = _dd(v, dy, 1, method)
+    div = div + _dd(u, dx, 0, method)
+    div = div + _dd(w, dz, 2, method)
+    return div
+
+
+def curl(u, v, w, dx, dy, dz, method="cd10"):
+    """operators.F90:55-116: (dw/dy - dv/dz, du/dz - dw/dx, dv/dx - du/dy), returned as an array (3, nz, ny, nx)."""
+    c1 = _dd(w, dy, 1, method) - _dd(v, dz, 2, method)
+    c2 = _dd(u, dz, 2, method) - _dd(w, dx, 0, method)
+    c3 = _dd(v, dx, 0, method) - _dd(u, dy, 1, method)
+    return np.stack([c1, c2, c3])

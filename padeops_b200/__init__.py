@@ -10,3 +10,4 @@ from .operators import (cd06, cd06stagg, cd10, cf90, derivatives, filters, gauss
 from .decomp import decomp_2d, decomp_info  # noqa: F401
 from .spectral import PoissonPeriodic, fft_3d  # noqa: F401
 from .igrid import Pade6stagg, igrid, padepoisson, spectral  # noqa: F401
+from .vecops import vector_ops  # noqa: F401

@@ -147,6 +147,18 @@ _PROTOS.update({
 })
 for _f in ("ddz_C2E", "ddz_E2C", "interpz_C2E", "interpz_E2C", "d2dz2_C2C", "d2dz2_E2E"):
     _PROTOS[f"pdo_pade6stagg_{_f}"] = (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_void_p])
+_PROTOS.update({
+    "pdo_operators_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_char_p, C.c_int]),
+    "pdo_operators_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_operators_zmode": (C.c_int, [C.c_void_p]),
+    "pdo_operators_ddx": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
+    "pdo_operators_ddy": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
+    "pdo_operators_ddz": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
+    "pdo_operators_gradient": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
+    "pdo_operators_curl": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
+    "pdo_operators_divergence": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
+})
+_PROTOS["pdo_debug_zslab_emulate"] = (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, C.c_longlong, C.c_int, C.c_int, C.c_void_p])
 _PROTOS["pdo_debug_cd10_generic"] = (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.c_int, C.c_void_p])
 
 _PROTOS["pdo_debug_set_variant"] = (C.c_int, [C.c_int, C.c_int])

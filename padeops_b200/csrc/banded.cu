@@ -1100,6 +1100,18 @@ chunk_strided_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
     if (tid == 0) bulk_wait_read<0>();
 }
 
+// Arguments of the z-slab (distributed line) mode of the cluster + TMA kernel.  The periodic line of tab.n points is cut
+// across GPUs into slabs; this GPU solves rows [0, n_local).  `tm_planes` views the received stencil halo rows
+// [2*HB][n1] (HB rows below the slab, then HB rows above it); glo / ghi hold the reduced-system pieces (gA, gB) of the
+// HW = W+1 chunks next to the slab on the lower / upper GPU, laid out [A|B][BW][HW][n1].
+struct ZSlabArgs {
+    CUtensorMap tm_planes;
+    const double* glo;
+    const double* ghi;
+    long long n1;
+    int enabled;
+};
+
 // ------------------------------------------------------------------------------------------------
 // Strided (y / z) kernel, cluster + TMA ("ctma"): for row strides of megabytes (solve axis outermost) what decides the
 // rate is how many bytes every visited row contributes, so the tile must be WIDE (XT = 32 / 64 columns = 256 / 512
@@ -1120,7 +1132,10 @@ template <int RK, int BW, int M>
 __global__ void __launch_bounds__(512, 1)
 chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_halo,
                           const __grid_constant__ CUtensorMap tm_out, int n, int XT, int C, int PC, int tiles_x, long long ntiles,
-                          const __grid_constant__ ChunkTables tab, const __grid_constant__ OpParams op) {
+                          const __grid_constant__ ChunkTables tab, const __grid_constant__ OpParams op,
+                          // z-slab (distributed line) mode: this GPU holds rows [0, n) of a longer periodic line; what lies
+                          // beyond either end was received from the neighbouring GPUs before the launch
+                          const __grid_constant__ ZSlabArgs zs) {
     constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
     constexpr int HB = HL > HR ? HL : HR;           // rows of a halo box
     constexpr int BWc = BW > 0 ? BW : 1;
@@ -1143,6 +1158,8 @@ chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __gri
     const int r0 = p0 * M;                          // first row of this CTA
     const long long ncl = gridDim.x / C;
     const unsigned load_bytes = (unsigned)tile_elems * (unsigned)sizeof(double);
+    const bool dist = zs.enabled != 0;
+    const bool ext_left = dist && rank == 0, ext_right = dist && rank == (unsigned)C - 1;  // halo from another GPU on that side
 
     if (tid == 0) {
 #pragma unroll
@@ -1161,9 +1178,11 @@ chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __gri
         mbar_arrive_expect_tx(bar, load_bytes);
         const int rl = r0 == 0 ? n - HB : r0 - HB;  // periodic wrap: whole halo boxes wrap, never straddle
         const int rr = r0 + RPC == n ? 0 : r0 + RPC;
-        tma_load_3d(smem_u32(buf), &tm_halo, x0, rl, k, bar);
+        if (dist && r0 == 0) tma_load_3d(smem_u32(buf), &zs.tm_planes, x0, 0, 0, bar);        // rows -HB..-1 of the lower GPU
+        else tma_load_3d(smem_u32(buf), &tm_halo, x0, rl, k, bar);
         tma_load_3d(smem_u32(buf + (size_t)HB * XT), &tm_in, x0, r0, k, bar);
-        tma_load_3d(smem_u32(buf + (size_t)(HB + RPC) * XT), &tm_halo, x0, rr, k, bar);
+        if (dist && r0 + RPC == n) tma_load_3d(smem_u32(buf + (size_t)(HB + RPC) * XT), &zs.tm_planes, x0, HB, 0, bar);  // rows n.. of the upper GPU
+        else tma_load_3d(smem_u32(buf + (size_t)(HB + RPC) * XT), &tm_halo, x0, rr, k, bar);
     };
 
     const long long t0 = blockIdx.x / C;
@@ -1176,6 +1195,27 @@ chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __gri
     for (long long tile = t0; tile < ntiles; tile += ncl, ++it) {
         const int b = it % kXtBuf;
         double* buf = smt + b * tile_elems;
+        // z-slab mode: the edge CTAs' halo pieces come from global memory; the loads are issued here, a whole tile's worth of
+        // work before their values are stored into the extended arrays, so their latency is off the cluster's critical path
+        double gl_[2 * BWc];
+        int gslot = -1;
+        if (dist) {
+            const bool lo = ext_left && pl < HW, hi = ext_right && pl >= PC - HW;
+            if (lo || hi) {
+                const long long x = (long long)(tile - (tile / tiles_x) * tiles_x) * XT + xi;
+                const int j = lo ? pl : pl - (PC - HW);
+                gslot = lo ? pl : HW + PC + j;
+                const double* g = lo ? zs.glo : zs.ghi;
+#pragma unroll
+                for (int c = 0; c < BWc; ++c) {
+                    gl_[c] = 0.0; gl_[BWc + c] = 0.0;
+                    if (x < zs.n1) {
+                        asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(gl_[c]) : "l"(g + ((long long)(0 * BWc + c) * HW + j) * zs.n1 + x));
+                        asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(gl_[BWc + c]) : "l"(g + ((long long)(1 * BWc + c) * HW + j) * zs.n1 + x));
+                    }
+                }
+            }
+        }
         mbar_wait_or_trap(smem_u32(&full_bar[b]), (unsigned)(it / kXtBuf) & 1u);
 
         double v[M + HL + HR];
@@ -1198,13 +1238,21 @@ chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __gri
             eB[me] = b_[0];
             if (BW == 2) { eA[ESL + me] = a_[1]; eB[ESL + me] = b_[1]; }
             {
-                const bool to_right = pl >= PC - HW;  // my tail chunks are the right neighbour's left halo
-                const bool to_left = pl < HW;         // my head chunks are the left neighbour's right halo
+                const bool to_right = pl >= PC - HW && !ext_right;  // my tail chunks are the right neighbour's left halo
+                const bool to_left = pl < HW && !ext_left;          // my head chunks are the left neighbour's right halo
                 const int er = (HW + pl - PC) * XT + xi;
                 const int el = (HW + PC + pl) * XT + xi;
+                if (gslot >= 0) {  // halo chunks that live on another GPU (values prefetched at the top of the iteration)
+#pragma unroll
+                    for (int c = 0; c < BW; ++c) {
+                        eA[c * ESL + gslot * XT + xi] = gl_[c];
+                        eB[c * ESL + gslot * XT + xi] = gl_[BWc + c];
+                    }
+                }
                 if (C > 1) {
                     const unsigned bar = smem_u32(&ex_bar);
-                    if (tid == 0) mbar_arrive_expect_tx(bar, (unsigned)(2 * HW * XT * 2 * BW * sizeof(double)));
+                    const unsigned sides_in = (ext_left ? 0u : 1u) + (ext_right ? 0u : 1u);
+                    if (tid == 0) mbar_arrive_expect_tx(bar, sides_in * (unsigned)(HW * XT * 2 * BW * sizeof(double)));
                     const unsigned aA = smem_u32(eA), aB = smem_u32(eB);
                     if (to_right) {
                         const unsigned rr = rank + 1 == (unsigned)C ? 0u : rank + 1;
@@ -1222,7 +1270,7 @@ chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __gri
                         st_async_f64(rB, b_[0], rb);
                         if (BW == 2) { st_async_f64(rA + ESL * 8, a_[1], rb); st_async_f64(rB + ESL * 8, b_[1], rb); }
                     }
-                } else {  // the line lives in this CTA: the halo is a periodic copy of my own edge chunks
+                } else if (!dist) {  // the line lives in this CTA: the halo is a periodic copy of my own edge chunks
                     if (to_right) {
                         eA[er] = a_[0]; eB[er] = b_[0];
                         if (BW == 2) { eA[ESL + er] = a_[1]; eB[ESL + er] = b_[1]; }
@@ -1617,31 +1665,83 @@ cudaError_t launch_stma(const BandedOp* h, const double* f, double* out, long lo
 
 constexpr int kCTma64 = 8, kCTma32 = 9, kCTma32s = 10;  // strided-mode codes of the cluster + TMA kernel (512- / 256-byte row segments)
 
+// z-slab mode, host side (see ZSlabArgs)
+struct ZSlabHost { int n_local; const double* planes; const double* glo; const double* ghi; };
+
+// Edge pass of the z-slab mode: the reduced-system pieces (gA, gB) of this slab's first and last HW chunks, which the
+// neighbouring GPUs need before they can close their separator systems.  One thread per (column, edge chunk); writes go
+// straight into the neighbours' buffers (peer memory over NVLink): to_lower = the lower GPU's `ghi`, to_upper = the
+// upper GPU's `glo`, both [A|B][BW][HW][n1].
+template <int RK, int BW, int M>
+__global__ void __launch_bounds__(128)
+zslab_edge_kernel(const double* __restrict__ f, long long n1, int n_local, const double* __restrict__ planes,
+                  double* __restrict__ to_lower, double* __restrict__ to_upper, int HW, const __grid_constant__ ChunkTables tab,
+                  const __grid_constant__ OpParams op) {
+    constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
+    constexpr int HB = HL > HR ? HL : HR;
+    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n1) return;
+    const int e = blockIdx.y;                       // 0..HW-1: head chunks, HW..2HW-1: tail chunks
+    const int P = n_local / M;
+    const int c = e < HW ? e : P - 2 * HW + e;      // chunk index inside the slab
+    double v[M + HL + HR];
+#pragma unroll
+    for (int j = 0; j < M + HL + HR; ++j) {
+        const int row = c * M - HL + j;
+        double val;
+        if (row < 0) val = planes[(long long)(HB + row) * n1 + x];                       // rows -HB..-1
+        else if (row >= n_local) val = planes[(long long)(HB + row - n_local) * n1 + x];  // rows n_local..
+        else val = f[(long long)row * n1 + x];
+        v[j] = val;
+    }
+    double r[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) r[i] = rhs_eval<RK>(&v[i + HL], op);
+    double a_[2], b_[2];
+    chunk_interior<BW, M>(r, tab, a_, b_);
+    double* dst = e < HW ? to_lower : to_upper;
+    const int j = e < HW ? e : e - HW;
+#pragma unroll
+    for (int k = 0; k < BW; ++k) {
+        dst[((long long)(0 * BW + k) * HW + j) * n1 + x] = a_[k];
+        dst[((long long)(1 * BW + k) * HW + j) * n1 + x] = b_[k];
+    }
+}
+
+// Chunks per CTA of the cluster + TMA kernel for P chunks per line and XT-column tiles: the largest power of two
+// <= pc_max that divides P into a cluster of at most 8 CTAs, keeps a CTA between 64 and 512 threads and 256 rows (one
+// tensor-map box), holds the halo reach HW, and fits three tile buffers in shared memory.  0: no such configuration.
+inline int ctma_chunks_per_cta(int P, int M, int XT, int HB, int HW, int BWc, bool banded, int pc_max, size_t* smem_out) {
+    constexpr size_t cap = 227 * 1024 - 256;
+    for (int pc = pc_max; pc >= 1; pc >>= 1) {
+        if (P % pc != 0) continue;
+        const int c = P / pc;
+        if (c < 1 || c > 8) continue;
+        if (XT * pc > 512 || XT * pc < 64 || pc * M > 256 || (banded && HW > pc)) continue;
+        const size_t need = sizeof(double) * ((size_t)kXtBuf * (pc * M + 2 * HB) * XT + 2 * BWc * (size_t)(pc + 2 * HW) * XT +
+                                              BWc * (size_t)pc * XT);
+        if (need > cap) continue;
+        if (smem_out) *smem_out = need;
+        return pc;
+    }
+    return 0;
+}
+
 template <int RK, int BW, int M>
 cudaError_t launch_ctma(const BandedOp* h, const double* f, double* out, long long n1, long long n3, long long in_slab,
-                        long long out_slab, cudaStream_t st, int XT, int pc_max = 16) {
-    const int n = h->n, P = n / M;
+                        long long out_slab, cudaStream_t st, int XT, int pc_max = 16, const ZSlabHost* z = nullptr) {
+    const int n = z ? z->n_local : h->n, P = n / M;   // z-slab mode: rows held here; the tables stay those of the whole line
     constexpr int BWc = BW > 0 ? BW : 1;
     if (n % M != 0 || (n1 & 1) || n1 >= (1LL << 31) || n3 >= (1LL << 31) || n1 < XT / 2) return cudaErrorInvalidConfiguration;
     if (h->op.edge_in || h->op.edge_out || in_slab != n1 * n || out_slab != n1 * n) return cudaErrorInvalidConfiguration;
     if (BW > 0 && (h->tab.dense || 2 * h->tab.W + 2 > P)) return cudaErrorInvalidConfiguration;
+    if (z && (BW == 0 || n3 != 1)) return cudaErrorInvalidConfiguration;
     constexpr int HB = Halo<RK>::L > Halo<RK>::R ? Halo<RK>::L : Halo<RK>::R;
     const int HW = (BW > 0 ? h->tab.W : 0) + 1;
     if (((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return cudaErrorInvalidConfiguration;
     constexpr size_t cap = 227 * 1024 - 256;
-    int PC = 0;
     size_t smem = 0;
-    for (int pc = pc_max; pc >= 1; pc >>= 1) {
-        if (P % pc != 0) continue;
-        const int c = P / pc;
-        if (!(c == 1 || c == 2 || c == 4 || c == 8)) continue;
-        if (XT * pc > 512 || XT * pc < 64 || pc * M > 256 || (BW > 0 && HW > pc)) continue;
-        const size_t need = sizeof(double) * ((size_t)kXtBuf * (pc * M + 2 * HB) * XT + 2 * BWc * (size_t)(pc + 2 * HW) * XT +
-                                              BWc * (size_t)pc * XT);
-        if (need > cap) continue;
-        PC = pc; smem = need;
-        break;
-    }
+    const int PC = ctma_chunks_per_cta(P, M, XT, HB, HW, BWc, BW > 0, pc_max, &smem);
     if (PC == 0) return cudaErrorInvalidConfiguration;
     const int C = P / PC;
     CUtensorMap tm_in, tm_halo, tm_out;
@@ -1651,6 +1751,12 @@ cudaError_t launch_ctma(const BandedOp* h, const double* f, double* out, long lo
     auto kern = chunk_strided_ctma_kernel<RK, BW, M>;
     static bool attr_done = false;
     static int max_clusters[9][3] = {};
+    ZSlabArgs zs;
+    std::memset(&zs, 0, sizeof(zs));
+    if (z) {
+        if (!encode_field_map(&zs.tm_planes, z->planes, n1, 2 * HB, 1, XT, HB)) return cudaErrorInvalidConfiguration;
+        zs.glo = z->glo; zs.ghi = z->ghi; zs.n1 = n1; zs.enabled = 1;
+    }
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
         if (e != cudaSuccess) return e;
@@ -1680,7 +1786,7 @@ cudaError_t launch_ctma(const BandedOp* h, const double* f, double* out, long lo
     const long long ncl = ntiles < mc ? ntiles : mc;
     cfg.gridDim = dim3((unsigned)(ncl * C));
     g_last_variant = pc_max < 16 ? kCTma32s : (XT == 64 ? kCTma64 : kCTma32);
-    return cudaLaunchKernelEx(&cfg, kern, tm_in, tm_halo, tm_out, n, XT, C, PC, tiles_x, ntiles, h->tab, h->op);
+    return cudaLaunchKernelEx(&cfg, kern, tm_in, tm_halo, tm_out, n, XT, C, PC, tiles_x, ntiles, h->tab, h->op, zs);
 }
 
 template <int RK, int BW, int M>
@@ -1930,6 +2036,72 @@ int banded_debug_last_variant() { return g_last_variant; }
 void banded_debug_set_variant(int strided_mode, int x_threads) {
     g_strided_mode = strided_mode;
     g_x_threads = x_threads;
+}
+
+// ---- z-slab (distributed line) entry points: see banded.cuh ----
+namespace {
+template <int RK, int BW>
+cudaError_t zslab_edges_t(const BandedOp* h, const double* f, long long n1, int n_local, const double* planes, double* to_lower,
+                          double* to_upper, cudaStream_t st) {
+    const int HW = h->tab.W + 1;
+    dim3 grid((unsigned)((n1 + 127) / 128), (unsigned)(2 * HW));
+    zslab_edge_kernel<RK, BW, 32><<<grid, 128, 0, st>>>(f, n1, n_local, planes, to_lower, to_upper, HW, h->tab, h->op);
+    return cudaGetLastError();
+}
+template <int RK, int BW>
+cudaError_t zslab_apply_t(const BandedOp* h, const double* f, double* out, long long n1, const ZSlabHost& z, cudaStream_t st) {
+    const long long slab = n1 * z.n_local;
+    cudaError_t e = launch_ctma<RK, BW, 32>(h, f, out, n1, 1, slab, slab, st, 32, 4, &z);   // two CTAs per SM
+    if (e == cudaErrorInvalidConfiguration) {
+        cudaGetLastError();
+        e = launch_ctma<RK, BW, 32>(h, f, out, n1, 1, slab, slab, st, 32, 16, &z);
+    }
+    return e;
+}
+}  // namespace
+
+int banded_zslab_halo_rows(const BandedOp* h) {
+    switch (h->rk) {
+        case RK_D1_7: case RK_D2_7: return 3;
+        case RK_D1_5: case RK_D2_5: return 2;
+        case RK_SYM_9: return 4;
+        default: return -1;
+    }
+}
+int banded_zslab_halo_chunks(const BandedOp* h, int n_local) {
+    if (h->M != 32 || h->bw == 0 || h->tab.dense || n_local % 32 != 0 || h->op.edge_in || h->op.edge_out) return -1;
+    const int HW = h->tab.W + 1, HB = banded_zslab_halo_rows(h);
+    if (n_local / 32 < 2 * HW || HB < 0) return -1;
+    if (!ctma_chunks_per_cta(n_local / 32, 32, 32, HB, HW, h->bw, true, 4, nullptr) &&
+        !ctma_chunks_per_cta(n_local / 32, 32, 32, HB, HW, h->bw, true, 16, nullptr))
+        return -1;  // no cluster shape covers this slab
+    return HW;
+}
+cudaError_t banded_zslab_edges(const BandedOp* h, const double* f, long long n1, int n_local, const double* planes, double* to_lower,
+                               double* to_upper, cudaStream_t st) {
+    if (banded_zslab_halo_chunks(h, n_local) < 0) return cudaErrorInvalidConfiguration;
+    switch (h->rk * 10 + h->bw) {
+        case RK_D1_7 * 10 + 2: return zslab_edges_t<RK_D1_7, 2>(h, f, n1, n_local, planes, to_lower, to_upper, st);
+        case RK_D2_7 * 10 + 2: return zslab_edges_t<RK_D2_7, 2>(h, f, n1, n_local, planes, to_lower, to_upper, st);
+        case RK_D1_5 * 10 + 1: return zslab_edges_t<RK_D1_5, 1>(h, f, n1, n_local, planes, to_lower, to_upper, st);
+        case RK_SYM_9 * 10 + 2: return zslab_edges_t<RK_SYM_9, 2>(h, f, n1, n_local, planes, to_lower, to_upper, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+cudaError_t banded_zslab_apply(const BandedOp* h, const double* f, double* out, long long n1, int n_local, const double* planes,
+                               const double* glo, const double* ghi, cudaStream_t st) {
+    if (banded_zslab_halo_chunks(h, n_local) < 0) return cudaErrorInvalidConfiguration;
+    ZSlabHost z{n_local, planes, glo, ghi};
+    cudaError_t e;
+    switch (h->rk * 10 + h->bw) {
+        case RK_D1_7 * 10 + 2: e = zslab_apply_t<RK_D1_7, 2>(h, f, out, n1, z, st); break;
+        case RK_D2_7 * 10 + 2: e = zslab_apply_t<RK_D2_7, 2>(h, f, out, n1, z, st); break;
+        case RK_D1_5 * 10 + 1: e = zslab_apply_t<RK_D1_5, 1>(h, f, out, n1, z, st); break;
+        case RK_SYM_9 * 10 + 2: e = zslab_apply_t<RK_SYM_9, 2>(h, f, out, n1, z, st); break;
+        default: e = cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) cudaGetLastError();
+    return e;
 }
 
 cudaError_t banded_dispatch(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3,

@@ -50,6 +50,22 @@ void banded_op_destroy(BandedOp* h);
 cudaError_t banded_op_apply(const BandedOp* h, int axis, const double* f, double* out, long long na, long long nb,
                             cudaStream_t stream, int force_generic = 0);
 
+// z-slab (distributed line) mode of the strided operators: the periodic line of h->n points (the operator is created for
+// the GLOBAL length) is cut across GPUs into slabs of n_local rows each, f(n1, n_local).  Instead of transposing the field
+// so that one GPU holds whole lines, neighbours exchange only (i) `halo_rows` stencil rows and (ii) the reduced-system
+// pieces of `halo_chunks` chunks on each side; the separator systems then close locally.  Buffers:
+//   planes  [2*halo_rows][n1]         rows below the slab (from the lower GPU), then rows above it (from the upper GPU)
+//   glo/ghi [2][bw][halo_chunks][n1]  (gA, gB) of the lower GPU's last / the upper GPU's first halo_chunks chunks
+// banded_zslab_edges computes this slab's own edge pieces and stores them into to_lower (= the lower GPU's ghi) and
+// to_upper (= the upper GPU's glo); both may be peer memory.  banded_zslab_apply is the fused solve.
+// halo_chunks < 0: this operator / slab size is not supported in z-slab mode (callers fall back to transposes).
+int banded_zslab_halo_rows(const BandedOp* h);
+int banded_zslab_halo_chunks(const BandedOp* h, int n_local);
+cudaError_t banded_zslab_edges(const BandedOp* h, const double* f, long long n1, int n_local, const double* planes, double* to_lower,
+                               double* to_upper, cudaStream_t stream);
+cudaError_t banded_zslab_apply(const BandedOp* h, const double* f, double* out, long long n1, int n_local, const double* planes,
+                               const double* glo, const double* ghi, cudaStream_t stream);
+
 // Test hook: force a kernel variant (strided_mode: -1 env/auto, 0 auto, 1 t512, 2 t256, 3 cluster, 4 cluster4,
 // 5 cpipe, 6 pipe1; x_threads: -1 env/default, 128, 256).
 void banded_debug_set_variant(int strided_mode, int x_threads);

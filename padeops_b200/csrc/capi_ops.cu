@@ -197,11 +197,7 @@ int apply(const BandedOp& op, bool is_filter, int axis, const double* f, double*
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-struct pdo_cd10_s { int n; BandedOp d1, d2; };
-struct pdo_cd06_s { int n; BandedOp d1; };
-struct pdo_cf90_s { int n; BandedOp op; };
-struct pdo_gaussian_s { int n; BandedOp op; };
-struct pdo_cd06stagg_s { int n; BandedOp ops[6]; };
+#include "handles.h"
 
 extern "C" {
 
@@ -441,12 +437,6 @@ PDO_STAGG_FN(pdo_cd06stagg_d2dz2_E2E, 5)
 }  // extern "C"
 
 // ---------------- DerivativesMod::derivatives / FiltersMod::filters ----------------
-struct pdo_derivatives_s {
-    int xsz[3], ysz[3], zsz[3];
-    int method[3];  // 0 cd10, 1 cd06
-    pdo_cd10_t c10[3];
-    pdo_cd06_t c06[3];
-};
 struct pdo_filters_s {
     int xsz[3], ysz[3], zsz[3];
     int method[3];  // 0 cf90, 1 gaussian

@@ -525,6 +525,56 @@ int transpose_any(pdo_decomp_t h, int dir, const double* src, double* dst, int w
 }  // namespace
 
 namespace pdo {
+// Collective: allocates `bytes` of zeroed device memory on every rank and maps every rank's copy into this process.
+// peers[r] (r = world rank) is rank r's copy; peers[me] == *local.  Returns 0, or -1 when peer access is unavailable
+// (the allocation is freed again, *local = nullptr) — identically on all ranks.
+// Symmetric allocations are pooled until pdo_comm_finalize: a peer keeps its CUDA-IPC mapping of a buffer open, and
+// freeing memory that is still mapped elsewhere (then getting the same address back from cudaMalloc) is a hazard.
+// alloc / free are collective and happen in the same order on every rank, so every rank picks the same pool entry.
+struct SymPoolEntry { void* base; size_t bytes; std::vector<void*> peers; bool used; };
+std::vector<SymPoolEntry> g_sym_pool;
+
+static int comm_barrier() {
+    int* d = (int*)g_comm.d_xchg;
+    if (ncclAllReduce(d, d + 1, 1, ncclInt, ncclMin, g_comm.comm, 0) != ncclSuccess) return -1;
+    return cudaStreamSynchronize(0) == cudaSuccess ? 0 : -1;
+}
+
+int comm_sym_alloc(size_t bytes, void** local, void** peers) {
+    *local = nullptr;
+    if (!g_comm.inited || g_comm.nproc == 1 || !g_comm.p2p) return -1;
+    for (auto& e : g_sym_pool) {
+        if (e.used || e.bytes < bytes) continue;
+        if (cudaMemset(e.base, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return -1; }
+        if (comm_barrier() != 0) return -1;   // nobody touches a peer's copy before every copy has been cleared
+        e.used = true;
+        for (int r = 0; r < g_comm.nproc; ++r) peers[r] = e.peers[r];
+        *local = e.base;
+        return 0;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
+    if (p) { cudaMemset(p, 0, bytes); cudaDeviceSynchronize(); }
+    if (!p) return -1;  // sizes are symmetric: an allocation failure is taken to be symmetric too
+    const int id = sym_register(p, bytes);
+    if (id < 0) { cudaFree(p); return -1; }
+    SymPoolEntry e;
+    e.base = p; e.bytes = bytes; e.used = true;
+    e.peers.assign(g_comm.sym[id].peer.begin(), g_comm.sym[id].peer.end());
+    for (int r = 0; r < g_comm.nproc; ++r) peers[r] = e.peers[r];
+    g_sym_pool.push_back(e);
+    *local = p;
+    return 0;
+}
+void comm_sym_free(void* p) {
+    for (auto& e : g_sym_pool) if (e.base == p) e.used = false;
+}
+void decomp_grid(pdo_decomp_t h, int* p_row, int* p_col, int* c1, int* c2) {
+    *p_row = h->p_row; *p_col = h->p_col; *c1 = h->c1; *c2 = h->c2;
+}
+void comm_info(int* rank, int* nproc, int* p2p) {
+    *rank = g_comm.rank; *nproc = g_comm.nproc; *p2p = (g_comm.inited && g_comm.p2p) ? 1 : 0;
+}
 void comm_deregister_buffer(void* p) { if (p) pdo_comm_deregister_buffer(p); }
 void comm_register_buffer_quiet(void* p, size_t bytes) { if (g_comm.inited && g_comm.nproc > 1 && g_comm.p2p) sym_register(p, bytes); }
 // used by spectral.cu: transposes on device pointers without the host-pointer probe
@@ -601,6 +651,8 @@ int pdo_comm_finalize(void) {
     if (g_comm.d_scalar) { cudaFree(g_comm.d_scalar); g_comm.d_scalar = nullptr; }
     cudaDeviceSynchronize();
     for (auto& m : g_comm.maps) cudaIpcCloseMemHandle(m.mapped);
+    for (auto& e : pdo::g_sym_pool) cudaFree(e.base);
+    pdo::g_sym_pool.clear();
     if (g_comm.flags) cudaFree(g_comm.flags);
     if (g_comm.d_xchg) cudaFree(g_comm.d_xchg);
     g_comm = Comm();

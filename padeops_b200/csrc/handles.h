@@ -1,0 +1,16 @@
+// handles.h — what the opaque operator handles of include/padeops_b200.h point to (shared by capi_ops.cu and distops.cu).
+#pragma once
+#include "banded.cuh"
+#include "../../include/padeops_b200.h"
+
+struct pdo_cd10_s { int n; pdo::BandedOp d1, d2; };
+struct pdo_cd06_s { int n; pdo::BandedOp d1; };
+struct pdo_cf90_s { int n; pdo::BandedOp op; };
+struct pdo_gaussian_s { int n; pdo::BandedOp op; };
+struct pdo_cd06stagg_s { int n; pdo::BandedOp ops[6]; };
+struct pdo_derivatives_s {
+    int xsz[3], ysz[3], zsz[3];
+    int method[3];  // 0 cd10, 1 cd06
+    pdo_cd10_t c10[3];
+    pdo_cd06_t c06[3];
+};

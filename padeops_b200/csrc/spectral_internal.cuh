@@ -11,6 +11,11 @@ int decomp_transpose_device(pdo_decomp_t h, int dir, const double* src, double* 
 // fused NVLink path.  No-op on one rank or when peer access is unavailable.
 void comm_register_buffer_quiet(void* p, size_t bytes);
 void comm_deregister_buffer(void* p);  // local; call before freeing a registered buffer
+// Collective symmetric allocation (zeroed; peers[world rank] = that rank's copy mapped here); -1 when peer access is unavailable
+int comm_sym_alloc(size_t bytes, void** local, void** peers);
+void comm_sym_free(void* p);
+void comm_info(int* rank, int* nproc, int* p2p);
+void decomp_grid(pdo_decomp_t h, int* p_row, int* p_col, int* c1, int* c2);
 int fft3d_forward_xy(pdo_fft3d_t f, const double* in_real_x, double2* out_cplx_y, cudaStream_t st);
 int fft3d_backward_yx(pdo_fft3d_t f, const double2* in_cplx_y, double* out_real_x, bool set_oddball, cudaStream_t st);
 int fft3d_backward_yx_scratch(pdo_fft3d_t f, double2* prescaled_scratch_cplx_y, double* out_real_x, cudaStream_t st);

@@ -91,6 +91,40 @@ def main():
             got = back(b, None, gp)
         err = np.abs(got.cpu().numpy() - ref).max() / np.abs(ref).max()
         ok(err < 1e-12, f"distributed cd10 axis {ax}: rel err {err:.2e}")
+    # operators.F90 drop-ins on decomposed fields; on 1 x world slabs of 256 planes per GPU
+    # the z-derivative takes the distributed z-slab solve, on world x 1 it is local, and allow_zslab=False is the
+    # reference's transpose choreography
+    for (pr, pc) in grids:
+        for method in ("cd10", "cd06"):
+            nx, ny = 32, 32
+            nz = 256 * pc if pc > 1 else 64         # 8 chunks per slab (CD10 needs 2 x 3 edge chunks and a power-of-two split)
+            if nx < pr or ny < pr:
+                continue
+            dx, dy, dz = 2 * np.pi / nx, 2 * np.pi / ny, 2 * np.pi / nz
+            rng = np.random.default_rng(21)
+            U, V, W = (rng.standard_normal((nz, ny, nx)) for _ in range(3))
+            gp = pdo.decomp_info(nx, ny, nz, pr, pc)
+            loc = [torch.from_numpy(O.scatter_global(A, nx, ny, nz, pr, pc, "y")[rank]).cuda() for A in (U, V, W)]
+            refs = {"grad": O.gradient(U, dx, dy, dz, method), "div": O.divergence(U, V, W, dx, dy, dz, method),
+                    "curl": O.curl(U, V, W, dx, dy, dz, method)}
+            sl = lambda A: O.scatter_global(A, nx, ny, nz, pr, pc, "y")[rank]
+            for allow in (True, False):
+                ops = pdo.vector_ops()
+                ops.init(gp, dx, dy, dz, method, allow_zslab=allow)
+                want_mode = 0 if pc == 1 else (1 if (allow and p2p) else 2)
+                ok(ops.zmode == want_mode, f"vector_ops zmode {ops.zmode} != {want_mode} grid {pr}x{pc} {method} allow={allow}")
+                for rep in range(3):   # parity buffers and epochs of the z-slab exchange
+                    g = ops.gradient(loc[0])
+                    for c in range(3):
+                        e = np.abs(g[c].cpu().numpy() - sl(refs["grad"][c])).max() / np.abs(refs["grad"][c]).max()
+                        ok(e < 1e-12, f"gradient[{c}] grid {pr}x{pc} {method} zmode {ops.zmode} rep {rep}: {e:.2e}")
+                dv = ops.divergence(*loc).cpu().numpy()
+                ok(np.abs(dv - sl(refs["div"])).max() < 1e-12 * np.abs(refs["div"]).max(), f"divergence grid {pr}x{pc} {method} zmode {ops.zmode}")
+                cu = ops.curl(*loc).cpu().numpy()
+                for c in range(3):
+                    ok(np.abs(cu[c] - sl(refs["curl"][c])).max() < 1e-12 * np.abs(refs["curl"]).max(), f"curl[{c}] grid {pr}x{pc} {method} zmode {ops.zmode}")
+                ops.destroy()
+            gp.destroy()
     # pencil-decomposed FFT and Poisson
     for (pr, pc) in grids:
         for (nx, ny, nz) in [(32, 16, 24), (18, 12, 10)]:

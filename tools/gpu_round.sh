@@ -9,7 +9,7 @@ tail -5 gpurun_out/${tag}_pytest_gpu.log
 timeout 300 python bench.py > gpurun_out/${tag}_bench_n1.json 2> gpurun_out/${tag}_bench_n1.err
 cat gpurun_out/${tag}_bench_n1.json
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
-    --log-file gpurun_out/${tag}_launches_bench_n1024.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --profile-region \
+    --log-file gpurun_out/${tag}_launches_bench_n1024.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-substep --profile-region \
     > gpurun_out/${tag}_launches.log 2>&1
 timeout 300 bash tools/ncu_top.sh ${tag}
 for sch in 1 2; do timeout 120 python tools/substep_bench.py 256 $sch 5; done > gpurun_out/${tag}_substep_n1.jsonl 2>&1

@@ -6,6 +6,6 @@ set -u
 tag=${1:-r01}
 mkdir -p gpurun_out
 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/${tag}_cd10_n1024 \
-    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --profile-region > gpurun_out/${tag}_ncu_full.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-substep --profile-region > gpurun_out/${tag}_ncu_full.log 2>&1
 ncu -i gpurun_out/${tag}_cd10_n1024.ncu-rep --page raw --csv > gpurun_out/${tag}_cd10_n1024_raw.csv 2>/dev/null
 ncu -i gpurun_out/${tag}_cd10_n1024.ncu-rep --page details --csv > gpurun_out/${tag}_cd10_n1024_details.csv 2>/dev/null
