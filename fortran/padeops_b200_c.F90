@@ -230,5 +230,34 @@ module padeops_b200_c
             integer(c_int) :: ierr
         end function
         PDO_FFT_FN(pdo_poisson_solve)
+        function pdo_operators_init(h, gp, dx, dy, dz, method, allow_zslab) bind(C, name="pdo_operators_init") result(ierr)
+            import :: c_ptr, c_int, c_double, c_char
+            type(c_ptr), intent(out) :: h
+            type(c_ptr), value :: gp
+            real(c_double), value :: dx, dy, dz
+            character(kind=c_char), dimension(*), intent(in) :: method
+            integer(c_int), value :: allow_zslab
+            integer(c_int) :: ierr
+        end function
+        function pdo_operators_destroy(h) bind(C, name="pdo_operators_destroy") result(ierr)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h
+            integer(c_int) :: ierr
+        end function
+        function pdo_operators_gradient(h, f, dfdx, dfdy, dfdz, stream) bind(C, name="pdo_operators_gradient") result(ierr)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h, f, dfdx, dfdy, dfdz, stream
+            integer(c_int) :: ierr
+        end function
+        function pdo_operators_curl(h, u, v, w, curlu, stream) bind(C, name="pdo_operators_curl") result(ierr)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h, u, v, w, curlu, stream
+            integer(c_int) :: ierr
+        end function
+        function pdo_operators_divergence(h, u, v, w, div, stream) bind(C, name="pdo_operators_divergence") result(ierr)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h, u, v, w, div, stream
+            integer(c_int) :: ierr
+        end function
     end interface
 end module padeops_b200_c

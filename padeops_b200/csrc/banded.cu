@@ -1447,7 +1447,10 @@ cudaError_t banded_op_create(BandedOp* h, int n, int rk, int bw, double b1, doub
         const int M = cands[c];
         if (n % M != 0) continue;
         const int P = n / M;
-        if (P > 128) continue;
+        // whole-line kernels hold a line's chunks in one CTA / cluster: at most 128 chunks.  Longer lines keep their
+        // 32-point tables for the z-slab (distributed) mode, where only the chunks of the local slab meet in a cluster,
+        // and take the any-n kernels when a whole line does arrive on one GPU.
+        if (P > 128 && (M != 32 || bw == 0)) continue;
         if (bw == 0) {
             std::memset(&h->tab, 0, sizeof(h->tab));
             h->tab.n = n; h->tab.M = M; h->tab.P = P;
@@ -2011,7 +2014,8 @@ cudaError_t launch_planned(const BandedOp* h, int axis, const double* f, double*
 template <int RK, int BW>
 cudaError_t launch_any(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3,
                        long long in_slab, long long out_slab, cudaStream_t st, int force_generic) {
-    if (h->M == 32 && !force_generic) return launch_planned<RK, BW, 32>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
+    const bool whole_line_chunked = h->M > 0 && h->n / h->M <= 128;
+    if (h->M == 32 && whole_line_chunked && !force_generic) return launch_planned<RK, BW, 32>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
     if (h->M == 16 && !force_generic) return launch_planned<RK, BW, 16>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
     if (h->M == 8 && !force_generic) return launch_planned<RK, BW, 8>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
     // generic

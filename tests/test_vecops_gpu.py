@@ -39,9 +39,11 @@ def test_vector_ops_single_rank(pdo, oracle, method):
 
 
 @pytest.mark.parametrize("which,nslabs,n,n1", [(0, 2, 512, 96), (0, 4, 1024, 64), (1, 2, 512, 130), (2, 2, 256, 64), (2, 4, 1024, 34),
-                                              (0, 8, 2048, 32)])
+                                              (0, 8, 2048, 32), (0, 8, 8192, 32)])
 def test_zslab_emulated(pdo, oracle, which, nslabs, n, n1):
-    """cd10 d1 / d2 and cd06 d1 along z with the line cut into `nslabs` slabs; n1 includes partial 32-column tiles."""
+    """cd10 d1 / d2 and cd06 d1 along z with the line cut into `nslabs` slabs; n1 includes partial 32-column tiles; the
+    8192-point line (256 chunks: the 8-GPU bench shape) exists only in z-slab mode, its whole-line reference runs on the
+    any-n kernels."""
     import torch
     d = 2 * np.pi / n
     f = broadband((n, 1, n1), seed=n + n1)
