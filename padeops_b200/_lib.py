@@ -161,6 +161,15 @@ _PROTOS.update({
 _PROTOS["pdo_debug_zslab_emulate"] = (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, C.c_longlong, C.c_int, C.c_int, C.c_void_p])
 _PROTOS["pdo_debug_cd10_generic"] = (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.c_int, C.c_void_p])
 
+class ChunkTables(C.Structure):
+    """Mirror of pdo::ChunkTables (csrc/tables.h): kMaxChunk = 32, kMaxW = 16."""
+    _fields_ = [("l1", C.c_double * 32), ("l2", C.c_double * 32), ("ginv", C.c_double * 32), ("ug", C.c_double * 32),
+                ("bg", C.c_double * 32), ("V", (C.c_double * 2) * 32), ("U", (C.c_double * 2) * 32), ("G", (C.c_double * 4) * 33),
+                ("b1", C.c_double), ("b2", C.c_double), ("W", C.c_int), ("dense", C.c_int), ("n", C.c_int), ("M", C.c_int),
+                ("P", C.c_int), ("BW", C.c_int)]
+
+
+_PROTOS["pdo_debug_chunk_tables"] = (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int])
 _PROTOS["pdo_debug_set_variant"] = (C.c_int, [C.c_int, C.c_int])
 _PROTOS["pdo_debug_last_variant"] = (C.c_int, [])
 

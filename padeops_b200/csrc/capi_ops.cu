@@ -205,6 +205,17 @@ const char* pdo_last_error(void) { return g_last_error.c_str(); }
 int pdo_version(void) { return 100; }
 int64_t pdo_launch_count(void) { return (int64_t)g_launches.load(); }
 
+/* Host-only test hook (no device needed): the chunk tables the kernels receive for the cyclic matrix circ[b2 b1 1 b1 b2]
+ * of size n cut into chunks of M points.  `out` receives a copy of pdo::ChunkTables (tables.h); returns 0, -1 if (n, M) is
+ * not chunkable, PDO_E_BADARG if out_bytes does not match the struct. */
+int pdo_debug_chunk_tables(int n, int M, int bw, double b1, double b2, void* out, int out_bytes) {
+    if (!out || out_bytes != (int)sizeof(ChunkTables)) return fail(PDO_E_BADARG, "out_bytes %d != sizeof(ChunkTables) %d", out_bytes, (int)sizeof(ChunkTables));
+    ChunkTables t;
+    const int rc = build_chunk_tables(n, M, bw, b1, b2, &t);
+    std::memcpy(out, &t, sizeof(t));
+    return rc;
+}
+
 int pdo_malloc(void** dptr, size_t bytes) {
     if (int rc = ensure_device()) return rc;
     PDO_CUDA(cudaMalloc(dptr, bytes));
