@@ -98,4 +98,4 @@ def test_cuda_reproduces_golden(pdo, gold):
     g.init(m, m, m, 2 * np.pi, 2 * np.pi, 2 * np.pi, 80.0, gold["ig_U0"], gold["ig_V0"], gold["ig_W0"], TimeSteppingScheme=1)
     g.timeAdvance(0.01)
     for nm in ("u", "v", "w"):
-        assert _rel(g.get(nm), gold[f"ig_{nm}1"]) < 5e-12
+        assert _rel(g.get(nm), gold[f"ig_{nm}1"]) < TOL

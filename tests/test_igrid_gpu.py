@@ -153,7 +153,8 @@ def test_igrid_substep_matches_oracle_broadband(pdo, IG, scheme, inviscid):
         g.timeAdvance(dt)
         for nm in ("u", "v", "w", "wC", "uhat", "vhat", "what"):
             r = getattr(ref, nm)
-            assert np.abs(g.get(nm) - r).max() < 5 * TOL * np.abs(r).max(), (it, nm, np.abs(g.get(nm) - r).max() / np.abs(r).max())
+            # measured: 1e-15 .. 2e-15 after 15 substeps (profiles/r01_igrid_parity.jsonl); the bar is north_star's 1e-12
+            assert np.abs(g.get(nm) - r).max() < TOL * np.abs(r).max(), (it, nm, np.abs(g.get(nm) - r).max() / np.abs(r).max())
     assert g.step == 2 and abs(g.tsim - 2 * dt) < 1e-15
     assert g.maxDivergence() < 1e-11 * scale
 
