@@ -44,3 +44,21 @@ def test_divergence_taylor_green(oracle):
     v = -np.cos(X) * np.sin(Y) * np.cos(Z)
     w = np.zeros_like(u) + 0 * Z
     assert np.abs(oracle.divergence(u, v, w, d, d, d, "cd10")).max() < 1e-9
+
+
+def test_curl_of_rotations_like_test_operators(oracle):
+    """tests/test_operators.F90:67-140 checks curl on the three rigid rotations (u, v, w) = (y, -x, 0), (0, z, -y),
+    (-z, 0, x) of a NON-periodic box (vorticity -2 along the rotation axis).  The periodic counterpart on the hot path:
+    replace each coordinate by its sine, vorticity = -(cos a + cos b) along the axis, zero elsewhere."""
+    n = 48
+    d, X, Y, Z = _grid(n)
+    zero = np.zeros((n, n, n))
+    S = lambda c: np.sin(c) + zero
+    cases = [((S(Y), -S(X), zero), 2, -(np.cos(X) + np.cos(Y))),
+             ((zero, S(Z), -S(Y)), 0, -(np.cos(Y) + np.cos(Z))),
+             ((-S(Z), zero, S(X)), 1, -(np.cos(Z) + np.cos(X)))]
+    for (u, v, w), axis, exact in cases:
+        c = oracle.curl(u, v, w, d, d, d, "cd10")
+        for k in range(3):
+            want = exact + zero if k == axis else zero
+            assert np.abs(c[k] - want).max() < 1e-9, (axis, k)
