@@ -20,7 +20,7 @@ _dp = C.POINTER(C.c_double)
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, s) for s in ("padeops_oracle.c", "decomp_oracle.c", "spectral_oracle.c")]
+    srcs = [os.path.join(_HERE, s) for s in ("padeops_oracle.c", "decomp_oracle.c", "spectral_oracle.c", "nonperiodic_oracle.c")]
     if (not force) and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
         return _SO
     subprocess.check_call(["make", "-C", _HERE, "-s", "all"])
@@ -271,3 +271,28 @@ def curl(u, v, w, dx, dy, dz, method="cd10"):
     c2 = _dd(u, dz, 2, method) - _dd(w, dx, 0, method)
     c3 = _dd(v, dx, 0, method) - _dd(u, dy, 1, method)
     return np.stack([c1, c2, c3])
+
+
+# ---- non-periodic CD10 closures (cd10.F90:29-96, 429-707, 823-851, 1143-1262, 1636-1731); SURVEY.md 8f rank 2 groundwork ----
+def cd10_np(f, dx, axis, which=1, bc1=0, bcn=0):
+    """cd10%dd* (which=1) / d2d* (which=2) with periodic=.false. and boundary codes bc1, bcn in {0, 1, -1}."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    n, na, nb = _na_nb(f, axis)
+    out = np.empty_like(f)
+    rc = lib().pdo_oracle_cd10_np(C.c_int(n), C.c_double(dx), C.c_int(which), C.c_int(bc1), C.c_int(bcn), C.c_int(axis), _p(f), _p(out),
+                                  C.c_int64(na), C.c_int64(nb))
+    assert rc == 0, rc
+    return out
+
+
+def cd10_np_penta(n, which, bc1, bcn):
+    """(ierr, penta(n,11)) of ComputePenta1/2: columns bt, b, d, a, at, e, obc, f, g, eobc (Fortran order: column-major)."""
+    P = np.zeros((11, n))
+    rc = lib().pdo_oracle_cd10_np_penta(C.c_int(n), C.c_int(which), C.c_int(bc1), C.c_int(bcn), _p(P))
+    return rc, P
+
+
+def cd10_np_solve_line(P, y):
+    y = np.ascontiguousarray(y, dtype=np.float64).copy()
+    lib().pdo_oracle_cd10_np_solve_line(C.c_int(y.size), _p(np.ascontiguousarray(P)), _p(y))
+    return y

@@ -1,0 +1,97 @@
+"""CPU: pins the oracle's restatement of the NON-PERIODIC CD10 closures (cd10.F90:29-96, 429-707, 823-851, 1143-1262,
+1636-1731; SURVEY.md §8f rank 2 — groundwork, the CUDA library still refuses periodic = .false.).  Known answers the
+closures must satisfy by construction: every row of the one-sided scheme is at least 4th-order, so polynomials up to
+degree 4 are differentiated exactly; the symmetric / antisymmetric closures are the interior 10th-order scheme applied to
+the even / odd extension of f; and the LU sweeps must solve the pentadiagonal rows they were built from."""
+import numpy as np
+import pytest
+
+
+def _lines(vals, axis, extra=(3, 2)):
+    """A field whose lines along `axis` all equal `vals` (Fortran f(n1,n2,n3) = shape (n3,n2,n1))."""
+    n = vals.size
+    shape = {0: (extra[1], extra[0], n), 1: (extra[1], n, extra[0]), 2: (n, extra[1], extra[0])}[axis]
+    idx = {0: (None, None, slice(None)), 1: (None, slice(None), None), 2: (slice(None), None, None)}[axis]
+    return np.ascontiguousarray(np.broadcast_to(vals[idx], shape))
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("which", [1, 2])
+def test_one_sided_closure_is_exact_for_quartics(oracle, axis, which):
+    n = 41
+    dx = 1.0 / (n - 1)
+    x = np.arange(n) * dx
+    for k in range(5):
+        f = _lines(x ** k, axis)
+        if which == 1:
+            exact = k * x ** (k - 1) if k > 0 else 0 * x
+        else:
+            exact = k * (k - 1) * x ** (k - 2) if k > 1 else 0 * x
+        got = oracle.cd10_np(f, dx, axis, which, 0, 0)
+        assert np.abs(got - _lines(exact, axis)).max() < (5e-13 if which == 1 else 5e-10), (k, axis, which)
+    # degree 5 is NOT exact (4th-order boundary rows): the closure really is in play
+    got = oracle.cd10_np(_lines(x ** 5, axis), dx, axis, which, 0, 0)
+    exact = 5 * x ** 4 if which == 1 else 20 * x ** 3
+    assert 1e-8 < np.abs(got - _lines(exact, axis)).max() < 1e-1
+
+
+@pytest.mark.parametrize("bc1,bcn,fn,d1,d2", [
+    (1, 1, np.cos, lambda x: -np.sin(x), lambda x: -np.cos(x)),                      # even about 0 and pi
+    (-1, -1, np.sin, np.cos, lambda x: -np.sin(x)),                                   # odd about 0 and pi
+    (1, -1, lambda x: np.cos(x / 2), lambda x: -0.5 * np.sin(x / 2), lambda x: -0.25 * np.cos(x / 2)),   # even at 0, odd at pi
+    (-1, 1, lambda x: np.sin(x / 2), lambda x: 0.5 * np.cos(x / 2), lambda x: -0.25 * np.sin(x / 2)),    # odd at 0, even at pi
+])
+def test_symmetry_closures_keep_tenth_order(oracle, bc1, bcn, fn, d1, d2):
+    errs = {1: [], 2: []}
+    for n in (17, 33):
+        dx = np.pi / (n - 1)
+        x = np.arange(n) * dx
+        f = _lines(fn(x), 0)
+        errs[1].append(np.abs(oracle.cd10_np(f, dx, 0, 1, bc1, bcn)[0, 0] - d1(x)).max())
+        errs[2].append(np.abs(oracle.cd10_np(f, dx, 0, 2, bc1, bcn)[0, 0] - d2(x)).max())
+    for which in (1, 2):
+        assert errs[which][1] < 1e-10, (which, errs)
+        order = np.log2(errs[which][0] / max(errs[which][1], 1e-300))
+        assert order > 8.5 or errs[which][0] < 1e-12, (which, errs, order)     # 10th-order interior scheme, no boundary degradation
+
+
+def test_symmetric_closure_equals_periodic_operator_on_the_even_extension(oracle):
+    """bc = (1, 1) on [0, pi] with n points is the periodic scheme on the 2(n-1)-point even extension: same matrix, same
+    right-hand side — the non-periodic restatement and the (separately pinned) periodic one must agree to rounding."""
+    n = 21
+    dx = np.pi / (n - 1)
+    rng = np.random.default_rng(4)
+    h = rng.standard_normal(n)
+    ext = np.concatenate([h, h[-2:0:-1]])                 # even about both ends, period 2(n-1)
+    per1 = oracle.cd10(_lines(ext, 0), dx, 0, 1)[0, 0]
+    per2 = oracle.cd10(_lines(ext, 0), dx, 0, 2)[0, 0]
+    np1 = oracle.cd10_np(_lines(h, 0), dx, 0, 1, 1, 1)[0, 0]
+    np2 = oracle.cd10_np(_lines(h, 0), dx, 0, 2, 1, 1)[0, 0]
+    assert np.abs(np1 - per1[:n]).max() < 1e-12 * np.abs(per1).max()
+    assert np.abs(np2 - per2[:n]).max() < 1e-12 * np.abs(per2).max()
+    odd = np.concatenate([h, -h[-2:0:-1]])
+    odd[0] = odd[n - 1] = 0.0
+    g = h.copy(); g[0] = g[-1] = 0.0
+    per1 = oracle.cd10(_lines(odd, 0), dx, 0, 1)[0, 0]
+    np1 = oracle.cd10_np(_lines(g, 0), dx, 0, 1, -1, -1)[0, 0]
+    assert np.abs(np1 - per1[:n]).max() < 1e-12 * np.abs(per1).max()
+
+
+@pytest.mark.parametrize("which", [1, 2])
+@pytest.mark.parametrize("bc1", [0, 1, -1])
+@pytest.mark.parametrize("bcn", [0, 1, -1])
+def test_lu_sweeps_solve_the_rows_they_were_built_from(oracle, which, bc1, bcn):
+    n = 24
+    rc, P = oracle.cd10_np_penta(n, which, bc1, bcn)
+    assert rc == 0
+    bt, b, d, a, at = P[0], P[1], P[2], P[3], P[4]
+    A = np.diag(d) + np.diag(a[:-1], 1) + np.diag(at[:-2], 2) + np.diag(b[1:], -1) + np.diag(bt[2:], -2)
+    r = np.random.default_rng(n + which).standard_normal(n)
+    x = oracle.cd10_np_solve_line(P, r)
+    assert np.abs(A @ x - r).max() < 1e-12 * np.abs(r).max() * np.linalg.cond(A)
+    assert np.abs(x - np.linalg.solve(A, r)).max() < 1e-12 * np.abs(x).max() * max(1.0, np.linalg.cond(A) / 10)
+
+
+def test_short_lines_and_bad_codes_are_refused(oracle):
+    assert oracle.cd10_np_penta(7, 1, 0, 0)[0] == 2
+    assert oracle.cd10_np_penta(16, 1, 2, 0)[0] == 324      # cd10.F90:2044-2046
