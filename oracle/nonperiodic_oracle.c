@@ -1,5 +1,5 @@
-/* nonperiodic_oracle.c — CPU restatement of the NON-PERIODIC CD10 closures (groundwork: the CUDA
- * library does not implement them yet and returns PDO_E_UNSUPPORTED for periodic = .false.).
+/* nonperiodic_oracle.c — CPU restatement of the NON-PERIODIC CD10 and CF90 closures (groundwork: the
+ * CUDA library does not implement them yet and returns PDO_E_UNSUPPORTED for periodic = .false.).
  *
  * TEST INFRASTRUCTURE ONLY (see padeops_oracle.c).  Follows derivatives/cd10.F90 statement by statement:
  *   boundary-scheme constants            cd10.F90:29-96
@@ -307,6 +307,132 @@ int pdo_oracle_cd10_np(int n, double dx, int which, int bc1, int bcn, int axis, 
             else d2_rhs_line(n, onebydx2, bc1, bcn, lf - 1, lr - 1);
             penta_solve_line(n, P, lr - 1);
             for (int i = 0; i < n; ++i) df[base + (int64_t)i * stride] = lr[i];
+        }
+    free(P); free(lf); free(lr);
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * CF90 non-periodic filter: filters/cf90.F90:24-47 (boundary constants), 276-418 (ComputePenta), 532-558 (SolveXPenta,
+ * the same sweeps as cd10's), 672-801 (ComputeXRHS, periodic = .false.).  First / last point are the identity for bc = 0.
+ * --------------------------------------------------------------------------------------------------------------- */
+static const double alpha90 = 6.6624e-1, beta90 = 1.6688e-1;
+static const double a90 = 9.9965e-1, b90 = 6.6652e-1, c90 = 1.6674e-1, d90 = 4.0e-5, e90 = -5.0e-6;
+static const double b2_alpha90 = 4.997e-1, b2_a90 = 9.997e-1, b2_b90 = 4.9985e-1;
+static const double b3_alpha90 = 6.6624e-1, b3_beta90 = 1.6688e-1, b3_a90 = 9.9952e-1, b3_b90 = 6.6656e-1, b3_c90 = 1.668e-1;
+static const double b4_alpha90 = 6.6624e-1, b4_beta90 = 1.6688e-1, b4_a90 = 9.9968e-1, b4_b90 = 6.6652e-1, b4_c90 = 1.6672e-1,
+                    b4_d90 = 4.0e-5;
+
+int pdo_oracle_cf90_np_penta(int n, int bc1, int bcn, double *P)
+{
+    if (n < 10) return 7; /* cf90.F90:128: the periodic guard; 10 points also keep the two closures apart */
+    memset(P, 0, sizeof(double) * 11 * (size_t)n);
+    double *bt = COL(P, 1), *b = COL(P, 2), *d = COL(P, 3), *a = COL(P, 4), *at = COL(P, 5);
+    for (int i = 1; i <= n; ++i) { at[i] = beta90; bt[i] = beta90; a[i] = alpha90; b[i] = alpha90; d[i] = 1.0; }
+    switch (bc1) {
+    case 0:
+        bt[1] = 0; b[1] = 0; d[1] = 1; a[1] = 0; at[1] = 0;
+        bt[2] = 0; b[2] = b2_alpha90; d[2] = 1; a[2] = b2_alpha90; at[2] = 0;
+        bt[3] = b3_beta90; b[3] = b3_alpha90; d[3] = 1; a[3] = b3_alpha90; at[3] = b3_beta90;
+        bt[4] = b4_beta90; b[4] = b4_alpha90; d[4] = 1; a[4] = b4_alpha90; at[4] = b4_beta90;
+        break;
+    case 1:
+        bt[1] = 0; b[1] = 0; d[1] = 1; a[1] = 2 * alpha90; at[1] = 2 * beta90;
+        bt[2] = 0; b[2] = alpha90; d[2] = 1 + beta90; a[2] = alpha90; at[2] = beta90;
+        break;
+    case -1:
+        bt[1] = 0; b[1] = 0; d[1] = 1; a[1] = 0; at[1] = 0;
+        bt[2] = 0; b[2] = alpha90; d[2] = 1 - beta90; a[2] = alpha90; at[2] = beta90;
+        break;
+    default: return 324;
+    }
+    switch (bcn) {
+    case 0:
+        bt[n] = 0; b[n] = 0; d[n] = 1; a[n] = 0; at[n] = 0;
+        bt[n - 1] = 0; b[n - 1] = b2_alpha90; d[n - 1] = 1; a[n - 1] = b2_alpha90; at[n - 1] = 0;
+        bt[n - 2] = b3_beta90; b[n - 2] = b3_alpha90; d[n - 2] = 1; a[n - 2] = b3_alpha90; at[n - 2] = b3_beta90;
+        bt[n - 3] = b4_beta90; b[n - 3] = b4_alpha90; d[n - 3] = 1; a[n - 3] = b4_alpha90; at[n - 3] = b4_beta90;
+        break;
+    case 1:
+        bt[n] = 2 * beta90; b[n] = 2 * alpha90; d[n] = 1; a[n] = 0; at[n] = 0;
+        bt[n - 1] = beta90; b[n - 1] = alpha90; d[n - 1] = 1 + beta90; a[n - 1] = alpha90; at[n - 1] = 0;
+        break;
+    case -1:
+        bt[n] = 0; b[n] = 0; d[n] = 1; a[n] = 0; at[n] = 0;
+        bt[n - 1] = beta90; b[n - 1] = alpha90; d[n - 1] = 1 - beta90; a[n - 1] = alpha90; at[n - 1] = 0;
+        break;
+    default: return 324;
+    }
+    penta_factor(n, P);
+    return 0;
+}
+
+/* ComputeXRHS, periodic = .false. (cf90.F90:672-801) on one line; 1-based views */
+static void cf90_rhs_line(int n, int bc1, int bcn, const double *f, double *R)
+{
+    switch (bc1) {
+    case 0:
+        R[1] = 1.0 * (f[1]);
+        R[2] = b2_a90 * (f[2]) + b2_b90 * (f[3] + f[1]);
+        R[3] = b3_a90 * (f[3]) + b3_b90 * (f[4] + f[2]) + b3_c90 * (f[5] + f[1]);
+        R[4] = b4_a90 * (f[4]) + b4_b90 * (f[5] + f[3]) + b4_c90 * (f[6] + f[2]) + b4_d90 * (f[7] + f[1]);
+        break;
+    case 1:
+        R[1] = a90 * (f[1]) + b90 * (f[2] + f[2]) + c90 * (f[3] + f[3]) + d90 * (f[4] + f[4]) + e90 * (f[5] + f[5]);
+        R[2] = a90 * (f[2]) + b90 * (f[3] + f[1]) + c90 * (f[4] + f[2]) + d90 * (f[5] + f[3]) + e90 * (f[6] + f[4]);
+        R[3] = a90 * (f[3]) + b90 * (f[4] + f[2]) + c90 * (f[5] + f[1]) + d90 * (f[6] + f[2]) + e90 * (f[7] + f[3]);
+        R[4] = a90 * (f[4]) + b90 * (f[5] + f[3]) + c90 * (f[6] + f[2]) + d90 * (f[7] + f[1]) + e90 * (f[8] + f[2]);
+        break;
+    default: /* -1 */
+        R[1] = a90 * (f[1]) + b90 * (f[2] - f[2]) + c90 * (f[3] - f[3]) + d90 * (f[4] - f[4]) + e90 * (f[5] - f[5]);
+        R[2] = a90 * (f[2]) + b90 * (f[3] + f[1]) + c90 * (f[4] - f[2]) + d90 * (f[5] - f[3]) + e90 * (f[6] - f[4]);
+        R[3] = a90 * (f[3]) + b90 * (f[4] + f[2]) + c90 * (f[5] + f[1]) + d90 * (f[6] - f[2]) + e90 * (f[7] - f[3]);
+        R[4] = a90 * (f[4]) + b90 * (f[5] + f[3]) + c90 * (f[6] + f[2]) + d90 * (f[7] + f[1]) + e90 * (f[8] - f[2]);
+        break;
+    }
+    for (int i = 5; i <= n - 4; ++i)
+        R[i] = a90 * (f[i]) + b90 * (f[i + 1] + f[i - 1]) + c90 * (f[i + 2] + f[i - 2]) + d90 * (f[i + 3] + f[i - 3]) + e90 * (f[i + 4] + f[i - 4]);
+    switch (bcn) {
+    case 0:
+        R[n - 3] = b4_a90 * (f[n - 3]) + b4_b90 * (f[n - 2] + f[n - 4]) + b4_c90 * (f[n - 1] + f[n - 5]) + b4_d90 * (f[n] + f[n - 6]);
+        R[n - 2] = b3_a90 * (f[n - 2]) + b3_b90 * (f[n - 1] + f[n - 3]) + b3_c90 * (f[n] + f[n - 4]);
+        R[n - 1] = b2_a90 * (f[n - 1]) + b2_b90 * (f[n] + f[n - 2]);
+        R[n] = 1.0 * (f[n]);
+        break;
+    case 1:
+        R[n - 3] = a90 * (f[n - 3]) + b90 * (f[n - 2] + f[n - 4]) + c90 * (f[n - 1] + f[n - 5]) + d90 * (f[n] + f[n - 6]) + e90 * (f[n - 1] + f[n - 7]);
+        R[n - 2] = a90 * (f[n - 2]) + b90 * (f[n - 1] + f[n - 3]) + c90 * (f[n] + f[n - 4]) + d90 * (f[n - 1] + f[n - 5]) + e90 * (f[n - 2] + f[n - 6]);
+        R[n - 1] = a90 * (f[n - 1]) + b90 * (f[n] + f[n - 2]) + c90 * (f[n - 1] + f[n - 3]) + d90 * (f[n - 2] + f[n - 4]) + e90 * (f[n - 3] + f[n - 5]);
+        R[n] = a90 * (f[n]) + b90 * (f[n - 1] + f[n - 1]) + c90 * (f[n - 2] + f[n - 2]) + d90 * (f[n - 3] + f[n - 3]) + e90 * (f[n - 4] + f[n - 4]);
+        break;
+    default: /* -1 */
+        R[n - 3] = a90 * (f[n - 3]) + b90 * (f[n - 2] + f[n - 4]) + c90 * (f[n - 1] + f[n - 5]) + d90 * (f[n] + f[n - 6]) + e90 * (-f[n - 1] + f[n - 7]);
+        R[n - 2] = a90 * (f[n - 2]) + b90 * (f[n - 1] + f[n - 3]) + c90 * (f[n] + f[n - 4]) + d90 * (-f[n - 1] + f[n - 5]) + e90 * (-f[n - 2] + f[n - 6]);
+        R[n - 1] = a90 * (f[n - 1]) + b90 * (f[n] + f[n - 2]) + c90 * (-f[n - 1] + f[n - 3]) + d90 * (-f[n - 2] + f[n - 4]) + e90 * (-f[n - 3] + f[n - 5]);
+        R[n] = a90 * (f[n]) + b90 * (-f[n - 1] + f[n - 1]) + c90 * (-f[n - 2] + f[n - 2]) + d90 * (-f[n - 3] + f[n - 3]) + e90 * (-f[n - 4] + f[n - 4]);
+        break;
+    }
+}
+
+/* cf90%filter1/2/3 with periodic = .false. along `axis`; (n, na, nb) as in pdo_oracle_cd10_np */
+int pdo_oracle_cf90_np(int n, int bc1, int bcn, int axis, const double *f, double *out, int64_t na, int64_t nb)
+{
+    double *P = (double *)malloc(sizeof(double) * 11 * (size_t)n);
+    double *lf = (double *)malloc(sizeof(double) * (size_t)n), *lr = (double *)malloc(sizeof(double) * (size_t)n);
+    if (!P || !lf || !lr) { free(P); free(lf); free(lr); return -1; }
+    int rc = pdo_oracle_cf90_np_penta(n, bc1, bcn, P);
+    if (rc) { free(P); free(lf); free(lr); return rc; }
+    int64_t stride, nlines_in, nlines_out, in_step, out_step;
+    if (axis == 0) { stride = 1; nlines_in = na * nb; nlines_out = 1; in_step = n; out_step = 0; }
+    else if (axis == 1) { stride = na; nlines_in = na; nlines_out = nb; in_step = 1; out_step = na * (int64_t)n; }
+    else { stride = na * nb; nlines_in = na * nb; nlines_out = 1; in_step = 1; out_step = 0; }
+    for (int64_t io = 0; io < nlines_out; ++io)
+        for (int64_t ii = 0; ii < nlines_in; ++ii) {
+            const int64_t base = io * out_step + ii * in_step;
+            for (int i = 0; i < n; ++i) lf[i] = f[base + (int64_t)i * stride];
+            cf90_rhs_line(n, bc1, bcn, lf - 1, lr - 1);
+            penta_solve_line(n, P, lr - 1);
+            for (int i = 0; i < n; ++i) out[base + (int64_t)i * stride] = lr[i];
         }
     free(P); free(lf); free(lr);
     return 0;

@@ -296,3 +296,19 @@ def cd10_np_solve_line(P, y):
     y = np.ascontiguousarray(y, dtype=np.float64).copy()
     lib().pdo_oracle_cd10_np_solve_line(C.c_int(y.size), _p(np.ascontiguousarray(P)), _p(y))
     return y
+
+
+def cf90_np(f, axis, bc1=0, bcn=0):
+    """cf90%filter1/2/3 with periodic=.false. (filters/cf90.F90:276-418, 532-558, 672-801)."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    n, na, nb = _na_nb(f, axis)
+    out = np.empty_like(f)
+    rc = lib().pdo_oracle_cf90_np(C.c_int(n), C.c_int(bc1), C.c_int(bcn), C.c_int(axis), _p(f), _p(out), C.c_int64(na), C.c_int64(nb))
+    assert rc == 0, rc
+    return out
+
+
+def cf90_np_penta(n, bc1, bcn):
+    P = np.zeros((11, n))
+    rc = lib().pdo_oracle_cf90_np_penta(C.c_int(n), C.c_int(bc1), C.c_int(bcn), _p(P))
+    return rc, P

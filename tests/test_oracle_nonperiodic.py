@@ -95,3 +95,53 @@ def test_lu_sweeps_solve_the_rows_they_were_built_from(oracle, which, bc1, bcn):
 def test_short_lines_and_bad_codes_are_refused(oracle):
     assert oracle.cd10_np_penta(7, 1, 0, 0)[0] == 2
     assert oracle.cd10_np_penta(16, 1, 2, 0)[0] == 324      # cd10.F90:2044-2046
+
+
+# ---- CF90 non-periodic (filters/cf90.F90:24-47, 276-418, 532-558, 672-801) ----
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_cf90_np_preserves_constants_and_keeps_the_end_points(oracle, axis):
+    n = 32
+    rng = np.random.default_rng(8)
+    f = _lines(rng.standard_normal(n), axis)
+    out = oracle.cf90_np(f, axis, 0, 0)
+    first = {0: (Ellipsis, 0), 1: (slice(None), 0, slice(None)), 2: (0,)}[axis]
+    last = {0: (Ellipsis, n - 1), 1: (slice(None), n - 1, slice(None)), 2: (n - 1,)}[axis]
+    assert np.array_equal(out[first], f[first]) and np.array_equal(out[last], f[last])      # "first point is just identity"
+    c = _lines(np.full(n, 2.5), axis)
+    for bc in ((0, 0), (1, 1), (1, 0), (0, 1)):
+        assert np.abs(oracle.cf90_np(c, axis, *bc) - 2.5).max() < 1e-12, bc
+    # the highest representable mode is removed in the interior (what the filter is for), smooth modes pass
+    x = np.arange(n)
+    saw = oracle.cf90_np(_lines((-1.0) ** x, 0), 0, 1, 1)[0, 0]
+    assert np.abs(saw[6:-6]).max() < 1e-3
+    smooth = np.cos(np.pi * x / (n - 1))
+    assert np.abs(oracle.cf90_np(_lines(smooth, 0), 0, 1, 1)[0, 0] - smooth).max() < 1e-6
+
+
+def test_cf90_np_symmetry_closures_equal_the_periodic_filter_on_the_extension(oracle):
+    n = 24
+    rng = np.random.default_rng(5)
+    h = rng.standard_normal(n)
+    ext = np.concatenate([h, h[-2:0:-1]])
+    per = oracle.cf90(_lines(ext, 0), 0)[0, 0]
+    got = oracle.cf90_np(_lines(h, 0), 0, 1, 1)[0, 0]
+    assert np.abs(got - per[:n]).max() < 1e-12 * np.abs(per).max()
+    g = h.copy(); g[0] = g[-1] = 0.0
+    odd = np.concatenate([g, -g[-2:0:-1]])
+    per = oracle.cf90(_lines(odd, 0), 0)[0, 0]
+    got = oracle.cf90_np(_lines(g, 0), 0, -1, -1)[0, 0]
+    assert np.abs(got - per[:n]).max() < 1e-12 * np.abs(per).max()
+
+
+@pytest.mark.parametrize("bc1", [0, 1, -1])
+@pytest.mark.parametrize("bcn", [0, 1, -1])
+def test_cf90_np_lu_solves_its_rows(oracle, bc1, bcn):
+    n = 20
+    rc, P = oracle.cf90_np_penta(n, bc1, bcn)
+    assert rc == 0
+    bt, b, d, a, at = P[0], P[1], P[2], P[3], P[4]
+    A = np.diag(d) + np.diag(a[:-1], 1) + np.diag(at[:-2], 2) + np.diag(b[1:], -1) + np.diag(bt[2:], -2)
+    r = np.random.default_rng(n).standard_normal(n)
+    x = oracle.cd10_np_solve_line(P, r)
+    assert np.abs(x - np.linalg.solve(A, r)).max() < 1e-12 * np.abs(x).max() * max(1.0, np.linalg.cond(A) / 10)
+    assert oracle.cf90_np_penta(9, 0, 0)[0] == 7
