@@ -48,7 +48,10 @@ int pdo_stream_sync(void* stream);
 
 /* ---- cd10stuff::cd10  (derivatives/cd10.F90) ------------------------------------------------- */
 typedef struct pdo_cd10_s* pdo_cd10_t;
-/* cd10%init(n, dx, periodic, bc1, bcn)                                     cd10.F90:195-315 */
+/* cd10%init(n, dx, periodic, bc1, bcn)                                     cd10.F90:195-315
+ * periodic = 1: cyclic pentadiagonal operators (the fast chunked kernels).  periodic = 0: the non-periodic closures
+ * (cd10.F90:29-96, 429-707), all nine tables built like the reference; dd* / d2d* then select by the bc1, bcn passed at the
+ * call (0 one-sided, 1 symmetric, -1 antisymmetric; anything else -> 324).  Correctness path (one thread per line). */
 int pdo_cd10_init(pdo_cd10_t* h, int n, double dx, int periodic, int bc1, int bcn);
 int pdo_cd10_destroy(pdo_cd10_t h);                                      /* cd10.F90:317-341 */
 int pdo_cd10_getsize(pdo_cd10_t h);                                      /* GetSize */
@@ -72,7 +75,8 @@ int pdo_cd06_dd3(pdo_cd06_t h, const double* f, double* df, int na, int nb, int 
 
 /* ---- cf90stuff::cf90  (filters/cf90.F90) ----------------------------------------------------- */
 typedef struct pdo_cf90_s* pdo_cf90_t;
-int pdo_cf90_init(pdo_cf90_t* h, int n, int periodic);                                 /* cf90.F90:107-196 */
+int pdo_cf90_init(pdo_cf90_t* h, int n, int periodic);                                 /* cf90.F90:107-196; periodic = 0: the
+                                                                                          closures of cf90.F90:24-47, 276-418 */
 int pdo_cf90_destroy(pdo_cf90_t h);
 int pdo_cf90_filter1(pdo_cf90_t h, const double* f, double* fil, int na, int nb, int bc1, int bcn, void* stream); /* :1020 */
 int pdo_cf90_filter2(pdo_cf90_t h, const double* f, double* fil, int na, int nb, int bc1, int bcn, void* stream); /* :1090 */

@@ -7,6 +7,7 @@
 
 #include "banded.cuh"
 #include "common.cuh"
+#include "nonperiodic.cuh"
 
 namespace pdo {
 thread_local std::string g_last_error;
@@ -194,6 +195,21 @@ int apply(const BandedOp& op, bool is_filter, int axis, const double* f, double*
                              });
 }
 
+// periodic = .false.: the closures of nonperiodic.cu (correctness path; host pointers take the plain staged route)
+int apply_np(const NpOp& op, bool is_filter, int axis, const double* f, double* out, long long na, long long nb, int bc1, int bcn,
+             void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!f || !out) return fail(PDO_E_BADARG, "null field pointer");
+    if (na < 0 || nb < 0) return fail(PDO_E_BADARG, "negative extent");
+    const size_t count = (size_t)op.n * na * nb;
+    if (op.n == 1) return degenerate(is_filter, f, out, count, st);
+    return with_device_views(f, count * sizeof(double), out, count * sizeof(double), st, [&](const void* din, void* dout) -> int {
+        PDO_CUDA(np_op_apply(&op, axis, (const double*)din, (double*)dout, na, nb, bc1, bcn, st));
+        g_launches += 2;
+        return 0;
+    });
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -214,6 +230,15 @@ int pdo_debug_chunk_tables(int n, int M, int bw, double b1, double b2, void* out
     const int rc = build_chunk_tables(n, M, bw, b1, b2, &t);
     std::memcpy(out, &t, sizeof(t));
     return rc;
+}
+
+/* Host-only test hook: the non-periodic closures computed by the SAME __host__ __device__ routines the kernels execute
+ * (nonperiodic.cuh), on the host, so that CPU tests can check the transcription of the boundary rows and the LU sweeps.
+ * kind: 0 cd10 d1, 1 cd10 d2, 2 cf90.  Not reachable from any public entry point: the API itself needs a GPU. */
+int pdo_debug_np_line_host(int kind, int n, double dx, int bc1, int bcn, int axis, const double* f, double* out, long long na,
+                           long long nb) {
+    if (!f || !out || axis < 0 || axis > 2) return fail(PDO_E_BADARG, "bad argument");
+    return np_apply_host(kind, n, dx, bc1, bcn, axis, f, out, na, nb);
 }
 
 int pdo_malloc(void** dptr, size_t bytes) {
@@ -240,11 +265,28 @@ int pdo_stream_sync(void* stream) {
 
 // ---------------- cd10 ----------------
 int pdo_cd10_init(pdo_cd10_t* h, int n, double dx, int periodic, int bc1, int bcn) {
-    (void)bc1; (void)bcn;
     if (!h) return fail(PDO_E_BADARG, "null handle");
     *h = nullptr;
     if (n < 1) return fail(PDO_E_BADARG, "n < 1");
-    if (!periodic) return fail(PDO_E_UNSUPPORTED, "cd10: non-periodic closures are out of scope (SURVEY.md 8f rank 2)");
+    if (!periodic) {   // cd10.F90:238-321: the nine penta tables of each derivative
+        if ((bc1 != 0 && bc1 != 1 && bc1 != -1) || (bcn != 0 && bcn != 1 && bcn != -1))
+            return fail(324, "Incorrect boundary specification for bc1/bcn (should be 0, 1 or -1)");
+        if (n != 1 && n < 8) return fail(2, "cd10: non-periodic n must be 1 or >= 8");
+        if (int rc = ensure_device()) return rc;
+        pdo_cd10_s* o = new (std::nothrow) pdo_cd10_s();
+        if (!o) return fail(PDO_E_BADARG, "out of memory");
+        o->n = n; o->periodic = false;
+        int ie1 = 0, ie2 = 0;
+        cudaError_t e = np_op_create(&o->np_d1, NP_CD10_D1, n, dx, &ie1);
+        if (e == cudaSuccess) e = np_op_create(&o->np_d2, NP_CD10_D2, n, dx, &ie2);
+        if (e != cudaSuccess || ie1 || ie2) {
+            np_op_destroy(&o->np_d1); np_op_destroy(&o->np_d2);
+            delete o;
+            return e != cudaSuccess ? fail(PDO_E_CUDA, "cd10 init: %s", cudaGetErrorString(e)) : fail(ie1 ? ie1 : ie2, "cd10: non-periodic tables");
+        }
+        *h = o;
+        return 0;
+    }
     if (n != 1 && n < 8) return fail(2, "cd10: periodic n must be 1 or >= 8");  // cd10.F90:219-226
     if (int rc = ensure_device()) return rc;
     pdo_cd10_s* o = new (std::nothrow) pdo_cd10_s();
@@ -265,8 +307,8 @@ int pdo_cd10_init(pdo_cd10_t* h, int n, double dx, int periodic, int bc1, int bc
 }
 int pdo_cd10_destroy(pdo_cd10_t h) {
     if (!h) return 0;
-    banded_op_destroy(&h->d1);
-    banded_op_destroy(&h->d2);
+    if (h->periodic) { banded_op_destroy(&h->d1); banded_op_destroy(&h->d2); }
+    else { np_op_destroy(&h->np_d1); np_op_destroy(&h->np_d2); }
     delete h;
     return 0;
 }
@@ -276,6 +318,7 @@ int pdo_cd10_getsize(pdo_cd10_t h) { return h ? h->n : -1; }
     int name(pdo_cd10_t h, const double* f, double* df, int na, int nb, int bc1, int bcn, void* stream) { \
         if (!h) return fail(PDO_E_BADARG, "null handle");                                                 \
         if (int rc = check_bc(bc1, bcn)) return rc;                                                       \
+        if (!h->periodic) return apply_np(h->np_##member, false, axis, f, df, na, nb, bc1, bcn, stream);   \
         return apply(h->member, false, axis, f, df, na, nb, stream);                                      \
     }
 PDO_CD10_FN(pdo_cd10_dd1, d1, 0)
@@ -330,12 +373,23 @@ int pdo_cf90_init(pdo_cf90_t* h, int n, int periodic) {
     if (!h) return fail(PDO_E_BADARG, "null handle");
     *h = nullptr;
     if (n < 1) return fail(PDO_E_BADARG, "n < 1");
-    if (!periodic) return fail(PDO_E_UNSUPPORTED, "cf90: non-periodic closures are out of scope (SURVEY.md 8f rank 2)");
-    if (n != 1 && n < 10) return fail(7, "cf90: periodic n must be 1 or >= 10");  // cf90.F90:121-129
+    if (n != 1 && n < 10) return fail(7, "cf90: n must be 1 or >= 10");  // cf90.F90:121-129
     if (int rc = ensure_device()) return rc;
     pdo_cf90_s* o = new (std::nothrow) pdo_cf90_s();
     if (!o) return fail(PDO_E_BADARG, "out of memory");
     o->n = n;
+    if (!periodic) {   // cf90.F90:131-172: the nine penta tables
+        o->periodic = false;
+        int ie = 0;
+        cudaError_t e = np_op_create(&o->np, NP_CF90, n, 1.0, &ie);
+        if (e != cudaSuccess || ie) {
+            np_op_destroy(&o->np);
+            delete o;
+            return e != cudaSuccess ? fail(PDO_E_CUDA, "cf90 init: %s", cudaGetErrorString(e)) : fail(ie, "cf90: non-periodic tables");
+        }
+        *h = o;
+        return 0;
+    }
     OpParams p{};
     p.co[0] = a90; p.co[1] = b90; p.co[2] = c90; p.co[3] = d90; p.co[4] = e90;
     cudaError_t e = banded_op_create(&o->op, n, RK_SYM_9, 2, alpha90, beta90, p);
@@ -348,19 +402,27 @@ int pdo_cf90_init(pdo_cf90_t* h, int n, int periodic) {
 }
 int pdo_cf90_destroy(pdo_cf90_t h) {
     if (!h) return 0;
-    banded_op_destroy(&h->op);
+    if (h->periodic) banded_op_destroy(&h->op);
+    else np_op_destroy(&h->np);
     delete h;
     return 0;
 }
+#define PDO_CF90_FN(name, axis)                                                                              \
+    int name(pdo_cf90_t h, const double* f, double* fil, int na, int nb, int bc1, int bcn, void* stream) {   \
+        if (!h) return fail(PDO_E_BADARG, "null handle");                                                    \
+        if (int rc = check_bc(bc1, bcn)) return rc;                                                          \
+        if (!h->periodic) return apply_np(h->np, true, axis, f, fil, na, nb, bc1, bcn, stream);              \
+        return apply(h->op, true, axis, f, fil, na, nb, stream);                                             \
+    }
+PDO_CF90_FN(pdo_cf90_filter1, 0)
+PDO_CF90_FN(pdo_cf90_filter2, 1)
+PDO_CF90_FN(pdo_cf90_filter3, 2)
 #define PDO_FIL_FN(T, name, axis)                                                                 \
     int name(T h, const double* f, double* fil, int na, int nb, int bc1, int bcn, void* stream) { \
         if (!h) return fail(PDO_E_BADARG, "null handle");                                         \
         if (int rc = check_bc(bc1, bcn)) return rc;                                               \
         return apply(h->op, true, axis, f, fil, na, nb, stream);                                  \
     }
-PDO_FIL_FN(pdo_cf90_t, pdo_cf90_filter1, 0)
-PDO_FIL_FN(pdo_cf90_t, pdo_cf90_filter2, 1)
-PDO_FIL_FN(pdo_cf90_t, pdo_cf90_filter3, 2)
 
 // ---------------- gaussian ----------------
 int pdo_gaussian_init(pdo_gaussian_t* h, int n, int periodic) {

@@ -1,11 +1,12 @@
 // handles.h — what the opaque operator handles of include/padeops_b200.h point to (shared by capi_ops.cu and distops.cu).
 #pragma once
 #include "banded.cuh"
+#include "nonperiodic.cuh"
 #include "../../include/padeops_b200.h"
 
-struct pdo_cd10_s { int n; pdo::BandedOp d1, d2; };
+struct pdo_cd10_s { int n; pdo::BandedOp d1, d2; bool periodic = true; pdo::NpOp np_d1, np_d2; };   // np*: periodic = .false. closures
 struct pdo_cd06_s { int n; pdo::BandedOp d1; };
-struct pdo_cf90_s { int n; pdo::BandedOp op; };
+struct pdo_cf90_s { int n; pdo::BandedOp op; bool periodic = true; pdo::NpOp np; };
 struct pdo_gaussian_s { int n; pdo::BandedOp op; };
 struct pdo_cd06stagg_s { int n; pdo::BandedOp ops[6]; };
 struct pdo_derivatives_s {

@@ -1,0 +1,82 @@
+"""GPU: the non-periodic CD10 / CF90 closures (correctness path) through the C ABI against the
+oracle: all nine (bc1, bcn) combinations, every axis, device and host arrays, and through the derivatives / filters
+dispatch types with periodic = .false. (derivatives.F90:447-569 forwards bc1, bcn)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+BCS = [(a, b) for a in (0, 1, -1) for b in (0, 1, -1)]
+
+
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _rel(got, ref):
+    return np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_cd10_nonperiodic_all_boundary_codes(pdo, oracle, axis):
+    shape = {0: (5, 6, 40), 1: (5, 40, 6), 2: (40, 5, 6)}[axis]
+    n, dx = 40, 0.05
+    f = np.random.default_rng(axis).standard_normal(shape)
+    fd = _dev(f)
+    h = pdo.cd10()
+    assert h.init(n, dx, periodic_=False) == 0
+    d1 = (h.dd1, h.dd2, h.dd3)[axis]
+    d2 = (h.d2d1, h.d2d2, h.d2d3)[axis]
+    for bc1, bcn in BCS:
+        assert _rel(d1(fd, bc1_=bc1, bcn_=bcn).cpu().numpy(), oracle.cd10_np(f, dx, axis, 1, bc1, bcn)) < TOL, (bc1, bcn)
+        assert _rel(d2(fd, bc1_=bc1, bcn_=bcn).cpu().numpy(), oracle.cd10_np(f, dx, axis, 2, bc1, bcn)) < TOL, (bc1, bcn)
+    # host arrays (the unmodified-caller path)
+    out = np.empty_like(f)
+    d1(f, out, bc1_=1, bcn_=-1)
+    assert _rel(out, oracle.cd10_np(f, dx, axis, 1, 1, -1)) < TOL
+    with pytest.raises(pdo.PadeOpsError) as e:
+        d1(fd, bc1_=2, bcn_=0)
+    assert e.value.code == 324
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_cf90_nonperiodic_all_boundary_codes(pdo, oracle, axis):
+    shape = {0: (4, 7, 33), 1: (4, 33, 7), 2: (33, 4, 7)}[axis]
+    f = np.random.default_rng(10 + axis).standard_normal(shape)
+    fd = _dev(f)
+    h = pdo.cf90()
+    assert h.init(33, periodic_=False) == 0
+    fil = (h.filter1, h.filter2, h.filter3)[axis]
+    for bc1, bcn in BCS:
+        assert _rel(fil(fd, bc1_=bc1, bcn_=bcn).cpu().numpy(), oracle.cf90_np(f, axis, bc1, bcn)) < TOL, (bc1, bcn)
+
+
+def test_dispatch_types_with_mixed_periodicity(pdo, oracle):
+    """x periodic, y and z walls: derivatives%ddx/ddy/ddz and filters%filterx/y/z pick the right closure per axis."""
+    nx, ny, nz = 32, 24, 16
+    dx, dy, dz = 2 * np.pi / nx, 1.0 / (ny - 1), 1.0 / (nz - 1)
+    f = np.random.default_rng(3).standard_normal((nz, ny, nx))
+    fd = _dev(f)
+    der = pdo.derivatives()
+    der.init((nx, ny, nz), dx, dy, dz, True, False, False, "cd10", "cd10", "cd10")
+    assert _rel(der.ddx(fd).cpu().numpy(), oracle.cd10(f, dx, 0, 1)) < TOL
+    assert _rel(der.ddy(fd, None, 0, 0).cpu().numpy(), oracle.cd10_np(f, dy, 1, 1, 0, 0)) < TOL
+    assert _rel(der.ddz(fd, None, 1, -1).cpu().numpy(), oracle.cd10_np(f, dz, 2, 1, 1, -1)) < TOL
+    assert _rel(der.d2dy2(fd, None, -1, 1).cpu().numpy(), oracle.cd10_np(f, dy, 1, 2, -1, 1)) < TOL
+    fil = pdo.filters()
+    fil.init((nx, ny, nz), True, False, False, "cf90", "cf90", "cf90")
+    assert _rel(fil.filterx(fd).cpu().numpy(), oracle.cf90(f, 0)) < TOL
+    assert _rel(fil.filtery(fd, None, 0, 0).cpu().numpy(), oracle.cf90_np(f, 1, 0, 0)) < TOL
+    assert _rel(fil.filterz(fd, None, 1, 1).cpu().numpy(), oracle.cf90_np(f, 2, 1, 1)) < TOL
+
+
+def test_one_sided_closure_exact_on_quartics_on_the_gpu(pdo):
+    n = 64
+    dx = 1.0 / (n - 1)
+    x = np.arange(n) * dx
+    f = np.ascontiguousarray(np.broadcast_to((x ** 4)[None, None, :], (2, 3, n)))
+    h = pdo.cd10()
+    assert h.init(n, dx, periodic_=False) == 0
+    assert np.abs(h.dd1(_dev(f)).cpu().numpy() - 4 * x ** 3).max() < 1e-11
+    assert np.abs(h.d2d1(_dev(f)).cpu().numpy() - 12 * x ** 2).max() < 1e-8
