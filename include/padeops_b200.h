@@ -30,7 +30,7 @@ extern "C" {
 
 #define PDO_OK 0
 #define PDO_E_BADARG 1001        /* null handle, bad axis, bad size */
-#define PDO_E_UNSUPPORTED 1002   /* a branch SURVEY.md §8 marks out of scope (non-periodic closures, ...) */
+#define PDO_E_UNSUPPORTED 1002   /* a branch SURVEY.md §8 marks out of scope (CD06 / staggered non-periodic closures, ...) */
 #define PDO_E_CUDA 1003          /* a CUDA / cuFFT / NCCL call failed; see pdo_last_error() */
 #define PDO_E_NODEVICE 1004      /* no CUDA device: this library has no CPU fallback */
 
