@@ -8,6 +8,7 @@
 #include "banded.cuh"
 #include "common.cuh"
 #include "nonperiodic.cuh"
+#include "np_chunk_tables.h"
 
 namespace pdo {
 thread_local std::string g_last_error;
@@ -240,6 +241,26 @@ int pdo_debug_np_line_host(int kind, int n, double dx, int bc1, int bcn, int axi
     if (!f || !out || axis < 0 || axis > 2) return fail(PDO_E_BADARG, "bad argument");
     return np_apply_host(kind, n, dx, bc1, bcn, axis, f, out, na, nb);
 }
+
+/* Host-only test hook: chunk tables of the non-periodic system of `kind` (0 cd10 d1, 1 cd10 d2, 2 cf90) with boundary codes
+ * (bc1, bcn): sets = 3 x NpChunkSet (first, mid, last) as doubles, G = [P][2W+1][4], meta = {P, W, doubles per set}. */
+int pdo_debug_np_chunk_tables(int kind, int n, int M, int bc1, int bcn, double* sets, double* G, int g_capacity, int* meta) {
+    if (!sets || !G || !meta) return fail(PDO_E_BADARG, "null argument");
+    std::vector<double> rows(5 * (size_t)(n > 0 ? n : 1));
+    if (int rc = np_build_rows(kind, n, bc1, bcn, rows.data())) return rc;
+    NpChunkTables t;
+    if (int rc = build_np_chunk_tables(n, M, rows.data(), &t)) return rc;
+    if ((int)t.G.size() > g_capacity) return fail(PDO_E_BADARG, "G capacity %d < %d", g_capacity, (int)t.G.size());
+    static_assert(sizeof(NpChunkSet) % sizeof(double) == 0, "NpChunkSet is all doubles");
+    std::memcpy(sets, &t.first, sizeof(NpChunkSet));
+    std::memcpy(sets + sizeof(NpChunkSet) / sizeof(double), &t.mid, sizeof(NpChunkSet));
+    std::memcpy(sets + 2 * sizeof(NpChunkSet) / sizeof(double), &t.last, sizeof(NpChunkSet));
+    std::memcpy(G, t.G.data(), sizeof(double) * t.G.size());
+    meta[0] = t.P; meta[1] = t.W; meta[2] = (int)(sizeof(NpChunkSet) / sizeof(double));
+    return 0;
+}
+/* Host-only: the rows (bt b d a at, 5n doubles) of the non-periodic system */
+int pdo_debug_np_rows(int kind, int n, int bc1, int bcn, double* rows5n) { return np_build_rows(kind, n, bc1, bcn, rows5n); }
 
 int pdo_malloc(void** dptr, size_t bytes) {
     if (int rc = ensure_device()) return rc;

@@ -86,11 +86,24 @@ int np_build_coefs(int kind, double dx, NpCoefs* c) {
     return 0;
 }
 
-// ComputePenta1 / ComputePenta2 (cd10.F90:429-707) and cf90's ComputePenta (cf90.F90:276-418): rows, then the LU recurrences.
-int np_build_table(int kind, int n, int bc1, int bcn, double* tab) {
+// The rows of ComputePenta1 / ComputePenta2 (cd10.F90:429-554, 577-686) and cf90's ComputePenta (cf90.F90:276-398):
+// rows5n = bt[n] b[n] d[n] a[n] at[n] (sub-sub, sub, diagonal, super, super-super entries of row i).
+static int np_rows(int kind, int n, int bc1, int bcn, std::vector<Row>& R);
+
+int np_build_rows(int kind, int n, int bc1, int bcn, double* rows5n) {
+    std::vector<Row> R;
+    if (int rc = np_rows(kind, n, bc1, bcn, R)) return rc;
+    for (int i = 1; i <= n; ++i) {
+        rows5n[i - 1] = R[i].bt; rows5n[(size_t)n + i - 1] = R[i].b; rows5n[2 * (size_t)n + i - 1] = R[i].d;
+        rows5n[3 * (size_t)n + i - 1] = R[i].a; rows5n[4 * (size_t)n + i - 1] = R[i].at;
+    }
+    return 0;
+}
+
+static int np_rows(int kind, int n, int bc1, int bcn, std::vector<Row>& R) {
     if (kind == NP_CF90 ? n < 10 : n < 8) return kind == NP_CF90 ? 7 : 2;
     if ((bc1 != 0 && bc1 != 1 && bc1 != -1) || (bcn != 0 && bcn != 1 && bcn != -1)) return 324;
-    std::vector<Row> R((size_t)n + 1);   // 1-based
+    R.assign((size_t)n + 1, Row{0, 0, 0, 0, 0});   // 1-based
     double al, be;
     if (kind == NP_CD10_D1) { al = alpha10d1; be = beta10d1; }
     else if (kind == NP_CD10_D2) { al = alpha10d2; be = beta10d2; }
@@ -127,7 +140,14 @@ int np_build_table(int kind, int n, int bc1, int bcn, double* tab) {
         if (bcn == 1) { R[n] = Row{2 * be, 2 * al, 1, 0, 0}; R[n - 1] = Row{be, al, 1 + be, al, 0}; }
         if (bcn == -1) { R[n] = Row{0, 0, 1, 0, 0}; R[n - 1] = Row{be, al, 1 - be, al, 0}; }
     }
-    // Steps 1-3 (cd10.F90:556-572): obc = 1/pivot, e = modified super-diagonal, f / g = multipliers
+    return 0;
+}
+
+// rows, then the LU recurrences of ComputePenta* (cd10.F90:556-572)
+int np_build_table(int kind, int n, int bc1, int bcn, double* tab) {
+    std::vector<Row> R;
+    if (int rc = np_rows(kind, n, bc1, bcn, R)) return rc;
+    // Steps 1-3: obc = 1/pivot, e = modified super-diagonal, f / g = multipliers
     std::vector<double> e((size_t)n + 1, 0.0), obc((size_t)n + 1, 0.0), f((size_t)n + 1, 0.0), g((size_t)n + 1, 0.0);
     obc[1] = 1.0 / R[1].d;
     obc[2] = 1.0 / (R[2].d - R[2].b * R[1].a * obc[1]);

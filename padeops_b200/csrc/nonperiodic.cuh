@@ -113,6 +113,7 @@ PDO_HD void np_solve_line(double* y, long long es, int n, const double* tab) {
 // Returns 0; 2 / 7 for lines shorter than the closures allow (cd10: 8, cf90: 10); 324 for bad boundary codes.
 int np_build_coefs(int kind, double dx, NpCoefs* out);
 int np_build_table(int kind, int n, int bc1, int bcn, double* tab5n);
+int np_build_rows(int kind, int n, int bc1, int bcn, double* rows5n);   // bt[n] b[n] d[n] a[n] at[n]
 
 struct NpOp {
     int kind = 0, n = 0;
