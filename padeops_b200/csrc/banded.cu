@@ -2037,6 +2037,14 @@ cudaError_t launch_any(const BandedOp* h, int axis, const double* f, double* out
 
 int banded_debug_last_variant() { return g_last_variant; }
 
+// host-only view of the cluster + TMA kernel's launch shape (tests check its invariants without a GPU)
+int banded_debug_ctma_config(int P, int XT, int HB, int HW, int BW, int pc_max, long long* smem_bytes) {
+    size_t smem = 0;
+    const int pc = ctma_chunks_per_cta(P, 32, XT, HB, HW, BW > 0 ? BW : 1, BW > 0, pc_max, &smem);
+    if (smem_bytes) *smem_bytes = (long long)smem;
+    return pc;
+}
+
 void banded_debug_set_variant(int strided_mode, int x_threads) {
     g_strided_mode = strided_mode;
     g_x_threads = x_threads;

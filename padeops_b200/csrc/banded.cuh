@@ -70,5 +70,6 @@ cudaError_t banded_zslab_apply(const BandedOp* h, const double* f, double* out, 
 // 5 cpipe, 6 pipe1; x_threads: -1 env/default, 128, 256).
 void banded_debug_set_variant(int strided_mode, int x_threads);
 int banded_debug_last_variant();
+int banded_debug_ctma_config(int P, int XT, int HB, int HW, int BW, int pc_max, long long* smem_bytes);
 
 }  // namespace pdo

@@ -259,6 +259,10 @@ int pdo_debug_np_chunk_tables(int kind, int n, int M, int bc1, int bcn, double* 
     meta[0] = t.P; meta[1] = t.W; meta[2] = (int)(sizeof(NpChunkSet) / sizeof(double));
     return 0;
 }
+/* Host-only: chunks per CTA (0 = no launch shape) and dynamic shared memory of the cluster + TMA strided kernel */
+int pdo_debug_ctma_config(int P, int XT, int HB, int HW, int BW, int pc_max, long long* smem_bytes) {
+    return banded_debug_ctma_config(P, XT, HB, HW, BW, pc_max, smem_bytes);
+}
 /* Host-only: the rows (bt b d a at, 5n doubles) of the non-periodic system */
 int pdo_debug_np_rows(int kind, int n, int bc1, int bcn, double* rows5n) { return np_build_rows(kind, n, bc1, bcn, rows5n); }
 
