@@ -205,7 +205,8 @@ int pdo_fft3d_ifft2_y2x(pdo_fft3d_t h, const double* in_cplx_y, double* out_real
 
 /* ---- PoissonPeriodicMod::PoissonPeriodic  (utilities/PoissonPeriodic.F90) --------------------- */
 typedef struct pdo_poisson_s* pdo_poisson_t;
-/* init(dx,dy,dz,gp,dir_id[,...,Get_ModKx,Get_ModKy,Get_ModKz]); dir_id 1 (x-pencil in/out) or 2 (y-pencil).
+/* init(dx,dy,dz,gp,dir_id[,...,Get_ModKx,Get_ModKy,Get_ModKz]); dir_id 1 (x-pencil in/out), 2 (y-pencil) or 3 (z-pencil:
+   brought to the x-pencil and back instead of the reference's z-base transforms; same solution); else -> 31243.
    modk{x,y,z}: optional full-length (nx, ny, nz) arrays of ALREADY MODIFIED wavenumbers replacing
    GetWaveNums output (what the Get_ModK* callbacks produce, :181-204); NULL = spectral wavenumbers. */
 int pdo_poisson_init(pdo_poisson_t* h, int nx, int ny, int nz, double dx, double dy, double dz, int p_row, int p_col,

@@ -220,7 +220,8 @@ struct pdo_poisson_s {
     pdo_fft3d_t ft = nullptr;
     int dir_id = 1;
     double2* hat = nullptr;
-    double* rbuf = nullptr;  // x-pencil real scratch for dir_id == 2
+    double* rbuf = nullptr;  // x-pencil real scratch for dir_id == 2, 3
+    double* ybuf = nullptr;  // y-pencil real scratch for dir_id == 3
     double *kx = nullptr, *ky = nullptr, *kz = nullptr;
     int have_zero = 0;
 };
@@ -352,8 +353,10 @@ int pdo_poisson_init(pdo_poisson_t* h, int nx, int ny, int nz, double dx, double
                      int dir_id, const double* modkx, const double* modky, const double* modkz) {
     if (!h) return fail(PDO_E_BADARG, "null handle");
     *h = nullptr;
-    if (dir_id == 3) return fail(PDO_E_UNSUPPORTED, "PoissonPeriodic dir_id=3 (z-base FFT) is out of scope (SURVEY.md 2.1 #11)");
-    if (dir_id != 1 && dir_id != 2) return fail(31243, "Incorrect option for DIR_ID");  // PoissonPeriodic.F90:156
+    // dir_id = 3 (z-pencil in / out): the reference switches fft_3d to its "z" base (PoissonPeriodic.F90:151-154); here the
+    // field is brought to the x-pencil (z->y->x), solved on the x-base transforms and taken back — the same solution, the
+    // transform order only changes the rounding.
+    if (dir_id != 1 && dir_id != 2 && dir_id != 3) return fail(31243, "Incorrect option for DIR_ID");  // PoissonPeriodic.F90:156
     pdo_poisson_s* p = new (std::nothrow) pdo_poisson_s();
     if (!p) return fail(PDO_E_BADARG, "out of memory");
     p->dir_id = dir_id;
@@ -368,7 +371,8 @@ int pdo_poisson_init(pdo_poisson_t* h, int nx, int ny, int nz, double dx, double
     if (e == cudaSuccess) e = cudaMalloc(&p->kx, sizeof(double) * zs[0]);
     if (e == cudaSuccess) e = cudaMalloc(&p->ky, sizeof(double) * zs[1]);
     if (e == cudaSuccess) e = cudaMalloc(&p->kz, sizeof(double) * zs[2]);
-    if (e == cudaSuccess && dir_id == 2) e = cudaMalloc(&p->rbuf, sizeof(double) * (size_t)cvol(f->pi.xsz));
+    if (e == cudaSuccess && dir_id >= 2) e = cudaMalloc(&p->rbuf, sizeof(double) * (size_t)cvol(f->pi.xsz));
+    if (e == cudaSuccess && dir_id == 3) e = cudaMalloc(&p->ybuf, sizeof(double) * (size_t)cvol(f->pi.ysz));
     // local slices kx(xst:xen) etc. of the spectral z-pencil (PoissonPeriodic.F90:169-179)
     if (e == cudaSuccess) e = cudaMemcpy(p->kx, kx.data() + (f->si.zst[0] - 1), sizeof(double) * zs[0], cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->ky, ky.data() + (f->si.zst[1] - 1), sizeof(double) * zs[1], cudaMemcpyHostToDevice);
@@ -383,6 +387,7 @@ int pdo_poisson_destroy(pdo_poisson_t p) {
     if (!p) return 0;
     if (p->hat) cudaFree(p->hat);
     if (p->rbuf) cudaFree(p->rbuf);
+    if (p->ybuf) cudaFree(p->ybuf);
     if (p->kx) cudaFree(p->kx);
     if (p->ky) cudaFree(p->ky);
     if (p->kz) cudaFree(p->kz);
@@ -395,13 +400,18 @@ int pdo_poisson_solve(pdo_poisson_t p, const double* rhs, double* fout, void* st
     if (!p || !rhs || !fout) return fail(PDO_E_BADARG, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     pdo_fft3d_s* f = p->ft;
-    const int* insz = (p->dir_id == 1) ? f->pi.xsz : f->pi.ysz;
+    const int* insz = (p->dir_id == 1) ? f->pi.xsz : (p->dir_id == 2 ? f->pi.ysz : f->pi.zsz);
     const size_t bytes = sizeof(double) * (size_t)cvol(insz);
     return with_device_views(rhs, bytes, fout, bytes, st, [&](const void* di, void* d_o) -> int {
         const double* x_in = (const double*)di;
         double* x_out = (double*)d_o;
         if (p->dir_id == 2) {  // PoissonPeriodic.F90:75-80
             if (int rc = decomp_transpose_device(f->phys, 1, (const double*)di, p->rbuf, 1, st)) return rc;
+            x_in = p->rbuf;
+            x_out = p->rbuf;
+        } else if (p->dir_id == 3) {
+            if (int rc = decomp_transpose_device(f->phys, 3, (const double*)di, p->ybuf, 1, st)) return rc;   // z -> y
+            if (int rc = decomp_transpose_device(f->phys, 1, p->ybuf, p->rbuf, 1, st)) return rc;             // y -> x
             x_in = p->rbuf;
             x_out = p->rbuf;
         }
@@ -414,6 +424,10 @@ int pdo_poisson_solve(pdo_poisson_t p, const double* rhs, double* fout, void* st
         g_launches += 1;
         if (int rc = ifft3_z2x_dev(f, p->hat, x_out, false, st)) return rc;
         if (p->dir_id == 2) return decomp_transpose_device(f->phys, 0, p->rbuf, (double*)d_o, 1, st);
+        if (p->dir_id == 3) {
+            if (int rc = decomp_transpose_device(f->phys, 0, p->rbuf, p->ybuf, 1, st)) return rc;             // x -> y
+            return decomp_transpose_device(f->phys, 2, p->ybuf, (double*)d_o, 1, st);                           // y -> z
+        }
         return 0;
     });
 }

@@ -149,7 +149,7 @@ def main():
             ok(np.abs(got2.cpu().numpy() - refy).max() < 1e-12 * np.abs(H2).max(), f"fft2_x2y grid {pr}x{pc}")
             ok(np.abs(ft.ifft2_y2x(got2).cpu().numpy() - fx.cpu().numpy()).max() < 1e-12 * np.abs(G).max(), f"ifft2_y2x grid {pr}x{pc}")
             ref = O.poisson_solve(G, dx, dy, dz)
-            for dir_id, pen in ((1, "x"), (2, "y")):
+            for dir_id, pen in ((1, "x"), (2, "y"), (3, "z")):
                 po = pdo.PoissonPeriodic()
                 po.init(dx, dy, dz, (nx, ny, nz), dir_id, p_row=pr, p_col=pc)
                 rin = torch.from_numpy(O.scatter_global(G, nx, ny, nz, pr, pc, pen)[rank]).cuda()

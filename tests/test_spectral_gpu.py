@@ -86,7 +86,7 @@ def test_poisson_manufactured_solution(pdo, oracle, comm):
     x, y, z = np.arange(nx) * dx, np.arange(ny) * dy, np.arange(nz) * dz
     ftrue = np.sin(6 * x)[None, None, :] * np.cos(3 * y)[None, :, None] * np.sin(z)[:, None, None]
     rhs = -(36 + 9 + 1) * ftrue
-    for dir_id in (1, 2):
+    for dir_id in (1, 2, 3):   # x-, y-, z-pencil in / out (one rank: the three pencils coincide)
         po = pdo.PoissonPeriodic()
         po.init(dx, dy, dz, (nx, ny, nz), dir_id)
         import torch
