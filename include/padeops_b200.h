@@ -66,7 +66,8 @@ int pdo_cd10_d2d3(pdo_cd10_t h, const double* f, double* df, int na, int nb, int
 
 /* ---- cd06stuff::cd06  (derivatives/cd06.F90) ------------------------------------------------- */
 typedef struct pdo_cd06_s* pdo_cd06_t;
-int pdo_cd06_init(pdo_cd06_t* h, int n, double dx, int periodic, int bc1, int bcn);   /* cd06.F90:129-219 */
+int pdo_cd06_init(pdo_cd06_t* h, int n, double dx, int periodic, int bc1, int bcn);   /* cd06.F90:129-219; periodic = 0: the
+                                                                                          one-sided closure (bc1 = bcn = 0 only) */
 int pdo_cd06_destroy(pdo_cd06_t h);
 int pdo_cd06_getsize(pdo_cd06_t h);
 int pdo_cd06_dd1(pdo_cd06_t h, const double* f, double* df, int na, int nb, int bc1, int bcn, void* stream); /* :775 */

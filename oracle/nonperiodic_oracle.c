@@ -1,4 +1,4 @@
-/* nonperiodic_oracle.c — CPU restatement of the NON-PERIODIC CD10 and CF90 closures (groundwork: the
+/* nonperiodic_oracle.c — CPU restatement of the NON-PERIODIC CD10, CF90 and CD06 closures (groundwork: the
  * CUDA library does not implement them yet and returns PDO_E_UNSUPPORTED for periodic = .false.).
  *
  * TEST INFRASTRUCTURE ONLY (see padeops_oracle.c).  Follows derivatives/cd10.F90 statement by statement:
@@ -435,6 +435,94 @@ int pdo_oracle_cf90_np(int n, int bc1, int bcn, int axis, const double *f, doubl
             for (int i = 0; i < n; ++i) out[base + (int64_t)i * stride] = lr[i];
         }
     free(P); free(lf); free(lr);
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * CD06 non-periodic first derivative: derivatives/cd06.F90:27-58 (boundary scheme and weights), 264-327 (ComputeTri1; only
+ * the one-sided closure bc = 0 is complete in the reference, the symmetric cases are marked "Incomplete"), 432-449
+ * (SolveXTri1), 551-590 (ComputeXD1RHS, periodic = .false.).  dd1/dd2/dd3 take no boundary codes (cd06.F90:775-839).
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct { double alpha, p, q, r, s, qhat, rhat, alpha_hat, q_p, alpha_p, alpha_pp, q_pp, r_pp, w1, w2, w3; } C6Consts;
+static C6Consts c6_consts(void)
+{
+    C6Consts c;
+    c.alpha = 3.0; c.p = 17.0 / 6.0; c.q = 3.0 / 2.0; c.r = 3.0 / 2.0; c.s = -1.0 / 6.0;
+    c.qhat = (14.0 / 9.0) / 2.0; c.rhat = (1.0 / 9.0) / 4.0; c.alpha_hat = 1.0 / 3.0;
+    c.q_p = 3.0 / 4.0; c.alpha_p = 1.0 / 4.0;
+    c.alpha_pp = ((40 * c.alpha_hat - 1) * c.q + 7 * (4 * c.alpha_hat - 1) * c.s) / (16 * (c.alpha_hat + 2) * c.q + 8 * (1 - 4 * c.alpha_hat) * c.s);
+    c.q_pp = (1.0 / 3.0) * (c.alpha_pp + 2);
+    c.r_pp = (1.0 / 12.0) * (4 * c.alpha_pp - 1);
+    c.w1 = (2 * c.alpha_hat + 1) / (2 * (c.q + c.s));
+    c.w2 = ((8 * c.alpha_hat + 7) * c.q - 6 * (2 * c.alpha_hat + 1) * c.r + (8 * c.alpha_hat + 7) * c.s) / (9 * (c.q + c.s));
+    c.w3 = (4 * (c.alpha_hat + 2) * c.q + 2 * (1 - 4 * c.alpha_hat) * c.s) / (9 * (c.q + c.s));
+    return c;
+}
+
+/* ComputeTri1 with bc1 = bcn = 0 (cd06.F90:264-327): T(n,3) column-major = a*den, den, cp */
+int pdo_oracle_cd06_np_tri(int n, double *T)
+{
+    if (n < 6) return 3;
+    const C6Consts k = c6_consts();
+    double *a = (double *)malloc(sizeof(double) * 5 * (size_t)n);
+    if (!a) return -1;
+    double *b = a + n, *c = b + n, *cp = c + n, *den = cp + n;
+    for (int i = 0; i < n; ++i) { a[i] = k.alpha_hat; b[i] = 1.0; c[i] = k.alpha_hat; }
+    a[0] = k.w1 * 0; a[1] = k.w2 * k.alpha_p; a[2] = k.w3 * k.alpha_pp;
+    b[0] = k.w1 * 1; b[1] = k.w2 * 1; b[2] = k.w3 * 1;
+    c[0] = k.w1 * k.alpha; c[1] = k.w2 * k.alpha_p; c[2] = k.w3 * k.alpha_pp;
+    c[n - 1] = k.w1 * 0; c[n - 2] = k.w2 * k.alpha_p; c[n - 3] = k.w3 * k.alpha_pp;
+    b[n - 1] = k.w1 * 1; b[n - 2] = k.w2 * 1; b[n - 3] = k.w3 * 1;
+    a[n - 1] = k.w1 * k.alpha; a[n - 2] = k.w2 * k.alpha_p; a[n - 3] = k.w3 * k.alpha_pp;
+    cp[0] = c[0] / b[0];
+    for (int i = 1; i < n - 1; ++i) cp[i] = c[i] / (b[i] - a[i] * cp[i - 1]);
+    cp[n - 1] = 0.0;   /* never read by the solve */
+    den[0] = 1.0 / b[0];
+    for (int i = 1; i < n; ++i) den[i] = 1.0 / (b[i] - a[i] * cp[i - 1]);
+    for (int i = 0; i < n; ++i) { T[i] = a[i] * den[i]; T[n + i] = den[i]; T[2 * (size_t)n + i] = cp[i]; }
+    /* also hand back the raw rows for tests: T[3n..6n) = a, b, c */
+    for (int i = 0; i < n; ++i) { T[3 * (size_t)n + i] = a[i]; T[4 * (size_t)n + i] = b[i]; T[5 * (size_t)n + i] = c[i]; }
+    free(a);
+    return 0;
+}
+
+int pdo_oracle_cd06_np(int n, double dx, int axis, const double *f, double *df, int64_t na, int64_t nb)
+{
+    double *T = (double *)malloc(sizeof(double) * 6 * (size_t)n);
+    double *lf = (double *)malloc(sizeof(double) * (size_t)n), *ly = (double *)malloc(sizeof(double) * (size_t)n);
+    if (!T || !lf || !ly) { free(T); free(lf); free(ly); return -1; }
+    int rc = pdo_oracle_cd06_np_tri(n, T);
+    if (rc) { free(T); free(lf); free(ly); return rc; }
+    const C6Consts k = c6_consts();
+    const double onebydx = 1.0 / dx;
+    const double a06 = k.qhat * onebydx, b06 = k.rhat * onebydx;
+    const double a_np_3 = k.w3 * k.q_pp * onebydx, b_np_3 = k.w3 * k.r_pp * onebydx, a_np_2 = k.w2 * k.q_p * onebydx;
+    const double a_np_1 = k.w1 * (-k.p * onebydx), b_np_1 = k.w1 * (k.q * onebydx), c_np_1 = k.w1 * (k.r * onebydx), d_np_1 = k.w1 * (k.s * onebydx);
+    int64_t stride, nlines_in, nlines_out, in_step, out_step;
+    if (axis == 0) { stride = 1; nlines_in = na * nb; nlines_out = 1; in_step = n; out_step = 0; }
+    else if (axis == 1) { stride = na; nlines_in = na; nlines_out = nb; in_step = 1; out_step = na * (int64_t)n; }
+    else { stride = na * nb; nlines_in = na * nb; nlines_out = 1; in_step = 1; out_step = 0; }
+    for (int64_t io = 0; io < nlines_out; ++io)
+        for (int64_t ii = 0; ii < nlines_in; ++ii) {
+            const int64_t base = io * out_step + ii * in_step;
+            for (int i = 0; i < n; ++i) lf[i] = f[base + (int64_t)i * stride];
+            const double *F = lf - 1;   /* 1-based */
+            double *R = ly - 1;
+            R[1] = a_np_1 * F[1] + b_np_1 * F[2] + c_np_1 * F[3] + d_np_1 * F[4];
+            R[2] = a_np_2 * (F[3] - F[1]);
+            R[3] = a_np_3 * (F[4] - F[2]) + b_np_3 * (F[5] - F[1]);
+            for (int i = 4; i <= n - 3; ++i) R[i] = b06 * (F[i + 2] - F[i - 2]) + a06 * (F[i + 1] - F[i - 1]);
+            R[n - 2] = a_np_3 * (F[n - 1] - F[n - 3]) + b_np_3 * (F[n] - F[n - 4]);
+            R[n - 1] = a_np_2 * (F[n] - F[n - 2]);
+            R[n] = -a_np_1 * F[n] - b_np_1 * F[n - 1] - c_np_1 * F[n - 2] - d_np_1 * F[n - 3];
+            /* SolveXTri1 (cd06.F90:439-447): Tri1(:,1) = a*den, (:,2) = den, (:,3) = cp */
+            const double *t1 = T - 1, *t2 = T + n - 1, *t3 = T + 2 * (size_t)n - 1;
+            R[1] = R[1] * t2[1];
+            for (int i = 2; i <= n; ++i) R[i] = R[i] * t2[i] - R[i - 1] * t1[i];
+            for (int i = n - 1; i >= 1; --i) R[i] = R[i] - t3[i] * R[i + 1];
+            for (int i = 0; i < n; ++i) df[base + (int64_t)i * stride] = ly[i];
+        }
+    free(T); free(lf); free(ly);
     return 0;
 }
 

@@ -312,3 +312,20 @@ def cf90_np_penta(n, bc1, bcn):
     P = np.zeros((11, n))
     rc = lib().pdo_oracle_cf90_np_penta(C.c_int(n), C.c_int(bc1), C.c_int(bcn), _p(P))
     return rc, P
+
+
+def cd06_np(f, dx, axis):
+    """cd06%dd1/dd2/dd3 with periodic=.false. (one-sided closure at both ends; cd06.F90:27-58, 264-327, 432-449, 551-590)."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    n, na, nb = _na_nb(f, axis)
+    out = np.empty_like(f)
+    rc = lib().pdo_oracle_cd06_np(C.c_int(n), C.c_double(dx), C.c_int(axis), _p(f), _p(out), C.c_int64(na), C.c_int64(nb))
+    assert rc == 0, rc
+    return out
+
+
+def cd06_np_tri(n):
+    """(ierr, T(6, n)): rows 0-2 = Tri1 columns (a*den, den, cp), rows 3-5 = the raw sub / diagonal / super entries."""
+    T = np.zeros((6, n))
+    rc = lib().pdo_oracle_cd06_np_tri(C.c_int(n), _p(T))
+    return rc, T

@@ -355,16 +355,28 @@ PDO_CD10_FN(pdo_cd10_d2d3, d2, 2)
 
 // ---------------- cd06 ----------------
 int pdo_cd06_init(pdo_cd06_t* h, int n, double dx, int periodic, int bc1, int bcn) {
-    (void)bc1; (void)bcn;
     if (!h) return fail(PDO_E_BADARG, "null handle");
     *h = nullptr;
     if (n < 1) return fail(PDO_E_BADARG, "n < 1");
-    if (!periodic) return fail(PDO_E_UNSUPPORTED, "cd06: non-periodic closures are out of scope (SURVEY.md 8f rank 2)");
-    if (n != 1 && n < 6) return fail(3, "cd06: periodic n must be 1 or >= 6");  // cd06.F90:151-160
+    if (!periodic && (bc1 != 0 || bcn != 0))
+        return fail(PDO_E_UNSUPPORTED, "cd06: only the one-sided non-periodic closure exists (the reference marks bc = 1 'Incomplete', cd06.F90:288-291)");
+    if (n != 1 && n < 6) return fail(3, "cd06: n must be 1 or >= 6");  // cd06.F90:151-160
     if (int rc = ensure_device()) return rc;
     pdo_cd06_s* o = new (std::nothrow) pdo_cd06_s();
     if (!o) return fail(PDO_E_BADARG, "out of memory");
     o->n = n;
+    if (!periodic) {   // cd06.F90:172-180: ComputeTri1
+        o->periodic = false;
+        int ie = 0;
+        cudaError_t e = np_op_create(&o->np, NP_CD06_D1, n, dx, &ie);
+        if (e != cudaSuccess || ie) {
+            np_op_destroy(&o->np);
+            delete o;
+            return e != cudaSuccess ? fail(PDO_E_CUDA, "cd06 init: %s", cudaGetErrorString(e)) : fail(ie, "cd06: non-periodic tables");
+        }
+        *h = o;
+        return 0;
+    }
     const double onebydx = 1.0 / dx;
     OpParams p{};
     p.co[0] = a06d1 * onebydx; p.co[1] = b06d1 * onebydx;  // cd06.F90:530-531
@@ -378,7 +390,8 @@ int pdo_cd06_init(pdo_cd06_t* h, int n, double dx, int periodic, int bc1, int bc
 }
 int pdo_cd06_destroy(pdo_cd06_t h) {
     if (!h) return 0;
-    banded_op_destroy(&h->d1);
+    if (h->periodic) banded_op_destroy(&h->d1);
+    else np_op_destroy(&h->np);
     delete h;
     return 0;
 }
@@ -387,6 +400,8 @@ int pdo_cd06_getsize(pdo_cd06_t h) { return h ? h->n : -1; }
     int name(pdo_cd06_t h, const double* f, double* df, int na, int nb, int bc1, int bcn, void* stream) { \
         if (!h) return fail(PDO_E_BADARG, "null handle");                                                 \
         if (int rc = check_bc(bc1, bcn)) return rc;                                                       \
+        /* the reference's cd06%dd* take no boundary codes (cd06.F90:775-839): always the one-sided closure */ \
+        if (!h->periodic) return apply_np(h->np, false, axis, f, df, na, nb, 0, 0, stream);               \
         return apply(h->d1, false, axis, f, df, na, nb, stream);                                          \
     }
 PDO_CD06_FN(pdo_cd06_dd1, 0)

@@ -52,6 +52,21 @@ constexpr double b2_alpha90 = 4.997e-1, b2_a90 = 9.997e-1, b2_b90 = 4.9985e-1;
 constexpr double b3_alpha90 = 6.6624e-1, b3_beta90 = 1.6688e-1, b3_a90 = 9.9952e-1, b3_b90 = 6.6656e-1, b3_c90 = 1.668e-1;
 constexpr double b4_alpha90 = 6.6624e-1, b4_beta90 = 1.6688e-1, b4_a90 = 9.9968e-1, b4_b90 = 6.6652e-1, b4_c90 = 1.6672e-1, b4_d90 = 4.0e-5;
 
+// ---- CD06 first-derivative boundary scheme and weights (cd06.F90:27-58) ----
+struct C6B {
+    double alpha = 3.0, p = 17.0 / 6.0, q = 3.0 / 2.0, r = 3.0 / 2.0, s = -1.0 / 6.0;
+    double qhat = (14.0 / 9.0) / 2.0, rhat = (1.0 / 9.0) / 4.0, alpha_hat = 1.0 / 3.0, q_p = 3.0 / 4.0, alpha_p = 1.0 / 4.0;
+    double alpha_pp, q_pp, r_pp, w1, w2, w3;
+    C6B() {
+        alpha_pp = ((40 * alpha_hat - 1) * q + 7 * (4 * alpha_hat - 1) * s) / (16 * (alpha_hat + 2) * q + 8 * (1 - 4 * alpha_hat) * s);
+        q_pp = (1.0 / 3.0) * (alpha_pp + 2);
+        r_pp = (1.0 / 12.0) * (4 * alpha_pp - 1);
+        w1 = (2 * alpha_hat + 1) / (2 * (q + s));
+        w2 = ((8 * alpha_hat + 7) * q - 6 * (2 * alpha_hat + 1) * r + (8 * alpha_hat + 7) * s) / (9 * (q + s));
+        w3 = (4 * (alpha_hat + 2) * q + 2 * (1 - 4 * alpha_hat) * s) / (9 * (q + s));
+    }
+};
+
 struct Row { double bt, b, d, a, at; };
 
 inline int slot(int bc) { return bc == 0 ? 0 : (bc == 1 ? 1 : 2); }
@@ -74,6 +89,12 @@ int np_build_coefs(int kind, double dx, NpCoefs* c) {
         c->r2[0] = b2_a10d2 * onebydx2;
         c->r1[0] = b1_a10d2 * onebydx2; c->r1[1] = b1_b10d2 * onebydx2; c->r1[2] = b1_c10d2 * onebydx2; c->r1[3] = b1_d10d2 * onebydx2;
         c->r1[4] = b1_e10d2 * onebydx2;
+    } else if (kind == NP_CD06_D1) {   // cd06.F90:551-563
+        const C6B k;
+        c->in[0] = k.qhat * onebydx; c->in[1] = k.rhat * onebydx;
+        c->r3[0] = k.w3 * k.q_pp * onebydx; c->r3[1] = k.w3 * k.r_pp * onebydx;
+        c->r2[0] = k.w2 * k.q_p * onebydx;
+        c->r1[0] = k.w1 * (-k.p * onebydx); c->r1[1] = k.w1 * (k.q * onebydx); c->r1[2] = k.w1 * (k.r * onebydx); c->r1[3] = k.w1 * (k.s * onebydx);
     } else if (kind == NP_CF90) {      // cf90.F90:672-801
         c->in[0] = a90; c->in[1] = b90; c->in[2] = c90; c->in[3] = d90; c->in[4] = e90;
         c->r1[0] = 1.0;
@@ -101,6 +122,16 @@ int np_build_rows(int kind, int n, int bc1, int bcn, double* rows5n) {
 }
 
 static int np_rows(int kind, int n, int bc1, int bcn, std::vector<Row>& R) {
+    if (kind == NP_CD06_D1) {   // ComputeTri1 (cd06.F90:264-327): a tridiagonal system carried as a pentadiagonal one with empty outer bands
+        if (n < 6) return 3;
+        if (bc1 != 0 || bcn != 0) return 1002;   // the reference's symmetric cases are marked incomplete
+        const C6B k;
+        R.assign((size_t)n + 1, Row{0, k.alpha_hat, 1.0, k.alpha_hat, 0});
+        const Row one_sided[3] = {{0, k.w1 * 0, k.w1 * 1, k.w1 * k.alpha, 0}, {0, k.w2 * k.alpha_p, k.w2 * 1, k.w2 * k.alpha_p, 0},
+                                  {0, k.w3 * k.alpha_pp, k.w3 * 1, k.w3 * k.alpha_pp, 0}};
+        for (int j = 0; j < 3; ++j) { R[1 + j] = one_sided[j]; const Row& s = one_sided[j]; R[n - j] = Row{0, s.a, s.d, s.b, 0}; }
+        return 0;
+    }
     if (kind == NP_CF90 ? n < 10 : n < 8) return kind == NP_CF90 ? 7 : 2;
     if ((bc1 != 0 && bc1 != 1 && bc1 != -1) || (bcn != 0 && bcn != 1 && bcn != -1)) return 324;
     R.assign((size_t)n + 1, Row{0, 0, 0, 0, 0});   // 1-based
@@ -223,8 +254,9 @@ cudaError_t np_op_create(NpOp* h, int kind, int n, double dx, int* ierr_out) {
     if (n == 1) return cudaSuccess;   // degenerate: handled by the callers (derivative 0 / filter identity)
     std::vector<double> tab(5 * (size_t)n);
     const int codes[3] = {0, 1, -1};
-    for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) {
+    const int ncodes = kind == NP_CD06_D1 ? 1 : 3;   // cd06: the one-sided closure only
+    for (int a = 0; a < ncodes; ++a)
+        for (int b = 0; b < ncodes; ++b) {
             const int rc = np_build_table(kind, n, codes[a], codes[b], tab.data());
             if (rc) { *ierr_out = rc; np_op_destroy(h); return cudaSuccess; }
             double* d = nullptr;
@@ -249,7 +281,8 @@ cudaError_t np_op_apply(const NpOp* h, int axis, const double* f, double* out, l
     const double* tab = h->d_tab[3 * slot(bc1) + slot(bcn)];
     if (!tab) return cudaErrorInvalidValue;
     const unsigned gb = blocks_for(tot, 256);
-    if (h->kind == NP_CD10_D1) np_rhs_kernel<NP_CD10_D1><<<gb, 256, 0, st>>>(f, out, n1, h->n, n3, bc1, bcn, h->co);
+    if (h->kind == NP_CD06_D1) np_rhs_kernel<NP_CD06_D1><<<gb, 256, 0, st>>>(f, out, n1, h->n, n3, bc1, bcn, h->co);
+    else if (h->kind == NP_CD10_D1) np_rhs_kernel<NP_CD10_D1><<<gb, 256, 0, st>>>(f, out, n1, h->n, n3, bc1, bcn, h->co);
     else if (h->kind == NP_CD10_D2) np_rhs_kernel<NP_CD10_D2><<<gb, 256, 0, st>>>(f, out, n1, h->n, n3, bc1, bcn, h->co);
     else np_rhs_kernel<NP_CF90><<<gb, 256, 0, st>>>(f, out, n1, h->n, n3, bc1, bcn, h->co);
     np_solve_kernel<<<blocks_for(n1 * n3, 128), 128, 0, st>>>(out, n1, h->n, n3, tab);
@@ -269,7 +302,8 @@ int np_apply_host(int kind, int n, double dx, int bc1, int bcn, int axis, const 
             double* y = out + k * n1 * n + x;
             for (int i = 0; i < n; ++i) {
                 double v;
-                if (kind == NP_CD10_D1) v = np_rhs_point<NP_CD10_D1>(i + 1, n, bc1, bcn, co, F);
+                if (kind == NP_CD06_D1) v = np_rhs_point<NP_CD06_D1>(i + 1, n, bc1, bcn, co, F);
+                else if (kind == NP_CD10_D1) v = np_rhs_point<NP_CD10_D1>(i + 1, n, bc1, bcn, co, F);
                 else if (kind == NP_CD10_D2) v = np_rhs_point<NP_CD10_D2>(i + 1, n, bc1, bcn, co, F);
                 else v = np_rhs_point<NP_CF90>(i + 1, n, bc1, bcn, co, F);
                 y[(long long)i * n1] = v;

@@ -16,7 +16,7 @@
 
 namespace pdo {
 
-enum NpKind { NP_CD10_D1 = 0, NP_CD10_D2 = 1, NP_CF90 = 2 };
+enum NpKind { NP_CD10_D1 = 0, NP_CD10_D2 = 1, NP_CF90 = 2, NP_CD06_D1 = 3 };   // CD06: one-sided closure only (cd06.F90:264-327)
 
 struct NpCoefs {
     double in[5];     // interior stencil: D1/D2: a, b, c (grid spacing folded in); CF90: a, b, c, d, e
@@ -35,7 +35,7 @@ struct NpCoefs {
 // F(j): value of the line at 1-based index j in [1, n]
 template <int KIND, class Acc>
 PDO_HD double np_rhs_point(int i, int n, int bc1, int bcn, const NpCoefs& c, Acc F) {
-    constexpr int NB = (KIND == NP_CD10_D2) ? 3 : 4;   // rows owned by the one-sided closure at each end
+    constexpr int NB = (KIND == NP_CD10_D2 || KIND == NP_CD06_D1) ? 3 : 4;   // rows owned by the one-sided closure at each end
     if (bc1 == 0 && i <= NB) {
         if (KIND == NP_CD10_D1) {
             if (i == 1) return c.r1[0] * F(1) + c.r1[1] * F(2) + c.r1[2] * F(3) + c.r1[3] * F(4);
@@ -46,6 +46,10 @@ PDO_HD double np_rhs_point(int i, int n, int bc1, int bcn, const NpCoefs& c, Acc
             if (i == 1) return c.r1[0] * F(1) + c.r1[1] * F(2) + c.r1[2] * F(3) + c.r1[3] * F(4) + c.r1[4] * F(5);
             if (i == 2) return c.r2[0] * (F(3) - 2.0 * F(2) + F(1));
             return c.r3[0] * (F(4) - 2.0 * F(3) + F(2)) + c.r3[1] * (F(5) - 2.0 * F(3) + F(1));
+        } else if (KIND == NP_CD06_D1) {
+            if (i == 1) return c.r1[0] * F(1) + c.r1[1] * F(2) + c.r1[2] * F(3) + c.r1[3] * F(4);
+            if (i == 2) return c.r2[0] * (F(3) - F(1));
+            return c.r3[0] * (F(4) - F(2)) + c.r3[1] * (F(5) - F(1));
         } else {
             if (i == 1) return c.r1[0] * (F(1));
             if (i == 2) return c.r2[0] * (F(2)) + c.r2[1] * (F(3) + F(1));
@@ -64,6 +68,10 @@ PDO_HD double np_rhs_point(int i, int n, int bc1, int bcn, const NpCoefs& c, Acc
             if (m == 1) return c.r1[0] * F(n) + c.r1[1] * F(n - 1) + c.r1[2] * F(n - 2) + c.r1[3] * F(n - 3) + c.r1[4] * F(n - 4);
             if (m == 2) return c.r2[0] * (F(n) - 2.0 * F(n - 1) + F(n - 2));
             return c.r3[0] * (F(n - 1) - 2.0 * F(n - 2) + F(n - 3)) + c.r3[1] * (F(n) - 2.0 * F(n - 2) + F(n - 4));
+        } else if (KIND == NP_CD06_D1) {
+            if (m == 1) return -c.r1[0] * F(n) - c.r1[1] * F(n - 1) - c.r1[2] * F(n - 2) - c.r1[3] * F(n - 3);
+            if (m == 2) return c.r2[0] * (F(n) - F(n - 2));
+            return c.r3[0] * (F(n - 1) - F(n - 3)) + c.r3[1] * (F(n) - F(n - 4));
         } else {
             if (m == 1) return c.r1[0] * (F(n));
             if (m == 2) return c.r2[0] * (F(n - 1)) + c.r2[1] * (F(n) + F(n - 2));
@@ -76,6 +84,8 @@ PDO_HD double np_rhs_point(int i, int n, int bc1, int bcn, const NpCoefs& c, Acc
     auto G = [&](int j) -> double { return j < 1 ? s1 * F(2 - j) : (j > n ? sn * F(2 * n - j) : F(j)); };
     if (KIND == NP_CD10_D1) {
         return c.in[0] * (G(i + 1) - G(i - 1)) + c.in[1] * (G(i + 2) - G(i - 2)) + c.in[2] * (G(i + 3) - G(i - 3));
+    } else if (KIND == NP_CD06_D1) {   // cd06.F90:574-575: the b06 term comes first
+        return c.in[1] * (G(i + 2) - G(i - 2)) + c.in[0] * (G(i + 1) - G(i - 1));
     } else if (KIND == NP_CD10_D2) {
         const double f0 = F(i);
         return c.in[0] * (G(i + 1) - 2.0 * f0 + G(i - 1)) + c.in[1] * (G(i + 2) - 2.0 * f0 + G(i - 2)) +

@@ -39,7 +39,8 @@ def test_init_error_codes_match_reference(pdo):
     assert pdo.cd10().init(5, 0.1) == 2      # cd10.F90:224
     assert pdo.cd06().init(4, 0.1) == 3      # cd06.F90:158
     assert pdo.cf90().init(9) == 7           # cf90.F90:128
-    assert pdo.cd06().init(16, 0.1, periodic_=False) == 1002  # out of scope, says so (the reference's own cd06 closures are marked incomplete)
+    assert pdo.cd06().init(16, 0.1, periodic_=False, bc1_=1) == 1002  # the reference marks cd06's symmetric closures "Incomplete"
+    assert pdo.cd06().init(5, 0.1, periodic_=False) == 3
     assert pdo.cd10().init(16, 0.1, periodic_=False, bc1_=2) == 324   # cd10.F90:2044-2046
     assert pdo.cd10().init(5, 0.1, periodic_=False) == 2
     with pytest.raises(pdo.PadeOpsError) as e:

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-KINDS = {"cd10_d1": 0, "cd10_d2": 1, "cf90": 2}
+KINDS = {"cd10_d1": 0, "cd10_d2": 1, "cf90": 2, "cd06_d1": 3}
 
 
 def product_host(pdo, kind, f, dx, axis, bc1, bcn):
@@ -24,6 +24,8 @@ def product_host(pdo, kind, f, dx, axis, bc1, bcn):
 def oracle_ref(oracle, kind, f, dx, axis, bc1, bcn):
     if kind == "cf90":
         return oracle.cf90_np(f, axis, bc1, bcn)
+    if kind == "cd06_d1":
+        return oracle.cd06_np(f, dx, axis)
     return oracle.cd10_np(f, dx, axis, 1 if kind == "cd10_d1" else 2, bc1, bcn)
 
 
@@ -32,13 +34,17 @@ def oracle_ref(oracle, kind, f, dx, axis, bc1, bcn):
 @pytest.mark.parametrize("bc1", [0, 1, -1])
 @pytest.mark.parametrize("bcn", [0, 1, -1])
 def test_product_np_routines_match_oracle(pdo, oracle, kind, axis, bc1, bcn):
+    if kind == "cd06_d1" and (bc1, bcn) != (0, 0):
+        pytest.skip("cd06 has the one-sided closure only")
     shape = {0: (3, 4, 19), 1: (3, 19, 4), 2: (19, 3, 4)}[axis]
     rng = np.random.default_rng(1000 + 100 * axis + 10 * bc1 + bcn)
     f = rng.standard_normal(shape)
     dx = 0.37
     got = product_host(pdo, kind, f, dx, axis, bc1, bcn)
     ref = oracle_ref(oracle, kind, f, dx, axis, bc1, bcn)
-    assert np.abs(got - ref).max() <= 1e-14 * np.abs(ref).max(), (kind, axis, bc1, bcn, np.abs(got - ref).max() / np.abs(ref).max())
+    # cd06: the product carries the tridiagonal system through its pentadiagonal sweeps, the reference through Thomas: rounding differs
+    tol = 1e-13 if kind == "cd06_d1" else 1e-14
+    assert np.abs(got - ref).max() <= tol * np.abs(ref).max(), (kind, axis, bc1, bcn, np.abs(got - ref).max() / np.abs(ref).max())
 
 
 def test_product_np_minimum_lengths_and_codes(pdo):

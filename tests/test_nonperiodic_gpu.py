@@ -80,3 +80,15 @@ def test_one_sided_closure_exact_on_quartics_on_the_gpu(pdo):
     assert h.init(n, dx, periodic_=False) == 0
     assert np.abs(h.dd1(_dev(f)).cpu().numpy() - 4 * x ** 3).max() < 1e-11
     assert np.abs(h.d2d1(_dev(f)).cpu().numpy() - 12 * x ** 2).max() < 1e-8
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_cd06_nonperiodic_one_sided(pdo, oracle, axis):
+    shape = {0: (3, 5, 24), 1: (3, 24, 5), 2: (24, 3, 5)}[axis]
+    n, dx = 24, 0.1
+    f = np.random.default_rng(20 + axis).standard_normal(shape)
+    h = pdo.cd06()
+    assert h.init(n, dx, periodic_=False) == 0
+    got = (h.dd1, h.dd2, h.dd3)[axis](_dev(f)).cpu().numpy()
+    assert _rel(got, oracle.cd06_np(f, dx, axis)) < TOL
+    assert pdo.cd06().init(n, dx, periodic_=False, bc1_=1) == 1002

@@ -145,3 +145,35 @@ def test_cf90_np_lu_solves_its_rows(oracle, bc1, bcn):
     x = oracle.cd10_np_solve_line(P, r)
     assert np.abs(x - np.linalg.solve(A, r)).max() < 1e-12 * np.abs(x).max() * max(1.0, np.linalg.cond(A) / 10)
     assert oracle.cf90_np_penta(9, 0, 0)[0] == 7
+
+
+# ---- CD06 non-periodic (derivatives/cd06.F90:27-58, 264-327, 432-449, 551-590): one-sided closure only ----
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_cd06_np_exact_for_quartics_and_sixth_order_inside(oracle, axis):
+    n = 41
+    dx = 1.0 / (n - 1)
+    x = np.arange(n) * dx
+    for k in range(5):
+        exact = k * x ** (k - 1) if k > 0 else 0 * x
+        assert np.abs(oracle.cd06_np(_lines(x ** k, axis), dx, axis) - _lines(exact, axis)).max() < 1e-12, (k, axis)
+    err = []
+    for m in (33, 65):
+        h = np.pi / (m - 1)
+        xx = np.arange(m) * h
+        err.append(np.abs(oracle.cd06_np(_lines(np.sin(xx), 0), h, 0)[0, 0] - np.cos(xx)).max())
+    assert err[1] < err[0] / 8       # at least third order globally (the boundary rows limit it), and converging
+
+
+def test_cd06_np_thomas_solves_its_rows(oracle):
+    n = 18
+    rc, T = oracle.cd06_np_tri(n)
+    assert rc == 0 and oracle.cd06_np_tri(5)[0] == 3
+    a, b, c = T[3], T[4], T[5]
+    A = np.diag(b) + np.diag(c[:-1], 1) + np.diag(a[1:], -1)
+    # interior rows are the periodic scheme's (alpha = 1/3), the three boundary rows at each end mirror each other
+    assert np.allclose(A[5, 4:7], [1 / 3, 1, 1 / 3]) and np.allclose(A[::-1, ::-1], A)
+    # derivative of a random smooth-ish line through the oracle == dense solve of (rows, RHS implied by the operator on polynomials)
+    x = np.linspace(0, 1, n)
+    f = x ** 3
+    got = oracle.cd06_np(_lines(f, 0), x[1] - x[0], 0)[0, 0]
+    assert np.abs(got - 3 * x ** 2).max() < 1e-12
