@@ -62,3 +62,17 @@ def test_reference_arm_under_torchrun_prints_once():
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1 and lines[0]["impl"] == "reference" and lines[0]["cpu_baseline"]["kind"] == "port"
     assert lines[0]["value"] > 0 and lines[0]["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_committed_bench_lines_meet_the_contract():
+    """The bench lines kept under profiles/ (written by bench.py on the B200 boxes) and a fresh reference-arm line satisfy the
+    driver's JSON contract: tools/check_bench_line.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from check_bench_line import check
+    for n in (1, 2, 4):
+        fn = os.path.join(ROOT, "profiles", f"r01_bench_n{n}.json")
+        line = [json.loads(l) for l in open(fn) if l.startswith("{")][0]
+        assert check(line) == [], (fn, check(line))
+        assert line["n_gpus"] == n
+    full = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_n1.json")))
+    assert full["e2e"]["h2d_bytes_per_step"] > 0 and full["cpu_baseline"]["kind"] == "port" and full["roofline"]["traffic"]
