@@ -281,7 +281,7 @@ int pdo_padepoisson_divergence_check(pdo_padepoisson_t h, double* uhat, double* 
                                      int fix_div, double* max_div, void* stream);
 
 /* ---- IncompressibleGrid::igrid, the periodic substep  (incompressible/igrid.F90) ---------------
-   Scope: PeriodicInZ, NumericalSchemeVert = 1 (CD06), AdvectionTerm = 1 (skew-symmetric), TimeSteppingScheme 1
+   Scope: PeriodicInZ, NumericalSchemeVert = 1 (CD06), AdvectionTerm = 1 (skew-symmetric) or 0 (rotational), TimeSteppingScheme 1
    (TVD-RK3) or 2 (SSP-RK45), viscous or inviscid, no SGS / forcing / Coriolis / stratification / turbines.
    The namelist file of igrid%init is replaced by this struct. */
 typedef struct pdo_igrid_s* pdo_igrid_t;
@@ -296,6 +296,7 @@ typedef struct {
     int p_row, p_col;             /* 0,0 = 1 x nproc */
     int use_d2dz2_c2c;            /* 1: d2dz2_C2C for the viscous z term (slip/periodic BC codes), 0: ddz_E2C(ddz_C2E) (igrid.F90:2642-2660) */
     int compute_all_gradients;    /* 1: all 18 duidxjC/E fields like the reference; 0: only the 9 the substep reads */
+    int rotational_advection;     /* 0: AdvectionTerm = 1, skew-symmetric (igrid.F90:1572-1679); 1: AdvectionTerm = 0, u x omega (:1527-1555) */
 } pdo_igrid_params;
 /* igrid%init: u, v on the cell grid, w on the edge grid (nz+1 planes, plane nz+1 == plane 1), x-pencil local blocks,
    host or device pointers (initfields_wallM is the caller's job).  Runs the fft / dealias / projection / gradient

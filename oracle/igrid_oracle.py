@@ -208,11 +208,13 @@ class PadePoisson:
 
 
 class IGrid:
-    """igrid, periodic in x, y, z; NumericalSchemeVert = 1 (CD06), AdvectionTerm = 1 (skew-symmetric), no SGS / forcing /
+    """igrid, periodic in x, y, z; NumericalSchemeVert = 1 (CD06), AdvectionTerm = 1 (skew-symmetric) or 0 (rotational), no SGS / forcing /
     Coriolis / stratification; viscous unless isInviscid.  u, v: (nz, ny, nx); w: (nz+1, ny, nx) with plane nz == plane 0."""
 
     def __init__(self, nx, ny, nz, Lx, Ly, Lz, Re, u, v, w, isInviscid=False, dealiasFact=2.0 / 3.0, t_DivergenceCheck=10,
-                 TimeSteppingScheme=1, use_d2dz2_C2C=True):
+                 TimeSteppingScheme=1, use_d2dz2_C2C=True, AdvectionTerm=1):
+        assert AdvectionTerm in (0, 1)      # 0 rotational (igrid.F90:1527-1555), 1 skew-symmetric (:1572-1679)
+        self.AdvectionTerm = AdvectionTerm
         self.nx, self.ny, self.nz = nx, ny, nz
         self.dx, self.dy, self.dz = Lx / nx, Ly / ny, Lz / nz
         self.Re, self.isInviscid = Re, isInviscid
@@ -310,9 +312,28 @@ class IGrid:
         w_rhs = w_rhs + E.mTimes_ik2(fT1E)
         return -0.5 * u_rhs, -0.5 * v_rhs, -0.5 * w_rhs
 
+    # ---- igrid.F90:1527-1555: u x omega, the z-components multiplied on the edge grid and interpolated back
+    def addNonLinearTerm_Rot(self):
+        C, E, ops, d = self.spectC, self.spectE, self.ops, self.duidxj
+        T1C = d["dvdx"] - d["dudy"]; T1C = T1C * self.v
+        fT1C = C.fft(T1C)
+        T2E = d["dwdx"] - d["dudz"]; T2E = T2E * self.w
+        fT2E = E.fft(T2E)
+        u_rhs = ops.interpz_E2C(fT2E) + fT1C
+        T1C = d["dudy"] - d["dvdx"]; T1C = T1C * self.u
+        fT1C = C.fft(T1C)
+        T2E = d["dwdy"] - d["dvdz"]; T2E = T2E * self.w
+        fT2E = E.fft(T2E)
+        v_rhs = ops.interpz_E2C(fT2E) + fT1C
+        T1E = d["dudz"] - d["dwdx"]; T1E = T1E * self.uE
+        T2E = d["dvdz"] - d["dwdy"]; T2E = T2E * self.vE
+        T1E = T1E + T2E
+        w_rhs = E.fft(T1E)
+        return u_rhs, v_rhs, w_rhs
+
     # ---- igrid.F90:1793-1912 (branches in scope) + 1914-1941
     def populate_rhs(self):
-        u_rhs, v_rhs, w_rhs = self.addNonLinearTerm_skewSymm()
+        u_rhs, v_rhs, w_rhs = self.addNonLinearTerm_skewSymm() if self.AdvectionTerm == 1 else self.addNonLinearTerm_Rot()
         if not self.isInviscid:
             oneByRe = 1.0 / self.Re
             u_rhs = u_rhs + oneByRe * (-self.spectC.kabs_sq * self.uhat + self.d2udz2hatC)

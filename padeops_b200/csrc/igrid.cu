@@ -750,6 +750,16 @@ int mul2(double* out, const double* a, const double* b, const double* c, const d
     if (c) return launch_ew(n, st, [=] __device__(long long i) { out[i] = a[i] * b[i] + c[i] * d[i]; });
     return launch_ew(n, st, [=] __device__(long long i) { out[i] = a[i] * b[i]; });
 }
+// out = (a - b) * c  (+ (d - e) * f): the rotational form's products (igrid.F90:1527-1549: "T = dvdx - dudy; T = T*v")
+int muldiff(double* out, const double* a, const double* b, const double* c, const double* d, const double* e, const double* f, long long n,
+            cudaStream_t st) {
+    if (d) return launch_ew(n, st, [=] __device__(long long i) {
+        const double t1 = (a[i] - b[i]) * c[i];
+        const double t2 = (d[i] - e[i]) * f[i];
+        out[i] = t1 + t2;
+    });
+    return launch_ew(n, st, [=] __device__(long long i) { out[i] = (a[i] - b[i]) * c[i]; });
+}
 // dst += src (complex arrays viewed as doubles)
 int cadd(double2* dst, const double2* src, long long n, cudaStream_t st) {
     double* d = (double*)dst;
@@ -942,9 +952,38 @@ int ig_nonlinear_skew(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cud
     return 0;
 }
 
-// rhs = -half*rhs, then addViscousTerm (igrid.F90:1663-1665, 1914-1941), one pass per component
+// ---- igrid.F90:1527-1555 into (ru, rv, rw): u x omega; the products with w live on the edge grid and come back through
+// interpz_E2C.  Gradient slots: C 1 dudy, 3 dvdx; E 2 dudz, 5 dvdz, 6 dwdx, 7 dwdy.
+int ig_nonlinear_rot(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStream_t st) {
+    double *T1C = g->rbC[0], *T1E = g->rbE[0];
+    double2 *fT1C = g->yC[0], *fT1E = g->yE[0];
+    double **GC = g->gradC, **GE = g->gradE;
+    const double2* z = nullptr;
+    double2* t = nullptr;
+    for (int c = 0; c < 2; ++c) {
+        double2* r = c == 0 ? ru : rv;
+        // c = 0: (dvdx - dudy) v and (dwdx - dudz) w;   c = 1: (dudy - dvdx) u and (dwdy - dvdz) w
+        if (c == 0) IG(muldiff(T1C, GC[3], GC[1], g->v, nullptr, nullptr, nullptr, g->nRC, st));
+        else IG(muldiff(T1C, GC[1], GC[3], g->u, nullptr, nullptr, nullptr, g->nRC, st));
+        IG(fftC(g, T1C, fT1C, st));
+        if (c == 0) IG(muldiff(T1E, GE[6], GE[2], g->w, nullptr, nullptr, nullptr, g->nRE, st));
+        else IG(muldiff(T1E, GE[7], GE[5], g->w, nullptr, nullptr, nullptr, g->nRE, st));
+        IG(fftE(g, T1E, fT1E, st));
+        IG(zviewE(g, fT1E, g->zE[0], &z, st));
+        t = ztarget(g, r, g->zC[0]);
+        ZOP(pdo_pade6stagg_interpz_E2C, z, t);
+        IG(zcommitC(g, t, r, st));
+        IG(cadd(r, fT1C, g->nYC, st));
+    }
+    // w_rhs = fft((dudz - dwdx) uE + (dvdz - dwdy) vE)
+    IG(muldiff(T1E, GE[2], GE[6], g->uE, GE[5], GE[7], g->vE, g->nRE, st));
+    return fftE(g, T1E, rw, st);
+}
+
+// rhs = -half*rhs (skew-symmetric form only), then addViscousTerm (igrid.F90:1663-1665, 1914-1941), one pass per component
 int ig_finish_rhs(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStream_t st) {
     const bool visc = !g->prm.is_inviscid;
+    const double scale = g->prm.rotational_advection ? 1.0 : -0.5;
     const double oneByRe = visc ? 1.0 / g->prm.Re : 0.0;
     for (int c = 0; c < 3; ++c) {
         pdo_spectral_s* s = c < 2 ? g->spC : g->spE;
@@ -955,7 +994,7 @@ int ig_finish_rhs(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStr
         const double *k1 = s->k1y, *k2 = s->k2;
         IG(launch_ew(vol(s->si.ysz), st, [=] __device__(long long i) {
             double2 a = r[i];
-            a.x = -0.5 * a.x; a.y = -0.5 * a.y;
+            a.x = scale * a.x; a.y = scale * a.y;
             if (visc) {
                 const double ka = k1[(int)(i % n1)], kb = k2[(int)((i / n1) % n2)];
                 const double ksq = ka * ka + kb * kb;  // kabs_sq = k1**2 + k2**2 (spectral.F90:1093-1099)
@@ -970,7 +1009,8 @@ int ig_finish_rhs(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStr
 }
 
 int ig_populate_rhs(pdo_igrid_s* g, double2** r, cudaStream_t st) {
-    IG(ig_nonlinear_skew(g, r[0], r[1], r[2], st));
+    if (g->prm.rotational_advection) IG(ig_nonlinear_rot(g, r[0], r[1], r[2], st));
+    else IG(ig_nonlinear_skew(g, r[0], r[1], r[2], st));
     return ig_finish_rhs(g, r[0], r[1], r[2], st);
 }
 

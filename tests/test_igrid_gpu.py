@@ -190,3 +190,25 @@ def test_igrid_all_gradients_flag_does_not_change_the_solution(pdo):
         g.timeAdvance(0.01)
         outs.append((g.get("u"), g.get("w")))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.xfail(strict=False, reason="rotational advection form added after the round's last GPU session: first hardware run "
+                                        "happens in the driver's round-end test pass (CPU oracle side is pinned in test_oracle_igrid.py)")
+@pytest.mark.parametrize("scheme", [1, 2])
+def test_igrid_substep_rotational_form_matches_oracle(pdo, IG, scheme):
+    """AdvectionTerm = 0 (u x omega, igrid.F90:1527-1555 — what the authors' HIT deck runs) against the oracle."""
+    nx, ny, nz = 24, 16, 32
+    L = (2 * np.pi, 2 * np.pi, 2 * np.pi)
+    u, v = broadband((nz, ny, nx), 1), broadband((nz, ny, nx), 2)
+    w = broadband((nz + 1, ny, nx), 3)
+    w[nz] = w[0]
+    ref = IG.IGrid(nx, ny, nz, *L, 50.0, u, v, w, TimeSteppingScheme=scheme, AdvectionTerm=0)
+    g = pdo.igrid()
+    g.init(nx, ny, nz, *L, 50.0, u, v, w, TimeSteppingScheme=scheme, AdvectionTerm=0)
+    for it in range(2):
+        ref.timeAdvance(0.01)
+        g.timeAdvance(0.01)
+        for nm in ("u", "v", "w", "uhat", "vhat", "what"):
+            r = getattr(ref, nm)
+            assert np.abs(g.get(nm) - r).max() < TOL * np.abs(r).max(), (it, nm)
+    assert g.maxDivergence() < 1e-11 * max(np.abs(ref.u).max(), np.abs(ref.w).max())
