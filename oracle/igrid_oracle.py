@@ -127,20 +127,49 @@ def getmodCD06stagg(k, dx):
 
 
 class Pade6stagg:
-    """PadeDerOps::Pade6stagg, isPeriodic = .true., scheme = cd06 (BC integers are ignored on this branch)."""
+    """PadeDerOps::Pade6stagg, isPeriodic = .true. (BC integers are ignored on this branch).  scheme = 1: cd06 (the compact
+    staggered operators); scheme = 2: fourierColl — every operator is `c2c-z forward, x table(k3), c2c-z backward, x 1/nz`
+    with the tables of spectral.F90:843-856 (k3 = GetWaveNums(nz, dz), shifts e^{+-i k3 dz/2} between cells and edges), the
+    complex procedures of spectral.F90:387-407, 462-482, 528-568, 596-680; edge outputs copy plane 1 into plane nz+1."""
 
-    def __init__(self, nz, dz):
-        self.nz, self.dz = nz, dz
+    def __init__(self, nz, dz, scheme=1):
+        assert scheme in (1, 2)
+        self.nz, self.dz, self.scheme = nz, dz, scheme
+        if scheme == 2:
+            k3 = O.wavenums(nz, dz)
+            self.mk3sq = -(k3 ** 2)
+            self.k3_C2Eshift = 1j * k3 * np.exp(-1j * k3 * dz / 2.0)
+            self.k3_E2Cshift = 1j * k3 * np.exp(1j * k3 * dz / 2.0)
+            self.C2Eshift = np.exp(-1j * k3 * dz / 2.0)
+            self.E2Cshift = np.exp(1j * k3 * dz / 2.0)
 
-    def ddz_E2C(self, fE): return O.stagg("ddz_E2C", fE, self.nz, self.dz)
-    def ddz_C2E(self, fC): return O.stagg("ddz_C2E", fC, self.nz, self.dz)
-    def interpz_E2C(self, fE): return O.stagg("interp_E2C", fE, self.nz, self.dz)
-    def interpz_C2E(self, fC): return O.stagg("interp_C2E", fC, self.nz, self.dz)
-    def d2dz2_C2C(self, fC): return O.stagg("d2dz2_C2C", fC, self.nz, self.dz)
-    def d2dz2_E2E(self, fE): return O.stagg("d2dz2_E2E", fE, self.nz, self.dz)
+    def _spect(self, f, table, edge_out):
+        nz = self.nz
+        out = np.fft.ifft(np.fft.fft(np.asarray(f)[:nz], axis=0) * table[:, None, None], axis=0)   # backward x normfactz = numpy's ifft
+        if edge_out:
+            out = np.concatenate([out, out[:1]], axis=0)
+        return out
+
+    def ddz_E2C(self, fE):
+        return O.stagg("ddz_E2C", fE, self.nz, self.dz) if self.scheme == 1 else self._spect(fE, self.k3_E2Cshift, False)
+
+    def ddz_C2E(self, fC):
+        return O.stagg("ddz_C2E", fC, self.nz, self.dz) if self.scheme == 1 else self._spect(fC, self.k3_C2Eshift, True)
+
+    def interpz_E2C(self, fE):
+        return O.stagg("interp_E2C", fE, self.nz, self.dz) if self.scheme == 1 else self._spect(fE, self.E2Cshift, False)
+
+    def interpz_C2E(self, fC):
+        return O.stagg("interp_C2E", fC, self.nz, self.dz) if self.scheme == 1 else self._spect(fC, self.C2Eshift, True)
+
+    def d2dz2_C2C(self, fC):
+        return O.stagg("d2dz2_C2C", fC, self.nz, self.dz) if self.scheme == 1 else self._spect(fC, self.mk3sq, False)
+
+    def d2dz2_E2E(self, fE):
+        return O.stagg("d2dz2_E2E", fE, self.nz, self.dz) if self.scheme == 1 else self._spect(fE, self.mk3sq, True)
 
     def getModifiedWavenumbers(self, k):
-        return getmodCD06stagg(k, self.dz)
+        return getmodCD06stagg(k, self.dz) if self.scheme == 1 else np.array(k, dtype=float)     # PadeDerOps.F90:1003-1006
 
 
 class PadePoisson:
@@ -208,12 +237,13 @@ class PadePoisson:
 
 
 class IGrid:
-    """igrid, periodic in x, y, z; NumericalSchemeVert = 1 (CD06), AdvectionTerm = 1 (skew-symmetric) or 0 (rotational), no SGS / forcing /
+    """igrid, periodic in x, y, z; NumericalSchemeVert = 1 (CD06) or 2 (Fourier collocation in z), AdvectionTerm = 1 (skew-symmetric) or 0 (rotational), no SGS / forcing /
     Coriolis / stratification; viscous unless isInviscid.  u, v: (nz, ny, nx); w: (nz+1, ny, nx) with plane nz == plane 0."""
 
     def __init__(self, nx, ny, nz, Lx, Ly, Lz, Re, u, v, w, isInviscid=False, dealiasFact=2.0 / 3.0, t_DivergenceCheck=10,
-                 TimeSteppingScheme=1, use_d2dz2_C2C=True, AdvectionTerm=1):
+                 TimeSteppingScheme=1, use_d2dz2_C2C=True, AdvectionTerm=1, NumericalSchemeVert=1):
         assert AdvectionTerm in (0, 1)      # 0 rotational (igrid.F90:1527-1555), 1 skew-symmetric (:1572-1679)
+        assert NumericalSchemeVert in (1, 2)  # 1 cd06, 2 fourierColl (PadeDerOps.F90:16-18)
         self.AdvectionTerm = AdvectionTerm
         self.nx, self.ny, self.nz = nx, ny, nz
         self.dx, self.dy, self.dz = Lx / nx, Ly / ny, Lz / nz
@@ -222,7 +252,7 @@ class IGrid:
         self.use_d2dz2_C2C = use_d2dz2_C2C
         self.spectC = Spectral(nx, ny, nz, self.dx, self.dy, self.dz, True, dealiasFact, False)
         self.spectE = Spectral(nx, ny, nz + 1, self.dx, self.dy, self.dz, False, dealiasFact, False)
-        self.ops = Pade6stagg(nz, self.dz)
+        self.ops = Pade6stagg(nz, self.dz, NumericalSchemeVert)
         self.poiss = PadePoisson(self.dx, self.dy, self.dz, self.spectC, self.spectE, self.ops)
         self.step, self.tsim = 0, 0.0
         # igrid.F90:625-655

@@ -150,3 +150,41 @@ def test_rotational_and_skew_symmetric_forms_agree_to_truncation_error():
         diffs.append(max(np.abs(a - b).max() for a, b in zip(*out)))
     # measured: 5.6e-5 (n = 16), 1.0e-6 (n = 32), 1.5e-8 (n = 64): sixth order, the z schemes' truncation error
     assert diffs[0] < 2e-4 and diffs[1] < diffs[0] / 30, diffs
+
+
+def test_fourier_collocation_z_operators_are_exact_on_resolved_modes():
+    """scheme = fourierColl (spectral.F90:843-856 tables): derivative, interpolation and second derivative between the cell
+    and edge grids are exact for every resolved z-mode, real or complex."""
+    nz = 16
+    dz = 2 * np.pi / nz
+    zC, zE = (np.arange(nz) + 0.5) * dz, np.arange(nz + 1) * dz
+    ops = IG.Pade6stagg(nz, dz, scheme=2)
+    for m in (1, 3, 5):
+        fC = (np.exp(1j * m * zC))[:, None, None] * np.ones((1, 2, 3))
+        fE = (np.exp(1j * m * zE))[:, None, None] * np.ones((1, 2, 3))
+        assert np.abs(ops.ddz_E2C(fE) - 1j * m * fC).max() < 1e-13 * m
+        assert np.abs(ops.ddz_C2E(fC) - 1j * m * fE).max() < 1e-13 * m
+        assert np.abs(ops.interpz_E2C(fE) - fC).max() < 1e-13
+        assert np.abs(ops.interpz_C2E(fC) - fE).max() < 1e-13
+        assert np.abs(ops.d2dz2_C2C(fC) + m * m * fC).max() < 1e-12 * m * m
+        assert np.abs(ops.d2dz2_E2E(fE) + m * m * fE).max() < 1e-12 * m * m
+    k = np.array([0.0, 1.0, -3.0])
+    assert np.array_equal(ops.getModifiedWavenumbers(k), k)      # PadeDerOps.F90:1003-1004
+
+
+@pytest.mark.parametrize("adv", [0, 1])
+def test_taylor_green_decay_fourier_z(adv):
+    """NumericalSchemeVert = 2: the x-z Taylor-Green vortex decays at the exact rate to rounding-level accuracy (no z
+    truncation error any more), with either form of the advection term."""
+    n = 16
+    Re = 100.0
+    x, y, zC, zE = _grid(n, n, n)
+    X, ZC, ZE = x[None, None, :], zC[:, None, None], zE[:, None, None]
+    u = np.sin(X) * np.cos(ZC) * np.ones((1, n, 1)); v = np.zeros((n, n, n)); w = -np.cos(X) * np.sin(ZE) * np.ones((1, n, 1))
+    g = IG.IGrid(n, n, n, 2 * np.pi, 2 * np.pi, 2 * np.pi, Re, u, v, w, TimeSteppingScheme=1, AdvectionTerm=adv, NumericalSchemeVert=2)
+    dt = 0.25 * (2 * np.pi / n)
+    for _ in range(4):
+        g.timeAdvance(dt)
+    decay = np.exp(-2.0 * g.tsim / Re)
+    assert np.abs(g.u - u * decay).max() < 1e-9 and np.abs(g.w - w * decay).max() < 1e-9 and np.abs(g.v).max() < 1e-12
+    assert np.abs(g.poiss.divergence(g.uhat, g.vhat, g.what)).max() < 1e-12
