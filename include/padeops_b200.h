@@ -249,9 +249,13 @@ typedef struct pdo_pade6stagg_s* pdo_pade6stagg_t;
 #define PDO_SCHEME_CD06 1
 #define PDO_SCHEME_FOURIER 2
 /* Pade6stagg%init(gpC, sp_gpC, gpE, sp_gpE, dz, scheme, isPeriodic, spectC)                        PadeDerOps.F90:57-88
-   gp_zsz / sp_zsz: z-pencil sizes of the physical / spectral CELL decompositions.  scheme: cd06 only (fourierColl
-   and fd02 return PDO_E_UNSUPPORTED this round). */
+   gp_zsz / sp_zsz: z-pencil sizes of the physical / spectral CELL decompositions.  scheme: cd06 here (fourierColl needs
+   the spectC of pdo_pade6stagg_init2 and returns code 43 through this entry; fd02 returns PDO_E_UNSUPPORTED). */
 int pdo_pade6stagg_init(pdo_pade6stagg_t* h, const int gp_zsz[3], const int sp_zsz[3], double dz, int scheme, int is_periodic);
+/* the reference's init takes the optional spectC (PadeDerOps.F90:57-78): required for scheme = fourierColl (else code 43), where
+   every operator becomes c2c-z forward, x table(k3), c2c-z backward, x 1/nz (spectral.F90:387-680, 843-856; complex arrays only) */
+int pdo_pade6stagg_init2(pdo_pade6stagg_t* h, const int gp_zsz[3], const int sp_zsz[3], double dz, int scheme, int is_periodic,
+                         struct pdo_spectral_s* spectC);
 int pdo_pade6stagg_destroy(pdo_pade6stagg_t h);
 /* generic over real (is_complex = 0, sizes from gp) / complex (is_complex = 1, sizes from sp_gp); bot/top BC integers
    are accepted and ignored, as on the reference's periodic branch (:146-160, 404-418, 572-585, 689-702, 879-892) */
@@ -281,7 +285,7 @@ int pdo_padepoisson_divergence_check(pdo_padepoisson_t h, double* uhat, double* 
                                      int fix_div, double* max_div, void* stream);
 
 /* ---- IncompressibleGrid::igrid, the periodic substep  (incompressible/igrid.F90) ---------------
-   Scope: PeriodicInZ, NumericalSchemeVert = 1 (CD06), AdvectionTerm = 1 (skew-symmetric) or 0 (rotational), TimeSteppingScheme 1
+   Scope: PeriodicInZ, NumericalSchemeVert = 1 (CD06) or 2 (Fourier collocation), AdvectionTerm = 1 (skew-symmetric) or 0 (rotational), TimeSteppingScheme 1
    (TVD-RK3) or 2 (SSP-RK45), viscous or inviscid, no SGS / forcing / Coriolis / stratification / turbines.
    The namelist file of igrid%init is replaced by this struct. */
 typedef struct pdo_igrid_s* pdo_igrid_t;
@@ -297,6 +301,7 @@ typedef struct {
     int use_d2dz2_c2c;            /* 1: d2dz2_C2C for the viscous z term (slip/periodic BC codes), 0: ddz_E2C(ddz_C2E) (igrid.F90:2642-2660) */
     int compute_all_gradients;    /* 1: all 18 duidxjC/E fields like the reference; 0: only the 9 the substep reads */
     int rotational_advection;     /* 0: AdvectionTerm = 1, skew-symmetric (igrid.F90:1572-1679); 1: AdvectionTerm = 0, u x omega (:1527-1555) */
+    int fourier_collocation_z;    /* 0: NumericalSchemeVert = 1, cd06 staggered operators; 1: NumericalSchemeVert = 2, Fourier collocation in z */
 } pdo_igrid_params;
 /* igrid%init: u, v on the cell grid, w on the edge grid (nz+1 planes, plane nz+1 == plane 1), x-pencil local blocks,
    host or device pointers (initfields_wallM is the caller's job).  Runs the fft / dealias / projection / gradient

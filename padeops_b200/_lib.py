@@ -107,7 +107,7 @@ class IgridParams(C.Structure):
     _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("Lx", C.c_double), ("Ly", C.c_double), ("Lz", C.c_double),
                 ("Re", C.c_double), ("is_inviscid", C.c_int), ("dealias_fact", C.c_double), ("t_divergence_check", C.c_int),
                 ("time_stepping_scheme", C.c_int), ("p_row", C.c_int), ("p_col", C.c_int), ("use_d2dz2_c2c", C.c_int),
-                ("compute_all_gradients", C.c_int), ("rotational_advection", C.c_int)]
+                ("compute_all_gradients", C.c_int), ("rotational_advection", C.c_int), ("fourier_collocation_z", C.c_int)]
 
 
 _PROTOS.update({
@@ -128,6 +128,7 @@ _PROTOS.update({
     "pdo_spectral_take_ifft1d_z2z_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "pdo_spectral_get_tables": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "pdo_pade6stagg_init": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_double, C.c_int, C.c_int]),
+    "pdo_pade6stagg_init2": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_double, C.c_int, C.c_int, C.c_void_p]),
     "pdo_pade6stagg_destroy": (C.c_int, [C.c_void_p]),
     "pdo_pade6stagg_get_modified_wavenumbers": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int]),
     "pdo_padepoisson_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -319,12 +319,50 @@ struct pdo_pade6stagg_s {
     double dz;
     int scheme;
     pdo_cd06stagg_t der = nullptr;
+    // scheme = fourierColl: the spectral type whose z transforms are used (borrowed) and the tables of spectral.F90:843-856
+    pdo_spectral_t spectC = nullptr;
+    double2* ftab[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // k3_E2Cshift, k3_C2Eshift, E2Cshift, C2Eshift, mk3sq
 };
 
 namespace {
 typedef int (*stagg_fn)(pdo_cd06stagg_t, const double*, double*, int, int, int, void*);
-int pade_apply(pdo_pade6stagg_s* p, stagg_fn fn, const double* in, double* out, int is_complex, void* st) {
+
+// Fourier collocation in z (spectral.F90:387-407, 462-482, 549-568, 596-680, the complex procedures): c2c-z forward on the first
+// nz planes, multiply plane k by table(k), c2c-z backward, x 1/nz; edge outputs get plane nz+1 := plane 1.
+// which: 0 ddz_E2C, 1 ddz_C2E, 2 interp_E2C, 3 interp_C2E, 4 d2dz2_C2C, 5 d2dz2_E2E
+int pade_fourier(pdo_pade6stagg_s* p, int which, const double* in, double* out, int is_complex, void* stream) {
+    if (!is_complex)
+        return fail(PDO_E_UNSUPPORTED, "Pade6stagg fourierColl: only the complex (spectral-array) procedures are built; the real ones drop the oddball mode");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nz = p->sp_zsz[2];
+    const size_t plane = (size_t)p->sp_zsz[0] * p->sp_zsz[1];
+    const bool edge_in = (which == 0 || which == 2 || which == 5), edge_out = (which == 1 || which == 3 || which == 5);
+    const size_t bin = sizeof(double2) * plane * (size_t)(nz + (edge_in ? 1 : 0)), bout = sizeof(double2) * plane * (size_t)(nz + (edge_out ? 1 : 0));
+    static const int tab_of[6] = {0, 1, 2, 3, 4, 4};
+    const double2* tab = p->ftab[tab_of[which]];
+    const double nf = 1.0 / (double)nz;
+    pdo_spectral_s* s = p->spectC;
+    return with_device_views(in, bin, out, bout, st, [&](const void* di, void* d_o) -> int {
+        double2* w = (double2*)d_o;
+        if (di != d_o) PDO_CUDA(cudaMemcpyAsync(w, di, sizeof(double2) * plane * (size_t)nz, cudaMemcpyDeviceToDevice, st));
+        if (int rc = fft3d_z_inplace(s->ft, w, -1, st)) return rc;
+        const long long pl = (long long)plane;
+        // one pass between the transforms: table(k) and the 1/nz of the backward transform together
+        if (int rc = launch_ew(pl * nz, st, [=] __device__(long long i) {
+                double2 t = tab[(int)(i / pl)];
+                const double2 v = w[i];
+                t.x *= nf; t.y *= nf;
+                w[i] = make_double2(v.x * t.x - v.y * t.y, v.x * t.y + v.y * t.x);
+            })) return rc;
+        if (int rc = fft3d_z_inplace(s->ft, w, +1, st)) return rc;
+        if (edge_out) PDO_CUDA(cudaMemcpyAsync(w + plane * (size_t)nz, w, sizeof(double2) * plane, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    });
+}
+
+int pade_apply(pdo_pade6stagg_s* p, stagg_fn fn, int which, const double* in, double* out, int is_complex, void* st) {
     if (!p) return fail(PDO_E_BADARG, "null handle");
+    if (p->scheme == PDO_SCHEME_FOURIER) return pade_fourier(p, which, in, out, is_complex, st);
     const int* z = is_complex ? p->sp_zsz : p->gp_zsz;
     return fn(p->der, in, out, z[0], z[1], is_complex, st);
 }
@@ -332,44 +370,79 @@ int pade_apply(pdo_pade6stagg_s* p, stagg_fn fn, const double* in, double* out, 
 
 extern "C" {
 
-int pdo_pade6stagg_init(pdo_pade6stagg_t* h, const int gp_zsz[3], const int sp_zsz[3], double dz, int scheme, int is_periodic) {
+int pdo_pade6stagg_init2(pdo_pade6stagg_t* h, const int gp_zsz[3], const int sp_zsz[3], double dz, int scheme, int is_periodic,
+                         pdo_spectral_t spectC) {
     if (!h || !gp_zsz || !sp_zsz) return fail(PDO_E_BADARG, "null argument");
     *h = nullptr;
     if (!is_periodic) return fail(PDO_E_UNSUPPORTED, "Pade6stagg: non-periodic closures are out of scope (SURVEY.md 8f rank 2)");
-    if (scheme == PDO_SCHEME_FOURIER || scheme == PDO_SCHEME_FD02)
-        return fail(PDO_E_UNSUPPORTED, "Pade6stagg: only scheme = cd06 is built (fourierColl / fd02 are SURVEY.md A.6 variants)");
-    if (scheme != PDO_SCHEME_CD06) return fail(434, "Invalid choice of numerical scheme in vertical");  // PadeDerOps.F90:84
+    if (scheme == PDO_SCHEME_FD02) return fail(PDO_E_UNSUPPORTED, "Pade6stagg: scheme fd02 is not built (cd06 and fourierColl are)");
+    if (scheme != PDO_SCHEME_CD06 && scheme != PDO_SCHEME_FOURIER) return fail(434, "Invalid choice of numerical scheme in vertical");  // PadeDerOps.F90:84
+    if (scheme == PDO_SCHEME_FOURIER) {
+        if (!spectC) return fail(43, "You need to pass in a spectral derived type if you want to use Fourier differentiation in z");  // :77
+        if (!spectC->periodicInZ) return fail(PDO_E_BADARG, "fourierColl needs a spectral type initialised with init_periodicInZ");
+        if (spectC->si.zsz[0] != sp_zsz[0] || spectC->si.zsz[1] != sp_zsz[1] || spectC->si.zsz[2] != sp_zsz[2])
+            return fail(PDO_E_BADARG, "spectral type and sp_gpC disagree on the z-pencil");
+    }
     pdo_pade6stagg_s* p = new (std::nothrow) pdo_pade6stagg_s();
     if (!p) return fail(PDO_E_BADARG, "out of memory");
     std::memcpy(p->gp_zsz, gp_zsz, sizeof(int) * 3);
     std::memcpy(p->sp_zsz, sp_zsz, sizeof(int) * 3);
     p->dz = dz; p->scheme = scheme;
-    int rc = pdo_cd06stagg_init_periodic(&p->der, gp_zsz[2], dz);  // derPeriodic%init(gp%zsz(3), dz)  :79-80
-    if (rc) { delete p; return rc; }
+    if (scheme == PDO_SCHEME_CD06) {
+        int rc = pdo_cd06stagg_init_periodic(&p->der, gp_zsz[2], dz);  // derPeriodic%init(gp%zsz(3), dz)  :79-80
+        if (rc) { delete p; return rc; }
+    } else {
+        // spectral.F90:849-856: k3 = GetWaveNums(nz, dz); tables as complex numbers
+        p->spectC = spectC;
+        const int nz = sp_zsz[2];
+        std::vector<double> k3 = wavenums(nz, dz);
+        std::vector<double2> t(5 * (size_t)nz);
+        for (int k = 0; k < nz; ++k) {
+            const double kk = k3[k], ph = kk * dz / 2.0, c = std::cos(ph), sn = std::sin(ph);
+            t[k] = make_double2(-kk * sn, kk * c);                  // i k e^{+i k dz/2}
+            t[(size_t)nz + k] = make_double2(kk * sn, kk * c);      // i k e^{-i k dz/2}
+            t[2 * (size_t)nz + k] = make_double2(c, sn);            // e^{+i k dz/2}
+            t[3 * (size_t)nz + k] = make_double2(c, -sn);           // e^{-i k dz/2}
+            t[4 * (size_t)nz + k] = make_double2(-(kk * kk), 0.0);  // -k^2
+        }
+        double2* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, sizeof(double2) * t.size());
+        if (e == cudaSuccess) e = cudaMemcpy(d, t.data(), sizeof(double2) * t.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { if (d) cudaFree(d); delete p; return fail(PDO_E_CUDA, "pade6stagg init: %s", cudaGetErrorString(e)); }
+        for (int i = 0; i < 5; ++i) p->ftab[i] = d + (size_t)i * nz;
+    }
     *h = p;
     return 0;
+}
+int pdo_pade6stagg_init(pdo_pade6stagg_t* h, const int gp_zsz[3], const int sp_zsz[3], double dz, int scheme, int is_periodic) {
+    return pdo_pade6stagg_init2(h, gp_zsz, sp_zsz, dz, scheme, is_periodic, nullptr);
 }
 int pdo_pade6stagg_destroy(pdo_pade6stagg_t p) {
     if (!p) return 0;
     pdo_cd06stagg_destroy(p->der);
+    if (p->ftab[0]) cudaFree(p->ftab[0]);
     delete p;
     return 0;
 }
-#define PDO_PADE_FN(name, target)                                                                                          \
+#define PDO_PADE_FN(name, target, which)                                                                                   \
     int name(pdo_pade6stagg_t p, const double* in, double* out, int is_complex, int bot, int top, void* st) {              \
         (void)bot; (void)top;                                                                                              \
-        return pade_apply(p, target, in, out, is_complex, st);                                                             \
+        return pade_apply(p, target, which, in, out, is_complex, st);                                                      \
     }
-PDO_PADE_FN(pdo_pade6stagg_ddz_C2E, pdo_cd06stagg_ddz_C2E)
-PDO_PADE_FN(pdo_pade6stagg_ddz_E2C, pdo_cd06stagg_ddz_E2C)
-PDO_PADE_FN(pdo_pade6stagg_interpz_C2E, pdo_cd06stagg_interpz_C2E)
-PDO_PADE_FN(pdo_pade6stagg_interpz_E2C, pdo_cd06stagg_interpz_E2C)
-PDO_PADE_FN(pdo_pade6stagg_d2dz2_C2C, pdo_cd06stagg_d2dz2_C2C)
-PDO_PADE_FN(pdo_pade6stagg_d2dz2_E2E, pdo_cd06stagg_d2dz2_E2E)
+PDO_PADE_FN(pdo_pade6stagg_ddz_C2E, pdo_cd06stagg_ddz_C2E, 1)
+PDO_PADE_FN(pdo_pade6stagg_ddz_E2C, pdo_cd06stagg_ddz_E2C, 0)
+PDO_PADE_FN(pdo_pade6stagg_interpz_C2E, pdo_cd06stagg_interpz_C2E, 3)
+PDO_PADE_FN(pdo_pade6stagg_interpz_E2C, pdo_cd06stagg_interpz_E2C, 2)
+PDO_PADE_FN(pdo_pade6stagg_d2dz2_C2C, pdo_cd06stagg_d2dz2_C2C, 4)
+PDO_PADE_FN(pdo_pade6stagg_d2dz2_E2E, pdo_cd06stagg_d2dz2_E2E, 5)
 
 // getmodCD06stagg (PadeDerOps.F90:1034-1053)
 int pdo_pade6stagg_get_modified_wavenumbers(pdo_pade6stagg_t p, const double* k, double* kp, int n) {
     if (!p || !k || !kp) return fail(PDO_E_BADARG, "null argument");
+    if (p->scheme == PDO_SCHEME_FOURIER) {   // PadeDerOps.F90:1003-1004
+        for (int i = 0; i < n; ++i) kp[i] = k[i];
+        return 0;
+    }
     const double alpha = 9.0 / 62.0, beta = 0.0, a = 63.0 / 62.0, b = 17.0 / 62.0, c = 0.0;
     for (int i = 0; i < n; ++i) {
         const double omega = k[i] * p->dz;
@@ -1129,7 +1202,8 @@ int pdo_igrid_init(pdo_igrid_t* h, const pdo_igrid_params* p, const double* u, c
     if (!rc) rc = pdo_spectral_init(&g->spE, p->nx, p->ny, p->nz + 1, g->dx, g->dy, g->dz, p->p_row, p->p_col, 0, 0, g->prm.dealias_fact);
     if (!rc) {
         g->gC = g->spC->pi; g->gE = g->spE->pi; g->sC = g->spC->si; g->sE = g->spE->si;
-        rc = pdo_pade6stagg_init(&g->ops, g->gC.zsz, g->sC.zsz, g->dz, PDO_SCHEME_CD06, 1);
+        rc = pdo_pade6stagg_init2(&g->ops, g->gC.zsz, g->sC.zsz, g->dz, p->fourier_collocation_z ? PDO_SCHEME_FOURIER : PDO_SCHEME_CD06, 1,
+                                  g->spC);   // igrid.F90:500
     }
     if (!rc) rc = pdo_padepoisson_init(&g->poiss, g->dx, g->dy, g->dz, g->spC, g->spE, g->ops);
     if (rc) { pdo_igrid_destroy(g); return rc; }

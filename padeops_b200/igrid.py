@@ -110,7 +110,10 @@ class Pade6stagg:
         g = gpC["zsz"] if isinstance(gpC, dict) else gpC.zsz
         s = sp_gpC["zsz"] if isinstance(sp_gpC, dict) else sp_gpC.zsz
         self.gp_zsz, self.sp_zsz = tuple(g), tuple(s)
-        check(lib().pdo_pade6stagg_init(C.byref(self._h), (C.c_int * 3)(*g), (C.c_int * 3)(*s), float(dz), int(scheme), int(bool(isPeriodic))))
+        # spectC is the spectral type whose z transforms scheme = fourierColl uses (PadeDerOps.F90:73-78; code 43 without it)
+        self._spectC = spectC
+        check(lib().pdo_pade6stagg_init2(C.byref(self._h), (C.c_int * 3)(*g), (C.c_int * 3)(*s), float(dz), int(scheme), int(bool(isPeriodic)),
+                                         spectC._h if spectC is not None else C.c_void_p(None)))
         return 0
 
     def destroy(self):
@@ -191,14 +194,17 @@ class igrid:
         self._h = C.c_void_p(None)
 
     def init(self, nx, ny, nz, Lx, Ly, Lz, Re, u, v, w, isInviscid=False, dealiasFact=2.0 / 3.0, t_DivergenceCheck=10,
-             TimeSteppingScheme=1, prow=0, pcol=0, use_d2dz2_C2C=True, computeAllGradients=False, AdvectionTerm=1):
-        """AdvectionTerm: 1 skew-symmetric (igrid.F90:1572-1679), 0 rotational u x omega (:1527-1555), as in the namelist."""
+             TimeSteppingScheme=1, prow=0, pcol=0, use_d2dz2_C2C=True, computeAllGradients=False, AdvectionTerm=1, NumericalSchemeVert=1):
+        """AdvectionTerm: 1 skew-symmetric (igrid.F90:1572-1679), 0 rotational u x omega (:1527-1555); NumericalSchemeVert: 1 cd06
+        staggered compact operators, 2 Fourier collocation in z (PadeDerOps.F90:16-18) — as in the namelist."""
         if AdvectionTerm not in (0, 1):
             raise ValueError("AdvectionTerm must be 0 (rotational) or 1 (skew-symmetric)")
+        if NumericalSchemeVert not in (1, 2):
+            raise ValueError("NumericalSchemeVert must be 1 (cd06) or 2 (fourierColl); fd02 is not built")
         decomp_2d.comm_init()
         p = IgridParams(int(nx), int(ny), int(nz), float(Lx), float(Ly), float(Lz), float(Re), int(bool(isInviscid)), float(dealiasFact),
                         int(t_DivergenceCheck), int(TimeSteppingScheme), int(prow), int(pcol), int(bool(use_d2dz2_C2C)),
-                        int(bool(computeAllGradients)), int(AdvectionTerm == 0))
+                        int(bool(computeAllGradients)), int(AdvectionTerm == 0), int(NumericalSchemeVert == 2))
         check(lib().pdo_igrid_init(C.byref(self._h), C.byref(p), ptr(u), ptr(v), ptr(w)))
         self.gpC = _info(lib().pdo_igrid_get_decomp_info, self._h, 0)
         self.gpE = _info(lib().pdo_igrid_get_decomp_info, self._h, 1)

@@ -212,3 +212,52 @@ def test_igrid_substep_rotational_form_matches_oracle(pdo, IG, scheme):
             r = getattr(ref, nm)
             assert np.abs(g.get(nm) - r).max() < TOL * np.abs(r).max(), (it, nm)
     assert g.maxDivergence() < 1e-11 * max(np.abs(ref.u).max(), np.abs(ref.w).max())
+
+
+_LATE = "added after the round's last GPU session: first hardware run happens in the driver's round-end test pass " \
+        "(the CPU oracle side is pinned in test_oracle_igrid.py)"
+
+
+@pytest.mark.xfail(strict=False, reason=_LATE)
+def test_pade6stagg_fourier_collocation_matches_oracle(pdo, IG):
+    """scheme = fourierColl (PadeDerOps.F90:57-78, spectral.F90:387-680, 843-856): the six z-operators on complex arrays."""
+    nx, ny, nz = 16, 12, 16
+    d = [2 * np.pi / n for n in (nx, ny, nz)]
+    spC = pdo.spectral()
+    spC.init("x", nx, ny, nz, *d, fixOddball=False, init_periodicInZ=True)
+    der = pdo.Pade6stagg()
+    der.init(spC.physdecomp, spC.spectdecomp, dz=d[2], scheme=2, isPeriodic=True, spectC=spC)
+    rops = IG.Pade6stagg(nz, d[2], scheme=2)
+    nxh = nx // 2 + 1
+    fC, fE = _cplx((nz, ny, nxh), 4), _cplx((nz + 1, ny, nxh), 5)
+    fE[nz] = fE[0]
+    for name in ("ddz_E2C", "interpz_E2C", "d2dz2_E2E"):
+        assert _rel(getattr(der, name)(_dev(fE)).cpu().numpy(), getattr(rops, name)(fE)) < TOL, name
+    for name in ("ddz_C2E", "interpz_C2E", "d2dz2_C2C"):
+        assert _rel(getattr(der, name)(_dev(fC)).cpu().numpy(), getattr(rops, name)(fC)) < TOL, name
+    k = np.linspace(-3.0, 3.0, 7)
+    assert np.array_equal(der.getModifiedWavenumbers(k), k)
+    with pytest.raises(pdo.PadeOpsError) as e:
+        pdo.Pade6stagg().init(spC.physdecomp, spC.spectdecomp, dz=d[2], scheme=2, isPeriodic=True)    # no spectC
+    assert e.value.code == 43
+
+
+@pytest.mark.xfail(strict=False, reason=_LATE)
+@pytest.mark.parametrize("adv", [0, 1])
+def test_igrid_substep_fourier_z_matches_oracle(pdo, IG, adv):
+    """NumericalSchemeVert = 2 with either advection form (rotational + Fourier-z is the authors' HIT deck's choice)."""
+    nx, ny, nz = 24, 16, 32
+    L = (2 * np.pi, 2 * np.pi, 2 * np.pi)
+    u, v = broadband((nz, ny, nx), 1), broadband((nz, ny, nx), 2)
+    w = broadband((nz + 1, ny, nx), 3)
+    w[nz] = w[0]
+    ref = IG.IGrid(nx, ny, nz, *L, 50.0, u, v, w, TimeSteppingScheme=2, AdvectionTerm=adv, NumericalSchemeVert=2)
+    g = pdo.igrid()
+    g.init(nx, ny, nz, *L, 50.0, u, v, w, TimeSteppingScheme=2, AdvectionTerm=adv, NumericalSchemeVert=2)
+    for it in range(2):
+        ref.timeAdvance(0.01)
+        g.timeAdvance(0.01)
+        for nm in ("u", "v", "w", "uhat", "vhat", "what"):
+            r = getattr(ref, nm)
+            assert np.abs(g.get(nm) - r).max() < TOL * np.abs(r).max(), (it, nm)
+    assert g.maxDivergence() < 1e-11 * max(np.abs(ref.u).max(), np.abs(ref.w).max())
