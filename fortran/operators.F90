@@ -1,4 +1,4 @@
-! Drop-in for utilities/operators.F90:17-151 (gradient, curl, divergence of y-pencil fields), periodic.
+! Drop-in for utilities/operators.F90:17-224 (gradient, curl, divergence, filter3D of y-pencil fields).
 ! Same subroutine names and argument lists; `der` is accepted for source compatibility and the work is done by
 ! pdo_operators_* of libpadeops_b200.so, which differentiates along z
 ! WITHOUT transposing when the z-slabs allow it (distributed compact solve over NVLink; include/padeops_b200.h).
@@ -9,10 +9,11 @@ module operators
     use kind_parameters, only: rkind
     use decomp_2d, only: decomp_info
     use DerivativesMod, only: derivatives
+    use FiltersMod, only: filters          ! the shim's filters type carries the library handle as fil%h (pattern of cd10.F90)
     use exits, only: GracefulExit
     implicit none
     private
-    public :: gradient, curl, divergence, operators_configure
+    public :: gradient, curl, divergence, filter3D, operators_configure
     type(c_ptr), save :: hops = c_null_ptr, hops_decomp = c_null_ptr
     real(rkind), save :: cfg_dx = 0, cfg_dy = 0, cfg_dz = 0
     character(len=4), save :: cfg_method = "cd10"
@@ -74,6 +75,23 @@ contains
         call ensure_handle(decomp)
         ierr = pdo_operators_divergence(hops, c_loc(u), c_loc(v), c_loc(w), c_loc(div), c_null_ptr)
         if (ierr /= 0) call GracefulExit("padeops_b200: divergence failed", ierr)
+    end subroutine
+
+    subroutine filter3D(decomp, fil, arr, numtimes, x_bc_, y_bc_, z_bc_)                ! operators.F90:158
+        type(decomp_info), intent(in) :: decomp
+        type(filters),     intent(in) :: fil
+        real(rkind), dimension(decomp%ysz(1), decomp%ysz(2), decomp%ysz(3)), intent(inout), target :: arr
+        integer, optional, intent(in) :: numtimes
+        integer, dimension(2), optional, intent(in) :: x_bc_, y_bc_, z_bc_
+        integer(c_int), dimension(2) :: x_bc, y_bc, z_bc
+        integer(c_int) :: ierr, times2fil
+        times2fil = 1; if (present(numtimes)) times2fil = numtimes
+        x_bc = 0; if (present(x_bc_)) x_bc = x_bc_
+        y_bc = 0; if (present(y_bc_)) y_bc = y_bc_
+        z_bc = 0; if (present(z_bc_)) z_bc = z_bc_
+        call ensure_handle(decomp)
+        ierr = pdo_operators_filter3d(hops, fil%h, c_loc(arr), times2fil, x_bc, y_bc, z_bc, c_null_ptr)
+        if (ierr /= 0) call GracefulExit("padeops_b200: filter3D failed", ierr)
     end subroutine
 
 end module

@@ -259,5 +259,12 @@ module padeops_b200_c
             type(c_ptr), value :: h, u, v, w, div, stream
             integer(c_int) :: ierr
         end function
+        function pdo_operators_filter3d(h, fil, arr, numtimes, x_bc, y_bc, z_bc, stream) bind(C, name="pdo_operators_filter3d") result(ierr)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h, fil, arr, stream
+            integer(c_int), value :: numtimes
+            integer(c_int), dimension(2), intent(in) :: x_bc, y_bc, z_bc
+            integer(c_int) :: ierr
+        end function
     end interface
 end module padeops_b200_c

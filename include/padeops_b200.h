@@ -189,6 +189,12 @@ int pdo_operators_ddz(pdo_operators_t h, const double* f, double* dfdz, void* st
 int pdo_operators_gradient(pdo_operators_t h, const double* f, double* dfdx, double* dfdy, double* dfdz, void* stream);      /* :17-53 */
 int pdo_operators_curl(pdo_operators_t h, const double* u, const double* v, const double* w, double* curlu, void* stream);   /* :55-116 */
 int pdo_operators_divergence(pdo_operators_t h, const double* u, const double* v, const double* w, double* div, void* stream); /* :118-151 */
+/* filter3D(decomp, fil, arr, numtimes, x_bc_, y_bc_, z_bc_)                                            operators.F90:158-224
+   `numtimes` passes of fil%filtery, then (through y->x / x->y) of fil%filterx, then (through y->z / z->y) of fil%filterz, in
+   place on the y-pencil field `arr` (device pointer).  `fil` must have been built from the same decomposition (else code 234).
+   x_bc / y_bc / z_bc: int[2] boundary codes handed to the filters, or NULL for (0, 0). */
+int pdo_operators_filter3d(pdo_operators_t h, pdo_filters_t fil, double* arr, int numtimes, const int* x_bc, const int* y_bc,
+                           const int* z_bc, void* stream);
 
 /* ---- fft_3d_stuff::fft_3d, "x" base pencil  (utilities/fft_3d.F90) ---------------------------- */
 typedef struct pdo_fft3d_s* pdo_fft3d_t;

@@ -273,6 +273,21 @@ def curl(u, v, w, dx, dy, dz, method="cd10"):
     return np.stack([c1, c2, c3])
 
 
+def filter3D(f, numtimes=1, methods=("cf90", "cf90", "cf90"), periodic=(True, True, True), x_bc=(0, 0), y_bc=(0, 0), z_bc=(0, 0)):
+    """operators.F90:158-224: numtimes passes of fil%filtery, then of fil%filterx, then of fil%filterz (this order; the
+    transposes between the stages are pure permutations).  f: global array (nz, ny, nx); returns the filtered copy."""
+    def one(a, axis, bc):
+        if methods[axis].startswith("gaussian"):
+            assert periodic[axis], "gaussian non-periodic closures are not restated"
+            return gaussian(a, axis)
+        return cf90(a, axis) if periodic[axis] else cf90_np(a, axis, bc[0], bc[1])
+    out = np.ascontiguousarray(f, dtype=np.float64)
+    for axis, bc in ((1, y_bc), (0, x_bc), (2, z_bc)):
+        for _ in range(max(int(numtimes), 1)):
+            out = one(out, axis, bc)
+    return out
+
+
 # ---- non-periodic CD10 closures (cd10.F90:29-96, 429-707, 823-851, 1143-1262, 1636-1731); SURVEY.md 8f rank 2 groundwork ----
 def cd10_np(f, dx, axis, which=1, bc1=0, bcn=0):
     """cd10%dd* (which=1) / d2d* (which=2) with periodic=.false. and boundary codes bc1, bcn in {0, 1, -1}."""

@@ -158,6 +158,7 @@ _PROTOS.update({
     "pdo_operators_gradient": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
     "pdo_operators_curl": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
     "pdo_operators_divergence": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, C.c_void_p]),
+    "pdo_operators_filter3d": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
 })
 _PROTOS["pdo_debug_zslab_emulate"] = (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, C.c_longlong, C.c_int, C.c_int, C.c_void_p])
 _PROTOS["pdo_debug_cd10_generic"] = (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.c_int, C.c_void_p])

@@ -550,13 +550,6 @@ PDO_STAGG_FN(pdo_cd06stagg_d2dz2_E2E, 5)
 }  // extern "C"
 
 // ---------------- DerivativesMod::derivatives / FiltersMod::filters ----------------
-struct pdo_filters_s {
-    int xsz[3], ysz[3], zsz[3];
-    int method[3];  // 0 cf90, 1 gaussian
-    pdo_cf90_t cf[3];
-    pdo_gaussian_t ga[3];
-};
-
 extern "C" {
 
 int pdo_derivatives_init(pdo_derivatives_t* h, const int xsz[3], const int ysz[3], const int zsz[3], double dx, double dy,

@@ -11,6 +11,7 @@
 // decomp.cu's transposes.  Results of the two paths agree to rounding (same per-chunk arithmetic, same tables).
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "banded.cuh"
@@ -134,7 +135,9 @@ struct pdo_operators_s {
     pdo_cd10_t c10[3] = {nullptr, nullptr, nullptr};
     pdo_cd06_t c06[3] = {nullptr, nullptr, nullptr};
     ZSlab zs;
-    double *xtmp = nullptr, *xdum = nullptr, *ztmp = nullptr, *zdum = nullptr, *ytmp = nullptr;  // lazily allocated work pencils
+    double *xtmp = nullptr, *xdum = nullptr, *ztmp = nullptr, *zdum = nullptr, *ytmp = nullptr, *ytmp2 = nullptr;  // lazily allocated work pencils
+    void* hbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // device copies of HOST arguments (grow-only)
+    size_t hcap[6] = {0, 0, 0, 0, 0, 0};
     cudaStream_t side = nullptr;             // z-slab exchange runs here while the caller's stream differentiates along x / y
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     const BandedOp* op(int axis) const { return method == 0 ? &c10[axis]->d1 : &c06[axis]->d1; }
@@ -215,6 +218,35 @@ int ops_add(double* a, const double* b, long long n, double sign, cudaStream_t s
     return 0;
 }
 
+// Arguments that arrive as HOST arrays (the unmodified Fortran caller) are staged through per-handle device
+// buffers: inputs copied in before `body`, outputs copied back after it, then one stream synchronise.  Device (or managed)
+// pointers pass straight through, stream-ordered, nothing synchronises.
+struct OpsArg { const void* ptr; size_t bytes; bool out; bool inout; void* dev; };
+template <class Body>
+int with_ops_args(pdo_operators_s* o, OpsArg* a, int na, cudaStream_t st, Body body) {
+    bool any_host = false;
+    for (int i = 0; i < na; ++i) {
+        if (!a[i].ptr) return fail(PDO_E_BADARG, "null argument");
+        if (is_device_ptr(a[i].ptr)) { a[i].dev = const_cast<void*>(a[i].ptr); continue; }
+        any_host = true;
+        if (o->hcap[i] < a[i].bytes) {
+            if (o->hbuf[i]) cudaFree(o->hbuf[i]);
+            o->hbuf[i] = nullptr; o->hcap[i] = 0;
+            PDO_CUDA(cudaMalloc(&o->hbuf[i], a[i].bytes));
+            o->hcap[i] = a[i].bytes;
+        }
+        a[i].dev = o->hbuf[i];
+        if (!a[i].out || a[i].inout) PDO_CUDA(cudaMemcpyAsync(a[i].dev, a[i].ptr, a[i].bytes, cudaMemcpyHostToDevice, st));
+    }
+    if (int rc = body()) return rc;
+    if (!any_host) return 0;
+    for (int i = 0; i < na; ++i)
+        if (a[i].out && a[i].dev != a[i].ptr) PDO_CUDA(cudaMemcpyAsync(const_cast<void*>(a[i].ptr), a[i].dev, a[i].bytes, cudaMemcpyDeviceToHost, st));
+    PDO_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+#define OPS_D(i) ((double*)a[i].dev)
+
 }  // namespace
 
 extern "C" {
@@ -273,7 +305,8 @@ int pdo_operators_destroy(pdo_operators_t o) {
     for (int a = 0; a < 3; ++a) { pdo_cd10_destroy(o->c10[a]); pdo_cd06_destroy(o->c06[a]); }
     if (o->zs.base) { cudaDeviceSynchronize(); comm_sym_free(o->zs.base); }
     if (o->side) { cudaStreamDestroy(o->side); cudaEventDestroy(o->ev_fork); cudaEventDestroy(o->ev_join); }
-    for (double* p : {o->xtmp, o->xdum, o->ztmp, o->zdum, o->ytmp}) if (p) cudaFree(p);
+    for (double* p : {o->xtmp, o->xdum, o->ztmp, o->zdum, o->ytmp, o->ytmp2}) if (p) cudaFree(p);
+    for (void* p : o->hbuf) if (p) cudaFree(p);
     delete o;
     return 0;
 }
@@ -281,18 +314,29 @@ int pdo_operators_destroy(pdo_operators_t o) {
 /* 0: z is local on this grid, 1: z-slab distributed solve, 2: transposes */
 int pdo_operators_zmode(pdo_operators_t o) { return !o ? -1 : (o->p_col == 1 ? 0 : (o->zs.on ? 1 : 2)); }
 
-int pdo_operators_ddx(pdo_operators_t o, const double* f, double* out, void* st) { return o ? ops_dd(o, 0, f, out, (cudaStream_t)st) : fail(PDO_E_BADARG, "null handle"); }
-int pdo_operators_ddy(pdo_operators_t o, const double* f, double* out, void* st) { return o ? ops_dd(o, 1, f, out, (cudaStream_t)st) : fail(PDO_E_BADARG, "null handle"); }
-int pdo_operators_ddz(pdo_operators_t o, const double* f, double* out, void* st) { return o ? ops_dd(o, 2, f, out, (cudaStream_t)st) : fail(PDO_E_BADARG, "null handle"); }
+static int ops_dd_entry(pdo_operators_t o, int axis, const double* f, double* out, void* stream) {
+    if (!o) return fail(PDO_E_BADARG, "null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t b = sizeof(double) * (size_t)vol3(o->info.ysz);
+    OpsArg a[2] = {{f, b, false, false, nullptr}, {out, b, true, false, nullptr}};
+    return with_ops_args(o, a, 2, st, [&]() { return ops_dd(o, axis, OPS_D(0), OPS_D(1), st); });
+}
+int pdo_operators_ddx(pdo_operators_t o, const double* f, double* out, void* st) { return ops_dd_entry(o, 0, f, out, st); }
+int pdo_operators_ddy(pdo_operators_t o, const double* f, double* out, void* st) { return ops_dd_entry(o, 1, f, out, st); }
+int pdo_operators_ddz(pdo_operators_t o, const double* f, double* out, void* st) { return ops_dd_entry(o, 2, f, out, st); }
 
 /* operators.F90:17-53 */
 int pdo_operators_gradient(pdo_operators_t o, const double* f, double* dfdx, double* dfdy, double* dfdz, void* stream) {
     if (!o) return fail(PDO_E_BADARG, "null handle");
     cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = ops_zbegin(o, f, st)) return rc;          // the z exchange overlaps the y and x derivatives
-    if (int rc = ops_dd(o, 1, f, dfdy, st)) return rc;
-    if (int rc = ops_dd(o, 0, f, dfdx, st)) return rc;
-    return ops_zend(o, f, dfdz, st);
+    const size_t b = sizeof(double) * (size_t)vol3(o->info.ysz);
+    OpsArg a[4] = {{f, b, false, false, nullptr}, {dfdx, b, true, false, nullptr}, {dfdy, b, true, false, nullptr}, {dfdz, b, true, false, nullptr}};
+    return with_ops_args(o, a, 4, st, [&]() -> int {
+        if (int rc = ops_zbegin(o, OPS_D(0), st)) return rc;          // the z exchange overlaps the y and x derivatives
+        if (int rc = ops_dd(o, 1, OPS_D(0), OPS_D(2), st)) return rc;
+        if (int rc = ops_dd(o, 0, OPS_D(0), OPS_D(1), st)) return rc;
+        return ops_zend(o, OPS_D(0), OPS_D(3), st);
+    });
 }
 
 /* operators.F90:118-151: div = dv/dy, += du/dx, += dw/dz (same order of additions) */
@@ -300,19 +344,23 @@ int pdo_operators_divergence(pdo_operators_t o, const double* u, const double* v
     if (!o) return fail(PDO_E_BADARG, "null handle");
     cudaStream_t st = (cudaStream_t)stream;
     const long long n = vol3(o->info.ysz);
-    if (int rc = ensure(&o->ytmp, n)) return rc;
-    if (int rc = ops_zbegin(o, w, st)) return rc;
-    if (int rc = ops_dd(o, 1, v, div, st)) return rc;
-    if (int rc = ops_dd(o, 0, u, o->ytmp, st)) return rc;
-    if (int rc = ops_add(div, o->ytmp, n, 1.0, st)) return rc;
-    if (int rc = ops_zend(o, w, o->ytmp, st)) return rc;
-    return ops_add(div, o->ytmp, n, 1.0, st);
+    const size_t b = sizeof(double) * (size_t)n;
+    OpsArg a[4] = {{u, b, false, false, nullptr}, {v, b, false, false, nullptr}, {w, b, false, false, nullptr}, {div, b, true, false, nullptr}};
+    return with_ops_args(o, a, 4, st, [&]() -> int {
+        const double *du = OPS_D(0), *dv = OPS_D(1), *dw = OPS_D(2);
+        double* dd = OPS_D(3);
+        if (int rc = ensure(&o->ytmp, n)) return rc;
+        if (int rc = ops_zbegin(o, dw, st)) return rc;
+        if (int rc = ops_dd(o, 1, dv, dd, st)) return rc;
+        if (int rc = ops_dd(o, 0, du, o->ytmp, st)) return rc;
+        if (int rc = ops_add(dd, o->ytmp, n, 1.0, st)) return rc;
+        if (int rc = ops_zend(o, dw, o->ytmp, st)) return rc;
+        return ops_add(dd, o->ytmp, n, 1.0, st);
+    });
 }
 
 /* operators.F90:55-116: curl(:,:,:,c) stored as three consecutive y-pencils */
-int pdo_operators_curl(pdo_operators_t o, const double* u, const double* v, const double* w, double* curl, void* stream) {
-    if (!o) return fail(PDO_E_BADARG, "null handle");
-    cudaStream_t st = (cudaStream_t)stream;
+static int curl_dev(pdo_operators_s* o, const double* u, const double* v, const double* w, double* curl, cudaStream_t st) {
     const long long n = vol3(o->info.ysz);
     if (int rc = ensure(&o->ytmp, n)) return rc;
     double *c1 = curl, *c2 = curl + n, *c3 = curl + 2 * n;
@@ -326,6 +374,71 @@ int pdo_operators_curl(pdo_operators_t o, const double* u, const double* v, cons
     if (int rc = ops_dd(o, 0, v, c3, st)) return rc;             // dv/dx
     if (int rc = ops_dd(o, 1, u, o->ytmp, st)) return rc;        // du/dy
     return ops_add(c3, o->ytmp, n, -1.0, st);
+}
+int pdo_operators_curl(pdo_operators_t o, const double* u, const double* v, const double* w, double* curl, void* stream) {
+    if (!o) return fail(PDO_E_BADARG, "null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t b = sizeof(double) * (size_t)vol3(o->info.ysz);
+    OpsArg a[4] = {{u, b, false, false, nullptr}, {v, b, false, false, nullptr}, {w, b, false, false, nullptr}, {curl, 3 * b, true, false, nullptr}};
+    return with_ops_args(o, a, 4, st, [&]() { return curl_dev(o, OPS_D(0), OPS_D(1), OPS_D(2), OPS_D(3), st); });
+}
+
+/* operators.F90:158-224 filter3D: `numtimes` passes of the y filter, then of the x filter, then of the z filter, on a y-pencil
+ * field, in place.  The reference copies the result back into the source before each re-filter and transposes around the x
+ * and z stages; here the passes ping-pong between two work pencils (same values, no copies), the last pass of the last stage
+ * writes `arr`, and a stage whose axis is already resident in the y-pencil (p_row == 1 / p_col == 1) runs without transposes.
+ * bc pairs may be null (periodic / 0, 0). */
+static int filter3d_dev(pdo_operators_s* o, pdo_filters_t fil, double* arr, int numtimes, const int* x_bc, const int* y_bc,
+                        const int* z_bc, cudaStream_t st) {
+    for (int i = 0; i < 3; ++i)
+        if (fil->xsz[i] != o->info.xsz[i] || fil->ysz[i] != o->info.ysz[i] || fil->zsz[i] != o->info.zsz[i])
+            return fail(234, "filter3D: the filters object was built for another decomposition");   // operators.F90:171-174
+    if (numtimes < 1) numtimes = 1;   // "do idx = 1, times2fil-1" runs zero times: one pass is always made
+    static const int zero[2] = {0, 0};
+    const int* bc[3] = {x_bc ? x_bc : zero, y_bc ? y_bc : zero, z_bc ? z_bc : zero};
+    const long long n = vol3(o->info.ysz);
+    if (int rc = ensure(&o->ytmp, n)) return rc;
+    if (int rc = ensure(&o->ytmp2, n)) return rc;
+    typedef int (*fil_fn)(pdo_filters_t, const double*, double*, int, int, void*);
+    static const fil_fn fns[3] = {pdo_filters_filterx, pdo_filters_filtery, pdo_filters_filterz};
+    const double* src = arr;
+    auto pick = [&](bool last) -> double* { return last ? arr : (src == o->ytmp ? o->ytmp2 : o->ytmp); };
+    static const int order[3] = {1, 0, 2};
+    for (int s = 0; s < 3; ++s) {
+        const int axis = order[s];
+        const bool resident = axis == 1 || (axis == 0 && o->p_row == 1) || (axis == 2 && o->p_col == 1);
+        if (resident) {
+            // x on a p_row = 1 grid: the y-pencil IS the x-pencil, the filters object holds the same sizes for both
+            for (int t = 0; t < numtimes; ++t) {
+                double* dst = pick(s == 2 && t == numtimes - 1);
+                if (int rc = fns[axis](fil, src, dst, bc[axis][0], bc[axis][1], st)) return rc;
+                src = dst;
+            }
+            continue;
+        }
+        const int* ps = axis == 0 ? o->info.xsz : o->info.zsz;
+        double** pa = axis == 0 ? &o->xtmp : &o->ztmp;
+        double** pb = axis == 0 ? &o->xdum : &o->zdum;
+        if (int rc = ensure(pa, vol3(ps))) return rc;
+        if (int rc = ensure(pb, vol3(ps))) return rc;
+        double *a = *pa, *b = *pb;
+        if (int rc = decomp_transpose_device(o->gp, axis == 0 ? 1 : 2, src, a, 1, st)) return rc;
+        for (int t = 0; t < numtimes; ++t) {
+            if (int rc = fns[axis](fil, a, b, bc[axis][0], bc[axis][1], st)) return rc;
+            std::swap(a, b);
+        }
+        double* dst = pick(s == 2);
+        if (int rc = decomp_transpose_device(o->gp, axis == 0 ? 0 : 3, a, dst, 1, st)) return rc;
+        src = dst;
+    }
+    return 0;
+}
+int pdo_operators_filter3d(pdo_operators_t o, pdo_filters_t fil, double* arr, int numtimes, const int* x_bc, const int* y_bc,
+                           const int* z_bc, void* stream) {
+    if (!o || !fil || !arr) return fail(PDO_E_BADARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    OpsArg a[1] = {{arr, sizeof(double) * (size_t)vol3(o->info.ysz), true, true, nullptr}};
+    return with_ops_args(o, a, 1, st, [&]() { return filter3d_dev(o, fil, OPS_D(0), numtimes, x_bc, y_bc, z_bc, st); });
 }
 
 /* Test hook: the z-slab algorithm on ONE GPU.  f(n1, n) holds whole lines; it is cut into `nslabs` slabs that exchange

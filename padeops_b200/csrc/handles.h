@@ -15,3 +15,9 @@ struct pdo_derivatives_s {
     pdo_cd10_t c10[3];
     pdo_cd06_t c06[3];
 };
+struct pdo_filters_s {
+    int xsz[3], ysz[3], zsz[3];
+    int method[3];  // 0 cf90, 1 gaussian
+    pdo_cf90_t cf[3];
+    pdo_gaussian_t ga[3];
+};

@@ -1,4 +1,4 @@
-"""Mirror of utilities/operators.F90 (gradient :17-53, curl :55-116, divergence :118-151) on the C ABI.
+"""Mirror of utilities/operators.F90 (gradient :17-53, curl :55-116, divergence :118-151, filter3D :158-224) on the C ABI.
 
 Every field is a y-pencil array of `gp` (shape (ysz[2], ysz[1], ysz[0]) in torch's row-major view of the Fortran
 layout), device-resident.  `vector_ops.init` is collective.  Along z the library distributes the compact solve across
@@ -73,3 +73,13 @@ class vector_ops:
         assert tuple(curlu.shape) == (3,) + self._shape() and curlu.is_contiguous()
         check(lib().pdo_operators_curl(self._h, ptr(u), ptr(v), ptr(w), ptr(curlu), stream_ptr(stream)))
         return curlu
+
+    def filter3D(self, fil, arr, numtimes=1, x_bc=None, y_bc=None, z_bc=None, stream=None):
+        """filter3D(decomp, fil, arr, numtimes, x_bc_, y_bc_, z_bc_) (operators.F90:158-224): numtimes passes of the y, then x,
+        then z filter of `fil` (a `filters` object built on the same gp), in place on the y-pencil field `arr`."""
+        self._chk(arr)
+
+        def bc(p):
+            return None if p is None else (C.c_int * 2)(int(p[0]), int(p[1]))
+        check(lib().pdo_operators_filter3d(self._h, fil._h, ptr(arr), int(numtimes), bc(x_bc), bc(y_bc), bc(z_bc), stream_ptr(stream)))
+        return arr

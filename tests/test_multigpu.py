@@ -18,3 +18,16 @@ def test_transposes_fft_poisson_multi_gpu(world):
            "--master-port", str(29510 + world), os.path.join(ROOT, "tests", "mp_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert "MP_WORKER_RESULT PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.xfail(strict=False, reason="worker sections written after the round's last multi-GPU session (Poisson dir_id 3, filter3D, igrid "
+                                        "rotational / Fourier-z on decomposed fields): first hardware run is the driver's")
+@pytest.mark.parametrize("world", [2, 4])
+def test_late_sections_multi_gpu(world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29530 + world), os.path.join(ROOT, "tests", "mp_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, PDO_MP_LATE="1"))
+    assert "MP_WORKER_LATE PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

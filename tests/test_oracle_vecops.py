@@ -62,3 +62,56 @@ def test_curl_of_rotations_like_test_operators(oracle):
         for k in range(3):
             want = exact + zero if k == axis else zero
             assert np.abs(c[k] - want).max() < 1e-9, (axis, k)
+
+
+def _T_cf90(w):
+    co = (9.9965e-1, 6.6652e-1, 1.6674e-1, 4.0e-5, -5.0e-6)
+    return (co[0] + 2 * co[1] * np.cos(w) + 2 * co[2] * np.cos(2 * w) + 2 * co[3] * np.cos(3 * w) + 2 * co[4] * np.cos(4 * w)) / \
+        (1 + 2 * 6.6624e-1 * np.cos(w) + 2 * 1.6688e-1 * np.cos(2 * w))
+
+
+def _T_gauss(w):
+    g = (3565 / 10368, 3091 / 12960, 1997 / 25920, 149 / 12960, 107 / 103680)
+    return g[0] + 2 * g[1] * np.cos(w) + 2 * g[2] * np.cos(2 * w) + 2 * g[3] * np.cos(3 * w) + 2 * g[4] * np.cos(4 * w)
+
+
+@pytest.mark.parametrize("numtimes", [1, 3])
+@pytest.mark.parametrize("methods", [("cf90", "cf90", "cf90"), ("gaussian", "cf90", "gaussian")])
+def test_filter3d_single_mode_transfer(oracle, numtimes, methods):
+    """filter3D (operators.F90:158-224) of one Fourier mode = product over the axes of (1-D transfer function)^numtimes — the
+    3-D version of tests/test_cf90.F90:108-116 / tests/test_filters_parallel.F90:9-26."""
+    nx, ny, nz = 32, 24, 40
+    kx, ky, kz = 5, 3, 9
+    x, y, z = (np.arange(n) * 2 * np.pi / n for n in (nx, ny, nz))
+    f = np.cos(kx * x[None, None, :] + 0.3) * np.sin(ky * y[None, :, None] - 0.2) * np.cos(kz * z[:, None, None] + 1.1)
+    T = 1.0
+    for m, k, n in zip(methods, (kx, ky, kz), (nx, ny, nz)):
+        T *= (_T_gauss if m == "gaussian" else _T_cf90)(2 * np.pi * k / n) ** numtimes
+    out = oracle.filter3D(f, numtimes, methods)
+    assert np.abs(out - T * f).max() < 2e-12
+    assert 0.0 < T < 1.0
+
+
+def test_filter3d_order_and_refilter(oracle):
+    """numtimes = 2 equals two numtimes = 1 applications axis by axis (y twice, then x twice, then z twice), and constants pass."""
+    rng = np.random.default_rng(11)
+    f = rng.standard_normal((16, 20, 24))
+    ref = f
+    for axis in (1, 0, 2):
+        for _ in range(2):
+            ref = oracle.cf90(ref, axis)
+    assert np.array_equal(oracle.filter3D(f, 2), ref)
+    c = np.full((12, 16, 20), 2.5)
+    assert np.abs(oracle.filter3D(c, 3) - 2.5).max() < 1e-11   # T(0) = 1 up to the rounding the nine pentadiagonal solves amplify
+    assert np.array_equal(oracle.filter3D(f, 0), oracle.filter3D(f, 1))   # "do idx = 1, times2fil - 1": at least one pass
+
+
+def test_filter3d_nonperiodic_z(oracle):
+    """z_bc reaches the z filter only: symmetric walls (1, 1) in z reproduce the periodic filter on the even extension."""
+    rng = np.random.default_rng(5)
+    nz, ny, nx = 24, 16, 16
+    f = rng.standard_normal((nz, ny, nx))
+    out = oracle.filter3D(f, 1, periodic=(True, True, False), z_bc=(1, 1))
+    ext = np.concatenate([f, f[-2:0:-1]], axis=0)    # even extension about both end points: 2 nz - 2 periodic points
+    ref = oracle.filter3D(ext, 1)[:nz]
+    assert np.abs(out - ref).max() < 1e-12
