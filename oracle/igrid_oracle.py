@@ -110,6 +110,28 @@ class Spectral:
         out[nz] = out[0]
         return out
 
+    # ---- z-Fourier operators on whole arrays (spectral.F90:409-437, 507-547) ----
+    def _real_z(self, a, table):
+        """The REAL procedures: r2c along z, modes 0 .. nz/2-1 times the table, the oddball (Nyquist) mode left as it came
+        out of the transform ("Note that the oddball is ignored"), c2r, x normfactz."""
+        nz = self.nz
+        c = np.fft.rfft(np.asarray(a, dtype=np.float64)[:nz], axis=0)
+        c[: nz // 2] = c[: nz // 2] * table[: nz // 2, None, None]
+        return np.fft.irfft(c, n=nz, axis=0)        # numpy's irfft = FFTW c2r x 1/nz; both drop Im of the Nyquist coefficient
+
+    def ddz_C2C_real_inplace(self, a):
+        return self._real_z(a, self.k3_C2Cder)
+
+    def ddz_C2C_complex_inplace(self, a):
+        return self.normfactz * (np.fft.ifft(np.fft.fft(a, axis=0) * self.k3_C2Cder[:, None, None], axis=0) * self.nz)
+
+    def shiftz_E2C(self, ahat_z):
+        """in place on an array that is ALREADY Fourier-transformed in z (spectral.F90:409-422)"""
+        return ahat_z * self.E2Cshift[:, None, None]
+
+    def shiftz_C2E(self, ahat_z):
+        return ahat_z * self.C2Eshift[:, None, None]
+
     def take_fft1d_z2z(self, a):
         return np.fft.fft(a, axis=0)
 
@@ -130,7 +152,8 @@ class Pade6stagg:
     """PadeDerOps::Pade6stagg, isPeriodic = .true. (BC integers are ignored on this branch).  scheme = 1: cd06 (the compact
     staggered operators); scheme = 2: fourierColl — every operator is `c2c-z forward, x table(k3), c2c-z backward, x 1/nz`
     with the tables of spectral.F90:843-856 (k3 = GetWaveNums(nz, dz), shifts e^{+-i k3 dz/2} between cells and edges), the
-    complex procedures of spectral.F90:387-407, 462-482, 528-568, 596-680; edge outputs copy plane 1 into plane nz+1."""
+    complex procedures of spectral.F90:387-407, 462-482, 528-568, 596-680 and their real twins (r2c / c2r, oddball mode untouched);
+    edge outputs copy plane 1 into plane nz+1."""
 
     def __init__(self, nz, dz, scheme=1):
         assert scheme in (1, 2)
@@ -145,7 +168,14 @@ class Pade6stagg:
 
     def _spect(self, f, table, edge_out):
         nz = self.nz
-        out = np.fft.ifft(np.fft.fft(np.asarray(f)[:nz], axis=0) * table[:, None, None], axis=0)   # backward x normfactz = numpy's ifft
+        if not np.iscomplexobj(f):
+            # the REAL procedures (spectral.F90:365-385, 439-459, 484-505, 572-593, 639-658, 682-702): r2c, modes 0 .. nz/2-1
+            # times the table, the oddball mode passes through untouched, c2r, x 1/nz
+            c = np.fft.rfft(np.asarray(f, dtype=np.float64)[:nz], axis=0)
+            c[: nz // 2] = c[: nz // 2] * table[: nz // 2, None, None]
+            out = np.fft.irfft(c, n=nz, axis=0)
+        else:
+            out = np.fft.ifft(np.fft.fft(np.asarray(f)[:nz], axis=0) * table[:, None, None], axis=0)   # backward x normfactz = numpy's ifft
         if edge_out:
             out = np.concatenate([out, out[:1]], axis=0)
         return out
