@@ -246,6 +246,13 @@ int pdo_spectral_dealias(pdo_spectral_t h, double* fhat_cplx_y, void* stream);  
 int pdo_spectral_dealias_edgefield(pdo_spectral_t h, double* fhatE_cplx_z, void* stream);
 int pdo_spectral_take_fft1d_z2z_ip(pdo_spectral_t h, double* a_cplx_z, void* stream);               /* :1483-1487 */
 int pdo_spectral_take_ifft1d_z2z_ip(pdo_spectral_t h, double* a_cplx_z, void* stream);              /* :1489-1494 */
+/* z-Fourier operators of the periodic-in-z type.  Complex arrays: z-pencil of the spectral decomposition; the real one: z-pencil
+   of the physical decomposition, transformed r2c / c2r in the reference with "the oddball ignored": modes 0 .. nz/2-1 are
+   multiplied, the Nyquist mode goes back as it came (here: pairs of real columns through one c2c, same result). */
+int pdo_spectral_ddz_c2c_real_ip(pdo_spectral_t h, double* a_real_z, void* stream);                 /* :507-526 */
+int pdo_spectral_ddz_c2c_complex_ip(pdo_spectral_t h, double* a_cplx_z, void* stream);              /* :528-547 */
+int pdo_spectral_shiftz_e2c(pdo_spectral_t h, double* ahat_cplx_z, void* stream);                   /* :409-422, array already z-transformed */
+int pdo_spectral_shiftz_c2e(pdo_spectral_t h, double* ahat_cplx_z, void* stream);                   /* :424-437 */
 /* the 1-D tables behind k1 / k2 / kabs_sq / Gdealias: full global length (nx/2+1, ny, nz); NULL entries are skipped */
 int pdo_spectral_get_tables(pdo_spectral_t h, double* k1, double* k2, double* gdealias_x, double* gdealias_y, double* gdealias_z);
 
@@ -323,6 +330,22 @@ int pdo_igrid_get_state(pdo_igrid_t h, int* step, double* tsim);
 /* compute_deltaT with useCFL (igrid.F90:1372-1396) */
 int pdo_igrid_compute_delta_t(pdo_igrid_t h, double cfl, double* dt, void* stream);
 int pdo_igrid_max_divergence(pdo_igrid_t h, double* max_div, void* stream);   /* printDivergence + p_maxval(|div|) */
+
+/* ---- igrid_Operators_Periodic::Ops_Periodic  (incompressible/igrid_operators_periodic.F90:13-161) ----------------
+   Fourier operators on x-pencil fields of a triply periodic box (the reference's post-processing programs use it):
+   its own spectral type (pencil "x", 2-D transforms, init_periodicInZ, 2/3 dealiasing, fixOddball = .false.) and a
+   PoissonPeriodic with spectral wavenumbers.  Real arguments are x-pencil arrays of the physical decomposition, the complex
+   one a y-pencil array of the spectral decomposition; host or device pointers.  gp enters as its process grid. */
+typedef struct pdo_ops_periodic_s* pdo_ops_periodic_t;
+int pdo_ops_periodic_init(pdo_ops_periodic_t* h, int nx, int ny, int nz, double dx, double dy, double dz, int p_row, int p_col);  /* :86-109 */
+int pdo_ops_periodic_destroy(pdo_ops_periodic_t h);
+pdo_spectral_t pdo_ops_periodic_spect(pdo_ops_periodic_t h);                                          /* link_spect :46-52 */
+int pdo_ops_periodic_ddx(pdo_ops_periodic_t h, const double* f, double* dfdx, void* stream);          /* :117-125 */
+int pdo_ops_periodic_ddy(pdo_ops_periodic_t h, const double* f, double* dfdy, void* stream);          /* :127-135 */
+int pdo_ops_periodic_ddz(pdo_ops_periodic_t h, const double* f, double* dfdz, void* stream);          /* :149-160 */
+int pdo_ops_periodic_ddz_cmplx2cmplx(pdo_ops_periodic_t h, double* fhat_cplx_y, void* stream);        /* :137-145 */
+int pdo_ops_periodic_solve_poisson(pdo_ops_periodic_t h, const double* rhs, double* p, void* stream); /* _oop :70-76; p == rhs: _ip :78-84 */
+int pdo_ops_periodic_dealias_field(pdo_ops_periodic_t h, double* f, void* stream);                    /* :56-62 */
 
 #ifdef __cplusplus
 }

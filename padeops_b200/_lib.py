@@ -126,6 +126,20 @@ _PROTOS.update({
     "pdo_spectral_dealias_edgefield": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "pdo_spectral_take_fft1d_z2z_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "pdo_spectral_take_ifft1d_z2z_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
+    "pdo_debug_ztables": (C.c_int, [C.c_int, C.c_double, c_dp]),
+    "pdo_spectral_ddz_c2c_real_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
+    "pdo_spectral_ddz_c2c_complex_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
+    "pdo_spectral_shiftz_e2c": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
+    "pdo_spectral_shiftz_c2e": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
+    "pdo_ops_periodic_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]),
+    "pdo_ops_periodic_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_ops_periodic_spect": (C.c_void_p, [C.c_void_p]),
+    "pdo_ops_periodic_ddx": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
+    "pdo_ops_periodic_ddy": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
+    "pdo_ops_periodic_ddz": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
+    "pdo_ops_periodic_ddz_cmplx2cmplx": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
+    "pdo_ops_periodic_solve_poisson": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
+    "pdo_ops_periodic_dealias_field": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "pdo_spectral_get_tables": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "pdo_pade6stagg_init": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_double, C.c_int, C.c_int]),
     "pdo_pade6stagg_init2": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_double, C.c_int, C.c_int, C.c_void_p]),

@@ -99,7 +99,15 @@ struct pdo_spectral_s {
     double *gx = nullptr, *gy = nullptr, *gyz = nullptr, *gz = nullptr;  // dealias masks: x slice, y full, y slice of the z-pencil, z
     double2* ctmpz = nullptr;
     double* partial = nullptr;  // reduction scratch
+    // z-Fourier tables of init_periodic_inZ_procedures (spectral.F90:843-856), built on first use: 6 tables of nz complex numbers
+    // (k3_E2Cshift, k3_C2Eshift, E2Cshift, C2Eshift, mk3sq, k3_C2Cder), then the same six with the oddball entry set to 1 for the
+    // REAL procedures, which leave that mode untouched
+    double2* ztab = nullptr;
+    ZColsPlan rz_plan;          // c2c-z over pairs of real columns
+    double2* rz_work = nullptr;
+    size_t rz_cap = 0;
 };
+enum { ZT_K3_E2C = 0, ZT_K3_C2E = 1, ZT_E2C = 2, ZT_C2E = 3, ZT_MK3SQ = 4, ZT_K3_C2C = 5, ZT_COUNT = 6 };
 
 namespace {
 
@@ -119,6 +127,78 @@ int spectral_mtimes(pdo_spectral_s* s, int which, const double2* fin, double2* f
         const double2 v = fin[i];
         fout[i] = make_double2(-kv * v.y, kv * v.x);
     });
+}
+
+// ---- z-Fourier operators: c2c-z forward, x table(k), c2c-z backward, x 1/nz (spectral.F90:365-702) ----
+// host side of the tables: [2][ZT_COUNT][nz], complex procedures first, then the REAL procedures' twins (oddball entry = 1)
+std::vector<double2> build_ztables_host(int nz, double dz) {
+    std::vector<double> k3 = wavenums(nz, dz);   // GetWaveNums(nz, dz), no sign flip of the oddball (spectral.F90:845)
+    std::vector<double2> t(2 * ZT_COUNT * (size_t)nz);
+    for (int k = 0; k < nz; ++k) {
+        const double kk = k3[k], ph = kk * dz / 2.0, c = std::cos(ph), sn = std::sin(ph);
+        t[(size_t)ZT_K3_E2C * nz + k] = make_double2(-kk * sn, kk * c);    // i k e^{+i k dz/2}
+        t[(size_t)ZT_K3_C2E * nz + k] = make_double2(kk * sn, kk * c);     // i k e^{-i k dz/2}
+        t[(size_t)ZT_E2C * nz + k] = make_double2(c, sn);                  // e^{+i k dz/2}
+        t[(size_t)ZT_C2E * nz + k] = make_double2(c, -sn);                 // e^{-i k dz/2}
+        t[(size_t)ZT_MK3SQ * nz + k] = make_double2(-(kk * kk), 0.0);      // -k^2
+        t[(size_t)ZT_K3_C2C * nz + k] = make_double2(0.0, kk);             // i k
+    }
+    for (int i = 0; i < ZT_COUNT; ++i)
+        for (int k = 0; k < nz; ++k)
+            t[(size_t)(ZT_COUNT + i) * nz + k] = k == nz / 2 ? make_double2(1.0, 0.0) : t[(size_t)i * nz + k];
+    return t;
+}
+int spectral_ztables(pdo_spectral_s* s) {
+    if (s->ztab) return 0;
+    if (!s->periodicInZ) return fail(PDO_E_BADARG, "spectral type was not initialised with init_periodicInZ");
+    std::vector<double2> t = build_ztables_host(s->nz, s->dz);
+    PDO_CUDA(cudaMalloc(&s->ztab, sizeof(double2) * t.size()));
+    PDO_CUDA(cudaMemcpy(s->ztab, t.data(), sizeof(double2) * t.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+inline const double2* ztable(const pdo_spectral_s* s, int which, bool real_variant) {
+    return s->ztab + (size_t)((real_variant ? ZT_COUNT : 0) + which) * s->nz;
+}
+// w(cols, nz) *= tab(k) * scale
+int ztable_multiply(double2* w, long long cols, int nz, const double2* tab, double scale, cudaStream_t st) {
+    return launch_ew(cols * nz, st, [=] __device__(long long i) {
+        double2 t = tab[(int)(i / cols)];
+        const double2 v = w[i];
+        t.x *= scale; t.y *= scale;
+        w[i] = make_double2(v.x * t.x - v.y * t.y, v.x * t.y + v.y * t.x);
+    });
+}
+// complex z-pencil array of the spectral decomposition, in place on the first nz planes of w
+int zfourier_complex(pdo_spectral_s* s, double2* w, int which, cudaStream_t st) {
+    if (int rc = spectral_ztables(s)) return rc;
+    const long long cols = (long long)s->si.zsz[0] * s->si.zsz[1];
+    if (int rc = fft3d_z_inplace(s->ft, w, -1, st)) return rc;
+    if (int rc = ztable_multiply(w, cols, s->nz, ztable(s, which, false), 1.0 / (double)s->nz, st)) return rc;
+    return fft3d_z_inplace(s->ft, w, +1, st);
+}
+// REAL z-pencil array of the physical decomposition: in(P, nz [+1]) -> out(P, nz).  The table with the oddball entry = 1 is
+// conjugate-symmetric in k, so the operator maps real columns to real columns and is linear over C: two real columns a, b
+// are transformed as ONE complex column a + i b and come back as a' + i b' (half the transform work of a zero-padded c2c,
+// the same arithmetic as the reference's r2c / c2r pair up to rounding).  P odd: the last column is paired with zeros.
+int zfourier_real(pdo_spectral_s* s, const double* in, double* out, int which, cudaStream_t st) {
+    if (int rc = spectral_ztables(s)) return rc;
+    const int nz = s->nz;
+    const long long P = (long long)s->pi.zsz[0] * s->pi.zsz[1], Pc = (P + 1) / 2;
+    const size_t need = sizeof(double2) * (size_t)Pc * nz;
+    if (s->rz_cap < need) {
+        if (s->rz_work) cudaFree(s->rz_work);
+        s->rz_work = nullptr; s->rz_cap = 0;
+        PDO_CUDA(cudaMalloc(&s->rz_work, need));
+        s->rz_cap = need;
+    }
+    double2* w = s->rz_work;
+    if (P & 1) PDO_CUDA(cudaMemsetAsync(w, 0, need, st));
+    PDO_CUDA(cudaMemcpy2DAsync(w, sizeof(double2) * Pc, in, sizeof(double) * P, sizeof(double) * P, nz, cudaMemcpyDeviceToDevice, st));
+    if (int rc = zcols_exec(&s->rz_plan, nz, Pc, w, -1, st)) return rc;
+    if (int rc = ztable_multiply(w, Pc, nz, ztable(s, which, true), 1.0 / (double)nz, st)) return rc;
+    if (int rc = zcols_exec(&s->rz_plan, nz, Pc, w, +1, st)) return rc;
+    PDO_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * P, w, sizeof(double2) * Pc, sizeof(double) * P, nz, cudaMemcpyDeviceToDevice, st));
+    return 0;
 }
 
 // z-pencil array a(zsz0, zsz1, nz) *= gx(i) gy(j) gz(k) * scale
@@ -239,6 +319,9 @@ int pdo_spectral_destroy(pdo_spectral_t s) {
     double* ptrs[] = {s->k1y, s->k2, s->gx, s->gy, s->gyz, s->gz, s->partial};
     for (double* p : ptrs) if (p) cudaFree(p);
     if (s->ctmpz) { comm_deregister_buffer(s->ctmpz); cudaFree(s->ctmpz); }
+    if (s->ztab) cudaFree(s->ztab);
+    if (s->rz_work) cudaFree(s->rz_work);
+    zcols_destroy(&s->rz_plan);
     pdo_fft3d_destroy(s->ft);
     delete s;
     return 0;
@@ -309,6 +392,42 @@ int pdo_spectral_dealias_edgefield(pdo_spectral_t s, double* fE, void* st) { ret
 int pdo_spectral_take_fft1d_z2z_ip(pdo_spectral_t s, double* a, void* st) { return spectral_zwise(s, a, st, 1); }
 int pdo_spectral_take_ifft1d_z2z_ip(pdo_spectral_t s, double* a, void* st) { return spectral_zwise(s, a, st, 2); }
 
+// ddz_C2C_complex_inplace (:528-547), shiftz_E2C / shiftz_C2E (:409-437): complex z-pencil arrays of the spectral decomposition
+static int spectral_zcomplex(pdo_spectral_t s, double* a, void* stream, int op) {
+    if (!s || !a) return fail(PDO_E_BADARG, "null argument");
+    if (!s->periodicInZ) return fail(PDO_E_BADARG, "spectral type was not initialised with init_periodicInZ");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long cols = (long long)s->si.zsz[0] * s->si.zsz[1];
+    const size_t bytes = sizeof(double2) * (size_t)cols * (size_t)s->nz;
+    return with_device_views(a, bytes, a, bytes, st, [&](const void* di, void* d_o) -> int {
+        if (di != d_o) PDO_CUDA(cudaMemcpyAsync(d_o, di, bytes, cudaMemcpyDeviceToDevice, st));
+        double2* w = (double2*)d_o;
+        if (op == 0) return zfourier_complex(s, w, ZT_K3_C2C, st);
+        if (int rc = spectral_ztables(s)) return rc;
+        return ztable_multiply(w, cols, s->nz, ztable(s, op == 1 ? ZT_E2C : ZT_C2E, false), 1.0, st);
+    });
+}
+// test hook (host only, not in the public header): the z-Fourier tables as the kernels get them, out[2][6][nz] complex
+int pdo_debug_ztables(int nz, double dz, double* out) {
+    if (nz < 2 || (nz & 1) || !out) return fail(PDO_E_BADARG, "bad argument");
+    std::vector<double2> t = build_ztables_host(nz, dz);
+    std::memcpy(out, t.data(), sizeof(double2) * t.size());
+    return 0;
+}
+int pdo_spectral_ddz_c2c_complex_ip(pdo_spectral_t s, double* a, void* st) { return spectral_zcomplex(s, a, st, 0); }
+int pdo_spectral_shiftz_e2c(pdo_spectral_t s, double* a, void* st) { return spectral_zcomplex(s, a, st, 1); }
+int pdo_spectral_shiftz_c2e(pdo_spectral_t s, double* a, void* st) { return spectral_zcomplex(s, a, st, 2); }
+// ddz_C2C_real_inplace (:507-526): real z-pencil array of the physical decomposition; the oddball mode passes through
+int pdo_spectral_ddz_c2c_real_ip(pdo_spectral_t s, double* a, void* stream) {
+    if (!s || !a) return fail(PDO_E_BADARG, "null argument");
+    if (!s->periodicInZ) return fail(PDO_E_BADARG, "spectral type was not initialised with init_periodicInZ");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t bytes = sizeof(double) * (size_t)vol(s->pi.zsz);
+    return with_device_views(a, bytes, a, bytes, st, [&](const void* di, void* d_o) -> int {
+        return zfourier_real(s, (const double*)di, (double*)d_o, ZT_K3_C2C, st);
+    });
+}
+
 }  // extern "C"
 
 // ================================================================================================
@@ -319,43 +438,35 @@ struct pdo_pade6stagg_s {
     double dz;
     int scheme;
     pdo_cd06stagg_t der = nullptr;
-    // scheme = fourierColl: the spectral type whose z transforms are used (borrowed) and the tables of spectral.F90:843-856
-    pdo_spectral_t spectC = nullptr;
-    double2* ftab[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // k3_E2Cshift, k3_C2Eshift, E2Cshift, C2Eshift, mk3sq
+    pdo_spectral_t spectC = nullptr;   // scheme = fourierColl: the spectral type whose z transforms and tables are used (borrowed)
 };
 
 namespace {
 typedef int (*stagg_fn)(pdo_cd06stagg_t, const double*, double*, int, int, int, void*);
 
-// Fourier collocation in z (spectral.F90:387-407, 462-482, 549-568, 596-680, the complex procedures): c2c-z forward on the first
-// nz planes, multiply plane k by table(k), c2c-z backward, x 1/nz; edge outputs get plane nz+1 := plane 1.
+// Fourier collocation in z (spectral.F90:365-702): c2c-z forward on the first nz planes, multiply plane k by table(k), c2c-z
+// backward, x 1/nz; edge outputs get plane nz+1 := plane 1.  Complex arrays live on the spectral z-pencil, real ones on the
+// physical z-pencil (r2c / c2r in the reference, oddball mode untouched: zfourier_real).
 // which: 0 ddz_E2C, 1 ddz_C2E, 2 interp_E2C, 3 interp_C2E, 4 d2dz2_C2C, 5 d2dz2_E2E
 int pade_fourier(pdo_pade6stagg_s* p, int which, const double* in, double* out, int is_complex, void* stream) {
-    if (!is_complex)
-        return fail(PDO_E_UNSUPPORTED, "Pade6stagg fourierColl: only the complex (spectral-array) procedures are built; the real ones drop the oddball mode");
     cudaStream_t st = (cudaStream_t)stream;
-    const int nz = p->sp_zsz[2];
-    const size_t plane = (size_t)p->sp_zsz[0] * p->sp_zsz[1];
-    const bool edge_in = (which == 0 || which == 2 || which == 5), edge_out = (which == 1 || which == 3 || which == 5);
-    const size_t bin = sizeof(double2) * plane * (size_t)(nz + (edge_in ? 1 : 0)), bout = sizeof(double2) * plane * (size_t)(nz + (edge_out ? 1 : 0));
-    static const int tab_of[6] = {0, 1, 2, 3, 4, 4};
-    const double2* tab = p->ftab[tab_of[which]];
-    const double nf = 1.0 / (double)nz;
     pdo_spectral_s* s = p->spectC;
+    const int nz = s->nz;
+    const int* zs = is_complex ? s->si.zsz : s->pi.zsz;
+    const size_t esz = is_complex ? sizeof(double2) : sizeof(double);
+    const size_t plane = (size_t)zs[0] * zs[1];
+    const bool edge_in = (which == 0 || which == 2 || which == 5), edge_out = (which == 1 || which == 3 || which == 5);
+    const size_t bin = esz * plane * (size_t)(nz + (edge_in ? 1 : 0)), bout = esz * plane * (size_t)(nz + (edge_out ? 1 : 0));
+    static const int tab_of[6] = {ZT_K3_E2C, ZT_K3_C2E, ZT_E2C, ZT_C2E, ZT_MK3SQ, ZT_MK3SQ};
     return with_device_views(in, bin, out, bout, st, [&](const void* di, void* d_o) -> int {
-        double2* w = (double2*)d_o;
-        if (di != d_o) PDO_CUDA(cudaMemcpyAsync(w, di, sizeof(double2) * plane * (size_t)nz, cudaMemcpyDeviceToDevice, st));
-        if (int rc = fft3d_z_inplace(s->ft, w, -1, st)) return rc;
-        const long long pl = (long long)plane;
-        // one pass between the transforms: table(k) and the 1/nz of the backward transform together
-        if (int rc = launch_ew(pl * nz, st, [=] __device__(long long i) {
-                double2 t = tab[(int)(i / pl)];
-                const double2 v = w[i];
-                t.x *= nf; t.y *= nf;
-                w[i] = make_double2(v.x * t.x - v.y * t.y, v.x * t.y + v.y * t.x);
-            })) return rc;
-        if (int rc = fft3d_z_inplace(s->ft, w, +1, st)) return rc;
-        if (edge_out) PDO_CUDA(cudaMemcpyAsync(w + plane * (size_t)nz, w, sizeof(double2) * plane, cudaMemcpyDeviceToDevice, st));
+        if (is_complex) {
+            double2* w = (double2*)d_o;
+            if (di != d_o) PDO_CUDA(cudaMemcpyAsync(w, di, esz * plane * (size_t)nz, cudaMemcpyDeviceToDevice, st));
+            if (int rc = zfourier_complex(s, w, tab_of[which], st)) return rc;
+        } else {
+            if (int rc = zfourier_real(s, (const double*)di, (double*)d_o, tab_of[which], st)) return rc;
+        }
+        if (edge_out) PDO_CUDA(cudaMemcpyAsync((char*)d_o + esz * plane * (size_t)nz, d_o, esz * plane, cudaMemcpyDeviceToDevice, st));
         return 0;
     });
 }
@@ -382,6 +493,8 @@ int pdo_pade6stagg_init2(pdo_pade6stagg_t* h, const int gp_zsz[3], const int sp_
         if (!spectC->periodicInZ) return fail(PDO_E_BADARG, "fourierColl needs a spectral type initialised with init_periodicInZ");
         if (spectC->si.zsz[0] != sp_zsz[0] || spectC->si.zsz[1] != sp_zsz[1] || spectC->si.zsz[2] != sp_zsz[2])
             return fail(PDO_E_BADARG, "spectral type and sp_gpC disagree on the z-pencil");
+        if (spectC->pi.zsz[0] != gp_zsz[0] || spectC->pi.zsz[1] != gp_zsz[1] || spectC->pi.zsz[2] != gp_zsz[2])
+            return fail(PDO_E_BADARG, "spectral type and gpC disagree on the z-pencil");
     }
     pdo_pade6stagg_s* p = new (std::nothrow) pdo_pade6stagg_s();
     if (!p) return fail(PDO_E_BADARG, "out of memory");
@@ -392,24 +505,8 @@ int pdo_pade6stagg_init2(pdo_pade6stagg_t* h, const int gp_zsz[3], const int sp_
         int rc = pdo_cd06stagg_init_periodic(&p->der, gp_zsz[2], dz);  // derPeriodic%init(gp%zsz(3), dz)  :79-80
         if (rc) { delete p; return rc; }
     } else {
-        // spectral.F90:849-856: k3 = GetWaveNums(nz, dz); tables as complex numbers
-        p->spectC = spectC;
-        const int nz = sp_zsz[2];
-        std::vector<double> k3 = wavenums(nz, dz);
-        std::vector<double2> t(5 * (size_t)nz);
-        for (int k = 0; k < nz; ++k) {
-            const double kk = k3[k], ph = kk * dz / 2.0, c = std::cos(ph), sn = std::sin(ph);
-            t[k] = make_double2(-kk * sn, kk * c);                  // i k e^{+i k dz/2}
-            t[(size_t)nz + k] = make_double2(kk * sn, kk * c);      // i k e^{-i k dz/2}
-            t[2 * (size_t)nz + k] = make_double2(c, sn);            // e^{+i k dz/2}
-            t[3 * (size_t)nz + k] = make_double2(c, -sn);           // e^{-i k dz/2}
-            t[4 * (size_t)nz + k] = make_double2(-(kk * kk), 0.0);  // -k^2
-        }
-        double2* d = nullptr;
-        cudaError_t e = cudaMalloc(&d, sizeof(double2) * t.size());
-        if (e == cudaSuccess) e = cudaMemcpy(d, t.data(), sizeof(double2) * t.size(), cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) { if (d) cudaFree(d); delete p; return fail(PDO_E_CUDA, "pade6stagg init: %s", cudaGetErrorString(e)); }
-        for (int i = 0; i < 5; ++i) p->ftab[i] = d + (size_t)i * nz;
+        p->spectC = spectC;   // the tables are the spectral type's own (spectral.F90:843-856), built on first use
+        if (int rc = spectral_ztables(spectC)) { delete p; return rc; }
     }
     *h = p;
     return 0;
@@ -420,7 +517,6 @@ int pdo_pade6stagg_init(pdo_pade6stagg_t* h, const int gp_zsz[3], const int sp_z
 int pdo_pade6stagg_destroy(pdo_pade6stagg_t p) {
     if (!p) return 0;
     pdo_cd06stagg_destroy(p->der);
-    if (p->ftab[0]) cudaFree(p->ftab[0]);
     delete p;
     return 0;
 }
@@ -1327,6 +1423,117 @@ int pdo_igrid_max_divergence(pdo_igrid_t g, double* max_div, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     IG(poiss_divergence(g->poiss, g->cur[0], g->cur[1], g->cur[2], g->divergence, st));
     return global_max(g->spC, g->divergence, g->nRC, 1, max_div, st);
+}
+
+}  // extern "C"
+
+
+// ================================================================================================
+// igrid_Operators_Periodic::Ops_Periodic (igrid_operators_periodic.F90:13-161): Fourier operators on x-pencil fields of a
+// triply periodic box — compositions of the spectral type's transforms, its pointwise passes and PoissonPeriodic
+// ================================================================================================
+struct pdo_ops_periodic_s {
+    pdo_spectral_t spect = nullptr;
+    pdo_poisson_t poiss = nullptr;
+    double2* cbuffy1 = nullptr;                     // spectral y-pencil
+    double *rbuffy = nullptr, *rbuffz1 = nullptr;   // physical y- / z-pencils (allocated only where they differ from the x- / y-pencil)
+};
+
+extern "C" {
+
+/* init(nx, ny, nz, dx, dy, dz, gp, InputDir, OutputDir) :86-109; gp enters as its process grid (0, 0 = 1 x nproc) */
+int pdo_ops_periodic_init(pdo_ops_periodic_t* h, int nx, int ny, int nz, double dx, double dy, double dz, int p_row, int p_col) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    *h = nullptr;
+    pdo_ops_periodic_s* o = new (std::nothrow) pdo_ops_periodic_s();
+    if (!o) return fail(PDO_E_BADARG, "out of memory");
+    // spect%init("x", nx, ny, nz, dx, dy, dz, "four", "2/3rd", 2, fixOddball=.false., init_periodicInZ=.TRUE., dealiasF=2/3)  :94-95
+    int rc = pdo_spectral_init(&o->spect, nx, ny, nz, dx, dy, dz, p_row, p_col, 0, 1, 2.0 / 3.0);
+    // poiss%init(dx, dy, dz, gp, 1, .true., GetKmod_Fourier x 3): the spectral wavenumbers themselves  :107-108
+    if (!rc) rc = pdo_poisson_init(&o->poiss, nx, ny, nz, dx, dy, dz, o->spect->p_row, o->spect->p_col, 1, nullptr, nullptr, nullptr);
+    if (!rc) {
+        pdo_spectral_s* s = o->spect;
+        cudaError_t e = cudaMalloc(&o->cbuffy1, sizeof(double2) * (size_t)vol(s->si.ysz));
+        if (e == cudaSuccess && s->p_row > 1) e = cudaMalloc(&o->rbuffy, sizeof(double) * (size_t)vol(s->pi.ysz));
+        if (e == cudaSuccess && s->p_col > 1) e = cudaMalloc(&o->rbuffz1, sizeof(double) * (size_t)vol(s->pi.zsz));
+        if (e != cudaSuccess) rc = fail(PDO_E_CUDA, "Ops_Periodic buffers: %s", cudaGetErrorString(e));
+    }
+    if (rc) { pdo_ops_periodic_destroy(o); return rc; }
+    *h = o;
+    return 0;
+}
+int pdo_ops_periodic_destroy(pdo_ops_periodic_t o) {
+    if (!o) return 0;
+    if (o->cbuffy1) cudaFree(o->cbuffy1);
+    if (o->rbuffy) cudaFree(o->rbuffy);
+    if (o->rbuffz1) cudaFree(o->rbuffz1);
+    pdo_poisson_destroy(o->poiss);
+    pdo_spectral_destroy(o->spect);
+    delete o;
+    return 0;
+}
+/* link_spect :46-52 */
+pdo_spectral_t pdo_ops_periodic_spect(pdo_ops_periodic_t o) { return o ? o->spect : nullptr; }
+
+// ddx :117-125, ddy :127-135 (which = 1, 2), dealiasField :56-62 (which = 0): fft, one pointwise pass, ifft
+static int ops_periodic_xy(pdo_ops_periodic_t o, int which, const double* f, double* out, void* stream) {
+    if (!o || !f || !out) return fail(PDO_E_BADARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    pdo_spectral_s* s = o->spect;
+    const size_t bytes = sizeof(double) * (size_t)vol(s->pi.xsz);
+    return with_device_views(f, bytes, out, bytes, st, [&](const void* di, void* d_o) -> int {
+        if (int rc = fft3d_forward_xy(s->ft, (const double*)di, o->cbuffy1, st)) return rc;
+        if (which == 0) { if (int rc = spectral_dealias(s, o->cbuffy1, st)) return rc; }
+        else if (int rc = spectral_mtimes(s, which, o->cbuffy1, o->cbuffy1, st)) return rc;
+        return fft3d_backward_yx(s->ft, o->cbuffy1, (double*)d_o, false, st);
+    });
+}
+int pdo_ops_periodic_ddx(pdo_ops_periodic_t o, const double* f, double* dfdx, void* st) { return ops_periodic_xy(o, 1, f, dfdx, st); }
+int pdo_ops_periodic_ddy(pdo_ops_periodic_t o, const double* f, double* dfdy, void* st) { return ops_periodic_xy(o, 2, f, dfdy, st); }
+int pdo_ops_periodic_dealias_field(pdo_ops_periodic_t o, double* f, void* st) { return ops_periodic_xy(o, 0, f, f, st); }
+
+/* ddz :149-160: x -> y -> z, spect%ddz_C2C_real_inplace, z -> y -> x (a transpose inside a 1-rank group is the identity and is skipped) */
+int pdo_ops_periodic_ddz(pdo_ops_periodic_t o, const double* f, double* dfdz, void* stream) {
+    if (!o || !f || !dfdz) return fail(PDO_E_BADARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    pdo_spectral_s* s = o->spect;
+    pdo_decomp_t gp = fft3d_phys_decomp(s->ft);
+    const size_t bytes = sizeof(double) * (size_t)vol(s->pi.xsz);
+    return with_device_views(f, bytes, dfdz, bytes, st, [&](const void* di, void* d_o) -> int {
+        const double* a = (const double*)di;
+        double* out = (double*)d_o;
+        const bool tx = s->p_row > 1, tz = s->p_col > 1;
+        double* ydst = tx ? o->rbuffy : out;          // where the y-pencil result lives
+        if (tx) { if (int rc = decomp_transpose_device(gp, 0, a, o->rbuffy, 1, st)) return rc; a = o->rbuffy; }
+        if (tz) {
+            if (int rc = decomp_transpose_device(gp, 2, a, o->rbuffz1, 1, st)) return rc;
+            if (int rc = zfourier_real(s, o->rbuffz1, o->rbuffz1, ZT_K3_C2C, st)) return rc;
+            if (int rc = decomp_transpose_device(gp, 3, o->rbuffz1, ydst, 1, st)) return rc;
+        } else if (int rc = zfourier_real(s, a, ydst, ZT_K3_C2C, st)) return rc;
+        if (tx) return decomp_transpose_device(gp, 1, o->rbuffy, out, 1, st);
+        return 0;
+    });
+}
+/* ddz_cmplx2cmplx :137-145: complex y-pencil of the spectral decomposition, in place */
+int pdo_ops_periodic_ddz_cmplx2cmplx(pdo_ops_periodic_t o, double* fhat, void* stream) {
+    if (!o || !fhat) return fail(PDO_E_BADARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    pdo_spectral_s* s = o->spect;
+    pdo_decomp_t spec = fft3d_spec_decomp(s->ft);
+    const size_t bytes = sizeof(double2) * (size_t)vol(s->si.ysz);
+    return with_device_views(fhat, bytes, fhat, bytes, st, [&](const void* di, void* d_o) -> int {
+        if (di != d_o) PDO_CUDA(cudaMemcpyAsync(d_o, di, bytes, cudaMemcpyDeviceToDevice, st));
+        double2* w = (double2*)d_o;
+        if (s->p_col == 1) return zfourier_complex(s, w, ZT_K3_C2C, st);
+        if (int rc = decomp_transpose_device(spec, 2, (const double*)w, (double*)s->ctmpz, 2, st)) return rc;
+        if (int rc = zfourier_complex(s, s->ctmpz, ZT_K3_C2C, st)) return rc;
+        return decomp_transpose_device(spec, 3, (const double*)s->ctmpz, (double*)w, 2, st);
+    });
+}
+/* SolvePoisson_oop :70-76 (p != rhs), SolvePoisson_ip :78-84 (p == rhs) */
+int pdo_ops_periodic_solve_poisson(pdo_ops_periodic_t o, const double* rhs, double* p, void* stream) {
+    if (!o) return fail(PDO_E_BADARG, "null handle");
+    return pdo_poisson_solve(o->poiss, rhs, p, stream);
 }
 
 }  // extern "C"

@@ -212,6 +212,25 @@ int fft3d_z_inplace(pdo_fft3d_t f, double2* a_cplx_z, int dir, cudaStream_t st) 
     g_launches += 1;
     return 0;
 }
+int zcols_exec(ZColsPlan* p, int nz, long long cols, double2* a, int dir, cudaStream_t st) {
+    if (!p || nz < 1 || cols < 1 || cols > 0x7fffffffLL) return fail(PDO_E_BADARG, "zcols: bad shape");
+    if (p->plan < 0 || p->nz != nz || p->cols != cols) {
+        zcols_destroy(p);
+        cufftHandle h;
+        int n1[1] = {nz}, emb[1] = {nz};
+        const int c = (int)cols;
+        PDO_CUFFT(cufftPlanMany(&h, 1, n1, emb, c, 1, emb, c, 1, CUFFT_Z2Z, c));   // same shape of plan as planz (fft_3d.F90:295-306)
+        p->plan = (int)h; p->nz = nz; p->cols = cols;
+    }
+    PDO_CUFFT(cufftSetStream((cufftHandle)p->plan, st));
+    PDO_CUFFT(cufftExecZ2Z((cufftHandle)p->plan, (cufftDoubleComplex*)a, (cufftDoubleComplex*)a, dir < 0 ? CUFFT_FORWARD : CUFFT_INVERSE));
+    g_launches += 1;
+    return 0;
+}
+void zcols_destroy(ZColsPlan* p) {
+    if (p && p->plan >= 0) cufftDestroy((cufftHandle)p->plan);
+    if (p) { p->plan = -1; p->cols = 0; p->nz = 0; }
+}
 pdo_decomp_t fft3d_phys_decomp(pdo_fft3d_t f) { return f->phys; }
 pdo_decomp_t fft3d_spec_decomp(pdo_fft3d_t f) { return f->spec; }
 }  // namespace pdo

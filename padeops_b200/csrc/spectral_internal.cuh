@@ -20,6 +20,11 @@ int fft3d_forward_xy(pdo_fft3d_t f, const double* in_real_x, double2* out_cplx_y
 int fft3d_backward_yx(pdo_fft3d_t f, const double2* in_cplx_y, double* out_real_x, bool set_oddball, cudaStream_t st);
 int fft3d_backward_yx_scratch(pdo_fft3d_t f, double2* prescaled_scratch_cplx_y, double* out_real_x, cudaStream_t st);
 int fft3d_z_inplace(pdo_fft3d_t f, double2* a_cplx_z, int dir, cudaStream_t st);
+// c2c along the slowest index of an array (nz, cols) with ANY column count (the real z-Fourier procedures transform pairs of
+// real columns as one complex column); the plan is cached in `p` and rebuilt when the shape changes.
+struct ZColsPlan { int plan = -1; long long cols = 0; int nz = 0; };
+int zcols_exec(ZColsPlan* p, int nz, long long cols, double2* a, int dir, cudaStream_t st);
+void zcols_destroy(ZColsPlan* p);
 pdo_decomp_t fft3d_phys_decomp(pdo_fft3d_t f);
 pdo_decomp_t fft3d_spec_decomp(pdo_fft3d_t f);
 }  // namespace pdo

@@ -97,6 +97,88 @@ class spectral:
         check(lib().pdo_spectral_take_ifft1d_z2z_ip(self._h, ptr(a), stream_ptr(stream)))
         return a
 
+    def ddz_C2C_real_inplace(self, a, stream=None):
+        """real z-pencil of physdecomp; the oddball mode passes through (spectral.F90:507-526)"""
+        check(lib().pdo_spectral_ddz_c2c_real_ip(self._h, ptr(a), stream_ptr(stream)))
+        return a
+
+    def ddz_C2C_complex_inplace(self, a, stream=None):
+        check(lib().pdo_spectral_ddz_c2c_complex_ip(self._h, ptr(a), stream_ptr(stream)))
+        return a
+
+    def shiftz_E2C(self, a, stream=None):
+        check(lib().pdo_spectral_shiftz_e2c(self._h, ptr(a), stream_ptr(stream)))
+        return a
+
+    def shiftz_C2E(self, a, stream=None):
+        check(lib().pdo_spectral_shiftz_c2e(self._h, ptr(a), stream_ptr(stream)))
+        return a
+
+
+class Ops_Periodic:
+    """igrid_Operators_Periodic::Ops_Periodic (igrid_operators_periodic.F90:13-161).  Real arrays: x-pencils of the physical
+    decomposition; `gp` enters as its process grid (p_row, p_col; 0, 0 = 1 x nproc).  The I/O procedures (ReadField3D /
+    WriteField3D) are outside the hot path."""
+
+    def __init__(self):
+        self._h = C.c_void_p(None)
+        self.spect = None
+
+    def init(self, nx, ny, nz, dx, dy, dz, p_row=0, p_col=0, InputDir="", OutputDir=""):
+        self.destroy()
+        decomp_2d.comm_init()
+        check(lib().pdo_ops_periodic_init(C.byref(self._h), int(nx), int(ny), int(nz), float(dx), float(dy), float(dz), int(p_row), int(p_col)))
+        sp = spectral()                      # link_spect: a borrowed view of the type the handle owns
+        sp._h = C.c_void_p(lib().pdo_ops_periodic_spect(self._h))
+        sp.nx_g, sp.ny_g, sp.nz_g = nx, ny, nz
+        sp.physdecomp = _info(lib().pdo_spectral_get_physical_info, sp._h)
+        sp.spectdecomp = _info(lib().pdo_spectral_get_spectral_info, sp._h)
+        sp.destroy = lambda: None
+        self.spect = sp
+        self.inputdir, self.outputdir = InputDir, OutputDir
+        return 0
+
+    def destroy(self):
+        if self._h:
+            lib().pdo_ops_periodic_destroy(self._h)
+            self._h = C.c_void_p(None)
+            self.spect = None
+
+    def link_spect(self):
+        return self.spect
+
+    def _rr(self, name, f, out, stream):
+        out = _empty(f, f.shape, False) if out is None else out
+        check(getattr(lib(), "pdo_ops_periodic_" + name)(self._h, ptr(f), ptr(out), stream_ptr(stream)))
+        return out
+
+    def ddx(self, f, dfdx=None, stream=None):
+        return self._rr("ddx", f, dfdx, stream)
+
+    def ddy(self, f, dfdy=None, stream=None):
+        return self._rr("ddy", f, dfdy, stream)
+
+    def ddz(self, f, dfdz=None, stream=None):
+        return self._rr("ddz", f, dfdz, stream)
+
+    def ddz_cmplx2cmplx(self, fhat, stream=None):
+        check(lib().pdo_ops_periodic_ddz_cmplx2cmplx(self._h, ptr(fhat), stream_ptr(stream)))
+        return fhat
+
+    def SolvePoisson_oop(self, rhs, p=None, stream=None):
+        return self._rr("solve_poisson", rhs, p, stream)
+
+    def SolvePoisson_ip(self, rhs, stream=None):
+        return self._rr("solve_poisson", rhs, rhs, stream)
+
+    def dealiasField(self, f, stream=None):
+        check(lib().pdo_ops_periodic_dealias_field(self._h, ptr(f), stream_ptr(stream)))
+        return f
+
+    def allocate3Dfield(self, device="cuda"):
+        import torch
+        return torch.empty(tuple(reversed(self.spect.physdecomp["xsz"])), dtype=torch.float64, device=device)
+
 
 fd02, cd06, fourierColl = 0, 1, 2
 
