@@ -175,6 +175,20 @@ module padeops_b200_c
         PDO_TRANSPOSE_FN(pdo_transpose_y_to_x)
         PDO_TRANSPOSE_FN(pdo_transpose_y_to_z)
         PDO_TRANSPOSE_FN(pdo_transpose_z_to_y)
+        function pdo_decomp_write_one(h, ipencil, var, elem_doubles, filename) bind(C, name="pdo_decomp_write_one") result(ierr)
+            import :: c_ptr, c_int, c_char
+            type(c_ptr), value :: h, var
+            integer(c_int), value :: ipencil, elem_doubles
+            character(kind=c_char), dimension(*), intent(in) :: filename
+            integer(c_int) :: ierr
+        end function
+        function pdo_decomp_read_one(h, ipencil, var, elem_doubles, filename) bind(C, name="pdo_decomp_read_one") result(ierr)
+            import :: c_ptr, c_int, c_char
+            type(c_ptr), value :: h, var
+            integer(c_int), value :: ipencil, elem_doubles
+            character(kind=c_char), dimension(*), intent(in) :: filename
+            integer(c_int) :: ierr
+        end function
         function pdo_p_maxval(xloc, xglob) bind(C, name="pdo_p_maxval") result(ierr)
             import :: c_double, c_int
             real(c_double), value :: xloc

@@ -168,6 +168,19 @@ int pdo_transpose_x_to_y(pdo_decomp_t h, const double* src, double* dst, int ele
 int pdo_transpose_y_to_x(pdo_decomp_t h, const double* src, double* dst, int elem_doubles, void* stream);
 int pdo_transpose_y_to_z(pdo_decomp_t h, const double* src, double* dst, int elem_doubles, void* stream);
 int pdo_transpose_z_to_y(pdo_decomp_t h, const double* src, double* dst, int elem_doubles, void* stream);
+/* decomp_2d_io: decomp_2d_write_one(ipencil, var, filename, opt_decomp) / decomp_2d_read_one       2D» io_write_one.f90:23-80, io_read_one.f90
+   ONE distributed array <-> the flat GLOBAL (nx, ny, nz) array in Fortran order, native doubles, no header (the format of the
+   reference's restart and field dumps).  ipencil 1 / 2 / 3 = var is this rank's x- / y- / z-pencil; host or device pointer;
+   elem_doubles 1 (real) or 2 (complex).  Collective; the file is truncated first; a missing file on read -> 321. */
+int pdo_decomp_write_one(pdo_decomp_t h, int ipencil, const double* var, int elem_doubles, const char* filename);
+int pdo_decomp_read_one(pdo_decomp_t h, int ipencil, double* var, int elem_doubles, const char* filename);
+/* the per-rank piece (pure host code, no communicator): sub-box (sub, st 0-based) of the global (sizes) array; create != 0
+   truncates / creates the file first (rank 0's job in the collective call) */
+int pdo_io_write_block(const char* filename, const int sizes[3], const int sub[3], const int st[3], int elem_doubles, const double* data,
+                       int create);
+int pdo_io_read_block(const char* filename, const int sizes[3], const int sub[3], const int st[3], int elem_doubles, double* data);
+/* Fortran's G15.5 edit descriptor (the restart info file's format, igrid.F90:2797); out holds 15 characters + NUL */
+int pdo_io_format_g15_5(double x, char out[16]);
 /* reductions::p_maxval / p_sum of one double over all ranks              utilities/reductions.F90:29-225 */
 int pdo_p_maxval(double local, double* global);
 int pdo_p_sum(double local, double* global);
@@ -327,6 +340,13 @@ int pdo_igrid_time_advance(pdo_igrid_t h, double dt, void* stream);        /* ti
 int pdo_igrid_get_field(pdo_igrid_t h, int which, double* out, void* stream);
 int pdo_igrid_get_decomp_info(pdo_igrid_t h, int which /*0 gpC, 1 gpE, 2 sp_gpC, 3 sp_gpE*/, pdo_decomp_info* info);
 int pdo_igrid_get_state(pdo_igrid_t h, int* step, double* tsim);
+/* Restart and field files exactly as the reference writes them (x-pencils of gpC / gpE through decomp_2d_write_one):
+   dumpRestartFile :2763-2803  ->  <dir>/RESTART_Run<rid>_{u,v,w}.<step, 6 digits> + RESTART_Run<rid>_info.<step> (tsim, g15.5)
+   readRestartFile :2719-2761 + init's :589-591, 625-655  ->  step = tid, tsim from the info file, fields projected, state rebuilt
+   dumpFullField   :2806-2823  ->  <dir>/Run<rid>_<label>_t<step>.out for field ids 0 u, 1 v, 2 w, 3 wC, 4 uE, 5 vE, 6 divergence */
+int pdo_igrid_dump_restart(pdo_igrid_t h, const char* outputdir, int run_id);
+int pdo_igrid_read_restart(pdo_igrid_t h, const char* inputdir, int run_id, int tid);
+int pdo_igrid_dump_full_field(pdo_igrid_t h, int which, const char* label4, const char* outputdir, int run_id);
 /* compute_deltaT with useCFL (igrid.F90:1372-1396) */
 int pdo_igrid_compute_delta_t(pdo_igrid_t h, double cfl, double* dt, void* stream);
 int pdo_igrid_max_divergence(pdo_igrid_t h, double* max_div, void* stream);   /* printDivergence + p_maxval(|div|) */

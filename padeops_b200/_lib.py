@@ -127,6 +127,14 @@ _PROTOS.update({
     "pdo_spectral_take_fft1d_z2z_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "pdo_spectral_take_ifft1d_z2z_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "pdo_debug_ztables": (C.c_int, [C.c_int, C.c_double, c_dp]),
+    "pdo_decomp_write_one": (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_int, C.c_char_p]),
+    "pdo_decomp_read_one": (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_int, C.c_char_p]),
+    "pdo_io_write_block": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, c_dp, C.c_int]),
+    "pdo_io_read_block": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, c_dp]),
+    "pdo_io_format_g15_5": (C.c_int, [C.c_double, C.c_char_p]),
+    "pdo_igrid_dump_restart": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "pdo_igrid_read_restart": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
+    "pdo_igrid_dump_full_field": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]),
     "pdo_spectral_ddz_c2c_real_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "pdo_spectral_ddz_c2c_complex_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "pdo_spectral_shiftz_e2c": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),

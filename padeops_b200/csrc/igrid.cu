@@ -20,6 +20,7 @@
 #include <cmath>
 #include <cstring>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -1279,6 +1280,27 @@ int pdo_igrid_destroy(pdo_igrid_t g) {
     return 0;
 }
 
+// From (u, v, w) on the x-pencils to a consistent state (igrid.F90:625-655): transforms, dealiasing, projection, back to
+// physical space, interpolations and the velocity gradients.  u, v, w: host or device.
+static int ig_set_fields(pdo_igrid_s* g, const double* u, const double* v, const double* w, cudaStream_t st) {
+    IG(copy_in(g->u, u, sizeof(double) * g->nRC, st));
+    IG(copy_in(g->v, v, sizeof(double) * g->nRC, st));
+    IG(copy_in(g->w, w, sizeof(double) * g->nRE, st));
+    IG(fftC(g, g->u, g->cur[0], st));
+    IG(fftC(g, g->v, g->cur[1], st));
+    IG(fftE(g, g->w, g->cur[2], st));
+    IG(ig_dealias_fields(g, st));
+    IG(poiss_divergence_check(g->poiss, g->cur[0], g->cur[1], g->cur[2], g->divergence, false, nullptr, st));
+    IG(poiss_projection(g->poiss, g->cur[0], g->cur[1], g->cur[2], st));
+    IG(ifftC(g, g->cur[0], g->u, st));
+    IG(ifftC(g, g->cur[1], g->v, st));
+    IG(ifftE(g, g->cur[2], g->w, st));
+    IG(ig_interp_primitive(g, st));
+    IG(ig_compute_duidxj(g, st));
+    PDO_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int pdo_igrid_init(pdo_igrid_t* h, const pdo_igrid_params* p, const double* u, const double* v, const double* w) {
     if (!h || !p || !u || !v || !w) return fail(PDO_E_BADARG, "null argument");
     *h = nullptr;
@@ -1327,25 +1349,7 @@ int pdo_igrid_init(pdo_igrid_t* h, const pdo_igrid_params* p, const double* u, c
     if (rc) { pdo_igrid_destroy(g); return rc; }
     for (int c = 0; c < 3; ++c) g->cur[c] = g->S[0][c];
     // igrid.F90:625-655
-    auto run = [&]() -> int {
-        IG(copy_in(g->u, u, sizeof(double) * g->nRC, st));
-        IG(copy_in(g->v, v, sizeof(double) * g->nRC, st));
-        IG(copy_in(g->w, w, sizeof(double) * g->nRE, st));
-        IG(fftC(g, g->u, g->cur[0], st));
-        IG(fftC(g, g->v, g->cur[1], st));
-        IG(fftE(g, g->w, g->cur[2], st));
-        IG(ig_dealias_fields(g, st));
-        IG(poiss_divergence_check(g->poiss, g->cur[0], g->cur[1], g->cur[2], g->divergence, false, nullptr, st));
-        IG(poiss_projection(g->poiss, g->cur[0], g->cur[1], g->cur[2], st));
-        IG(ifftC(g, g->cur[0], g->u, st));
-        IG(ifftC(g, g->cur[1], g->v, st));
-        IG(ifftE(g, g->cur[2], g->w, st));
-        IG(ig_interp_primitive(g, st));
-        IG(ig_compute_duidxj(g, st));
-        PDO_CUDA(cudaStreamSynchronize(st));
-        return 0;
-    };
-    rc = run();
+    rc = ig_set_fields(g, u, v, w, st);
     if (rc) { pdo_igrid_destroy(g); return rc; }
     *h = g;
     return 0;
@@ -1396,6 +1400,84 @@ int pdo_igrid_get_state(pdo_igrid_t g, int* step, double* tsim) {
     if (step) *step = g->step;
     if (tsim) *tsim = g->tsim;
     return 0;
+}
+
+// ---- restart / field files in the reference's format (igrid.F90:2719-2823; 2DECOMP io_write_one.f90) ----
+static std::string restart_name(const char* dir, int rid, const char* tag, int tid) {
+    char name[64];
+    std::snprintf(name, sizeof(name), "RESTART_Run%02d_%s.%06d", rid, tag, tid);   // "(A7,A4,I2.2,A3,I6.6)"
+    return std::string(dir ? dir : ".") + "/" + name;
+}
+/* dumpRestartFile :2763-2799: u, v on gpC and w on gpE as flat global arrays + the info file with tsim in g15.5, at this%step */
+int pdo_igrid_dump_restart(pdo_igrid_t g, const char* outputdir, int run_id) {
+    if (!g) return fail(PDO_E_BADARG, "null handle");
+    PDO_CUDA(cudaDeviceSynchronize());
+    pdo_decomp_t dC = fft3d_phys_decomp(g->spC->ft), dE = fft3d_phys_decomp(g->spE->ft);
+    if (int rc = pdo_decomp_write_one(dC, 1, g->u, 1, restart_name(outputdir, run_id, "u", g->step).c_str())) return rc;
+    if (int rc = pdo_decomp_write_one(dC, 1, g->v, 1, restart_name(outputdir, run_id, "v", g->step).c_str())) return rc;
+    if (int rc = pdo_decomp_write_one(dE, 1, g->w, 1, restart_name(outputdir, run_id, "w", g->step).c_str())) return rc;
+    int rc = 0;
+    if (pdo_comm_rank() == 0) {
+        char line[16];
+        pdo_io_format_g15_5(g->tsim, line);
+        FILE* f = std::fopen(restart_name(outputdir, run_id, "info", g->step).c_str(), "w");
+        if (!f) rc = fail(PDO_E_BADARG, "cannot write the restart info file in '%s'", outputdir ? outputdir : ".");
+        else { std::fprintf(f, "%s\n", line); std::fclose(f); }
+    }
+    double dummy;
+    if (int b = pdo_p_sum(0.0, &dummy)) return b;   // mpi_barrier :2801
+    return rc;
+}
+/* readRestartFile :2719-2761 followed by what init does with freshly read fields (:589-591, 625-655): step = tid, tsim from the
+   info file (rank 0 reads, everyone gets it), fields projected and all dependent state rebuilt */
+int pdo_igrid_read_restart(pdo_igrid_t g, const char* inputdir, int run_id, int tid) {
+    if (!g) return fail(PDO_E_BADARG, "null handle");
+    cudaStream_t st = nullptr;
+    pdo_decomp_t dC = fft3d_phys_decomp(g->spC->ft), dE = fft3d_phys_decomp(g->spE->ft);
+    // rbC / rbE scratch pencils receive the file contents; ig_set_fields copies them into u, v, w
+    double *ru = g->rbC[0], *rv = g->rbC[1], *rw = g->rbE[0];
+    if (int rc = pdo_decomp_read_one(dC, 1, ru, 1, restart_name(inputdir, run_id, "u", tid).c_str())) return rc;
+    if (int rc = pdo_decomp_read_one(dC, 1, rv, 1, restart_name(inputdir, run_id, "v", tid).c_str())) return rc;
+    if (int rc = pdo_decomp_read_one(dE, 1, rw, 1, restart_name(inputdir, run_id, "w", tid).c_str())) return rc;
+    double tsim = 0.0;
+    int bad = 0;
+    if (pdo_comm_rank() == 0) {
+        FILE* f = std::fopen(restart_name(inputdir, run_id, "info", tid).c_str(), "r");
+        if (!f || std::fscanf(f, "%lf", &tsim) != 1) bad = 1;
+        if (f) std::fclose(f);
+    }
+    // mpi_bcast(tsim) from rank 0: the other ranks contribute zero to a sum
+    double tsum = 0.0, badsum = 0.0;
+    if (int b = pdo_p_sum(pdo_comm_rank() == 0 ? tsim : 0.0, &tsum)) return b;
+    if (int b = pdo_p_sum((double)bad, &badsum)) return b;
+    if (badsum != 0.0) return fail(PDO_E_BADARG, "cannot read the restart info file in '%s'", inputdir ? inputdir : ".");
+    for (int c = 0; c < 3; ++c) g->cur[c] = g->S[0][c];
+    if (int rc = ig_set_fields(g, ru, rv, rw, st)) return rc;
+    g->tsim = tsum;
+    g->step = tid;
+    return 0;
+}
+/* dumpFullField(arr, label, gp2use) :2806-2823 for the fields the handle owns (ids of pdo_igrid_get_field: 0 u, 1 v, 2 w, 3 wC,
+   4 uE, 5 vE, 6 divergence): "Run<rid>_<label>_t<step>.out", x-pencil of gpC, or of gpE for the edge fields */
+int pdo_igrid_dump_full_field(pdo_igrid_t g, int which, const char* label4, const char* outputdir, int run_id) {
+    if (!g || !label4) return fail(PDO_E_BADARG, "null argument");
+    const double* src = nullptr;
+    bool edge = false;
+    switch (which) {
+        case 0: src = g->u; break;
+        case 1: src = g->v; break;
+        case 2: src = g->w; edge = true; break;
+        case 3: src = g->wC; break;
+        case 4: src = g->uE; edge = true; break;
+        case 5: src = g->vE; edge = true; break;
+        case 6: src = g->divergence; break;
+        default: return fail(PDO_E_BADARG, "unknown field id %d", which);
+    }
+    PDO_CUDA(cudaDeviceSynchronize());
+    char name[64];
+    std::snprintf(name, sizeof(name), "Run%02d_%.4s_t%06d.out", run_id, label4, g->step);   // "(A3,I2.2,A1,A4,A2,I6.6,A4)"
+    const std::string fname = std::string(outputdir ? outputdir : ".") + "/" + name;
+    return pdo_decomp_write_one(fft3d_phys_decomp((edge ? g->spE : g->spC)->ft), 1, src, 1, fname.c_str());
 }
 
 int pdo_igrid_compute_delta_t(pdo_igrid_t g, double cfl, double* dt, void* stream) {

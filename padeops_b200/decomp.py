@@ -134,3 +134,21 @@ def transpose_y_to_z(src, dst=None, decomp=None, stream=None):
 
 def transpose_z_to_y(src, dst=None, decomp=None, stream=None):
     return _transpose("z_to_y", src, dst, decomp, "z", "y", stream)
+
+
+# ---- decomp_2d_io (2D» io_write_one.f90, io_read_one.f90): one distributed array <-> the flat global Fortran-order file ----
+def decomp_2d_write_one(ipencil, var, filename, opt_decomp=None):
+    decomp = opt_decomp or decomp_2d.main
+    pen = "xyz"[int(ipencil) - 1]
+    assert tuple(var.shape) == tuple(reversed(getattr(decomp, pen + "sz"))), (tuple(var.shape), getattr(decomp, pen + "sz"))
+    w = 2 if "complex" in str(var.dtype) else 1
+    check(lib().pdo_decomp_write_one(decomp._h, int(ipencil), ptr(var), w, str(filename).encode()))
+
+
+def decomp_2d_read_one(ipencil, var, filename, opt_decomp=None):
+    decomp = opt_decomp or decomp_2d.main
+    pen = "xyz"[int(ipencil) - 1]
+    assert tuple(var.shape) == tuple(reversed(getattr(decomp, pen + "sz"))), (tuple(var.shape), getattr(decomp, pen + "sz"))
+    w = 2 if "complex" in str(var.dtype) else 1
+    check(lib().pdo_decomp_read_one(decomp._h, int(ipencil), ptr(var), w, str(filename).encode()))
+    return var

@@ -342,3 +342,14 @@ class igrid:
         md = C.c_double(0.0)
         check(lib().pdo_igrid_max_divergence(self._h, C.byref(md), stream_ptr(stream)))
         return md.value
+
+    # ---- the reference's restart / field files (igrid.F90:2719-2823) ----
+    def dumpRestartFile(self, OutputDir, runID=1):
+        check(lib().pdo_igrid_dump_restart(self._h, str(OutputDir).encode(), int(runID)))
+
+    def readRestartFile(self, tid, rid, InputDir):
+        check(lib().pdo_igrid_read_restart(self._h, str(InputDir).encode(), int(rid), int(tid)))
+
+    def dumpFullField(self, name, label, OutputDir, runID=1):
+        assert len(label) == 4, "label is character(len=4) in the reference"
+        check(lib().pdo_igrid_dump_full_field(self._h, self.FIELDS[name], label.encode(), str(OutputDir).encode(), int(runID)))

@@ -261,3 +261,37 @@ def test_igrid_substep_fourier_z_matches_oracle(pdo, IG, adv):
             r = getattr(ref, nm)
             assert np.abs(g.get(nm) - r).max() < TOL * np.abs(r).max(), (it, nm)
     assert g.maxDivergence() < 1e-11 * max(np.abs(ref.u).max(), np.abs(ref.w).max())
+
+
+@pytest.mark.xfail(strict=False, reason=_LATE)
+def test_restart_files_round_trip(pdo, IG, tmp_path):
+    """dumpRestartFile / readRestartFile / dumpFullField in the reference's format (igrid.F90:2719-2823): flat global
+    Fortran-order doubles per field + the g15.5 info file; a run restarted from them continues like the original."""
+    nx, ny, nz = 16, 16, 16
+    L = (2 * np.pi,) * 3
+    u, v = broadband((nz, ny, nx), 1), broadband((nz, ny, nx), 2)
+    w = broadband((nz + 1, ny, nx), 3)
+    w[nz] = w[0]
+    g = pdo.igrid()
+    g.init(nx, ny, nz, *L, 50.0, u, v, w, TimeSteppingScheme=1)
+    for _ in range(2):
+        g.timeAdvance(0.01)
+    g.dumpRestartFile(tmp_path, runID=7)
+    for nm in ("u", "v", "w"):
+        assert (tmp_path / f"RESTART_Run07_{nm}.000002").read_bytes() == g.get(nm).tobytes()
+    assert (tmp_path / "RESTART_Run07_info.000002").read_text() == "    0.20000E-01\n"
+    g.dumpFullField("wC", "wCel", tmp_path, runID=7)
+    assert (tmp_path / "Run07_wCel_t000002.out").read_bytes() == g.get("wC").tobytes()
+    h = pdo.igrid()
+    h.init(nx, ny, nz, *L, 50.0, np.zeros_like(u), np.zeros_like(v), np.zeros_like(w), TimeSteppingScheme=1)
+    h.readRestartFile(2, 7, tmp_path)
+    assert h.step == 2 and abs(h.tsim - 0.02) < 1e-15
+    for nm in ("u", "v", "w", "wC"):
+        assert np.abs(h.get(nm) - g.get(nm)).max() < TOL * np.abs(g.get(nm)).max(), nm     # re-projection of a projected field
+    g.timeAdvance(0.01)
+    h.timeAdvance(0.01)
+    for nm in ("u", "v", "w"):
+        assert np.abs(h.get(nm) - g.get(nm)).max() < TOL * np.abs(g.get(nm)).max(), nm
+    with pytest.raises(pdo.PadeOpsError) as e:
+        h.readRestartFile(3, 7, tmp_path)
+    assert e.value.code == 321
