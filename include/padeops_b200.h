@@ -94,6 +94,11 @@ int pdo_gaussian_filter3(pdo_gaussian_t h, const double* f, double* fil, int na,
 /* ---- cd06staggstuff::cd06stagg, periodic  (derivatives/cd06stagg.F90) ------------------------ */
 typedef struct pdo_cd06stagg_s* pdo_cd06stagg_t;
 int pdo_cd06stagg_init_periodic(pdo_cd06stagg_t* h, int n, double dx);                  /* cd06stagg.F90:170-195 */
+/* init(nx, dx, isTopEven, isBotEven, isTopSided, isBotSided): walls in z, cd06stagg.F90:197-231 + the STAGG_CD06_files includes.
+   The FIELD is even / odd about a wall (is*Even), or that wall takes the one-sided closure (is*Sided).  Correctness path:
+   one thread per z-line, right-hand side formed inside the Thomas sweep (csrc/stagg_np.cu). */
+int pdo_cd06stagg_init_nonperiodic(pdo_cd06stagg_t* h, int nx, double dx, int is_top_even, int is_bot_even, int is_top_sided,
+                                   int is_bot_sided);
 int pdo_cd06stagg_destroy(pdo_cd06stagg_t h);
 /* (in, out, n1, n2); cells have n planes, edges n+1.  `is_complex` = the CMPLX specific of the generic.
    ddz_E2C :820-848  ddz_C2E :850-881  InterpZ_E2C :928-956  InterpZ_C2E :958-993
@@ -104,6 +109,9 @@ int pdo_cd06stagg_interpz_E2C(pdo_cd06stagg_t h, const double* fE, double* fC, i
 int pdo_cd06stagg_interpz_C2E(pdo_cd06stagg_t h, const double* fC, double* fE, int n1, int n2, int is_complex, void* stream);
 int pdo_cd06stagg_d2dz2_C2C(pdo_cd06stagg_t h, const double* fC, double* d2fC, int n1, int n2, int is_complex, void* stream);
 int pdo_cd06stagg_d2dz2_E2E(pdo_cd06stagg_t h, const double* fE, double* d2fE, int n1, int n2, int is_complex, void* stream);
+/* collocated first derivatives on the staggered grids (cd06stagg.F90:883-925); non-periodic handles only, as in the reference */
+int pdo_cd06stagg_ddz_C2C(pdo_cd06stagg_t h, const double* fC, double* dfC, int n1, int n2, int is_complex, void* stream);
+int pdo_cd06stagg_ddz_E2E(pdo_cd06stagg_t h, const double* fE, double* dfE, int n1, int n2, int is_complex, void* stream);
 
 /* ---- DerivativesMod::derivatives  (derivatives/derivatives.F90) ------------------------------ */
 typedef struct pdo_derivatives_s* pdo_derivatives_t;
@@ -269,7 +277,7 @@ int pdo_spectral_shiftz_c2e(pdo_spectral_t h, double* ahat_cplx_z, void* stream)
 /* the 1-D tables behind k1 / k2 / kabs_sq / Gdealias: full global length (nx/2+1, ny, nz); NULL entries are skipped */
 int pdo_spectral_get_tables(pdo_spectral_t h, double* k1, double* k2, double* gdealias_x, double* gdealias_y, double* gdealias_z);
 
-/* ---- PadeDerOps::Pade6stagg, isPeriodic = .true.  (incompressible/PadeDerOps.F90) ------------- */
+/* ---- PadeDerOps::Pade6stagg  (incompressible/PadeDerOps.F90) --------------------------------- */
 typedef struct pdo_pade6stagg_s* pdo_pade6stagg_t;
 #define PDO_SCHEME_FD02 0
 #define PDO_SCHEME_CD06 1
@@ -283,8 +291,11 @@ int pdo_pade6stagg_init(pdo_pade6stagg_t* h, const int gp_zsz[3], const int sp_z
 int pdo_pade6stagg_init2(pdo_pade6stagg_t* h, const int gp_zsz[3], const int sp_zsz[3], double dz, int scheme, int is_periodic,
                          struct pdo_spectral_s* spectC);
 int pdo_pade6stagg_destroy(pdo_pade6stagg_t h);
-/* generic over real (is_complex = 0, sizes from gp) / complex (is_complex = 1, sizes from sp_gp); bot/top BC integers
-   are accepted and ignored, as on the reference's periodic branch (:146-160, 404-418, 572-585, 689-702, 879-892) */
+/* generic over real (is_complex = 0, sizes from gp) / complex (is_complex = 1, sizes from sp_gp).  isPeriodic = .true.: the
+   bot / top integers are accepted and ignored, as in the reference (:146-160, 404-418, 572-585, 689-702, 879-892).
+   isPeriodic = .false. (scheme cd06; any other scheme -> 323): init builds the nine wall operators derOO .. derSS (:92-110) and
+   bot / top select one per call: -1 the field is odd about that wall, +1 even, 0 one-sided closure (first-order operators
+   only); any other combination gives output = 0, as the reference's select-case does (:185-205, 449-482). */
 int pdo_pade6stagg_ddz_C2E(pdo_pade6stagg_t h, const double* in, double* out, int is_complex, int bot, int top, void* stream);
 int pdo_pade6stagg_ddz_E2C(pdo_pade6stagg_t h, const double* in, double* out, int is_complex, int bot, int top, void* stream);
 int pdo_pade6stagg_interpz_C2E(pdo_pade6stagg_t h, const double* in, double* out, int is_complex, int bot, int top, void* stream);

@@ -155,9 +155,17 @@ class Pade6stagg:
     complex procedures of spectral.F90:387-407, 462-482, 528-568, 596-680 and their real twins (r2c / c2r, oddball mode untouched);
     edge outputs copy plane 1 into plane nz+1."""
 
-    def __init__(self, nz, dz, scheme=1):
+    def __init__(self, nz, dz, scheme=1, isPeriodic=True):
         assert scheme in (1, 2)
         self.nz, self.dz, self.scheme = nz, dz, scheme
+        self.isPeriodic = isPeriodic
+        if not isPeriodic:
+            # PadeDerOps.F90:92-110: derOO .. derSS, keyed here by (bot, top) in {-1 odd, 0 one-sided, +1 even}^2; the Even flag of
+            # a one-sided wall never reaches a row
+            assert scheme == 1, "Invalid choice for numerical scheme in vertical direction (323)"
+            from . import stagg_np_oracle as SN
+            self.wall = {(b, t): SN.CD06StaggNP(nz, dz, isTopEven=(t == 1), isBotEven=(b == 1), isTopSided=(t == 0), isBotSided=(b == 0))
+                         for b in (-1, 0, 1) for t in (-1, 0, 1)}
         if scheme == 2:
             k3 = O.wavenums(nz, dz)
             self.mk3sq = -(k3 ** 2)
@@ -180,22 +188,42 @@ class Pade6stagg:
             out = np.concatenate([out, out[:1]], axis=0)
         return out
 
-    def ddz_E2C(self, fE):
+    def _wall(self, name, f, bot, top, edge_out, second):
+        """isPeriodic = .false. (PadeDerOps.F90:185-205, 449-482, ...): unsupported (bot, top) combinations give output = 0"""
+        f = np.asarray(f)
+        ok = bot in (-1, 0, 1) and top in (-1, 0, 1) and not (second and (bot == 0 or top == 0))
+        if not ok:
+            return np.zeros((self.nz + (1 if edge_out else 0),) + f.shape[1:], dtype=f.dtype)
+        return getattr(self.wall[(bot, top)], name)(f)
+
+    def ddz_E2C(self, fE, bot=0, top=0):
+        if not self.isPeriodic:
+            return self._wall("ddz_E2C", fE, bot, top, False, False)
         return O.stagg("ddz_E2C", fE, self.nz, self.dz) if self.scheme == 1 else self._spect(fE, self.k3_E2Cshift, False)
 
-    def ddz_C2E(self, fC):
+    def ddz_C2E(self, fC, bot=0, top=0):
+        if not self.isPeriodic:
+            return self._wall("ddz_C2E", fC, bot, top, True, False)
         return O.stagg("ddz_C2E", fC, self.nz, self.dz) if self.scheme == 1 else self._spect(fC, self.k3_C2Eshift, True)
 
-    def interpz_E2C(self, fE):
+    def interpz_E2C(self, fE, bot=0, top=0):
+        if not self.isPeriodic:
+            return self._wall("InterpZ_E2C", fE, bot, top, False, False)
         return O.stagg("interp_E2C", fE, self.nz, self.dz) if self.scheme == 1 else self._spect(fE, self.E2Cshift, False)
 
-    def interpz_C2E(self, fC):
+    def interpz_C2E(self, fC, bot=0, top=0):
+        if not self.isPeriodic:
+            return self._wall("InterpZ_C2E", fC, bot, top, True, False)
         return O.stagg("interp_C2E", fC, self.nz, self.dz) if self.scheme == 1 else self._spect(fC, self.C2Eshift, True)
 
-    def d2dz2_C2C(self, fC):
+    def d2dz2_C2C(self, fC, bot=0, top=0):
+        if not self.isPeriodic:
+            return self._wall("d2dz2_C2C", fC, bot, top, False, True)
         return O.stagg("d2dz2_C2C", fC, self.nz, self.dz) if self.scheme == 1 else self._spect(fC, self.mk3sq, False)
 
-    def d2dz2_E2E(self, fE):
+    def d2dz2_E2E(self, fE, bot=0, top=0):
+        if not self.isPeriodic:
+            return self._wall("d2dz2_E2E", fE, bot, top, True, True)
         return O.stagg("d2dz2_E2E", fE, self.nz, self.dz) if self.scheme == 1 else self._spect(fE, self.mk3sq, True)
 
     def getModifiedWavenumbers(self, k):

@@ -127,6 +127,11 @@ _PROTOS.update({
     "pdo_spectral_take_fft1d_z2z_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "pdo_spectral_take_ifft1d_z2z_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "pdo_debug_ztables": (C.c_int, [C.c_int, C.c_double, c_dp]),
+    "pdo_cd06stagg_init_nonperiodic": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "pdo_cd06stagg_ddz_C2C": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "pdo_cd06stagg_ddz_E2E": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "pdo_debug_stagg_np_host": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, C.c_longlong]),
+    "pdo_debug_stagg_np_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_dp]),
     "pdo_decomp_write_one": (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_int, C.c_char_p]),
     "pdo_decomp_read_one": (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_int, C.c_char_p]),
     "pdo_io_write_block": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, c_dp, C.c_int]),

@@ -528,24 +528,82 @@ int pdo_cd06stagg_init_periodic(pdo_cd06stagg_t* h, int n, double dx) {
     *h = o;
     return 0;
 }
+/* cd06stagg%init(nx, dx, isTopEven, isBotEven, isTopSided, isBotSided)  (init_nonperiodic, cd06stagg.F90:197-231) */
+int pdo_cd06stagg_init_nonperiodic(pdo_cd06stagg_t* h, int n, double dx, int is_top_even, int is_bot_even, int is_top_sided,
+                                   int is_bot_sided) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    *h = nullptr;
+    if (n <= 4) return fail(21, "CD06_stagg requires at least 4 points");  // :216-218
+    if (int rc = ensure_device()) return rc;
+    pdo_cd06stagg_s* o = new (std::nothrow) pdo_cd06stagg_s();
+    if (!o) return fail(PDO_E_BADARG, "out of memory");
+    o->n = n;
+    o->periodic = false;
+    StaggNpFlags fl{is_bot_even != 0, is_top_even != 0, is_bot_sided != 0, is_top_sided != 0};
+    int ierr = 0;
+    cudaError_t e = snp_create(&o->np, n, dx, fl, &ierr);
+    if (e != cudaSuccess || ierr) {
+        delete o;
+        return e != cudaSuccess ? fail(PDO_E_CUDA, "cd06stagg init: %s", cudaGetErrorString(e)) : fail(ierr, "cd06stagg init_nonperiodic failed");
+    }
+    *h = o;
+    return 0;
+}
 int pdo_cd06stagg_destroy(pdo_cd06stagg_t h) {
     if (!h) return 0;
-    for (int i = 0; i < 6; ++i) banded_op_destroy(&h->ops[i]);
+    if (h->periodic) for (int i = 0; i < 6; ++i) banded_op_destroy(&h->ops[i]);
+    else snp_destroy(&h->np);
     delete h;
     return 0;
 }
-#define PDO_STAGG_FN(name, idx)                                                                                \
+// non-periodic operator `op` (stagg_np.cuh) on in(n1, n2, rows_in) -> out(n1, n2, rows_out); host pointers are staged
+static int apply_snp(pdo_cd06stagg_t h, int op, const double* in, double* out, int n1, int n2, int is_complex, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!in || !out) return fail(PDO_E_BADARG, "null field pointer");
+    if (n1 < 0 || n2 < 0) return fail(PDO_E_BADARG, "negative extent");
+    const long long ncols = (long long)n1 * n2 * (is_complex ? 2 : 1);
+    const size_t bin = sizeof(double) * (size_t)ncols * snp_rows_in(op, h->n), bout = sizeof(double) * (size_t)ncols * snp_rows_out(op, h->n);
+    return with_device_views(in, bin, out, bout, st, [&](const void* di, void* d_o) -> int {
+        if (di == d_o) return fail(PDO_E_BADARG, "cd06stagg: input and output must not alias");
+        PDO_CUDA(snp_apply(&h->np, op, (const double*)di, (double*)d_o, ncols, st));
+        g_launches += 1;
+        return 0;
+    });
+}
+#define PDO_STAGG_FN(name, idx, snp)                                                                           \
     int name(pdo_cd06stagg_t h, const double* in, double* out, int n1, int n2, int is_complex, void* stream) { \
         if (!h) return fail(PDO_E_BADARG, "null handle");                                                      \
+        if (!h->periodic) return apply_snp(h, snp, in, out, n1, n2, is_complex, stream);                       \
         /* complex data, real LU: re/im are independent lines -> a real field with 2*n1 points in x */         \
         return apply(h->ops[idx], false, 2, in, out, (long long)n1 * (is_complex ? 2 : 1), n2, stream);        \
     }
-PDO_STAGG_FN(pdo_cd06stagg_ddz_E2C, 0)
-PDO_STAGG_FN(pdo_cd06stagg_ddz_C2E, 1)
-PDO_STAGG_FN(pdo_cd06stagg_interpz_E2C, 2)
-PDO_STAGG_FN(pdo_cd06stagg_interpz_C2E, 3)
-PDO_STAGG_FN(pdo_cd06stagg_d2dz2_C2C, 4)
-PDO_STAGG_FN(pdo_cd06stagg_d2dz2_E2E, 5)
+PDO_STAGG_FN(pdo_cd06stagg_ddz_E2C, 0, SNP_D1_E2C)
+PDO_STAGG_FN(pdo_cd06stagg_ddz_C2E, 1, SNP_D1_C2E)
+PDO_STAGG_FN(pdo_cd06stagg_interpz_E2C, 2, SNP_INTERP_E2C)
+PDO_STAGG_FN(pdo_cd06stagg_interpz_C2E, 3, SNP_INTERP_C2E)
+PDO_STAGG_FN(pdo_cd06stagg_d2dz2_C2C, 4, SNP_D2_C2C)
+PDO_STAGG_FN(pdo_cd06stagg_d2dz2_E2E, 5, SNP_D2_E2E)
+// collocated first derivatives on the staggered grids: tables exist only after init_nonperiodic (cd06stagg.F90:883-925)
+int pdo_cd06stagg_ddz_C2C(pdo_cd06stagg_t h, const double* in, double* out, int n1, int n2, int is_complex, void* stream) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    if (h->periodic) return fail(PDO_E_UNSUPPORTED, "cd06stagg ddz_C2C: the reference builds TriD1_C2C only in init_nonperiodic");
+    return apply_snp(h, SNP_D1_C2C, in, out, n1, n2, is_complex, stream);
+}
+int pdo_cd06stagg_ddz_E2E(pdo_cd06stagg_t h, const double* in, double* out, int n1, int n2, int is_complex, void* stream) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    if (h->periodic) return fail(PDO_E_UNSUPPORTED, "cd06stagg ddz_E2E: the reference builds TriD1_E2E only in init_nonperiodic");
+    return apply_snp(h, SNP_D1_E2E, in, out, n1, n2, is_complex, stream);
+}
+// test hooks (host only, not in the public header): the kernel's per-line routine and the tridiagonal rows on the CPU
+int pdo_debug_stagg_np_host(int op, int n, double dx, int bot_even, int top_even, int bot_sided, int top_sided, const double* in, double* out,
+                            long long ncols) {
+    StaggNpFlags fl{bot_even != 0, top_even != 0, bot_sided != 0, top_sided != 0};
+    return snp_apply_host(op, n, dx, fl, in, out, ncols);
+}
+int pdo_debug_stagg_np_rows(int op, int n, int bot_even, int top_even, int bot_sided, int top_sided, double* rows3n) {
+    StaggNpFlags fl{bot_even != 0, top_even != 0, bot_sided != 0, top_sided != 0};
+    return snp_build_rows(op, n, fl, rows3n);
+}
 
 }  // extern "C"
 

@@ -440,6 +440,10 @@ struct pdo_pade6stagg_s {
     int scheme;
     pdo_cd06stagg_t der = nullptr;
     pdo_spectral_t spectC = nullptr;   // scheme = fourierColl: the spectral type whose z transforms and tables are used (borrowed)
+    // isPeriodic = .false., cd06: the nine wall handles derOO .. derSS (PadeDerOps.F90:92-110) at index 3 (bot + 1) + (top + 1),
+    // bot / top = -1 odd, 0 one-sided, +1 even
+    bool periodic = true;
+    pdo_cd06stagg_t wall[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -472,10 +476,25 @@ int pade_fourier(pdo_pade6stagg_s* p, int which, const double* in, double* out, 
     });
 }
 
-int pade_apply(pdo_pade6stagg_s* p, stagg_fn fn, int which, const double* in, double* out, int is_complex, void* st) {
+int pade_apply(pdo_pade6stagg_s* p, stagg_fn fn, int which, const double* in, double* out, int is_complex, int bot, int top, void* st) {
     if (!p) return fail(PDO_E_BADARG, "null handle");
-    if (p->scheme == PDO_SCHEME_FOURIER) return pade_fourier(p, which, in, out, is_complex, st);
     const int* z = is_complex ? p->sp_zsz : p->gp_zsz;
+    if (!p->periodic) {
+        // PadeDerOps.F90:185-205, 449-482, ...: the first-order operators take bot, top in {-1, 0, +1}, the second derivatives
+        // {-1, +1}; any other code gives output = 0
+        const bool second = which >= 4;
+        const bool ok = bot >= -1 && bot <= 1 && top >= -1 && top <= 1 && !(second && (bot == 0 || top == 0));
+        if (!ok) {
+            if (!out) return fail(PDO_E_BADARG, "null field pointer");
+            const bool edge_out = (which == 1 || which == 3 || which == 5);
+            const size_t bytes = sizeof(double) * (is_complex ? 2 : 1) * (size_t)z[0] * z[1] * (size_t)(z[2] + (edge_out ? 1 : 0));
+            if (is_device_ptr(out)) PDO_CUDA(cudaMemsetAsync(out, 0, bytes, (cudaStream_t)st));
+            else std::memset(out, 0, bytes);
+            return 0;
+        }
+        return fn(p->wall[3 * (bot + 1) + (top + 1)], in, out, z[0], z[1], is_complex, st);
+    }
+    if (p->scheme == PDO_SCHEME_FOURIER) return pade_fourier(p, which, in, out, is_complex, st);
     return fn(p->der, in, out, z[0], z[1], is_complex, st);
 }
 }  // namespace
@@ -486,8 +505,8 @@ int pdo_pade6stagg_init2(pdo_pade6stagg_t* h, const int gp_zsz[3], const int sp_
                          pdo_spectral_t spectC) {
     if (!h || !gp_zsz || !sp_zsz) return fail(PDO_E_BADARG, "null argument");
     *h = nullptr;
-    if (!is_periodic) return fail(PDO_E_UNSUPPORTED, "Pade6stagg: non-periodic closures are out of scope (SURVEY.md 8f rank 2)");
     if (scheme == PDO_SCHEME_FD02) return fail(PDO_E_UNSUPPORTED, "Pade6stagg: scheme fd02 is not built (cd06 and fourierColl are)");
+    if (!is_periodic && scheme != PDO_SCHEME_CD06) return fail(323, "Invalid choice for numerical scheme in vertical direction");  // PadeDerOps.F90:121
     if (scheme != PDO_SCHEME_CD06 && scheme != PDO_SCHEME_FOURIER) return fail(434, "Invalid choice of numerical scheme in vertical");  // PadeDerOps.F90:84
     if (scheme == PDO_SCHEME_FOURIER) {
         if (!spectC) return fail(43, "You need to pass in a spectral derived type if you want to use Fourier differentiation in z");  // :77
@@ -502,7 +521,15 @@ int pdo_pade6stagg_init2(pdo_pade6stagg_t* h, const int gp_zsz[3], const int sp_
     std::memcpy(p->gp_zsz, gp_zsz, sizeof(int) * 3);
     std::memcpy(p->sp_zsz, sp_zsz, sizeof(int) * 3);
     p->dz = dz; p->scheme = scheme;
-    if (scheme == PDO_SCHEME_CD06) {
+    p->periodic = is_periodic != 0;
+    if (!p->periodic) {
+        // derOO .. derSS (:92-110): the Even flag of a one-sided wall never reaches a row (the sided branch comes first)
+        for (int bot = -1; bot <= 1; ++bot)
+            for (int top = -1; top <= 1; ++top) {
+                int rc = pdo_cd06stagg_init_nonperiodic(&p->wall[3 * (bot + 1) + (top + 1)], gp_zsz[2], dz, top == 1, bot == 1, top == 0, bot == 0);
+                if (rc) { pdo_pade6stagg_destroy(p); return rc; }
+            }
+    } else if (scheme == PDO_SCHEME_CD06) {
         int rc = pdo_cd06stagg_init_periodic(&p->der, gp_zsz[2], dz);  // derPeriodic%init(gp%zsz(3), dz)  :79-80
         if (rc) { delete p; return rc; }
     } else {
@@ -518,13 +545,13 @@ int pdo_pade6stagg_init(pdo_pade6stagg_t* h, const int gp_zsz[3], const int sp_z
 int pdo_pade6stagg_destroy(pdo_pade6stagg_t p) {
     if (!p) return 0;
     pdo_cd06stagg_destroy(p->der);
+    for (int i = 0; i < 9; ++i) pdo_cd06stagg_destroy(p->wall[i]);
     delete p;
     return 0;
 }
 #define PDO_PADE_FN(name, target, which)                                                                                   \
     int name(pdo_pade6stagg_t p, const double* in, double* out, int is_complex, int bot, int top, void* st) {              \
-        (void)bot; (void)top;                                                                                              \
-        return pade_apply(p, target, which, in, out, is_complex, st);                                                      \
+        return pade_apply(p, target, which, in, out, is_complex, bot, top, st);                                            \
     }
 PDO_PADE_FN(pdo_pade6stagg_ddz_C2E, pdo_cd06stagg_ddz_C2E, 1)
 PDO_PADE_FN(pdo_pade6stagg_ddz_E2C, pdo_cd06stagg_ddz_E2C, 0)
@@ -709,6 +736,8 @@ int pdo_padepoisson_init(pdo_padepoisson_t* h, double dx, double dy, double dz, 
     if (!h || !sp || !spE || !derivZ) return fail(PDO_E_BADARG, "null argument");
     *h = nullptr;
     if (spE->nz != sp->nz + 1 || spE->nx != sp->nx || spE->ny != sp->ny) return fail(PDO_E_BADARG, "spE must be the (nx, ny, nz+1) edge type of sp");
+    if (!derivZ->periodic)
+        return fail(PDO_E_UNSUPPORTED, "padepoisson: only the PeriodicInZ solver is built; derivZ was initialised with isPeriodic = .false.");
     // PadePoisson.F90:215-218 — the two decompositions must split x and y identically in the z-pencil
     if (sp->si.zst[0] != spE->si.zst[0] || sp->si.zst[1] != spE->si.zst[1])
         return fail(423, "Failed at initializing Padepoisson. sp_gp and sp_gpE have different x and y starts in z-decomp");

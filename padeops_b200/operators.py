@@ -153,18 +153,23 @@ class gaussian(_Filter):
 
 
 class cd06stagg:
-    """Periodic staggered CD06 in z.  Cells: n planes; edges: n+1 planes (plane n+1 == plane 1)."""
+    """Staggered CD06 in z, periodic or with walls.  Cells: n planes; edges: n+1 planes (periodic: plane n+1 == plane 1)."""
 
     def __init__(self):
         self._h = C.c_void_p(None)
         self.n = 0
 
-    def init(self, nx, dx):
-        """The periodic overload init(nx, dx) (cd06stagg.F90:92, 170-195).  Raises code 21 for nx <= 4
-        where the reference calls GracefulExit."""
+    def init(self, nx, dx, isTopEven=None, isBotEven=None, isTopSided=False, isBotSided=False):
+        """The generic init: init(nx, dx) is the periodic overload (cd06stagg.F90:92, 170-195); with isTopEven / isBotEven it is
+        init_nonperiodic (:197-231): the field is even / odd about that wall, or the wall takes the one-sided closure.
+        Raises code 21 for nx <= 4 where the reference calls GracefulExit."""
         self.destroy()
         self.n = nx
-        check(lib().pdo_cd06stagg_init_periodic(C.byref(self._h), int(nx), float(dx)))
+        if isTopEven is None and isBotEven is None:
+            check(lib().pdo_cd06stagg_init_periodic(C.byref(self._h), int(nx), float(dx)))
+        else:
+            check(lib().pdo_cd06stagg_init_nonperiodic(C.byref(self._h), int(nx), float(dx), int(bool(isTopEven)), int(bool(isBotEven)),
+                                                       int(bool(isTopSided)), int(bool(isBotSided))))
 
     def destroy(self):
         if self._h:
@@ -205,6 +210,13 @@ class cd06stagg:
 
     def d2dz2_E2E(self, fE, d2fE=None, stream=None):
         return self._call("d2dz2_E2E", fE, d2fE, self.n + 1, self.n + 1, stream)
+
+    def ddz_C2C(self, fC, dfC=None, stream=None):
+        """non-periodic handles only (the reference builds TriD1_C2C / TriD1_E2E in init_nonperiodic)"""
+        return self._call("ddz_C2C", fC, dfC, self.n, self.n, stream)
+
+    def ddz_E2E(self, fE, dfE=None, stream=None):
+        return self._call("ddz_E2E", fE, dfE, self.n + 1, self.n + 1, stream)
 
 
 def _i3(v):

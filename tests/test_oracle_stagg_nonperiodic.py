@@ -111,3 +111,27 @@ def test_complex_fields_take_the_same_path():
     assert np.allclose(got.real, st.ddz_E2C(fr), rtol=0, atol=1e-15) and np.allclose(got.imag, st.ddz_E2C(fi), rtol=0, atol=1e-15)
     with pytest.raises(ValueError):
         CD06StaggNP(4, 0.1, True, True)
+
+
+def test_pade6stagg_wall_dispatch_of_the_oracle():
+    """Pade6stagg with isPeriodic = .false. (PadeDerOps.F90:92-110, 185-205): (bot, top) picks one of derOO .. derSS; the second
+    derivatives have no one-sided variant and return zero there; a field even about both walls differentiates like its
+    periodic even extension."""
+    from oracle import igrid_oracle as IG
+    n, dz = 32, 1.0 / 32
+    ops = IG.Pade6stagg(n, dz, scheme=1, isPeriodic=False)
+    zc, ze = (np.arange(n) + 0.5) * dz, np.arange(n + 1) * dz
+    fC = np.cos(3 * np.pi * zc)[:, None, None] * np.ones((1, 2, 3))      # even about z = 0 and z = 1
+    dE = ops.ddz_C2E(fC, 1, 1)
+    assert np.abs(dE + 3 * np.pi * np.sin(3 * np.pi * ze)[:, None, None]).max() < 1e-5
+    assert not np.any(ops.d2dz2_C2C(fC, 0, 1)) and not np.any(ops.d2dz2_E2E(np.zeros((n + 1, 2, 3)) + 1.0, 1, 0))
+    assert not np.any(ops.ddz_C2E(fC, 2, 1))
+    errs = []
+    for m in (32, 64):                                                   # no symmetry assumed: 3rd-order boundary rows
+        o2 = IG.Pade6stagg(m, 1.0 / m, scheme=1, isPeriodic=False)
+        zc2, ze2 = (np.arange(m) + 0.5) / m, np.arange(m + 1) / m
+        one_sided = o2.ddz_C2E(np.cos(3 * np.pi * zc2)[:, None, None] * np.ones((1, 2, 3)), 0, 0)
+        errs.append(np.abs(one_sided + 3 * np.pi * np.sin(3 * np.pi * ze2)[:, None, None]).max())
+    assert errs[0] < 0.3 and errs[1] < errs[0] / 6.0
+    with pytest.raises(AssertionError):
+        IG.Pade6stagg(n, dz, scheme=2, isPeriodic=False)
