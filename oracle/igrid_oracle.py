@@ -294,12 +294,100 @@ class PadePoisson:
         return uhat, vhat, what, div
 
 
+def splitmix64_uniform(seed, count):
+    """`count` doubles in [0, 1) from SplitMix64 seeded with `seed`.  Fortran's random_seed(put = seed) / random_number, which
+    utilities/random.F90:154-174 uses, is compiler-specific (gfortran: xoshiro256**, ifort: L'Ecuyer) — no drop-in can
+    reproduce its stream, so the GPU library and this oracle share this documented generator instead, and both accept the
+    reference's own draw through set_wavenumbers."""
+    mask = (1 << 64) - 1
+    state = int(seed) & mask
+    out = np.empty(count)
+    for i in range(count):
+        state = (state + 0x9E3779B97F4A7C15) & mask
+        z = state
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & mask
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & mask
+        z ^= z >> 31
+        out[i] = (z >> 11) * (1.0 / 9007199254740992.0)
+    return out
+
+
+class HITForcing:
+    """forcingmod::HIT_shell_forcing (incompressible/forcingIsotropic.F90:45-314): every time step Nwaves integer wavenumber
+    triplets are drawn on the shell kmin <= |k| <= kmax; each forced mode receives EpsAmplitude / Nwaves of energy injection
+    rate, f_hat(mode) += normfact * Eps / (|u_hat|^2 + |v_hat|^2 + |w_hat|^2 + 1e-14) / Nwaves * conjg(u_hat(mode)), in the
+    fully (x, y, z)-transformed space; w lives on edges and is shifted to cells and back with the spectral type's tables."""
+
+    def __init__(self, spectC, kmin=2.0, kmax=10.0, Nwaves=20, EpsAmplitude=0.1, tidStart=0, RandSeedToAdd=0):
+        self.spectC = spectC
+        self.kmin, self.kmax, self.Nwaves, self.Eps = kmin, kmax, int(Nwaves), EpsAmplitude
+        self.seed0 = tidStart + RandSeedToAdd                        # :86
+        self.update_seeds()
+        self.normfact = (float(spectC.nx) * float(spectC.ny) * float(spectC.nz)) ** 2    # :89
+        self.wave_x = self.wave_y = self.wave_z = None
+
+    def update_seeds(self):                                          # :122-128
+        self.seed0 = abs(self.seed0 + 2223345)
+        self.seed1 = abs(self.seed0 + 1423246)
+        self.seed2 = abs(self.seed0 + 8723446)
+        self.seed3 = abs(self.seed0 + 3423444)
+
+    @staticmethod
+    def _uniform(n, left, right, seed):                              # unrand1R, random.F90:154-174
+        a = splitmix64_uniform(seed, n)
+        a = (right - left) * a
+        return a + left
+
+    def wavenumbers_from_samples(self, kabs, zeta, theta):           # :137-147
+        t = kabs * np.sqrt(1 - zeta ** 2) * np.cos(theta)
+        self.wave_x = np.ceil(np.abs(t)).astype(int)
+        t = kabs * np.sqrt(1 - zeta ** 2) * np.sin(theta)
+        self.wave_y = np.ceil(np.abs(t)).astype(int)
+        t = kabs * zeta
+        self.wave_z = np.ceil(np.abs(t)).astype(int)
+
+    def pick_random_wavenumbers(self):                               # :131-149
+        n = self.Nwaves
+        self.wavenumbers_from_samples(self._uniform(n, self.kmin, self.kmax, self.seed1), self._uniform(n, -1.0, 1.0, self.seed2),
+                                      self._uniform(n, 0.0, 2.0 * np.pi, self.seed3))
+
+    def set_wavenumbers(self, wx, wy, wz):
+        self.wave_x, self.wave_y, self.wave_z = (np.asarray(a, dtype=int) for a in (wx, wy, wz))
+
+    def getRHS_HITforcing(self, urhs, vrhs, wrhs, uhat_xy, vhat_xy, what_xy, newTimestep):     # :254-311
+        sp = self.spectC
+        nz = sp.nz
+        if newTimestep:
+            self.pick_random_wavenumbers()
+            self.update_seeds()
+        uh = sp.take_fft1d_z2z(uhat_xy)
+        vh = sp.take_fft1d_z2z(vhat_xy)
+        wh = sp.shiftz_E2C(sp.take_fft1d_z2z(what_xy[:nz]))
+        fx, fy, fz = (np.zeros_like(uh) for _ in range(3))
+        ny = sp.ny
+        for kx, ky, kz in zip(self.wave_x, self.wave_y, self.wave_z):       # compute_forcing / embed_forcing_mode :203-251
+            if not (0 <= kx < sp.nxh and 0 <= ky < ny):
+                continue                                                      # "not on this processor" for every rank
+            den = abs(uh[kz, ky, kx]) ** 2 + abs(vh[kz, ky, kx]) ** 2 + abs(wh[kz, ky, kx]) ** 2 + 1.0e-14
+            fac = self.normfact * self.Eps / den / float(self.Nwaves)
+            fx[kz, ky, kx] += fac * np.conj(uh[kz, ky, kx])
+            fy[kz, ky, kx] += fac * np.conj(vh[kz, ky, kx])
+            fz[kz, ky, kx] += fac * np.conj(wh[kz, ky, kx])
+        urhs = urhs + sp.take_ifft1d_z2z(fx)
+        vrhs = vrhs + sp.take_ifft1d_z2z(fy)
+        fzE = sp.take_ifft1d_z2z(sp.shiftz_C2E(fz))
+        wrhs = wrhs + np.concatenate([fzE, fzE[:1]], axis=0)
+        return urhs, vrhs, wrhs
+
+
 class IGrid:
     """igrid, periodic in x, y, z; NumericalSchemeVert = 1 (CD06) or 2 (Fourier collocation in z), AdvectionTerm = 1 (skew-symmetric) or 0 (rotational), no SGS / forcing /
     Coriolis / stratification; viscous unless isInviscid.  u, v: (nz, ny, nx); w: (nz+1, ny, nx) with plane nz == plane 0."""
 
     def __init__(self, nx, ny, nz, Lx, Ly, Lz, Re, u, v, w, isInviscid=False, dealiasFact=2.0 / 3.0, t_DivergenceCheck=10,
-                 TimeSteppingScheme=1, use_d2dz2_C2C=True, AdvectionTerm=1, NumericalSchemeVert=1):
+                 TimeSteppingScheme=1, use_d2dz2_C2C=True, AdvectionTerm=1, NumericalSchemeVert=1, HITForcing_=None):
+        """HITForcing_: None, or the &HIT_Forcing namelist as a dict (kmin, kmax, Nwaves, EpsAmplitude, RandSeedToAdd) for
+        useHITForcing = .true. (igrid.F90:940-944, 1908-1910)."""
         assert AdvectionTerm in (0, 1)      # 0 rotational (igrid.F90:1527-1555), 1 skew-symmetric (:1572-1679)
         assert NumericalSchemeVert in (1, 2)  # 1 cd06, 2 fourierColl (PadeDerOps.F90:16-18)
         self.AdvectionTerm = AdvectionTerm
@@ -313,6 +401,8 @@ class IGrid:
         self.ops = Pade6stagg(nz, self.dz, NumericalSchemeVert)
         self.poiss = PadePoisson(self.dx, self.dy, self.dz, self.spectC, self.spectE, self.ops)
         self.step, self.tsim = 0, 0.0
+        self.newTimeStep = True
+        self.hitforce = HITForcing(self.spectC, tidStart=self.step, **HITForcing_) if HITForcing_ is not None else None
         # igrid.F90:625-655
         self.uhat = self.spectC.fft(u)
         self.vhat = self.spectC.fft(v)
@@ -427,6 +517,9 @@ class IGrid:
             u_rhs = u_rhs + oneByRe * (-self.spectC.kabs_sq * self.uhat + self.d2udz2hatC)
             v_rhs = v_rhs + oneByRe * (-self.spectC.kabs_sq * self.vhat + self.d2vdz2hatC)
             w_rhs = w_rhs + oneByRe * (-self.spectE.kabs_sq * self.what + self.d2wdz2hatE)
+        if self.hitforce is not None:       # Step 8 (:1907-1910)
+            u_rhs, v_rhs, w_rhs = self.hitforce.getRHS_HITforcing(u_rhs, v_rhs, w_rhs, self.uhat, self.vhat, self.what, self.newTimeStep)
+        self.newTimeStep = False            # :1128, 1203: cleared after the first stage's right-hand side
         return u_rhs, v_rhs, w_rhs
 
     # ---- igrid.F90:1961-1990
@@ -445,6 +538,7 @@ class IGrid:
         (self.TVD_RK3 if self.scheme == 1 else self.SSP_RK45)(dt)
         self.step += 1       # wrapup_timestep
         self.tsim += dt
+        self.newTimeStep = True   # :2075
 
     # ---- igrid.F90:1105-1173
     def TVD_RK3(self, dt):

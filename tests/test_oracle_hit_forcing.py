@@ -1,0 +1,101 @@
+"""Pins the oracle's restatement of HIT_shell_forcing (incompressible/forcingIsotropic.F90:45-314): seed arithmetic, the
+sample -> integer-wavenumber map, and the forcing itself — a forced mode receives, in physical space, the plane wave
+(normfact Eps / den / Nwaves / (nx ny nz)) conj(u_hat) e^{i k.x} projected the way the 2-D real transform projects it; the energy
+injection rate sum(u . f) per forced (non-degenerate) mode is Eps / Nwaves x (|u_hat|^2 / den) by construction."""
+import numpy as np
+import pytest
+
+from oracle import igrid_oracle as IG
+
+
+def _setup(nx=16, ny=12, nz=16, **kw):
+    d = [2 * np.pi / n for n in (nx, ny, nz)]
+    sp = IG.Spectral(nx, ny, nz, *d, init_periodicInZ=True)
+    return sp, IG.HITForcing(sp, **kw), d
+
+
+def test_seed_arithmetic_and_splitmix():
+    sp, f, _ = _setup(tidStart=5, RandSeedToAdd=2)
+    assert (f.seed0, f.seed1, f.seed2, f.seed3) == (7 + 2223345, 7 + 2223345 + 1423246, 7 + 2223345 + 8723446, 7 + 2223345 + 3423444)
+    f.update_seeds()
+    assert f.seed0 == 7 + 2 * 2223345 and f.seed1 == f.seed0 + 1423246
+    # SplitMix64 known answers (seed 0: the published first outputs of the reference implementation)
+    mask = (1 << 64) - 1
+    first = [0xE220A8397B1DCDAF, 0x6E789E6AA1B965F4, 0x06C45D188009454F]
+    u = IG.splitmix64_uniform(0, 3)
+    assert [int(x * 9007199254740992.0) for x in u] == [v >> 11 for v in first]
+    assert np.all((u >= 0) & (u < 1)) and mask
+
+
+def test_wavenumbers_from_samples_and_shell():
+    sp, f, _ = _setup(kmin=4.0, kmax=5.0, Nwaves=200)
+    f.wavenumbers_from_samples(np.array([4.5, 5.0]), np.array([0.0, -1.0]), np.array([0.0, 1.0]))
+    assert f.wave_x.tolist() == [5, 1] or f.wave_x.tolist() == [5, 0]      # ceiling(|4.5|) = 5; sqrt(1 - 1) = 0 -> ceiling(0) = 0
+    assert f.wave_x.tolist() == [5, 0] and f.wave_y.tolist() == [0, 0] and f.wave_z.tolist() == [0, 5]
+    f.pick_random_wavenumbers()
+    k = np.sqrt(f.wave_x ** 2.0 + f.wave_y ** 2.0 + f.wave_z ** 2.0)
+    assert np.all(k >= 4.0 - 1e-12) and np.all(k <= 5.0 + np.sqrt(3.0))   # ceiling moves each component up by < 1
+    assert f.wave_x.min() >= 0 and len(set(zip(f.wave_x, f.wave_y, f.wave_z))) > 20
+
+
+def test_forcing_of_a_single_mode_is_the_scaled_conjugate_wave():
+    nx, ny, nz = 16, 12, 16
+    sp, f, d = _setup(nx, ny, nz, Nwaves=1, EpsAmplitude=0.3)
+    rng = np.random.default_rng(2)
+    u, v = rng.standard_normal((nz, ny, nx)), rng.standard_normal((nz, ny, nx))
+    w = rng.standard_normal((nz + 1, ny, nx)); w[nz] = w[0]
+    spE = IG.Spectral(nx, ny, nz + 1, *d)
+    uh, vh, wh = sp.fft(u), sp.fft(v), spE.fft(w)
+    kx, ky, kz = 2, 3, 4
+    f.set_wavenumbers([kx], [ky], [kz])
+    zero = np.zeros_like(uh)
+    zeroE = np.zeros_like(wh)
+    ur, vr, wr = f.getRHS_HITforcing(zero, zero, zeroE, uh, vh, wh, False)
+    U = np.fft.fft(uh, axis=0)[kz, ky, kx]
+    V = np.fft.fft(vh, axis=0)[kz, ky, kx]
+    W = (np.fft.fft(wh[:nz], axis=0) * sp.E2Cshift[:, None, None])[kz, ky, kx]
+    den = abs(U) ** 2 + abs(V) ** 2 + abs(W) ** 2 + 1e-14
+    fac = (nx * ny * nz) ** 2 * 0.3 / den
+    z = np.arange(nz)
+    wave = np.exp(2j * np.pi * kz * z / nz) / nz
+    exp_u = np.zeros_like(uh); exp_u[:, ky, kx] = fac * np.conj(U) * wave
+    assert np.abs(ur - exp_u).max() < 1e-12 * np.abs(exp_u).max()
+    exp_v = np.zeros_like(uh); exp_v[:, ky, kx] = fac * np.conj(V) * wave
+    assert np.abs(vr - exp_v).max() < 1e-12 * np.abs(exp_v).max()
+    exp_w = np.zeros_like(wh)
+    exp_w[:nz, ky, kx] = fac * np.conj(W) * sp.C2Eshift[kz] * wave
+    exp_w[nz] = exp_w[0]
+    assert np.abs(wr - exp_w).max() < 1e-12 * np.abs(exp_w).max()
+    # duplicates add up; modes outside the half-spectrum are skipped
+    f.Nwaves = 3
+    f.set_wavenumbers([kx, kx, nx], [ky, ky, 1], [kz, kz, 1])
+    ur3, _, _ = f.getRHS_HITforcing(zero, zero, zeroE, uh, vh, wh, False)
+    assert np.abs(ur3 - (2.0 / 3.0) * exp_u).max() < 1e-12 * np.abs(exp_u).max()
+
+
+@pytest.mark.parametrize("scheme", [1, 2])
+def test_forced_taylor_green_gains_energy_and_stays_solenoidal(scheme):
+    """igrid with useHITForcing: the forcing enters populate_rhs after the viscous term (igrid.F90:1907-1910), wavenumbers are
+    redrawn once per time step; the projected field stays divergence-free and, at high Re, its energy grows."""
+    n = 16
+    L = 2 * np.pi
+    rng = np.random.default_rng(7)          # energy in every mode of the forced shell (an empty mode has den = 1e-14: unbounded forcing)
+    u, v = 0.3 * rng.standard_normal((n, n, n)), 0.3 * rng.standard_normal((n, n, n))
+    w = 0.3 * rng.standard_normal((n + 1, n, n))
+    w[n] = w[0]
+    hit = dict(kmin=1.0, kmax=2.5, Nwaves=12, EpsAmplitude=0.5, RandSeedToAdd=3)
+    g = IG.IGrid(n, n, n, L, L, L, 1.0e4, u, v, w, TimeSteppingScheme=scheme, HITForcing_=hit)
+    g0 = IG.IGrid(n, n, n, L, L, L, 1.0e4, u, v, w, TimeSteppingScheme=scheme)
+    e_start = (g.u ** 2 + g.v ** 2 + g.wC ** 2).mean()
+    waves = []
+    for _ in range(3):
+        g.timeAdvance(0.01)
+        g0.timeAdvance(0.01)
+        waves.append(tuple(g.hitforce.wave_x))
+    assert len(set(waves)) == 3                                       # a new draw every step, none inside the RK stages
+    e_forced, e_free = (g.u ** 2 + g.v ** 2 + g.wC ** 2).mean(), (g0.u ** 2 + g0.v ** 2 + g0.wC ** 2).mean()
+    assert e_forced > e_free and e_forced > e_start
+    rate = 0.5 * (e_forced - e_free) / 0.03                           # kinetic energy per unit time: of the order of EpsAmplitude
+    assert 0.5 * 0.5 < rate < 6.0 * 0.5
+    _, _, _, div = g.poiss.DivergenceCheck(g.uhat, g.vhat, g.what)
+    assert np.abs(div).max() < 1e-11
