@@ -355,12 +355,32 @@ int pdo_igrid_get_state(pdo_igrid_t h, int* step, double* tsim);
    dumpRestartFile :2763-2803  ->  <dir>/RESTART_Run<rid>_{u,v,w}.<step, 6 digits> + RESTART_Run<rid>_info.<step> (tsim, g15.5)
    readRestartFile :2719-2761 + init's :589-591, 625-655  ->  step = tid, tsim from the info file, fields projected, state rebuilt
    dumpFullField   :2806-2823  ->  <dir>/Run<rid>_<label>_t<step>.out for field ids 0 u, 1 v, 2 w, 3 wC, 4 uE, 5 vE, 6 divergence */
+/* useHITForcing = .true. (igrid.F90:940-944, 1907-1910): call once after init; the forcing is added to every right-hand side
+   after the viscous term, with a new draw at the first stage of every time step (tidStart = the current step) */
+int pdo_igrid_enable_hit_forcing(pdo_igrid_t h, double kmin, double kmax, int nwaves, double eps_amplitude, int rand_seed_to_add);
 int pdo_igrid_dump_restart(pdo_igrid_t h, const char* outputdir, int run_id);
 int pdo_igrid_read_restart(pdo_igrid_t h, const char* inputdir, int run_id, int tid);
 int pdo_igrid_dump_full_field(pdo_igrid_t h, int which, const char* label4, const char* outputdir, int run_id);
 /* compute_deltaT with useCFL (igrid.F90:1372-1396) */
 int pdo_igrid_compute_delta_t(pdo_igrid_t h, double cfl, double* dt, void* stream);
 int pdo_igrid_max_divergence(pdo_igrid_t h, double* max_div, void* stream);   /* printDivergence + p_maxval(|div|) */
+
+/* ---- forcingmod::HIT_shell_forcing  (incompressible/forcingIsotropic.F90:45-314) ---------------
+   Every time step Nwaves integer wavenumber triplets are drawn on the shell kmin <= |k| <= kmax; each forced mode gets
+   f_hat += normfact EpsAmplitude / (|u_hat|^2 + |v_hat|^2 + |w_hat|^2 + 1e-14) / Nwaves * conjg(u_hat) in the fully transformed
+   space, w shifted edges -> cells and back.  Evaluated as a direct DFT of the Nwaves forced columns and plane-wave updates of
+   the right-hand sides instead of the reference's six whole-field z transforms.  The &HIT_Forcing namelist enters as arguments.
+   The random draw: Fortran's random_number is compiler-specific, the library uses SplitMix64 on the reference's seed
+   arithmetic (:122-128); set_wavenumbers injects the reference's own draw for an A/B run.  Arrays: DEVICE pointers, complex
+   y-pencils of the cell (u, v) and edge (w) spectral decompositions. */
+typedef struct pdo_hit_forcing_s* pdo_hit_forcing_t;
+int pdo_hit_forcing_init(pdo_hit_forcing_t* h, pdo_spectral_t spectC, pdo_spectral_t spectE, double kmin, double kmax, int nwaves,
+                         double eps_amplitude, int tid_start, int rand_seed_to_add);
+int pdo_hit_forcing_destroy(pdo_hit_forcing_t h);
+int pdo_hit_forcing_set_wavenumbers(pdo_hit_forcing_t h, const int* wave_x, const int* wave_y, const int* wave_z);
+int pdo_hit_forcing_get_wavenumbers(pdo_hit_forcing_t h, int* wave_x, int* wave_y, int* wave_z);
+int pdo_hit_forcing_get_rhs(pdo_hit_forcing_t h, double* urhs_xy, double* vrhs_xy, double* wrhs_xy, const double* uhat_xy,
+                            const double* vhat_xy, const double* what_xy, int new_timestep, void* stream);   /* :254-311 */
 
 /* ---- igrid_Operators_Periodic::Ops_Periodic  (incompressible/igrid_operators_periodic.F90:13-161) ----------------
    Fourier operators on x-pencil fields of a triply periodic box (the reference's post-processing programs use it):

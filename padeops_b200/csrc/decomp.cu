@@ -576,6 +576,12 @@ void comm_info(int* rank, int* nproc, int* p2p) {
     *rank = g_comm.rank; *nproc = g_comm.nproc; *p2p = (g_comm.inited && g_comm.p2p) ? 1 : 0;
 }
 void comm_deregister_buffer(void* p) { if (p) pdo_comm_deregister_buffer(p); }
+// in-place sum of a small device array over all ranks, stream-ordered (no-op on one rank)
+int comm_allreduce_sum(double* dev, int count, cudaStream_t st) {
+    if (g_comm.nproc == 1 || count <= 0) return 0;
+    PDO_NCCL(ncclAllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, g_comm.comm, st));
+    return 0;
+}
 void comm_register_buffer_quiet(void* p, size_t bytes) { if (g_comm.inited && g_comm.nproc > 1 && g_comm.p2p) sym_register(p, bytes); }
 // used by spectral.cu: transposes on device pointers without the host-pointer probe
 int decomp_transpose_device(pdo_decomp_t h, int dir, const double* src, double* dst, int w, cudaStream_t st) {

@@ -15,6 +15,7 @@ void comm_deregister_buffer(void* p);  // local; call before freeing a registere
 int comm_sym_alloc(size_t bytes, void** local, void** peers);
 void comm_sym_free(void* p);
 void comm_info(int* rank, int* nproc, int* p2p);
+int comm_allreduce_sum(double* dev, int count, cudaStream_t st);   // in place, stream-ordered
 void decomp_grid(pdo_decomp_t h, int* p_row, int* p_col, int* c1, int* c2);
 int fft3d_forward_xy(pdo_fft3d_t f, const double* in_real_x, double2* out_cplx_y, cudaStream_t st);
 int fft3d_backward_yx(pdo_fft3d_t f, const double2* in_cplx_y, double* out_real_x, bool set_oddball, cudaStream_t st);

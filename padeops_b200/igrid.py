@@ -115,6 +115,42 @@ class spectral:
         return a
 
 
+class HIT_shell_forcing:
+    """forcingmod::HIT_shell_forcing (forcingIsotropic.F90:45-314); the &HIT_Forcing namelist enters as keyword arguments.
+    Right-hand sides and fields: device tensors, complex y-pencils of the cell / edge spectral decompositions."""
+
+    def __init__(self):
+        self._h = C.c_void_p(None)
+        self.Nwaves = 0
+
+    def init(self, spectC, spectE, kmin=2.0, kmax=10.0, Nwaves=20, EpsAmplitude=0.1, tidStart=0, RandSeedToAdd=0):
+        self.destroy()
+        self._keep = (spectC, spectE)
+        self.Nwaves = int(Nwaves)
+        check(lib().pdo_hit_forcing_init(C.byref(self._h), spectC._h, spectE._h, float(kmin), float(kmax), int(Nwaves), float(EpsAmplitude),
+                                         int(tidStart), int(RandSeedToAdd)))
+        return 0
+
+    def destroy(self):
+        if self._h:
+            lib().pdo_hit_forcing_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def set_wavenumbers(self, wave_x, wave_y, wave_z):
+        a = [(C.c_int * self.Nwaves)(*[int(v) for v in w]) for w in (wave_x, wave_y, wave_z)]
+        check(lib().pdo_hit_forcing_set_wavenumbers(self._h, *a))
+
+    def get_wavenumbers(self):
+        a = [(C.c_int * self.Nwaves)() for _ in range(3)]
+        check(lib().pdo_hit_forcing_get_wavenumbers(self._h, *a))
+        return tuple(list(x) for x in a)
+
+    def getRHS_HITforcing(self, urhs_xy, vrhs_xy, wrhs_xy, uhat_xy, vhat_xy, what_xy, newTimestep, stream=None):
+        check(lib().pdo_hit_forcing_get_rhs(self._h, ptr(urhs_xy), ptr(vrhs_xy), ptr(wrhs_xy), ptr(uhat_xy), ptr(vhat_xy), ptr(what_xy),
+                                            int(bool(newTimestep)), stream_ptr(stream)))
+        return urhs_xy, vrhs_xy, wrhs_xy
+
+
 class Ops_Periodic:
     """igrid_Operators_Periodic::Ops_Periodic (igrid_operators_periodic.F90:13-161).  Real arrays: x-pencils of the physical
     decomposition; `gp` enters as its process grid (p_row, p_col; 0, 0 = 1 x nproc).  The I/O procedures (ReadField3D /
@@ -353,3 +389,7 @@ class igrid:
     def dumpFullField(self, name, label, OutputDir, runID=1):
         assert len(label) == 4, "label is character(len=4) in the reference"
         check(lib().pdo_igrid_dump_full_field(self._h, self.FIELDS[name], label.encode(), str(OutputDir).encode(), int(runID)))
+
+    def enableHITForcing(self, kmin=2.0, kmax=10.0, Nwaves=20, EpsAmplitude=0.1, RandSeedToAdd=0):
+        """useHITForcing = .true. with the &HIT_Forcing namelist (igrid.F90:940-944); call once after init"""
+        check(lib().pdo_igrid_enable_hit_forcing(self._h, float(kmin), float(kmax), int(Nwaves), float(EpsAmplitude), int(RandSeedToAdd)))

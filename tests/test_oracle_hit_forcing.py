@@ -99,3 +99,72 @@ def test_forced_taylor_green_gains_energy_and_stays_solenoidal(scheme):
     assert 0.5 * 0.5 < rate < 6.0 * 0.5
     _, _, _, div = g.poiss.DivergenceCheck(g.uhat, g.vhat, g.what)
     assert np.abs(div).max() < 1e-11
+
+
+@pytest.mark.parametrize("tid,add,updates", [(0, 0, 0), (5, 2, 3), (1000, 17, 1200)])
+def test_product_draw_matches_the_oracle(tid, add, updates):
+    """The PRODUCT's host side of the forcing (seed arithmetic, SplitMix64, the sample -> wavenumber map) through a host-only
+    hook, against the oracle: the two must pick the same modes at every step of a long run."""
+    import ctypes as C
+    import padeops_b200 as pdo
+    n = 40
+    sp, f, _ = _setup(kmin=3.0, kmax=7.5, Nwaves=n, tidStart=tid, RandSeedToAdd=add)
+    for _ in range(updates):
+        f.update_seeds()
+    f.pick_random_wavenumbers()
+    seeds = (C.c_longlong * 4)()
+    w = [(C.c_int * n)() for _ in range(3)]
+    assert pdo.lib().pdo_debug_hit_draw(3.0, 7.5, n, tid, add, updates, seeds, *w) == 0
+    assert list(seeds) == [f.seed0, f.seed1, f.seed2, f.seed3]
+    assert list(w[0]) == f.wave_x.tolist() and list(w[1]) == f.wave_y.tolist() and list(w[2]) == f.wave_z.tolist()
+
+
+def test_sparse_dft_algorithm_of_the_kernels_equals_the_fft_formulation():
+    """csrc/igrid.cu evaluates the forcing without whole-field transforms: (U, V, Wraw) = direct DFT of the forced columns
+    (partial sums per z-slab, summed over ranks), then every wave adds its plane wave to the right-hand sides.  Re-enacted here
+    in numpy, two z-slabs with the uneven cell / edge plane split of a 1 x 2 grid, against the oracle's FFT formulation."""
+    nx, ny, nz = 12, 10, 16
+    sp, f, d = _setup(nx, ny, nz, Nwaves=6, EpsAmplitude=0.2)
+    spE = IG.Spectral(nx, ny, nz + 1, *d)
+    rng = np.random.default_rng(4)
+    u, v = rng.standard_normal((nz, ny, nx)), rng.standard_normal((nz, ny, nx))
+    w = rng.standard_normal((nz + 1, ny, nx)); w[nz] = w[0]
+    uh, vh, wh = sp.fft(u), sp.fft(v), spE.fft(w)
+    waves = ([2, 3, 2, 0, 6, 40], [1, 9, 1, 0, 3, 1], [4, 0, 4, 7, 15, 1])      # a duplicate, ky in the upper half, one mode off the grid
+    f.set_wavenumbers(*waves)
+    r0 = [rng.standard_normal(uh.shape) + 1j * rng.standard_normal(uh.shape) for _ in range(2)] + \
+         [rng.standard_normal(wh.shape) + 1j * rng.standard_normal(wh.shape)]
+    want = f.getRHS_HITforcing(r0[0], r0[1], r0[2], uh, vh, wh, False)
+    # --- the kernels' algorithm ---
+    nxh = nx // 2 + 1
+    slabsC = [(0, 8), (8, 16)]
+    slabsE = [(0, 8), (8, 17)]
+    n = len(waves[0])
+    part = np.zeros((n, 3), dtype=np.complex128)
+    for (c0, c1), (e0, e1) in zip(slabsC, slabsE):                  # hit_reduce_kernel on each rank, then the allreduce
+        for i, (kx, ky, kz) in enumerate(zip(*waves)):
+            if not (0 <= kx < nxh and 0 <= ky < ny and 0 <= kz < nz):
+                continue
+            zc = np.arange(c0, c1)
+            ph = np.exp(-2j * np.pi * ((kz * zc) % nz) / nz)
+            part[i, 0] += (uh[c0:c1, ky, kx] * ph).sum()
+            part[i, 1] += (vh[c0:c1, ky, kx] * ph).sum()
+            ze = np.arange(e0, min(e1, nz))
+            part[i, 2] += (wh[e0:min(e1, nz), ky, kx] * np.exp(-2j * np.pi * ((kz * ze) % nz) / nz)).sum()
+    got = [a.copy() for a in r0]
+    normfact = (nx * ny * nz) ** 2.0
+    for i, (kx, ky, kz) in enumerate(zip(*waves)):                  # hit_apply_kernel: waves one after another, every plane
+        if not (0 <= kx < nxh and 0 <= ky < ny and 0 <= kz < nz):
+            continue
+        U, V, W = part[i, 0], part[i, 1], part[i, 2] * sp.E2Cshift[kz]
+        den = abs(U) ** 2 + abs(V) ** 2 + abs(W) ** 2 + 1e-14
+        fac = normfact * 0.2 / den / n
+        zc = np.arange(nz)
+        ph = np.exp(2j * np.pi * ((kz * zc) % nz) / nz)
+        got[0][:, ky, kx] += fac * np.conj(U) / nz * ph
+        got[1][:, ky, kx] += fac * np.conj(V) / nz * ph
+        ze = np.arange(nz + 1)
+        ze[nz] = 0
+        got[2][:, ky, kx] += fac * np.conj(W) * sp.C2Eshift[kz] / nz * np.exp(2j * np.pi * ((kz * ze) % nz) / nz)
+    for a, b in zip(got, want):
+        assert np.abs(a - b).max() < 1e-12 * np.abs(b).max()
