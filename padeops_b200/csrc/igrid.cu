@@ -905,7 +905,7 @@ void hit_update_seeds(pdo_hit_forcing_s* f) {   // :122-128
     f->seed3 = ab(f->seed0 + 3423444);
 }
 // `count` doubles in [0, 1): SplitMix64.  Fortran's random_seed(put) / random_number (utilities/random.F90:154-174) is
-// compiler-specific, so the stream is this documented generator (shared with the oracle); the reference's own draw can be
+// compiler-specific, so the stream is this documented generator; the reference's own draw can be
 // injected with pdo_hit_forcing_set_wavenumbers.
 void hit_uniform(double* out, int count, double left, double right, long long seed) {
     unsigned long long state = (unsigned long long)seed;
