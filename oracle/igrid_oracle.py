@@ -380,14 +380,120 @@ class HITForcing:
         return urhs, vrhs, wrhs
 
 
+class SGS:
+    """sgs_igrid (incompressible/sgsmod_igrid.F90:156-251 + sgs_models/{smagorinsky, sigma, AMD, eddyViscosity}.F90) for the
+    periodic box: eddy-viscosity models 0 Smagorinsky, 1 sigma, 2 AMD with a global constant — no wall damping, no dynamic
+    procedure, no wall model (the HIT deck's settings: SGSModelID = 2, DynamicProcedureType = 0, WallModelType = 0).
+    duidxj arrays: lists of the nine gradients dudx, dudy, dudz, dvdx, ... in the reference's order, on cells (C) and edges (E)."""
+
+    def __init__(self, spectC, spectE, ops, SGSModelID=2, Csgs=0.17, explicitCalcEdgeEddyViscosity=False):
+        self.spectC, self.spectE, self.ops = spectC, spectE, ops
+        self.mid, self.explicitE = SGSModelID, explicitCalcEdgeEddyViscosity
+        dx, dy, dz = spectC.dx, spectC.dy, spectC.dz
+        deltaLES = (1.5 * dx * 1.5 * dy * 1.5 * dz) ** (1.0 / 3.0)            # isPeriodic branch (smagorinsky.F90:17, sigma.F90:15)
+        if SGSModelID in (0, 1):
+            self.cmodel_global = (Csgs * deltaLES) ** 2
+        elif SGSModelID == 2:                                               # AMD.F90:1-14
+            poincare = 1.0 / np.sqrt(10.0) if ops.scheme == 1 else 1.0 / np.sqrt(12.0)     # PadeDerOps.F90:1018-1031
+            self.camd_x = Csgs * dx * np.sqrt(1.0 / 12.0)
+            self.camd_y = Csgs * dy * np.sqrt(1.0 / 12.0)
+            self.camd_z = Csgs * dz * poincare
+            self.cmodel_global = 1.0
+        else:
+            raise ValueError("Incorrect choice for SGS model ID. (213)")
+
+    @staticmethod
+    def get_Sij(d):                                                          # eddyViscosity.F90:1-24: S11 S12 S13 S22 S23 S33
+        return [d[0], 0.5 * (d[1] + d[3]), 0.5 * (d[2] + d[6]), d[4], 0.5 * (d[5] + d[7]), d[8]]
+
+    def kernel(self, d, S):
+        if self.mid == 0:                                                    # smagorinsky.F90:44-66
+            t = S[0] * S[0]
+            t = t + 2.0 * (S[1] * S[1])
+            t = t + 2.0 * (S[2] * S[2])
+            t = t + (S[3] * S[3])
+            t = t + 2.0 * (S[4] * S[4])
+            t = t + (S[5] * S[5])
+            return np.sqrt(2.0 * t)
+        if self.mid == 1:                                                    # sigma.F90:31-98
+            G11 = d[0] * d[0] + d[3] * d[3] + d[6] * d[6]
+            G12 = d[0] * d[1] + d[3] * d[4] + d[6] * d[7]
+            G13 = d[0] * d[2] + d[3] * d[5] + d[6] * d[8]
+            G22 = d[1] * d[1] + d[4] * d[4] + d[7] * d[7]
+            G23 = d[1] * d[2] + d[4] * d[5] + d[7] * d[8]
+            G33 = d[2] * d[2] + d[5] * d[5] + d[8] * d[8]
+            I1 = G11 + G22 + G33
+            I1sq = I1 * I1
+            I1cu = I1sq * I1
+            I2 = -G11 * G11 - G22 * G22 - G33 * G33
+            I2 = I2 - 2.0 * G12 * G12 - 2.0 * G13 * G13
+            I2 = I2 - 2.0 * G23 * G23
+            I2 = I2 + I1sq
+            I2 = 0.5 * I2
+            I3 = G11 * (G22 * G33 - G23 * G23)
+            I3 = I3 + G12 * (G13 * G23 - G12 * G33)
+            I3 = I3 + G13 * (G12 * G23 - G22 * G13)
+            alpha1 = np.maximum(I1sq / 9.0 - I2 / 3.0, 0.0)
+            alpha2 = I1cu / 27.0 - I1 * I2 / 6.0 + I3 / 2.0
+            a1s = np.sqrt(alpha1)
+            t = alpha2 / (alpha1 * a1s + 1.0e-13)
+            t = np.arccos(np.maximum(np.minimum(t, 1.0), -1.0))
+            alpha3 = (1.0 / 3.0) * t
+            s1sq = np.maximum(I1 / 3.0 + 2.0 * a1s * np.cos(alpha3), 0.0)
+            s1 = np.sqrt(s1sq)
+            s2 = np.sqrt(np.maximum((-2.0) * a1s * np.cos(np.pi / 3.0 + alpha3) + I1 / 3.0, 0.0))
+            s3 = np.sqrt(np.maximum((-2.0) * a1s * np.cos(np.pi / 3.0 - alpha3) + I1 / 3.0, 0.0))
+            return s3 * (s1 - s2) * (s2 - s3) / (s1sq + 1.0e-15)
+        cx, cy, cz = self.camd_x, self.camd_y, self.camd_z                  # AMD.F90:24-72
+        row = lambda a, b: (d[a] * cx) * (d[b] * cx) + (d[a + 1] * cy) * (d[b + 1] * cy) + (d[a + 2] * cz) * (d[b + 2] * cz)
+        num = row(0, 0) * S[0]
+        num = num + row(3, 3) * S[3]
+        num = num + row(6, 6) * S[5]
+        num = num + 2.0 * row(0, 3) * S[1]
+        num = num + 2.0 * row(0, 6) * S[2]
+        num = num + 2.0 * row(3, 6) * S[4]
+        den = sum(x * x for x in d)
+        return np.maximum(-num / (den + 1.0e-32), 0.0)
+
+    def getTauSGS(self, duidxjC, duidxjE):                                   # sgsmod_igrid.F90:156-203
+        C, E = self.spectC, self.spectE
+        SC, SE = self.get_Sij(duidxjC), self.get_Sij(duidxjE)
+        nuC = self.cmodel_global * self.kernel(duidxjC, SC)
+        if self.explicitE:
+            nuE = self.cmodel_global * self.kernel(duidxjE, SE)
+        else:                                                                # interpolate_eddy_viscosity(.true.): eddyViscosity.F90:97-113
+            nuE = self.ops.interpz_C2E(nuC)
+            nuE = np.where(nuE < 0.0, 0.0, nuE)
+        self.nu_sgs_C, self.nu_sgs_E = nuC, nuE
+        return (-2.0 * nuC * SC[0], -2.0 * nuC * SC[1], -2.0 * nuE * SE[2], -2.0 * nuC * SC[3], -2.0 * nuE * SE[4], -2.0 * nuC * SC[5])
+
+    def getRHS_SGS(self, urhs, vrhs, wrhs, duidxjC, duidxjE):                # :206-268
+        C, E, ops = self.spectC, self.spectE, self.ops
+        t11, t12, t13, t22, t23, t33 = self.getTauSGS(duidxjC, duidxjE)
+        urhs = urhs - C.mTimes_ik1(C.fft(t11))
+        vrhs = vrhs - C.mTimes_ik2(C.fft(t22))
+        wrhs = wrhs - ops.ddz_C2E(C.fft(t33))
+        c = C.fft(t12)
+        vrhs = vrhs - C.mTimes_ik1(c)
+        urhs = urhs - C.mTimes_ik2(c)
+        c = E.fft(t13)
+        urhs = urhs - ops.ddz_E2C(c)
+        wrhs = wrhs - E.mTimes_ik1(c)
+        c = E.fft(t23)
+        vrhs = vrhs - ops.ddz_E2C(c)
+        wrhs = wrhs - E.mTimes_ik2(c)
+        return urhs, vrhs, wrhs
+
+
 class IGrid:
     """igrid, periodic in x, y, z; NumericalSchemeVert = 1 (CD06) or 2 (Fourier collocation in z), AdvectionTerm = 1 (skew-symmetric) or 0 (rotational), no SGS / forcing /
     Coriolis / stratification; viscous unless isInviscid.  u, v: (nz, ny, nx); w: (nz+1, ny, nx) with plane nz == plane 0."""
 
     def __init__(self, nx, ny, nz, Lx, Ly, Lz, Re, u, v, w, isInviscid=False, dealiasFact=2.0 / 3.0, t_DivergenceCheck=10,
-                 TimeSteppingScheme=1, use_d2dz2_C2C=True, AdvectionTerm=1, NumericalSchemeVert=1, HITForcing_=None):
+                 TimeSteppingScheme=1, use_d2dz2_C2C=True, AdvectionTerm=1, NumericalSchemeVert=1, HITForcing_=None, SGS_=None):
         """HITForcing_: None, or the &HIT_Forcing namelist as a dict (kmin, kmax, Nwaves, EpsAmplitude, RandSeedToAdd) for
-        useHITForcing = .true. (igrid.F90:940-944, 1908-1910)."""
+        useHITForcing = .true. (igrid.F90:940-944, 1908-1910).  SGS_: None, or the &SGS_MODEL namelist entries in scope as a dict
+        (SGSModelID, Csgs, explicitCalcEdgeEddyViscosity) for useSGS = .true. (:1866-1871)."""
         assert AdvectionTerm in (0, 1)      # 0 rotational (igrid.F90:1527-1555), 1 skew-symmetric (:1572-1679)
         assert NumericalSchemeVert in (1, 2)  # 1 cd06, 2 fourierColl (PadeDerOps.F90:16-18)
         self.AdvectionTerm = AdvectionTerm
@@ -403,6 +509,7 @@ class IGrid:
         self.step, self.tsim = 0, 0.0
         self.newTimeStep = True
         self.hitforce = HITForcing(self.spectC, tidStart=self.step, **HITForcing_) if HITForcing_ is not None else None
+        self.sgsmodel = SGS(self.spectC, self.spectE, self.ops, **SGS_) if SGS_ is not None else None
         # igrid.F90:625-655
         self.uhat = self.spectC.fft(u)
         self.vhat = self.spectC.fft(v)
@@ -517,6 +624,11 @@ class IGrid:
             u_rhs = u_rhs + oneByRe * (-self.spectC.kabs_sq * self.uhat + self.d2udz2hatC)
             v_rhs = v_rhs + oneByRe * (-self.spectC.kabs_sq * self.vhat + self.d2vdz2hatC)
             w_rhs = w_rhs + oneByRe * (-self.spectE.kabs_sq * self.what + self.d2wdz2hatE)
+        if self.sgsmodel is not None:       # Step 6 (:1866-1871)
+            d = self.duidxj
+            dC = [d["dudx"], d["dudy"], d["dudzC"], d["dvdx"], d["dvdy"], d["dvdzC"], d["dwdxC"], d["dwdyC"], d["dwdz"]]
+            dE = [d["dudxE"], d["dudyE"], d["dudz"], d["dvdxE"], d["dvdyE"], d["dvdz"], d["dwdx"], d["dwdy"], d["dwdzE"]]
+            u_rhs, v_rhs, w_rhs = self.sgsmodel.getRHS_SGS(u_rhs, v_rhs, w_rhs, dC, dE)
         if self.hitforce is not None:       # Step 8 (:1907-1910)
             u_rhs, v_rhs, w_rhs = self.hitforce.getRHS_HITforcing(u_rhs, v_rhs, w_rhs, self.uhat, self.vhat, self.what, self.newTimeStep)
         self.newTimeStep = False            # :1128, 1203: cleared after the first stage's right-hand side

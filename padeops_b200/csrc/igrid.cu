@@ -890,7 +890,7 @@ struct pdo_hit_forcing_s {
     int nwaves = 0;
     long long seed0 = 0, seed1 = 0, seed2 = 0, seed3 = 0;
     std::vector<int> waves;      // wave_x[n], wave_y[n], wave_z[n]
-    bool have_waves = false;
+    bool have_waves = false, waves_dirty = false;   // dirty: the host copy is newer than d_waves
     int* d_waves = nullptr;
     double2* d_part = nullptr;   // (U, V, Wraw) per wave
 };
@@ -932,6 +932,7 @@ void hit_waves_from_samples(pdo_hit_forcing_s* f, const double* kabs, const doub
         f->waves[2 * n + i] = (int)std::ceil(std::fabs(t));
     }
     f->have_waves = true;
+    f->waves_dirty = true;
 }
 
 struct HitGeom {
@@ -1029,9 +1030,10 @@ int hit_get_rhs_dev(pdo_hit_forcing_s* f, double2* ur, double2* vr, double2* wr,
         hit_update_seeds(f);
     }
     if (!f->have_waves) return fail(PDO_E_BADARG, "HIT forcing: no wavenumbers yet (newTimestep was never true and none were set)");
-    // the previous right-hand side's kernels may still be reading d_waves: the copy is stream-ordered from pageable memory
-    PDO_CUDA(cudaMemcpyAsync(f->d_waves, f->waves.data(), sizeof(int) * 3 * n, cudaMemcpyHostToDevice, st));
-    PDO_CUDA(cudaStreamSynchronize(st));   // f->waves may be redrawn by the next call before the copy engine has read it
+    if (f->waves_dirty) {   // once per time step: stream-ordered copy from pageable memory (staged before the call returns)
+        PDO_CUDA(cudaMemcpyAsync(f->d_waves, f->waves.data(), sizeof(int) * 3 * n, cudaMemcpyHostToDevice, st));
+        f->waves_dirty = false;
+    }
     if (int rc = spectral_ztables(f->spC)) return rc;
     pdo_spectral_s *C = f->spC, *E = f->spE;
     HitGeom g;
@@ -1092,6 +1094,7 @@ int pdo_hit_forcing_set_wavenumbers(pdo_hit_forcing_t f, const int* wave_x, cons
     const int n = f->nwaves;
     for (int i = 0; i < n; ++i) { f->waves[i] = wave_x[i]; f->waves[n + i] = wave_y[i]; f->waves[2 * n + i] = wave_z[i]; }
     f->have_waves = true;
+    f->waves_dirty = true;
     return 0;
 }
 int pdo_hit_forcing_get_wavenumbers(pdo_hit_forcing_t f, int* wave_x, int* wave_y, int* wave_z) {
