@@ -355,6 +355,12 @@ int pdo_igrid_get_state(pdo_igrid_t h, int* step, double* tsim);
    dumpRestartFile :2763-2803  ->  <dir>/RESTART_Run<rid>_{u,v,w}.<step, 6 digits> + RESTART_Run<rid>_info.<step> (tsim, g15.5)
    readRestartFile :2719-2761 + init's :589-591, 625-655  ->  step = tid, tsim from the info file, fields projected, state rebuilt
    dumpFullField   :2806-2823  ->  <dir>/Run<rid>_<label>_t<step>.out for field ids 0 u, 1 v, 2 w, 3 wC, 4 uE, 5 vE, 6 divergence */
+/* useSGS = .true. (igrid.F90:1866-1871; sgsmod_igrid.F90:156-268, sgs_models/{smagorinsky, sigma, AMD, eddyViscosity}.F90): the
+   eddy-viscosity models with a global constant on the periodic box — SGSModelID 0 Smagorinsky, 1 sigma, 2 AMD; Csgs;
+   explicitCalcEdgeEddyViscosity (0: nu is interpolated cells -> edges and clipped at zero).  Wall damping, the dynamic
+   procedure and wall models are out of scope.  The handle must have been initialised with compute_all_gradients = 1.
+   Bad model id -> 213.  The term enters every right-hand side after the viscous term. */
+int pdo_igrid_enable_sgs(pdo_igrid_t h, int sgs_model_id, double csgs, int explicit_calc_edge_eddy_viscosity);
 /* useHITForcing = .true. (igrid.F90:940-944, 1907-1910): call once after init; the forcing is added to every right-hand side
    after the viscous term, with a new draw at the first stage of every time step (tidStart = the current step) */
 int pdo_igrid_enable_hit_forcing(pdo_igrid_t h, double kmin, double kmax, int nwaves, double eps_amplitude, int rand_seed_to_add);

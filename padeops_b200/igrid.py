@@ -393,3 +393,7 @@ class igrid:
     def enableHITForcing(self, kmin=2.0, kmax=10.0, Nwaves=20, EpsAmplitude=0.1, RandSeedToAdd=0):
         """useHITForcing = .true. with the &HIT_Forcing namelist (igrid.F90:940-944); call once after init"""
         check(lib().pdo_igrid_enable_hit_forcing(self._h, float(kmin), float(kmax), int(Nwaves), float(EpsAmplitude), int(RandSeedToAdd)))
+
+    def enableSGS(self, SGSModelID=2, Csgs=0.17, explicitCalcEdgeEddyViscosity=False):
+        """useSGS = .true. with the &SGS_MODEL entries in scope (igrid.F90:1866-1871); init with computeAllGradients=True"""
+        check(lib().pdo_igrid_enable_sgs(self._h, int(SGSModelID), float(Csgs), int(bool(explicitCalcEdgeEddyViscosity))))

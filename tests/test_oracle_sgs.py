@@ -79,3 +79,25 @@ def test_sgs_term_drains_resolved_energy(mid, Csgs, explicitE):
     g0.timeAdvance(0.01)
     e = lambda q: (q.u ** 2 + q.v ** 2 + q.wC ** 2).mean()
     assert e(g) < e(g0)
+
+
+@pytest.mark.parametrize("mid,Csgs", [(0, 0.17), (1, 1.5), (2, 1.67)])
+def test_product_point_kernels_match_the_oracle(mid, Csgs):
+    """The PRODUCT's pointwise SGS kernels (csrc/sgs_kernels.cuh, the __host__ __device__ code the CUDA kernels run) through a
+    host-only hook, against the oracle on random velocity-gradient tensors, degenerate ones included."""
+    import ctypes as C
+    import padeops_b200 as pdo
+    m, _ = _model(mid, Csgs)
+    rng = np.random.default_rng(mid)
+    cases = [rng.standard_normal(9) * s for s in (1.0, 1e-3, 50.0) for _ in range(40)]
+    cases += [np.zeros(9), np.array([0, 0, 2.0, 0, 0, 0, 0, 0, 0]), np.array([0, -1.5, 0, 1.5, 0, 0, 0, 0, 0]), np.array([0.7, 0, 0, 0, 0.7, 0, 0, 0, 0.7])]
+    cx, cy, cz = (m.camd_x, m.camd_y, m.camd_z) if mid == 2 else (0.0, 0.0, 0.0)
+    for d in cases:
+        g = [np.full((1,), v) for v in d]
+        S = m.get_Sij(g)
+        want = m.cmodel_global * m.kernel(g, S)[0]
+        nu, S6 = C.c_double(0.0), np.zeros(6)
+        dd = np.ascontiguousarray(d, dtype=np.float64)
+        assert pdo.lib().pdo_debug_sgs_point(mid, m.cmodel_global, cx, cy, cz, C.c_void_p(dd.ctypes.data), C.byref(nu), C.c_void_p(S6.ctypes.data)) == 0
+        assert np.allclose(S6, [s[0] for s in S], rtol=0, atol=0)
+        assert abs(nu.value - want) <= 1e-12 * max(abs(want), 1e-3 * np.abs(d).max() ** (1 if mid == 0 else 1)), (mid, d, nu.value, want)
