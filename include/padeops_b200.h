@@ -403,6 +403,10 @@ int pdo_ops_periodic_ddz(pdo_ops_periodic_t h, const double* f, double* dfdz, vo
 int pdo_ops_periodic_ddz_cmplx2cmplx(pdo_ops_periodic_t h, double* fhat_cplx_y, void* stream);        /* :137-145 */
 int pdo_ops_periodic_solve_poisson(pdo_ops_periodic_t h, const double* rhs, double* p, void* stream); /* _oop :70-76; p == rhs: _ip :78-84 */
 int pdo_ops_periodic_dealias_field(pdo_ops_periodic_t h, double* f, void* stream);                    /* :56-62 */
+/* WriteField3D :189-205 / ReadField3D :162-187: "<dir>/Run<runID, 2 digits>_<label, 4 chars>_t<tidx, 6 digits>.out" in the
+   decomp_2d_io format; a missing file on read -> 321 */
+int pdo_ops_periodic_write_field3d(pdo_ops_periodic_t h, const double* field, const char* label4, int tidx, int run_id, const char* outputdir);
+int pdo_ops_periodic_read_field3d(pdo_ops_periodic_t h, double* field, const char* label4, int tidx, int run_id, const char* inputdir);
 
 #ifdef __cplusplus
 }

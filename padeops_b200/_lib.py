@@ -162,6 +162,8 @@ _PROTOS.update({
     "pdo_ops_periodic_ddz_cmplx2cmplx": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "pdo_ops_periodic_solve_poisson": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_void_p]),
     "pdo_ops_periodic_dealias_field": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
+    "pdo_ops_periodic_write_field3d": (C.c_int, [C.c_void_p, c_dp, C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
+    "pdo_ops_periodic_read_field3d": (C.c_int, [C.c_void_p, c_dp, C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
     "pdo_spectral_get_tables": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "pdo_pade6stagg_init": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_double, C.c_int, C.c_int]),
     "pdo_pade6stagg_init2": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_double, C.c_int, C.c_int, C.c_void_p]),

@@ -2068,6 +2068,20 @@ int pdo_ops_periodic_ddz_cmplx2cmplx(pdo_ops_periodic_t o, double* fhat, void* s
         return decomp_transpose_device(spec, 3, (const double*)s->ctmpz, (double*)w, 2, st);
     });
 }
+/* ReadField3D :162-187 / WriteField3D :189-205: "<dir>/Run<runID>_<label>_t<tidx>.out", x-pencil of gp through decomp_2d_io */
+static std::string ops_periodic_fname(const char* dir, const char* label4, int tidx, int run_id) {
+    char name[64];
+    std::snprintf(name, sizeof(name), "Run%02d_%.4s_t%06d.out", run_id, label4, tidx);   // "(A3,I2.2,A1,A4,A2,I6.6,A4)"
+    return std::string(dir ? dir : ".") + "/" + name;
+}
+int pdo_ops_periodic_write_field3d(pdo_ops_periodic_t o, const double* field, const char* label4, int tidx, int run_id, const char* outputdir) {
+    if (!o || !field || !label4) return fail(PDO_E_BADARG, "null argument");
+    return pdo_decomp_write_one(fft3d_phys_decomp(o->spect->ft), 1, field, 1, ops_periodic_fname(outputdir, label4, tidx, run_id).c_str());
+}
+int pdo_ops_periodic_read_field3d(pdo_ops_periodic_t o, double* field, const char* label4, int tidx, int run_id, const char* inputdir) {
+    if (!o || !field || !label4) return fail(PDO_E_BADARG, "null argument");
+    return pdo_decomp_read_one(fft3d_phys_decomp(o->spect->ft), 1, field, 1, ops_periodic_fname(inputdir, label4, tidx, run_id).c_str());   // missing file -> 321
+}
 /* SolvePoisson_oop :70-76 (p != rhs), SolvePoisson_ip :78-84 (p == rhs) */
 int pdo_ops_periodic_solve_poisson(pdo_ops_periodic_t o, const double* rhs, double* p, void* stream) {
     if (!o) return fail(PDO_E_BADARG, "null handle");

@@ -153,8 +153,7 @@ class HIT_shell_forcing:
 
 class Ops_Periodic:
     """igrid_Operators_Periodic::Ops_Periodic (igrid_operators_periodic.F90:13-161).  Real arrays: x-pencils of the physical
-    decomposition; `gp` enters as its process grid (p_row, p_col; 0, 0 = 1 x nproc).  The I/O procedures (ReadField3D /
-    WriteField3D) are outside the hot path."""
+    decomposition; `gp` enters as its process grid (p_row, p_col; 0, 0 = 1 x nproc)."""
 
     def __init__(self):
         self._h = C.c_void_p(None)
@@ -210,6 +209,17 @@ class Ops_Periodic:
     def dealiasField(self, f, stream=None):
         check(lib().pdo_ops_periodic_dealias_field(self._h, ptr(f), stream_ptr(stream)))
         return f
+
+    def WriteField3D(self, field, label, tidx, runID, newOutputDir=None):
+        assert len(label) == 4, "label is character(len=4) in the reference"
+        check(lib().pdo_ops_periodic_write_field3d(self._h, ptr(field), label.encode(), int(tidx), int(runID),
+                                                   str(newOutputDir if newOutputDir is not None else self.outputdir).encode()))
+
+    def ReadField3D(self, field, label, tidx, runID, newinputdir=None):
+        assert len(label) == 4
+        check(lib().pdo_ops_periodic_read_field3d(self._h, ptr(field), label.encode(), int(tidx), int(runID),
+                                                  str(newinputdir if newinputdir is not None else self.inputdir).encode()))
+        return field
 
     def allocate3Dfield(self, device="cuda"):
         import torch

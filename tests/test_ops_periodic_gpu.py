@@ -111,3 +111,20 @@ def test_pade6stagg_real_fourier_collocation(pdo, oracle, shape):
         assert got.shape == ref.shape and _rel(got, ref) < TOL, name
     der.destroy()
     spC.destroy()
+
+
+def test_field_files_round_trip(pdo, tmp_path):
+    """WriteField3D / ReadField3D (igrid_operators_periodic.F90:162-205): Run<rid>_<label>_t<tidx>.out, flat global Fortran order"""
+    nx, ny, nz = 16, 12, 8
+    d = [2 * np.pi / n for n in (nx, ny, nz)]
+    op = pdo.Ops_Periodic()
+    op.init(nx, ny, nz, *d, InputDir=str(tmp_path), OutputDir=str(tmp_path))
+    f = broadband((nz, ny, nx), seed=1)
+    op.WriteField3D(_dev(f), "uVel", 12, 3)
+    assert (tmp_path / "Run03_uVel_t000012.out").read_bytes() == f.tobytes()
+    back = op.ReadField3D(op.allocate3Dfield(), "uVel", 12, 3)
+    assert np.array_equal(back.cpu().numpy(), f)
+    with pytest.raises(pdo.PadeOpsError) as e:
+        op.ReadField3D(op.allocate3Dfield(), "vVel", 12, 3)
+    assert e.value.code == 321
+    op.destroy()
