@@ -304,11 +304,18 @@ int pdo_pade6stagg_d2dz2_C2C(pdo_pade6stagg_t h, const double* in, double* out, 
 int pdo_pade6stagg_d2dz2_E2E(pdo_pade6stagg_t h, const double* in, double* out, int is_complex, int bot, int top, void* stream);
 int pdo_pade6stagg_get_modified_wavenumbers(pdo_pade6stagg_t h, const double* k, double* kp, int n);   /* :997-1053 */
 
-/* ---- PadePoissonMod::padepoisson, PeriodicInZ = .true.  (incompressible/PadePoisson.F90) ------ */
+/* ---- PadePoissonMod::padepoisson  (incompressible/PadePoisson.F90) ----------------------------- */
 typedef struct pdo_padepoisson_s* pdo_padepoisson_t;
 /* padepoisson%init(dx,dy,dz, sp, spE, computeStokesPressure=F, Lz, storePressure, gpC, derivZ, PeriodicInZ=T)   :130-180, 76-128 */
 int pdo_padepoisson_init(pdo_padepoisson_t* h, double dx, double dy, double dz, pdo_spectral_t sp, pdo_spectral_t spE,
                          pdo_pade6stagg_t derivZ);
+/* the same with the reference's PeriodicInZ argument.  PeriodicInZ = .false., computeStokesPressure = .false. (:180-230, 459-623):
+   walls at both ends of z — PressureProjection extends the horizontal divergence evenly and w oddly to 2 nz planes, solves in
+   z-Fourier space with the z scheme's modified wavenumber and the half-cell shifts, and leaves w = 0 on both walls;
+   DivergenceCheck uses derivZ%ddz_E2C(-1, -1).  derivZ must have been initialised with the same periodicity; the pressure getters
+   are periodic-only (PDO_E_UNSUPPORTED otherwise). */
+int pdo_padepoisson_init2(pdo_padepoisson_t* h, double dx, double dy, double dz, pdo_spectral_t sp, pdo_spectral_t spE,
+                          pdo_pade6stagg_t derivZ, int periodic_in_z);
 int pdo_padepoisson_destroy(pdo_padepoisson_t h);
 /* uhat, vhat: complex y-pencils of sp; what: complex y-pencil of spE (nz+1 planes); all updated in place   :386-432 */
 int pdo_padepoisson_pressure_projection(pdo_padepoisson_t h, double* uhat, double* vhat, double* what, void* stream);

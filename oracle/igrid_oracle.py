@@ -231,13 +231,28 @@ class Pade6stagg:
 
 
 class PadePoisson:
-    """PadePoissonMod::padepoisson with PeriodicInZ = .true."""
+    """PadePoissonMod::padepoisson.  PeriodicInZ = .true.: the z-periodic solver (PadePoisson.F90:76-128, 386-432, ...).
+    PeriodicInZ = .false., computeStokesPressure = .false. (:130-230, 434-624): walls at z = 0 and z = Lz; the divergence is
+    extended evenly and w oddly to 2 nz points, transformed in z, solved with the z-scheme's modified wavenumber carrying the
+    half-cell shifts (k3modcm / k3modcp), and cut back; w is zero on both walls afterwards."""
 
-    def __init__(self, dx, dy, dz, spC, spE, derivZ):
+    def __init__(self, dx, dy, dz, spC, spE, derivZ, PeriodicInZ=True):
         self.sp, self.spE, self.derivZ = spC, spE, derivZ
+        self.PeriodicInZ = PeriodicInZ
         nx, ny, nz = spC.nx, spC.ny, spC.nz
         k1 = O.wavenums(nx, dx)[: spC.nxh]
         k2 = O.wavenums(ny, dy)
+        if not PeriodicInZ:
+            nzExt = 2 * nz
+            k3 = O.wavenums(nzExt, dz)
+            k3mod = derivZ.getModifiedWavenumbers(k3)
+            tfm, tfp = np.exp(imi * (-dz / 2.0) * k3), np.exp(imi * (dz / 2.0) * k3)
+            self.k3modcm, self.k3modcp = k3mod * tfm, k3mod * tfp
+            kradsq = k1[None, None, :] ** 2 + k2[None, :, None] ** 2 + k3mod[:, None, None] ** 2
+            with np.errstate(divide="ignore"):
+                self.kradsq_inv = np.where(kradsq <= 1e-14, 0.0, 1.0 / kradsq)
+            self.mfact = 1.0 / float(nzExt)
+            return
         k3mod = derivZ.getModifiedWavenumbers(O.wavenums(nz, dz))
         kradsq = k1[None, None, :] ** 2 + k2[None, :, None] ** 2 + k3mod[:, None, None] ** 2
         with np.errstate(divide="ignore"):
@@ -258,7 +273,34 @@ class PadePoisson:
         f2d = f2d * self.mfact
         return f2d, w2
 
+    def _wall_projection(self, uhat, vhat, what):
+        """PadePoisson.F90:459-623 (computeStokesPressure = .false.)"""
+        sp = self.sp
+        nz = sp.nz
+        f2dy = sp.k1 * uhat
+        f2dy = f2dy + sp.k2 * vhat
+        f2d = -f2dy.imag + 1j * f2dy.real
+        w2 = what
+        f2dext = np.concatenate([f2d[::-1], f2d], axis=0)                      # Step 3: even extension, 2 nz planes
+        wext = np.empty_like(f2dext)
+        wext[0:nz - 1] = -w2[nz - 1:0:-1]                                      # wext(kk-1) = -w2(nzG-kk+2), kk = 2..nzG
+        wext[nz - 1:2 * nz] = w2                                               # wext(nzG+kk-1) = w2(kk), kk = 1..nzG+1
+        f2dext = np.fft.fft(f2dext, axis=0)
+        wext = np.fft.fft(wext, axis=0)
+        f2dext = f2dext + imi * self.k3modcm[:, None, None] * wext             # Step 5
+        f2dext = -f2dext * self.kradsq_inv
+        wext = wext - imi * self.k3modcp[:, None, None] * f2dext               # Step 6
+        f2dext = self.mfact * (np.fft.ifft(f2dext, axis=0) * (2 * nz))         # Step 7
+        wext = (np.fft.ifft(wext, axis=0) * (2 * nz)) * self.mfact
+        f2d = f2dext[nz:]
+        w2 = wext[nz - 1:].copy()
+        w2[0] = 0.0
+        w2[nz] = 0.0
+        return uhat - imi * sp.k1 * f2d, vhat - imi * sp.k2 * f2d, w2
+
     def PressureProjection(self, uhat, vhat, what):
+        if not self.PeriodicInZ:
+            return self._wall_projection(uhat, vhat, what)
         sp = self.sp
         f2d, w2 = self._solve(uhat, vhat, what)
         dwdz = self.derivZ.ddz_C2E(f2d)
@@ -279,7 +321,7 @@ class PadePoisson:
 
     def divergence(self, uhat, vhat, what):
         sp = self.sp
-        f2dy = self.derivZ.ddz_E2C(what)
+        f2dy = self.derivZ.ddz_E2C(what) if self.PeriodicInZ else self.derivZ.ddz_E2C(what, -1, -1)    # :1188
         f2dy = f2dy + imi * sp.k1 * uhat + imi * sp.k2 * vhat
         return sp.ifft(f2dy)
 

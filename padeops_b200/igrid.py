@@ -277,11 +277,11 @@ class padepoisson:
         self._h = C.c_void_p(None)
 
     def init(self, dx, dy, dz, sp, spE, computeStokesPressure=False, Lz=None, storePressure=True, gpC=None, derivZ=None, PeriodicInZ=True):
-        if not PeriodicInZ or computeStokesPressure:
-            raise NotImplementedError("only the PeriodicInZ branch is in scope")
+        if computeStokesPressure:
+            raise NotImplementedError("computeStokesPressure = .true. is out of scope")
         self._keep = (sp, spE, derivZ)
         self._sp = sp
-        check(lib().pdo_padepoisson_init(C.byref(self._h), float(dx), float(dy), float(dz), sp._h, spE._h, derivZ._h))
+        check(lib().pdo_padepoisson_init2(C.byref(self._h), float(dx), float(dy), float(dz), sp._h, spE._h, derivZ._h, int(bool(PeriodicInZ))))
         return 0
 
     def destroy(self):

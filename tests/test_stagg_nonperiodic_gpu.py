@@ -88,3 +88,37 @@ def test_pade6stagg_wall_dispatch(pdo, oracle):
         pdo.Pade6stagg().init(spC.physdecomp, spC.spectdecomp, dz=d[2], scheme=2, isPeriodic=False, spectC=spC)
     assert e.value.code == 323
     der.destroy()
+
+
+@pytest.mark.parametrize("shape", [(16, 12, 24), (12, 16, 10)])
+def test_wall_bounded_projection(pdo, oracle, shape):
+    """padepoisson PressureProjection / DivergenceCheck with PeriodicInZ = .false. (PadePoisson.F90:459-623, 1165-1244)"""
+    from oracle import igrid_oracle as IG
+    nx, ny, nz = shape
+    d = [2 * np.pi / nx, 2 * np.pi / ny, 1.0 / nz]
+    spC, spE = pdo.spectral(), pdo.spectral()
+    spC.init("x", nx, ny, nz, *d, fixOddball=False, init_periodicInZ=False)
+    spE.init("x", nx, ny, nz + 1, *d, fixOddball=False, init_periodicInZ=False)
+    der = pdo.Pade6stagg()
+    der.init(spC.physdecomp, spC.spectdecomp, dz=d[2], scheme=1, isPeriodic=False)
+    po = pdo.padepoisson()
+    po.init(*d, spC, spE, derivZ=der, PeriodicInZ=False)
+    rC, rE = IG.Spectral(nx, ny, nz, *d), IG.Spectral(nx, ny, nz + 1, *d)
+    rP = IG.PadePoisson(*d, rC, rE, IG.Pade6stagg(nz, d[2], 1, isPeriodic=False), PeriodicInZ=False)
+    rng = np.random.default_rng(nz)
+    u, v = rng.standard_normal((nz, ny, nx)), rng.standard_normal((nz, ny, nx))
+    w = rng.standard_normal((nz + 1, ny, nx))
+    w[0] = 0.0
+    w[nz] = 0.0        # no penetration: the odd extension of w is continuous only then
+    uh, vh, wh = rC.fft(u), rC.fft(v), rE.fft(w)
+    want = rP.PressureProjection(uh, vh, wh)
+    du, dv, dw = _dev(uh), _dev(vh), _dev(wh)
+    po.PressureProjection(du, dv, dw)
+    for got, ref in zip((du, dv, dw), want):
+        assert _rel(got.cpu().numpy(), ref) < TOL
+    div, _ = po.DivergenceCheck(du, dv, dw)
+    assert np.abs(div.cpu().numpy()).max() < 1e-11 * np.abs(rP.divergence(uh, vh, wh)).max()
+    with pytest.raises(pdo.PadeOpsError):
+        po.getPressure(du, dv, dw)                                               # periodic-only
+    with pytest.raises(pdo.PadeOpsError):
+        pdo.padepoisson().init(*d, spC, spE, derivZ=der, PeriodicInZ=True)      # periodicity of derivZ and the solver must agree
