@@ -532,10 +532,14 @@ class IGrid:
     Coriolis / stratification; viscous unless isInviscid.  u, v: (nz, ny, nx); w: (nz+1, ny, nx) with plane nz == plane 0."""
 
     def __init__(self, nx, ny, nz, Lx, Ly, Lz, Re, u, v, w, isInviscid=False, dealiasFact=2.0 / 3.0, t_DivergenceCheck=10,
-                 TimeSteppingScheme=1, use_d2dz2_C2C=True, AdvectionTerm=1, NumericalSchemeVert=1, HITForcing_=None, SGS_=None):
+                 TimeSteppingScheme=1, use_d2dz2_C2C=True, AdvectionTerm=1, NumericalSchemeVert=1, HITForcing_=None, SGS_=None,
+                 PeriodicInZ=True, topWall=2, botWall=2):
         """HITForcing_: None, or the &HIT_Forcing namelist as a dict (kmin, kmax, Nwaves, EpsAmplitude, RandSeedToAdd) for
         useHITForcing = .true. (igrid.F90:940-944, 1908-1910).  SGS_: None, or the &SGS_MODEL namelist entries in scope as a dict
-        (SGSModelID, Csgs, explicitCalcEdgeEddyViscosity) for useSGS = .true. (:1866-1871)."""
+        (SGSModelID, Csgs, explicitCalcEdgeEddyViscosity) for useSGS = .true. (:1866-1871).
+        PeriodicInZ = .false. (&BCs namelist): walls at z = 0 and z = Lz, topWall / botWall = 1 no-slip, 2 slip (3, wall model, is
+        out of scope); the stencil codes of get_boundary_conditions_stencil (:5148-5204) then reach every z-operator, the
+        staggered operators use their wall closures, the Poisson solver its even / odd extension, and w is dealiased in 2-D."""
         assert AdvectionTerm in (0, 1)      # 0 rotational (igrid.F90:1527-1555), 1 skew-symmetric (:1572-1679)
         assert NumericalSchemeVert in (1, 2)  # 1 cd06, 2 fourierColl (PadeDerOps.F90:16-18)
         self.AdvectionTerm = AdvectionTerm
@@ -544,10 +548,16 @@ class IGrid:
         self.Re, self.isInviscid = Re, isInviscid
         self.t_DivergenceCheck, self.scheme = t_DivergenceCheck, TimeSteppingScheme
         self.use_d2dz2_C2C = use_d2dz2_C2C
-        self.spectC = Spectral(nx, ny, nz, self.dx, self.dy, self.dz, True, dealiasFact, False)
+        self.PeriodicInZ = PeriodicInZ
+        if not PeriodicInZ:
+            assert NumericalSchemeVert == 1, "If you use Fourier Collocation in Z, the problem must be periodic in Z. (123)"
+            assert HITForcing_ is None and SGS_ is None
+            self.use_d2dz2_C2C = True      # uBC, vBC are +-1 for slip / no-slip walls (:2653, 2671)
+        self.bc = self.get_boundary_conditions_stencil(topWall, botWall)
+        self.spectC = Spectral(nx, ny, nz, self.dx, self.dy, self.dz, PeriodicInZ, dealiasFact, False)
         self.spectE = Spectral(nx, ny, nz + 1, self.dx, self.dy, self.dz, False, dealiasFact, False)
-        self.ops = Pade6stagg(nz, self.dz, NumericalSchemeVert)
-        self.poiss = PadePoisson(self.dx, self.dy, self.dz, self.spectC, self.spectE, self.ops)
+        self.ops = Pade6stagg(nz, self.dz, NumericalSchemeVert, isPeriodic=PeriodicInZ)
+        self.poiss = PadePoisson(self.dx, self.dy, self.dz, self.spectC, self.spectE, self.ops, PeriodicInZ=PeriodicInZ)
         self.step, self.tsim = 0, 0.0
         self.newTimeStep = True
         self.hitforce = HITForcing(self.spectC, tidStart=self.step, **HITForcing_) if HITForcing_ is not None else None
@@ -563,11 +573,26 @@ class IGrid:
         self.interp_PrimitiveVars()
         self.compute_duidxj()
 
+    @staticmethod
+    def get_boundary_conditions_stencil(topWall, botWall):
+        """igrid.F90:5148-5204: (bottom, top) stencil codes per quantity; -1 odd, +1 even, 0 one-sided"""
+        bc = {"w": [-1, -1], "WdWdz": [-1, -1], "WW": [1, 1], "dWdz": [0, 0]}
+        for side, wall in ((0, botWall), (1, topWall)):
+            if wall == 1:      # no-slip: w = 0 and dwdz = 0, so w is extended evenly
+                vals = {"u": -1, "v": -1, "dUdz": 0, "dVdz": 0, "WdUdz": 0, "WdVdz": 0, "UW": 1, "VW": 1, "w": 1, "WdWdz": -1, "WW": 1, "dWdz": -1}
+            elif wall == 2:    # slip
+                vals = {"u": 1, "v": 1, "dUdz": -1, "dVdz": -1, "WdUdz": 1, "WdVdz": 1, "UW": -1, "VW": -1}
+            else:
+                raise ValueError("Invalid choice for wall BCs (423 / 13); the wall model (3) is out of scope")
+            for k, v in vals.items():
+                bc.setdefault(k, [0, 0])[side] = v
+        return {k: tuple(v) for k, v in bc.items()}
+
     # ---- igrid.F90:1020-1037
     def dealiasFields(self):
         self.uhat = self.spectC.dealias(self.uhat)
         self.vhat = self.spectC.dealias(self.vhat)
-        self.what = self.spectC.dealias_edgeField(self.what)
+        self.what = self.spectC.dealias_edgeField(self.what) if self.PeriodicInZ else self.spectE.dealias(self.what)
 
     def _to_physical(self):
         self.u = self.spectC.ifft(self.uhat)
@@ -576,11 +601,11 @@ class IGrid:
 
     # ---- igrid.F90:1423-1447
     def interp_PrimitiveVars(self):
-        self.whatC = self.ops.interpz_E2C(self.what)
+        self.whatC = self.ops.interpz_E2C(self.what, *self.bc["w"])
         self.wC = self.spectC.ifft(self.whatC)
-        self.uEhat = self.ops.interpz_C2E(self.uhat)
+        self.uEhat = self.ops.interpz_C2E(self.uhat, *self.bc["u"])
         self.uE = self.spectE.ifft(self.uEhat)
-        self.vEhat = self.ops.interpz_C2E(self.vhat)
+        self.vEhat = self.ops.interpz_C2E(self.vhat, *self.bc["v"])
         self.vE = self.spectE.ifft(self.vEhat)
 
     # ---- igrid.F90:2553-2683
@@ -593,18 +618,19 @@ class IGrid:
         d["dvdy"] = C.ifft(C.mTimes_ik2(self.vhat)); d["dvdyE"] = E.ifft(E.mTimes_ik2(self.vEhat))
         d["dwdxC"] = C.ifft(C.mTimes_ik1(self.whatC)); d["dwdx"] = E.ifft(E.mTimes_ik1(self.what))
         d["dwdyC"] = C.ifft(C.mTimes_ik2(self.whatC)); d["dwdy"] = E.ifft(E.mTimes_ik2(self.what))
-        dwdzH = ops.ddz_E2C(self.what)
+        dwdzH = ops.ddz_E2C(self.what, *self.bc["w"])
         d["dwdz"] = C.ifft(dwdzH)
-        d["dwdzE"] = E.ifft(ops.interpz_C2E(dwdzH))
+        d["dwdzE"] = E.ifft(ops.interpz_C2E(dwdzH, *self.bc["dWdz"]))
         if not self.isInviscid:
-            self.d2wdz2hatE = ops.d2dz2_E2E(self.what)
+            self.d2wdz2hatE = ops.d2dz2_E2E(self.what, *self.bc["w"])
         for nm, fhat in (("u", self.uhat), ("v", self.vhat)):
-            dEH = ops.ddz_C2E(fhat)
+            bcf, bcd = self.bc[nm], self.bc["d%sdz" % nm.upper()]
+            dEH = ops.ddz_C2E(fhat, *bcf)
             d["d%sdz" % nm] = E.ifft(dEH)
             if not self.isInviscid:
-                d2 = ops.d2dz2_C2C(fhat) if self.use_d2dz2_C2C else ops.ddz_E2C(ops.ddz_C2E(fhat))
+                d2 = ops.d2dz2_C2C(fhat, *bcf) if self.use_d2dz2_C2C else ops.ddz_E2C(ops.ddz_C2E(fhat, *bcf), *bcd)
                 setattr(self, "d2%sdz2hatC" % nm, d2)
-            d["d%sdzC" % nm] = C.ifft(ops.interpz_E2C(dEH))
+            d["d%sdzC" % nm] = C.ifft(ops.interpz_E2C(dEH, *bcd))
         self.duidxj = d
 
     # ---- igrid.F90:1572-1679
@@ -614,28 +640,28 @@ class IGrid:
         T1C = d["dudx"] * u; T2C = d["dudy"] * v; T1C = T1C + T2C
         T1E = d["dudz"] * w
         fT1C = C.fft(T1C); fT1E = E.fft(T1E)
-        u_rhs = ops.interpz_E2C(fT1E) + fT1C
+        u_rhs = ops.interpz_E2C(fT1E, *self.bc["WdUdz"]) + fT1C
         T1C = d["dvdx"] * u; T2C = d["dvdy"] * v; T1C = T1C + T2C
         T1E = d["dvdz"] * w
         fT1C = C.fft(T1C); fT1E = E.fft(T1E)
-        v_rhs = ops.interpz_E2C(fT1E) + fT1C
+        v_rhs = ops.interpz_E2C(fT1E, *self.bc["WdVdz"]) + fT1C
         T1E = d["dwdx"] * uE; T2E = d["dwdy"] * vE; T2E = T1E + T2E
         fT2E = E.fft(T2E)
         T1C = d["dwdz"] * wC
         fT1C = C.fft(T1C)
-        w_rhs = ops.interpz_C2E(fT1C) + fT2E
+        w_rhs = ops.interpz_C2E(fT1C, *self.bc["WdWdz"]) + fT2E
         fT1C = C.mTimes_ik1(C.fft(u * u)); u_rhs = u_rhs + fT1C
         fT1C = C.mTimes_ik2(C.fft(v * v)); v_rhs = v_rhs + fT1C
         fT1C = C.fft(wC * wC)
-        w_rhs = w_rhs + ops.ddz_C2E(fT1C)
+        w_rhs = w_rhs + ops.ddz_C2E(fT1C, *self.bc["WW"])
         fT1C = C.fft(u * v)
         u_rhs = u_rhs + C.mTimes_ik2(fT1C)
         v_rhs = v_rhs + C.mTimes_ik1(fT1C)
         fT1E = E.fft(uE * w)
-        u_rhs = u_rhs + ops.ddz_E2C(fT1E)
+        u_rhs = u_rhs + ops.ddz_E2C(fT1E, *self.bc["UW"])
         w_rhs = w_rhs + E.mTimes_ik1(fT1E)
         fT1E = E.fft(vE * w)
-        v_rhs = v_rhs + ops.ddz_E2C(fT1E)
+        v_rhs = v_rhs + ops.ddz_E2C(fT1E, *self.bc["VW"])
         w_rhs = w_rhs + E.mTimes_ik2(fT1E)
         return -0.5 * u_rhs, -0.5 * v_rhs, -0.5 * w_rhs
 
@@ -646,12 +672,12 @@ class IGrid:
         fT1C = C.fft(T1C)
         T2E = d["dwdx"] - d["dudz"]; T2E = T2E * self.w
         fT2E = E.fft(T2E)
-        u_rhs = ops.interpz_E2C(fT2E) + fT1C
+        u_rhs = ops.interpz_E2C(fT2E, 0, 0) + fT1C
         T1C = d["dudy"] - d["dvdx"]; T1C = T1C * self.u
         fT1C = C.fft(T1C)
         T2E = d["dwdy"] - d["dvdz"]; T2E = T2E * self.w
         fT2E = E.fft(T2E)
-        v_rhs = ops.interpz_E2C(fT2E) + fT1C
+        v_rhs = ops.interpz_E2C(fT2E, 0, 0) + fT1C
         T1E = d["dudz"] - d["dwdx"]; T1E = T1E * self.uE
         T2E = d["dvdz"] - d["dwdy"]; T2E = T2E * self.vE
         T1E = T1E + T2E

@@ -217,3 +217,71 @@ def test_wall_bounded_projection(shape):
     assert np.abs(div).max() < 1e-12 * scale
     # the mean horizontal flow (kx = ky = 0) is untouched: kradsq_inv = 0 there only for k3 = 0, and its divergence is zero anyway
     assert np.abs(u2[:, 0, 0] - uh[:, 0, 0]).max() < 1e-12 * np.abs(uh[:, 0, 0]).max()
+
+
+def _channel_fields(nx, ny, nz, Lz, slip=True):
+    x = np.arange(nx) * 2 * np.pi / nx
+    y = np.arange(ny) * 2 * np.pi / ny
+    zc = (np.arange(nz) + 0.5) * Lz / nz
+    ze = np.arange(nz + 1) * Lz / nz
+    X, Y = x[None, None, :], y[None, :, None]
+    a = np.pi / Lz
+    if slip:      # u, v even about both walls, w odd
+        u = np.sin(X) * np.cos(Y) * np.cos(a * zc)[:, None, None] + 0.3 * np.cos(2 * Y) * np.cos(2 * a * zc)[:, None, None] + 0 * X
+        v = -np.cos(X) * np.sin(Y) * np.cos(a * zc)[:, None, None] + 0.2 * np.sin(2 * X) * np.cos(3 * a * zc)[:, None, None] + 0 * Y
+        w = 0.25 * np.sin(X) * np.sin(2 * Y) * np.sin(2 * a * ze)[:, None, None]
+    else:         # u, v vanish on the walls, w and dw/dz too
+        u = np.sin(X) * np.cos(Y) * np.sin(a * zc)[:, None, None] + 0.3 * np.cos(2 * Y) * np.sin(2 * a * zc)[:, None, None] + 0 * X
+        v = -np.cos(X) * np.sin(Y) * np.sin(a * zc)[:, None, None] + 0 * X
+        w = 0.25 * np.sin(X) * np.sin(2 * Y) * (np.sin(a * ze) ** 2)[:, None, None]
+    return u, v, w
+
+
+@pytest.mark.parametrize("adv", [1, 0])
+def test_slip_wall_channel_equals_the_periodic_run_on_the_doubled_box(adv):
+    """PeriodicInZ = .false. with slip walls (topWall = botWall = 2): u, v even and w odd about both walls, so the wall-bounded run
+    on [0, Lz] is the lower half of a periodic run on [0, 2 Lz) started from the extended fields — the wall closures of the
+    staggered operators, the stencil codes of get_boundary_conditions_stencil and the even / odd Poisson solver all have to be
+    right for that.  (The periodic run's z-dealiasing is switched off: the wall-bounded code dealiases in x and y only.)"""
+    nx, ny, nz, Lz = 16, 12, 16, np.pi
+    L = 2 * np.pi
+    u, v, w = _channel_fields(nx, ny, nz, Lz)
+    g = IG.IGrid(nx, ny, nz, L, L, Lz, 200.0, u, v, w, TimeSteppingScheme=1, AdvectionTerm=adv, PeriodicInZ=False, topWall=2, botWall=2)
+    ue = np.concatenate([u, u[::-1]], axis=0)
+    ve = np.concatenate([v, v[::-1]], axis=0)
+    we = np.concatenate([w[:nz], -w[nz:0:-1], w[:1]], axis=0)
+    p = IG.IGrid.__new__(IG.IGrid)
+    # build the periodic twin, then widen its dealiasing mask to the 2-D one before any z-dealiasing can act on products
+    p.__init__(nx, ny, 2 * nz, L, L, 2 * Lz, 200.0, ue, ve, we, TimeSteppingScheme=1, AdvectionTerm=adv)
+    p.spectC.Gdealias = np.broadcast_to(p.spectE.Gdealias[:1], p.spectC.Gdealias.shape).copy()
+    for it in range(2):
+        g.timeAdvance(0.01)
+        p.timeAdvance(0.01)
+        # the rotational form interpolates its edge products with the ONE-SIDED closures (interpz_E2C(.., 0, 0), igrid.F90:1534, 1546):
+        # there the two runs agree to the truncation error of those rows only
+        tol = 2e-10 if adv == 1 else 5e-3
+        assert np.abs(g.u - p.u[:nz]).max() < tol * np.abs(p.u).max(), it
+        assert np.abs(g.v - p.v[:nz]).max() < tol * np.abs(p.v).max(), it
+        assert np.abs(g.w - p.w[:nz + 1]).max() < tol * np.abs(p.u).max(), it
+    assert not np.any(g.what[0]) and not np.any(g.what[nz])
+
+
+@pytest.mark.parametrize("walls", [(1, 1), (1, 2)])
+def test_no_slip_channel_stays_solenoidal_and_decays(walls):
+    nx, ny, nz, Lz = 16, 12, 24, 2.0
+    L = 2 * np.pi
+    u, v, w = _channel_fields(nx, ny, nz, Lz, slip=False)
+    g = IG.IGrid(nx, ny, nz, L, L, Lz, 50.0, u, v, w, TimeSteppingScheme=2, PeriodicInZ=False, botWall=walls[0], topWall=walls[1])
+    assert g.bc["u"] == (-1, -1 if walls[1] == 1 else 1) and g.bc["w"] == (1, 1 if walls[1] == 1 else -1) and g.bc["dWdz"][0] == -1
+    e0 = (g.u ** 2 + g.v ** 2 + g.wC ** 2).mean()
+    for _ in range(3):
+        g.timeAdvance(0.005)
+    # without the Stokes-pressure correction (computeStokesPressure, out of scope) the right-hand side leaves w* nonzero on a
+    # no-slip wall, the projection zeroes it afterwards: the divergence is small, not rounding-level, next to such a wall
+    _, _, _, div = g.poiss.DivergenceCheck(g.uhat, g.vhat, g.what)
+    assert np.abs(div).max() < 1e-3 * np.abs(g.duidxj["dudx"]).max()
+    assert not np.any(g.what[0]) and not np.any(g.what[nz])
+    e1 = (g.u ** 2 + g.v ** 2 + g.wC ** 2).mean()
+    assert 0.5 * e0 < e1 < e0
+    with pytest.raises(ValueError):
+        IG.IGrid(nx, ny, nz, L, L, Lz, 50.0, u, v, w, PeriodicInZ=False, botWall=3)
