@@ -328,9 +328,12 @@ int pdo_padepoisson_get_pressure_and_update_rhs(pdo_padepoisson_t h, double* uha
 int pdo_padepoisson_divergence_check(pdo_padepoisson_t h, double* uhat, double* vhat, double* what, double* divergence_real_x,
                                      int fix_div, double* max_div, void* stream);
 
-/* ---- IncompressibleGrid::igrid, the periodic substep  (incompressible/igrid.F90) ---------------
-   Scope: PeriodicInZ, NumericalSchemeVert = 1 (CD06) or 2 (Fourier collocation), AdvectionTerm = 1 (skew-symmetric) or 0 (rotational), TimeSteppingScheme 1
-   (TVD-RK3) or 2 (SSP-RK45), viscous or inviscid, no SGS / forcing / Coriolis / stratification / turbines.
+/* ---- IncompressibleGrid::igrid, the RK substep  (incompressible/igrid.F90) ----------------------
+   Scope: PeriodicInZ (the hot path) or walls in z with slip / no-slip stencils (get_boundary_conditions_stencil :5148-5204, wall
+   closures of the staggered operators, even / odd Poisson solver, no Stokes-pressure correction); NumericalSchemeVert = 1 (CD06)
+   or 2 (Fourier collocation, periodic only); AdvectionTerm = 1 (skew-symmetric) or 0 (rotational); TimeSteppingScheme 1
+   (TVD-RK3) or 2 (SSP-RK45); viscous or inviscid; optional SGS model and HIT forcing (periodic only, pdo_igrid_enable_*);
+   no Coriolis / stratification / turbines / fringe.
    The namelist file of igrid%init is replaced by this struct. */
 typedef struct pdo_igrid_s* pdo_igrid_t;
 typedef struct {
@@ -346,6 +349,8 @@ typedef struct {
     int compute_all_gradients;    /* 1: all 18 duidxjC/E fields like the reference; 0: only the 9 the substep reads */
     int rotational_advection;     /* 0: AdvectionTerm = 1, skew-symmetric (igrid.F90:1572-1679); 1: AdvectionTerm = 0, u x omega (:1527-1555) */
     int fourier_collocation_z;    /* 0: NumericalSchemeVert = 1, cd06 staggered operators; 1: NumericalSchemeVert = 2, Fourier collocation in z */
+    int wall_bounded;             /* 0: PeriodicInZ = .true.; 1: PeriodicInZ = .false. — walls at z = 0 and z = Lz (&BCs namelist) */
+    int top_wall, bot_wall;       /* topWall / botWall when wall_bounded: 1 no-slip, 2 slip (3, the wall model, is out of scope) */
 } pdo_igrid_params;
 /* igrid%init: u, v on the cell grid, w on the edge grid (nz+1 planes, plane nz+1 == plane 1), x-pencil local blocks,
    host or device pointers (initfields_wallM is the caller's job).  Runs the fft / dealias / projection / gradient

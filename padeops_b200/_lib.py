@@ -107,7 +107,8 @@ class IgridParams(C.Structure):
     _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("Lx", C.c_double), ("Ly", C.c_double), ("Lz", C.c_double),
                 ("Re", C.c_double), ("is_inviscid", C.c_int), ("dealias_fact", C.c_double), ("t_divergence_check", C.c_int),
                 ("time_stepping_scheme", C.c_int), ("p_row", C.c_int), ("p_col", C.c_int), ("use_d2dz2_c2c", C.c_int),
-                ("compute_all_gradients", C.c_int), ("rotational_advection", C.c_int), ("fourier_collocation_z", C.c_int)]
+                ("compute_all_gradients", C.c_int), ("rotational_advection", C.c_int), ("fourier_collocation_z", C.c_int),
+                ("wall_bounded", C.c_int), ("top_wall", C.c_int), ("bot_wall", C.c_int)]
 
 
 _PROTOS.update({

@@ -1265,6 +1265,9 @@ struct pdo_igrid_s {
     long long nRC, nRE, nYC, nYE, nZC, nZE;   // element counts: real x-pencils, complex y- and z-pencils
     int step = 0;
     double tsim = 0.0, dt = 0.0;
+    // PeriodicInZ = .false.: (bottom, top) stencil codes of get_boundary_conditions_stencil (igrid.F90:5148-5204); ignored by the
+    // periodic operators
+    int bc[12][2] = {};
     pdo_hit_forcing_t hit = nullptr;   // useHITForcing
     // useSGS: eddy-viscosity model with a global constant (sgsmod_igrid.F90); nu on cells / edges, real work pencils for the
     // cell -> edge interpolation of nu on decomposed grids
@@ -1328,6 +1331,8 @@ inline int zcommitE(pdo_igrid_s* g, const double2* z, double2* ydst, cudaStream_
 
 #define IG(expr) do { if (int _rc = (expr)) return _rc; } while (0)
 #define ZOP(fn, in, out) IG(fn(g->ops, (const double*)(in), (double*)(out), 1, 0, 0, st))
+#define ZOPB(fn, in, out, q) IG(fn(g->ops, (const double*)(in), (double*)(out), 1, g->bc[q][0], g->bc[q][1], st))
+enum { BC_W = 0, BC_U, BC_V, BC_WdUdz, BC_WdVdz, BC_WdWdz, BC_WW, BC_UW, BC_VW, BC_dUdz, BC_dVdz, BC_dWdz };
 
 // out = a*b (+ c*d)
 int mul2(double* out, const double* a, const double* b, const double* c, const double* d, long long n, cudaStream_t st) {
@@ -1379,6 +1384,7 @@ int lincomb(double2* out, const Lin5& L, long long ncplx, cudaStream_t st) {
 int ig_dealias_fields(pdo_igrid_s* g, cudaStream_t st) {
     IG(spectral_dealias(g->spC, g->cur[0], st));
     IG(spectral_dealias(g->spC, g->cur[1], st));
+    if (g->prm.wall_bounded) return spectral_dealias(g->spE, g->cur[2], st);   // igrid.F90:1029-1031: spectE's 2-D mask
     double2* we = ztarget(g, g->cur[2], g->zE[0]);
     if (!g->alias) IG(y2zE(g, g->cur[2], we, st));
     IG(spectral_dealias_edge(g->spC, we, st));
@@ -1390,14 +1396,14 @@ int ig_interp_primitive(pdo_igrid_s* g, cudaStream_t st) {
     const double2* z = nullptr;
     IG(zviewE(g, g->cur[2], g->zE[0], &z, st));
     double2* t = ztarget(g, g->whatC, g->zC[0]);
-    ZOP(pdo_pade6stagg_interpz_E2C, z, t);
+    ZOPB(pdo_pade6stagg_interpz_E2C, z, t, BC_W);
     IG(zcommitC(g, t, g->whatC, st));
     IG(ifftC(g, g->whatC, g->wC, st));
     for (int c = 0; c < 2; ++c) {
         double2* eh = c == 0 ? g->uEhat : g->vEhat;
         IG(zviewC(g, g->cur[c], g->zC[0], &z, st));
         t = ztarget(g, eh, g->zE[0]);
-        ZOP(pdo_pade6stagg_interpz_C2E, z, t);
+        ZOPB(pdo_pade6stagg_interpz_C2E, z, t, c == 0 ? BC_U : BC_V);
         IG(zcommitE(g, t, eh, st));
         IG(ifftE(g, eh, c == 0 ? g->uE : g->vE, st));
     }
@@ -1431,18 +1437,18 @@ int ig_compute_duidxj(pdo_igrid_s* g, cudaStream_t st) {
     const double2* wz = nullptr;
     IG(zviewE(g, g->cur[2], g->zE[0], &wz, st));
     double2* dwz = ztarget(g, g->yC[0], g->zC[0]);
-    ZOP(pdo_pade6stagg_ddz_E2C, wz, dwz);
+    ZOPB(pdo_pade6stagg_ddz_E2C, wz, dwz, BC_W);
     IG(zcommitC(g, dwz, g->yC[0], st));
     IG(ifftC(g, g->yC[0], g->gradC[8], st));
     if (g->gradE[8]) {
         double2* t = ztarget(g, g->yE[0], g->zE[1]);
-        ZOP(pdo_pade6stagg_interpz_C2E, dwz, t);
+        ZOPB(pdo_pade6stagg_interpz_C2E, dwz, t, BC_dWdz);
         IG(zcommitE(g, t, g->yE[0], st));
         IG(ifftE(g, g->yE[0], g->gradE[8], st));
     }
     if (visc) {
         double2* t = ztarget(g, g->d2w, g->zE[1]);
-        ZOP(pdo_pade6stagg_d2dz2_E2E, wz, t);
+        ZOPB(pdo_pade6stagg_d2dz2_E2E, wz, t, BC_W);
         IG(zcommitE(g, t, g->d2w, st));
     }
     // dudz / dvdz on edges, their cell interpolants, and the viscous second derivatives
@@ -1450,23 +1456,23 @@ int ig_compute_duidxj(pdo_igrid_s* g, cudaStream_t st) {
         const double2* fz = nullptr;
         IG(zviewC(g, g->cur[c], g->zC[0], &fz, st));
         double2* te = ztarget(g, g->yE[0], g->zE[0]);
-        ZOP(pdo_pade6stagg_ddz_C2E, fz, te);
+        ZOPB(pdo_pade6stagg_ddz_C2E, fz, te, c == 0 ? BC_U : BC_V);
         IG(zcommitE(g, te, g->yE[0], st));
         IG(ifftE(g, g->yE[0], g->gradE[2 + 3 * c], st));
         if (visc) {
             double2* d2 = c == 0 ? g->d2u : g->d2v;
             double2* td = ztarget(g, d2, g->zC[1]);
             if (g->prm.use_d2dz2_c2c) {
-                ZOP(pdo_pade6stagg_d2dz2_C2C, fz, td);
+                ZOPB(pdo_pade6stagg_d2dz2_C2C, fz, td, c == 0 ? BC_U : BC_V);
             } else {
-                ZOP(pdo_pade6stagg_ddz_C2E, fz, g->zE[1]);
-                ZOP(pdo_pade6stagg_ddz_E2C, g->zE[1], td);
+                ZOPB(pdo_pade6stagg_ddz_C2E, fz, g->zE[1], c == 0 ? BC_U : BC_V);
+                ZOPB(pdo_pade6stagg_ddz_E2C, g->zE[1], td, c == 0 ? BC_dUdz : BC_dVdz);
             }
             IG(zcommitC(g, td, d2, st));
         }
         if (g->gradC[2 + 3 * c]) {
             double2* tc = ztarget(g, g->yC[0], g->zC[0]);
-            ZOP(pdo_pade6stagg_interpz_E2C, te, tc);
+            ZOPB(pdo_pade6stagg_interpz_E2C, te, tc, c == 0 ? BC_dUdz : BC_dVdz);
             IG(zcommitC(g, tc, g->yC[0], st));
             IG(ifftC(g, g->yC[0], g->gradC[2 + 3 * c], st));
         }
@@ -1491,7 +1497,7 @@ int ig_nonlinear_skew(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cud
         IG(fftE(g, T1E, fT1E, st));
         IG(zviewE(g, fT1E, g->zE[0], &z, st));
         t = ztarget(g, r, g->zC[0]);
-        ZOP(pdo_pade6stagg_interpz_E2C, z, t);
+        ZOPB(pdo_pade6stagg_interpz_E2C, z, t, c == 0 ? BC_WdUdz : BC_WdVdz);
         IG(zcommitC(g, t, r, st));
         IG(cadd(r, fT1C, g->nYC, st));
     }
@@ -1502,7 +1508,7 @@ int ig_nonlinear_skew(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cud
     IG(fftC(g, T1C, fT1C, st));
     IG(zviewC(g, fT1C, g->zC[0], &z, st));
     t = ztarget(g, rw, g->zE[0]);
-    ZOP(pdo_pade6stagg_interpz_C2E, z, t);
+    ZOPB(pdo_pade6stagg_interpz_C2E, z, t, BC_WdWdz);
     IG(zcommitE(g, t, rw, st));
     IG(cadd(rw, fT2E, g->nYE, st));
     // conservative half: d(uu)/dx, d(vv)/dy, d(wC wC)/dz, d(uv)/dy & /dx, d(uE w)/dz & /dx, d(vE w)/dz & /dy
@@ -1516,7 +1522,7 @@ int ig_nonlinear_skew(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cud
     IG(fftC(g, T1C, fT1C, st));
     IG(zviewC(g, fT1C, g->zC[0], &z, st));
     t = ztarget(g, fT1E, g->zE[0]);
-    ZOP(pdo_pade6stagg_ddz_C2E, z, t);
+    ZOPB(pdo_pade6stagg_ddz_C2E, z, t, BC_WW);
     IG(zcommitE(g, t, fT1E, st));
     IG(cadd(rw, fT1E, g->nYE, st));
     IG(mul2(T1C, g->u, g->v, nullptr, nullptr, g->nRC, st));
@@ -1528,7 +1534,7 @@ int ig_nonlinear_skew(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cud
         IG(fftE(g, T1E, fT1E, st));
         IG(zviewE(g, fT1E, g->zE[0], &z, st));
         t = ztarget(g, fT1C, g->zC[0]);
-        ZOP(pdo_pade6stagg_ddz_E2C, z, t);
+        ZOPB(pdo_pade6stagg_ddz_E2C, z, t, c == 0 ? BC_UW : BC_VW);
         IG(zcommitC(g, t, fT1C, st));
         IG(cadd(c == 0 ? ru : rv, fT1C, g->nYC, st));
         IG(cadd_ik(E, c == 0 ? 1 : 2, rw, fT1E, st));
@@ -1832,22 +1838,44 @@ int pdo_igrid_init(pdo_igrid_t* h, const pdo_igrid_params* p, const double* u, c
         return fail(423, "The code hasn't been tested for odd values of Nx, Ny or Nz");  // igrid.F90:437-445
     if (p->time_stepping_scheme != 1 && p->time_stepping_scheme != 2)
         return fail(PDO_E_UNSUPPORTED, "TimeSteppingScheme must be 1 (TVD-RK3) or 2 (SSP-RK45); Adams-Bashforth is out of scope");
+    if (p->wall_bounded) {
+        if (p->fourier_collocation_z) return fail(123, "If you use Fourier Collocation in Z, the problem must be periodic in Z.");   // igrid.F90:458-460
+        if (p->bot_wall == 3 || p->top_wall == 3) return fail(PDO_E_UNSUPPORTED, "wall-model walls (3) are out of scope: no-slip (1) and slip (2) are built");
+        if (p->bot_wall != 1 && p->bot_wall != 2) return fail(423, "Invalid choice for BOTTOM WALL BCs");                          // :5180
+        if (p->top_wall != 1 && p->top_wall != 2) return fail(13, "Invalid choice for TOP WALL BCs");                               // :5204
+    }
     pdo_igrid_s* g = new (std::nothrow) pdo_igrid_s();
     if (!g) return fail(PDO_E_BADARG, "out of memory");
     std::memset(g->gradC, 0, sizeof(g->gradC));
     std::memset(g->gradE, 0, sizeof(g->gradE));
     g->prm = *p;
     if (g->prm.dealias_fact <= 0.0) g->prm.dealias_fact = 2.0 / 3.0;
+    if (p->wall_bounded) {   // get_boundary_conditions_stencil (igrid.F90:5148-5204); index 0 bottom, 1 top
+        const int walls[2] = {p->bot_wall, p->top_wall};
+        for (int sd = 0; sd < 2; ++sd) {
+            g->bc[BC_W][sd] = -1; g->bc[BC_WdWdz][sd] = -1; g->bc[BC_WW][sd] = +1; g->bc[BC_dWdz][sd] = 0;
+            if (walls[sd] == 1) {        // no-slip: w = 0 and dwdz = 0, so w is extended evenly
+                g->bc[BC_U][sd] = -1; g->bc[BC_V][sd] = -1; g->bc[BC_dUdz][sd] = 0; g->bc[BC_dVdz][sd] = 0;
+                g->bc[BC_WdUdz][sd] = 0; g->bc[BC_WdVdz][sd] = 0; g->bc[BC_UW][sd] = +1; g->bc[BC_VW][sd] = +1;
+                g->bc[BC_W][sd] = +1; g->bc[BC_WdWdz][sd] = -1; g->bc[BC_WW][sd] = +1; g->bc[BC_dWdz][sd] = -1;
+            } else {                     // slip
+                g->bc[BC_U][sd] = +1; g->bc[BC_V][sd] = +1; g->bc[BC_dUdz][sd] = -1; g->bc[BC_dVdz][sd] = -1;
+                g->bc[BC_WdUdz][sd] = +1; g->bc[BC_WdVdz][sd] = +1; g->bc[BC_UW][sd] = -1; g->bc[BC_VW][sd] = -1;
+            }
+        }
+        g->prm.use_d2dz2_c2c = 1;   // uBC, vBC are +-1 for these walls (:2653, 2671)
+    }
     g->dx = p->Lx / p->nx; g->dy = p->Ly / p->ny; g->dz = p->Lz / p->nz;
     cudaStream_t st = nullptr;
-    int rc = pdo_spectral_init(&g->spC, p->nx, p->ny, p->nz, g->dx, g->dy, g->dz, p->p_row, p->p_col, 0, 1, g->prm.dealias_fact);
+    const int perz = p->wall_bounded ? 0 : 1;
+    int rc = pdo_spectral_init(&g->spC, p->nx, p->ny, p->nz, g->dx, g->dy, g->dz, p->p_row, p->p_col, 0, perz, g->prm.dealias_fact);
     if (!rc) rc = pdo_spectral_init(&g->spE, p->nx, p->ny, p->nz + 1, g->dx, g->dy, g->dz, p->p_row, p->p_col, 0, 0, g->prm.dealias_fact);
     if (!rc) {
         g->gC = g->spC->pi; g->gE = g->spE->pi; g->sC = g->spC->si; g->sE = g->spE->si;
-        rc = pdo_pade6stagg_init2(&g->ops, g->gC.zsz, g->sC.zsz, g->dz, p->fourier_collocation_z ? PDO_SCHEME_FOURIER : PDO_SCHEME_CD06, 1,
+        rc = pdo_pade6stagg_init2(&g->ops, g->gC.zsz, g->sC.zsz, g->dz, p->fourier_collocation_z ? PDO_SCHEME_FOURIER : PDO_SCHEME_CD06, perz,
                                   g->spC);   // igrid.F90:500
     }
-    if (!rc) rc = pdo_padepoisson_init(&g->poiss, g->dx, g->dy, g->dz, g->spC, g->spE, g->ops);
+    if (!rc) rc = pdo_padepoisson_init2(&g->poiss, g->dx, g->dy, g->dz, g->spC, g->spE, g->ops, perz);   // :585-586
     if (rc) { pdo_igrid_destroy(g); return rc; }
     g->dC = fft3d_spec_decomp(g->spC->ft); g->dE = fft3d_spec_decomp(g->spE->ft);
     g->alias = (g->spC->p_col == 1);
@@ -1926,6 +1954,7 @@ int pdo_igrid_enable_sgs(pdo_igrid_t g, int sgs_model_id, double csgs, int expli
     if (!g) return fail(PDO_E_BADARG, "null handle");
     if (sgs_model_id < 0 || sgs_model_id > 2) return fail(213, "Incorrect choice for SGS model ID.");   // init_destroy_sgs_igrid.F90:165
     if (!g->prm.compute_all_gradients) return fail(PDO_E_BADARG, "the SGS models need all eighteen velocity gradients: init with compute_all_gradients");
+    if (g->prm.wall_bounded) return fail(PDO_E_UNSUPPORTED, "SGS with walls (wall damping / wall models, non-periodic filter width) is out of scope");
     const double dx = g->dx, dy = g->dy, dz = g->dz;
     SgsConst c{};
     c.mid = sgs_model_id;

@@ -265,6 +265,28 @@ def late(pdo, O, rank, world, grids):
                 ok(got.shape == rr.shape and np.abs(got - rr).max() < 5e-12 * np.abs(getattr(ref, nm)).max(),
                    f"igrid adv={adv} vert={vert} {nm} grid {pr}x{pc}")
             g.destroy()
+    # wall-bounded igrid (slip walls) on decomposed fields
+    nx, ny, nz, Lz = 16, 16, 16, 2.0
+    xx = np.arange(nx) * 2 * np.pi / nx
+    zc, ze = (np.arange(nz) + 0.5) * Lz / nz, np.arange(nz + 1) * Lz / nz
+    X, Y = xx[None, None, :], xx[None, :, None]
+    U = np.sin(X) * np.cos(Y) * np.cos(np.pi * zc / Lz)[:, None, None]
+    V = -np.cos(X) * np.sin(Y) * np.cos(np.pi * zc / Lz)[:, None, None]
+    W = 0.25 * np.sin(X) * np.sin(2 * Y) * np.sin(2 * np.pi * ze / Lz)[:, None, None]
+    box = (2 * np.pi, 2 * np.pi, Lz)
+    ref = IG.IGrid(nx, ny, nz, *box, 100.0, U, V, W, TimeSteppingScheme=1, PeriodicInZ=False, topWall=2, botWall=2)
+    ref.timeAdvance(0.005)
+    for (pr, pc) in grids:
+        if min(nx // 2 + 1, ny) < pr or min(ny, nz) < pc:
+            continue
+        loc = [O.scatter_global(A, nx, ny, n3, pr, pc, "x")[rank] for A, n3 in ((U, nz), (V, nz), (W, nz + 1))]
+        g = pdo.igrid()
+        g.init(nx, ny, nz, *box, 100.0, *loc, TimeSteppingScheme=1, prow=pr, pcol=pc, PeriodicInZ=False, topWall=2, botWall=2)
+        g.timeAdvance(0.005)
+        for nm, n3 in (("u", nz), ("v", nz), ("w", nz + 1)):
+            rr = O.scatter_global(getattr(ref, nm), nx, ny, n3, pr, pc, "x")[rank]
+            ok(np.abs(g.get(nm) - rr).max() < 5e-12 * np.abs(ref.u).max(), f"wall-bounded igrid {nm} grid {pr}x{pc}")
+        g.destroy()
     t = torch.tensor([nfail], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
