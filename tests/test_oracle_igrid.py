@@ -285,3 +285,70 @@ def test_no_slip_channel_stays_solenoidal_and_decays(walls):
     assert 0.5 * e0 < e1 < e0
     with pytest.raises(ValueError):
         IG.IGrid(nx, ny, nz, L, L, Lz, 50.0, u, v, w, PeriodicInZ=False, botWall=3)
+
+
+def test_wall_projection_kernels_index_arithmetic():
+    """csrc/igrid.cu poiss_wall_projection re-enacted in numpy with the kernels' own flat-index expressions (extension, fused
+    solve + project with the complex products written out in components, extraction) against the oracle's array formulation."""
+    nx, ny, nz = 8, 6, 10
+    dx, dy, dz = 2 * np.pi / nx, 2 * np.pi / ny, 1.0 / nz
+    spC, spE = IG.Spectral(nx, ny, nz, dx, dy, dz), IG.Spectral(nx, ny, nz + 1, dx, dy, dz)
+    ops = IG.Pade6stagg(nz, dz, 1, isPeriodic=False)
+    P = IG.PadePoisson(dx, dy, dz, spC, spE, ops, PeriodicInZ=False)
+    rng = np.random.default_rng(1)
+    nxh = nx // 2 + 1
+    uh = rng.standard_normal((nz, ny, nxh)) + 1j * rng.standard_normal((nz, ny, nxh))
+    vh = rng.standard_normal((nz, ny, nxh)) + 1j * rng.standard_normal((nz, ny, nxh))
+    wh = rng.standard_normal((nz + 1, ny, nxh)) + 1j * rng.standard_normal((nz + 1, ny, nxh))
+    wh[0] = 0
+    wh[nz] = 0
+    want = P.PressureProjection(uh, vh, wh)
+    # --- kernels ---
+    n1, n2 = nxh, ny
+    cols = n1 * n2
+    f2dy = spC.k1 * uh + spC.k2 * vh
+    uz = (-f2dy.imag + 1j * f2dy.real).reshape(-1)             # poiss_div_xy; flat index = c + cols * k
+    wz = wh.reshape(-1)
+    fe = np.zeros(cols * 2 * nz, dtype=complex)
+    we = np.zeros(cols * 2 * nz, dtype=complex)
+    for i in range(cols * 2 * nz):
+        c, kk = i % cols, i // cols
+        fe[i] = uz[c + cols * (nz - 1 - kk)] if kk < nz else uz[c + cols * (kk - nz)]
+        we[i] = -wz[c + cols * (nz - 1 - kk)] if kk < nz - 1 else wz[c + cols * (kk - (nz - 1))]
+    fe = np.fft.fft(fe.reshape(2 * nz, cols), axis=0).reshape(-1)
+    we = np.fft.fft(we.reshape(2 * nz, cols), axis=0).reshape(-1)
+    k1sq = (IG.O.wavenums(nx, dx)[:nxh]) ** 2
+    k2sq = IG.O.wavenums(ny, dy) ** 2
+    k3e = IG.O.wavenums(2 * nz, dz)
+    k3m = ops.getModifiedWavenumbers(k3e)
+    cm = np.stack([k3m * np.cos((dz / 2) * k3e), -k3m * np.sin((dz / 2) * k3e)], axis=1)
+    cp = np.stack([k3m * np.cos((dz / 2) * k3e), k3m * np.sin((dz / 2) * k3e)], axis=1)
+    mfact = 1.0 / (2 * nz)
+    for i in range(cols * 2 * nz):
+        ii = i % n1
+        t = i // n1
+        jj, kk = t % n2, t // n2
+        kradsq = k1sq[ii] + k2sq[jj] + k3m[kk] ** 2
+        kinv = 0.0 if kradsq <= 1e-14 else 1.0 / kradsq
+        fx, fy, wx, wy = fe[i].real, fe[i].imag, we[i].real, we[i].imag
+        ax, ay, bx, by = cm[kk, 0], cm[kk, 1], cp[kk, 0], cp[kk, 1]
+        fx += -(ax * wy + ay * wx)
+        fy += ax * wx - ay * wy
+        fx, fy = -fx * kinv, -fy * kinv
+        wx -= -(bx * fy + by * fx)
+        wy -= bx * fx - by * fy
+        fe[i] = (fx + 1j * fy) * mfact
+        we[i] = (wx + 1j * wy) * mfact
+    fe = (np.fft.ifft(fe.reshape(2 * nz, cols), axis=0) * (2 * nz)).reshape(-1)
+    we = (np.fft.ifft(we.reshape(2 * nz, cols), axis=0) * (2 * nz)).reshape(-1)
+    f2d = np.zeros(cols * nz, dtype=complex)
+    w2 = np.zeros(cols * (nz + 1), dtype=complex)
+    for i in range(cols * (nz + 1)):
+        kk = i // cols
+        if kk < nz:
+            f2d[i] = fe[i + cols * nz]
+        w2[i] = 0.0 if kk in (0, nz) else we[i + cols * (nz - 1)]
+    f2d = f2d.reshape(nz, ny, nxh)
+    got = (uh - 1j * spC.k1 * f2d, vh - 1j * spC.k2 * f2d, w2.reshape(nz + 1, ny, nxh))
+    for a, b in zip(got, want):
+        assert np.abs(a - b).max() < 1e-12 * np.abs(b).max()
