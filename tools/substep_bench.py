@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """ms per igrid time step / RK substep (BASELINE.json metric iii) on synthetic Taylor-Green + broadband fields.
-Usage: python tools/substep_bench.py [n] [scheme] [steps]   (torchrun for multi-GPU; grid 1 x N)"""
+Usage: python tools/substep_bench.py [n] [scheme] [steps] [variant]   (torchrun for multi-GPU; grid 1 x N)
+variant: "base" (skew-symmetric, CD06 in z, viscous: the BASELINE workload), "hit" (the authors' HIT_Periodic deck: rotational form,
+Fourier collocation in z, AMD model Csgs = 1.67, shell forcing kmin 4 kmax 5 Nwaves 20 Eps 0.05, Re = 1e10), "slip" (slip walls)."""
 import json
 import os
 import sys
@@ -21,6 +23,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     scheme = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+    variant = sys.argv[4] if len(sys.argv) > 4 else "base"
     pdo.decomp_2d.comm_init()
     info = pdo.decomp_info.for_rank(n, n, n, 1, world, rank)
     infoE = pdo.decomp_info.for_rank(n, n, n + 1, 1, world, rank)
@@ -35,7 +38,19 @@ def main():
     v = (-torch.cos(X) * torch.sin(Y) * torch.cos(ZC)).contiguous()
     w = (0.1 * torch.sin(2 * X) * torch.sin(Y) * torch.sin(ZE)).contiguous()
     g = pdo.igrid()
-    g.init(n, n, n, 2 * np.pi, 2 * np.pi, 2 * np.pi, 1600.0, u, v, w, TimeSteppingScheme=scheme, prow=1, pcol=world)
+    if variant == "hit":
+        g.init(n, n, n, 2 * np.pi, 2 * np.pi, 2 * np.pi, 1.0e10, u, v, w, TimeSteppingScheme=scheme, prow=1, pcol=world, AdvectionTerm=0,
+               NumericalSchemeVert=2, computeAllGradients=True)
+        g.enableSGS(SGSModelID=2, Csgs=1.67)
+        g.enableHITForcing(kmin=4.0, kmax=5.0, Nwaves=20, EpsAmplitude=0.05)
+        label = "HIT_Periodic deck: rotational, Fourier z, AMD, shell forcing"
+    elif variant == "slip":
+        w = (0.1 * torch.sin(2 * X) * torch.sin(Y) * torch.sin(ZE / 2)).contiguous()     # w = 0 on both walls of [0, 2 pi]
+        g.init(n, n, n, 2 * np.pi, 2 * np.pi, 2 * np.pi, 1600.0, u, v, w, TimeSteppingScheme=scheme, prow=1, pcol=world, PeriodicInZ=False)
+        label = "slip walls, skew-symmetric, CD06 z, viscous"
+    else:
+        g.init(n, n, n, 2 * np.pi, 2 * np.pi, 2 * np.pi, 1600.0, u, v, w, TimeSteppingScheme=scheme, prow=1, pcol=world)
+        label = "skew-symmetric, CD06 z, viscous"
     dt = 0.2 * d
     g.timeAdvance(dt)
     torch.cuda.synchronize()
@@ -54,7 +69,7 @@ def main():
         ms = t.item()
     nsub = 3 if scheme == 1 else 5
     if rank == 0:
-        print(json.dumps({"workload": f"igrid periodic {n}^3, skew-symmetric, CD06 z, viscous, {'TVD-RK3' if scheme == 1 else 'SSP-RK45'}",
+        print(json.dumps({"workload": f"igrid {n}^3, {label}, {'TVD-RK3' if scheme == 1 else 'SSP-RK45'}",
                           "n_gpus": world, "ms_per_step": round(ms, 3), "ms_per_substep": round(ms / nsub, 3),
                           "launches_per_substep": (L.pdo_launch_count() - l0) // (steps * nsub),
                           "Mpoints_per_s_per_substep": round(n ** 3 / (ms / nsub) / 1e3, 1), "max_div": g.maxDivergence()}), flush=True)
