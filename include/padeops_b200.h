@@ -85,6 +85,8 @@ int pdo_cf90_filter3(pdo_cf90_t h, const double* f, double* fil, int na, int nb,
 
 /* ---- gaussianstuff::gaussian  (filters/gaussian.F90) ----------------------------------------- */
 typedef struct pdo_gaussian_s* pdo_gaussian_t;
+/* periodic = 0: the explicit boundary rows b1..b4 (bc 0) or the interior stencil on the even / odd reflection (bc +1 / -1),
+   gaussian.F90:22-46, 215-330; needs n >= 8 */
 int pdo_gaussian_init(pdo_gaussian_t* h, int n, int periodic);                          /* gaussian.F90:74-102 */
 int pdo_gaussian_destroy(pdo_gaussian_t h);
 int pdo_gaussian_filter1(pdo_gaussian_t h, const double* f, double* fil, int na, int nb, int bc1, int bcn, void* stream); /* :104 */

@@ -278,8 +278,7 @@ def filter3D(f, numtimes=1, methods=("cf90", "cf90", "cf90"), periodic=(True, Tr
     transposes between the stages are pure permutations).  f: global array (nz, ny, nx); returns the filtered copy."""
     def one(a, axis, bc):
         if methods[axis].startswith("gaussian"):
-            assert periodic[axis], "gaussian non-periodic closures are not restated"
-            return gaussian(a, axis)
+            return gaussian(a, axis) if periodic[axis] else gaussian_np(a, axis, bc[0], bc[1])
         return cf90(a, axis) if periodic[axis] else cf90_np(a, axis, bc[0], bc[1])
     out = np.ascontiguousarray(f, dtype=np.float64)
     for axis, bc in ((1, y_bc), (0, x_bc), (2, z_bc)):
@@ -321,6 +320,48 @@ def cf90_np(f, axis, bc1=0, bcn=0):
     rc = lib().pdo_oracle_cf90_np(C.c_int(n), C.c_int(bc1), C.c_int(bcn), C.c_int(axis), _p(f), _p(out), C.c_int64(na), C.c_int64(nb))
     assert rc == 0, rc
     return out
+
+
+def gaussian_np(f, axis, bc1=0, bcn=0):
+    """gaussian%filter1/2/3 with periodic=.false. (filters/gaussian.F90:22-46, 215-330): explicit filter; bc = 0: the four boundary
+    rows b1..b4 at that end, bc = +1 / -1: the interior 9-point stencil on the even / odd reflection about the end point.
+    Statement-by-statement numpy restatement (the line axis is moved to the front)."""
+    agf, bgf, cgf, dgf, egf = 3565.0 / 10368.0, 3091.0 / 12960.0, 1997.0 / 25920.0, 149.0 / 12960.0, 107.0 / 103680.0
+    b1 = (5.0 / 6.0, 1.0 / 6.0)
+    b2 = (2.0 / 3.0, 1.0 / 6.0)
+    b3 = (31.0 / 64.0, 7.0 / 32.0, 5.0 / 128.0)
+    b4 = (17.0 / 48.0, 15.0 / 64.0, 7.0 / 96.0, 1.0 / 64.0)
+    if bc1 not in (0, 1, -1) or bcn not in (0, 1, -1):
+        raise ValueError("Incorrect boundary specification (324)")
+    ax = {0: 2, 1: 1, 2: 0}[axis]                      # numpy axis of the Fortran index `axis + 1`
+    g = np.moveaxis(np.asarray(f, dtype=np.float64), ax, 0)
+    n = g.shape[0]
+    assert n >= 8
+    out = np.empty_like(g)
+    F = lambda i: g[i - 1]                              # 1-based like the Fortran
+
+    def interior(i, L, R):
+        """row i with left neighbours L(k) = f(i-k) and right neighbours R(k) = f(i+k), possibly reflected"""
+        return agf * (F(i)) + bgf * (R(1) + L(1)) + cgf * (R(2) + L(2)) + dgf * (R(3) + L(3)) + egf * (R(4) + L(4))
+    for i in range(5, n - 3):
+        out[i - 1] = interior(i, lambda k: F(i - k), lambda k: F(i + k))
+    if bc1 == 0:
+        out[0] = b1[0] * (F(1)) + b1[1] * (F(2))
+        out[1] = b2[0] * (F(2)) + b2[1] * (F(3) + F(1))
+        out[2] = b3[0] * (F(3)) + b3[1] * (F(4) + F(2)) + b3[2] * (F(5) + F(1))
+        out[3] = b4[0] * (F(4)) + b4[1] * (F(5) + F(3)) + b4[2] * (F(6) + F(2)) + b4[3] * (F(7) + F(1))
+    else:
+        for i in range(1, 5):                           # f(1-m) := +- f(1+m): "f(2) + f(2)", "- f(2) + ..." written out in the reference
+            out[i - 1] = interior(i, lambda k: F(i - k) if i - k >= 1 else bc1 * F(2 - (i - k)), lambda k: F(i + k))
+    if bcn == 0:
+        out[n - 4] = b4[0] * (F(n - 3)) + b4[1] * (F(n - 2) + F(n - 4)) + b4[2] * (F(n - 1) + F(n - 5)) + b4[3] * (F(n) + F(n - 6))
+        out[n - 3] = b3[0] * (F(n - 2)) + b3[1] * (F(n - 1) + F(n - 3)) + b3[2] * (F(n) + F(n - 4))
+        out[n - 2] = b2[0] * (F(n - 1)) + b2[1] * (F(n) + F(n - 2))
+        out[n - 1] = b1[0] * (F(n)) + b1[1] * (F(n - 1))
+    else:
+        for i in range(n - 3, n + 1):
+            out[i - 1] = interior(i, lambda k: F(i - k), lambda k: F(i + k) if i + k <= n else bcn * F(2 * n - (i + k)))
+    return np.ascontiguousarray(np.moveaxis(out, 0, ax))
 
 
 def cf90_np_penta(n, bc1, bcn):

@@ -457,24 +457,25 @@ int pdo_cf90_destroy(pdo_cf90_t h) {
 PDO_CF90_FN(pdo_cf90_filter1, 0)
 PDO_CF90_FN(pdo_cf90_filter2, 1)
 PDO_CF90_FN(pdo_cf90_filter3, 2)
-#define PDO_FIL_FN(T, name, axis)                                                                 \
-    int name(T h, const double* f, double* fil, int na, int nb, int bc1, int bcn, void* stream) { \
-        if (!h) return fail(PDO_E_BADARG, "null handle");                                         \
-        if (int rc = check_bc(bc1, bcn)) return rc;                                               \
-        return apply(h->op, true, axis, f, fil, na, nb, stream);                                  \
-    }
-
 // ---------------- gaussian ----------------
 int pdo_gaussian_init(pdo_gaussian_t* h, int n, int periodic) {
     if (!h) return fail(PDO_E_BADARG, "null handle");
     *h = nullptr;
     if (n < 1) return fail(PDO_E_BADARG, "n < 1");
-    if (!periodic) return fail(PDO_E_UNSUPPORTED, "gaussian: non-periodic closures are out of scope (SURVEY.md 8f rank 2)");
-    if (n != 1 && n < 9) return fail(PDO_E_BADARG, "gaussian: periodic 9-point stencil needs n >= 9");
+    if (periodic && n != 1 && n < 9) return fail(PDO_E_BADARG, "gaussian: periodic 9-point stencil needs n >= 9");
+    if (!periodic && n != 1 && n < 8) return fail(PDO_E_BADARG, "gaussian: the non-periodic closure needs n >= 8 (four boundary rows at each end)");
     if (int rc = ensure_device()) return rc;
     pdo_gaussian_s* o = new (std::nothrow) pdo_gaussian_s();
     if (!o) return fail(PDO_E_BADARG, "out of memory");
     o->n = n;
+    if (!periodic) {   // gaussian.F90:215-330: explicit boundary rows (bc 0) or the interior stencil on the reflected line (bc +-1)
+        o->periodic = false;
+        int ie = 0;
+        cudaError_t e = np_op_create(&o->np, NP_GAUSS, n, 1.0, &ie);
+        if (e != cudaSuccess || ie) { delete o; return e != cudaSuccess ? fail(PDO_E_CUDA, "gaussian init: %s", cudaGetErrorString(e)) : fail(ie, "gaussian: non-periodic init"); }
+        *h = o;
+        return 0;
+    }
     OpParams p{};
     p.co[0] = agf; p.co[1] = bgf; p.co[2] = cgf; p.co[3] = dgf; p.co[4] = egf;
     cudaError_t e = banded_op_create(&o->op, n, RK_SYM_9, 0, 0.0, 0.0, p);
@@ -487,13 +488,21 @@ int pdo_gaussian_init(pdo_gaussian_t* h, int n, int periodic) {
 }
 int pdo_gaussian_destroy(pdo_gaussian_t h) {
     if (!h) return 0;
-    banded_op_destroy(&h->op);
+    if (h->periodic) banded_op_destroy(&h->op);
+    else np_op_destroy(&h->np);
     delete h;
     return 0;
 }
-PDO_FIL_FN(pdo_gaussian_t, pdo_gaussian_filter1, 0)
-PDO_FIL_FN(pdo_gaussian_t, pdo_gaussian_filter2, 1)
-PDO_FIL_FN(pdo_gaussian_t, pdo_gaussian_filter3, 2)
+#define PDO_GAUSS_FN(name, axis)                                                                               \
+    int name(pdo_gaussian_t h, const double* f, double* fil, int na, int nb, int bc1, int bcn, void* stream) { \
+        if (!h) return fail(PDO_E_BADARG, "null handle");                                                      \
+        if (int rc = check_bc(bc1, bcn)) return rc;                                                            \
+        if (!h->periodic) return apply_np(h->np, true, axis, f, fil, na, nb, bc1, bcn, stream);                \
+        return apply(h->op, true, axis, f, fil, na, nb, stream);                                               \
+    }
+PDO_GAUSS_FN(pdo_gaussian_filter1, 0)
+PDO_GAUSS_FN(pdo_gaussian_filter2, 1)
+PDO_GAUSS_FN(pdo_gaussian_filter3, 2)
 
 // ---------------- cd06stagg (periodic) ----------------
 int pdo_cd06stagg_init_periodic(pdo_cd06stagg_t* h, int n, double dx) {

@@ -8,7 +8,7 @@
 struct pdo_cd10_s { int n; pdo::BandedOp d1, d2; bool periodic = true; pdo::NpOp np_d1, np_d2; };   // np*: periodic = .false. closures
 struct pdo_cd06_s { int n; pdo::BandedOp d1; bool periodic = true; pdo::NpOp np; };
 struct pdo_cf90_s { int n; pdo::BandedOp op; bool periodic = true; pdo::NpOp np; };
-struct pdo_gaussian_s { int n; pdo::BandedOp op; };
+struct pdo_gaussian_s { int n; pdo::BandedOp op; bool periodic = true; pdo::NpOp np; };
 struct pdo_cd06stagg_s { int n; pdo::BandedOp ops[6]; bool periodic = true; pdo::StaggNp np; };   // np: init_nonperiodic (walls)
 struct pdo_derivatives_s {
     int xsz[3], ysz[3], zsz[3];

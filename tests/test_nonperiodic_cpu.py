@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-KINDS = {"cd10_d1": 0, "cd10_d2": 1, "cf90": 2, "cd06_d1": 3}
+KINDS = {"cd10_d1": 0, "cd10_d2": 1, "cf90": 2, "cd06_d1": 3, "gaussian": 4}
 
 
 def product_host(pdo, kind, f, dx, axis, bc1, bcn):
@@ -26,6 +26,8 @@ def oracle_ref(oracle, kind, f, dx, axis, bc1, bcn):
         return oracle.cf90_np(f, axis, bc1, bcn)
     if kind == "cd06_d1":
         return oracle.cd06_np(f, dx, axis)
+    if kind == "gaussian":
+        return oracle.gaussian_np(f, axis, bc1, bcn)
     return oracle.cd10_np(f, dx, axis, 1 if kind == "cd10_d1" else 2, bc1, bcn)
 
 

@@ -94,3 +94,30 @@ def test_cd06_nonperiodic_one_sided(pdo, oracle, axis):
     got = (h.dd1, h.dd2, h.dd3)[axis](_dev(f)).cpu().numpy()
     assert _rel(got, oracle.cd06_np(f, dx, axis)) < TOL
     assert pdo.cd06().init(n, dx, periodic_=False, bc1_=1) == 1002
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's last GPU session (the pointwise kernel of the CD10 / CF90 cases above with the "
+                                        "Gaussian rows; its host-device routine is verified on the CPU in tests/test_nonperiodic_cpu.py)")
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_gaussian_nonperiodic_all_boundary_codes(pdo, oracle, axis):
+    """gaussian%filter* with periodic = .false. (filters/gaussian.F90:215-330), also through the filters dispatch type and filter3D"""
+    shape = {0: (5, 6, 40), 1: (5, 40, 6), 2: (40, 5, 6)}[axis]
+    n = 40
+    f = np.random.default_rng(10 + axis).standard_normal(shape)
+    fd = _dev(f)
+    h = pdo.gaussian()
+    assert h.init(n, periodic_=False) == 0
+    fil = (h.filter1, h.filter2, h.filter3)[axis]
+    for bc1, bcn in BCS:
+        assert _rel(fil(fd, bc1_=bc1, bcn_=bcn).cpu().numpy(), oracle.gaussian_np(f, axis, bc1, bcn)) < TOL, (bc1, bcn)
+    if axis == 2:
+        nz, ny, nx = 40, 16, 16
+        g = np.random.default_rng(3).standard_normal((nz, ny, nx))
+        gp = pdo.decomp_2d.init(nx, ny, nz, 1, 1)
+        fl = pdo.filters()
+        fl.init(gp, True, True, False, "cf90", "gaussian", "gaussian")
+        ops = pdo.vector_ops()
+        ops.init(gp, 0.1, 0.1, 0.1, "cd10")
+        a = _dev(g)
+        ops.filter3D(fl, a, 2, z_bc=(0, 1))
+        assert _rel(a.cpu().numpy(), oracle.filter3D(g, 2, ("cf90", "gaussian", "gaussian"), (True, True, False), z_bc=(0, 1))) < TOL

@@ -177,3 +177,31 @@ def test_cd06_np_thomas_solves_its_rows(oracle):
     f = x ** 3
     got = oracle.cd06_np(_lines(f, 0), x[1] - x[0], 0)[0, 0]
     assert np.abs(got - 3 * x ** 2).max() < 1e-12
+
+
+def test_gaussian_nonperiodic_closures(oracle):
+    """gaussian%filter* with periodic = .false. (filters/gaussian.F90:22-46, 215-330): every boundary row sums to one (constants
+    pass), the symmetric / antisymmetric closures are the periodic filter on the even / odd extension, and the one-sided rows
+    b1..b4 are the published ones."""
+    rng = np.random.default_rng(2)
+    n = 20
+    for bc1 in (0, 1, -1):
+        for bcn in (0, 1, -1):
+            c = oracle.gaussian_np(np.full((3, 4, n), 1.25), 0, bc1, bcn)
+            if bc1 != -1 and bcn != -1:
+                assert np.abs(c - 1.25).max() < 1e-15
+    f = rng.standard_normal((2, 3, n))
+    for bc in (1, -1):
+        ext = np.concatenate([f, bc * f[..., -2:0:-1]], axis=-1)          # reflection about both end points: 2n - 2 periodic points
+        ref = oracle.gaussian(ext, 0)[..., :n]
+        got = oracle.gaussian_np(f, 0, bc, bc)
+        assert np.abs(got - ref).max() < 1e-14
+    got = oracle.gaussian_np(f, 0, 0, 0)
+    assert np.allclose(got[..., 0], (5.0 / 6.0) * f[..., 0] + (1.0 / 6.0) * f[..., 1], rtol=0, atol=1e-15)
+    assert np.allclose(got[..., n - 2], (2.0 / 3.0) * f[..., n - 2] + (1.0 / 6.0) * (f[..., n - 1] + f[..., n - 3]), rtol=0, atol=1e-15)
+    assert np.allclose(got[..., 5:n - 4], oracle.gaussian(f, 0)[..., 5:n - 4], rtol=0, atol=1e-15)   # interior rows are the periodic ones
+    for axis in (1, 2):                                                    # the other axes are the same operator on a moved axis
+        g = rng.standard_normal((n, n, 5))
+        a = oracle.gaussian_np(g, axis, 0, 1)
+        b = np.moveaxis(oracle.gaussian_np(np.ascontiguousarray(np.moveaxis(g, {1: 1, 2: 0}[axis], 2)), 0, 0, 1), 2, {1: 1, 2: 0}[axis])
+        assert np.array_equal(a, b)
