@@ -130,9 +130,17 @@ int pdo_derivatives_d2dx2(pdo_derivatives_t h, const double* f, double* d2f, int
 int pdo_derivatives_d2dy2(pdo_derivatives_t h, const double* f, double* d2f, int bc1, int bcn, void* stream);  /* :534-550 */
 int pdo_derivatives_d2dz2(pdo_derivatives_t h, const double* f, double* d2f, int bc1, int bcn, void* stream);  /* :552-569 */
 
+/* ---- lstsqstuff::lstsq  (filters/lstsq.F90): explicit 9-point least-squares filter --------------- */
+typedef struct pdo_lstsq_s* pdo_lstsq_t;
+int pdo_lstsq_init(pdo_lstsq_t* h, int n, int periodic);   /* periodic = 0: one-sided rows b1..b4 at both ends (:169-212), n >= 8 */
+int pdo_lstsq_destroy(pdo_lstsq_t h);
+int pdo_lstsq_filter1(pdo_lstsq_t h, const double* f, double* fil, int na, int nb, void* stream);
+int pdo_lstsq_filter2(pdo_lstsq_t h, const double* f, double* fil, int na, int nb, void* stream);
+int pdo_lstsq_filter3(pdo_lstsq_t h, const double* f, double* fil, int na, int nb, void* stream);
+
 /* ---- FiltersMod::filters  (filters/filters.F90) ---------------------------------------------- */
 typedef struct pdo_filters_s* pdo_filters_t;
-/* filters%init(gp, periodicx,y,z, methodx,y,z)   filters.F90:274-297; methods "cf90" | "gaussian" */
+/* filters%init(gp, periodicx,y,z, methodx,y,z)   filters.F90:274-297; methods "cf90" | "gaussian" | "lstsq" (else 52) */
 int pdo_filters_init(pdo_filters_t* h, const int xsz[3], const int ysz[3], const int zsz[3], int periodicx, int periodicy,
                      int periodicz, const char* methodx, const char* methody, const char* methodz);
 int pdo_filters_destroy(pdo_filters_t h);

@@ -279,6 +279,8 @@ def filter3D(f, numtimes=1, methods=("cf90", "cf90", "cf90"), periodic=(True, Tr
     def one(a, axis, bc):
         if methods[axis].startswith("gaussian"):
             return gaussian(a, axis) if periodic[axis] else gaussian_np(a, axis, bc[0], bc[1])
+        if methods[axis].startswith("lstsq"):
+            return lstsq(a, axis) if periodic[axis] else lstsq_np(a, axis)
         return cf90(a, axis) if periodic[axis] else cf90_np(a, axis, bc[0], bc[1])
     out = np.ascontiguousarray(f, dtype=np.float64)
     for axis, bc in ((1, y_bc), (0, x_bc), (2, z_bc)):
@@ -322,11 +324,30 @@ def cf90_np(f, axis, bc1=0, bcn=0):
     return out
 
 
-def gaussian_np(f, axis, bc1=0, bcn=0):
+GAUSS_COEFS = (3565.0 / 10368.0, 3091.0 / 12960.0, 1997.0 / 25920.0, 149.0 / 12960.0, 107.0 / 103680.0)    # gaussian.F90:15-19
+LSTSQ_COEFS = (0.5, 0.6744132 / 2.0, 0.0 / 2.0, -0.1744132 / 2.0, 0.0 / 2.0)                               # lstsq.F90:14-19
+
+
+def lstsq(f, axis):
+    """lstsq%filter1/2/3, periodic (filters/lstsq.F90:117-167): the explicit symmetric 9-point stencil with the least-squares
+    coefficients, periodic wrap."""
+    a, b, c, d, e = LSTSQ_COEFS
+    ax = {0: 2, 1: 1, 2: 0}[axis]
+    g = np.asarray(f, dtype=np.float64)
+    R = lambda k: np.roll(g, -k, axis=ax)
+    return a * (g) + b * (R(1) + R(-1)) + c * (R(2) + R(-2)) + d * (R(3) + R(-3)) + e * (R(4) + R(-4))
+
+
+def lstsq_np(f, axis):
+    """lstsq%filter* with periodic=.false. (lstsq.F90:169-212): always the one-sided rows b1..b4 (the same as the Gaussian filter's)"""
+    return gaussian_np(f, axis, 0, 0, LSTSQ_COEFS)
+
+
+def gaussian_np(f, axis, bc1=0, bcn=0, coefs=GAUSS_COEFS):
     """gaussian%filter1/2/3 with periodic=.false. (filters/gaussian.F90:22-46, 215-330): explicit filter; bc = 0: the four boundary
     rows b1..b4 at that end, bc = +1 / -1: the interior 9-point stencil on the even / odd reflection about the end point.
     Statement-by-statement numpy restatement (the line axis is moved to the front)."""
-    agf, bgf, cgf, dgf, egf = 3565.0 / 10368.0, 3091.0 / 12960.0, 1997.0 / 25920.0, 149.0 / 12960.0, 107.0 / 103680.0
+    agf, bgf, cgf, dgf, egf = coefs
     b1 = (5.0 / 6.0, 1.0 / 6.0)
     b2 = (2.0 / 3.0, 1.0 / 6.0)
     b3 = (31.0 / 64.0, 7.0 / 32.0, 5.0 / 128.0)

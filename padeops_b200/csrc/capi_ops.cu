@@ -504,6 +504,49 @@ PDO_GAUSS_FN(pdo_gaussian_filter1, 0)
 PDO_GAUSS_FN(pdo_gaussian_filter2, 1)
 PDO_GAUSS_FN(pdo_gaussian_filter3, 2)
 
+// ---------------- lstsq (filters/lstsq.F90): the Gaussian filter's structure with the least-squares coefficients; no bc arguments ----------------
+int pdo_lstsq_init(pdo_lstsq_t* h, int n, int periodic) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    *h = nullptr;
+    if (n < 1) return fail(PDO_E_BADARG, "n < 1");
+    if (periodic && n != 1 && n < 9) return fail(PDO_E_BADARG, "lstsq: periodic 9-point stencil needs n >= 9");
+    if (!periodic && n != 1 && n < 8) return fail(PDO_E_BADARG, "lstsq: the non-periodic closure needs n >= 8 (four boundary rows at each end)");
+    if (int rc = ensure_device()) return rc;
+    pdo_lstsq_s* o = new (std::nothrow) pdo_lstsq_s();
+    if (!o) return fail(PDO_E_BADARG, "out of memory");
+    o->n = n;
+    if (!periodic) {   // lstsq.F90:169-212: one-sided rows at both ends, always
+        o->periodic = false;
+        int ie = 0;
+        cudaError_t e = np_op_create(&o->np, NP_LSTSQ, n, 1.0, &ie);
+        if (e != cudaSuccess || ie) { delete o; return e != cudaSuccess ? fail(PDO_E_CUDA, "lstsq init: %s", cudaGetErrorString(e)) : fail(ie, "lstsq: non-periodic init"); }
+        *h = o;
+        return 0;
+    }
+    OpParams p{};
+    p.co[0] = 0.5; p.co[1] = 0.6744132 / 2.0; p.co[2] = 0.0 / 2.0; p.co[3] = -0.1744132 / 2.0; p.co[4] = 0.0 / 2.0;   // lstsq.F90:14-19
+    cudaError_t e = banded_op_create(&o->op, n, RK_SYM_9, 0, 0.0, 0.0, p);
+    if (e != cudaSuccess) { delete o; return fail(PDO_E_CUDA, "lstsq init: %s", cudaGetErrorString(e)); }
+    *h = o;
+    return 0;
+}
+int pdo_lstsq_destroy(pdo_lstsq_t h) {
+    if (!h) return 0;
+    if (h->periodic) banded_op_destroy(&h->op);
+    else np_op_destroy(&h->np);
+    delete h;
+    return 0;
+}
+#define PDO_LSTSQ_FN(name, axis)                                                                \
+    int name(pdo_lstsq_t h, const double* f, double* fil, int na, int nb, void* stream) {     \
+        if (!h) return fail(PDO_E_BADARG, "null handle");                                       \
+        if (!h->periodic) return apply_np(h->np, true, axis, f, fil, na, nb, 0, 0, stream);     \
+        return apply(h->op, true, axis, f, fil, na, nb, stream);                                \
+    }
+PDO_LSTSQ_FN(pdo_lstsq_filter1, 0)
+PDO_LSTSQ_FN(pdo_lstsq_filter2, 1)
+PDO_LSTSQ_FN(pdo_lstsq_filter3, 2)
+
 // ---------------- cd06stagg (periodic) ----------------
 int pdo_cd06stagg_init_periodic(pdo_cd06stagg_t* h, int n, double dx) {
     if (!h) return fail(PDO_E_BADARG, "null handle");
@@ -694,7 +737,7 @@ int pdo_filters_init(pdo_filters_t* h, const int xsz[3], const int ysz[3], const
     const int n[3] = {xsz[0], ysz[1], zsz[2]};
     const int per[3] = {px, py, pz};
     const char* m[3] = {mx, my, mz};
-    for (int a = 0; a < 3; ++a) { o->cf[a] = nullptr; o->ga[a] = nullptr; }
+    for (int a = 0; a < 3; ++a) { o->cf[a] = nullptr; o->ga[a] = nullptr; o->ls[a] = nullptr; }
     for (int a = 0; a < 3; ++a) {
         int rc;
         if (std::strncmp(m[a], "cf90", 4) == 0) {
@@ -703,8 +746,11 @@ int pdo_filters_init(pdo_filters_t* h, const int xsz[3], const int ysz[3], const
         } else if (std::strncmp(m[a], "gaussian", 8) == 0) {
             o->method[a] = 1;
             rc = pdo_gaussian_init(&o->ga[a], n[a], per[a]);
+        } else if (std::strncmp(m[a], "lstsq", 5) == 0) {
+            o->method[a] = 2;
+            rc = pdo_lstsq_init(&o->ls[a], n[a], per[a]);
         } else {
-            rc = fail(PDO_E_UNSUPPORTED, "filters: method '%s' is out of scope (cf90, gaussian only; SURVEY.md 2.1 #9)", m[a]);
+            rc = fail(52, "Incorrect method select in direction %c", "XYZ"[a]);   // filters.F90:120, 151, 181 ("spectral" is not built)
         }
         if (rc) {
             pdo_filters_destroy(o);
@@ -716,7 +762,7 @@ int pdo_filters_init(pdo_filters_t* h, const int xsz[3], const int ysz[3], const
 }
 int pdo_filters_destroy(pdo_filters_t h) {
     if (!h) return 0;
-    for (int a = 0; a < 3; ++a) { pdo_cf90_destroy(h->cf[a]); pdo_gaussian_destroy(h->ga[a]); }
+    for (int a = 0; a < 3; ++a) { pdo_cf90_destroy(h->cf[a]); pdo_gaussian_destroy(h->ga[a]); pdo_lstsq_destroy(h->ls[a]); }
     delete h;
     return 0;
 }
@@ -731,6 +777,11 @@ static int fil_apply(pdo_filters_t h, int axis, const double* f, double* out, in
         typedef int (*fn_t)(pdo_cf90_t, const double*, double*, int, int, int, int, void*);
         static const fn_t fns[3] = {pdo_cf90_filter1, pdo_cf90_filter2, pdo_cf90_filter3};
         return fns[axis](h->cf[axis], f, out, na, nb, bc1, bcn, st);
+    }
+    if (h->method[axis] == 2) {   // filters.F90:231, 248, 265: the least-squares filter takes no boundary codes
+        typedef int (*fnl_t)(pdo_lstsq_t, const double*, double*, int, int, void*);
+        static const fnl_t fl[3] = {pdo_lstsq_filter1, pdo_lstsq_filter2, pdo_lstsq_filter3};
+        return fl[axis](h->ls[axis], f, out, na, nb, st);
     }
     typedef int (*fng_t)(pdo_gaussian_t, const double*, double*, int, int, int, int, void*);
     static const fng_t fg[3] = {pdo_gaussian_filter1, pdo_gaussian_filter2, pdo_gaussian_filter3};

@@ -9,6 +9,7 @@ struct pdo_cd10_s { int n; pdo::BandedOp d1, d2; bool periodic = true; pdo::NpOp
 struct pdo_cd06_s { int n; pdo::BandedOp d1; bool periodic = true; pdo::NpOp np; };
 struct pdo_cf90_s { int n; pdo::BandedOp op; bool periodic = true; pdo::NpOp np; };
 struct pdo_gaussian_s { int n; pdo::BandedOp op; bool periodic = true; pdo::NpOp np; };
+struct pdo_lstsq_s { int n; pdo::BandedOp op; bool periodic = true; pdo::NpOp np; };
 struct pdo_cd06stagg_s { int n; pdo::BandedOp ops[6]; bool periodic = true; pdo::StaggNp np; };   // np: init_nonperiodic (walls)
 struct pdo_derivatives_s {
     int xsz[3], ysz[3], zsz[3];
@@ -18,7 +19,8 @@ struct pdo_derivatives_s {
 };
 struct pdo_filters_s {
     int xsz[3], ysz[3], zsz[3];
-    int method[3];  // 0 cf90, 1 gaussian
+    int method[3];  // 0 cf90, 1 gaussian, 2 lstsq
     pdo_cf90_t cf[3];
     pdo_gaussian_t ga[3];
+    pdo_lstsq_t ls[3];
 };

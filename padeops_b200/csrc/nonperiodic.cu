@@ -101,8 +101,12 @@ int np_build_coefs(int kind, double dx, NpCoefs* c) {
         c->r2[0] = b2_a90; c->r2[1] = b2_b90;
         c->r3[0] = b3_a90; c->r3[1] = b3_b90; c->r3[2] = b3_c90;
         c->r4[0] = b4_a90; c->r4[1] = b4_b90; c->r4[2] = b4_c90; c->r4[3] = b4_d90;
-    } else if (kind == NP_GAUSS) {     // gaussian.F90:15-46
-        c->in[0] = 3565.0 / 10368.0; c->in[1] = 3091.0 / 12960.0; c->in[2] = 1997.0 / 25920.0; c->in[3] = 149.0 / 12960.0; c->in[4] = 107.0 / 103680.0;
+    } else if (kind == NP_GAUSS || kind == NP_LSTSQ) {     // gaussian.F90:15-46, lstsq.F90:14-46 (the same boundary rows)
+        if (kind == NP_GAUSS) {
+            c->in[0] = 3565.0 / 10368.0; c->in[1] = 3091.0 / 12960.0; c->in[2] = 1997.0 / 25920.0; c->in[3] = 149.0 / 12960.0; c->in[4] = 107.0 / 103680.0;
+        } else {
+            c->in[0] = 0.5; c->in[1] = 0.6744132 / 2.0; c->in[2] = 0.0 / 2.0; c->in[3] = -0.1744132 / 2.0; c->in[4] = 0.0 / 2.0;
+        }
         c->r1[0] = 5.0 / 6.0; c->r1[1] = 1.0 / 6.0;
         c->r2[0] = 2.0 / 3.0; c->r2[1] = 1.0 / 6.0;
         c->r3[0] = 31.0 / 64.0; c->r3[1] = 7.0 / 32.0; c->r3[2] = 5.0 / 128.0;
@@ -258,7 +262,7 @@ cudaError_t np_op_create(NpOp* h, int kind, int n, double dx, int* ierr_out) {
     for (auto& p : h->d_tab) p = nullptr;
     if (np_build_coefs(kind, dx, &h->co) != 0) return cudaErrorInvalidValue;
     if (n == 1) return cudaSuccess;   // degenerate: handled by the callers (derivative 0 / filter identity)
-    if (kind == NP_GAUSS) {           // explicit filter: no system, no tables
+    if (kind == NP_GAUSS || kind == NP_LSTSQ) {           // explicit filters: no system, no tables
         if (n < 8) *ierr_out = 1001;
         return cudaSuccess;
     }
@@ -289,7 +293,7 @@ cudaError_t np_op_apply(const NpOp* h, int axis, const double* f, double* out, l
     const long long tot = n1 * h->n * n3;
     if (tot == 0) return cudaSuccess;
     const unsigned gb = blocks_for(tot, 256);
-    if (h->kind == NP_GAUSS) {
+    if (h->kind == NP_GAUSS || h->kind == NP_LSTSQ) {   // the two kinds differ in their coefficients only
         np_rhs_kernel<NP_GAUSS><<<gb, 256, 0, st>>>(f, out, n1, h->n, n3, bc1, bcn, h->co);
         return cudaGetLastError();
     }
@@ -307,7 +311,7 @@ int np_apply_host(int kind, int n, double dx, int bc1, int bcn, int axis, const 
     NpCoefs co;
     if (np_build_coefs(kind, dx, &co) != 0) return -1;
     std::vector<double> tab(5 * (size_t)n);
-    if (kind == NP_GAUSS) { if (n < 8) return 1001; }
+    if (kind == NP_GAUSS || kind == NP_LSTSQ) { if (n < 8) return 1001; }
     else if (int rc = np_build_table(kind, n, bc1, bcn, tab.data())) return rc;
     long long n1, n3;
     shape(axis, n, na, nb, &n1, &n3);
@@ -320,11 +324,11 @@ int np_apply_host(int kind, int n, double dx, int bc1, int bcn, int axis, const 
                 if (kind == NP_CD06_D1) v = np_rhs_point<NP_CD06_D1>(i + 1, n, bc1, bcn, co, F);
                 else if (kind == NP_CD10_D1) v = np_rhs_point<NP_CD10_D1>(i + 1, n, bc1, bcn, co, F);
                 else if (kind == NP_CD10_D2) v = np_rhs_point<NP_CD10_D2>(i + 1, n, bc1, bcn, co, F);
-                else if (kind == NP_GAUSS) v = np_rhs_point<NP_GAUSS>(i + 1, n, bc1, bcn, co, F);
+                else if (kind == NP_GAUSS || kind == NP_LSTSQ) v = np_rhs_point<NP_GAUSS>(i + 1, n, bc1, bcn, co, F);
                 else v = np_rhs_point<NP_CF90>(i + 1, n, bc1, bcn, co, F);
                 y[(long long)i * n1] = v;
             }
-            if (kind != NP_GAUSS) np_solve_line(y, n1, n, tab.data());
+            if (kind != NP_GAUSS && kind != NP_LSTSQ) np_solve_line(y, n1, n, tab.data());
         }
     return 0;
 }

@@ -16,7 +16,7 @@
 
 namespace pdo {
 
-enum NpKind { NP_CD10_D1 = 0, NP_CD10_D2 = 1, NP_CF90 = 2, NP_CD06_D1 = 3, NP_GAUSS = 4 };   // CD06: one-sided closure only (cd06.F90:264-327); Gaussian: explicit, no solve (gaussian.F90:22-46, 215-330)
+enum NpKind { NP_CD10_D1 = 0, NP_CD10_D2 = 1, NP_CF90 = 2, NP_CD06_D1 = 3, NP_GAUSS = 4, NP_LSTSQ = 5 };   // CD06: one-sided closure only (cd06.F90:264-327); Gaussian / least-squares: explicit, no solve (gaussian.F90:22-46, 215-330; lstsq.F90:14-46, 169-212)
 
 struct NpCoefs {
     double in[5];     // interior stencil: D1/D2: a, b, c (grid spacing folded in); CF90: a, b, c, d, e
@@ -51,7 +51,7 @@ PDO_HD double np_rhs_point(int i, int n, int bc1, int bcn, const NpCoefs& c, Acc
             if (i == 2) return c.r2[0] * (F(3) - F(1));
             return c.r3[0] * (F(4) - F(2)) + c.r3[1] * (F(5) - F(1));
         } else {
-            if (i == 1) return KIND == NP_GAUSS ? c.r1[0] * (F(1)) + c.r1[1] * (F(2)) : c.r1[0] * (F(1));
+            if (i == 1) return (KIND == NP_GAUSS || KIND == NP_LSTSQ) ? c.r1[0] * (F(1)) + c.r1[1] * (F(2)) : c.r1[0] * (F(1));
             if (i == 2) return c.r2[0] * (F(2)) + c.r2[1] * (F(3) + F(1));
             if (i == 3) return c.r3[0] * (F(3)) + c.r3[1] * (F(4) + F(2)) + c.r3[2] * (F(5) + F(1));
             return c.r4[0] * (F(4)) + c.r4[1] * (F(5) + F(3)) + c.r4[2] * (F(6) + F(2)) + c.r4[3] * (F(7) + F(1));
@@ -73,7 +73,7 @@ PDO_HD double np_rhs_point(int i, int n, int bc1, int bcn, const NpCoefs& c, Acc
             if (m == 2) return c.r2[0] * (F(n) - F(n - 2));
             return c.r3[0] * (F(n - 1) - F(n - 3)) + c.r3[1] * (F(n) - F(n - 4));
         } else {
-            if (m == 1) return KIND == NP_GAUSS ? c.r1[0] * (F(n)) + c.r1[1] * (F(n - 1)) : c.r1[0] * (F(n));
+            if (m == 1) return (KIND == NP_GAUSS || KIND == NP_LSTSQ) ? c.r1[0] * (F(n)) + c.r1[1] * (F(n - 1)) : c.r1[0] * (F(n));
             if (m == 2) return c.r2[0] * (F(n - 1)) + c.r2[1] * (F(n) + F(n - 2));
             if (m == 3) return c.r3[0] * (F(n - 2)) + c.r3[1] * (F(n - 1) + F(n - 3)) + c.r3[2] * (F(n) + F(n - 4));
             return c.r4[0] * (F(n - 3)) + c.r4[1] * (F(n - 2) + F(n - 4)) + c.r4[2] * (F(n - 1) + F(n - 5)) + c.r4[3] * (F(n) + F(n - 6));

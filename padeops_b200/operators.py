@@ -152,6 +152,18 @@ class gaussian(_Filter):
     _prefix = "gaussian"
 
 
+class lstsq(_Filter):
+    """lstsqstuff::lstsq (filters/lstsq.F90): filter1/2/3(f, fil, na, nb) take no boundary codes"""
+    _prefix = "lstsq"
+
+    def _call(self, fn, f, out, na, nb, bc1, bcn, stream):
+        _contig(f)
+        if out is None:
+            out = _alloc_like(f)
+        check(getattr(lib(), f"pdo_lstsq_{fn}")(self._h, ptr(f), ptr(out), int(na), int(nb), stream_ptr(stream)))
+        return out
+
+
 class cd06stagg:
     """Staggered CD06 in z, periodic or with walls.  Cells: n planes; edges: n+1 planes (periodic: plane n+1 == plane 1)."""
 

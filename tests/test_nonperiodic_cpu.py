@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-KINDS = {"cd10_d1": 0, "cd10_d2": 1, "cf90": 2, "cd06_d1": 3, "gaussian": 4}
+KINDS = {"cd10_d1": 0, "cd10_d2": 1, "cf90": 2, "cd06_d1": 3, "gaussian": 4, "lstsq": 5}
 
 
 def product_host(pdo, kind, f, dx, axis, bc1, bcn):
@@ -28,6 +28,8 @@ def oracle_ref(oracle, kind, f, dx, axis, bc1, bcn):
         return oracle.cd06_np(f, dx, axis)
     if kind == "gaussian":
         return oracle.gaussian_np(f, axis, bc1, bcn)
+    if kind == "lstsq":
+        return oracle.lstsq_np(f, axis)
     return oracle.cd10_np(f, dx, axis, 1 if kind == "cd10_d1" else 2, bc1, bcn)
 
 
@@ -36,8 +38,8 @@ def oracle_ref(oracle, kind, f, dx, axis, bc1, bcn):
 @pytest.mark.parametrize("bc1", [0, 1, -1])
 @pytest.mark.parametrize("bcn", [0, 1, -1])
 def test_product_np_routines_match_oracle(pdo, oracle, kind, axis, bc1, bcn):
-    if kind == "cd06_d1" and (bc1, bcn) != (0, 0):
-        pytest.skip("cd06 has the one-sided closure only")
+    if kind in ("cd06_d1", "lstsq") and (bc1, bcn) != (0, 0):
+        pytest.skip("cd06 and lstsq have the one-sided closure only")
     shape = {0: (3, 4, 19), 1: (3, 19, 4), 2: (19, 3, 4)}[axis]
     rng = np.random.default_rng(1000 + 100 * axis + 10 * bc1 + bcn)
     f = rng.standard_normal(shape)

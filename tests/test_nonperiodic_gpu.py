@@ -121,3 +121,27 @@ def test_gaussian_nonperiodic_all_boundary_codes(pdo, oracle, axis):
         a = _dev(g)
         ops.filter3D(fl, a, 2, z_bc=(0, 1))
         assert _rel(a.cpu().numpy(), oracle.filter3D(g, 2, ("cf90", "gaussian", "gaussian"), (True, True, False), z_bc=(0, 1))) < TOL
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's last GPU session (the Gaussian filter's kernels with the least-squares coefficients)")
+def test_lstsq_filter_periodic_and_walls(pdo, oracle):
+    """lstsq%filter1/2/3 (filters/lstsq.F90), alone and through the filters dispatch type (method "lstsq", filters.F90:111-118)"""
+    n = 40
+    for axis in (0, 1, 2):
+        shape = {0: (5, 6, n), 1: (5, n, 6), 2: (n, 5, 6)}[axis]
+        f = np.random.default_rng(20 + axis).standard_normal(shape)
+        for periodic in (True, False):
+            h = pdo.lstsq()
+            assert h.init(n, periodic_=periodic) == 0
+            got = (h.filter1, h.filter2, h.filter3)[axis](_dev(f)).cpu().numpy()
+            assert _rel(got, oracle.lstsq(f, axis) if periodic else oracle.lstsq_np(f, axis)) < TOL, (axis, periodic)
+    nz, ny, nx = 24, 16, 20
+    g = np.random.default_rng(7).standard_normal((nz, ny, nx))
+    gp = pdo.decomp_2d.init(nx, ny, nz, 1, 1)
+    fl = pdo.filters()
+    fl.init(gp, True, True, False, "lstsq", "cf90", "lstsq")
+    assert _rel(fl.filterx(_dev(g)).cpu().numpy(), oracle.lstsq(g, 0)) < TOL
+    assert _rel(fl.filterz(_dev(g)).cpu().numpy(), oracle.lstsq_np(g, 2)) < TOL
+    with pytest.raises(pdo.PadeOpsError) as e:
+        pdo.filters().init(gp, True, True, True, "spectral", "cf90", "cf90")
+    assert e.value.code == 52

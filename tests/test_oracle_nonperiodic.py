@@ -205,3 +205,21 @@ def test_gaussian_nonperiodic_closures(oracle):
         a = oracle.gaussian_np(g, axis, 0, 1)
         b = np.moveaxis(oracle.gaussian_np(np.ascontiguousarray(np.moveaxis(g, {1: 1, 2: 0}[axis], 2)), 0, 0, 1), 2, {1: 1, 2: 0}[axis])
         assert np.array_equal(a, b)
+
+
+def test_lstsq_filter(oracle):
+    """lstsq%filter* (filters/lstsq.F90): the Gaussian filter's structure with the least-squares coefficients — transfer function
+    0.5 + 0.6744132 cos w - 0.1744132 cos 3w (T(0) = 1, T(pi) = 0), the Gaussian's one-sided rows when non-periodic."""
+    n = 32
+    x = np.arange(n) * 2 * np.pi / n
+    for k in (0, 3, 16):
+        f = np.cos(k * x)[None, None, :] + np.zeros((2, 3, n))
+        T = 0.5 + 0.6744132 * np.cos(2 * np.pi * k / n) - 0.1744132 * np.cos(3 * 2 * np.pi * k / n)
+        assert np.abs(oracle.lstsq(f, 0) - T * f).max() < 1e-14
+    assert abs(0.5 + 0.6744132 - 0.1744132 - 1.0) < 1e-15 and abs(0.5 - 0.6744132 + 0.1744132) < 1e-15
+    f = np.random.default_rng(4).standard_normal((2, 3, n))
+    got = oracle.lstsq_np(f, 0)
+    assert np.array_equal(got[..., :4], oracle.gaussian_np(f, 0, 0, 0)[..., :4]) and np.array_equal(got[..., -4:], oracle.gaussian_np(f, 0, 0, 0)[..., -4:])
+    assert np.allclose(got[..., 4:n - 4], oracle.lstsq(f, 0)[..., 4:n - 4], rtol=0, atol=1e-15)
+    g = np.random.default_rng(5).standard_normal((n, 12, 10))
+    assert np.allclose(oracle.lstsq(g, 2), np.moveaxis(oracle.lstsq(np.ascontiguousarray(np.moveaxis(g, 0, 2)), 0), 2, 0), rtol=0, atol=0)
