@@ -1,0 +1,413 @@
+// ig_padepoisson.inc.cuh — part of igrid.cu: textually included there, ONE translation unit (the sections share file-local helpers).
+// PadePoissonMod::padepoisson: periodic and wall-bounded projection, pressure, divergence check, C ABI.
+// Not a stand-alone header: do not include it anywhere else.
+
+// ================================================================================================
+// padepoisson (periodic in z)
+// ================================================================================================
+struct pdo_padepoisson_s {
+    pdo_spectral_t sp = nullptr, spE = nullptr;
+    pdo_pade6stagg_t derivZ = nullptr;
+    pdo_decomp_t dC = nullptr, dE = nullptr;  // spectral decompositions of the cell / edge grids (borrowed from sp / spE)
+    pdo_decomp_info sC, sE;
+    double *k1sq = nullptr, *k2sq = nullptr, *k3sq = nullptr;  // z-pencil slices of GetWaveNums(nx,dx)^2, (ny,dy)^2; k3mod^2
+    double mfact = 1.0;
+    double2 *f2d = nullptr, *f2dy = nullptr, *w2 = nullptr, *uhatInZ = nullptr, *dwdz = nullptr;
+    double* div_tmp = nullptr;  // real x-pencil, used when the caller passes no divergence array
+    bool alias = false;         // one rank in the column communicator: y- and z-pencil layouts coincide, transposes are skipped
+    const double2* phat_y = nullptr;  // where the last projection left the pressure (y-pencil layout)
+    // PeriodicInZ = .false. (walls; PadePoisson.F90:180-230, 459-623): even / odd extensions to 2 nz planes and their tables
+    bool periodic_in_z = true;
+    double2 *fext = nullptr, *wext = nullptr, *k3modcm = nullptr, *k3modcp = nullptr;
+    double* k3sq_ext = nullptr;
+    ZColsPlan ext_plan;
+};
+
+namespace {
+
+// f2dy = i (k1 u + k2 v)   (PadePoisson.F90:392-401)
+int poiss_div_xy(pdo_padepoisson_s* p, const double2* u, const double2* v, double2* out, cudaStream_t st) {
+    const pdo_spectral_s* s = p->sp;
+    const int n1 = s->si.ysz[0], n2 = s->si.ysz[1];
+    const double *k1 = s->k1y, *k2 = s->k2;
+    return launch_ew(vol(s->si.ysz), st, [=] __device__(long long i) {
+        const double a = k1[(int)(i % n1)], b = k2[(int)((i / n1) % n2)];
+        const double2 uu = u[i], vv = v[i];
+        const double re = a * uu.x + b * vv.x, im = a * uu.y + b * vv.y;
+        out[i] = make_double2(-im, re);
+    });
+}
+
+// steps shared by PeriodicProjection / Periodic_getPressure*: leaves phat in f2d (z-pencil) and what in w2 (z-pencil)
+int poiss_solve(pdo_padepoisson_s* p, const double2* uhat, const double2* vhat, const double2* what, cudaStream_t st) {
+    if (int rc = poiss_div_xy(p, uhat, vhat, p->f2dy, st)) return rc;
+    const double2 *uz = p->f2dy, *wz = what;
+    if (!p->alias) {
+        if (int rc = decomp_transpose_device(p->dC, 2, (const double*)p->f2dy, (double*)p->uhatInZ, 2, st)) return rc;
+        if (int rc = decomp_transpose_device(p->dE, 2, (const double*)what, (double*)p->w2, 2, st)) return rc;
+        uz = p->uhatInZ; wz = p->w2;
+    }
+    if (int rc = pdo_pade6stagg_ddz_E2C(p->derivZ, (const double*)wz, (double*)p->f2d, 1, 0, 0, st)) return rc;
+    const long long n = vol(p->sC.zsz);
+    double2* f2d = p->f2d;
+    if (int rc = launch_ew(n, st, [=] __device__(long long i) { double2 a = f2d[i]; const double2 b = uz[i]; a.x += b.x; a.y += b.y; f2d[i] = a; })) return rc;
+    if (int rc = fft3d_z_inplace(p->sp->ft, f2d, -1, st)) return rc;
+    const int n1 = p->sC.zsz[0], n2 = p->sC.zsz[1];
+    const double *k1sq = p->k1sq, *k2sq = p->k2sq, *k3sq = p->k3sq;
+    const double mfact = p->mfact;
+    if (int rc = launch_ew(n, st, [=] __device__(long long i) {  // f2d = -kradsq_inv f2d, mfact folded in (:413-415, 103-108)
+            const int ii = (int)(i % n1);
+            const long long t = i / n1;
+            const int jj = (int)(t % n2), kk = (int)(t / n2);
+            const double kradsq = k1sq[ii] + k2sq[jj] + k3sq[kk];
+            const double m = (kradsq <= 1.e-14) ? 0.0 : -(1.0 / kradsq) * mfact;
+            double2 a = f2d[i];
+            a.x *= m; a.y *= m;
+            f2d[i] = a;
+        })) return rc;
+    return fft3d_z_inplace(p->sp->ft, f2d, +1, st);
+}
+
+// w2 -= ddz_C2E(f2d); what <- w2; f2dy <- f2d; u -= i k1 p, v -= i k2 p   (:417-431)
+int poiss_correct(pdo_padepoisson_s* p, double2* uhat, double2* vhat, double2* what, cudaStream_t st) {
+    if (int rc = pdo_pade6stagg_ddz_C2E(p->derivZ, (const double*)p->f2d, (double*)p->dwdz, 1, 0, 0, st)) return rc;
+    double2* w2 = p->alias ? what : p->w2;
+    const double2* dw = p->dwdz;
+    if (int rc = launch_ew(vol(p->sE.zsz), st, [=] __device__(long long i) { double2 a = w2[i]; const double2 b = dw[i]; a.x -= b.x; a.y -= b.y; w2[i] = a; })) return rc;
+    const double2* ph = p->f2d;
+    if (!p->alias) {
+        if (int rc = decomp_transpose_device(p->dE, 3, (const double*)p->w2, (double*)what, 2, st)) return rc;
+        if (int rc = decomp_transpose_device(p->dC, 3, (const double*)p->f2d, (double*)p->f2dy, 2, st)) return rc;
+        ph = p->f2dy;
+    }
+    p->phat_y = ph;
+    const pdo_spectral_s* s = p->sp;
+    const int n1 = s->si.ysz[0], n2 = s->si.ysz[1];
+    const double *k1 = s->k1y, *k2 = s->k2;
+    return launch_ew(vol(s->si.ysz), st, [=] __device__(long long i) {
+        const double a = k1[(int)(i % n1)], b = k2[(int)((i / n1) % n2)];
+        const double2 q = ph[i];
+        double2 uu = uhat[i], vv = vhat[i];
+        uu.x += a * q.y; uu.y -= a * q.x;  // u - i k1 p
+        vv.x += b * q.y; vv.y -= b * q.x;
+        uhat[i] = uu; vhat[i] = vv;
+    });
+}
+
+int poiss_divergence(pdo_padepoisson_s* p, const double2* uhat, const double2* vhat, const double2* what, double* div, cudaStream_t st) {
+    const double2* wz = what;
+    if (!p->alias) {
+        if (int rc = decomp_transpose_device(p->dE, 2, (const double*)what, (double*)p->w2, 2, st)) return rc;
+        wz = p->w2;
+    }
+    if (int rc = pdo_pade6stagg_ddz_E2C(p->derivZ, (const double*)wz, (double*)p->f2d, 1, -1, -1, st)) return rc;
+    double2* f = p->f2d;
+    if (!p->alias) {
+        if (int rc = decomp_transpose_device(p->dC, 3, (const double*)p->f2d, (double*)p->f2dy, 2, st)) return rc;
+        f = p->f2dy;
+    }
+    const pdo_spectral_s* s = p->sp;
+    const int n1 = s->si.ysz[0], n2 = s->si.ysz[1];
+    const double *k1 = s->k1y, *k2 = s->k2;
+    if (int rc = launch_ew(vol(s->si.ysz), st, [=] __device__(long long i) {  // + i k1 u + i k2 v  (:1191-1200)
+            const double a = k1[(int)(i % n1)], b = k2[(int)((i / n1) % n2)];
+            const double2 uu = uhat[i], vv = vhat[i];
+            double2 q = f[i];
+            q.x += -a * uu.y - b * vv.y;
+            q.y += a * uu.x + b * vv.x;
+            f[i] = q;
+        })) return rc;
+    return fft3d_backward_yx(s->ft, f, div, false, st);
+}
+
+// p_maxval(maxval(a)) (use_abs = 0, as DivergenceCheck does) or of |a|
+int global_max(pdo_spectral_s* s, const double* a, long long n, int use_abs, double* out, cudaStream_t st) {
+    const int blocks = 1024;
+    max_kernel<<<blocks, 256, 0, st>>>(a, n, use_abs, s->partial);
+    PDO_CUDA(cudaGetLastError());
+    g_launches += 1;
+    double hpart[1024];
+    PDO_CUDA(cudaMemcpyAsync(hpart, s->partial, sizeof(double) * blocks, cudaMemcpyDeviceToHost, st));
+    PDO_CUDA(cudaStreamSynchronize(st));
+    double m = -1.0e300;
+    for (int i = 0; i < blocks; ++i) m = hpart[i] > m ? hpart[i] : m;
+    return pdo_p_maxval(m, out);
+}
+
+// PressureProjection with walls, computeStokesPressure = .false. (PadePoisson.F90:459-623): the horizontal divergence is extended
+// evenly and w oddly about both walls to 2 nz planes, one c2c-z pair solves and projects (the half-cell shifts ride on
+// k3modcm / k3modcp), the upper halves come back and w is zero on both walls.
+int poiss_wall_projection(pdo_padepoisson_s* p, double2* uhat, double2* vhat, double2* what, cudaStream_t st) {
+    if (int rc = poiss_div_xy(p, uhat, vhat, p->f2dy, st)) return rc;                       // Step 1
+    const double2 *uz = p->f2dy, *wz = what;
+    if (!p->alias) {                                                                          // Step 2
+        if (int rc = decomp_transpose_device(p->dC, 2, (const double*)p->f2dy, (double*)p->uhatInZ, 2, st)) return rc;
+        if (int rc = decomp_transpose_device(p->dE, 2, (const double*)what, (double*)p->w2, 2, st)) return rc;
+        uz = p->uhatInZ; wz = p->w2;
+    }
+    const int nz = p->sp->nz, n1 = p->sC.zsz[0], n2 = p->sC.zsz[1];
+    const long long cols = (long long)n1 * n2, next = cols * 2 * nz;
+    double2 *fe = p->fext, *we = p->wext;
+    if (int rc = launch_ew(next, st, [=] __device__(long long i) {                            // Step 3
+            const long long c = i % cols;
+            const int kk = (int)(i / cols);
+            fe[i] = kk < nz ? uz[c + cols * (nz - 1 - kk)] : uz[c + cols * (kk - nz)];
+            if (kk < nz - 1) { const double2 a = wz[c + cols * (nz - 1 - kk)]; we[i] = make_double2(-a.x, -a.y); }
+            else we[i] = wz[c + cols * (kk - (nz - 1))];
+        })) return rc;
+    if (int rc = zcols_exec(&p->ext_plan, 2 * nz, cols, fe, -1, st)) return rc;               // Step 4
+    if (int rc = zcols_exec(&p->ext_plan, 2 * nz, cols, we, -1, st)) return rc;
+    const double *k1sq = p->k1sq, *k2sq = p->k2sq, *k3sq = p->k3sq_ext;
+    const double2 *cm = p->k3modcm, *cp = p->k3modcp;
+    const double mfact = p->mfact;
+    if (int rc = launch_ew(next, st, [=] __device__(long long i) {                            // Steps 5-6 (+ mfact of Step 7)
+            const int ii = (int)(i % n1);
+            const long long t = i / n1;
+            const int jj = (int)(t % n2), kk = (int)(t / n2);
+            const double kradsq = k1sq[ii] + k2sq[jj] + k3sq[kk];
+            const double kinv = (kradsq <= 1.e-14) ? 0.0 : 1.0 / kradsq;
+            double2 f = fe[i], w = we[i];
+            const double2 a = cm[kk], b = cp[kk];
+            // f = f + i cm w;  f = -f kinv
+            f.x += -(a.x * w.y + a.y * w.x);
+            f.y += a.x * w.x - a.y * w.y;
+            f.x = -f.x * kinv; f.y = -f.y * kinv;
+            // w = w - i cp f
+            w.x -= -(b.x * f.y + b.y * f.x);
+            w.y -= b.x * f.x - b.y * f.y;
+            fe[i] = make_double2(f.x * mfact, f.y * mfact);
+            we[i] = make_double2(w.x * mfact, w.y * mfact);
+        })) return rc;
+    if (int rc = zcols_exec(&p->ext_plan, 2 * nz, cols, fe, +1, st)) return rc;               // Step 7
+    if (int rc = zcols_exec(&p->ext_plan, 2 * nz, cols, we, +1, st)) return rc;
+    double2* f2d = p->f2d;
+    double2* w2 = p->alias ? what : p->w2;
+    if (int rc = launch_ew(cols * (nz + 1), st, [=] __device__(long long i) {
+            const int kk = (int)(i / cols);
+            if (kk < nz) f2d[i] = fe[i + cols * nz];
+            w2[i] = (kk == 0 || kk == nz) ? make_double2(0.0, 0.0) : we[i + cols * (nz - 1)];
+        })) return rc;
+    const double2* ph = p->f2d;
+    if (!p->alias) {                                                                          // Step 8
+        if (int rc = decomp_transpose_device(p->dE, 3, (const double*)p->w2, (double*)what, 2, st)) return rc;
+        if (int rc = decomp_transpose_device(p->dC, 3, (const double*)p->f2d, (double*)p->f2dy, 2, st)) return rc;
+        ph = p->f2dy;
+    }
+    p->phat_y = ph;
+    const pdo_spectral_s* s = p->sp;
+    const int m1 = s->si.ysz[0], m2 = s->si.ysz[1];
+    const double *k1 = s->k1y, *k2 = s->k2;
+    return launch_ew(vol(s->si.ysz), st, [=] __device__(long long i) {                        // Step 9
+        const double a = k1[(int)(i % m1)], b = k2[(int)((i / m1) % m2)];
+        const double2 q = ph[i];
+        double2 uu = uhat[i], vv = vhat[i];
+        uu.x += a * q.y; uu.y -= a * q.x;
+        vv.x += b * q.y; vv.y -= b * q.x;
+        uhat[i] = uu; vhat[i] = vv;
+    });
+}
+
+int poiss_projection(pdo_padepoisson_s* p, double2* u, double2* v, double2* w, cudaStream_t st) {
+    if (!p->periodic_in_z) return poiss_wall_projection(p, u, v, w, st);
+    if (int rc = poiss_solve(p, u, v, w, st)) return rc;
+    return poiss_correct(p, u, v, w, st);
+}
+
+int poiss_divergence_check(pdo_padepoisson_s* p, double2* u, double2* v, double2* w, double* div, bool fix, double* max_div, cudaStream_t st) {
+    if (!div) div = p->div_tmp;
+    const long long n = vol(p->sp->pi.xsz);
+    if (int rc = poiss_divergence(p, u, v, w, div, st)) return rc;
+    double md = 0.0;
+    if (fix || max_div) { if (int rc = global_max(p->sp, div, n, 0, &md, st)) return rc; }
+    if (fix && md > 1.e-13) {  // PadePoisson.F90:1209-1241
+        if (int rc = poiss_projection(p, u, v, w, st)) return rc;
+        if (int rc = poiss_divergence(p, u, v, w, div, st)) return rc;
+        if (int rc = global_max(p->sp, div, n, 0, &md, st)) return rc;
+        if (md > 1.e-10) { if (int rc = poiss_projection(p, u, v, w, st)) return rc; }
+    }
+    if (max_div) *max_div = md;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pdo_padepoisson_init(pdo_padepoisson_t* h, double dx, double dy, double dz, pdo_spectral_t sp, pdo_spectral_t spE,
+                         pdo_pade6stagg_t derivZ) {
+    return pdo_padepoisson_init2(h, dx, dy, dz, sp, spE, derivZ, 1);
+}
+int pdo_padepoisson_init2(pdo_padepoisson_t* h, double dx, double dy, double dz, pdo_spectral_t sp, pdo_spectral_t spE,
+                          pdo_pade6stagg_t derivZ, int periodic_in_z) {
+    if (!h || !sp || !spE || !derivZ) return fail(PDO_E_BADARG, "null argument");
+    *h = nullptr;
+    if (spE->nz != sp->nz + 1 || spE->nx != sp->nx || spE->ny != sp->ny) return fail(PDO_E_BADARG, "spE must be the (nx, ny, nz+1) edge type of sp");
+    if (periodic_in_z && !derivZ->periodic)
+        return fail(PDO_E_BADARG, "padepoisson: PeriodicInZ = .true. needs a derivZ initialised with isPeriodic = .true.");
+    if (!periodic_in_z && derivZ->periodic)
+        return fail(PDO_E_BADARG, "padepoisson: PeriodicInZ = .false. needs a derivZ initialised with isPeriodic = .false.");
+    // PadePoisson.F90:215-218 — the two decompositions must split x and y identically in the z-pencil
+    if (sp->si.zst[0] != spE->si.zst[0] || sp->si.zst[1] != spE->si.zst[1])
+        return fail(423, "Failed at initializing Padepoisson. sp_gp and sp_gpE have different x and y starts in z-decomp");
+    pdo_padepoisson_s* p = new (std::nothrow) pdo_padepoisson_s();
+    if (!p) return fail(PDO_E_BADARG, "out of memory");
+    p->sp = sp; p->spE = spE; p->derivZ = derivZ;
+    p->dC = fft3d_spec_decomp(sp->ft); p->dE = fft3d_spec_decomp(spE->ft);
+    p->sC = sp->si; p->sE = spE->si;
+    const int nz = sp->nz;
+    // InitPeriodicPoissonSolver (:76-128): k1, k2 straight from GetWaveNums (no oddball flip), k3 through the z scheme's symbol
+    std::vector<double> k1 = wavenums(sp->nx, dx), k2 = wavenums(sp->ny, dy), k3 = wavenums(nz, dz), k3m(nz);
+    pdo_pade6stagg_get_modified_wavenumbers(derivZ, k3.data(), k3m.data(), nz);
+    for (auto& v : k1) v = v * v;
+    for (auto& v : k2) v = v * v;
+    for (auto& v : k3m) v = v * v;
+    int rc = upload(&p->k1sq, k1, p->sC.zst[0] - 1, p->sC.zsz[0]);
+    if (!rc) rc = upload(&p->k2sq, k2, p->sC.zst[1] - 1, p->sC.zsz[1]);
+    if (!rc) rc = upload(&p->k3sq, k3m, 0, nz);
+    p->mfact = 1.0 / (double)nz;
+    p->alias = (sp->p_col == 1);
+    p->periodic_in_z = periodic_in_z != 0;
+    cudaError_t e = cudaSuccess;
+    if (!rc && !p->periodic_in_z) {
+        // :183-210: k3 = GetWaveNums(2 nz, dz) through the z scheme's symbol; tfm / tfp = exp(-+ i dz/2 k3); mfact = 1 / (2 nz)
+        const int nze = 2 * nz;
+        std::vector<double> k3e = wavenums(nze, dz), k3me(nze), k3sq(nze);
+        pdo_pade6stagg_get_modified_wavenumbers(derivZ, k3e.data(), k3me.data(), nze);
+        std::vector<double2> cm(nze), cp(nze);
+        for (int k = 0; k < nze; ++k) {
+            const double ph = (dz / 2.0) * k3e[k];
+            cm[k] = make_double2(k3me[k] * std::cos(ph), -k3me[k] * std::sin(ph));   // k3mod exp(-i dz/2 k3)
+            cp[k] = make_double2(k3me[k] * std::cos(ph), k3me[k] * std::sin(ph));    // k3mod exp(+i dz/2 k3)
+            k3sq[k] = k3me[k] * k3me[k];
+        }
+        p->mfact = 1.0 / (double)nze;
+        rc = upload(&p->k3sq_ext, k3sq, 0, nze);
+        const size_t ext = sizeof(double2) * (size_t)p->sC.zsz[0] * p->sC.zsz[1] * (size_t)nze;
+        if (!rc) {
+            e = cudaMalloc(&p->k3modcm, sizeof(double2) * nze);
+            if (e == cudaSuccess) e = cudaMalloc(&p->k3modcp, sizeof(double2) * nze);
+            if (e == cudaSuccess) e = cudaMemcpy(p->k3modcm, cm.data(), sizeof(double2) * nze, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(p->k3modcp, cp.data(), sizeof(double2) * nze, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMalloc(&p->fext, ext);
+            if (e == cudaSuccess) e = cudaMalloc(&p->wext, ext);
+            if (e != cudaSuccess) rc = fail(PDO_E_CUDA, "padepoisson wall buffers: %s", cudaGetErrorString(e));
+        }
+    }
+    if (!rc) {
+        e = cudaMalloc(&p->f2d, sizeof(double2) * (size_t)vol(p->sC.zsz));
+        if (e == cudaSuccess) e = cudaMalloc(&p->uhatInZ, sizeof(double2) * (size_t)vol(p->sC.zsz));
+        if (e == cudaSuccess) e = cudaMalloc(&p->f2dy, sizeof(double2) * (size_t)vol(p->sC.ysz));
+        if (e == cudaSuccess) e = cudaMalloc(&p->w2, sizeof(double2) * (size_t)vol(p->sE.zsz));
+        if (e == cudaSuccess) e = cudaMalloc(&p->dwdz, sizeof(double2) * (size_t)vol(p->sE.zsz));
+        if (e == cudaSuccess) e = cudaMalloc(&p->div_tmp, sizeof(double) * (size_t)vol(sp->pi.xsz));
+        if (e != cudaSuccess) rc = fail(PDO_E_CUDA, "padepoisson buffers: %s", cudaGetErrorString(e));
+        if (!rc) {  // transpose destinations (collective, same order on every rank)
+            comm_register_buffer_quiet(p->uhatInZ, sizeof(double2) * (size_t)vol(p->sC.zsz));
+            comm_register_buffer_quiet(p->w2, sizeof(double2) * (size_t)vol(p->sE.zsz));
+            comm_register_buffer_quiet(p->f2dy, sizeof(double2) * (size_t)vol(p->sC.ysz));
+        }
+    }
+    if (rc) { pdo_padepoisson_destroy(p); return rc; }
+    *h = p;
+    return 0;
+}
+
+int pdo_padepoisson_destroy(pdo_padepoisson_t p) {
+    if (!p) return 0;
+    void* ptrs[] = {p->k1sq, p->k2sq, p->k3sq, p->f2d, p->f2dy, p->w2, p->uhatInZ, p->dwdz, p->div_tmp};
+    for (void* q : ptrs) if (q) { comm_deregister_buffer(q); cudaFree(q); }
+    void* wall[] = {p->fext, p->wext, p->k3modcm, p->k3modcp, p->k3sq_ext};
+    for (void* q : wall) if (q) cudaFree(q);
+    zcols_destroy(&p->ext_plan);
+    delete p;
+    return 0;
+}
+
+}  // extern "C"
+
+namespace {
+// Runs body(u, v, w) on device views of the three spectral arrays; host arrays are staged in and (when writable) out.
+template <class Body>
+int with_uvw(pdo_padepoisson_s* p, const double* u, const double* v, const double* w, bool writeback, cudaStream_t st, Body body) {
+    const size_t bC = sizeof(double2) * (size_t)vol(p->sC.ysz), bE = sizeof(double2) * (size_t)vol(p->sE.ysz);
+    const double* in[3] = {u, v, w};
+    const size_t bytes[3] = {bC, bC, bE};
+    double2* dev[3];
+    bool staged[3];
+    for (int i = 0; i < 3; ++i) {
+        staged[i] = !is_device_ptr(in[i]);
+        if (staged[i]) {
+            PDO_CUDA(cudaMalloc(&dev[i], bytes[i]));
+            PDO_CUDA(cudaMemcpyAsync(dev[i], in[i], bytes[i], cudaMemcpyHostToDevice, st));
+        } else {
+            dev[i] = (double2*)in[i];
+        }
+    }
+    int rc = body(dev[0], dev[1], dev[2]);
+    for (int i = 0; i < 3; ++i) {
+        if (!staged[i]) continue;
+        if (!rc && writeback) {
+            if (cudaMemcpyAsync((void*)in[i], dev[i], bytes[i], cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = fail(PDO_E_CUDA, "D2H failed");
+        }
+        cudaStreamSynchronize(st);
+        cudaFree(dev[i]);
+    }
+    return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int pdo_padepoisson_pressure_projection(pdo_padepoisson_t p, double* uhat, double* vhat, double* what, void* stream) {
+    if (!p || !uhat || !vhat || !what) return fail(PDO_E_BADARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    return with_uvw(p, uhat, vhat, what, true, st, [&](double2* u, double2* v, double2* w) { return poiss_projection(p, u, v, w, st); });
+}
+
+int pdo_padepoisson_get_pressure(pdo_padepoisson_t p, const double* uhat, const double* vhat, const double* what, double* pressure,
+                                 void* stream) {
+    if (!p || !uhat || !vhat || !what || !pressure) return fail(PDO_E_BADARG, "null argument");
+    if (!p->periodic_in_z) return fail(PDO_E_UNSUPPORTED, "padepoisson getPressure: only PressureProjection and DivergenceCheck are built for PeriodicInZ = .false.");
+    cudaStream_t st = (cudaStream_t)stream;
+    return with_uvw(p, uhat, vhat, what, false, st, [&](double2* u, double2* v, double2* w) -> int {
+        if (int rc = poiss_solve(p, u, v, w, st)) return rc;
+        const double2* ph = p->f2d;
+        if (!p->alias) {
+            if (int rc = decomp_transpose_device(p->dC, 3, (const double*)p->f2d, (double*)p->f2dy, 2, st)) return rc;
+            ph = p->f2dy;
+        }
+        const size_t bytes = sizeof(double) * (size_t)vol(p->sp->pi.xsz);
+        return with_device_views(pressure, 0, pressure, bytes, st, [&](const void*, void* d_o) {
+            return fft3d_backward_yx(p->sp->ft, ph, (double*)d_o, false, st);
+        });
+    });
+}
+
+int pdo_padepoisson_get_pressure_and_update_rhs(pdo_padepoisson_t p, double* uhat, double* vhat, double* what, double* pressure,
+                                                void* stream) {
+    if (!p || !uhat || !vhat || !what || !pressure) return fail(PDO_E_BADARG, "null argument");
+    if (!p->periodic_in_z) return fail(PDO_E_UNSUPPORTED, "padepoisson getPressureAndUpdateRHS: only PressureProjection and DivergenceCheck are built for PeriodicInZ = .false.");
+    cudaStream_t st = (cudaStream_t)stream;
+    return with_uvw(p, uhat, vhat, what, true, st, [&](double2* u, double2* v, double2* w) -> int {
+        if (int rc = poiss_projection(p, u, v, w, st)) return rc;  // leaves phat at phat_y
+        const size_t bytes = sizeof(double) * (size_t)vol(p->sp->pi.xsz);
+        return with_device_views(pressure, 0, pressure, bytes, st, [&](const void*, void* d_o) {
+            return fft3d_backward_yx(p->sp->ft, p->phat_y, (double*)d_o, false, st);
+        });
+    });
+}
+
+int pdo_padepoisson_divergence_check(pdo_padepoisson_t p, double* uhat, double* vhat, double* what, double* divergence, int fix_div,
+                                     double* max_div, void* stream) {
+    if (!p || !uhat || !vhat || !what) return fail(PDO_E_BADARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    return with_uvw(p, uhat, vhat, what, fix_div != 0, st, [&](double2* u, double2* v, double2* w) -> int {
+        if (!divergence) return poiss_divergence_check(p, u, v, w, nullptr, fix_div != 0, max_div, st);
+        const size_t bytes = sizeof(double) * (size_t)vol(p->sp->pi.xsz);
+        return with_device_views(divergence, 0, divergence, bytes, st, [&](const void*, void* d_o) {
+            return poiss_divergence_check(p, u, v, w, (double*)d_o, fix_div != 0, max_div, st);
+        });
+    });
+}
+
+}  // extern "C"
