@@ -1,11 +1,17 @@
 #!/bin/bash
-# First hardware run of the GPU tests written after a round's last GPU session: they carry xfail(strict=False), so the ordinary
-# `pytest -m gpu` run can never turn red on them; here they run with --runxfail (real failures, full tracebacks) and the log goes
-# to gpurun_out/.  Once green, remove their xfail marks.
-# Usage: gpurun --timeout 900 -- 'bash tools/late_tests.sh <tag>'        (add --gpus 2 for the multi-GPU late sections)
+# First hardware run of the GPU tests written after a round's last GPU session.  They carry xfail(strict=False) and are kept out of
+# the main pytest process (tests/conftest.py); tests/test_late_isolated.py runs them in child processes.  This script does the
+# same by hand, file by file, with --runxfail (real failures, full tracebacks), and keeps the log under gpurun_out/.
+# Once green, remove their xfail marks (they then run with the validated suite).
+# Usage: gpurun --timeout 1200 -- 'bash tools/late_tests.sh <tag>'        (add --gpus 2 for the multi-GPU late sections)
 tag=${1:-late}
 mkdir -p gpurun_out
-files="tests/test_ops_periodic_gpu.py tests/test_stagg_nonperiodic_gpu.py tests/test_igrid_gpu.py tests/test_vecops_gpu.py \
-       tests/test_spectral_gpu.py tests/test_nonperiodic_gpu.py tests/test_multigpu.py"
-( time timeout 800 python -m pytest $files -m gpu --runxfail -q -rf ) > gpurun_out/${tag}_late_tests.log 2>&1
-tail -40 gpurun_out/${tag}_late_tests.log
+log=gpurun_out/${tag}_late_tests.log
+: > $log
+for f in test_golden.py test_igrid_gpu.py test_nonperiodic_gpu.py test_ops_periodic_gpu.py test_spectral_gpu.py \
+         test_stagg_nonperiodic_gpu.py test_vecops_gpu.py test_multigpu.py; do
+    echo "===== $f" >> $log
+    PDO_RUN_LATE=1 timeout 600 python -m pytest tests/$f -m gpu --runxfail -q -rf -p no:cacheprovider >> $log 2>&1
+    echo "exit $?" >> $log
+done
+grep -E "^=====|passed|failed|error|exit" $log | tail -40
