@@ -21,7 +21,7 @@ FILES = ["test_golden.py", "test_igrid_gpu.py", "test_nonperiodic_gpu.py", "test
 def test_late_gpu_tests_in_a_child_process(fname):
     env = dict(os.environ, PDO_RUN_LATE="1")
     cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", fname), "-m", "gpu", "--runxfail", "-q", "-rf", "-p", "no:cacheprovider"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)   # the late tests are small: a hang must not eat the GPU tier
     tail = r.stdout[-6000:] + r.stderr[-2000:]
     assert r.returncode in (0, 5), tail      # 5: nothing collected (every late test of the file has been promoted)
 
