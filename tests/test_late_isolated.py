@@ -21,9 +21,16 @@ FILES = ["test_golden.py", "test_igrid_gpu.py", "test_nonperiodic_gpu.py", "test
 def test_late_gpu_tests_in_a_child_process(fname):
     env = dict(os.environ, PDO_RUN_LATE="1")
     cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", fname), "-m", "gpu", "--runxfail", "-q", "-rf", "-p", "no:cacheprovider"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)   # the late tests are small: a hang must not eat the GPU tier
-    tail = r.stdout[-6000:] + r.stderr[-2000:]
-    assert r.returncode in (0, 5), tail      # 5: nothing collected (every late test of the file has been promoted)
+    # own session: on a hang the whole process group goes (torchrun workers of the multi-GPU file included), nothing keeps a GPU
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT, start_new_session=True)
+    try:
+        out, _ = p.communicate(timeout=300)      # the late tests are small: a hang must not eat the GPU tier
+    except subprocess.TimeoutExpired:
+        import signal
+        os.killpg(p.pid, signal.SIGKILL)
+        out, _ = p.communicate()
+        raise AssertionError("timed out\n" + out[-4000:])
+    assert p.returncode in (0, 5), out[-8000:]   # 5: nothing collected (every late test of the file has been promoted)
 
 
 def test_every_late_file_is_listed():
