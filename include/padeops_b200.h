@@ -322,10 +322,15 @@ int pdo_padepoisson_init(pdo_padepoisson_t* h, double dx, double dy, double dz, 
 /* the same with the reference's PeriodicInZ argument.  PeriodicInZ = .false., computeStokesPressure = .false. (:180-230, 459-623):
    walls at both ends of z — PressureProjection extends the horizontal divergence evenly and w oddly to 2 nz planes, solves in
    z-Fourier space with the z scheme's modified wavenumber and the half-cell shifts, and leaves w = 0 on both walls;
-   DivergenceCheck uses derivZ%ddz_E2C(-1, -1).  derivZ must have been initialised with the same periodicity; the pressure getters
+   DivergenceCheck uses derivZ%ddz_E2C(-1, -1).  derivZ must have been initialised with the same periodicity; computeStokesPressure: init3; the pressure getters
    are periodic-only (PDO_E_UNSUPPORTED otherwise). */
 int pdo_padepoisson_init2(pdo_padepoisson_t* h, double dx, double dy, double dz, pdo_spectral_t sp, pdo_spectral_t spE,
                           pdo_pade6stagg_t derivZ, int periodic_in_z);
+/* ... and with computeStokesPressure and Lz (:232-296, 320-384, 444-458, 597-609; walls only): before the projection the harmonic
+   pressure chat cosh(lambda (Lz - z)) / chat cosh(lambda z), lambda = |(k1, k2)|, cancels w on the bottom and then the top wall,
+   so w* need not vanish there on input. */
+int pdo_padepoisson_init3(pdo_padepoisson_t* h, double dx, double dy, double dz, pdo_spectral_t sp, pdo_spectral_t spE,
+                          pdo_pade6stagg_t derivZ, int periodic_in_z, int compute_stokes_pressure, double Lz);
 int pdo_padepoisson_destroy(pdo_padepoisson_t h);
 /* uhat, vhat: complex y-pencils of sp; what: complex y-pencil of spE (nz+1 planes); all updated in place   :386-432 */
 int pdo_padepoisson_pressure_projection(pdo_padepoisson_t h, double* uhat, double* vhat, double* what, void* stream);
@@ -340,7 +345,7 @@ int pdo_padepoisson_divergence_check(pdo_padepoisson_t h, double* uhat, double* 
 
 /* ---- IncompressibleGrid::igrid, the RK substep  (incompressible/igrid.F90) ----------------------
    Scope: PeriodicInZ (the hot path) or walls in z with slip / no-slip stencils (get_boundary_conditions_stencil :5148-5204, wall
-   closures of the staggered operators, even / odd Poisson solver, no Stokes-pressure correction); NumericalSchemeVert = 1 (CD06)
+   closures of the staggered operators, even / odd Poisson solver with the Stokes-pressure step); NumericalSchemeVert = 1 (CD06)
    or 2 (Fourier collocation, periodic only); AdvectionTerm = 1 (skew-symmetric) or 0 (rotational); TimeSteppingScheme 1
    (TVD-RK3) or 2 (SSP-RK45); viscous or inviscid; optional SGS model and HIT forcing (periodic only, pdo_igrid_enable_*);
    no Coriolis / stratification / turbines / fringe.
@@ -361,6 +366,8 @@ typedef struct {
     int fourier_collocation_z;    /* 0: NumericalSchemeVert = 1, cd06 staggered operators; 1: NumericalSchemeVert = 2, Fourier collocation in z */
     int wall_bounded;             /* 0: PeriodicInZ = .true.; 1: PeriodicInZ = .false. — walls at z = 0 and z = Lz (&BCs namelist) */
     int top_wall, bot_wall;       /* topWall / botWall when wall_bounded: 1 no-slip, 2 slip (3, the wall model, is out of scope) */
+    int no_stokes_pressure;       /* wall_bounded only.  0: ComputeStokesPressure = .true. (the reference's default): the projection first
+                                     removes the wall-normal velocity with the harmonic Stokes pressure; 1: .false. */
 } pdo_igrid_params;
 /* igrid%init: u, v on the cell grid, w on the edge grid (nz+1 planes, plane nz+1 == plane 1), x-pencil local blocks,
    host or device pointers (initfields_wallM is the caller's job).  Runs the fft / dealias / projection / gradient

@@ -236,9 +236,10 @@ class PadePoisson:
     extended evenly and w oddly to 2 nz points, transformed in z, solved with the z-scheme's modified wavenumber carrying the
     half-cell shifts (k3modcm / k3modcp), and cut back; w is zero on both walls afterwards."""
 
-    def __init__(self, dx, dy, dz, spC, spE, derivZ, PeriodicInZ=True):
+    def __init__(self, dx, dy, dz, spC, spE, derivZ, PeriodicInZ=True, computeStokesPressure=False, Lz=None):
         self.sp, self.spE, self.derivZ = spC, spE, derivZ
         self.PeriodicInZ = PeriodicInZ
+        self.computeStokesPressure = computeStokesPressure and not PeriodicInZ
         nx, ny, nz = spC.nx, spC.ny, spC.nz
         k1 = O.wavenums(nx, dx)[: spC.nxh]
         k2 = O.wavenums(ny, dy)
@@ -252,6 +253,27 @@ class PadePoisson:
             with np.errstate(divide="ignore"):
                 self.kradsq_inv = np.where(kradsq <= 1e-14, 0.0, 1.0 / kradsq)
             self.mfact = 1.0 / float(nzExt)
+            if self.computeStokesPressure:       # PadePoisson.F90:232-296
+                Lz = float(nz) * dz if Lz is None else Lz
+                zEdge = np.linspace(0.0, Lz, nz + 1)
+                zCell = 0.5 * (zEdge[:nz] + zEdge[1:])
+                self.k1inZ = np.broadcast_to(k1[None, :], (ny, spC.nxh)).copy()           # GetWaveNums, no oddball flip (:248-249)
+                self.k2inZ = np.broadcast_to(k2[:, None], (ny, spC.nxh)).copy()
+                lam = np.sqrt(self.k1inZ ** 2 + self.k2inZ ** 2)
+                temp = lam * Lz
+                with np.errstate(over="ignore"):
+                    den = np.where(temp < 500.0, 1.0 / (lam * np.sinh(np.minimum(lam * Lz, 700.0)) + 1.0e-13), 0.0)
+                den = np.where(den < 1e-16, 0.0, den)
+                den[0, 0] = 0.0                                                          # nrank == 0 owns the mean mode
+                self.denFact = den
+                t = lam[None] * (Lz - zCell)[:, None, None]
+                self.cosh_bot = np.where(t < 32.0, np.cosh(np.minimum(t, 32.0)), 4.0e13)
+                t = lam[None] * zCell[:, None, None]
+                self.cosh_top = np.where(t < 32.0, np.cosh(np.minimum(t, 32.0)), 1.0e13)
+                t = lam[None] * (Lz - zEdge)[:, None, None]
+                self.sinh_bot = np.where(t < 32.0, -lam[None] * np.sinh(np.minimum(t, 32.0)), -4.0e13)
+                t = lam[None] * zEdge[:, None, None]
+                self.sinh_top = np.where(t < 32.0, lam[None] * np.sinh(np.minimum(t, 32.0)), 4.0e13)
             return
         k3mod = derivZ.getModifiedWavenumbers(O.wavenums(nz, dz))
         kradsq = k1[None, None, :] ** 2 + k2[None, :, None] ** 2 + k3mod[:, None, None] ** 2
@@ -273,14 +295,39 @@ class PadePoisson:
         f2d = f2d * self.mfact
         return f2d, w2
 
+    def ProjectStokesPressure(self, uhat, vhat, what):
+        """PadePoisson.F90:320-384: the harmonic (Stokes) pressure that cancels w on the two walls, bottom first, then top with the
+        already corrected top plane; returns (uhatInZ, vhatInZ, w2)."""
+        nz = self.sp.nz
+        u, v, w2 = np.array(uhat, dtype=complex), np.array(vhat, dtype=complex), np.array(what, dtype=complex)
+        chat = -w2[0] * self.denFact
+        phat = imi * chat[None] * self.cosh_bot
+        u = u - self.k1inZ[None] * phat
+        v = v - self.k2inZ[None] * phat
+        w2[0] = 0.0
+        w2[1:] = w2[1:] - chat[None] * self.sinh_bot[1:]
+        chat = w2[nz] * self.denFact
+        phat = imi * chat[None] * self.cosh_top
+        u = u - self.k1inZ[None] * phat
+        v = v - self.k2inZ[None] * phat
+        w2[:nz] = w2[:nz] - chat[None] * self.sinh_top[:nz]
+        w2[nz] = 0.0
+        return u, v, w2
+
     def _wall_projection(self, uhat, vhat, what):
-        """PadePoisson.F90:459-623 (computeStokesPressure = .false.)"""
+        """PadePoisson.F90:444-623"""
         sp = self.sp
         nz = sp.nz
-        f2dy = sp.k1 * uhat
-        f2dy = f2dy + sp.k2 * vhat
-        f2d = -f2dy.imag + 1j * f2dy.real
-        w2 = what
+        if self.computeStokesPressure:
+            uZ, vZ, w2 = self.ProjectStokesPressure(uhat, vhat, what)
+            f2d = self.k1inZ[None] * uZ
+            f2d = f2d + self.k2inZ[None] * vZ
+            f2d = -f2d.imag + 1j * f2d.real
+        else:
+            f2dy = sp.k1 * uhat
+            f2dy = f2dy + sp.k2 * vhat
+            f2d = -f2dy.imag + 1j * f2dy.real
+            w2 = what
         f2dext = np.concatenate([f2d[::-1], f2d], axis=0)                      # Step 3: even extension, 2 nz planes
         wext = np.empty_like(f2dext)
         wext[0:nz - 1] = -w2[nz - 1:0:-1]                                      # wext(kk-1) = -w2(nzG-kk+2), kk = 2..nzG
@@ -296,6 +343,9 @@ class PadePoisson:
         w2 = wext[nz - 1:].copy()
         w2[0] = 0.0
         w2[nz] = 0.0
+        if self.computeStokesPressure:                                         # :597-609
+            g = -f2d.imag + 1j * f2d.real
+            return uZ - g * self.k1inZ[None], vZ - g * self.k2inZ[None], w2
         return uhat - imi * sp.k1 * f2d, vhat - imi * sp.k2 * f2d, w2
 
     def PressureProjection(self, uhat, vhat, what):
@@ -533,7 +583,7 @@ class IGrid:
 
     def __init__(self, nx, ny, nz, Lx, Ly, Lz, Re, u, v, w, isInviscid=False, dealiasFact=2.0 / 3.0, t_DivergenceCheck=10,
                  TimeSteppingScheme=1, use_d2dz2_C2C=True, AdvectionTerm=1, NumericalSchemeVert=1, HITForcing_=None, SGS_=None,
-                 PeriodicInZ=True, topWall=2, botWall=2):
+                 PeriodicInZ=True, topWall=2, botWall=2, ComputeStokesPressure=True):
         """HITForcing_: None, or the &HIT_Forcing namelist as a dict (kmin, kmax, Nwaves, EpsAmplitude, RandSeedToAdd) for
         useHITForcing = .true. (igrid.F90:940-944, 1908-1910).  SGS_: None, or the &SGS_MODEL namelist entries in scope as a dict
         (SGSModelID, Csgs, explicitCalcEdgeEddyViscosity) for useSGS = .true. (:1866-1871).
@@ -557,7 +607,8 @@ class IGrid:
         self.spectC = Spectral(nx, ny, nz, self.dx, self.dy, self.dz, PeriodicInZ, dealiasFact, False)
         self.spectE = Spectral(nx, ny, nz + 1, self.dx, self.dy, self.dz, False, dealiasFact, False)
         self.ops = Pade6stagg(nz, self.dz, NumericalSchemeVert, isPeriodic=PeriodicInZ)
-        self.poiss = PadePoisson(self.dx, self.dy, self.dz, self.spectC, self.spectE, self.ops, PeriodicInZ=PeriodicInZ)
+        self.poiss = PadePoisson(self.dx, self.dy, self.dz, self.spectC, self.spectE, self.ops, PeriodicInZ=PeriodicInZ,
+                                 computeStokesPressure=ComputeStokesPressure, Lz=Lz)     # igrid.F90:585-586 (&NUMERICS, default .true.)
         self.step, self.tsim = 0, 0.0
         self.newTimeStep = True
         self.hitforce = HITForcing(self.spectC, tidStart=self.step, **HITForcing_) if HITForcing_ is not None else None

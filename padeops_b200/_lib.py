@@ -108,7 +108,7 @@ class IgridParams(C.Structure):
                 ("Re", C.c_double), ("is_inviscid", C.c_int), ("dealias_fact", C.c_double), ("t_divergence_check", C.c_int),
                 ("time_stepping_scheme", C.c_int), ("p_row", C.c_int), ("p_col", C.c_int), ("use_d2dz2_c2c", C.c_int),
                 ("compute_all_gradients", C.c_int), ("rotational_advection", C.c_int), ("fourier_collocation_z", C.c_int),
-                ("wall_bounded", C.c_int), ("top_wall", C.c_int), ("bot_wall", C.c_int)]
+                ("wall_bounded", C.c_int), ("top_wall", C.c_int), ("bot_wall", C.c_int), ("no_stokes_pressure", C.c_int)]
 
 
 _PROTOS.update({
@@ -134,6 +134,7 @@ _PROTOS.update({
     "pdo_lstsq_filter2": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_void_p]),
     "pdo_lstsq_filter3": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_void_p]),
     "pdo_padepoisson_init2": (C.c_int, [C.POINTER(C.c_void_p), C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "pdo_padepoisson_init3": (C.c_int, [C.POINTER(C.c_void_p), C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double]),
     "pdo_igrid_enable_sgs": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),
     "pdo_debug_sgs_point": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_dp, c_dp, c_dp]),
     "pdo_hit_forcing_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int]),

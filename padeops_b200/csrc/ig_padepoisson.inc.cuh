@@ -21,6 +21,11 @@ struct pdo_padepoisson_s {
     double2 *fext = nullptr, *wext = nullptr, *k3modcm = nullptr, *k3modcp = nullptr;
     double* k3sq_ext = nullptr;
     ZColsPlan ext_plan;
+    // computeStokesPressure (:232-296, 320-384): signed z-pencil slices of GetWaveNums, 1 / (lambda sinh(lambda Lz)) per column
+    bool stokes = false;
+    double Lz = 0.0;
+    double *k1z = nullptr, *k2z = nullptr, *denfact = nullptr;
+    double2* vhatInZ = nullptr;
 };
 
 namespace {
@@ -134,19 +139,88 @@ int global_max(pdo_spectral_s* s, const double* a, long long n, int use_abs, dou
     return pdo_p_maxval(m, out);
 }
 
-// PressureProjection with walls, computeStokesPressure = .false. (PadePoisson.F90:459-623): the horizontal divergence is extended
+// ProjectStokesPressure (PadePoisson.F90:320-384), in place on the z-pencil arrays: one thread per (kx, ky) column.  The harmonic
+// pressure chat cosh(lambda (Lz - z)) (bottom wall) and chat cosh(lambda z) (top wall, computed from the ALREADY corrected top
+// plane) cancels w on the walls; cosh / sinh are evaluated on the fly with the reference's clipping (arguments >= 32 -> 4e13 /
+// 1e13 / -4e13 / 4e13) instead of being read from four 3-D tables.
+__global__ void __launch_bounds__(128) stokes_kernel(double2* __restrict__ u, double2* __restrict__ v, double2* __restrict__ w2, long long cols,
+                                                     int n1, int nz, double Lz, const double* __restrict__ k1z, const double* __restrict__ k2z,
+                                                     const double* __restrict__ denfact) {
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const double k1 = k1z[(int)(c % n1)], k2 = k2z[(int)(c / n1)];
+    const double lam = sqrt(k1 * k1 + k2 * k2), den = denfact[c], dzl = Lz / (double)nz;
+    // bottom BC
+    const double2 w0 = w2[c];
+    double2 ch = make_double2(-w0.x * den, -w0.y * den);
+    for (int k = 0; k < nz; ++k) {
+        const double zc = 0.5 * ((double)k * dzl + (double)(k + 1) * dzl);
+        const double t = lam * (Lz - zc);
+        const double cb = t < 32.0 ? cosh(t) : 4.0e13;
+        const double2 ph = make_double2(-ch.y * cb, ch.x * cb);      // imi * chat * cosh_bot
+        double2 a = u[c + cols * k]; a.x -= k1 * ph.x; a.y -= k1 * ph.y; u[c + cols * k] = a;
+        double2 b = v[c + cols * k]; b.x -= k2 * ph.x; b.y -= k2 * ph.y; v[c + cols * k] = b;
+    }
+    w2[c] = make_double2(0.0, 0.0);
+    for (int k = 1; k <= nz; ++k) {
+        const double t = lam * (Lz - (double)k * dzl);
+        const double sb = t < 32.0 ? -lam * sinh(t) : -4.0e13;
+        double2 a = w2[c + cols * k]; a.x -= ch.x * sb; a.y -= ch.y * sb; w2[c + cols * k] = a;
+    }
+    // top BC
+    const double2 wn = w2[c + cols * nz];
+    ch = make_double2(wn.x * den, wn.y * den);
+    for (int k = 0; k < nz; ++k) {
+        const double zc = 0.5 * ((double)k * dzl + (double)(k + 1) * dzl);
+        double t = lam * zc;
+        const double ct = t < 32.0 ? cosh(t) : 1.0e13;
+        const double2 ph = make_double2(-ch.y * ct, ch.x * ct);
+        double2 a = u[c + cols * k]; a.x -= k1 * ph.x; a.y -= k1 * ph.y; u[c + cols * k] = a;
+        double2 b = v[c + cols * k]; b.x -= k2 * ph.x; b.y -= k2 * ph.y; v[c + cols * k] = b;
+        t = lam * ((double)k * dzl);
+        const double stp = t < 32.0 ? lam * sinh(t) : 4.0e13;
+        double2 e = w2[c + cols * k]; e.x -= ch.x * stp; e.y -= ch.y * stp; w2[c + cols * k] = e;
+    }
+    w2[c + cols * nz] = make_double2(0.0, 0.0);
+}
+
+// PressureProjection with walls (PadePoisson.F90:444-623): the horizontal divergence is extended
 // evenly and w oddly about both walls to 2 nz planes, one c2c-z pair solves and projects (the half-cell shifts ride on
 // k3modcm / k3modcp), the upper halves come back and w is zero on both walls.
 int poiss_wall_projection(pdo_padepoisson_s* p, double2* uhat, double2* vhat, double2* what, cudaStream_t st) {
-    if (int rc = poiss_div_xy(p, uhat, vhat, p->f2dy, st)) return rc;                       // Step 1
-    const double2 *uz = p->f2dy, *wz = what;
-    if (!p->alias) {                                                                          // Step 2
-        if (int rc = decomp_transpose_device(p->dC, 2, (const double*)p->f2dy, (double*)p->uhatInZ, 2, st)) return rc;
-        if (int rc = decomp_transpose_device(p->dE, 2, (const double*)what, (double*)p->w2, 2, st)) return rc;
-        uz = p->uhatInZ; wz = p->w2;
-    }
     const int nz = p->sp->nz, n1 = p->sC.zsz[0], n2 = p->sC.zsz[1];
     const long long cols = (long long)n1 * n2, next = cols * 2 * nz;
+    const double2 *uz = nullptr, *wz = what;
+    double2 *uZ = uhat, *vZ = vhat;          // computeStokesPressure: u and v in the z-pencil, corrected in place
+    if (p->stokes) {                          // Step 0 (:444-458)
+        double2* w2 = what;
+        if (!p->alias) {
+            if (int rc = decomp_transpose_device(p->dC, 2, (const double*)uhat, (double*)p->uhatInZ, 2, st)) return rc;
+            if (int rc = decomp_transpose_device(p->dC, 2, (const double*)vhat, (double*)p->vhatInZ, 2, st)) return rc;
+            if (int rc = decomp_transpose_device(p->dE, 2, (const double*)what, (double*)p->w2, 2, st)) return rc;
+            uZ = p->uhatInZ; vZ = p->vhatInZ; w2 = p->w2;
+        }
+        stokes_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(uZ, vZ, w2, cols, n1, nz, p->Lz, p->k1z, p->k2z, p->denfact);
+        PDO_CUDA(cudaGetLastError());
+        g_launches += 1;
+        const double *k1z = p->k1z, *k2z = p->k2z;
+        double2* f2d = p->f2d;
+        const double2 *cu = uZ, *cv = vZ;
+        if (int rc = launch_ew(cols * nz, st, [=] __device__(long long i) {   // f2d = i (k1inZ u + k2inZ v)
+                const double a = k1z[(int)(i % n1)], b = k2z[(int)((i / n1) % n2)];
+                const double2 uu = cu[i], vv = cv[i];
+                f2d[i] = make_double2(-(a * uu.y + b * vv.y), a * uu.x + b * vv.x);
+            })) return rc;
+        uz = p->f2d; wz = w2;
+    } else {
+        if (int rc = poiss_div_xy(p, uhat, vhat, p->f2dy, st)) return rc;                       // Step 1
+        uz = p->f2dy;
+        if (!p->alias) {                                                                          // Step 2
+            if (int rc = decomp_transpose_device(p->dC, 2, (const double*)p->f2dy, (double*)p->uhatInZ, 2, st)) return rc;
+            if (int rc = decomp_transpose_device(p->dE, 2, (const double*)what, (double*)p->w2, 2, st)) return rc;
+            uz = p->uhatInZ; wz = p->w2;
+        }
+    }
     double2 *fe = p->fext, *we = p->wext;
     if (int rc = launch_ew(next, st, [=] __device__(long long i) {                            // Step 3
             const long long c = i % cols;
@@ -187,6 +261,25 @@ int poiss_wall_projection(pdo_padepoisson_s* p, double2* uhat, double2* vhat, do
             if (kk < nz) f2d[i] = fe[i + cols * nz];
             w2[i] = (kk == 0 || kk == nz) ? make_double2(0.0, 0.0) : we[i + cols * (nz - 1)];
         })) return rc;
+    if (p->stokes) {                                                                          // :597-609
+        const double *k1z = p->k1z, *k2z = p->k2z;
+        const double2* pr = p->f2d;
+        if (int rc = launch_ew(cols * nz, st, [=] __device__(long long i) {   // u -= i k1inZ p, v -= i k2inZ p, in the z-pencil
+                const double a = k1z[(int)(i % n1)], b = k2z[(int)((i / n1) % n2)];
+                const double2 q = pr[i];
+                double2 uu = uZ[i], vv = vZ[i];
+                uu.x += a * q.y; uu.y -= a * q.x;
+                vv.x += b * q.y; vv.y -= b * q.x;
+                uZ[i] = uu; vZ[i] = vv;
+            })) return rc;
+        p->phat_y = nullptr;
+        if (!p->alias) {
+            if (int rc = decomp_transpose_device(p->dE, 3, (const double*)p->w2, (double*)what, 2, st)) return rc;
+            if (int rc = decomp_transpose_device(p->dC, 3, (const double*)uZ, (double*)uhat, 2, st)) return rc;
+            if (int rc = decomp_transpose_device(p->dC, 3, (const double*)vZ, (double*)vhat, 2, st)) return rc;
+        }
+        return 0;
+    }
     const double2* ph = p->f2d;
     if (!p->alias) {                                                                          // Step 8
         if (int rc = decomp_transpose_device(p->dE, 3, (const double*)p->w2, (double*)what, 2, st)) return rc;
@@ -239,6 +332,10 @@ int pdo_padepoisson_init(pdo_padepoisson_t* h, double dx, double dy, double dz, 
 }
 int pdo_padepoisson_init2(pdo_padepoisson_t* h, double dx, double dy, double dz, pdo_spectral_t sp, pdo_spectral_t spE,
                           pdo_pade6stagg_t derivZ, int periodic_in_z) {
+    return pdo_padepoisson_init3(h, dx, dy, dz, sp, spE, derivZ, periodic_in_z, 0, 0.0);
+}
+int pdo_padepoisson_init3(pdo_padepoisson_t* h, double dx, double dy, double dz, pdo_spectral_t sp, pdo_spectral_t spE,
+                          pdo_pade6stagg_t derivZ, int periodic_in_z, int compute_stokes_pressure, double Lz) {
     if (!h || !sp || !spE || !derivZ) return fail(PDO_E_BADARG, "null argument");
     *h = nullptr;
     if (spE->nz != sp->nz + 1 || spE->nx != sp->nx || spE->ny != sp->ny) return fail(PDO_E_BADARG, "spE must be the (nx, ny, nz+1) edge type of sp");
@@ -292,6 +389,26 @@ int pdo_padepoisson_init2(pdo_padepoisson_t* h, double dx, double dy, double dz,
             if (e == cudaSuccess) e = cudaMalloc(&p->wext, ext);
             if (e != cudaSuccess) rc = fail(PDO_E_CUDA, "padepoisson wall buffers: %s", cudaGetErrorString(e));
         }
+        if (!rc && compute_stokes_pressure) {   // :232-296
+            p->stokes = true;
+            p->Lz = Lz > 0.0 ? Lz : (double)nz * dz;
+            std::vector<double> w1 = wavenums(sp->nx, dx), w2v = wavenums(sp->ny, dy);   // GetWaveNums, no oddball flip (:248-249)
+            const int c1 = p->sC.zsz[0], c2 = p->sC.zsz[1], o1 = p->sC.zst[0] - 1, o2 = p->sC.zst[1] - 1;
+            std::vector<double> den((size_t)c1 * c2);
+            for (int j = 0; j < c2; ++j)
+                for (int i = 0; i < c1; ++i) {
+                    const double lam = std::sqrt(w1[o1 + i] * w1[o1 + i] + w2v[o2 + j] * w2v[o2 + j]);
+                    double d = (lam * p->Lz < 500.0) ? 1.0 / (lam * std::sinh(lam * p->Lz) + 1.0e-13) : 0.0;
+                    if (d < 1.0e-16) d = 0.0;
+                    den[(size_t)j * c1 + i] = d;
+                }
+            if (o1 == 0 && o2 == 0) den[0] = 0.0;   // "if (nrank == 0) this%denFact(1,1) = 0": the owner of the mean mode
+            rc = upload(&p->k1z, w1, o1, c1);
+            if (!rc) rc = upload(&p->k2z, w2v, o2, c2);
+            if (!rc) rc = upload(&p->denfact, den, 0, den.size());
+            if (!rc && cudaMalloc(&p->vhatInZ, sizeof(double2) * (size_t)vol(p->sC.zsz)) != cudaSuccess) rc = fail(PDO_E_CUDA, "padepoisson: vhatInZ");
+            if (!rc) comm_register_buffer_quiet(p->vhatInZ, sizeof(double2) * (size_t)vol(p->sC.zsz));
+        }
     }
     if (!rc) {
         e = cudaMalloc(&p->f2d, sizeof(double2) * (size_t)vol(p->sC.zsz));
@@ -316,8 +433,9 @@ int pdo_padepoisson_destroy(pdo_padepoisson_t p) {
     if (!p) return 0;
     void* ptrs[] = {p->k1sq, p->k2sq, p->k3sq, p->f2d, p->f2dy, p->w2, p->uhatInZ, p->dwdz, p->div_tmp};
     for (void* q : ptrs) if (q) { comm_deregister_buffer(q); cudaFree(q); }
-    void* wall[] = {p->fext, p->wext, p->k3modcm, p->k3modcp, p->k3sq_ext};
+    void* wall[] = {p->fext, p->wext, p->k3modcm, p->k3modcp, p->k3sq_ext, p->k1z, p->k2z, p->denfact};
     for (void* q : wall) if (q) cudaFree(q);
+    if (p->vhatInZ) { comm_deregister_buffer(p->vhatInZ); cudaFree(p->vhatInZ); }
     zcols_destroy(&p->ext_plan);
     delete p;
     return 0;

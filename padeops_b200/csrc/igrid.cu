@@ -624,7 +624,8 @@ int pdo_igrid_init(pdo_igrid_t* h, const pdo_igrid_params* p, const double* u, c
         rc = pdo_pade6stagg_init2(&g->ops, g->gC.zsz, g->sC.zsz, g->dz, p->fourier_collocation_z ? PDO_SCHEME_FOURIER : PDO_SCHEME_CD06, perz,
                                   g->spC);   // igrid.F90:500
     }
-    if (!rc) rc = pdo_padepoisson_init2(&g->poiss, g->dx, g->dy, g->dz, g->spC, g->spE, g->ops, perz);   // :585-586
+    if (!rc) rc = pdo_padepoisson_init3(&g->poiss, g->dx, g->dy, g->dz, g->spC, g->spE, g->ops, perz,
+                                        p->wall_bounded && !p->no_stokes_pressure, p->Lz);   // :585-586 (ComputeStokesPressure, default .true.)
     if (rc) { pdo_igrid_destroy(g); return rc; }
     g->dC = fft3d_spec_decomp(g->spC->ft); g->dE = fft3d_spec_decomp(g->spE->ft);
     g->alias = (g->spC->p_col == 1);

@@ -277,11 +277,10 @@ class padepoisson:
         self._h = C.c_void_p(None)
 
     def init(self, dx, dy, dz, sp, spE, computeStokesPressure=False, Lz=None, storePressure=True, gpC=None, derivZ=None, PeriodicInZ=True):
-        if computeStokesPressure:
-            raise NotImplementedError("computeStokesPressure = .true. is out of scope")
         self._keep = (sp, spE, derivZ)
         self._sp = sp
-        check(lib().pdo_padepoisson_init2(C.byref(self._h), float(dx), float(dy), float(dz), sp._h, spE._h, derivZ._h, int(bool(PeriodicInZ))))
+        check(lib().pdo_padepoisson_init3(C.byref(self._h), float(dx), float(dy), float(dz), sp._h, spE._h, derivZ._h, int(bool(PeriodicInZ)),
+                                          int(bool(computeStokesPressure) and not PeriodicInZ), float(Lz) if Lz is not None else 0.0))
         return 0
 
     def destroy(self):
@@ -323,7 +322,7 @@ class igrid:
 
     def init(self, nx, ny, nz, Lx, Ly, Lz, Re, u, v, w, isInviscid=False, dealiasFact=2.0 / 3.0, t_DivergenceCheck=10,
              TimeSteppingScheme=1, prow=0, pcol=0, use_d2dz2_C2C=True, computeAllGradients=False, AdvectionTerm=1, NumericalSchemeVert=1,
-             PeriodicInZ=True, topWall=2, botWall=2):
+             PeriodicInZ=True, topWall=2, botWall=2, ComputeStokesPressure=True):
         """AdvectionTerm: 1 skew-symmetric (igrid.F90:1572-1679), 0 rotational u x omega (:1527-1555); NumericalSchemeVert: 1 cd06
         staggered compact operators, 2 Fourier collocation in z (PadeDerOps.F90:16-18) — as in the namelist."""
         if AdvectionTerm not in (0, 1):
@@ -334,7 +333,7 @@ class igrid:
         p = IgridParams(int(nx), int(ny), int(nz), float(Lx), float(Ly), float(Lz), float(Re), int(bool(isInviscid)), float(dealiasFact),
                         int(t_DivergenceCheck), int(TimeSteppingScheme), int(prow), int(pcol), int(bool(use_d2dz2_C2C)),
                         int(bool(computeAllGradients)), int(AdvectionTerm == 0), int(NumericalSchemeVert == 2),
-                        int(not PeriodicInZ), int(topWall), int(botWall))
+                        int(not PeriodicInZ), int(topWall), int(botWall), int(not ComputeStokesPressure))
         check(lib().pdo_igrid_init(C.byref(self._h), C.byref(p), ptr(u), ptr(v), ptr(w)))
         self.gpC = _info(lib().pdo_igrid_get_decomp_info, self._h, 0)
         self.gpE = _info(lib().pdo_igrid_get_decomp_info, self._h, 1)

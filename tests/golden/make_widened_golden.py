@@ -42,7 +42,9 @@ def igrid_cases():
     Ww[0] = 0.0
     Ww[m] = 0.0
     return {"deck": ((U, V, W), (*L, 1.0e10), deck), "slip": ((U, V, Ww), (*L[:2], 2.0, 100.0), dict(TimeSteppingScheme=1, PeriodicInZ=False, topWall=2, botWall=2)),
-            "noslip": ((U, V, Ww), (*L[:2], 2.0, 100.0), dict(TimeSteppingScheme=1, PeriodicInZ=False, topWall=1, botWall=1))}
+            "noslip": ((U, V, Ww), (*L[:2], 2.0, 100.0), dict(TimeSteppingScheme=1, PeriodicInZ=False, topWall=1, botWall=1)),      # Stokes pressure on (default)
+            "noslip_nostokes": ((U, V, Ww), (*L[:2], 2.0, 100.0), dict(TimeSteppingScheme=1, PeriodicInZ=False, topWall=1, botWall=2,
+                                                                      ComputeStokesPressure=False))}
 
 
 def main():
@@ -94,6 +96,10 @@ def main():
     wh[pz] = 0
     out["wp_u"], out["wp_v"], out["wp_w"] = uh, vh, wh
     out["wp_u1"], out["wp_v1"], out["wp_w1"] = P.PressureProjection(uh, vh, wh)
+    Ps = IG.PadePoisson(*pd, spC, spE, IG.Pade6stagg(pz, pd[2], 1, isPeriodic=False), PeriodicInZ=False, computeStokesPressure=True, Lz=1.0)
+    whs = rnd((pz + 1, py, px // 2 + 1), 9, True)        # nonzero on the walls
+    out["wps_w"] = whs
+    out["wps_u1"], out["wps_v1"], out["wps_w1"] = Ps.PressureProjection(uh, vh, whs)
     # igrid variants, one step on 8^3
     for tag, ((U, V, W), (Lx, Ly, Lz, Re), kw) in igrid_cases().items():
         m = U.shape[0]

@@ -151,6 +151,10 @@ def test_oracle_reproduces_widened_golden(oracle, wide):
     P = IG.PadePoisson(*pd, IG.Spectral(px, py, pz, *pd), IG.Spectral(px, py, pz + 1, *pd), IG.Pade6stagg(pz, pd[2], 1, isPeriodic=False), PeriodicInZ=False)
     for a, nm in zip(P.PressureProjection(uh, vh, wh), ("wp_u1", "wp_v1", "wp_w1")):
         assert _rel(a, wide[nm]) < 1e-13
+    Ps = IG.PadePoisson(*pd, IG.Spectral(px, py, pz, *pd), IG.Spectral(px, py, pz + 1, *pd), IG.Pade6stagg(pz, pd[2], 1, isPeriodic=False),
+                        PeriodicInZ=False, computeStokesPressure=True, Lz=1.0)
+    for a, nm in zip(Ps.PressureProjection(uh, vh, wide["wps_w"]), ("wps_u1", "wps_v1", "wps_w1")):
+        assert _rel(a, wide[nm]) < 1e-13
     for tag, ((U, V, W), (Lx, Ly, Lz, Re), kw) in M.igrid_cases().items():
         assert np.array_equal(U, wide[f"ig_{tag}_U0"]) and np.array_equal(W, wide[f"ig_{tag}_W0"])
         m = U.shape[0]

@@ -432,14 +432,14 @@ def _channel_fields(nx, ny, nz, Lz, slip):
 
 @pytest.mark.xfail(strict=False, reason=_LATE)
 @pytest.mark.parametrize("walls", [(2, 2), (1, 1), (1, 2)])
-@pytest.mark.parametrize("adv,scheme", [(1, 1), (0, 2)])
-def test_wall_bounded_igrid_matches_oracle(pdo, IG, walls, adv, scheme):
+@pytest.mark.parametrize("adv,scheme,stokes", [(1, 1, True), (0, 2, True), (1, 2, False)])
+def test_wall_bounded_igrid_matches_oracle(pdo, IG, walls, adv, scheme, stokes):
     """PeriodicInZ = .false. with slip / no-slip walls: the stencil codes reach every z-operator, the staggered operators take their
     wall closures, the projection its even / odd extension (igrid.F90:5148-5204, PadeDerOps.F90:92-110, PadePoisson.F90:459-623)."""
     nx, ny, nz, Lz = 16, 12, 24, 2.0
     L = 2 * np.pi
     u, v, w = _channel_fields(nx, ny, nz, Lz, slip=(walls == (2, 2)))
-    kw = dict(TimeSteppingScheme=scheme, AdvectionTerm=adv, PeriodicInZ=False, botWall=walls[0], topWall=walls[1])
+    kw = dict(TimeSteppingScheme=scheme, AdvectionTerm=adv, PeriodicInZ=False, botWall=walls[0], topWall=walls[1], ComputeStokesPressure=stokes)
     ref = IG.IGrid(nx, ny, nz, L, L, Lz, 100.0, u, v, w, **kw)
     g = pdo.igrid()
     g.init(nx, ny, nz, L, L, Lz, 100.0, u, v, w, **kw)

@@ -190,6 +190,34 @@ def test_taylor_green_decay_fourier_z(adv):
     assert np.abs(g.poiss.divergence(g.uhat, g.vhat, g.what)).max() < 1e-12
 
 
+def test_stokes_pressure_projection():
+    """computeStokesPressure = .true. (PadePoisson.F90:232-296, 320-384, 444-458, 597-609): w* need not vanish on the walls — the
+    harmonic pressure removes the wall-normal velocity first, bottom then top; the projected field is solenoidal to rounding,
+    w = 0 on both walls, the projection is idempotent, and it reduces to the plain wall projection when w* is already zero there."""
+    nx, ny, nz, Lz = 16, 12, 24, 2.0
+    dx, dy, dz = 2 * np.pi / nx, 2 * np.pi / ny, Lz / nz
+    spC, spE = IG.Spectral(nx, ny, nz, dx, dy, dz), IG.Spectral(nx, ny, nz + 1, dx, dy, dz)
+    ops = IG.Pade6stagg(nz, dz, 1, isPeriodic=False)
+    P = IG.PadePoisson(dx, dy, dz, spC, spE, ops, PeriodicInZ=False, computeStokesPressure=True, Lz=Lz)
+    P0 = IG.PadePoisson(dx, dy, dz, spC, spE, ops, PeriodicInZ=False)
+    rng = np.random.default_rng(0)
+    u, v, w = rng.standard_normal((nz, ny, nx)), rng.standard_normal((nz, ny, nx)), rng.standard_normal((nz + 1, ny, nx))
+    uh, vh, wh = spC.dealias(spC.fft(u)), spC.dealias(spC.fft(v)), spE.dealias(spE.fft(w))   # the oddball mode is never alive in a run
+    scale = np.abs(P.divergence(uh, vh, wh)).max()
+    a, b, c = P.PressureProjection(uh, vh, wh)
+    assert np.abs(P.divergence(a, b, c)).max() < 1e-12 * scale
+    assert not np.any(c[0]) and not np.any(c[nz])
+    a0, b0, c0 = P0.PressureProjection(uh, vh, wh)
+    assert np.abs(P0.divergence(a0, b0, c0)).max() > 1e-3 * scale          # without it the wall values are simply cut off
+    a2, b2, c2 = P.PressureProjection(a, b, c)
+    assert np.abs(a2 - a).max() < 1e-12 * np.abs(a).max() and np.abs(c2 - c).max() < 1e-12 * np.abs(c).max()
+    wh0 = wh.copy()
+    wh0[0] = 0
+    wh0[nz] = 0
+    for x, y in zip(P.PressureProjection(uh, vh, wh0), P0.PressureProjection(uh, vh, wh0)):
+        assert np.abs(x - y).max() < 1e-12 * np.abs(y).max()
+
+
 @pytest.mark.parametrize("shape", [(16, 12, 24), (12, 16, 10)])
 def test_wall_bounded_projection(shape):
     """padepoisson with PeriodicInZ = .false., computeStokesPressure = .false. (PadePoisson.F90:180-230, 459-623): after the
@@ -276,11 +304,17 @@ def test_no_slip_channel_stays_solenoidal_and_decays(walls):
     e0 = (g.u ** 2 + g.v ** 2 + g.wC ** 2).mean()
     for _ in range(3):
         g.timeAdvance(0.005)
-    # without the Stokes-pressure correction (computeStokesPressure, out of scope) the right-hand side leaves w* nonzero on a
-    # no-slip wall, the projection zeroes it afterwards: the divergence is small, not rounding-level, next to such a wall
+    # the right-hand side leaves w* nonzero on a no-slip wall; the Stokes-pressure step of the projection (ComputeStokesPressure, the
+    # reference's default) removes it harmonically, so the projected field is solenoidal to rounding; without it only approximately
     _, _, _, div = g.poiss.DivergenceCheck(g.uhat, g.vhat, g.what)
-    assert np.abs(div).max() < 1e-3 * np.abs(g.duidxj["dudx"]).max()
+    assert np.abs(div).max() < 1e-11 * np.abs(g.duidxj["dudx"]).max()
     assert not np.any(g.what[0]) and not np.any(g.what[nz])
+    h = IG.IGrid(nx, ny, nz, L, L, Lz, 50.0, u, v, w, TimeSteppingScheme=2, PeriodicInZ=False, botWall=walls[0], topWall=walls[1],
+                 ComputeStokesPressure=False)
+    for _ in range(3):
+        h.timeAdvance(0.005)
+    _, _, _, div0 = h.poiss.DivergenceCheck(h.uhat, h.vhat, h.what)
+    assert 1e-9 < np.abs(div0).max() < 1e-3 * np.abs(h.duidxj["dudx"]).max()
     e1 = (g.u ** 2 + g.v ** 2 + g.wC ** 2).mean()
     assert 0.5 * e0 < e1 < e0
     with pytest.raises(ValueError):
@@ -352,3 +386,57 @@ def test_wall_projection_kernels_index_arithmetic():
     got = (uh - 1j * spC.k1 * f2d, vh - 1j * spC.k2 * f2d, w2.reshape(nz + 1, ny, nxh))
     for a, b in zip(got, want):
         assert np.abs(a - b).max() < 1e-12 * np.abs(b).max()
+
+
+def test_stokes_kernel_arithmetic():
+    """csrc/ig_padepoisson.inc.cuh stokes_kernel re-enacted in numpy column by column (cosh / sinh on the fly with the reference's
+    clipping, bottom wall first, top wall from the corrected top plane) against the oracle's table formulation; large lambda Lz
+    included so that the clipped branches are exercised."""
+    nx, ny, nz, Lz = 16, 12, 10, 6.0
+    dx, dy, dz = 2 * np.pi / nx / 8, 2 * np.pi / ny / 8, Lz / nz          # small box in x, y: lambda up to ~90, lambda Lz >> 32
+    spC, spE = IG.Spectral(nx, ny, nz, dx, dy, dz), IG.Spectral(nx, ny, nz + 1, dx, dy, dz)
+    P = IG.PadePoisson(dx, dy, dz, spC, spE, IG.Pade6stagg(nz, dz, 1, isPeriodic=False), PeriodicInZ=False, computeStokesPressure=True, Lz=Lz)
+    rng = np.random.default_rng(3)
+    nxh = nx // 2 + 1
+    u = rng.standard_normal((nz, ny, nxh)) + 1j * rng.standard_normal((nz, ny, nxh))
+    v = rng.standard_normal((nz, ny, nxh)) + 1j * rng.standard_normal((nz, ny, nxh))
+    w = rng.standard_normal((nz + 1, ny, nxh)) + 1j * rng.standard_normal((nz + 1, ny, nxh))
+    wu, wv, ww = P.ProjectStokesPressure(u, v, w)
+    k1 = IG.O.wavenums(nx, dx)[:nxh]
+    k2 = IG.O.wavenums(ny, dy)
+    gu, gv, gw = u.copy(), v.copy(), w.copy()
+    dzl = Lz / nz
+    for jj in range(ny):
+        for ii in range(nxh):
+            lam = np.sqrt(k1[ii] ** 2 + k2[jj] ** 2)
+            den = 1.0 / (lam * np.sinh(lam * Lz) + 1e-13) if lam * Lz < 500.0 else 0.0
+            den = 0.0 if den < 1e-16 else den
+            if ii == 0 and jj == 0:
+                den = 0.0
+            ch = -gw[0, jj, ii] * den
+            for k in range(nz):
+                zc = 0.5 * (k * dzl + (k + 1) * dzl)
+                t = lam * (Lz - zc)
+                cb = np.cosh(t) if t < 32.0 else 4.0e13
+                ph = 1j * ch * cb
+                gu[k, jj, ii] -= k1[ii] * ph
+                gv[k, jj, ii] -= k2[jj] * ph
+            gw[0, jj, ii] = 0.0
+            for k in range(1, nz + 1):
+                t = lam * (Lz - k * dzl)
+                sb = -lam * np.sinh(t) if t < 32.0 else -4.0e13
+                gw[k, jj, ii] -= ch * sb
+            ch = gw[nz, jj, ii] * den
+            for k in range(nz):
+                zc = 0.5 * (k * dzl + (k + 1) * dzl)
+                t = lam * zc
+                ct = np.cosh(t) if t < 32.0 else 1.0e13
+                ph = 1j * ch * ct
+                gu[k, jj, ii] -= k1[ii] * ph
+                gv[k, jj, ii] -= k2[jj] * ph
+                t = lam * (k * dzl)
+                stp = lam * np.sinh(t) if t < 32.0 else 4.0e13
+                gw[k, jj, ii] -= ch * stp
+            gw[nz, jj, ii] = 0.0
+    for a, b in ((gu, wu), (gv, wv), (gw, ww)):
+        assert np.abs(a - b).max() < 1e-12 * max(np.abs(b).max(), 1.0)

@@ -122,3 +122,16 @@ def test_wall_bounded_projection(pdo, oracle, shape):
         po.getPressure(du, dv, dw)                                               # periodic-only
     with pytest.raises(pdo.PadeOpsError):
         pdo.padepoisson().init(*d, spC, spE, derivZ=der, PeriodicInZ=True)      # periodicity of derivZ and the solver must agree
+    # computeStokesPressure = .true. (:320-384): w* nonzero on the walls on input
+    ps = pdo.padepoisson()
+    ps.init(*d, spC, spE, computeStokesPressure=True, Lz=1.0, derivZ=der, PeriodicInZ=False)
+    rS = IG.PadePoisson(*d, rC, rE, IG.Pade6stagg(nz, d[2], 1, isPeriodic=False), PeriodicInZ=False, computeStokesPressure=True, Lz=1.0)
+    uhd, vhd = rC.dealias(uh), rC.dealias(vh)
+    whs = rE.dealias(rE.fft(rng.standard_normal((nz + 1, ny, nx))))
+    want = rS.PressureProjection(uhd, vhd, whs)
+    du, dv, dw = _dev(uhd), _dev(vhd), _dev(whs)
+    ps.PressureProjection(du, dv, dw)
+    for got, ref in zip((du, dv, dw), want):
+        assert _rel(got.cpu().numpy(), ref) < TOL
+    div, _ = ps.DivergenceCheck(du, dv, dw)
+    assert np.abs(div.cpu().numpy()).max() < 1e-11 * np.abs(rS.divergence(uhd, vhd, whs)).max()
