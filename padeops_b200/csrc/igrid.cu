@@ -559,6 +559,29 @@ int pdo_igrid_destroy(pdo_igrid_t g) {
     return 0;
 }
 
+// get_boundary_conditions_stencil (igrid.F90:5148-5204): (bottom, top) stencil codes per quantity; -1 odd, +1 even, 0 one-sided
+static void ig_fill_bcs(int bc[12][2], int bot_wall, int top_wall) {
+    const int walls[2] = {bot_wall, top_wall};
+    for (int sd = 0; sd < 2; ++sd) {
+        bc[BC_W][sd] = -1; bc[BC_WdWdz][sd] = -1; bc[BC_WW][sd] = +1; bc[BC_dWdz][sd] = 0;
+        if (walls[sd] == 1) {        // no-slip: w = 0 and dwdz = 0, so w is extended evenly
+            bc[BC_U][sd] = -1; bc[BC_V][sd] = -1; bc[BC_dUdz][sd] = 0; bc[BC_dVdz][sd] = 0;
+            bc[BC_WdUdz][sd] = 0; bc[BC_WdVdz][sd] = 0; bc[BC_UW][sd] = +1; bc[BC_VW][sd] = +1;
+            bc[BC_W][sd] = +1; bc[BC_WdWdz][sd] = -1; bc[BC_WW][sd] = +1; bc[BC_dWdz][sd] = -1;
+        } else {                     // slip
+            bc[BC_U][sd] = +1; bc[BC_V][sd] = +1; bc[BC_dUdz][sd] = -1; bc[BC_dVdz][sd] = -1;
+            bc[BC_WdUdz][sd] = +1; bc[BC_WdVdz][sd] = +1; bc[BC_UW][sd] = -1; bc[BC_VW][sd] = -1;
+        }
+    }
+}
+/* test hook (host only): the stencil codes for (botWall, topWall), order w u v WdUdz WdVdz WdWdz WW UW VW dUdz dVdz dWdz, (bottom, top) each */
+int pdo_debug_igrid_bcs(int bot_wall, int top_wall, int* out24) {
+    int bc[12][2] = {};
+    ig_fill_bcs(bc, bot_wall, top_wall);
+    for (int q = 0; q < 12; ++q) { out24[2 * q] = bc[q][0]; out24[2 * q + 1] = bc[q][1]; }
+    return 0;
+}
+
 // From (u, v, w) on the x-pencils to a consistent state (igrid.F90:625-655): transforms, dealiasing, projection, back to
 // physical space, interpolations and the velocity gradients.  u, v, w: host or device.
 static int ig_set_fields(pdo_igrid_s* g, const double* u, const double* v, const double* w, cudaStream_t st) {
@@ -599,19 +622,8 @@ int pdo_igrid_init(pdo_igrid_t* h, const pdo_igrid_params* p, const double* u, c
     std::memset(g->gradE, 0, sizeof(g->gradE));
     g->prm = *p;
     if (g->prm.dealias_fact <= 0.0) g->prm.dealias_fact = 2.0 / 3.0;
-    if (p->wall_bounded) {   // get_boundary_conditions_stencil (igrid.F90:5148-5204); index 0 bottom, 1 top
-        const int walls[2] = {p->bot_wall, p->top_wall};
-        for (int sd = 0; sd < 2; ++sd) {
-            g->bc[BC_W][sd] = -1; g->bc[BC_WdWdz][sd] = -1; g->bc[BC_WW][sd] = +1; g->bc[BC_dWdz][sd] = 0;
-            if (walls[sd] == 1) {        // no-slip: w = 0 and dwdz = 0, so w is extended evenly
-                g->bc[BC_U][sd] = -1; g->bc[BC_V][sd] = -1; g->bc[BC_dUdz][sd] = 0; g->bc[BC_dVdz][sd] = 0;
-                g->bc[BC_WdUdz][sd] = 0; g->bc[BC_WdVdz][sd] = 0; g->bc[BC_UW][sd] = +1; g->bc[BC_VW][sd] = +1;
-                g->bc[BC_W][sd] = +1; g->bc[BC_WdWdz][sd] = -1; g->bc[BC_WW][sd] = +1; g->bc[BC_dWdz][sd] = -1;
-            } else {                     // slip
-                g->bc[BC_U][sd] = +1; g->bc[BC_V][sd] = +1; g->bc[BC_dUdz][sd] = -1; g->bc[BC_dVdz][sd] = -1;
-                g->bc[BC_WdUdz][sd] = +1; g->bc[BC_WdVdz][sd] = +1; g->bc[BC_UW][sd] = -1; g->bc[BC_VW][sd] = -1;
-            }
-        }
+    if (p->wall_bounded) {
+        ig_fill_bcs(g->bc, p->bot_wall, p->top_wall);
         g->prm.use_d2dz2_c2c = 1;   // uBC, vBC are +-1 for these walls (:2653, 2671)
     }
     g->dx = p->Lx / p->nx; g->dy = p->Ly / p->ny; g->dz = p->Lz / p->nz;

@@ -440,3 +440,18 @@ def test_stokes_kernel_arithmetic():
             gw[nz, jj, ii] = 0.0
     for a, b in ((gu, wu), (gv, wv), (gw, ww)):
         assert np.abs(a - b).max() < 1e-12 * max(np.abs(b).max(), 1.0)
+
+
+@pytest.mark.parametrize("bot,top", [(1, 1), (1, 2), (2, 1), (2, 2)])
+def test_product_stencil_codes_match_the_oracle(bot, top):
+    """The PRODUCT's get_boundary_conditions_stencil table (host-only hook) against the oracle's restatement of igrid.F90:5148-5204."""
+    import ctypes as C
+    import padeops_b200 as pdo
+    out = (C.c_int * 24)()
+    L = pdo.lib()
+    L.pdo_debug_igrid_bcs.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
+    assert L.pdo_debug_igrid_bcs(bot, top, out) == 0
+    ref = IG.IGrid.get_boundary_conditions_stencil(top, bot)
+    order = ("w", "u", "v", "WdUdz", "WdVdz", "WdWdz", "WW", "UW", "VW", "dUdz", "dVdz", "dWdz")
+    for q, name in enumerate(order):
+        assert (out[2 * q], out[2 * q + 1]) == ref[name], name
