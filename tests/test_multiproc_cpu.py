@@ -26,6 +26,27 @@ for pen in "xyz":
         st, en = d[pen + "st"], d[pen + "en"]
         cover[st[2]-1:en[2], st[1]-1:en[1], st[0]-1:en[0]] += 1
     assert (cover == 1).all(), pen
+# 1b) decomp_2d_write_one's per-rank writer with REAL concurrency: rank 0 creates / truncates, everyone else writes its own sub-box of
+#     the same file at the same time; the file must be the global array, and every rank reads its pencil back (io_test.f90)
+import ctypes as C
+L = pdo.lib()
+i3 = lambda v: (C.c_int * 3)(*[int(x) for x in v])
+G = np.arange(1, nx * ny * nz + 1, dtype=np.float64).reshape(nz, ny, nx)
+fn = os.path.join(os.environ["PDO_TMPDIR"], "u.dat").encode()
+for pen in "xyz":
+    sz, st = info[pen + "sz"], [a - 1 for a in info[pen + "st"]]
+    blk = np.ascontiguousarray(G[st[2]:st[2] + sz[2], st[1]:st[1] + sz[1], st[0]:st[0] + sz[0]])
+    if rank == 0:
+        assert L.pdo_io_write_block(fn, i3((nx, ny, nz)), i3(sz), i3(st), 1, C.c_void_p(blk.ctypes.data), 1) == 0
+    dist.barrier()
+    if rank != 0:
+        assert L.pdo_io_write_block(fn, i3((nx, ny, nz)), i3(sz), i3(st), 1, C.c_void_p(blk.ctypes.data), 0) == 0
+    dist.barrier()
+    assert open(fn, "rb").read() == G.tobytes(), pen
+    back = np.zeros_like(blk)
+    assert L.pdo_io_read_block(fn, i3((nx, ny, nz)), i3(sz), i3(st), 1, C.c_void_p(back.ctypes.data)) == 0
+    assert np.array_equal(back, blk)
+    dist.barrier()
 # 2) the NCCL-id broadcast reaches pdo_comm_init on every rank; without a GPU it must refuse (no CPU fallback)
 try:
     pdo.decomp_2d.comm_init()
@@ -46,7 +67,7 @@ def test_world2_gloo_host_logic(tmp_path):
     w.write_text(WORKER)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", str(w)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, PDO_TMPDIR=str(tmp_path)))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     import torch
     want = "inited" if torch.cuda.is_available() else "err1004"
