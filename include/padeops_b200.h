@@ -351,6 +351,7 @@ int pdo_padepoisson_divergence_check(pdo_padepoisson_t h, double* uhat, double* 
    no Coriolis / stratification / turbines / fringe.
    The namelist file of igrid%init is replaced by this struct. */
 typedef struct pdo_igrid_s* pdo_igrid_t;
+typedef struct pdo_hit_forcing_s* pdo_hit_forcing_t;   /* the forcing type, declared with its entry points further down */
 typedef struct {
     int nx, ny, nz;
     double Lx, Ly, Lz;
@@ -393,6 +394,7 @@ int pdo_igrid_enable_sgs(pdo_igrid_t h, int sgs_model_id, double csgs, int expli
 /* useHITForcing = .true. (igrid.F90:940-944, 1907-1910): call once after init; the forcing is added to every right-hand side
    after the viscous term, with a new draw at the first stage of every time step (tidStart = the current step) */
 int pdo_igrid_enable_hit_forcing(pdo_igrid_t h, double kmin, double kmax, int nwaves, double eps_amplitude, int rand_seed_to_add);
+pdo_hit_forcing_t pdo_igrid_hit_forcing(pdo_igrid_t h);   /* borrowed; NULL without forcing.  set_wavenumbers on it before a time step injects that step's draw */
 int pdo_igrid_dump_restart(pdo_igrid_t h, const char* outputdir, int run_id);
 int pdo_igrid_read_restart(pdo_igrid_t h, const char* inputdir, int run_id, int tid);
 int pdo_igrid_dump_full_field(pdo_igrid_t h, int which, const char* label4, const char* outputdir, int run_id);
@@ -406,9 +408,8 @@ int pdo_igrid_max_divergence(pdo_igrid_t h, double* max_div, void* stream);   /*
    space, w shifted edges -> cells and back.  Evaluated as a direct DFT of the Nwaves forced columns and plane-wave updates of
    the right-hand sides instead of the reference's six whole-field z transforms.  The &HIT_Forcing namelist enters as arguments.
    The random draw: Fortran's random_number is compiler-specific, the library uses SplitMix64 on the reference's seed
-   arithmetic (:122-128); set_wavenumbers injects the reference's own draw for an A/B run.  Arrays: DEVICE pointers, complex
+   arithmetic (:122-128); set_wavenumbers injects the reference's own draw for an A/B run (kept through the next new time step).  Arrays: DEVICE pointers, complex
    y-pencils of the cell (u, v) and edge (w) spectral decompositions. */
-typedef struct pdo_hit_forcing_s* pdo_hit_forcing_t;
 int pdo_hit_forcing_init(pdo_hit_forcing_t* h, pdo_spectral_t spectC, pdo_spectral_t spectE, double kmin, double kmax, int nwaves,
                          double eps_amplitude, int tid_start, int rand_seed_to_add);
 int pdo_hit_forcing_destroy(pdo_hit_forcing_t h);

@@ -444,13 +444,17 @@ class HITForcing:
                                       self._uniform(n, 0.0, 2.0 * np.pi, self.seed3))
 
     def set_wavenumbers(self, wx, wy, wz):
+        """inject a draw (the reference RNG's, say): the next new time step keeps it instead of drawing; its seeds still advance"""
         self.wave_x, self.wave_y, self.wave_z = (np.asarray(a, dtype=int) for a in (wx, wy, wz))
+        self._injected = True
 
     def getRHS_HITforcing(self, urhs, vrhs, wrhs, uhat_xy, vhat_xy, what_xy, newTimestep):     # :254-311
         sp = self.spectC
         nz = sp.nz
         if newTimestep:
-            self.pick_random_wavenumbers()
+            if not getattr(self, "_injected", False):
+                self.pick_random_wavenumbers()
+            self._injected = False
             self.update_seeds()
         uh = sp.take_fft1d_z2z(uhat_xy)
         vh = sp.take_fft1d_z2z(vhat_xy)

@@ -143,6 +143,7 @@ _PROTOS.update({
     "pdo_hit_forcing_get_wavenumbers": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pdo_hit_forcing_get_rhs": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int, C.c_void_p]),
     "pdo_igrid_enable_hit_forcing": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int]),
+    "pdo_igrid_hit_forcing": (C.c_void_p, [C.c_void_p]),
     "pdo_debug_hit_draw": (C.c_int, [C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pdo_cd06stagg_init_nonperiodic": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]),
     "pdo_cd06stagg_ddz_C2C": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -20,6 +20,7 @@ struct pdo_hit_forcing_s {
     long long seed0 = 0, seed1 = 0, seed2 = 0, seed3 = 0;
     std::vector<int> waves;      // wave_x[n], wave_y[n], wave_z[n]
     bool have_waves = false, waves_dirty = false;   // dirty: the host copy is newer than d_waves
+    bool injected = false;       // set_wavenumbers: the next new time step keeps these instead of drawing (A/B runs against the reference's RNG)
     int* d_waves = nullptr;
     double2* d_part = nullptr;   // (U, V, Wraw) per wave
 };
@@ -151,11 +152,14 @@ int hit_get_rhs_dev(pdo_hit_forcing_s* f, double2* ur, double2* vr, double2* wr,
                     bool new_timestep, cudaStream_t st) {
     const int n = f->nwaves;
     if (new_timestep) {     // :265-268
-        std::vector<double> a(3 * (size_t)n);
-        hit_uniform(a.data(), n, f->kmin, f->kmax, f->seed1);
-        hit_uniform(a.data() + n, n, -1.0, 1.0, f->seed2);
-        hit_uniform(a.data() + 2 * n, n, 0.0, 2.0 * kPi, f->seed3);
-        hit_waves_from_samples(f, a.data(), a.data() + n, a.data() + 2 * n);
+        if (!f->injected) {
+            std::vector<double> a(3 * (size_t)n);
+            hit_uniform(a.data(), n, f->kmin, f->kmax, f->seed1);
+            hit_uniform(a.data() + n, n, -1.0, 1.0, f->seed2);
+            hit_uniform(a.data() + 2 * n, n, 0.0, 2.0 * kPi, f->seed3);
+            hit_waves_from_samples(f, a.data(), a.data() + n, a.data() + 2 * n);
+        }
+        f->injected = false;
         hit_update_seeds(f);
     }
     if (!f->have_waves) return fail(PDO_E_BADARG, "HIT forcing: no wavenumbers yet (newTimestep was never true and none were set)");
@@ -217,13 +221,15 @@ int pdo_hit_forcing_destroy(pdo_hit_forcing_t f) {
     delete f;
     return 0;
 }
-/* the draw of the CURRENT step, e.g. the reference RNG's wave_x / wave_y / wave_z for an A/B run */
+/* the draw of the CURRENT (or the next new) time step, e.g. the reference RNG's wave_x / wave_y / wave_z for an A/B run: the next
+   call with newTimestep keeps these instead of drawing (its seeds still advance), later steps draw again */
 int pdo_hit_forcing_set_wavenumbers(pdo_hit_forcing_t f, const int* wave_x, const int* wave_y, const int* wave_z) {
     if (!f || !wave_x || !wave_y || !wave_z) return fail(PDO_E_BADARG, "null argument");
     const int n = f->nwaves;
     for (int i = 0; i < n; ++i) { f->waves[i] = wave_x[i]; f->waves[n + i] = wave_y[i]; f->waves[2 * n + i] = wave_z[i]; }
     f->have_waves = true;
     f->waves_dirty = true;
+    f->injected = true;
     return 0;
 }
 int pdo_hit_forcing_get_wavenumbers(pdo_hit_forcing_t f, int* wave_x, int* wave_y, int* wave_z) {

@@ -752,6 +752,8 @@ int pdo_debug_sgs_point(int mid, double cmodel, double cx, double cy, double cz,
     *nu = c.cmodel * sgs_kernel_point(c, d9, S6);
     return 0;
 }
+/* the forcing object of a handle with useHITForcing (borrowed; e.g. for pdo_hit_forcing_set_wavenumbers before a time step) */
+pdo_hit_forcing_t pdo_igrid_hit_forcing(pdo_igrid_t g) { return g ? g->hit : nullptr; }
 int pdo_igrid_enable_hit_forcing(pdo_igrid_t g, double kmin, double kmax, int nwaves, double eps_amplitude, int rand_seed_to_add) {
     if (!g) return fail(PDO_E_BADARG, "null handle");
     pdo_hit_forcing_destroy(g->hit);

@@ -404,6 +404,13 @@ class igrid:
     def enableHITForcing(self, kmin=2.0, kmax=10.0, Nwaves=20, EpsAmplitude=0.1, RandSeedToAdd=0):
         """useHITForcing = .true. with the &HIT_Forcing namelist (igrid.F90:940-944); call once after init"""
         check(lib().pdo_igrid_enable_hit_forcing(self._h, float(kmin), float(kmax), int(Nwaves), float(EpsAmplitude), int(RandSeedToAdd)))
+        self._hit_nwaves = int(Nwaves)
+
+    def setHITWavenumbers(self, wave_x, wave_y, wave_z):
+        """inject the draw of the next time step (e.g. the reference RNG's) into the handle's forcing object"""
+        n = self._hit_nwaves
+        a = [(C.c_int * n)(*[int(v) for v in w]) for w in (wave_x, wave_y, wave_z)]
+        check(lib().pdo_hit_forcing_set_wavenumbers(C.c_void_p(lib().pdo_igrid_hit_forcing(self._h)), *a))
 
     def enableSGS(self, SGSModelID=2, Csgs=0.17, explicitCalcEdgeEddyViscosity=False):
         """useSGS = .true. with the &SGS_MODEL entries in scope (igrid.F90:1866-1871); init with computeAllGradients=True"""

@@ -168,3 +168,18 @@ def test_sparse_dft_algorithm_of_the_kernels_equals_the_fft_formulation():
         got[2][:, ky, kx] += fac * np.conj(W) * sp.C2Eshift[kz] / nz * np.exp(2j * np.pi * ((kz * ze) % nz) / nz)
     for a, b in zip(got, want):
         assert np.abs(a - b).max() < 1e-12 * np.abs(b).max()
+
+
+def test_injected_draw_is_kept_through_the_next_new_step_only():
+    sp, f, _ = _setup(kmin=1.0, kmax=3.0, Nwaves=4, tidStart=0)
+    g = IG.HITForcing(sp, kmin=1.0, kmax=3.0, Nwaves=4, tidStart=0)
+    z = np.zeros((sp.nz, sp.ny, sp.nxh), dtype=complex)
+    zE = np.zeros((sp.nz + 1, sp.ny, sp.nxh), dtype=complex)
+    f.set_wavenumbers([1, 2, 1, 0], [0, 1, 1, 2], [1, 1, 2, 1])
+    f.getRHS_HITforcing(z, z, zE, z + 1.0, z + 1.0, zE + 1.0, True)
+    g.getRHS_HITforcing(z, z, zE, z + 1.0, z + 1.0, zE + 1.0, True)
+    assert f.wave_x.tolist() == [1, 2, 1, 0]                      # kept ...
+    assert (f.seed0, f.seed1) == (g.seed0, g.seed1)               # ... while the seeds advance like in an undisturbed run
+    f.getRHS_HITforcing(z, z, zE, z + 1.0, z + 1.0, zE + 1.0, True)
+    g.getRHS_HITforcing(z, z, zE, z + 1.0, z + 1.0, zE + 1.0, True)
+    assert f.wave_x.tolist() == g.wave_x.tolist() and f.wave_z.tolist() == g.wave_z.tolist()    # the next step draws again, in step
