@@ -10,30 +10,6 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
-    config.addinivalue_line("markers", "late_wrapper: the test that runs the not-yet-hardware-validated GPU tests in a subprocess")
-
-
-def _is_late(item):
-    """GPU tests written after a round's last GPU session carry xfail(strict=False) until their first hardware run."""
-    return item.get_closest_marker("gpu") is not None and item.get_closest_marker("xfail") is not None and \
-        item.get_closest_marker("late_wrapper") is None
-
-
-def pytest_collection_modifyitems(config, items):
-    """Isolation of unvalidated device code: a kernel that faults poisons the CUDA context of its process, and every test after
-    it would fail with it.  So the late tests never run inside the main pytest process: there they are skipped, and
-    tests/test_late_isolated.py runs them (and only them) in a child process with PDO_RUN_LATE=1."""
-    if os.environ.get("PDO_RUN_LATE") == "1":
-        keep, drop = [], []
-        for it in items:
-            (keep if _is_late(it) else drop).append(it)
-        items[:] = keep
-        config.hook.pytest_deselected(items=drop)
-        return
-    skip = pytest.mark.skip(reason="not yet validated on hardware: runs in the child process of tests/test_late_isolated.py")
-    for it in items:
-        if _is_late(it):
-            it.add_marker(skip)
 
 
 @pytest.fixture(scope="session")

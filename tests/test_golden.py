@@ -193,7 +193,6 @@ def test_product_host_code_reproduces_widened_golden(pdo, wide):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="added after the round's last GPU session: first hardware run is the driver's round-end pass")
 def test_cuda_reproduces_widened_golden(pdo, wide):
     import torch
     M = _wide_module()

@@ -192,8 +192,6 @@ def test_igrid_all_gradients_flag_does_not_change_the_solution(pdo):
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
 
 
-@pytest.mark.xfail(strict=False, reason="rotational advection form added after the round's last GPU session: first hardware run "
-                                        "happens in the driver's round-end test pass (CPU oracle side is pinned in test_oracle_igrid.py)")
 @pytest.mark.parametrize("scheme", [1, 2])
 def test_igrid_substep_rotational_form_matches_oracle(pdo, IG, scheme):
     """AdvectionTerm = 0 (u x omega, igrid.F90:1527-1555 — what the authors' HIT deck runs) against the oracle."""
@@ -214,11 +212,6 @@ def test_igrid_substep_rotational_form_matches_oracle(pdo, IG, scheme):
     assert g.maxDivergence() < 1e-11 * max(np.abs(ref.u).max(), np.abs(ref.w).max())
 
 
-_LATE = "added after the round's last GPU session: first hardware run happens in the driver's round-end test pass " \
-        "(the CPU oracle side is pinned in test_oracle_igrid.py)"
-
-
-@pytest.mark.xfail(strict=False, reason=_LATE)
 def test_pade6stagg_fourier_collocation_matches_oracle(pdo, IG):
     """scheme = fourierColl (PadeDerOps.F90:57-78, spectral.F90:387-680, 843-856): the six z-operators on complex arrays."""
     nx, ny, nz = 16, 12, 16
@@ -242,7 +235,6 @@ def test_pade6stagg_fourier_collocation_matches_oracle(pdo, IG):
     assert e.value.code == 43
 
 
-@pytest.mark.xfail(strict=False, reason=_LATE)
 @pytest.mark.parametrize("adv", [0, 1])
 def test_igrid_substep_fourier_z_matches_oracle(pdo, IG, adv):
     """NumericalSchemeVert = 2 with either advection form (rotational + Fourier-z is the authors' HIT deck's choice)."""
@@ -263,7 +255,6 @@ def test_igrid_substep_fourier_z_matches_oracle(pdo, IG, adv):
     assert g.maxDivergence() < 1e-11 * max(np.abs(ref.u).max(), np.abs(ref.w).max())
 
 
-@pytest.mark.xfail(strict=False, reason=_LATE)
 def test_restart_files_round_trip(pdo, IG, tmp_path):
     """dumpRestartFile / readRestartFile / dumpFullField in the reference's format (igrid.F90:2719-2823): flat global
     Fortran-order doubles per field + the g15.5 info file; a run restarted from them continues like the original."""
@@ -297,7 +288,6 @@ def test_restart_files_round_trip(pdo, IG, tmp_path):
     assert e.value.code == 321
 
 
-@pytest.mark.xfail(strict=False, reason=_LATE)
 def test_hit_forcing_matches_oracle(pdo, IG):
     """HIT_shell_forcing%getRHS_HITforcing (forcingIsotropic.F90:254-311) on device-resident right-hand sides: the library's
     direct-DFT evaluation against the oracle's whole-field FFT formulation, with injected and with drawn wavenumbers."""
@@ -333,7 +323,6 @@ def test_hit_forcing_matches_oracle(pdo, IG):
     assert torch.cuda.is_available()
 
 
-@pytest.mark.xfail(strict=False, reason=_LATE)
 @pytest.mark.parametrize("vert", [1, 2])
 def test_igrid_with_hit_forcing_matches_oracle(pdo, IG, vert):
     """useHITForcing = .true. (igrid.F90:940-944, 1907-1910): a new draw per step, the same waves through the RK stages."""
@@ -357,7 +346,6 @@ def test_igrid_with_hit_forcing_matches_oracle(pdo, IG, vert):
     assert g.maxDivergence() < 1e-10
 
 
-@pytest.mark.xfail(strict=False, reason=_LATE)
 @pytest.mark.parametrize("mid,Csgs,explicitE", [(0, 0.17, False), (1, 1.5, False), (2, 1.67, False), (2, 1.67, True)])
 def test_igrid_with_sgs_matches_oracle(pdo, IG, mid, Csgs, explicitE):
     """useSGS = .true. (igrid.F90:1866-1871): Smagorinsky / sigma / AMD with a global constant, interpolated or explicit edge
@@ -388,7 +376,6 @@ def test_igrid_with_sgs_matches_oracle(pdo, IG, mid, Csgs, explicitE):
     assert e.value.code == 213
 
 
-@pytest.mark.xfail(strict=False, reason=_LATE)
 def test_hit_periodic_deck_configuration(pdo, IG):
     """The combination the authors' HIT_Periodic deck runs (problems/incompressible/HIT_Periodic_moving_files/input_fourier.dat):
     rotational advection, Fourier collocation in z, SSP-RK45, AMD model (Csgs = 1.67), HIT shell forcing (kmin 4 ... here 1-2.5 on
@@ -430,7 +417,6 @@ def _channel_fields(nx, ny, nz, Lz, slip):
     return u, v, w
 
 
-@pytest.mark.xfail(strict=False, reason=_LATE)
 @pytest.mark.parametrize("walls", [(2, 2), (1, 1), (1, 2)])
 @pytest.mark.parametrize("adv,scheme,stokes", [(1, 1, True), (0, 2, True), (1, 2, False)])
 def test_wall_bounded_igrid_matches_oracle(pdo, IG, walls, adv, scheme, stokes):

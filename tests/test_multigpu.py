@@ -20,8 +20,6 @@ def test_transposes_fft_poisson_multi_gpu(world):
     assert "MP_WORKER_RESULT PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-@pytest.mark.xfail(strict=False, reason="worker sections written after the round's last multi-GPU session (Poisson dir_id 3, filter3D, igrid "
-                                        "rotational / Fourier-z on decomposed fields): first hardware run is the driver's")
 @pytest.mark.parametrize("world", [2, 4])
 def test_late_sections_multi_gpu(world):
     import torch

@@ -82,8 +82,6 @@ def test_one_sided_closure_exact_on_quartics_on_the_gpu(pdo):
     assert np.abs(h.d2d1(_dev(f)).cpu().numpy() - 12 * x ** 2).max() < 1e-8
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's last GPU session (same kernels as the CD10 / CF90 cases above, which ran "
-                                        "green on B200; the CD06 rows and stencils are verified on the host in test_nonperiodic_cpu.py)")
 @pytest.mark.parametrize("axis", [0, 1, 2])
 def test_cd06_nonperiodic_one_sided(pdo, oracle, axis):
     shape = {0: (3, 5, 24), 1: (3, 24, 5), 2: (24, 3, 5)}[axis]
@@ -96,8 +94,6 @@ def test_cd06_nonperiodic_one_sided(pdo, oracle, axis):
     assert pdo.cd06().init(n, dx, periodic_=False, bc1_=1) == 1002
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's last GPU session (the pointwise kernel of the CD10 / CF90 cases above with the "
-                                        "Gaussian rows; its host-device routine is verified on the CPU in tests/test_nonperiodic_cpu.py)")
 @pytest.mark.parametrize("axis", [0, 1, 2])
 def test_gaussian_nonperiodic_all_boundary_codes(pdo, oracle, axis):
     """gaussian%filter* with periodic = .false. (filters/gaussian.F90:215-330), also through the filters dispatch type and filter3D"""
@@ -123,7 +119,6 @@ def test_gaussian_nonperiodic_all_boundary_codes(pdo, oracle, axis):
         assert _rel(a.cpu().numpy(), oracle.filter3D(g, 2, ("cf90", "gaussian", "gaussian"), (True, True, False), z_bc=(0, 1))) < TOL
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's last GPU session (the Gaussian filter's kernels with the least-squares coefficients)")
 def test_lstsq_filter_periodic_and_walls(pdo, oracle):
     """lstsq%filter1/2/3 (filters/lstsq.F90), alone and through the filters dispatch type (method "lstsq", filters.F90:111-118)"""
     n = 40

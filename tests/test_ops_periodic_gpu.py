@@ -1,15 +1,13 @@
 """GPU parity of Ops_Periodic (igrid_operators_periodic.F90:13-161), of the spectral type's z-Fourier in-place procedures and of
 the REAL fourierColl procedures of Pade6stagg against the CPU oracle.  Bar: 1e-12 relative to max|ref| (north_star).
 
-Written after the round's last GPU session: every test is xfail(strict=False) until its first hardware run (the driver's
-round-end pass); the oracle side is pinned in tests/test_oracle_ops_periodic.py."""
+The oracle side is pinned in tests/test_oracle_ops_periodic.py."""
 import numpy as np
 import pytest
 
 from conftest import broadband
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="added after the round's last GPU session: first hardware run is the driver's round-end pass")]
+pytestmark = [pytest.mark.gpu]
 TOL = 1e-12
 
 

@@ -96,7 +96,6 @@ def test_poisson_manufactured_solution(pdo, oracle, comm):
         assert _relerr(out.cpu().numpy(), oracle.poisson_solve(rhs, dx, dy, dz)) < TOL
 
 
-@pytest.mark.xfail(strict=False, reason="dir_id = 3 added after the round's last GPU session: first hardware run at round end")
 def test_poisson_z_pencil_entry(pdo, oracle, comm):
     """dir_id = 3 (z-pencil in / out, PoissonPeriodic.F90:151-154): on one rank the three pencils coincide, so the result
     must equal the oracle's like dir_id = 1 does."""

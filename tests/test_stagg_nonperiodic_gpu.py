@@ -1,8 +1,8 @@
 """GPU parity of the NON-PERIODIC staggered compact operators (cd06stagg%init_nonperiodic) and of
 Pade6stagg's wall dispatch (PadeDerOps.F90:92-110, 185-205, 449-482) against the oracle.  Bar: 1e-12 relative.
 
-Written after the round's last GPU session: xfail(strict=False) until the first hardware run.  The kernel's per-line routine
-is already verified on the host for every operator and wall combination (tests/test_stagg_nonperiodic_cpu.py)."""
+The kernel's per-line routine
+is also verified on the host for every operator and wall combination (tests/test_stagg_nonperiodic_cpu.py)."""
 import itertools
 
 import numpy as np
@@ -10,8 +10,7 @@ import pytest
 
 from conftest import broadband
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="added after the round's last GPU session: first hardware run is the driver's round-end pass")]
+pytestmark = [pytest.mark.gpu]
 TOL = 1e-12
 OPS = [("ddz_E2C", 1, 0), ("ddz_C2E", 0, 1), ("ddz_C2C", 0, 0), ("ddz_E2E", 1, 1), ("InterpZ_E2C", 1, 0), ("InterpZ_C2E", 0, 1),
        ("d2dz2_C2C", 0, 0), ("d2dz2_E2E", 1, 1)]

@@ -74,11 +74,6 @@ def test_zslab_unsupported_fails_loudly(pdo):
     assert rc != 0
 
 
-_LATE = "added after the round's last GPU session: first hardware run happens in the driver's round-end test pass " \
-        "(composition of GPU-validated filters and transposes; the oracle side is pinned in test_oracle_vecops.py)"
-
-
-@pytest.mark.xfail(strict=False, reason=_LATE)
 @pytest.mark.parametrize("numtimes", [1, 2, 3])
 @pytest.mark.parametrize("methods", [("cf90", "cf90", "cf90"), ("gaussian", "cf90", "gaussian")])
 def test_filter3d_single_rank(pdo, oracle, numtimes, methods):
@@ -98,7 +93,6 @@ def test_filter3d_single_rank(pdo, oracle, numtimes, methods):
     ops.destroy()
 
 
-@pytest.mark.xfail(strict=False, reason=_LATE)
 def test_filter3d_nonperiodic_z_and_mismatched_filters(pdo, oracle):
     nx, ny, nz = 32, 32, 40
     d = 2 * np.pi / nx
@@ -119,7 +113,6 @@ def test_filter3d_nonperiodic_z_and_mismatched_filters(pdo, oracle):
     ops.destroy()
 
 
-@pytest.mark.xfail(strict=False, reason=_LATE)
 def test_vector_ops_host_arrays(pdo, oracle):
     """the unmodified caller hands HOST arrays to gradient / divergence / curl / filter3D."""
     nx, ny, nz = 32, 24, 16
