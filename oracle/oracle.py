@@ -325,7 +325,8 @@ def cf90_np(f, axis, bc1=0, bcn=0):
 
 
 GAUSS_COEFS = (3565.0 / 10368.0, 3091.0 / 12960.0, 1997.0 / 25920.0, 149.0 / 12960.0, 107.0 / 103680.0)    # gaussian.F90:15-19
-LSTSQ_COEFS = (0.5, 0.6744132 / 2.0, 0.0 / 2.0, -0.1744132 / 2.0, 0.0 / 2.0)                               # lstsq.F90:14-19
+# lstsq.F90:14-19: real(0.6744132, rkind) is a default-real (single precision) literal widened to double
+LSTSQ_COEFS = (0.5, float(np.float32(0.6744132)) / 2.0, 0.0 / 2.0, float(np.float32(-0.1744132)) / 2.0, 0.0 / 2.0)
 
 
 def lstsq(f, axis):

@@ -223,6 +223,7 @@ _PROTOS["pdo_debug_ctma_config"] = (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int
 _PROTOS["pdo_debug_np_rows"] = (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_dp])
 _PROTOS["pdo_debug_np_line_host"] = (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, c_dp, c_dp, C.c_longlong, C.c_longlong])
 _PROTOS["pdo_debug_chunk_tables"] = (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int])
+_PROTOS["pdo_debug_transpose_emulate"] = (C.c_int, [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_void_p])
 _PROTOS["pdo_debug_set_variant"] = (C.c_int, [C.c_int, C.c_int])
 _PROTOS["pdo_debug_last_variant"] = (C.c_int, [])
 

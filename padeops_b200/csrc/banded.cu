@@ -1135,21 +1135,22 @@ chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __gri
                           const __grid_constant__ ChunkTables tab, const __grid_constant__ OpParams op,
                           // z-slab (distributed line) mode: this GPU holds rows [0, n) of a longer periodic line; what lies
                           // beyond either end was received from the neighbouring GPUs before the launch
-                          const __grid_constant__ ZSlabArgs zs) {
+                          const __grid_constant__ ZSlabArgs zs, int nbuf) {
     constexpr int HL = Halo<RK>::L, HR = Halo<RK>::R;
     constexpr int HB = HL > HR ? HL : HR;           // rows of a halo box
     constexpr int BWc = BW > 0 ? BW : 1;
     extern __shared__ __align__(128) double smt[];
     __shared__ __align__(8) unsigned long long full_bar[kXtBuf];
-    __shared__ __align__(8) unsigned long long ex_bar;
+    __shared__ __align__(8) unsigned long long ex_bar[2];   // "the halo of parity b has landed" (pushed by the neighbour CTAs)
     const int RPC = PC * M;
     const size_t tile_elems = (size_t)(RPC + 2 * HB) * XT;
     const int W = tab.W, HW = W + 1;
     const int EC = PC + 2 * HW;                     // extended chunk slots: [HW left halo][PC own][HW right halo]
     const int ESL = EC * XT;
-    double* eA = smt + kXtBuf * tile_elems;         // [BWc][EC][XT]
-    double* eB = eA + BWc * ESL;
-    double* sS = eB + BWc * ESL;                    // [BWc][PC][XT]
+    // 2 x { eA[BWc][EC][XT], eB[BWc][EC][XT] }: ping-pong per tile.  A neighbour CTA can run at most one tile ahead (its next
+    // separator solve needs MY next push), so it only ever pushes into the half I am not reading: no cluster barrier, no
+    // fence on the per-tile path, and the CTAs of a cluster drift freely within that one-tile window.
+    double* ex = smt + nbuf * tile_elems;         // nbuf = 3 rotating tile buffers (2 when the exchange arrays are large: CF90)
     const int tid = threadIdx.x;
     const int xt_shift = __ffs(XT) - 1;
     const int xi = tid & (XT - 1), pl = tid >> xt_shift;
@@ -1164,7 +1165,8 @@ chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __gri
     if (tid == 0) {
 #pragma unroll
         for (int b = 0; b < kXtBuf; ++b) mbar_init(smem_u32(&full_bar[b]), 1);
-        mbar_init(smem_u32(&ex_bar), 1);
+        mbar_init(smem_u32(&ex_bar[0]), 1);
+        mbar_init(smem_u32(&ex_bar[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (BW > 0 && C > 1) cluster_sync_all();        // peers' barriers exist before anyone pushes
@@ -1193,7 +1195,7 @@ chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __gri
 
     int it = 0;
     for (long long tile = t0; tile < ntiles; tile += ncl, ++it) {
-        const int b = it % kXtBuf;
+        const int b = it % nbuf;
         double* buf = smt + b * tile_elems;
         // z-slab mode: the edge CTAs' halo pieces come from global memory; the loads are issued here, a whole tile's worth of
         // work before their values are stored into the extended arrays, so their latency is off the cluster's critical path
@@ -1216,7 +1218,7 @@ chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __gri
                 }
             }
         }
-        mbar_wait_or_trap(smem_u32(&full_bar[b]), (unsigned)(it / kXtBuf) & 1u);
+        mbar_wait_or_trap(smem_u32(&full_bar[b]), (unsigned)(it / nbuf) & 1u);
 
         double v[M + HL + HR];
         {
@@ -1231,8 +1233,9 @@ chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __gri
         if constexpr (BW > 0) {
             double a_[2], b_[2];
             chunk_interior<BW, M>(r, tab, a_, b_);
-            // everyone in the cluster has finished reading the previous tile's extended arrays
-            if (C > 1 && it > 0) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+            const int par = it & 1;
+            double* eA = ex + par * (2 * BWc * ESL);
+            double* eB = eA + BWc * ESL;
             const int me = (HW + pl) * XT + xi;
             eA[me] = a_[0];
             eB[me] = b_[0];
@@ -1250,7 +1253,7 @@ chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __gri
                     }
                 }
                 if (C > 1) {
-                    const unsigned bar = smem_u32(&ex_bar);
+                    const unsigned bar = smem_u32(&ex_bar[par]);
                     const unsigned sides_in = (ext_left ? 0u : 1u) + (ext_right ? 0u : 1u);
                     if (tid == 0) mbar_arrive_expect_tx(bar, sides_in * (unsigned)(HW * XT * 2 * BW * sizeof(double)));
                     const unsigned aA = smem_u32(eA), aB = smem_u32(eB);
@@ -1282,49 +1285,33 @@ chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __gri
                 }
             }
             __syncthreads();
-            if (C > 1) mbar_wait_or_trap(smem_u32(&ex_bar), (unsigned)it & 1u);
+            if (C > 1) mbar_wait_or_trap(smem_u32(&ex_bar[par]), (unsigned)(it >> 1) & 1u);
             // separator solve from local shared memory: s_p = sum_d G[d] (gA_{p+d} + gB_{p+d+1})
-            double s0 = 0.0, s1 = 0.0, t0_ = 0.0, t1_ = 0.0;
+            // s of my chunk and of the chunk before it (whose separator values close my left side), both from the same window
+            // of 2W + 2 reduced right-hand sides: nothing is exchanged a second time and no barrier sits between the two
+            double s0 = 0.0, s1 = 0.0, sp0 = 0.0, sp1 = 0.0;
             {
-                int e = (HW + pl - W) * XT + xi;
+                int e = (HW + pl - 1 - W) * XT + xi;
+                double hp0 = eA[e] + eB[e + XT], hp1 = 0.0;
+                if (BW == 2) hp1 = eA[ESL + e] + eB[ESL + e + XT];
                 for (int d = 0; d <= 2 * W; ++d) {
+                    e += XT;
+                    const double h0 = eA[e] + eB[e + XT];
                     if (BW == 2) {
-                        const double h0 = eA[e] + eB[e + XT];
                         const double h1 = eA[ESL + e] + eB[ESL + e + XT];
+                        sp0 += tab.G[d][0] * hp0 + tab.G[d][1] * hp1;
+                        sp1 += tab.G[d][2] * hp0 + tab.G[d][3] * hp1;
                         s0 += tab.G[d][0] * h0 + tab.G[d][1] * h1;
                         s1 += tab.G[d][2] * h0 + tab.G[d][3] * h1;
+                        hp1 = h1;
                     } else {
-                        s0 += tab.G[d][0] * (eA[e] + eB[e + XT]);
+                        sp0 += tab.G[d][0] * hp0;
+                        s0 += tab.G[d][0] * h0;
                     }
-                    e += XT;
+                    hp0 = h0;
                 }
             }
-            if (pl == 0) {  // previous chunk lives in another CTA: recompute its separator values from the halo
-                int e = (HW - 1 - W) * XT + xi;
-                for (int d = 0; d <= 2 * W; ++d) {
-                    if (BW == 2) {
-                        const double h0 = eA[e] + eB[e + XT];
-                        const double h1 = eA[ESL + e] + eB[ESL + e + XT];
-                        t0_ += tab.G[d][0] * h0 + tab.G[d][1] * h1;
-                        t1_ += tab.G[d][2] * h0 + tab.G[d][3] * h1;
-                    } else {
-                        t0_ += tab.G[d][0] * (eA[e] + eB[e + XT]);
-                    }
-                    e += XT;
-                }
-            }
-            sS[pl * XT + xi] = s0;
-            if (BW == 2) sS[PC * XT + pl * XT + xi] = s1;
-            __syncthreads();
-            double sp0, sp1 = 0.0;
-            if (pl == 0) { sp0 = t0_; sp1 = t1_; }
-            else { sp0 = sS[(pl - 1) * XT + xi]; if (BW == 2) sp1 = sS[PC * XT + (pl - 1) * XT + xi]; }
             chunk_finish<BW, M>(r, tab, s0, s1, sp0, sp1);
-            // My reads of the extended arrays are done (their values have been consumed above): neighbours may push the
-            // next tile's values once every CTA has said so.  Nothing is published through this barrier, it only orders
-            // my completed shared-memory reads before the peers' later pushes, so the arrive is .relaxed: a .release
-            // arrive costs a MEMBAR.ALL.GPU + ERRBAR per tile (28 % of all stall samples in the first ncu capture).
-            if (C > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n" ::: "memory");
         } else {
             __syncthreads();  // everyone has read the tile (neighbours' halo rows overlap my rows)
         }
@@ -1340,16 +1327,15 @@ chunk_strided_ctma_kernel(const __grid_constant__ CUtensorMap tm_in, const __gri
             const int x0 = (int)(tile - (long long)k * tiles_x) * XT;
             tma_store_3d(&tm_out, x0, r0, k, smem_u32(buf + (size_t)HB * XT));
             bulk_commit();
-            bulk_wait_read<1>();
+            // the buffer tile it+2 lands in was drained by the store committed one iteration ago (three buffers) or just now (two)
+            if (nbuf == 3) bulk_wait_read<1>(); else bulk_wait_read<0>();
             const long long nxt = tile + 2 * ncl;
-            if (nxt < ntiles) issue_load(nxt, (it + 2) % kXtBuf);
+            if (nxt < ntiles) issue_load(nxt, (it + 2) % nbuf);
         }
     }
     if (tid == 0) bulk_wait_read<0>();
-    if constexpr (BW > 0) {
-        // pair the last arrive; also keeps every CTA resident until no peer can still push into it
-        if (C > 1 && it > 0) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-    }
+    // Exit is safe without a barrier: nobody reads a peer's shared memory, and every push aimed at this CTA was awaited by
+    // its last wait on ex_bar.
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1714,18 +1700,21 @@ zslab_edge_kernel(const double* __restrict__ f, long long n1, int n_local, const
 // Chunks per CTA of the cluster + TMA kernel for P chunks per line and XT-column tiles: the largest power of two
 // <= pc_max that divides P into a cluster of at most 8 CTAs, keeps a CTA between 64 and 512 threads and 256 rows (one
 // tensor-map box), holds the halo reach HW, and fits three tile buffers in shared memory.  0: no such configuration.
-inline int ctma_chunks_per_cta(int P, int M, int XT, int HB, int HW, int BWc, bool banded, int pc_max, size_t* smem_out) {
+inline int ctma_chunks_per_cta(int P, int M, int XT, int HB, int HW, int BWc, bool banded, int pc_max, size_t* smem_out,
+                               int* nbuf_out = nullptr) {
     constexpr size_t cap = 227 * 1024 - 256;
     for (int pc = pc_max; pc >= 1; pc >>= 1) {
         if (P % pc != 0) continue;
         const int c = P / pc;
         if (c < 1 || c > 8) continue;
         if (XT * pc > 512 || XT * pc < 64 || pc * M > 256 || (banded && HW > pc)) continue;
-        const size_t need = sizeof(double) * ((size_t)kXtBuf * (pc * M + 2 * HB) * XT + 2 * BWc * (size_t)(pc + 2 * HW) * XT +
-                                              BWc * (size_t)pc * XT);
-        if (need > cap) continue;
-        if (smem_out) *smem_out = need;
-        return pc;
+        for (int nbuf = kXtBuf; nbuf >= 2; --nbuf) {   // three rotating tile buffers; two when the ping-pong exchange arrays are large
+            const size_t need = sizeof(double) * ((size_t)nbuf * (pc * M + 2 * HB) * XT + 4 * BWc * (size_t)(pc + 2 * HW) * XT);
+            if (need > cap) continue;
+            if (smem_out) *smem_out = need;
+            if (nbuf_out) *nbuf_out = nbuf;
+            return pc;
+        }
     }
     return 0;
 }
@@ -1744,7 +1733,8 @@ cudaError_t launch_ctma(const BandedOp* h, const double* f, double* out, long lo
     if (((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return cudaErrorInvalidConfiguration;
     constexpr size_t cap = 227 * 1024 - 256;
     size_t smem = 0;
-    const int PC = ctma_chunks_per_cta(P, M, XT, HB, HW, BWc, BW > 0, pc_max, &smem);
+    int nbuf = kXtBuf;
+    const int PC = ctma_chunks_per_cta(P, M, XT, HB, HW, BWc, BW > 0, pc_max, &smem, &nbuf);
     if (PC == 0) return cudaErrorInvalidConfiguration;
     const int C = P / PC;
     CUtensorMap tm_in, tm_halo, tm_out;
@@ -1789,7 +1779,7 @@ cudaError_t launch_ctma(const BandedOp* h, const double* f, double* out, long lo
     const long long ncl = ntiles < mc ? ntiles : mc;
     cfg.gridDim = dim3((unsigned)(ncl * C));
     g_last_variant = pc_max < 16 ? kCTma32s : (XT == 64 ? kCTma64 : kCTma32);
-    return cudaLaunchKernelEx(&cfg, kern, tm_in, tm_halo, tm_out, n, XT, C, PC, tiles_x, ntiles, h->tab, h->op, zs);
+    return cudaLaunchKernelEx(&cfg, kern, tm_in, tm_halo, tm_out, n, XT, C, PC, tiles_x, ntiles, h->tab, h->op, zs, nbuf);
 }
 
 template <int RK, int BW, int M>
@@ -2063,10 +2053,10 @@ cudaError_t zslab_edges_t(const BandedOp* h, const double* f, long long n1, int 
 template <int RK, int BW>
 cudaError_t zslab_apply_t(const BandedOp* h, const double* f, double* out, long long n1, const ZSlabHost& z, cudaStream_t st) {
     const long long slab = n1 * z.n_local;
-    cudaError_t e = launch_ctma<RK, BW, 32>(h, f, out, n1, 1, slab, slab, st, 32, 4, &z);   // two CTAs per SM
+    cudaError_t e = launch_ctma<RK, BW, 32>(h, f, out, n1, 1, slab, slab, st, 32, 16, &z);  // 8 chunks x 32 columns per CTA
     if (e == cudaErrorInvalidConfiguration) {
         cudaGetLastError();
-        e = launch_ctma<RK, BW, 32>(h, f, out, n1, 1, slab, slab, st, 32, 16, &z);
+        e = launch_ctma<RK, BW, 32>(h, f, out, n1, 1, slab, slab, st, 32, 4, &z);
     }
     return e;
 }

@@ -524,7 +524,9 @@ int pdo_lstsq_init(pdo_lstsq_t* h, int n, int periodic) {
         return 0;
     }
     OpParams p{};
-    p.co[0] = 0.5; p.co[1] = 0.6744132 / 2.0; p.co[2] = 0.0 / 2.0; p.co[3] = -0.1744132 / 2.0; p.co[4] = 0.0 / 2.0;   // lstsq.F90:14-19
+    // lstsq.F90:14-19 writes real(0.6744132, rkind): a default-real (single precision) literal widened to double, i.e.
+    // 0.67441320419311523 and -0.17441320419311523, not the decimal values
+    p.co[0] = 0.5; p.co[1] = (double)0.6744132f / 2.0; p.co[2] = 0.0 / 2.0; p.co[3] = (double)(-0.1744132f) / 2.0; p.co[4] = 0.0 / 2.0;
     cudaError_t e = banded_op_create(&o->op, n, RK_SYM_9, 0, 0.0, 0.0, p);
     if (e != cudaSuccess) { delete o; return fail(PDO_E_CUDA, "lstsq init: %s", cudaGetErrorString(e)); }
     *h = o;

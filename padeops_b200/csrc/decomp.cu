@@ -288,10 +288,132 @@ __global__ void box_wait_kernel(const __grid_constant__ PushBatch b) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// TMA bulk push ("bulk" data plane of the fused transposes).  A persistent CTA streams 32 KB pieces of its source boxes
+// through a ring of shared-memory stages: cp.async.bulk global -> shared (one elected thread, transaction mbarrier per
+// stage), then cp.async.bulk shared -> the OWNER's dst in peer memory over NVLink.  Every piece is a run that is contiguous
+// on both sides (2DECOMP's blocks are contiguous for whole x-rows, for whole (x, y) planes on the y<->z pair), so the
+// fabric sees long bursts instead of per-thread 16-byte stores, and no thread touches the data.  Work items interleave the
+// destination ranks (item i -> peer order[i % np]) so that all links carry traffic all the time.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBulkStages = 6;
+constexpr int kBulkAhead = 4;                 // loads in flight per CTA; kBulkStages - kBulkAhead stores may still be reading
+constexpr unsigned kBulkChunk = 32768;        // bytes per stage
+
+struct BulkBox {
+    const char* src; char* dst;               // absolute byte addresses of the box origin on each side
+    long long s_ld2, s_ld3, d_ld2, d_ld3;     // byte strides of the piece indices (inner, outer)
+    long long piece_bytes;                    // contiguous run on both sides
+    int n_inner, n_outer;                     // pieces = n_inner x n_outer
+    int cpp;                                  // chunks per piece
+    long long nchunks;                        // n_inner * n_outer * cpp
+};
+struct BulkBatch {
+    int count;
+    BulkBox c[kMaxPeers];
+    long long max_chunks;
+    int npeers;
+    unsigned long long* peer_flags[kMaxPeers];
+    int peer_rank[kMaxPeers];
+    unsigned long long* my_flags;
+    unsigned int* counter;
+    unsigned long long epoch;
+    int me, nproc;
+};
+
+__device__ __forceinline__ unsigned d_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(128) bulk_push_kernel(const __grid_constant__ BulkBatch b) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) unsigned long long full_bar[kBulkStages];
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid < b.npeers) flag_store(b.peer_flags[tid] + b.me, b.epoch);
+    if (tid < b.npeers) {
+        const unsigned long long* f = b.my_flags + b.peer_rank[tid];
+        while (flag_load(f) < b.epoch) { }
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kBulkStages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(d_smem_u32(&full_bar[s])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const long long total = b.max_chunks * b.count;     // item -> (box = item % count, chunk = item / count)
+        auto locate = [&](long long item, const char*& src, char*& dst, unsigned& bytes) -> bool {
+            const BulkBox& c = b.c[(int)(item % b.count)];
+            const long long ch = item / b.count;
+            if (ch >= c.nchunks) return false;
+            const long long piece = ch / c.cpp;
+            const long long sub = ch - piece * c.cpp;
+            const long long po = piece / c.n_inner, pi = piece - po * c.n_inner;
+            const long long off = sub * (long long)kBulkChunk;
+            const long long left = c.piece_bytes - off;
+            bytes = (unsigned)(left < (long long)kBulkChunk ? left : (long long)kBulkChunk);
+            src = c.src + pi * c.s_ld2 + po * c.s_ld3 + off;
+            dst = c.dst + pi * c.d_ld2 + po * c.d_ld3 + off;
+            return true;
+        };
+        // my items: blockIdx.x, blockIdx.x + gridDim.x, ...; slot numbers count the items that exist
+        long long li = blockIdx.x, si = blockIdx.x;       // next item to load / to store
+        long long nl = 0, ns = 0;                          // slots loaded / stored so far
+        auto next_valid = [&](long long& it, const char*& s_, char*& d_, unsigned& n_) -> bool {
+            while (it < total) {
+                if (locate(it, s_, d_, n_)) return true;
+                it += gridDim.x;
+            }
+            return false;
+        };
+        const char* ls; char* ld; unsigned ln;
+        const char* ss; char* sd; unsigned sn;
+        bool more_l = next_valid(li, ls, ld, ln);
+        bool more_s = next_valid(si, ss, sd, sn);
+        while (more_s) {
+            // keep kBulkAhead loads in flight
+            while (more_l && nl < ns + kBulkAhead) {
+                const int st = (int)(nl % kBulkStages);
+                // the store that last used this stage (slot nl - kBulkStages) must have read its shared source: every store
+                // commits its own group and at least kBulkStages - kBulkAhead groups are newer than that one
+                if (nl >= kBulkStages) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kBulkStages - kBulkAhead) : "memory");
+                const unsigned bar = d_smem_u32(&full_bar[st]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(ln) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(d_smem_u32(ring + (size_t)st * kBulkChunk)), "l"(ls), "r"(ln), "r"(bar) : "memory");
+                ++nl;
+                li += gridDim.x;
+                more_l = next_valid(li, ls, ld, ln);
+            }
+            const int st = (int)(ns % kBulkStages);
+            const unsigned bar = d_smem_u32(&full_bar[st]);
+            const unsigned parity = (unsigned)((ns / kBulkStages) & 1);
+            unsigned ok = 0;
+            for (unsigned spin = 0; !ok; ++spin) {
+                asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}"
+                             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                if (spin > (1u << 26)) __trap();
+            }
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(sd), "r"(d_smem_u32(ring + (size_t)st * kBulkChunk)), "r"(sn) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            ++ns;
+            si += gridDim.x;
+            more_s = next_valid(si, ss, sd, sn);
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every write of this CTA has been performed
+        __threadfence_system();
+        if (atomicAdd(b.counter, 1u) == gridDim.x - 1) {
+            *b.counter = 0;
+            __threadfence_system();
+            for (int t = 0; t < b.npeers; ++t) flag_store(b.peer_flags[t] + b.nproc + b.me, b.epoch);
+        }
+    }
+}
+
 }  // namespace
 
 struct pdo_decomp_s {
     int nx, ny, nz, p_row, p_col, c1, c2;
+    int world_rank = 0;
     unsigned int* push_counter = nullptr;
     cudaStream_t ce_stream[kMaxPeers] = {};   // copy-engine variant of the fused path: one stream per peer
     cudaEvent_t ce_fork = nullptr, ce_join[kMaxPeers] = {};
@@ -319,197 +441,301 @@ int ensure_work(pdo_decomp_s* d, size_t doubles) {
 
 inline long long vol3(const int* s) { return (long long)s[0] * s[1] * s[2]; }
 
-// dir: 0 x→y, 1 y→x, 2 y→z, 3 z→y.  Device pointers.  w = doubles per element.
-int transpose_device(pdo_decomp_s* d, int dir, const double* src, double* dst, int w, cudaStream_t st) {
-    const bool col = (dir == 0 || dir == 1);
-    const int np = col ? d->p_row : d->p_col;
-    const int me = col ? d->c1 : d->c2;
-    const int* ssz = (dir == 0) ? d->info.xsz : (dir == 3) ? d->info.zsz : d->info.ysz;
-    const int* dsz = (dir == 1) ? d->info.xsz : (dir == 2) ? d->info.zsz : d->info.ysz;
-    const long long s1 = (long long)ssz[0] * w, s2 = ssz[1], s3 = ssz[2];
-    const long long d1 = (long long)dsz[0] * w, d2 = dsz[1], d3 = dsz[2];
-    if (np == 1) {  // same layout on both sides
-        PDO_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * s1 * s2 * s3, cudaMemcpyDeviceToDevice, st));
-        return 0;
-    }
-    if (np > kMaxPeers) return fail(PDO_E_UNSUPPORTED, "more than %d ranks in one sub-communicator", kMaxPeers);
-    const std::vector<int>& sdist = (dir == 0) ? d->x1dist : (dir == 3) ? d->z2dist : (dir == 1) ? d->y1dist : d->y2dist;
-    const std::vector<int>& rdist = (dir == 0) ? d->y1dist : (dir == 3) ? d->y2dist : (dir == 1) ? d->x1dist : d->z2dist;
-    // send block to peer m = a range of SRC index (1 for x→y, 2 for y→x / y→z, 3 for z→y);
-    // recv block from peer m = a range of DST index (2 for x→y / z→y, 1 for y→x, 3 for y→z).
-    std::vector<long long> scnt(np), sdisp(np), rcnt(np), rdisp(np), sst(np), rst(np);
-    long long sacc = 0, racc = 0, sa = 0, ra = 0;
-    for (int m = 0; m < np; ++m) {
-        sst[m] = sa; rst[m] = ra;
-        scnt[m] = (dir == 0) ? (long long)sdist[m] * w * s2 * s3 : (dir == 3) ? s1 * s2 * sdist[m] : s1 * sdist[m] * s3;
-        rcnt[m] = (dir == 1) ? (long long)rdist[m] * w * d2 * d3 : (dir == 2) ? d1 * d2 * rdist[m] : d1 * rdist[m] * d3;
-        sdisp[m] = sacc; rdisp[m] = racc;
-        sacc += scnt[m]; racc += rcnt[m];
-        sa += sdist[m]; ra += rdist[m];
-    }
-    // Fused path: dst is a registered (IPC-shared) buffer on every rank of the group -> each rank stores its blocks
-    // straight into their final place in the owners' dst over NVLink.  No pack buffer, no unpack pass, no NCCL.
-    if (g_comm.p2p) {
-        if (const SymBuf* sb = sym_find(dst, sizeof(double) * (size_t)(d1 * d2 * d3))) {
-            if (!d->push_counter) {
-                PDO_CUDA(cudaMalloc(&d->push_counter, sizeof(unsigned int)));
-                PDO_CUDA(cudaMemset(d->push_counter, 0, sizeof(unsigned int)));
-            }
-            PushBatch b;
-            std::memset(&b, 0, sizeof(b));
-            b.count = np; b.npeers = 0; b.me = g_comm.rank; b.nproc = g_comm.nproc;
-            b.my_flags = g_comm.flags; b.counter = d->push_counter; b.epoch = ++g_comm.epoch;
-            const size_t off = (const char*)dst - sb->base;
-            bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
-            long long max_rows = 0;
-            int min_b1 = 1 << 30;
-            for (int m = 0; m < np; ++m) {
-                const int pw = col ? (m * d->p_col + d->c2) : (d->c1 * d->p_col + m);
-                BoxCopy& c = b.c[m];
-                c.s_ld2 = s1; c.s_ld3 = s1 * s2;
-                if (dir == 0) { c.src_off = sst[m] * w; c.b1 = sdist[m] * w; c.b2 = (int)s2; c.b3 = (int)s3; }
-                else if (dir == 3) { c.src_off = sst[m] * s1 * s2; c.b1 = (int)s1; c.b2 = (int)s2; c.b3 = sdist[m]; }
-                else { c.src_off = sst[m] * s1; c.b1 = (int)s1; c.b2 = sdist[m]; c.b3 = (int)s3; }
-                // where my block lands in rank m's dst (m's pencil extents differ from mine along the split index)
-                if (dir == 0) { c.d_ld2 = (long long)sdist[m] * w; c.d_ld3 = c.d_ld2 * d->ny; c.dst_off = rst[me] * c.d_ld2; }
-                else if (dir == 1) { c.d_ld2 = (long long)d->nx * w; c.d_ld3 = c.d_ld2 * sdist[m]; c.dst_off = rst[me] * w; }
-                else if (dir == 2) { c.d_ld2 = s1; c.d_ld3 = s1 * sdist[m]; c.dst_off = rst[me] * c.d_ld3; }
-                else { c.d_ld2 = s1; c.d_ld3 = s1 * d->ny; c.dst_off = rst[me] * s1; }
-                b.dst[m] = (double*)(sb->peer[pw] + off);
-                if ((c.b1 | c.src_off | c.dst_off | c.s_ld2 | c.s_ld3 | c.d_ld2 | c.d_ld3) & 1) vec = false;
-                if (reinterpret_cast<uintptr_t>(b.dst[m]) & 15) vec = false;
-                const long long rows = (long long)c.b2 * c.b3;
-                if (rows > max_rows) max_rows = rows;
-                if (c.b1 < min_b1) min_b1 = c.b1;
-                if (m != me) {
-                    b.peer_flags[b.npeers] = g_comm.peer_flags[pw];
-                    b.peer_rank[b.npeers] = pw;
-                    b.npeers++;
-                }
-            }
-            static int p2p_mode = -1;  // PDO_P2P_MODE = sm (store kernel) | ce (copy engines, SMs stay free); default ce for large blocks
-            if (p2p_mode < 0) {
-                const char* e = std::getenv("PDO_P2P_MODE");
-                p2p_mode = (e && std::strcmp(e, "sm") == 0) ? 1 : ((e && std::strcmp(e, "ce") == 0) ? 2 : 0);
-            }
-            const long long box_bytes = (long long)b.c[me == 0 ? np - 1 : 0].b1 * b.c[me == 0 ? np - 1 : 0].b2 * b.c[me == 0 ? np - 1 : 0].b3 * 8;
-            const bool use_ce = (p2p_mode == 2) || (p2p_mode == 0 && box_bytes >= (4LL << 20));
-            if (use_ce) {
-                if (!d->ce_ready) {
-                    for (int m = 0; m < kMaxPeers; ++m) {
-                        PDO_CUDA(cudaStreamCreateWithFlags(&d->ce_stream[m], cudaStreamNonBlocking));
-                        PDO_CUDA(cudaEventCreateWithFlags(&d->ce_join[m], cudaEventDisableTiming));
-                    }
-                    PDO_CUDA(cudaEventCreateWithFlags(&d->ce_fork, cudaEventDisableTiming));
-                    d->ce_ready = true;
-                }
-                box_entry_kernel<<<1, 32, 0, st>>>(b);
-                PDO_CUDA(cudaGetLastError());
-                PDO_CUDA(cudaEventRecord(d->ce_fork, st));
-                for (int q = 0; q < np; ++q) {
-                    const int m = (me + 1 + q) % np;  // start with my right neighbour: spreads the ingress over the destinations
-                    const BoxCopy& c = b.c[m];
-                    if (c.b1 <= 0 || c.b2 <= 0 || c.b3 <= 0) continue;
-                    cudaStream_t cs = d->ce_stream[m];
-                    PDO_CUDA(cudaStreamWaitEvent(cs, d->ce_fork, 0));
-                    const double* sp = src + c.src_off;
-                    double* dp = b.dst[m] + c.dst_off;
-                    if (c.b1 == c.s_ld2 && c.b1 == c.d_ld2) {  // rows are contiguous on both sides: (i, j) collapse into wide rows
-                        PDO_CUDA(cudaMemcpy2DAsync(dp, (size_t)c.d_ld3 * 8, sp, (size_t)c.s_ld3 * 8, (size_t)c.b1 * c.b2 * 8, (size_t)c.b3,
-                                                   cudaMemcpyDeviceToDevice, cs));
-                    } else {
-                        cudaMemcpy3DParms pr;
-                        std::memset(&pr, 0, sizeof(pr));
-                        pr.srcPtr = make_cudaPitchedPtr((void*)sp, (size_t)c.s_ld2 * 8, (size_t)c.s_ld2, (size_t)(c.s_ld3 / c.s_ld2));
-                        pr.dstPtr = make_cudaPitchedPtr((void*)dp, (size_t)c.d_ld2 * 8, (size_t)c.d_ld2, (size_t)(c.d_ld3 / c.d_ld2));
-                        pr.extent = make_cudaExtent((size_t)c.b1 * 8, (size_t)c.b2, (size_t)c.b3);
-                        pr.kind = cudaMemcpyDeviceToDevice;
-                        PDO_CUDA(cudaMemcpy3DAsync(&pr, cs));
-                    }
-                    PDO_CUDA(cudaEventRecord(d->ce_join[m], cs));
-                    PDO_CUDA(cudaStreamWaitEvent(st, d->ce_join[m], 0));
-                }
-                box_exit_kernel<<<1, 32, 0, st>>>(b);
-                PDO_CUDA(cudaGetLastError());
-                g_launches += 2;
-                return 0;
-            }
-            const int tx = (min_b1 / (vec ? 2 : 1)) >= 128 ? 128 : ((min_b1 / (vec ? 2 : 1)) >= 64 ? 64 : 32);
-            dim3 block(tx, 256 / tx);
-            long long gx = (max_rows + block.y - 1) / block.y;
-            const long long cap = (148LL * 8 + np - 1) / np;
-            if (gx > cap) gx = cap;
-            if (gx < 1) gx = 1;
-            dim3 grid((unsigned)gx, (unsigned)np);
-            if (vec) box_push_kernel<double2><<<grid, block, 0, st>>>(src, b);
-            else box_push_kernel<double><<<grid, block, 0, st>>>(src, b);
-            PDO_CUDA(cudaGetLastError());
-            box_wait_kernel<<<1, 32, 0, st>>>(b);
-            PDO_CUDA(cudaGetLastError());
-            g_launches += 2;
-            return 0;
+pdo_decomp_s* decomp_new(int nx, int ny, int nz, int p_row, int p_col, int rank) {
+    pdo_decomp_s* d = new (std::nothrow) pdo_decomp_s();
+    if (!d) return nullptr;
+    d->nx = nx; d->ny = ny; d->nz = nz; d->p_row = p_row; d->p_col = p_col;
+    d->world_rank = rank;
+    d->c1 = rank / p_col; d->c2 = rank % p_col;
+    fill_info(nx, ny, nz, p_row, p_col, rank, &d->info);
+    for (int i = 0; i < p_row; ++i) { d->x1dist.push_back(dist_size(nx, p_row, i)); d->y1dist.push_back(dist_size(ny, p_row, i)); }
+    for (int i = 0; i < p_col; ++i) { d->y2dist.push_back(dist_size(ny, p_col, i)); d->z2dist.push_back(dist_size(nz, p_col, i)); }
+    return d;
+}
+
+// Geometry of one transpose as seen from one rank: 2DECOMP's counts / displacements (prepare_buffer, 2D» decomp_2d.f90:739-794)
+// and the boxes of the pack (mem_split_*) and unpack (mem_merge_*) loops (2D» transpose_x_to_y.f90:332-513 and siblings).
+// dir: 0 x→y, 1 y→x, 2 y→z, 3 z→y.  w = doubles per element.  Pure host arithmetic: the same object drives the real exchange
+// and the single-GPU emulation of a p_row x p_col grid.
+struct XGeom {
+    const pdo_decomp_s* d;
+    int dir, w, np, me;
+    bool col;
+    long long s1, s2, s3, d1, d2, d3;
+    std::vector<int> sdist, rdist;
+    std::vector<long long> scnt, sdisp, rcnt, rdisp, sst, rst;
+    long long stot = 0, rtot = 0;
+    XGeom(const pdo_decomp_s* dd, int dir_, int w_) : d(dd), dir(dir_), w(w_) {
+        col = (dir == 0 || dir == 1);
+        np = col ? d->p_row : d->p_col;
+        me = col ? d->c1 : d->c2;
+        const int* ssz = (dir == 0) ? d->info.xsz : (dir == 3) ? d->info.zsz : d->info.ysz;
+        const int* dsz = (dir == 1) ? d->info.xsz : (dir == 2) ? d->info.zsz : d->info.ysz;
+        s1 = (long long)ssz[0] * w; s2 = ssz[1]; s3 = ssz[2];
+        d1 = (long long)dsz[0] * w; d2 = dsz[1]; d3 = dsz[2];
+        sdist = (dir == 0) ? d->x1dist : (dir == 3) ? d->z2dist : (dir == 1) ? d->y1dist : d->y2dist;
+        rdist = (dir == 0) ? d->y1dist : (dir == 3) ? d->y2dist : (dir == 1) ? d->x1dist : d->z2dist;
+        // send block to peer m = a range of SRC index (1 for x→y, 2 for y→x / y→z, 3 for z→y);
+        // recv block from peer m = a range of DST index (2 for x→y / z→y, 1 for y→x, 3 for y→z).
+        scnt.resize(np); sdisp.resize(np); rcnt.resize(np); rdisp.resize(np); sst.resize(np); rst.resize(np);
+        long long sa = 0, ra = 0;
+        for (int m = 0; m < np; ++m) {
+            sst[m] = sa; rst[m] = ra;
+            scnt[m] = (dir == 0) ? (long long)sdist[m] * w * s2 * s3 : (dir == 3) ? s1 * s2 * sdist[m] : s1 * sdist[m] * s3;
+            rcnt[m] = (dir == 1) ? (long long)rdist[m] * w * d2 * d3 : (dir == 2) ? d1 * d2 * rdist[m] : d1 * rdist[m] * d3;
+            sdisp[m] = stot; rdisp[m] = rtot;
+            stot += scnt[m]; rtot += rcnt[m];
+            sa += sdist[m]; ra += rdist[m];
         }
     }
-    const bool need_pack = (dir != 3), need_unpack = (dir != 2);
-    if (int rc = ensure_work(d, (size_t)((sacc > racc ? sacc : racc) + 2))) return rc;
-
-    auto src_box = [&](int m, BoxCopy& c) {  // where peer m's block lives in src
+    int world_rank(int m) const { return col ? (m * d->p_col + d->c2) : (d->c1 * d->p_col + m); }
+    void src_box(int m, BoxCopy& c) const {  // where peer m's block lives in src
         c.s_ld2 = s1; c.s_ld3 = s1 * s2;
         if (dir == 0) { c.src_off = sst[m] * w; c.b1 = sdist[m] * w; c.b2 = (int)s2; c.b3 = (int)s3; }
         else if (dir == 3) { c.src_off = sst[m] * s1 * s2; c.b1 = (int)s1; c.b2 = (int)s2; c.b3 = sdist[m]; }
         else { c.src_off = sst[m] * s1; c.b1 = (int)s1; c.b2 = sdist[m]; c.b3 = (int)s3; }
-    };
-    auto dst_box = [&](int m, BoxCopy& c) {  // where the block from peer m lands in dst
+    }
+    void dst_box(int m, BoxCopy& c) const {  // where the block from peer m lands in my dst
         c.d_ld2 = d1; c.d_ld3 = d1 * d2;
         if (dir == 1) { c.dst_off = rst[m] * w; c.b1 = rdist[m] * w; c.b2 = (int)d2; c.b3 = (int)d3; }
         else if (dir == 2) { c.dst_off = rst[m] * d1 * d2; c.b1 = (int)d1; c.b2 = (int)d2; c.b3 = rdist[m]; }
         else { c.dst_off = rst[m] * d1; c.b1 = (int)d1; c.b2 = rdist[m]; c.b3 = (int)d3; }
-    };
-    // 1) my own block: src box → dst box directly
+    }
+    void push_box(int m, BoxCopy& c) const {  // my block for peer m and where it lands in RANK m's dst (its extents differ from mine)
+        src_box(m, c);
+        if (dir == 0) { c.d_ld2 = (long long)sdist[m] * w; c.d_ld3 = c.d_ld2 * d->ny; c.dst_off = rst[me] * c.d_ld2; }
+        else if (dir == 1) { c.d_ld2 = (long long)d->nx * w; c.d_ld3 = c.d_ld2 * sdist[m]; c.dst_off = rst[me] * w; }
+        else if (dir == 2) { c.d_ld2 = s1; c.d_ld3 = s1 * sdist[m]; c.dst_off = rst[me] * c.d_ld3; }
+        else { c.d_ld2 = s1; c.d_ld3 = s1 * d->ny; c.dst_off = rst[me] * s1; }
+    }
+};
+
+// Who the peers are for one call: the real thing (CUDA-IPC mappings + epoch flags) or, in the single-GPU emulation, the
+// other simulated ranks' buffers on this device with the handshakes switched off (the emulation orders ranks by stream).
+struct PeerView {
+    double* const* dst_of_world;          // dst base of every world rank (byte offset already applied)
+    bool handshake;
+};
+
+enum { kPlaneAuto = 0, kPlaneSm = 1, kPlaneCe = 2, kPlaneBulk = 3 };
+
+int plane_from_env() {
+    static int mode = -1;  // PDO_P2P_MODE = sm (store kernel) | ce (copy engines) | bulk (TMA bulk push); default: bulk when aligned
+    if (mode < 0) {
+        const char* e = std::getenv("PDO_P2P_MODE");
+        mode = !e ? kPlaneAuto : !std::strcmp(e, "sm") ? kPlaneSm : !std::strcmp(e, "ce") ? kPlaneCe : !std::strcmp(e, "bulk") ? kPlaneBulk : kPlaneAuto;
+    }
+    return mode;
+}
+
+template <class B>
+void fill_sync(B& b, const XGeom& g, const PeerView& pv, pdo_decomp_s* d, unsigned long long epoch) {
+    b.npeers = 0; b.me = g_comm.rank; b.nproc = g_comm.nproc;
+    b.my_flags = g_comm.flags; b.counter = d->push_counter; b.epoch = epoch;
+    if (!pv.handshake) return;
+    for (int m = 0; m < g.np; ++m) {
+        if (m == g.me) continue;
+        const int pw = g.world_rank(m);
+        b.peer_flags[b.npeers] = g_comm.peer_flags[pw];
+        b.peer_rank[b.npeers] = pw;
+        b.npeers++;
+    }
+}
+
+// Fused path: every rank stores its blocks straight into their final place in the owners' dst.  No pack buffer, no unpack
+// pass, no NCCL.  `plane` picks who moves the bytes.
+int transpose_push(pdo_decomp_s* d, const XGeom& g, const double* src, const PeerView& pv, int plane, cudaStream_t st) {
+    const int np = g.np, me = g.me;
+    if (!d->push_counter) {
+        PDO_CUDA(cudaMalloc(&d->push_counter, sizeof(unsigned int)));
+        PDO_CUDA(cudaMemset(d->push_counter, 0, sizeof(unsigned int)));
+    }
+    PushBatch b;
+    std::memset(&b, 0, sizeof(b));
+    b.count = np;
+    const unsigned long long epoch = pv.handshake ? ++g_comm.epoch : 0ull;
+    fill_sync(b, g, pv, d, epoch);
+    bool vec = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    long long max_rows = 0, max_box_bytes = 0;
+    int min_b1 = 1 << 30;
+    for (int m = 0; m < np; ++m) {
+        BoxCopy& c = b.c[m];
+        g.push_box(m, c);
+        b.dst[m] = pv.dst_of_world[g.world_rank(m)];
+        if ((c.b1 | c.src_off | c.dst_off | c.s_ld2 | c.s_ld3 | c.d_ld2 | c.d_ld3) & 1) vec = false;
+        if (reinterpret_cast<uintptr_t>(b.dst[m]) & 15) vec = false;
+        const long long rows = (long long)c.b2 * c.b3;
+        if (rows > max_rows) max_rows = rows;
+        if (c.b1 < min_b1) min_b1 = c.b1;
+        if (m != me && rows * c.b1 * 8 > max_box_bytes) max_box_bytes = rows * c.b1 * 8;
+    }
+    if (plane == kPlaneAuto) plane = plane_from_env();
+    if (plane == kPlaneAuto) plane = (vec && max_box_bytes >= (1LL << 20)) ? kPlaneBulk : kPlaneSm;
+    if (plane == kPlaneBulk && !vec) plane = kPlaneSm;    // bulk copies need 16-byte aligned runs
+    if (plane == kPlaneBulk) {
+        BulkBatch bb;
+        std::memset(&bb, 0, sizeof(bb));
+        bb.count = np;
+        fill_sync(bb, g, pv, d, epoch);
+        long long all_chunks = 0;
+        for (int q = 0; q < np; ++q) {
+            const int m = (me + 1 + q) % np;               // start with my right neighbour: spreads the ingress over the destinations
+            const BoxCopy& c = b.c[m];
+            BulkBox& x = bb.c[q];
+            x.src = (const char*)(src + c.src_off);
+            x.dst = (char*)(b.dst[m] + c.dst_off);
+            const bool rows_join = (c.b1 == c.s_ld2 && c.b1 == c.d_ld2);             // (i, j) collapse into one run per k
+            const bool planes_join = rows_join && c.s_ld3 == (long long)c.b1 * c.b2 && c.d_ld3 == c.s_ld3;  // the whole box is one run
+            if (planes_join) { x.piece_bytes = 8LL * c.b1 * c.b2 * c.b3; x.n_inner = 1; x.n_outer = 1; x.s_ld2 = x.d_ld2 = x.s_ld3 = x.d_ld3 = 0; }
+            else if (rows_join) { x.piece_bytes = 8LL * c.b1 * c.b2; x.n_inner = 1; x.n_outer = c.b3; x.s_ld2 = x.d_ld2 = 0; x.s_ld3 = 8 * c.s_ld3; x.d_ld3 = 8 * c.d_ld3; }
+            else { x.piece_bytes = 8LL * c.b1; x.n_inner = c.b2; x.n_outer = c.b3; x.s_ld2 = 8 * c.s_ld2; x.d_ld2 = 8 * c.d_ld2; x.s_ld3 = 8 * c.s_ld3; x.d_ld3 = 8 * c.d_ld3; }
+            if (x.piece_bytes <= 0 || c.b2 <= 0 || c.b3 <= 0) { x.piece_bytes = 0; x.nchunks = 0; x.cpp = 1; x.n_inner = x.n_outer = 1; continue; }
+            x.cpp = (int)((x.piece_bytes + kBulkChunk - 1) / kBulkChunk);
+            x.nchunks = (long long)x.n_inner * x.n_outer * x.cpp;
+            if (x.nchunks > bb.max_chunks) bb.max_chunks = x.nchunks;
+            all_chunks += x.nchunks;
+        }
+        static int smem_set = 0;
+        const int smem = kBulkStages * (int)kBulkChunk;
+        if (!smem_set) {
+            PDO_CUDA(cudaFuncSetAttribute(bulk_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            smem_set = 1;
+        }
+        static int bulk_ctas = -1;
+        if (bulk_ctas < 0) { const char* e = std::getenv("PDO_BULK_CTAS"); bulk_ctas = e ? std::atoi(e) : 148; if (bulk_ctas < 1) bulk_ctas = 148; }
+        long long grid = all_chunks < bulk_ctas ? (all_chunks > 0 ? all_chunks : 1) : bulk_ctas;
+        bulk_push_kernel<<<(unsigned)grid, 128, smem, st>>>(bb);
+        PDO_CUDA(cudaGetLastError());
+        if (pv.handshake) { box_wait_kernel<<<1, 32, 0, st>>>(b); PDO_CUDA(cudaGetLastError()); }
+        g_launches += 2;
+        return 0;
+    }
+    if (plane == kPlaneCe) {
+        if (!d->ce_ready) {
+            for (int m = 0; m < kMaxPeers; ++m) {
+                PDO_CUDA(cudaStreamCreateWithFlags(&d->ce_stream[m], cudaStreamNonBlocking));
+                PDO_CUDA(cudaEventCreateWithFlags(&d->ce_join[m], cudaEventDisableTiming));
+            }
+            PDO_CUDA(cudaEventCreateWithFlags(&d->ce_fork, cudaEventDisableTiming));
+            d->ce_ready = true;
+        }
+        if (pv.handshake) { box_entry_kernel<<<1, 32, 0, st>>>(b); PDO_CUDA(cudaGetLastError()); }
+        PDO_CUDA(cudaEventRecord(d->ce_fork, st));
+        for (int q = 0; q < np; ++q) {
+            const int m = (me + 1 + q) % np;
+            const BoxCopy& c = b.c[m];
+            if (c.b1 <= 0 || c.b2 <= 0 || c.b3 <= 0) continue;
+            cudaStream_t cs = d->ce_stream[m];
+            PDO_CUDA(cudaStreamWaitEvent(cs, d->ce_fork, 0));
+            const double* sp = src + c.src_off;
+            double* dp = b.dst[m] + c.dst_off;
+            if (c.b1 == c.s_ld2 && c.b1 == c.d_ld2) {  // rows are contiguous on both sides: (i, j) collapse into wide rows
+                PDO_CUDA(cudaMemcpy2DAsync(dp, (size_t)c.d_ld3 * 8, sp, (size_t)c.s_ld3 * 8, (size_t)c.b1 * c.b2 * 8, (size_t)c.b3,
+                                           cudaMemcpyDeviceToDevice, cs));
+            } else {
+                cudaMemcpy3DParms pr;
+                std::memset(&pr, 0, sizeof(pr));
+                pr.srcPtr = make_cudaPitchedPtr((void*)sp, (size_t)c.s_ld2 * 8, (size_t)c.s_ld2, (size_t)(c.s_ld3 / c.s_ld2));
+                pr.dstPtr = make_cudaPitchedPtr((void*)dp, (size_t)c.d_ld2 * 8, (size_t)c.d_ld2, (size_t)(c.d_ld3 / c.d_ld2));
+                pr.extent = make_cudaExtent((size_t)c.b1 * 8, (size_t)c.b2, (size_t)c.b3);
+                pr.kind = cudaMemcpyDeviceToDevice;
+                PDO_CUDA(cudaMemcpy3DAsync(&pr, cs));
+            }
+            PDO_CUDA(cudaEventRecord(d->ce_join[m], cs));
+            PDO_CUDA(cudaStreamWaitEvent(st, d->ce_join[m], 0));
+        }
+        if (pv.handshake) { box_exit_kernel<<<1, 32, 0, st>>>(b); PDO_CUDA(cudaGetLastError()); }
+        g_launches += 2;
+        return 0;
+    }
+    const int tx = (min_b1 / (vec ? 2 : 1)) >= 128 ? 128 : ((min_b1 / (vec ? 2 : 1)) >= 64 ? 64 : 32);
+    dim3 block(tx, 256 / tx);
+    long long gx = (max_rows + block.y - 1) / block.y;
+    const long long cap = (148LL * 8 + np - 1) / np;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)np);
+    if (vec) box_push_kernel<double2><<<grid, block, 0, st>>>(src, b);
+    else box_push_kernel<double><<<grid, block, 0, st>>>(src, b);
+    PDO_CUDA(cudaGetLastError());
+    if (pv.handshake) { box_wait_kernel<<<1, 32, 0, st>>>(b); PDO_CUDA(cudaGetLastError()); }
+    g_launches += 2;
+    return 0;
+}
+
+// NCCL path, stage 1: my own block goes src box → dst box directly; the other peers' blocks are packed contiguously, in peer
+// order, at the ALLTOALLV displacements (y→z's z-side and z→y's z-side need no pack / unpack: the block is a contiguous k-slab).
+int transpose_pack(pdo_decomp_s* d, const XGeom& g, const double* src, double* dst, cudaStream_t st) {
+    if (int rc = ensure_work(d, (size_t)((g.stot > g.rtot ? g.stot : g.rtot) + 2))) return rc;
     {
         BoxBatch b{};
         b.count = 1;
-        src_box(me, b.c[0]);
+        g.src_box(g.me, b.c[0]);
         const int sb1 = b.c[0].b1, sb2 = b.c[0].b2, sb3 = b.c[0].b3;
-        dst_box(me, b.c[0]);
+        g.dst_box(g.me, b.c[0]);
         if (sb1 != b.c[0].b1 || sb2 != b.c[0].b2 || sb3 != b.c[0].b3) return fail(PDO_E_BADARG, "transpose: self block mismatch");
         if (int rc = launch_box_copy(src, dst, b, st)) return rc;
     }
-    // 2) pack the other peers' blocks (contiguous, in peer order, at the ALLTOALLV displacements)
-    if (need_pack) {
+    if (g.dir != 3) {
         BoxBatch b{};
-        for (int m = 0; m < np; ++m) {
-            if (m == me) continue;
+        for (int m = 0; m < g.np; ++m) {
+            if (m == g.me) continue;
             BoxCopy& c = b.c[b.count++];
-            src_box(m, c);
-            c.dst_off = sdisp[m]; c.d_ld2 = c.b1; c.d_ld3 = (long long)c.b1 * c.b2;
+            g.src_box(m, c);
+            c.dst_off = g.sdisp[m]; c.d_ld2 = c.b1; c.d_ld3 = (long long)c.b1 * c.b2;
         }
         if (int rc = launch_box_copy(src, d->work_send, b, st)) return rc;
     }
-    // 3) the exchange
+    return 0;
+}
+inline const double* xchg_send_ptr(const pdo_decomp_s* d, const XGeom& g, const double* src, int m) {
+    return g.dir != 3 ? d->work_send + g.sdisp[m] : src + g.sst[m] * g.s1 * g.s2;
+}
+inline double* xchg_recv_ptr(const pdo_decomp_s* d, const XGeom& g, double* dst, int m) {
+    return g.dir != 2 ? d->work_recv + g.rdisp[m] : dst + g.rst[m] * g.d1 * g.d2;
+}
+int transpose_unpack(pdo_decomp_s* d, const XGeom& g, double* dst, cudaStream_t st) {
+    if (g.dir == 2) return 0;
+    BoxBatch b{};
+    for (int m = 0; m < g.np; ++m) {
+        if (m == g.me) continue;
+        BoxCopy& c = b.c[b.count++];
+        g.dst_box(m, c);
+        c.src_off = g.rdisp[m]; c.s_ld2 = c.b1; c.s_ld3 = (long long)c.b1 * c.b2;
+    }
+    return launch_box_copy(d->work_recv, dst, b, st);
+}
+
+// dir: 0 x→y, 1 y→x, 2 y→z, 3 z→y.  Device pointers.  w = doubles per element.
+int transpose_device(pdo_decomp_s* d, int dir, const double* src, double* dst, int w, cudaStream_t st) {
+    const XGeom g(d, dir, w);
+    const int np = g.np, me = g.me;
+    if (np == 1) {  // same layout on both sides
+        PDO_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * g.s1 * g.s2 * g.s3, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    if (np > kMaxPeers) return fail(PDO_E_UNSUPPORTED, "more than %d ranks in one sub-communicator", kMaxPeers);
+    // Fused path: dst is a registered (IPC-shared) buffer on every rank of the group
+    if (g_comm.p2p) {
+        if (const SymBuf* sb = sym_find(dst, sizeof(double) * (size_t)(g.d1 * g.d2 * g.d3))) {
+            const size_t off = (const char*)dst - sb->base;
+            std::vector<double*> peers(g_comm.nproc);
+            for (int r = 0; r < g_comm.nproc; ++r) peers[r] = (double*)(sb->peer[r] + off);
+            PeerView pv{peers.data(), true};
+            return transpose_push(d, g, src, pv, kPlaneAuto, st);
+        }
+    }
+    if (int rc = transpose_pack(d, g, src, dst, st)) return rc;
     PDO_NCCL(ncclGroupStart());
     for (int m = 0; m < np; ++m) {
         if (m == me) continue;
-        const int peer = col ? (m * d->p_col + d->c2) : (d->c1 * d->p_col + m);
-        const double* sp = need_pack ? d->work_send + sdisp[m] : src + sst[m] * s1 * s2;
-        double* rp = need_unpack ? d->work_recv + rdisp[m] : dst + rst[m] * d1 * d2;
-        PDO_NCCL(ncclSend(sp, (size_t)scnt[m], ncclDouble, peer, g_comm.comm, st));
-        PDO_NCCL(ncclRecv(rp, (size_t)rcnt[m], ncclDouble, peer, g_comm.comm, st));
+        const int peer = g.world_rank(m);
+        PDO_NCCL(ncclSend(xchg_send_ptr(d, g, src, m), (size_t)g.scnt[m], ncclDouble, peer, g_comm.comm, st));
+        PDO_NCCL(ncclRecv(xchg_recv_ptr(d, g, dst, m), (size_t)g.rcnt[m], ncclDouble, peer, g_comm.comm, st));
     }
     PDO_NCCL(ncclGroupEnd());
     g_launches += 1;
-    // 4) unpack
-    if (need_unpack) {
-        BoxBatch b{};
-        for (int m = 0; m < np; ++m) {
-            if (m == me) continue;
-            BoxCopy& c = b.c[b.count++];
-            dst_box(m, c);
-            c.src_off = rdisp[m]; c.s_ld2 = c.b1; c.s_ld3 = (long long)c.b1 * c.b2;
-        }
-        if (int rc = launch_box_copy(d->work_recv, dst, b, st)) return rc;
-    }
-    return 0;
+    return transpose_unpack(d, g, dst, st);
 }
 
 int transpose_any(pdo_decomp_t h, int dir, const double* src, double* dst, int w, void* stream) {
@@ -543,12 +769,23 @@ static int comm_barrier() {
 int comm_sym_alloc(size_t bytes, void** local, void** peers) {
     *local = nullptr;
     if (!g_comm.inited || g_comm.nproc == 1 || !g_comm.p2p) return -1;
-    for (auto& e : g_sym_pool) {
-        if (e.used || e.bytes < bytes) continue;
+    {   // pencils are uneven: agree on the largest request so that every rank takes the same pool decision
+        unsigned long long mine = bytes, all = 0;
+        unsigned long long* d = (unsigned long long*)g_comm.d_xchg;
+        if (cudaMemcpy(d, &mine, sizeof(mine), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+        if (ncclAllReduce(d, d + 1, 1, ncclUint64, ncclMax, g_comm.comm, 0) != ncclSuccess) return -1;
+        if (cudaMemcpy(&all, d + 1, sizeof(all), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        bytes = (size_t)((all + 255) & ~255ull);
+    }
+    SymPoolEntry* best = nullptr;
+    for (auto& e : g_sym_pool)
+        if (!e.used && e.bytes >= bytes && (!best || e.bytes < best->bytes)) best = &e;
+    if (best) {
+        SymPoolEntry& e = *best;
         if (cudaMemset(e.base, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return -1; }
         if (comm_barrier() != 0) return -1;   // nobody touches a peer's copy before every copy has been cleared
         e.used = true;
-        for (int r = 0; r < g_comm.nproc; ++r) peers[r] = e.peers[r];
+        if (peers) for (int r = 0; r < g_comm.nproc; ++r) peers[r] = e.peers[r];
         *local = e.base;
         return 0;
     }
@@ -561,13 +798,30 @@ int comm_sym_alloc(size_t bytes, void** local, void** peers) {
     SymPoolEntry e;
     e.base = p; e.bytes = bytes; e.used = true;
     e.peers.assign(g_comm.sym[id].peer.begin(), g_comm.sym[id].peer.end());
-    for (int r = 0; r < g_comm.nproc; ++r) peers[r] = e.peers[r];
+    if (peers) for (int r = 0; r < g_comm.nproc; ++r) peers[r] = e.peers[r];
     g_sym_pool.push_back(e);
     *local = p;
     return 0;
 }
 void comm_sym_free(void* p) {
     for (auto& e : g_sym_pool) if (e.base == p) e.used = false;
+}
+// Library-owned buffers that peers write into (transpose destinations of fft_3d, spectral, padepoisson, igrid).  With more than
+// one rank and peer access they come from the symmetric pool, so a create / destroy cycle never cudaFree's memory that is still
+// mapped in a peer process (importers keep their CUDA-IPC mappings until pdo_comm_finalize) and never hands a stale mapping to
+// a later allocation at the same address.  Collective in that case: every rank allocates and frees in the same order (the
+// constructors and destructors that call this are SPMD).  Otherwise plain cudaMalloc / cudaFree.
+int comm_shared_malloc(void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 8;
+    if (g_comm.inited && g_comm.nproc > 1 && g_comm.p2p && comm_sym_alloc(bytes, p, nullptr) == 0) return 0;
+    PDO_CUDA(cudaMalloc(p, bytes));
+    return 0;
+}
+void comm_shared_free(void* p) {
+    if (!p) return;
+    for (auto& e : g_sym_pool) if (e.base == p) { cudaDeviceSynchronize(); e.used = false; return; }
+    cudaFree(p);
 }
 void decomp_grid(pdo_decomp_t h, int* p_row, int* p_col, int* c1, int* c2) {
     *p_row = h->p_row; *p_col = h->p_col; *c1 = h->c1; *c2 = h->c2;
@@ -583,6 +837,48 @@ int comm_allreduce_sum(double* dev, int count, cudaStream_t st) {
     return 0;
 }
 void comm_register_buffer_quiet(void* p, size_t bytes) { if (g_comm.inited && g_comm.nproc > 1 && g_comm.p2p) sym_register(p, bytes); }
+// Single-GPU emulation of a p_row x p_col grid (test hook; tests/test_transpose_emulated_gpu.py): every simulated rank owns a
+// device buffer pair, runs the SAME geometry, pack / unpack kernels and push kernels the multi-GPU path runs, and "peer memory"
+// is simply the other ranks' buffers on this device.  path: 1 SM store kernel, 2 copy-engine copies, 3 TMA bulk push,
+// 4 pack -> exchange -> unpack (cudaMemcpyAsync stands in for the grouped ncclSend / ncclRecv).
+int decomp_transpose_emulate(int nx, int ny, int nz, int p_row, int p_col, int dir, int w, int path, const double* const* src,
+                             double* const* dst, cudaStream_t st) {
+    const int R = p_row * p_col;
+    if (R < 1 || R > 64 || dir < 0 || dir > 3 || (w != 1 && w != 2) || path < 1 || path > 4) return fail(PDO_E_BADARG, "bad argument");
+    if (nx < p_row || ny < p_row || ny < p_col || nz < p_col) return fail(6, "Invalid 2D processor grid");
+    std::vector<pdo_decomp_s*> ds(R, nullptr);
+    int rc = 0;
+    for (int r = 0; r < R && !rc; ++r) if (!(ds[r] = decomp_new(nx, ny, nz, p_row, p_col, r))) rc = fail(PDO_E_BADARG, "out of memory");
+    std::vector<double*> dstv(dst, dst + R);
+    PeerView pv{dstv.data(), false};
+    if (!rc && path != 4) {
+        for (int r = 0; r < R && !rc; ++r) {
+            const XGeom g(ds[r], dir, w);
+            if (g.np > kMaxPeers) { rc = fail(PDO_E_UNSUPPORTED, "too many peers"); break; }
+            rc = transpose_push(ds[r], g, src[r], pv, path, st);
+        }
+    } else if (!rc) {
+        std::vector<XGeom> gs;
+        for (int r = 0; r < R; ++r) gs.emplace_back(ds[r], dir, w);
+        for (int r = 0; r < R && !rc; ++r) rc = transpose_pack(ds[r], gs[r], src[r], dst[r], st);
+        for (int r = 0; r < R && !rc; ++r) {
+            const XGeom& g = gs[r];
+            for (int m = 0; m < g.np && !rc; ++m) {
+                if (m == g.me) continue;
+                const int peer = g.world_rank(m);
+                const XGeom& gp = gs[peer];
+                if (g.scnt[m] != gp.rcnt[g.me]) { rc = fail(PDO_E_BADARG, "count mismatch"); break; }
+                if (cudaMemcpyAsync(xchg_recv_ptr(ds[peer], gp, dst[peer], g.me), xchg_send_ptr(ds[r], g, src[r], m),
+                                    sizeof(double) * (size_t)g.scnt[m], cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+                    rc = fail(PDO_E_CUDA, "emulated exchange failed");
+            }
+        }
+        for (int r = 0; r < R && !rc; ++r) rc = transpose_unpack(ds[r], gs[r], dst[r], st);
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess && !rc) rc = fail(PDO_E_CUDA, "emulated transpose failed: %s", cudaGetErrorString(cudaGetLastError()));
+    for (auto* d : ds) if (d) pdo_decomp_destroy(d);
+    return rc;
+}
 // used by spectral.cu: transposes on device pointers without the host-pointer probe
 int decomp_transpose_device(pdo_decomp_t h, int dir, const double* src, double* dst, int w, cudaStream_t st) {
     return transpose_device(h, dir, src, dst, w, st);
@@ -684,13 +980,8 @@ int pdo_decomp_init(pdo_decomp_t* h, int nx, int ny, int nz, int p_row, int p_co
     if (p_row * p_col != nproc) return fail(1, "Invalid 2D processor grid - nproc /= p_row*p_col");  // 2D» decomp_2d.f90:331-334
     pdo_decomp_info info;
     if (int rc = pdo_decomp_info_for(nx, ny, nz, p_row, p_col, g_comm.rank, &info)) return rc;
-    pdo_decomp_s* d = new (std::nothrow) pdo_decomp_s();
+    pdo_decomp_s* d = decomp_new(nx, ny, nz, p_row, p_col, g_comm.rank);
     if (!d) return fail(PDO_E_BADARG, "out of memory");
-    d->nx = nx; d->ny = ny; d->nz = nz; d->p_row = p_row; d->p_col = p_col;
-    d->c1 = g_comm.rank / p_col; d->c2 = g_comm.rank % p_col;
-    d->info = info;
-    for (int i = 0; i < p_row; ++i) { d->x1dist.push_back(dist_size(nx, p_row, i)); d->y1dist.push_back(dist_size(ny, p_row, i)); }
-    for (int i = 0; i < p_col; ++i) { d->y2dist.push_back(dist_size(ny, p_col, i)); d->z2dist.push_back(dist_size(nz, p_col, i)); }
     *h = d;
     return 0;
 }
@@ -724,6 +1015,10 @@ static int allreduce1(double local, double* global, ncclRedOp_t op) {
     PDO_NCCL(ncclAllReduce(g_comm.d_scalar, g_comm.d_scalar + 1, 1, ncclDouble, op, g_comm.comm, 0));
     PDO_CUDA(cudaMemcpy(global, g_comm.d_scalar + 1, sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
+}
+int pdo_debug_transpose_emulate(int nx, int ny, int nz, int p_row, int p_col, int dir, int w, int path, const double* const* src,
+                                double* const* dst, void* stream) {
+    return pdo::decomp_transpose_emulate(nx, ny, nz, p_row, p_col, dir, w, path, src, dst, (cudaStream_t)stream);
 }
 int pdo_p_maxval(double local, double* global) { return allreduce1(local, global, ncclMax); }
 int pdo_p_sum(double local, double* global) { return allreduce1(local, global, ncclSum); }

@@ -406,23 +406,18 @@ int pdo_padepoisson_init3(pdo_padepoisson_t* h, double dx, double dy, double dz,
             rc = upload(&p->k1z, w1, o1, c1);
             if (!rc) rc = upload(&p->k2z, w2v, o2, c2);
             if (!rc) rc = upload(&p->denfact, den, 0, den.size());
-            if (!rc && cudaMalloc(&p->vhatInZ, sizeof(double2) * (size_t)vol(p->sC.zsz)) != cudaSuccess) rc = fail(PDO_E_CUDA, "padepoisson: vhatInZ");
-            if (!rc) comm_register_buffer_quiet(p->vhatInZ, sizeof(double2) * (size_t)vol(p->sC.zsz));
+            if (!rc) rc = comm_shared_malloc((void**)&p->vhatInZ, sizeof(double2) * (size_t)vol(p->sC.zsz));
         }
     }
     if (!rc) {
         e = cudaMalloc(&p->f2d, sizeof(double2) * (size_t)vol(p->sC.zsz));
-        if (e == cudaSuccess) e = cudaMalloc(&p->uhatInZ, sizeof(double2) * (size_t)vol(p->sC.zsz));
-        if (e == cudaSuccess) e = cudaMalloc(&p->f2dy, sizeof(double2) * (size_t)vol(p->sC.ysz));
-        if (e == cudaSuccess) e = cudaMalloc(&p->w2, sizeof(double2) * (size_t)vol(p->sE.zsz));
         if (e == cudaSuccess) e = cudaMalloc(&p->dwdz, sizeof(double2) * (size_t)vol(p->sE.zsz));
         if (e == cudaSuccess) e = cudaMalloc(&p->div_tmp, sizeof(double) * (size_t)vol(sp->pi.xsz));
         if (e != cudaSuccess) rc = fail(PDO_E_CUDA, "padepoisson buffers: %s", cudaGetErrorString(e));
-        if (!rc) {  // transpose destinations (collective, same order on every rank)
-            comm_register_buffer_quiet(p->uhatInZ, sizeof(double2) * (size_t)vol(p->sC.zsz));
-            comm_register_buffer_quiet(p->w2, sizeof(double2) * (size_t)vol(p->sE.zsz));
-            comm_register_buffer_quiet(p->f2dy, sizeof(double2) * (size_t)vol(p->sC.ysz));
-        }
+        // transpose destinations: peer-writable (collective, same order on every rank)
+        if (!rc) rc = comm_shared_malloc((void**)&p->uhatInZ, sizeof(double2) * (size_t)vol(p->sC.zsz));
+        if (!rc) rc = comm_shared_malloc((void**)&p->w2, sizeof(double2) * (size_t)vol(p->sE.zsz));
+        if (!rc) rc = comm_shared_malloc((void**)&p->f2dy, sizeof(double2) * (size_t)vol(p->sC.ysz));
     }
     if (rc) { pdo_padepoisson_destroy(p); return rc; }
     *h = p;
@@ -431,11 +426,14 @@ int pdo_padepoisson_init3(pdo_padepoisson_t* h, double dx, double dy, double dz,
 
 int pdo_padepoisson_destroy(pdo_padepoisson_t p) {
     if (!p) return 0;
-    void* ptrs[] = {p->k1sq, p->k2sq, p->k3sq, p->f2d, p->f2dy, p->w2, p->uhatInZ, p->dwdz, p->div_tmp};
-    for (void* q : ptrs) if (q) { comm_deregister_buffer(q); cudaFree(q); }
+    void* ptrs[] = {p->k1sq, p->k2sq, p->k3sq, p->f2d, p->dwdz, p->div_tmp};
+    for (void* q : ptrs) if (q) cudaFree(q);
     void* wall[] = {p->fext, p->wext, p->k3modcm, p->k3modcp, p->k3sq_ext, p->k1z, p->k2z, p->denfact};
     for (void* q : wall) if (q) cudaFree(q);
-    if (p->vhatInZ) { comm_deregister_buffer(p->vhatInZ); cudaFree(p->vhatInZ); }
+    comm_shared_free(p->vhatInZ);       // same order as the allocations on every rank
+    comm_shared_free(p->uhatInZ);
+    comm_shared_free(p->w2);
+    comm_shared_free(p->f2dy);
     zcols_destroy(&p->ext_plan);
     delete p;
     return 0;
@@ -450,18 +448,19 @@ int with_uvw(pdo_padepoisson_s* p, const double* u, const double* v, const doubl
     const size_t bC = sizeof(double2) * (size_t)vol(p->sC.ysz), bE = sizeof(double2) * (size_t)vol(p->sE.ysz);
     const double* in[3] = {u, v, w};
     const size_t bytes[3] = {bC, bC, bE};
-    double2* dev[3];
-    bool staged[3];
-    for (int i = 0; i < 3; ++i) {
-        staged[i] = !is_device_ptr(in[i]);
-        if (staged[i]) {
-            PDO_CUDA(cudaMalloc(&dev[i], bytes[i]));
-            PDO_CUDA(cudaMemcpyAsync(dev[i], in[i], bytes[i], cudaMemcpyHostToDevice, st));
-        } else {
-            dev[i] = (double2*)in[i];
+    double2* dev[3] = {nullptr, nullptr, nullptr};
+    bool staged[3] = {false, false, false};
+    int rc = 0;
+    for (int i = 0; i < 3 && !rc; ++i) {       // no early return: the staged copies made so far are released on every exit path
+        if (is_device_ptr(in[i])) { dev[i] = (double2*)in[i]; continue; }
+        cudaError_t e = cudaMalloc(&dev[i], bytes[i]);
+        if (e == cudaSuccess) {
+            staged[i] = true;
+            e = cudaMemcpyAsync(dev[i], in[i], bytes[i], cudaMemcpyHostToDevice, st);
         }
+        if (e != cudaSuccess) rc = fail(PDO_E_CUDA, "padepoisson staging: %s", cudaGetErrorString(e));
     }
-    int rc = body(dev[0], dev[1], dev[2]);
+    if (!rc) rc = body(dev[0], dev[1], dev[2]);
     for (int i = 0; i < 3; ++i) {
         if (!staged[i]) continue;
         if (!rc && writeback) {

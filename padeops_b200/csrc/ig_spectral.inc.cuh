@@ -219,9 +219,7 @@ int pdo_spectral_init(pdo_spectral_t* h, int nx, int ny, int nz, double dx, doub
     if (!rc) rc = upload(&s->gyz, s->h_gy, s->si.zst[1] - 1, s->si.zsz[1]);
     if (!rc) rc = upload(&s->gz, s->h_gz, 0, nz);
     if (!rc && s->periodicInZ && p_col > 1) {
-        cudaError_t e = cudaMalloc(&s->ctmpz, sizeof(double2) * (size_t)vol(s->si.zsz));
-        if (e != cudaSuccess) rc = fail(PDO_E_CUDA, "spectral ctmpz: %s", cudaGetErrorString(e));
-        else comm_register_buffer_quiet(s->ctmpz, sizeof(double2) * (size_t)vol(s->si.zsz));
+        rc = comm_shared_malloc((void**)&s->ctmpz, sizeof(double2) * (size_t)vol(s->si.zsz));
     }
     if (!rc) {
         cudaError_t e = cudaMalloc(&s->partial, sizeof(double) * 2048);
@@ -236,7 +234,7 @@ int pdo_spectral_destroy(pdo_spectral_t s) {
     if (!s) return 0;
     double* ptrs[] = {s->k1y, s->k2, s->gx, s->gy, s->gyz, s->gz, s->partial};
     for (double* p : ptrs) if (p) cudaFree(p);
-    if (s->ctmpz) { comm_deregister_buffer(s->ctmpz); cudaFree(s->ctmpz); }
+    comm_shared_free(s->ctmpz);
     if (s->ztab) cudaFree(s->ztab);
     if (s->rz_work) cudaFree(s->rz_work);
     zcols_destroy(&s->rz_plan);

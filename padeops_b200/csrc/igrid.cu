@@ -148,10 +148,13 @@ int ig_alloc(pdo_igrid_s* g, void** p, size_t bytes) {
 }
 template <class T>
 int ig_alloc_n(pdo_igrid_s* g, T** p, long long count) {
-    if (int rc = ig_alloc(g, (void**)p, sizeof(T) * (size_t)count)) return rc;
-    // every spectral (complex) array can be the destination of a y<->z transpose: make it peer-writable
-    if (sizeof(T) == sizeof(double2)) comm_register_buffer_quiet(*p, sizeof(T) * (size_t)count);
-    return 0;
+    // every spectral (complex) array can be the destination of a y<->z transpose: peer-writable memory
+    if (sizeof(T) == sizeof(double2)) {
+        if (int rc = comm_shared_malloc((void**)p, sizeof(T) * (size_t)count)) return rc;
+        g->allocs.push_back(*p);
+        return 0;
+    }
+    return ig_alloc(g, (void**)p, sizeof(T) * (size_t)count);
 }
 
 inline int fftC(pdo_igrid_s* g, const double* in, double2* out, cudaStream_t st) { return fft3d_forward_xy(g->spC->ft, in, out, st); }
@@ -549,7 +552,7 @@ extern "C" {
 
 int pdo_igrid_destroy(pdo_igrid_t g) {
     if (!g) return 0;
-    for (void* p : g->allocs) { comm_deregister_buffer(p); cudaFree(p); }
+    for (void* p : g->allocs) comm_shared_free(p);
     pdo_padepoisson_destroy(g->poiss);
     pdo_hit_forcing_destroy(g->hit);
     pdo_pade6stagg_destroy(g->ops);
@@ -795,26 +798,50 @@ int pdo_igrid_dump_restart(pdo_igrid_t g, const char* outputdir, int run_id) {
 }
 /* readRestartFile :2719-2761 followed by what init does with freshly read fields (:589-591, 625-655): step = tid, tsim from the
    info file (rank 0 reads, everyone gets it), fields projected and all dependent state rebuilt */
+/* A real as Fortran list / G editing writes it: "0.12346E+02", "1.5", and — when the exponent needs three digits — the form
+   without the exponent letter, "0.12346+123" / "0.12346-123" (what pdo_io_format_g15_5 and gfortran emit); 'D' is accepted too. */
+static bool parse_fortran_real(const char* tok, double* out) {
+    std::string t(tok);
+    for (auto& c : t) if (c == 'D' || c == 'd') c = 'E';
+    if (t.find('E') == std::string::npos && t.find('e') == std::string::npos) {
+        // a sign after the first character that does not follow an exponent letter starts the exponent
+        for (size_t i = 1; i < t.size(); ++i)
+            if ((t[i] == '+' || t[i] == '-') && (t[i - 1] == '.' || (t[i - 1] >= '0' && t[i - 1] <= '9'))) { t.insert(i, "E"); break; }
+    }
+    char* end = nullptr;
+    const double v = std::strtod(t.c_str(), &end);
+    if (end == t.c_str() || *end != 0) return false;
+    *out = v;
+    return true;
+}
 int pdo_igrid_read_restart(pdo_igrid_t g, const char* inputdir, int run_id, int tid) {
     if (!g) return fail(PDO_E_BADARG, "null handle");
     cudaStream_t st = nullptr;
     pdo_decomp_t dC = fft3d_phys_decomp(g->spC->ft), dE = fft3d_phys_decomp(g->spE->ft);
     // rbC / rbE scratch pencils receive the file contents; ig_set_fields copies them into u, v, w
     double *ru = g->rbC[0], *rv = g->rbC[1], *rw = g->rbE[0];
-    if (int rc = pdo_decomp_read_one(dC, 1, ru, 1, restart_name(inputdir, run_id, "u", tid).c_str())) return rc;
-    if (int rc = pdo_decomp_read_one(dC, 1, rv, 1, restart_name(inputdir, run_id, "v", tid).c_str())) return rc;
-    if (int rc = pdo_decomp_read_one(dE, 1, rw, 1, restart_name(inputdir, run_id, "w", tid).c_str())) return rc;
+    // pdo_decomp_read_one is rank-local (a short file fails only on the ranks whose sub-box reaches past its end): every rank
+    // goes through all three reads and the collectives below, and the outcome is agreed on before anyone returns
+    int rc_local = pdo_decomp_read_one(dC, 1, ru, 1, restart_name(inputdir, run_id, "u", tid).c_str());
+    if (!rc_local) rc_local = pdo_decomp_read_one(dC, 1, rv, 1, restart_name(inputdir, run_id, "v", tid).c_str());
+    if (!rc_local) rc_local = pdo_decomp_read_one(dE, 1, rw, 1, restart_name(inputdir, run_id, "w", tid).c_str());
+    const std::string read_err = rc_local ? std::string(pdo_last_error()) : std::string();
     double tsim = 0.0;
     int bad = 0;
     if (pdo_comm_rank() == 0) {
         FILE* f = std::fopen(restart_name(inputdir, run_id, "info", tid).c_str(), "r");
-        if (!f || std::fscanf(f, "%lf", &tsim) != 1) bad = 1;
+        char tok[64] = {0};
+        if (!f || std::fscanf(f, "%63s", tok) != 1 || !parse_fortran_real(tok, &tsim)) bad = 1;
         if (f) std::fclose(f);
     }
     // mpi_bcast(tsim) from rank 0: the other ranks contribute zero to a sum
-    double tsum = 0.0, badsum = 0.0;
+    double tsum = 0.0, badsum = 0.0, rcsum = 0.0;
     if (int b = pdo_p_sum(pdo_comm_rank() == 0 ? tsim : 0.0, &tsum)) return b;
     if (int b = pdo_p_sum((double)bad, &badsum)) return b;
+    if (int b = pdo_p_sum(rc_local ? 1.0 : 0.0, &rcsum)) return b;
+    if (rcsum != 0.0)
+        return rc_local ? fail(rc_local, "%s", read_err.c_str())
+                        : fail(PDO_E_BADARG, "restart files in '%s' could not be read on %d other rank(s)", inputdir ? inputdir : ".", (int)rcsum);
     if (badsum != 0.0) return fail(PDO_E_BADARG, "cannot read the restart info file in '%s'", inputdir ? inputdir : ".");
     for (int c = 0; c < 3; ++c) g->cur[c] = g->S[0][c];
     if (int rc = ig_set_fields(g, ru, rv, rw, st)) return rc;

@@ -105,7 +105,7 @@ int np_build_coefs(int kind, double dx, NpCoefs* c) {
         if (kind == NP_GAUSS) {
             c->in[0] = 3565.0 / 10368.0; c->in[1] = 3091.0 / 12960.0; c->in[2] = 1997.0 / 25920.0; c->in[3] = 149.0 / 12960.0; c->in[4] = 107.0 / 103680.0;
         } else {
-            c->in[0] = 0.5; c->in[1] = 0.6744132 / 2.0; c->in[2] = 0.0 / 2.0; c->in[3] = -0.1744132 / 2.0; c->in[4] = 0.0 / 2.0;
+            c->in[0] = 0.5; c->in[1] = (double)0.6744132f / 2.0; c->in[2] = 0.0 / 2.0; c->in[3] = (double)(-0.1744132f) / 2.0; c->in[4] = 0.0 / 2.0;   // real(0.6744132, rkind): a default-real literal widened to double
         }
         c->r1[0] = 5.0 / 6.0; c->r1[1] = 1.0 / 6.0;
         c->r2[0] = 2.0 / 3.0; c->r2[1] = 1.0 / 6.0;

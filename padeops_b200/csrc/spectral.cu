@@ -265,14 +265,11 @@ int pdo_fft3d_init(pdo_fft3d_t* h, int nx, int ny, int nz, double dx, double dy,
     f->normfactor2d = 1.0 / ((double)nx * (double)ny);
     f->slab2d = (p_row == 1);
     const long long ny_c = cvol(f->si.ysz), nz_c = cvol(f->si.zsz), nx_c = cvol(f->si.xsz);
-    cudaError_t e = cudaMalloc(&f->bufY, sizeof(double2) * (size_t)ny_c);
-    if (e == cudaSuccess && p_col > 1) e = cudaMalloc(&f->bufZ, sizeof(double2) * (size_t)nz_c);
-    if (e == cudaSuccess && !f->slab2d) e = cudaMalloc(&f->bufX, sizeof(double2) * (size_t)nx_c);
-    if (e != cudaSuccess) { pdo_fft3d_destroy(f); return fail(PDO_E_CUDA, "fft3d buffers: %s", cudaGetErrorString(e)); }
     // scratch pencils are transpose destinations: peer-writable for the fused NVLink path (collective, same order everywhere)
-    pdo::comm_register_buffer_quiet(f->bufY, sizeof(double2) * (size_t)ny_c);
-    if (f->bufZ) pdo::comm_register_buffer_quiet(f->bufZ, sizeof(double2) * (size_t)nz_c);
-    if (f->bufX) pdo::comm_register_buffer_quiet(f->bufX, sizeof(double2) * (size_t)nx_c);
+    rc = pdo::comm_shared_malloc((void**)&f->bufY, sizeof(double2) * (size_t)ny_c);
+    if (!rc && p_col > 1) rc = pdo::comm_shared_malloc((void**)&f->bufZ, sizeof(double2) * (size_t)nz_c);
+    if (!rc && !f->slab2d) rc = pdo::comm_shared_malloc((void**)&f->bufX, sizeof(double2) * (size_t)nx_c);
+    if (rc) { pdo_fft3d_destroy(f); return rc; }
     cufftResult r = CUFFT_SUCCESS;
     if (f->slab2d) {
         int n2[2] = {ny, nx};
@@ -315,9 +312,9 @@ int pdo_fft3d_destroy(pdo_fft3d_t f) {
     if (f->hasx) { cufftDestroy(f->planx_f); cufftDestroy(f->planx_b); }
     if (f->hasy) cufftDestroy(f->plany);
     if (f->hasz) cufftDestroy(f->planz);
-    if (f->bufX) { pdo::comm_deregister_buffer(f->bufX); cudaFree(f->bufX); }
-    if (f->bufY) { pdo::comm_deregister_buffer(f->bufY); cudaFree(f->bufY); }
-    if (f->bufZ) { pdo::comm_deregister_buffer(f->bufZ); cudaFree(f->bufZ); }
+    pdo::comm_shared_free(f->bufY);     // same order as the allocation on every rank
+    pdo::comm_shared_free(f->bufZ);
+    pdo::comm_shared_free(f->bufX);
     pdo_decomp_destroy(f->phys);
     pdo_decomp_destroy(f->spec);
     delete f;

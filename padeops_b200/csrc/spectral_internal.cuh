@@ -14,6 +14,10 @@ void comm_deregister_buffer(void* p);  // local; call before freeing a registere
 // Collective symmetric allocation (zeroed; peers[world rank] = that rank's copy mapped here); -1 when peer access is unavailable
 int comm_sym_alloc(size_t bytes, void** local, void** peers);
 void comm_sym_free(void* p);
+// peer-writable library-owned memory: pooled symmetric allocation with > 1 rank and peer access (collective, same order on every
+// rank; never cudaFree'd while a peer may still map it), cudaMalloc / cudaFree otherwise
+int comm_shared_malloc(void** p, size_t bytes);
+void comm_shared_free(void* p);
 void comm_info(int* rank, int* nproc, int* p2p);
 int comm_allreduce_sum(double* dev, int count, cudaStream_t st);   // in place, stream-ordered
 void decomp_grid(pdo_decomp_t h, int* p_row, int* p_col, int* c1, int* c2);

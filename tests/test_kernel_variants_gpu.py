@@ -101,8 +101,6 @@ def test_contiguous_variants(pdo, oracle, variant, xth, n):
     chunk length / on 16-point chunks.  A variant that does not cover a shape must fail loudly, never fall back."""
     if xth == 1016 and n % 32 != 0:
         pytest.skip("the M=16 alternate tables exist only next to M=32 ones")
-    if xth >= 1000 and n == 2048:
-        pytest.skip("three 2048-point tiles of 8 lines exceed 227 KB of shared memory")
     variant("auto", xth)
     d = 2 * np.pi / n
     c10, cf = pdo.cd10(), pdo.cf90()

@@ -214,9 +214,12 @@ def test_lstsq_filter(oracle):
     x = np.arange(n) * 2 * np.pi / n
     for k in (0, 3, 16):
         f = np.cos(k * x)[None, None, :] + np.zeros((2, 3, n))
-        T = 0.5 + 0.6744132 * np.cos(2 * np.pi * k / n) - 0.1744132 * np.cos(3 * 2 * np.pi * k / n)
+        # the reference's coefficients are default-real literals widened to double: real(0.6744132, rkind) (lstsq.F90:16-18)
+        b, dd = float(np.float32(0.6744132)), float(np.float32(-0.1744132))
+        T = 0.5 + b * np.cos(2 * np.pi * k / n) + dd * np.cos(3 * 2 * np.pi * k / n)
         assert np.abs(oracle.lstsq(f, 0) - T * f).max() < 1e-14
-    assert abs(0.5 + 0.6744132 - 0.1744132 - 1.0) < 1e-15 and abs(0.5 - 0.6744132 + 0.1744132) < 1e-15
+    assert oracle.LSTSQ_COEFS[1] * 2 == 0.67441320419311523 and oracle.LSTSQ_COEFS[3] * 2 == -0.17441320419311523
+    assert abs(0.5 + 0.6744132 - 0.1744132 - 1.0) < 1e-15 and abs(0.5 - 0.6744132 + 0.1744132) < 1e-15   # the decimal design values
     f = np.random.default_rng(4).standard_normal((2, 3, n))
     got = oracle.lstsq_np(f, 0)
     assert np.array_equal(got[..., :4], oracle.gaussian_np(f, 0, 0, 0)[..., :4]) and np.array_equal(got[..., -4:], oracle.gaussian_np(f, 0, 0, 0)[..., -4:])
