@@ -9,10 +9,15 @@ points (weak scaling); ddx / ddy are pencil-local, ddz goes y->z transpose, deri
 over NCCL, exactly the choreography of tests/test_derivatives_parallel.F90:94-126.
 
 `value`       device-resident throughput (inputs already in HBM), CUDA-event timed, max over ranks.
-`e2e`         same metric through the C ABI with HOST (pinned) buffers: H2D + kernel + D2H per call.
-`roofline`    dominant kernel: 16 B/pt algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json.
-`cpu_baseline` the oracle port (flat-MPI emulation: one worker per host core, each owning a pencil),
-              timed on a bounded 512^3 sample.  `--impl reference` prints that arm alone.
+`e2e`         same metric through the C ABI with HOST (pinned) buffers: H2D + kernel + D2H per call; next to it the box's own
+              full-duplex pinned-copy ceiling (`pcie_ceiling_GBps_per_gpu_each_way`), which is what bounds this leg.
+`roofline`    the slowest of the three legs: 16 B/pt algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json.
+`cpu_baseline` the oracle port (flat-MPI emulation: one worker per host core, each owning a pencil) on the SAME 1024^3 field,
+              1 warm-up + 2 timed passes.  `--impl reference` runs that arm alone with the given --steps / --warmup.
+`substep`     BASELINE metric (iii): ms per igrid RK substep at 512^3 (strong scaling); flat copy in `substep_ms`.
+`transposes`, `poisson`, `cd10_2048`   BASELINE configs 3 and 5 at this N: the four pencil transposes of the 1024^3 field (real +
+              complex, grids 1xN and 2xN/2) with their NVLink fraction, PoissonPeriodic on 1024^3 (strong), CD10 ddx/ddy/ddz/d2dx2 on
+              2048^3 (strong; skipped where two 64 GiB/N fields do not fit).
 """
 import argparse
 import json
@@ -44,7 +49,10 @@ def peaks():
 # each worker owning the pencil a 2DECOMP rank would own (transposes between pencils are not timed,
 # which favours the CPU).
 # ------------------------------------------------------------------------------------------------
-def cpu_arm(n_global, steps, warmup, cores=None):
+def cpu_arm(n_global, steps, warmup, cores=None, budget_s=None):
+    """CD10 ddx + ddy + ddz of an n^3 field on the host cores.  Worker i owns the pencil a 2DECOMP rank of a 1 x C grid would own:
+    (n, n, n/C) for x and y, (n, n/C, n) for z; input and output arrays are allocated and touched before the timed region
+    (the reference's callers own both).  budget_s caps the timed steps by the rate measured during warm-up."""
     import numpy as np
     from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle as O
@@ -52,44 +60,62 @@ def cpu_arm(n_global, steps, warmup, cores=None):
     cores = cores or os.cpu_count() or 1
     n = n_global
     d = 2 * np.pi / n
-    # 1 x C slabs: each worker owns (n, n, n/C) of the x/y-pencil and (n, n/C, n) of the z-pencil
     nloc = [n // cores + (1 if i >= cores - n % cores else 0) for i in range(cores)]
-    rng = np.random.default_rng(20240607)
-    fxy = [rng.standard_normal((max(1, nl), n, n)) for nl in nloc]     # f(n, n, nl): x- and y-pencil
-    fz = [rng.standard_normal((n, max(1, nl), n)) for nl in nloc]      # f(n, nl, n): z-pencil
-    O.cd10(fxy[0][:1], d, 0, 1)  # builds LU once (untimed, like init)
+    nloc = [nl for nl in nloc if nl > 0]
+    W = len(nloc)
+    fxy, oxy, fz, oz = [None] * W, [None] * W, [None] * W, [None] * W
+
+    def make(i):   # the z-pencil block reuses the memory of the x/y one (values are immaterial to the timing): 16 n^3 bytes in all
+        rng = np.random.default_rng(20240607 + i)
+        fxy[i] = np.empty((nloc[i], n, n))
+        rng.random(out=fxy[i].reshape(-1))
+        oxy[i] = np.zeros((nloc[i], n, n))
+        fz[i] = fxy[i].reshape(n, nloc[i], n)
+        oz[i] = oxy[i].reshape(n, nloc[i], n)
+
+    O.cd10(np.zeros((1, 1, n)), d, 0, 1)  # builds LU once (untimed, like init)
 
     def work(i):
-        O.cd10(fxy[i], d, 0, 1)
-        O.cd10(fxy[i], d, 1, 1)
-        O.cd10(fz[i], d, 2, 1)
+        O.cd10(fxy[i], d, 0, 1, out=oxy[i])
+        O.cd10(fxy[i], d, 1, 1, out=oxy[i])
+        O.cd10(fz[i], d, 2, 1, out=oz[i])
 
     pts = 3.0 * n ** 3
-    times = []
-    with ThreadPoolExecutor(max_workers=cores) as ex:
-        for it in range(warmup + steps):
+    times, wt = [], []
+    with ThreadPoolExecutor(max_workers=W) as ex:
+        list(ex.map(make, range(W)))
+        for it in range(max(1, warmup)):
             t0 = time.perf_counter()
-            list(ex.map(work, range(cores)))
-            dt = time.perf_counter() - t0
-            if it >= warmup:
-                times.append(dt)
+            list(ex.map(work, range(W)))
+            wt.append(time.perf_counter() - t0)
+        if budget_s is not None:
+            steps = max(1, min(steps, int(budget_s / max(wt[-1], 1e-9))))
+        for it in range(steps):
+            t0 = time.perf_counter()
+            list(ex.map(work, range(W)))
+            times.append(time.perf_counter() - t0)
     t = sum(times) / len(times)
-    return {"value": pts / t / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"CD10 ddx+ddy+ddz on a {n}^3 field split 1x{cores} (one worker per core, own pencil each); "
-                      f"{len(times)} passes, {t*1e3:.1f} ms/pass; oracle/padeops_oracle.c compiled -O3 -march=native"}, t
+    return {"value": pts / t / 1e9, "unit": UNIT, "cores": W, "kind": "port",
+            "sample": f"CD10 ddx+ddy+ddz on the full {n}^3 field split 1x{W} (one worker per core, own pencil each; arrays caller-owned "
+                      f"and pre-touched); {len(times)} timed passes after {max(1, warmup)} warm-up, {t*1e3:.1f} ms/pass; "
+                      f"oracle/padeops_oracle.c compiled -O3 -march=native"}, t, len(times)
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of the reference's own path (the Fortran + MPI original cannot be built in this image,
+    DESIGN.md 3) on all host cores, SAME config as our arm (cd10 ddx+ddy+ddz on n^3, n = --n = 1024), same steps / warm-up; the
+    timed steps are capped only if they would run past ~3 minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    ncpu = int(os.environ.get("PDO_BENCH_CPU_N", "512"))
-    cb, t = cpu_arm(ncpu, steps, min(args.warmup, 1))
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+    ncpu = int(os.environ.get("PDO_BENCH_CPU_N", str(args.n)))
+    warm = max(1, min(args.warmup, 3))
+    cb, t, used = cpu_arm(ncpu, args.steps, warm, budget_s=170.0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": used,
+            "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"cd10 ddx+ddy+ddz, periodic, {ncpu}^3 sample of the 1024^3 workload (CPU arm)", "n": ncpu},
+            "config": {"workload": f"cd10 ddx+ddy+ddz, periodic, {ncpu}x{ncpu}x{ncpu} field (CPU arm: the same field our 1-GPU arm runs)",
+                       "n": ncpu, "global": [ncpu, ncpu, ncpu]},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -188,6 +214,183 @@ def substep_leg(n, world, rank, steps=2):
            "Mpoints_per_s": n ** 3 / (ms / 3.0) / 1e3, "max_divergence": float(g.maxDivergence())}
     g.destroy() if hasattr(g, "destroy") else None
     return out
+
+
+NVLINK_GBS = 900.0   # NVLink 5, per direction per GPU
+
+
+def _ev_time(fn, st, reps, warm, world):
+    """median-free device timing: warm-up, barrier, reps back to back between two events on the launching stream; max over ranks"""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(st)
+    for _ in range(reps):
+        fn()
+    b.record(st)
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return ms
+
+
+def transposes_leg(n, world, rank):
+    """BASELINE config 3, first half: the four pencil transposes of an n^3 real field and of its (n/2+1) x n x n complex spectrum on
+    grids 1 x N and 2 x N/2; bytes sent per GPU = L (p-1)/p against 900 GB/s per direction.  Destinations are
+    registered (peer-writable), so the fused NVLink path runs; bit-exactness is tests/mp_worker.py's and the emulated-grid test's job."""
+    import torch
+    import padeops_b200 as pdo
+    from padeops_b200 import decomp as dc
+    st = torch.cuda.current_stream()
+    grids = [(1, world)] + ([(2, world // 2)] if world >= 4 else [])
+    rows = []
+    for (pr, pc) in grids:
+        for cplx in (False, True):
+            nx = n // 2 + 1 if cplx else n
+            gp = pdo.decomp_info(nx, n, n, pr, pc)
+            dt = torch.complex128 if cplx else torch.float64
+            bufs = {p: torch.zeros(tuple(reversed(getattr(gp, p + "sz"))), dtype=dt, device="cuda") for p in "xyz"}
+            (bufs["x"].real if cplx else bufs["x"]).uniform_()
+            for p in "xyz":
+                pdo.decomp_2d.register(bufs[p])
+            for name, fn, s_, d_, p in (("x_to_y", dc.transpose_x_to_y, "x", "y", pr), ("y_to_x", dc.transpose_y_to_x, "y", "x", pr),
+                                        ("y_to_z", dc.transpose_y_to_z, "y", "z", pc), ("z_to_y", dc.transpose_z_to_y, "z", "y", pc)):
+                if p == 1:
+                    continue   # one rank in that sub-communicator: the pencils coincide, nothing crosses a link
+                ms = _ev_time(lambda: fn(bufs[s_], bufs[d_], gp), st, 8, 3, world)
+                L = bufs[s_].numel() * bufs[s_].element_size()
+                sent = L * (p - 1) / p
+                rows.append({"op": name, "complex": cplx, "grid": [pr, pc], "ms": round(ms, 4), "sent_MB_per_gpu": round(sent / 1e6, 1),
+                             "link_GBps_per_gpu": round(sent / ms / 1e6, 1), "nvlink_frac": round(sent / ms / 1e6 / NVLINK_GBS, 3)})
+            for p in "xyz":
+                pdo.decomp_2d.deregister(bufs[p])
+            del bufs
+            gp.destroy()
+            torch.cuda.empty_cache()
+    worst = min(rows, key=lambda r: r["nvlink_frac"]) if rows else None
+    return {"workload": f"pencil transposes of a {n}^3 real field / its {n//2+1}x{n}x{n} complex spectrum, {world} GPUs", "peak_GBps": NVLINK_GBS,
+            "rows": rows, "min_nvlink_frac": worst["nvlink_frac"] if worst else None, "plane": os.environ.get("PDO_P2P_MODE", "auto")}
+
+
+def poisson_leg(n, world, rank):
+    """BASELINE config 3, second half: PoissonPeriodic%poisson_solve (dir_id = 1) on the global n^3 grid, slabs 1 x N (strong scaling):
+    fft3_x2z + multiply + ifft3_z2x = 176 algorithmic bytes per real point."""
+    import numpy as np
+    import torch
+    import padeops_b200 as pdo
+    st = torch.cuda.current_stream()
+    d = 2 * np.pi / n
+    po = pdo.PoissonPeriodic()
+    po.init(d, d, d, (n, n, n), 1, p_row=1, p_col=world)
+    info = pdo.decomp_info.for_rank(n, n, n, 1, world, rank)
+    rhs = torch.rand(tuple(reversed(info["xsz"])), dtype=torch.float64, device="cuda")
+    out = torch.empty_like(rhs)
+    ms = _ev_time(lambda: po.poisson_solve(rhs, out), st, 5, 2, world)
+    po.destroy()
+    peak, _ = peaks()
+    gb = 176.0 * n ** 3 / world / 1e9
+    return {"workload": f"PoissonPeriodic poisson_solve, {n}^3 global, grid 1x{world} (strong scaling)", "ms": round(ms, 4),
+            "Gpoints_per_s": round(n ** 3 / ms / 1e6, 2), "algorithmic_GB_per_gpu": round(gb, 3),
+            "hbm_frac_per_gpu": round(gb / (ms * 1e-3) / peak, 3)}
+
+
+def cd10_2048_leg(world, rank):
+    """BASELINE config 5: CD10 ddx / ddy / ddz + d2dx2 on a 2048^3 field (64 GiB), y-pencil, slabs 1 x N, strong scaling.  x and y are
+    pencil-local; z goes through the distributed z-slab solve (pdo_operators_ddz).  Skipped when 2 fields + scratch do not fit."""
+    import numpy as np
+    import torch
+    import padeops_b200 as pdo
+    n = 2048
+    st = torch.cuda.current_stream()
+    need = 2 * 8 * n ** 3 / world * 1.12 + (2 << 30)
+    free, _tot = torch.cuda.mem_get_info()
+    ok = free > need
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(t.item())
+    if not ok:
+        return {"skipped": f"needs {need/2**30:.0f} GiB per GPU at {world} GPU(s), {free/2**30:.0f} GiB free"}
+    d = 2 * np.pi / n
+    gp = pdo.decomp_2d.init(n, n, n, 1, world)
+    f = torch.empty(tuple(reversed(gp.ysz)), dtype=torch.float64, device="cuda")
+    f.uniform_()
+    df = torch.empty_like(f)
+    npts = f.numel()
+    der = pdo.derivatives()
+    der.init(gp, d, d, d, True, True, True, "cd10", "cd10", "cd10")
+    ops = None
+    if world > 1:
+        ops = pdo.vector_ops()
+        ops.init(gp, d, d, d, "cd10", allow_zslab=True)
+    peak, _ = peaks()
+    out = {"workload": f"cd10 ddx / ddy / ddz / d2dx2, 2048^3 global (64 GiB per field), grid 1x{world}, {npts} points per GPU (strong scaling)",
+           "z_path": "local" if ops is None else ("z-slab distributed solve" if ops.zmode == 1 else "transposes"), "ops": {}}
+    calls = [("ddx", lambda: der.ddx(f, df)), ("ddy", lambda: der.ddy(f, df)),
+             ("ddz", (lambda: der.ddz(f, df)) if ops is None else (lambda: ops.ddz(f, df))), ("d2dx2", lambda: der.d2dx2(f, df))]
+    tot = 0.0
+    for nm, fn in calls:
+        ms = _ev_time(fn, st, 4, 2, world)
+        tot += ms
+        out["ops"][nm] = {"ms": round(ms, 4), "Gpoints_per_s": round(n ** 3 / ms / 1e6, 1),
+                          "hbm_frac_per_gpu": round(BYTES_PER_POINT * npts / (ms * 1e-3) / 1e9 / peak, 3)}
+    out["ms_all_four"] = round(tot, 4)
+    out["Gpoints_per_s_all_four"] = round(4.0 * n ** 3 / tot / 1e6, 1)
+    if ops is not None:
+        ops.destroy()
+    der.destroy()
+    del f, df
+    torch.cuda.empty_cache()
+    return out
+
+
+def pcie_ceiling(nbytes, world):
+    """What the host gives a plain pinned full-duplex copy of the e2e leg's size (H2D and D2H at once, all ranks at once): the
+    ceiling of any host-pointer path on this box."""
+    import torch
+    try:
+        h_in = torch.empty(nbytes // 8, dtype=torch.float64).pin_memory()
+        h_out = torch.empty(nbytes // 8, dtype=torch.float64).pin_memory()
+        d_in = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+        d_out = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+    except RuntimeError:
+        return None
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def go():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+    go()
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        go()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 2
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = t.item()
+    return nbytes / dt / 1e9
+
+
 
 
 def run_ours(args):
@@ -374,8 +577,18 @@ def run_ours(args):
             dt = t.item()
         e2e = {"value": 3.0 * ne ** 3 * world / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 3 * 8 * ne ** 3,
                "d2h_bytes_per_step": 3 * 8 * ne ** 3, "n": ne, "ms_per_step": dt * 1e3,
-               "note": "pdo_cd10_dd1/dd2/dd3 called with pinned HOST pointers; the library stages H2D/D2H"}
+               "pcie_GBps_per_gpu_each_way": 3 * 8 * ne ** 3 / dt / 1e9,
+               "note": "pdo_cd10_dd1/dd2/dd3 called with pinned HOST pointers; the library stages H2D/D2H (chunked, full duplex)"}
         del fh, oh, bufs
+        # the box's own ceiling for this leg: a plain pinned full-duplex copy of one field each way, all ranks at once
+        try:
+            ceil = pcie_ceiling(8 * ne ** 3, world)
+            if ceil:
+                e2e["pcie_ceiling_GBps_per_gpu_each_way"] = ceil
+                e2e["frac_of_pcie_ceiling"] = e2e["pcie_GBps_per_gpu_each_way"] / ceil
+        except Exception as ex:  # noqa
+            e2e["pcie_ceiling_error"] = str(ex)[:120]
+        torch.cuda.empty_cache()
 
     # ---- igrid RK substep (metric iii), guarded: a failure or a stall here must not cost the headline line ----
     sub = None
@@ -389,18 +602,29 @@ def run_ours(args):
         del f, df, tin, tout, gx, gy
         torch.cuda.empty_cache()
 
-        def _run_sub():
+        def _guard(key, fn):
             try:
-                torch.cuda.set_device(local)   # the current device is per thread
-                sub_holder["v"] = substep_leg(args.substep_n, world, rank)
+                sub_holder[key] = fn()
             except Exception as ex:  # noqa
-                sub_holder["v"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+                sub_holder[key] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+            torch.cuda.empty_cache()
+
+        def _run_sub():
+            torch.cuda.set_device(local)   # the current device is per thread
+            _guard("v", lambda: substep_leg(args.substep_n, world, rank))
+            if not args.no_legs:
+                # BASELINE configs 3 and 5 (collective legs: every rank runs them in the same order)
+                if world > 1:
+                    _guard("transposes", lambda: transposes_leg(args.n, world, rank))
+                _guard("poisson", lambda: poisson_leg(args.n, world, rank))
+                _guard("cd10_2048", lambda: cd10_2048_leg(world, rank))
+            sub_holder["done"] = True
         th = threading.Thread(target=_run_sub, daemon=True)
         th.start()
-        th.join(timeout=float(args.substep_timeout))
+        th.join(timeout=float(args.substep_timeout + (0 if args.no_legs else args.legs_timeout)))
         sub = sub_holder.get("v", {"error": f"substep leg did not finish within {args.substep_timeout} s"})
     if rank != 0:
-        if not args.no_substep and "v" not in sub_holder:
+        if not args.no_substep and "done" not in sub_holder:
             os._exit(0)
         return
     peak, peak_src = peaks()
@@ -408,9 +632,9 @@ def run_ours(args):
     per_k = {}
     for nm, t in zip(names, per):
         per_k[nm] = {"ms": t, "GBps": BYTES_PER_POINT * npts_rank / (t * 1e-3) / 1e9}
-    kern_only = [t for j, t in enumerate(per) if (j == 1) or (j == 0 and p_row == 1) or (j == 2 and p_col == 1)]
-    kidx = [j for j in range(3) if (j == 1) or (j == 0 and p_row == 1) or (j == 2 and p_col == 1)]
-    dom = kidx[max(range(len(kern_only)), key=lambda j: kern_only[j])]
+    # the genuinely slowest leg, also when it is the distributed z solve (halo exchange + edge pass + kernel): its 16 B/pt are
+    # still the algorithmic bytes, so the fraction says what the decomposition costs
+    dom = max(range(3), key=lambda j: per[j])
     ach = BYTES_PER_POINT * npts_rank / (per[dom] * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_POINT * npts_rank, "per_kernel": per_k}
@@ -427,7 +651,7 @@ def run_ours(args):
             pass
     cb = None
     if not args.no_cpu:
-        cb, _ = cpu_arm(512, 1, 1)
+        cb, _, _ = cpu_arm(n, 2, 1)      # bounded sample: the full field, 1 warm-up + 2 timed passes (~10 s on 16 cores)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
@@ -438,9 +662,21 @@ def run_ours(args):
                        "n": n, "global": [nx, ny, nz], "grid": [p_row, p_col],
                        "l2": "inputs (8 GiB per field at n=1024) larger than the 126 MB L2, no flush needed"},
             "roofline": roof, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "substep": sub}
+    if isinstance(sub, dict) and "ms_per_substep" in sub:   # metric (iii) as flat top-level keys too
+        line["substep_ms"] = sub["ms_per_substep"]
+        line["substep_launches"] = sub.get("launches_per_substep")
+    for key in ("transposes", "poisson", "cd10_2048"):      # BASELINE configs 3 and 5
+        if key in sub_holder:
+            line[key] = sub_holder[key]
+    if isinstance(line.get("transposes"), dict) and line["transposes"].get("min_nvlink_frac") is not None:
+        line["transposes_min_nvlink_frac"] = line["transposes"]["min_nvlink_frac"]
+    if isinstance(line.get("poisson"), dict) and "ms" in line["poisson"]:
+        line["poisson_ms"] = line["poisson"]["ms"]
+    if isinstance(line.get("cd10_2048"), dict) and "ms_all_four" in line["cd10_2048"]:
+        line["cd10_2048_ms"] = line["cd10_2048"]["ms_all_four"]
     print(json.dumps(line), flush=True)
-    if not args.no_substep and "v" not in sub_holder:
-        os._exit(0)   # the guarded leg is still stuck in a collective: leave without joining it
+    if not args.no_substep and "done" not in sub_holder:
+        os._exit(0)   # a guarded leg is still stuck in a collective: leave without joining it
 
 
 def main():
@@ -457,6 +693,8 @@ def main():
     ap.add_argument("--no-substep", action="store_true", dest="no_substep")
     ap.add_argument("--substep-n", type=int, default=512, dest="substep_n", help="global grid of the igrid substep leg")
     ap.add_argument("--substep-timeout", type=int, default=150, dest="substep_timeout")
+    ap.add_argument("--no-legs", action="store_true", dest="no_legs", help="skip the config-3 / config-5 legs (transposes, Poisson, 2048^3)")
+    ap.add_argument("--legs-timeout", type=int, default=240, dest="legs_timeout")
     ap.add_argument("--profile-region", action="store_true", dest="profile_region",
                     help="cudaProfilerStart/Stop around the timed region (for ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -93,6 +93,20 @@ int pdo_gaussian_filter1(pdo_gaussian_t h, const double* f, double* fil, int na,
 int pdo_gaussian_filter2(pdo_gaussian_t h, const double* f, double* fil, int na, int nb, int bc1, int bcn, void* stream); /* :336 */
 int pdo_gaussian_filter3(pdo_gaussian_t h, const double* f, double* fil, int na, int nb, int bc1, int bcn, void* stream); /* :564 */
 
+/* ---- kernel planning (no counterpart in the reference's operators; the analogue of FFTW's planner, which the reference runs
+ *      inside fft_3d%init with FFTW_MEASURE / FFTW_EXHAUSTIVE, fft_3d.F90:150-158) ------------------------------------------
+ * Without a plan every operator call picks its kernel from a fixed table: same kernel on every box, nothing timed, nothing
+ * synchronised inside a call (stream order and graph capture are safe from the first call on).  pdo_*_plan times the kernel
+ * candidates for ONE shape — axis 0 / 1 / 2 = x / y / z, (na, nb) as the dd* / filter* calls take them — on scratch arrays,
+ * stores the winner in the handle and reports its code in *variant (may be NULL).  It synchronises the device; call it at
+ * set-up time.  All candidates agree to rounding, so a plan changes the speed, not the result beyond 1e-15. */
+int pdo_cd10_plan(pdo_cd10_t h, int axis, int na, int nb, int* variant_d1, int* variant_d2);
+int pdo_cd06_plan(pdo_cd06_t h, int axis, int na, int nb, int* variant);
+int pdo_cf90_plan(pdo_cf90_t h, int axis, int na, int nb, int* variant);
+int pdo_gaussian_plan(pdo_gaussian_t h, int axis, int na, int nb, int* variant);
+/* enable != 0: the first large call of an operator on a shape plans by itself (same as the environment variable PDO_TUNE=1) */
+int pdo_plan_on_first_call(int enable);
+
 /* ---- cd06staggstuff::cd06stagg, periodic  (derivatives/cd06stagg.F90) ------------------------ */
 typedef struct pdo_cd06stagg_s* pdo_cd06stagg_t;
 int pdo_cd06stagg_init_periodic(pdo_cd06stagg_t* h, int n, double dx);                  /* cd06stagg.F90:170-195 */

@@ -87,13 +87,16 @@ def _na_nb(f, axis):
     return n3, n1, n2
 
 
-def cd10(f, dx, axis, which=1):
-    """cd10%dd1/dd2/dd3 (which=1) or d2d1/d2d2/d2d3 (which=2) along `axis` (0=x fastest)."""
+def cd10(f, dx, axis, which=1, out=None):
+    """cd10%dd1/dd2/dd3 (which=1) or d2d1/d2d2/d2d3 (which=2) along `axis` (0=x fastest).  `out`: caller-owned result array
+    (the reference's df is the caller's too; the timed CPU baseline passes it so that no page faults sit in the timed region)."""
     f = np.ascontiguousarray(f, dtype=np.float64)
     n, na, nb = _na_nb(f, axis)
     ierr, LU = cd10_lu(n, which)
     assert ierr == 0
-    out = np.empty_like(f)
+    if out is None:
+        out = np.empty_like(f)
+    assert out.shape == f.shape and out.dtype == np.float64 and out.flags.c_contiguous
     lib().pdo_oracle_cd10(_p(LU), C.c_int(n), C.c_double(dx), C.c_int(which), C.c_int(axis), _p(f), _p(out),
                           C.c_int64(na), C.c_int64(nb))
     return out

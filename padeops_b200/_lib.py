@@ -52,6 +52,11 @@ _PROTOS = {
     "pdo_cf90_destroy": (C.c_int, [C.c_void_p]),
     "pdo_gaussian_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "pdo_gaussian_destroy": (C.c_int, [C.c_void_p]),
+    "pdo_cd10_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "pdo_cd06_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "pdo_cf90_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "pdo_gaussian_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "pdo_plan_on_first_call": (C.c_int, [C.c_int]),
     "pdo_cd06stagg_init_periodic": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_double]),
     "pdo_cd06stagg_destroy": (C.c_int, [C.c_void_p]),
     "pdo_derivatives_init": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -220,6 +225,7 @@ class ChunkTables(C.Structure):
 
 _PROTOS["pdo_debug_np_chunk_tables"] = (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.POINTER(C.c_int)])
 _PROTOS["pdo_debug_ctma_config"] = (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)])
+_PROTOS["pdo_debug_np_fast"] = (C.c_int, [C.c_int])
 _PROTOS["pdo_debug_np_rows"] = (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_dp])
 _PROTOS["pdo_debug_np_line_host"] = (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, c_dp, c_dp, C.c_longlong, C.c_longlong])
 _PROTOS["pdo_debug_chunk_tables"] = (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int])

@@ -1511,12 +1511,15 @@ int x_threads() {  // 0 = auto
     return v;
 }
 
-// PDO_TUNE=0 disables the first-call planner (heuristic dispatch only)
+// PDO_TUNE=1 lets the FIRST large call of an operator on a shape time the candidates (the round-1 behaviour).  Off by default:
+// a user call never synchronises, never breaks stream ordering or graph capture and picks the same kernel on every box; timing
+// is an explicit, separate step (banded_op_plan / pdo_*_plan).
+int g_tuning = -1;
 bool tuning_enabled() {
-    static int v = -1;
+    int& v = g_tuning;
     if (v < 0) {
         const char* e = std::getenv("PDO_TUNE");
-        v = (e && std::atoi(e) == 0) ? 0 : 1;
+        v = (e && std::atoi(e) == 1) ? 1 : 0;
     }
     return v != 0;
 }
@@ -1933,41 +1936,59 @@ cudaError_t launch_chunk(const BandedOp* h, int axis, const double* f, double* o
     return cudaGetLastError();
 }
 
-// Planner.  Which kernel variant wins depends on the operator (how much FP64 work sits between the load and the
-// store), the line length and the row stride, and the differences are tens of percent.  Like FFTW's planner and
-// 2DECOMP's best_2d_grid (both timing-based in the reference), the first large call of an operator on a given
-// (axis, shape) times the candidates on the caller's own arrays (out-of-place operators: re-running is harmless)
-// and remembers the winner in the handle.  All candidates produce bit-identical results (same per-chunk
-// arithmetic), so the choice never changes the answer.  Small problems and captured streams use the heuristic.
+// Deterministic dispatch: the variant a shape gets when no plan has been made for it.  Measured on B200 at the BASELINE shapes
+// (profiles/r02*_vsweep*.jsonl); every entry falls back to the shape heuristic (mode 0) when the variant does not cover the shape.
+//   x axis                       TMA bulk-copy pipeline
+//   y axis (rows KBs apart)      banded: single-CTA pipelines while a whole line fits one CTA 16 columns wide (pipe1; the TMA one at
+//                                <= 16 chunks), cpipe with tensor-map loads beyond; CD06: cluster + TMA; stencils: streaming kernel
+//   z axis (rows MBs apart)      256-byte row segments always: cpipe (cpipe_t for lines of 64 chunks), CD06: cluster + TMA
 template <int RK, int BW, int M>
-cudaError_t launch_planned(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3,
-                           long long in_slab, long long out_slab, cudaStream_t st) {
-    const int forced_mode = strided_mode(), forced_x = x_threads();
-    const bool forced = (axis == 0) ? forced_x != 0 : forced_mode != 0;
-    const long long pts = n1 * h->n * n3;
-    if (forced || !tuning_enabled() || pts < (1LL << 24))
-        return launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, forced_mode, forced_x);
-    {
-        std::lock_guard<std::mutex> lk(g_plan_mutex);
-        for (int i = 0; i < h->nplans; ++i)
-            if (h->plans[i].axis == axis && h->plans[i].n1 == n1 && h->plans[i].n3 == n3)
-                return launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, h->plans[i].choice, h->plans[i].choice);
+int default_variant(const BandedOp* h, int axis, long long n1, long long n3) {
+    (void)n3;
+    if (axis == 0) return kXTma;
+    const int P = h->n / M;
+    if (BW == 0) return 0;                                   // explicit stencils: the heuristic's streaming kernel
+    const bool far_rows = n1 * (long long)sizeof(double) >= (1 << 20);
+    if (M != 32) return 0;
+    if (BW == 1 && RK == RK_D1_5) return (n1 % 2 == 0 && P >= 8) ? kCTma32 : 0;
+    if (BW == 1) return 0;                                   // staggered operators (edge planes): heuristic
+    if (!far_rows) {
+        if (P <= 16) return (n1 % 2 == 0) ? kSTma : 6;
+        if (P <= 32) return (RK == RK_SYM_9) ? kCpipeT : 6;  // CF90's 9-point stencil + 13-block gather: the cluster split wins
+        return kCpipeT;
     }
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
-        cudaGetLastError();
-        return launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, 0, 0);
+    if (P <= 16) return (RK == RK_SYM_9) ? kCpipeT : 6;
+    if (P <= 32) return (RK == RK_SYM_9) ? kCpipeT : 5;
+    return kCpipeT;
+}
+
+template <int RK, int BW, int M>
+cudaError_t launch_default(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3, long long in_slab,
+                           long long out_slab, cudaStream_t st) {
+    const int v = default_variant<RK, BW, M>(h, axis, n1, n3);
+    if (v != 0) {
+        const cudaError_t e = launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, v, v);
+        if (e != cudaErrorInvalidConfiguration) return e;
+        cudaGetLastError();                                  // the table's pick does not cover this shape (odd n1, tiny extents, ...)
     }
-    const int cand_x[3] = {128, 256, kXTma};  // kXTma16 regroups the arithmetic (not bit-identical): opt-in only
-    // pipe1, cpipe, cluster / streaming, t512, then the TMA-staged ones: single-CTA pipeline, cluster kernel (two small CTAs
-    // per SM / one large), cpipe with tensor-map loads
+    return launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, 0, 0);
+}
+
+// Timing-based plan (explicit: banded_op_plan, or the first call when PDO_TUNE=1): like FFTW's planner and 2DECOMP's
+// best_2d_grid (both timing-based in the reference) it times the candidates on real arrays of the shape and remembers the
+// winner in the handle.  The candidates agree to rounding (same per-chunk algebra), so the choice does not change the answer
+// beyond 1e-15.
+template <int RK, int BW, int M>
+cudaError_t plan_by_timing(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3, long long in_slab,
+                           long long out_slab, cudaStream_t st) {
+    const int cand_x[3] = {128, 256, kXTma};
     const int cand_s[8] = {6, 5, 3, 1, kSTma, kCTma32s, kCTma32, kCpipeT};
     const int* cand = axis == 0 ? cand_x : cand_s;
     const int ncand = axis == 0 ? (xtma_in_planner() ? 3 : 2) : (xtma_in_planner() ? 8 : 4);
     cudaEvent_t e0, e1;
     if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
         cudaGetLastError();
-        return launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, 0, 0);
+        return launch_default<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
     }
     int best = 0;
     float best_ms = 1e30f;
@@ -1989,25 +2010,52 @@ cudaError_t launch_planned(const BandedOp* h, int axis, const double* f, double*
     cudaEventDestroy(e1);
     {
         std::lock_guard<std::mutex> lk(g_plan_mutex);
-        if (h->nplans < BandedOp::kMaxPlans) {
-            h->plans[h->nplans].axis = axis; h->plans[h->nplans].n1 = n1; h->plans[h->nplans].n3 = n3;
-            h->plans[h->nplans].choice = best;
-            h->nplans++;
-        }
+        int slot = -1;
+        for (int i = 0; i < h->nplans; ++i)
+            if (h->plans[i].axis == axis && h->plans[i].n1 == n1 && h->plans[i].n3 == n3) slot = i;
+        if (slot < 0 && h->nplans < BandedOp::kMaxPlans) slot = h->nplans++;
+        if (slot >= 0) { h->plans[slot].axis = axis; h->plans[slot].n1 = n1; h->plans[slot].n3 = n3; h->plans[slot].choice = best; }
     }
     if (std::getenv("PDO_TUNE_VERBOSE"))
         std::fprintf(stderr, "[padeops_b200] plan rk=%d bw=%d n=%d axis=%d n1=%lld n3=%lld -> variant %d (%.3f ms)\n", RK, BW, h->n, axis,
                      n1, n3, best, best_ms);
+    g_last_variant = best;
     return cudaSuccess;  // the timed runs already produced `out`
+}
+
+template <int RK, int BW, int M>
+cudaError_t launch_planned(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3,
+                           long long in_slab, long long out_slab, cudaStream_t st, bool make_plan = false) {
+    const int forced_mode = strided_mode(), forced_x = x_threads();
+    const bool forced = (axis == 0) ? forced_x != 0 : forced_mode != 0;
+    if (make_plan) return plan_by_timing<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
+    if (forced) return launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, forced_mode, forced_x);
+    const long long pts = n1 * h->n * n3;
+    if (pts < (1LL << 24)) return launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, 0, 0);
+    {
+        std::lock_guard<std::mutex> lk(g_plan_mutex);
+        for (int i = 0; i < h->nplans; ++i)
+            if (h->plans[i].axis == axis && h->plans[i].n1 == n1 && h->plans[i].n3 == n3)
+                return launch_chunk<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st, h->plans[i].choice, h->plans[i].choice);
+    }
+    if (tuning_enabled()) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone)
+            return plan_by_timing<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
+        cudaGetLastError();
+    }
+    return launch_default<RK, BW, M>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
 }
 
 template <int RK, int BW>
 cudaError_t launch_any(const BandedOp* h, int axis, const double* f, double* out, long long n1, long long n3,
                        long long in_slab, long long out_slab, cudaStream_t st, int force_generic) {
     const bool whole_line_chunked = h->M > 0 && h->n / h->M <= 128;
-    if (h->M == 32 && whole_line_chunked && !force_generic) return launch_planned<RK, BW, 32>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
-    if (h->M == 16 && !force_generic) return launch_planned<RK, BW, 16>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
-    if (h->M == 8 && !force_generic) return launch_planned<RK, BW, 8>(h, axis, f, out, n1, n3, in_slab, out_slab, st);
+    const bool mk = force_generic == 2;     // 2: time the candidates and store the plan (banded_op_plan)
+    if (mk) force_generic = 0;
+    if (h->M == 32 && whole_line_chunked && !force_generic) return launch_planned<RK, BW, 32>(h, axis, f, out, n1, n3, in_slab, out_slab, st, mk);
+    if (h->M == 16 && !force_generic) return launch_planned<RK, BW, 16>(h, axis, f, out, n1, n3, in_slab, out_slab, st, mk);
+    if (h->M == 8 && !force_generic) return launch_planned<RK, BW, 8>(h, axis, f, out, n1, n3, in_slab, out_slab, st, mk);
     // generic
     const int n = h->n;
     const long long tot = n1 * n * n3;
@@ -2026,6 +2074,7 @@ cudaError_t launch_any(const BandedOp* h, int axis, const double* f, double* out
 }  // namespace
 
 int banded_debug_last_variant() { return g_last_variant; }
+void banded_set_tuning(bool on) { g_tuning = on ? 1 : 0; }
 
 // host-only view of the cluster + TMA kernel's launch shape (tests check its invariants without a GPU)
 int banded_debug_ctma_config(int P, int XT, int HB, int HW, int BW, int pc_max, long long* smem_bytes) {
@@ -2122,6 +2171,27 @@ cudaError_t banded_op_apply(const BandedOp* h, int axis, const double* f, double
     const long long out_slab = n1 * (n + (h->op.edge_out ? 1 : 0));
     const cudaError_t e = banded_dispatch(h, axis, f, out, n1, n3, in_slab, out_slab, st, force_generic);
     if (e != cudaSuccess) cudaGetLastError();  // do not leave a stale error for the next launch check to trip over
+    return e;
+}
+
+// Explicit planning: times the kernel candidates for this operator along `axis` of a pencil with extents (na, nb) on scratch
+// arrays of that shape and stores the winner in the handle; later calls on the same shape use it.  Synchronises the device.
+cudaError_t banded_op_plan(const BandedOp* h, int axis, long long na, long long nb, int* chosen) {
+    const int n = h->n;
+    if (chosen) *chosen = 0;
+    if (n <= 1 || na * nb <= 0 || axis < 0 || axis > 2) return cudaSuccess;
+    const size_t planes_in = (size_t)n + ((h->op.edge_in || (h->op.edge_out && h->rk == RK_D2_5)) ? 1 : 0);
+    const size_t planes_out = (size_t)n + (h->op.edge_out ? 1 : 0);
+    double *f = nullptr, *o = nullptr;
+    cudaError_t e = cudaMalloc(&f, sizeof(double) * planes_in * (size_t)na * (size_t)nb);
+    if (e == cudaSuccess) e = cudaMalloc(&o, sizeof(double) * planes_out * (size_t)na * (size_t)nb);
+    if (e == cudaSuccess) e = cudaMemset(f, 0, sizeof(double) * planes_in * (size_t)na * (size_t)nb);
+    if (e == cudaSuccess) e = banded_op_apply(h, axis, f, o, na, nb, nullptr, 2);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && chosen) *chosen = g_last_variant;
+    if (f) cudaFree(f);
+    if (o) cudaFree(o);
+    if (e != cudaSuccess) cudaGetLastError();
     return e;
 }
 

@@ -33,7 +33,8 @@ struct BandedOp {
     ChunkTables tab16{};  // the same matrix cut into 16-point chunks, for the TMA x kernel (valid when has_tab16)
     int has_tab16 = 0;
     double* d_line = nullptr;  // generic path tables (device)
-    // planner memory: winning kernel variant per (axis, n1, n3), filled by the first large call (banded.cu: launch_planned)
+    // planner memory: winning kernel variant per (axis, n1, n3), filled by banded_op_plan (or, with PDO_TUNE=1, by the first
+    // large call on a shape); without a plan the deterministic table of banded.cu: default_variant decides
     static constexpr int kMaxPlans = 8;
     struct Plan { int axis; long long n1, n3; int choice; };
     mutable Plan plans[kMaxPlans];
@@ -49,6 +50,11 @@ void banded_op_destroy(BandedOp* h);
 // that side.  force_generic != 0 routes through the any-n kernels (used by tests to cross-check).
 cudaError_t banded_op_apply(const BandedOp* h, int axis, const double* f, double* out, long long na, long long nb,
                             cudaStream_t stream, int force_generic = 0);
+
+// Times the kernel candidates for `axis` of a pencil with extents (na, nb) on scratch arrays and stores the winner in the handle
+// (FFTW-planner style; explicit, never inside a user call).  Synchronises the device.  *chosen: the variant code.
+cudaError_t banded_op_plan(const BandedOp* h, int axis, long long na, long long nb, int* chosen);
+void banded_set_tuning(bool plan_on_first_call);   // default off (PDO_TUNE=1 turns it on)
 
 // z-slab (distributed line) mode of the strided operators: the periodic line of h->n points (the operator is created for
 // the GLOBAL length) is cut across GPUs into slabs of n_local rows each, f(n1, n_local).  Instead of transposing the field

@@ -265,6 +265,8 @@ int pdo_debug_ctma_config(int P, int XT, int HB, int HW, int BW, int pc_max, lon
 }
 /* Host-only: the rows (bt b d a at, 5n doubles) of the non-periodic system */
 int pdo_debug_np_rows(int kind, int n, int bc1, int bcn, double* rows5n) { return np_build_rows(kind, n, bc1, bcn, rows5n); }
+/* -1 default (on), 0: non-periodic calls keep the one-thread-per-line sweeps, 1: chunked fast path where the line is chunkable */
+int pdo_debug_np_fast(int mode) { np_set_fast_path(mode); return 0; }
 
 int pdo_malloc(void** dptr, size_t bytes) {
     if (int rc = ensure_device()) return rc;
@@ -659,6 +661,41 @@ int pdo_debug_stagg_np_rows(int op, int n, int bot_even, int top_even, int bot_s
     return snp_build_rows(op, n, fl, rows3n);
 }
 
+}  // extern "C"
+
+// ---------------- explicit planning (FFTW-planner style; never inside an operator call) ----------------
+extern "C" {
+static int plan_one(const BandedOp& op, int axis, int na, int nb, int* variant) {
+    if (axis < 0 || axis > 2 || na < 1 || nb < 1) return fail(PDO_E_BADARG, "plan: axis must be 0..2 and the extents positive");
+    int v = 0;
+    PDO_CUDA(banded_op_plan(&op, axis, na, nb, &v));
+    if (variant) *variant = v;
+    return 0;
+}
+/* Times the kernel candidates of this operator along `axis` (0 x, 1 y, 2 z) of a pencil whose other two extents are (na, nb) —
+   the same (na, nb) the dd* / filter* calls take — and stores the winner in the handle: later calls on that shape use it.
+   Without a plan the deterministic table of banded.cu decides.  Synchronises the device; allocates two scratch fields. */
+int pdo_cd10_plan(pdo_cd10_t h, int axis, int na, int nb, int* variant_d1, int* variant_d2) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    if (!h->periodic) return 0;
+    if (int rc = plan_one(h->d1, axis, na, nb, variant_d1)) return rc;
+    return plan_one(h->d2, axis, na, nb, variant_d2);
+}
+int pdo_cd06_plan(pdo_cd06_t h, int axis, int na, int nb, int* variant) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    return h->periodic ? plan_one(h->d1, axis, na, nb, variant) : 0;
+}
+int pdo_cf90_plan(pdo_cf90_t h, int axis, int na, int nb, int* variant) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    return h->periodic ? plan_one(h->op, axis, na, nb, variant) : 0;
+}
+int pdo_gaussian_plan(pdo_gaussian_t h, int axis, int na, int nb, int* variant) {
+    if (!h) return fail(PDO_E_BADARG, "null handle");
+    return h->periodic ? plan_one(h->op, axis, na, nb, variant) : 0;
+}
+/* 0: deterministic dispatch (default); 1: the first large call of an operator on a shape times the candidates itself (the
+   PDO_TUNE=1 behaviour) — synchronises inside that call, so not for captured streams. */
+int pdo_plan_on_first_call(int enable) { banded_set_tuning(enable != 0); return 0; }
 }  // extern "C"
 
 // ---------------- DerivativesMod::derivatives / FiltersMod::filters ----------------

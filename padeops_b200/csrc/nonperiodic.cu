@@ -278,13 +278,28 @@ cudaError_t np_op_create(NpOp* h, int kind, int n, double dx, int* ierr_out) {
             if (e == cudaSuccess) e = cudaMemcpy(d, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice);
             if (e != cudaSuccess) { if (d) cudaFree(d); np_op_destroy(h); return e; }
             h->d_tab[3 * a + b] = d;
+            e = np_fast_create(&h->fast[3 * a + b], kind, n, codes[a], codes[b]);
+            if (e != cudaSuccess) { np_op_destroy(h); return e; }
         }
     return cudaSuccess;
 }
 
 void np_op_destroy(NpOp* h) {
     for (auto& p : h->d_tab) { if (p) cudaFree(p); p = nullptr; }
+    for (auto& t : h->fast) np_fast_destroy(&t);
 }
+
+namespace {
+int g_np_fast = -1;
+bool np_fast_enabled() {
+    if (g_np_fast < 0) {
+        const char* e = std::getenv("PDO_NP_FAST");
+        g_np_fast = (e && std::atoi(e) == 0) ? 0 : 1;
+    }
+    return g_np_fast != 0;
+}
+}  // namespace
+void np_set_fast_path(int mode) { g_np_fast = mode; }
 
 cudaError_t np_op_apply(const NpOp* h, int axis, const double* f, double* out, long long na, long long nb, int bc1, int bcn, cudaStream_t st) {
     if (axis < 0 || axis > 2 || (bc1 != 0 && bc1 != 1 && bc1 != -1) || (bcn != 0 && bcn != 1 && bcn != -1)) return cudaErrorInvalidValue;
@@ -299,6 +314,13 @@ cudaError_t np_op_apply(const NpOp* h, int axis, const double* f, double* out, l
     }
     const double* tab = h->d_tab[3 * slot(bc1) + slot(bcn)];
     if (!tab) return cudaErrorInvalidValue;
+    // chunked fast path: one fused pass (np_chunk.cu); lines it does not cover keep the sweeps below
+    const NpFast& fast = h->fast[3 * slot(bc1) + slot(bcn)];
+    if (fast.ok && np_fast_enabled()) {
+        const cudaError_t e = np_fast_apply(fast, h->kind, h->co, h->n, axis, f, out, n1, n3, bc1, bcn, st);
+        if (e != cudaErrorInvalidConfiguration) return e;
+        cudaGetLastError();
+    }
     if (h->kind == NP_CD06_D1) np_rhs_kernel<NP_CD06_D1><<<gb, 256, 0, st>>>(f, out, n1, h->n, n3, bc1, bcn, h->co);
     else if (h->kind == NP_CD10_D1) np_rhs_kernel<NP_CD10_D1><<<gb, 256, 0, st>>>(f, out, n1, h->n, n3, bc1, bcn, h->co);
     else if (h->kind == NP_CD10_D2) np_rhs_kernel<NP_CD10_D2><<<gb, 256, 0, st>>>(f, out, n1, h->n, n3, bc1, bcn, h->co);

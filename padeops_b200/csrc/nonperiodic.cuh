@@ -125,11 +125,27 @@ int np_build_coefs(int kind, double dx, NpCoefs* out);
 int np_build_table(int kind, int n, int bc1, int bcn, double* tab5n);
 int np_build_rows(int kind, int n, int bc1, int bcn, double* rows5n);   // bt[n] b[n] d[n] a[n] at[n]
 
+// Chunked fast path of one (bc1, bcn) system (np_chunk.cu): three table sets (first / mid / last chunk; sizeof = 3 NpChunkSet,
+// kept as raw doubles so that this header does not pull np_chunk_tables.h in) + the position-dependent separator inverse on the device.
+struct NpFast {
+    bool ok = false;
+    int P = 0, W = 0;
+    double sets[3][(5 * 32 + 2 * 64 + 6)];
+    double* d_G = nullptr;
+};
+cudaError_t np_fast_create(NpFast* t, int kind, int n, int bc1, int bcn);
+void np_fast_destroy(NpFast* t);
+
 struct NpOp {
     int kind = 0, n = 0;
     NpCoefs co{};
     double* d_tab[9] = {};   // device tables for (bc1, bcn) in {0, 1, -1}^2, index 3*slot(bc1) + slot(bcn), slot: 0 -> 0, 1 -> 1, -1 -> 2
+    NpFast fast[9];          // same indexing; ok = false where the line is not chunkable (the sweeps above then do the work)
 };
+cudaError_t np_fast_apply(const NpFast& t, int kind, const NpCoefs& co, int n, int axis, const double* f, double* out, long long n1,
+                          long long n3, int bc1, int bcn, cudaStream_t st);
+// PDO_NP_FAST=0 keeps every non-periodic call on the one-thread-per-line sweeps (tests compare the two paths)
+void np_set_fast_path(int mode);   // -1 environment / default (on), 0 off, 1 on
 cudaError_t np_op_create(NpOp* h, int kind, int n, double dx, int* ierr_out);
 void np_op_destroy(NpOp* h);
 // axis 0: f(n,na,nb); 1: f(na,n,nb); 2: f(na,nb,n).  Device pointers; f and out must not alias.

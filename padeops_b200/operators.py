@@ -70,6 +70,17 @@ class _LineOp:
         n3, n2, n1 = f.shape
         return ((n2, n3), (n1, n3), (n1, n2))[axis]
 
+    def plan(self, axis, na, nb):
+        """Time the kernel candidates for `axis` (0 x, 1 y, 2 z) of a pencil with the other extents (na, nb) and keep the winner
+        in the handle (pdo_*_plan: explicit, set-up time; without it a fixed table picks the kernel).  Returns the variant code(s)."""
+        if self._prefix == "cd10":
+            v1, v2 = C.c_int(0), C.c_int(0)
+            check(lib().pdo_cd10_plan(self._h, int(axis), int(na), int(nb), C.byref(v1), C.byref(v2)))
+            return v1.value, v2.value
+        v = C.c_int(0)
+        check(getattr(lib(), f"pdo_{self._prefix}_plan")(self._h, int(axis), int(na), int(nb), C.byref(v)))
+        return v.value
+
 
 class cd10(_LineOp):
     _prefix = "cd10"

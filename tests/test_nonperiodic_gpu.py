@@ -140,3 +140,73 @@ def test_lstsq_filter_periodic_and_walls(pdo, oracle):
     with pytest.raises(pdo.PadeOpsError) as e:
         pdo.filters().init(gp, True, True, True, "spectral", "cf90", "cf90")
     assert e.value.code == 52
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# chunked fast path (csrc/np_chunk.cu): lines that are a multiple of 32 long take one fused pass; same bar against the oracle, and the
+# two paths of the library against each other
+# ---------------------------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def np_path(pdo):
+    L = pdo.lib()
+    yield lambda mode: L.pdo_debug_np_fast(mode)
+    L.pdo_debug_np_fast(-1)
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("n", [64, 128, 256])
+def test_chunked_fast_path_cd10_all_boundary_codes(pdo, oracle, np_path, axis, n):
+    """ragged cross-sections (partial x tiles, lines that do not fill the last CTA) on purpose"""
+    shape = {0: (5, 13, n), 1: (5, n, 37), 2: (n, 5, 21)}[axis]
+    dx = 1.0 / (n - 1)
+    f = np.random.default_rng(100 * axis + n).standard_normal(shape)
+    fd = _dev(f)
+    h = pdo.cd10()
+    assert h.init(n, dx, periodic_=False) == 0
+    d1 = (h.dd1, h.dd2, h.dd3)[axis]
+    d2 = (h.d2d1, h.d2d2, h.d2d3)[axis]
+    for bc1, bcn in BCS:
+        np_path(1)
+        g1, g2 = d1(fd, bc1_=bc1, bcn_=bcn).cpu().numpy(), d2(fd, bc1_=bc1, bcn_=bcn).cpu().numpy()
+        np_path(0)
+        s1, s2 = d1(fd, bc1_=bc1, bcn_=bcn).cpu().numpy(), d2(fd, bc1_=bc1, bcn_=bcn).cpu().numpy()
+        r1, r2 = oracle.cd10_np(f, dx, axis, 1, bc1, bcn), oracle.cd10_np(f, dx, axis, 2, bc1, bcn)
+        assert _rel(g1, r1) < TOL and _rel(g2, r2) < TOL, (bc1, bcn, _rel(g1, r1), _rel(g2, r2))
+        assert _rel(s1, r1) < TOL and _rel(s2, r2) < TOL
+        assert not np.array_equal(g1, s1) or n < 0      # the two paths associate differently: identical bits would mean one path ran twice
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("n", [128, 256])
+def test_chunked_fast_path_cf90_and_cd06(pdo, oracle, np_path, axis, n):
+    shape = {0: (3, 9, n), 1: (3, n, 41), 2: (n, 3, 19)}[axis]
+    f = np.random.default_rng(7 * axis + n).standard_normal(shape)
+    fd = _dev(f)
+    cf = pdo.cf90()
+    assert cf.init(n, periodic_=False) == 0
+    fil = (cf.filter1, cf.filter2, cf.filter3)[axis]
+    np_path(1)
+    for bc1, bcn in BCS:
+        assert _rel(fil(fd, bc1_=bc1, bcn_=bcn).cpu().numpy(), oracle.cf90_np(f, axis, bc1, bcn)) < TOL, (bc1, bcn)
+    dx = 1.0 / (n - 1)
+    c6 = pdo.cd06()
+    assert c6.init(n, dx, periodic_=False) == 0
+    d = (c6.dd1, c6.dd2, c6.dd3)[axis]
+    assert _rel(d(fd).cpu().numpy(), oracle.cd06_np(f, dx, axis)) < TOL
+
+
+def test_chunked_fast_path_exact_on_quartics_and_large_lines(pdo, np_path):
+    """one-sided rows exact on x^4 (cd10.F90:33-77's closure is 4th-order at the wall), on 1024-point lines along every axis"""
+    import torch
+    n = 1024
+    dx = 1.0 / (n - 1)
+    x = np.arange(n) * dx
+    np_path(1)
+    h = pdo.cd10()
+    assert h.init(n, dx, periodic_=False) == 0
+    for axis, shape in ((0, (2, 40, n)), (1, (2, n, 48)), (2, (n, 2, 48))):
+        sl = [None, None, None]
+        sl[2 - axis] = slice(None)
+        f = np.ascontiguousarray(np.broadcast_to((x ** 4)[tuple(sl)], shape))
+        got = (h.dd1, h.dd2, h.dd3)[axis](torch.from_numpy(f).cuda()).cpu().numpy()
+        assert np.abs(got - np.broadcast_to((4 * x ** 3)[tuple(sl)], shape)).max() < 2e-10, axis
