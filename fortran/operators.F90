@@ -83,14 +83,14 @@ contains
         real(rkind), dimension(decomp%ysz(1), decomp%ysz(2), decomp%ysz(3)), intent(inout), target :: arr
         integer, optional, intent(in) :: numtimes
         integer, dimension(2), optional, intent(in) :: x_bc_, y_bc_, z_bc_
-        integer(c_int), dimension(2) :: x_bc, y_bc, z_bc
+        integer(c_int), dimension(2), target :: x_bc, y_bc, z_bc
         integer(c_int) :: ierr, times2fil
         times2fil = 1; if (present(numtimes)) times2fil = numtimes
         x_bc = 0; if (present(x_bc_)) x_bc = x_bc_
         y_bc = 0; if (present(y_bc_)) y_bc = y_bc_
         z_bc = 0; if (present(z_bc_)) z_bc = z_bc_
         call ensure_handle(decomp)
-        ierr = pdo_operators_filter3d(hops, fil%h, c_loc(arr), times2fil, x_bc, y_bc, z_bc, c_null_ptr)
+        ierr = pdo_operators_filter3d(hops, fil%h, c_loc(arr), times2fil, c_loc(x_bc), c_loc(y_bc), c_loc(z_bc), c_null_ptr)
         if (ierr /= 0) call GracefulExit("padeops_b200: filter3D failed", ierr)
     end subroutine
 
