@@ -225,6 +225,7 @@ class ChunkTables(C.Structure):
 
 _PROTOS["pdo_debug_np_chunk_tables"] = (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.POINTER(C.c_int)])
 _PROTOS["pdo_debug_ctma_config"] = (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)])
+_PROTOS["pdo_debug_igrid_bcs"] = (C.c_int, [C.c_int, C.c_int, C.c_void_p])
 _PROTOS["pdo_debug_np_fast"] = (C.c_int, [C.c_int])
 _PROTOS["pdo_debug_np_rows"] = (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_dp])
 _PROTOS["pdo_debug_np_line_host"] = (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, c_dp, c_dp, C.c_longlong, C.c_longlong])
@@ -234,6 +235,34 @@ _PROTOS["pdo_debug_set_variant"] = (C.c_int, [C.c_int, C.c_int])
 _PROTOS["pdo_debug_last_variant"] = (C.c_int, [])
 
 EXPORTED = sorted(k for k in _PROTOS if not k.startswith("pdo_debug"))
+
+
+_HOOKS_SO = os.path.join(_HERE, "lib", "libpadeops_b200_testhooks.so")
+
+
+class _Library:
+    """The product library plus, for tests only, the separate hooks library: attribute access to a pdo_debug_* name loads
+    libpadeops_b200_testhooks.so (extern "C" wrappers around pdo::hooks::*, csrc/testhooks.cu) on first use.  The product
+    library itself exports no pdo_debug_* symbol, and nothing in this package's public classes touches one."""
+
+    def __init__(self, main):
+        self._main = main
+        self._hooks = None
+
+    def __getattr__(self, name):
+        if name.startswith("pdo_debug"):
+            if self._hooks is None:
+                if not os.path.exists(_HOOKS_SO):
+                    raise PadeOpsError(-1, f"{_HOOKS_SO} not found (test hooks; built by the same make as the library)")
+                H = C.CDLL(_HOOKS_SO, mode=C.RTLD_GLOBAL)
+                for nm, (res, args) in _PROTOS.items():
+                    if nm.startswith("pdo_debug"):
+                        fn = getattr(H, nm)
+                        fn.restype = res
+                        fn.argtypes = args
+                self._hooks = H
+            return getattr(self._hooks, name)
+        return getattr(self._main, name)
 
 
 def lib():
@@ -249,12 +278,14 @@ def lib():
             import torch  # noqa: F401
         except ImportError:
             pass
-        L = C.CDLL(_SO)
+        L = C.CDLL(_SO, mode=C.RTLD_GLOBAL)
         for name, (res, args) in _PROTOS.items():
+            if name.startswith("pdo_debug"):
+                continue
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        _lib = L
+        _lib = _Library(L)
     return _lib
 
 

@@ -225,26 +225,36 @@ int64_t pdo_launch_count(void) { return (int64_t)g_launches.load(); }
 /* Host-only test hook (no device needed): the chunk tables the kernels receive for the cyclic matrix circ[b2 b1 1 b1 b2]
  * of size n cut into chunks of M points.  `out` receives a copy of pdo::ChunkTables (tables.h); returns 0, -1 if (n, M) is
  * not chunkable, PDO_E_BADARG if out_bytes does not match the struct. */
-int pdo_debug_chunk_tables(int n, int M, int bw, double b1, double b2, void* out, int out_bytes) {
+}  // extern "C"
+namespace pdo { namespace hooks {
+int chunk_tables(int n, int M, int bw, double b1, double b2, void* out, int out_bytes) {
     if (!out || out_bytes != (int)sizeof(ChunkTables)) return fail(PDO_E_BADARG, "out_bytes %d != sizeof(ChunkTables) %d", out_bytes, (int)sizeof(ChunkTables));
     ChunkTables t;
     const int rc = build_chunk_tables(n, M, bw, b1, b2, &t);
     std::memcpy(out, &t, sizeof(t));
     return rc;
 }
+}}  // namespace pdo::hooks
+extern "C" {
 
 /* Host-only test hook: the non-periodic closures computed by the SAME __host__ __device__ routines the kernels execute
  * (nonperiodic.cuh), on the host, so that CPU tests can check the transcription of the boundary rows and the LU sweeps.
  * kind: 0 cd10 d1, 1 cd10 d2, 2 cf90.  Not reachable from any public entry point: the API itself needs a GPU. */
-int pdo_debug_np_line_host(int kind, int n, double dx, int bc1, int bcn, int axis, const double* f, double* out, long long na,
+}  // extern "C"
+namespace pdo { namespace hooks {
+int np_line_host(int kind, int n, double dx, int bc1, int bcn, int axis, const double* f, double* out, long long na,
                            long long nb) {
     if (!f || !out || axis < 0 || axis > 2) return fail(PDO_E_BADARG, "bad argument");
     return np_apply_host(kind, n, dx, bc1, bcn, axis, f, out, na, nb);
 }
+}}  // namespace pdo::hooks
+extern "C" {
 
 /* Host-only test hook: chunk tables of the non-periodic system of `kind` (0 cd10 d1, 1 cd10 d2, 2 cf90) with boundary codes
  * (bc1, bcn): sets = 3 x NpChunkSet (first, mid, last) as doubles, G = [P][2W+1][4], meta = {P, W, doubles per set}. */
-int pdo_debug_np_chunk_tables(int kind, int n, int M, int bc1, int bcn, double* sets, double* G, int g_capacity, int* meta) {
+}  // extern "C"
+namespace pdo { namespace hooks {
+int np_chunk_tables(int kind, int n, int M, int bc1, int bcn, double* sets, double* G, int g_capacity, int* meta) {
     if (!sets || !G || !meta) return fail(PDO_E_BADARG, "null argument");
     std::vector<double> rows(5 * (size_t)(n > 0 ? n : 1));
     if (int rc = np_build_rows(kind, n, bc1, bcn, rows.data())) return rc;
@@ -259,14 +269,28 @@ int pdo_debug_np_chunk_tables(int kind, int n, int M, int bc1, int bcn, double* 
     meta[0] = t.P; meta[1] = t.W; meta[2] = (int)(sizeof(NpChunkSet) / sizeof(double));
     return 0;
 }
+}}  // namespace pdo::hooks
+extern "C" {
 /* Host-only: chunks per CTA (0 = no launch shape) and dynamic shared memory of the cluster + TMA strided kernel */
-int pdo_debug_ctma_config(int P, int XT, int HB, int HW, int BW, int pc_max, long long* smem_bytes) {
+}  // extern "C"
+namespace pdo { namespace hooks {
+int ctma_config(int P, int XT, int HB, int HW, int BW, int pc_max, long long* smem_bytes) {
     return banded_debug_ctma_config(P, XT, HB, HW, BW, pc_max, smem_bytes);
 }
+}}  // namespace pdo::hooks
+extern "C" {
 /* Host-only: the rows (bt b d a at, 5n doubles) of the non-periodic system */
-int pdo_debug_np_rows(int kind, int n, int bc1, int bcn, double* rows5n) { return np_build_rows(kind, n, bc1, bcn, rows5n); }
+}  // extern "C"
+namespace pdo { namespace hooks {
+int np_rows(int kind, int n, int bc1, int bcn, double* rows5n) { return np_build_rows(kind, n, bc1, bcn, rows5n); }
+}}  // namespace pdo::hooks
+extern "C" {
 /* -1 default (on), 0: non-periodic calls keep the one-thread-per-line sweeps, 1: chunked fast path where the line is chunkable */
-int pdo_debug_np_fast(int mode) { np_set_fast_path(mode); return 0; }
+}  // extern "C"
+namespace pdo { namespace hooks {
+int np_fast(int mode) { np_set_fast_path(mode); return 0; }
+}}  // namespace pdo::hooks
+extern "C" {
 
 int pdo_malloc(void** dptr, size_t bytes) {
     if (int rc = ensure_device()) return rc;
@@ -651,15 +675,23 @@ int pdo_cd06stagg_ddz_E2E(pdo_cd06stagg_t h, const double* in, double* out, int 
     return apply_snp(h, SNP_D1_E2E, in, out, n1, n2, is_complex, stream);
 }
 // test hooks (host only, not in the public header): the kernel's per-line routine and the tridiagonal rows on the CPU
-int pdo_debug_stagg_np_host(int op, int n, double dx, int bot_even, int top_even, int bot_sided, int top_sided, const double* in, double* out,
+}  // extern "C"
+namespace pdo { namespace hooks {
+int stagg_np_host(int op, int n, double dx, int bot_even, int top_even, int bot_sided, int top_sided, const double* in, double* out,
                             long long ncols) {
     StaggNpFlags fl{bot_even != 0, top_even != 0, bot_sided != 0, top_sided != 0};
     return snp_apply_host(op, n, dx, fl, in, out, ncols);
 }
-int pdo_debug_stagg_np_rows(int op, int n, int bot_even, int top_even, int bot_sided, int top_sided, double* rows3n) {
+}}  // namespace pdo::hooks
+extern "C" {
+}  // extern "C"
+namespace pdo { namespace hooks {
+int stagg_np_rows(int op, int n, int bot_even, int top_even, int bot_sided, int top_sided, double* rows3n) {
     StaggNpFlags fl{bot_even != 0, top_even != 0, bot_sided != 0, top_sided != 0};
     return snp_build_rows(op, n, fl, rows3n);
 }
+}}  // namespace pdo::hooks
+extern "C" {
 
 }  // extern "C"
 
@@ -831,18 +863,30 @@ int pdo_filters_filtery(pdo_filters_t h, const double* f, double* o, int b1, int
 int pdo_filters_filterz(pdo_filters_t h, const double* f, double* o, int b1, int bn, void* s) { return fil_apply(h, 2, f, o, b1, bn, s); }
 
 // test hook (not in the public header): run the any-n kernels even when a chunked path exists
-int pdo_debug_cd10_generic(pdo_cd10_t h, int which, int axis, const double* f, double* df, int na, int nb, void* stream) {
+}  // extern "C"
+namespace pdo { namespace hooks {
+int cd10_generic(pdo_cd10_t h, int which, int axis, const double* f, double* df, int na, int nb, void* stream) {
     if (!h) return fail(PDO_E_BADARG, "null handle");
     PDO_CUDA(banded_op_apply(which == 1 ? &h->d1 : &h->d2, axis, f, df, na, nb, (cudaStream_t)stream, 1));
     g_launches += 2;
     return 0;
 }
+}}  // namespace pdo::hooks
+extern "C" {
 
 // test hook (not in the public header): force a kernel variant, see banded.cuh
-int pdo_debug_last_variant(void) { return banded_debug_last_variant(); }
-int pdo_debug_set_variant(int strided_mode, int x_threads) {
+}  // extern "C"
+namespace pdo { namespace hooks {
+int last_variant(void) { return banded_debug_last_variant(); }
+}}  // namespace pdo::hooks
+extern "C" {
+}  // extern "C"
+namespace pdo { namespace hooks {
+int set_variant(int strided_mode, int x_threads) {
     banded_debug_set_variant(strided_mode, x_threads);
     return 0;
 }
+}}  // namespace pdo::hooks
+extern "C" {
 
 }  // extern "C"

@@ -306,8 +306,10 @@ struct BulkBox {
     long long s_ld2, s_ld3, d_ld2, d_ld3;     // byte strides of the piece indices (inner, outer)
     long long piece_bytes;                    // contiguous run on both sides
     int n_inner, n_outer;                     // pieces = n_inner x n_outer
-    int cpp;                                  // chunks per piece
-    long long nchunks;                        // n_inner * n_outer * cpp
+    int cpp;                                  // chunks per piece (long pieces are cut into kBulkChunk-byte chunks) ...
+    int ppc;                                  // ... or pieces per chunk (short pieces, e.g. 4 KB x-rows, share a stage)
+    int cpo;                                  // chunks per outer index when ppc > 1
+    long long nchunks;
 };
 struct BulkBatch {
     int count;
@@ -341,16 +343,29 @@ __global__ void __launch_bounds__(128) bulk_push_kernel(const __grid_constant__ 
     __syncthreads();
     if (tid == 0) {
         const long long total = b.max_chunks * b.count;     // item -> (box = item % count, chunk = item / count)
-        auto locate = [&](long long item, const char*& src, char*& dst, unsigned& bytes) -> bool {
+        // item -> the pieces of one stage: `np` runs of `pb` bytes each, strides (ss, ds) apart, starting at (src, dst)
+        auto locate = [&](long long item, const char*& src, char*& dst, unsigned& pb, int& np, long long& ss, long long& ds) -> bool {
             const BulkBox& c = b.c[(int)(item % b.count)];
             const long long ch = item / b.count;
             if (ch >= c.nchunks) return false;
+            if (c.ppc > 1) {                                   // several short pieces (consecutive inner indices) per stage
+                const long long po = ch / c.cpo;
+                const long long pi = (ch - po * c.cpo) * c.ppc;
+                const long long left = c.n_inner - pi;
+                np = (int)(left < c.ppc ? left : c.ppc);
+                pb = (unsigned)c.piece_bytes;
+                ss = c.s_ld2; ds = c.d_ld2;
+                src = c.src + pi * c.s_ld2 + po * c.s_ld3;
+                dst = c.dst + pi * c.d_ld2 + po * c.d_ld3;
+                return true;
+            }
             const long long piece = ch / c.cpp;
             const long long sub = ch - piece * c.cpp;
             const long long po = piece / c.n_inner, pi = piece - po * c.n_inner;
             const long long off = sub * (long long)kBulkChunk;
             const long long left = c.piece_bytes - off;
-            bytes = (unsigned)(left < (long long)kBulkChunk ? left : (long long)kBulkChunk);
+            pb = (unsigned)(left < (long long)kBulkChunk ? left : (long long)kBulkChunk);
+            np = 1; ss = ds = 0;
             src = c.src + pi * c.s_ld2 + po * c.s_ld3 + off;
             dst = c.dst + pi * c.d_ld2 + po * c.d_ld3 + off;
             return true;
@@ -358,17 +373,17 @@ __global__ void __launch_bounds__(128) bulk_push_kernel(const __grid_constant__ 
         // my items: blockIdx.x, blockIdx.x + gridDim.x, ...; slot numbers count the items that exist
         long long li = blockIdx.x, si = blockIdx.x;       // next item to load / to store
         long long nl = 0, ns = 0;                          // slots loaded / stored so far
-        auto next_valid = [&](long long& it, const char*& s_, char*& d_, unsigned& n_) -> bool {
+        struct Item { const char* s; char* d; unsigned pb; int np; long long ss, ds; };
+        auto next_valid = [&](long long& it, Item& x) -> bool {
             while (it < total) {
-                if (locate(it, s_, d_, n_)) return true;
+                if (locate(it, x.s, x.d, x.pb, x.np, x.ss, x.ds)) return true;
                 it += gridDim.x;
             }
             return false;
         };
-        const char* ls; char* ld; unsigned ln;
-        const char* ss; char* sd; unsigned sn;
-        bool more_l = next_valid(li, ls, ld, ln);
-        bool more_s = next_valid(si, ss, sd, sn);
+        Item L, S;
+        bool more_l = next_valid(li, L);
+        bool more_s = next_valid(si, S);
         while (more_s) {
             // keep kBulkAhead loads in flight
             while (more_l && nl < ns + kBulkAhead) {
@@ -377,12 +392,13 @@ __global__ void __launch_bounds__(128) bulk_push_kernel(const __grid_constant__ 
                 // commits its own group and at least kBulkStages - kBulkAhead groups are newer than that one
                 if (nl >= kBulkStages) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kBulkStages - kBulkAhead) : "memory");
                 const unsigned bar = d_smem_u32(&full_bar[st]);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(ln) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(d_smem_u32(ring + (size_t)st * kBulkChunk)), "l"(ls), "r"(ln), "r"(bar) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(L.pb * (unsigned)L.np) : "memory");
+                for (int j = 0; j < L.np; ++j)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(d_smem_u32(ring + (size_t)st * kBulkChunk + (size_t)j * L.pb)), "l"(L.s + j * L.ss), "r"(L.pb), "r"(bar) : "memory");
                 ++nl;
                 li += gridDim.x;
-                more_l = next_valid(li, ls, ld, ln);
+                more_l = next_valid(li, L);
             }
             const int st = (int)(ns % kBulkStages);
             const unsigned bar = d_smem_u32(&full_bar[st]);
@@ -393,11 +409,13 @@ __global__ void __launch_bounds__(128) bulk_push_kernel(const __grid_constant__ 
                              : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
                 if (spin > (1u << 26)) __trap();
             }
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(sd), "r"(d_smem_u32(ring + (size_t)st * kBulkChunk)), "r"(sn) : "memory");
+            for (int j = 0; j < S.np; ++j)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(S.d + j * S.ds),
+                             "r"(d_smem_u32(ring + (size_t)st * kBulkChunk + (size_t)j * S.pb)), "r"(S.pb) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             ++ns;
             si += gridDim.x;
-            more_s = next_valid(si, ss, sd, sn);
+            more_s = next_valid(si, S);
         }
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every write of this CTA has been performed
         __threadfence_system();
@@ -589,9 +607,17 @@ int transpose_push(pdo_decomp_s* d, const XGeom& g, const double* src, const Pee
             if (planes_join) { x.piece_bytes = 8LL * c.b1 * c.b2 * c.b3; x.n_inner = 1; x.n_outer = 1; x.s_ld2 = x.d_ld2 = x.s_ld3 = x.d_ld3 = 0; }
             else if (rows_join) { x.piece_bytes = 8LL * c.b1 * c.b2; x.n_inner = 1; x.n_outer = c.b3; x.s_ld2 = x.d_ld2 = 0; x.s_ld3 = 8 * c.s_ld3; x.d_ld3 = 8 * c.d_ld3; }
             else { x.piece_bytes = 8LL * c.b1; x.n_inner = c.b2; x.n_outer = c.b3; x.s_ld2 = 8 * c.s_ld2; x.d_ld2 = 8 * c.d_ld2; x.s_ld3 = 8 * c.s_ld3; x.d_ld3 = 8 * c.d_ld3; }
+            x.ppc = 1; x.cpo = 1;
             if (x.piece_bytes <= 0 || c.b2 <= 0 || c.b3 <= 0) { x.piece_bytes = 0; x.nchunks = 0; x.cpp = 1; x.n_inner = x.n_outer = 1; continue; }
             x.cpp = (int)((x.piece_bytes + kBulkChunk - 1) / kBulkChunk);
             x.nchunks = (long long)x.n_inner * x.n_outer * x.cpp;
+            if (x.piece_bytes * 2 <= (long long)kBulkChunk && x.n_inner > 1) {   // short rows: several consecutive ones share a stage
+                x.ppc = (int)((long long)kBulkChunk / x.piece_bytes);
+                if (x.ppc > x.n_inner) x.ppc = x.n_inner;
+                x.cpo = (x.n_inner + x.ppc - 1) / x.ppc;
+                x.cpp = 1;
+                x.nchunks = (long long)x.cpo * x.n_outer;
+            }
             if (x.nchunks > bb.max_chunks) bb.max_chunks = x.nchunks;
             all_chunks += x.nchunks;
         }
@@ -1016,10 +1042,14 @@ static int allreduce1(double local, double* global, ncclRedOp_t op) {
     PDO_CUDA(cudaMemcpy(global, g_comm.d_scalar + 1, sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
-int pdo_debug_transpose_emulate(int nx, int ny, int nz, int p_row, int p_col, int dir, int w, int path, const double* const* src,
+}  // extern "C"
+namespace pdo { namespace hooks {
+int transpose_emulate(int nx, int ny, int nz, int p_row, int p_col, int dir, int w, int path, const double* const* src,
                                 double* const* dst, void* stream) {
     return pdo::decomp_transpose_emulate(nx, ny, nz, p_row, p_col, dir, w, path, src, dst, (cudaStream_t)stream);
 }
+}}  // namespace pdo::hooks
+extern "C" {
 int pdo_p_maxval(double local, double* global) { return allreduce1(local, global, ncclMax); }
 int pdo_p_sum(double local, double* global) { return allreduce1(local, global, ncclSum); }
 

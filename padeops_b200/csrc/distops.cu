@@ -444,7 +444,9 @@ int pdo_operators_filter3d(pdo_operators_t o, pdo_filters_t fil, double* arr, in
 /* Test hook: the z-slab algorithm on ONE GPU.  f(n1, n) holds whole lines; it is cut into `nslabs` slabs that exchange
  * halo planes and edge pieces through ordinary device buffers, exactly as `nslabs` GPUs would through peer memory.
  * `which`: 0 cd10 d1, 1 cd10 d2, 2 cd06 d1 (handle = pdo_cd10_t / pdo_cd06_t created for n). */
-int pdo_debug_zslab_emulate(void* handle, int which, const double* f, double* out, long long n1, int n, int nslabs, void* stream) {
+}  // extern "C"
+namespace pdo { namespace hooks {
+int zslab_emulate(void* handle, int which, const double* f, double* out, long long n1, int n, int nslabs, void* stream) {
     if (!handle || nslabs < 2 || n % nslabs) return fail(PDO_E_BADARG, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const BandedOp* op = which == 0 ? &((pdo_cd10_t)handle)->d1 : which == 1 ? &((pdo_cd10_t)handle)->d2 : &((pdo_cd06_t)handle)->d1;
@@ -474,5 +476,7 @@ int pdo_debug_zslab_emulate(void* handle, int which, const double* f, double* ou
     for (int s = 0; s < nslabs; ++s) { cudaFree(planes[s]); cudaFree(glo[s]); cudaFree(ghi[s]); }
     return rc;
 }
+}}  // namespace pdo::hooks
+extern "C" {
 
 }  // extern "C"

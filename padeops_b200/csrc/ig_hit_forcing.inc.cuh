@@ -248,7 +248,9 @@ int pdo_hit_forcing_get_rhs(pdo_hit_forcing_t f, double* urhs, double* vrhs, dou
                            new_timestep != 0, (cudaStream_t)stream);
 }
 /* test hook (host only, not in the public header): seeds after init + `updates` further update_seeds, the draw for the current seeds */
-int pdo_debug_hit_draw(double kmin, double kmax, int nwaves, int tid_start, int rand_seed_to_add, int updates, long long seeds[4], int* wx,
+}  // extern "C"
+namespace pdo { namespace hooks {
+int hit_draw(double kmin, double kmax, int nwaves, int tid_start, int rand_seed_to_add, int updates, long long seeds[4], int* wx,
                        int* wy, int* wz) {
     pdo_hit_forcing_s f;
     f.kmin = kmin; f.kmax = kmax; f.nwaves = nwaves;
@@ -265,5 +267,7 @@ int pdo_debug_hit_draw(double kmin, double kmax, int nwaves, int tid_start, int 
     for (int i = 0; i < nwaves; ++i) { wx[i] = f.waves[i]; wy[i] = f.waves[nwaves + i]; wz[i] = f.waves[2 * nwaves + i]; }
     return 0;
 }
+}}  // namespace pdo::hooks
+extern "C" {
 
 }  // extern "C"

@@ -324,12 +324,16 @@ static int spectral_zcomplex(pdo_spectral_t s, double* a, void* stream, int op) 
     });
 }
 // test hook (host only, not in the public header): the z-Fourier tables as the kernels get them, out[2][6][nz] complex
-int pdo_debug_ztables(int nz, double dz, double* out) {
+}  // extern "C"
+namespace pdo { namespace hooks {
+int ztables(int nz, double dz, double* out) {
     if (nz < 2 || (nz & 1) || !out) return fail(PDO_E_BADARG, "bad argument");
     std::vector<double2> t = build_ztables_host(nz, dz);
     std::memcpy(out, t.data(), sizeof(double2) * t.size());
     return 0;
 }
+}}  // namespace pdo::hooks
+extern "C" {
 int pdo_spectral_ddz_c2c_complex_ip(pdo_spectral_t s, double* a, void* st) { return spectral_zcomplex(s, a, st, 0); }
 int pdo_spectral_shiftz_e2c(pdo_spectral_t s, double* a, void* st) { return spectral_zcomplex(s, a, st, 1); }
 int pdo_spectral_shiftz_c2e(pdo_spectral_t s, double* a, void* st) { return spectral_zcomplex(s, a, st, 2); }

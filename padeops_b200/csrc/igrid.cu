@@ -578,12 +578,16 @@ static void ig_fill_bcs(int bc[12][2], int bot_wall, int top_wall) {
     }
 }
 /* test hook (host only): the stencil codes for (botWall, topWall), order w u v WdUdz WdVdz WdWdz WW UW VW dUdz dVdz dWdz, (bottom, top) each */
-int pdo_debug_igrid_bcs(int bot_wall, int top_wall, int* out24) {
+}  // extern "C"
+namespace pdo { namespace hooks {
+int igrid_bcs(int bot_wall, int top_wall, int* out24) {
     int bc[12][2] = {};
     ig_fill_bcs(bc, bot_wall, top_wall);
     for (int q = 0; q < 12; ++q) { out24[2 * q] = bc[q][0]; out24[2 * q + 1] = bc[q][1]; }
     return 0;
 }
+}}  // namespace pdo::hooks
+extern "C" {
 
 // From (u, v, w) on the x-pencils to a consistent state (igrid.F90:625-655): transforms, dealiasing, projection, back to
 // physical space, interpolations and the velocity gradients.  u, v, w: host or device.
@@ -749,12 +753,16 @@ int pdo_igrid_enable_sgs(pdo_igrid_t g, int sgs_model_id, double csgs, int expli
     return 0;
 }
 /* test hook (host only): nu = cmodel * kernel for one point, and S_ij */
-int pdo_debug_sgs_point(int mid, double cmodel, double cx, double cy, double cz, const double* d9, double* nu, double* S6) {
+}  // extern "C"
+namespace pdo { namespace hooks {
+int sgs_point(int mid, double cmodel, double cx, double cy, double cz, const double* d9, double* nu, double* S6) {
     SgsConst c{mid, cmodel, cx, cy, cz};
     sgs_sij(d9, S6);
     *nu = c.cmodel * sgs_kernel_point(c, d9, S6);
     return 0;
 }
+}}  // namespace pdo::hooks
+extern "C" {
 /* the forcing object of a handle with useHITForcing (borrowed; e.g. for pdo_hit_forcing_set_wavenumbers before a time step) */
 pdo_hit_forcing_t pdo_igrid_hit_forcing(pdo_igrid_t g) { return g ? g->hit : nullptr; }
 int pdo_igrid_enable_hit_forcing(pdo_igrid_t g, double kmin, double kmax, int nwaves, double eps_amplitude, int rand_seed_to_add) {

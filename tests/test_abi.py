@@ -25,6 +25,24 @@ def test_header_symbols_are_exported(pdo):
     assert set(declared) == set(_lib.EXPORTED), set(declared) ^ set(_lib.EXPORTED)
 
 
+def test_product_library_exports_the_header_and_nothing_else_in_c(pdo):
+    """The C symbols of libpadeops_b200.so are exactly the functions of include/padeops_b200.h: no pdo_debug_* test hook ships in
+    the product (they live in libpadeops_b200_testhooks.so, wrappers around pdo::hooks::* C++ functions), and the hooks library
+    exports nothing but those wrappers."""
+    import subprocess
+    from padeops_b200 import _lib
+
+    def c_exports(path):
+        out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+        return {l.split()[-1] for l in out.splitlines() if " T " in l and l.split()[-1].startswith("pdo_")}
+    prod = c_exports(pdo.library_path())
+    assert not [s for s in prod if s.startswith("pdo_debug")], sorted(s for s in prod if s.startswith("pdo_debug"))
+    assert prod == set(_declared_symbols()), sorted(prod ^ set(_declared_symbols()))
+    hooks = c_exports(_lib._HOOKS_SO)
+    assert hooks and all(s.startswith("pdo_debug_") for s in hooks)
+    assert hooks == {k for k in _lib._PROTOS if k.startswith("pdo_debug")}
+
+
 def test_no_cpu_fallback(pdo):
     import torch
     if torch.cuda.is_available():
