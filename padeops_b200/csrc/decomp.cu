@@ -588,7 +588,10 @@ int transpose_push(pdo_decomp_s* d, const XGeom& g, const double* src, const Pee
         if (m != me && rows * c.b1 * 8 > max_box_bytes) max_box_bytes = rows * c.b1 * 8;
     }
     if (plane == kPlaneAuto) plane = plane_from_env();
-    if (plane == kPlaneAuto) plane = (vec && max_box_bytes >= (1LL << 20)) ? kPlaneBulk : kPlaneSm;
+    // measured at 1024^3 (profiles/r02o_transposes_8gpu.jsonl, r02m_transposes_2gpu.jsonl): with 4 or 8 peers the TMA bulk push
+    // keeps every link busy (0.70-0.75 of NVLink on 1x8 and 2x4, copy engines 0.45-0.68, store kernel 0.37-0.67); between two
+    // GPUs one copy-engine stream per direction already runs at 0.85 (bulk 0.77)
+    if (plane == kPlaneAuto) plane = (max_box_bytes < (1LL << 20)) ? kPlaneSm : ((vec && np >= 3) ? kPlaneBulk : kPlaneCe);
     if (plane == kPlaneBulk && !vec) plane = kPlaneSm;    // bulk copies need 16-byte aligned runs
     if (plane == kPlaneBulk) {
         BulkBatch bb;
