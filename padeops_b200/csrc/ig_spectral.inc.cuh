@@ -154,8 +154,12 @@ int spectral_dealias(pdo_spectral_s* s, double2* fhat, cudaStream_t st) {
         if (int rc = decomp_transpose_device(spec, 2, (const double*)fhat, (double*)work, 2, st)) return rc;  // take_fftz
     }
     if (int rc = fft3d_z_inplace(s->ft, work, -1, st)) return rc;
-    if (int rc = spectral_mask_z(s, work, s->normfactz, st)) return rc;
-    if (int rc = fft3d_z_inplace(s->ft, work, +1, st)) return rc;  // take_ifftz
+    if (fft3d_own_z(s->ft)) {   // the mask and 1/nz ride on the first load of the inverse pass
+        if (int rc = fft3d_z_pro(s->ft, work, work, +1, s->gx, s->gyz, s->gz, s->normfactz, st)) return rc;
+    } else {
+        if (int rc = spectral_mask_z(s, work, s->normfactz, st)) return rc;
+        if (int rc = fft3d_z_inplace(s->ft, work, +1, st)) return rc;  // take_ifftz
+    }
     if (s->p_col > 1) return decomp_transpose_device(spec, 3, (const double*)work, (double*)fhat, 2, st);
     return 0;
 }
@@ -163,8 +167,12 @@ int spectral_dealias(pdo_spectral_s* s, double2* fhat, cudaStream_t st) {
 int spectral_dealias_edge(pdo_spectral_s* s, double2* fE, cudaStream_t st) {
     if (!s->periodicInZ) return 0;  // the reference does nothing on this branch (spectral.F90:348)
     if (int rc = fft3d_z_inplace(s->ft, fE, -1, st)) return rc;
-    if (int rc = spectral_mask_z(s, fE, s->normfactz, st)) return rc;
-    if (int rc = fft3d_z_inplace(s->ft, fE, +1, st)) return rc;
+    if (fft3d_own_z(s->ft)) {
+        if (int rc = fft3d_z_pro(s->ft, fE, fE, +1, s->gx, s->gyz, s->gz, s->normfactz, st)) return rc;
+    } else {
+        if (int rc = spectral_mask_z(s, fE, s->normfactz, st)) return rc;
+        if (int rc = fft3d_z_inplace(s->ft, fE, +1, st)) return rc;
+    }
     const size_t plane = (size_t)s->si.zsz[0] * s->si.zsz[1];
     PDO_CUDA(cudaMemcpyAsync(fE + plane * s->nz, fE, sizeof(double2) * plane, cudaMemcpyDeviceToDevice, st));  // :361
     return 0;

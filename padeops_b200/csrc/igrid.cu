@@ -137,6 +137,12 @@ struct pdo_igrid_s {
     double2 *cur[3];
     double2 *whatC, *uEhat, *vEhat, *d2u, *d2v, *d2w;
     double2 *yC[2], *yE[2], *zC[2], *zE[2];
+    // terms of the advection right-hand side, each in its own y-pencil array until ONE assembly pass per component sums them,
+    // applies the -1/2 and adds the viscous term (replaces the reference's chain of in-place adds, igrid.F90:1572-1679, 1914-1941).
+    // cell: 0 A_u 1 P_u 2 F_uu 3 B_u 4 A_v 5 P_v 6 F_vv 7 B_v 8 F_uv; edge: 0 A_w 1 P_w 2 B_w 3 F_uEw 4 F_vEw
+    double2 *TC[9] = {}, *TE[5] = {};
+    struct AsmTerm { const double2* p; int kind; };   // kind 0: + p, 1: + i k1 p, 2: + i k2 p
+    struct AsmDesc { AsmTerm t[5]; int n; } asmd[3];
 };
 
 namespace {
@@ -188,20 +194,20 @@ inline int zcommitE(pdo_igrid_s* g, const double2* z, double2* ydst, cudaStream_
 #define ZOPB(fn, in, out, q) IG(fn(g->ops, (const double*)(in), (double*)(out), 1, g->bc[q][0], g->bc[q][1], st))
 enum { BC_W = 0, BC_U, BC_V, BC_WdUdz, BC_WdVdz, BC_WdWdz, BC_WW, BC_UW, BC_VW, BC_dUdz, BC_dVdz, BC_dWdz };
 
-// out = a*b (+ c*d)
-int mul2(double* out, const double* a, const double* b, const double* c, const double* d, long long n, cudaStream_t st) {
-    if (c) return launch_ew(n, st, [=] __device__(long long i) { out[i] = a[i] * b[i] + c[i] * d[i]; });
-    return launch_ew(n, st, [=] __device__(long long i) { out[i] = a[i] * b[i]; });
+// fft(a*b (+ c*d)) on the cell (E = false) or edge grid: the product is formed on the first load of the x pass
+int fft_mul2(pdo_igrid_s* g, bool edge, double2* out, const double* a, const double* b, const double* c, const double* d, cudaStream_t st) {
+    RealPro rp;
+    rp.p[0] = a; rp.p[1] = b; rp.p[2] = c; rp.p[3] = d;
+    rp.mode = c ? 2 : 1;
+    return fft3d_forward_xy_pro(edge ? g->spE->ft : g->spC->ft, rp, out, st);
 }
-// out = (a - b) * c  (+ (d - e) * f): the rotational form's products (igrid.F90:1527-1549: "T = dvdx - dudy; T = T*v")
-int muldiff(double* out, const double* a, const double* b, const double* c, const double* d, const double* e, const double* f, long long n,
-            cudaStream_t st) {
-    if (d) return launch_ew(n, st, [=] __device__(long long i) {
-        const double t1 = (a[i] - b[i]) * c[i];
-        const double t2 = (d[i] - e[i]) * f[i];
-        out[i] = t1 + t2;
-    });
-    return launch_ew(n, st, [=] __device__(long long i) { out[i] = (a[i] - b[i]) * c[i]; });
+// fft((a - b)*c (+ (d - e)*f))
+int fft_muldiff(pdo_igrid_s* g, bool edge, double2* out, const double* a, const double* b, const double* c, const double* d, const double* e,
+                const double* f, cudaStream_t st) {
+    RealPro rp;
+    rp.p[0] = a; rp.p[1] = b; rp.p[2] = c; rp.p[3] = d; rp.p[4] = e; rp.p[5] = f;
+    rp.mode = d ? 4 : 3;
+    return fft3d_forward_xy_pro(edge ? g->spE->ft : g->spC->ft, rp, out, st);
 }
 // dst += src (complex arrays viewed as doubles)
 int cadd(double2* dst, const double2* src, long long n, cudaStream_t st) {
@@ -268,18 +274,16 @@ int ig_interp_primitive(pdo_igrid_s* g, cudaStream_t st) {
 int ig_compute_duidxj(pdo_igrid_s* g, cudaStream_t st) {
     pdo_spectral_s *C = g->spC, *E = g->spE;
     const bool visc = !g->prm.is_inviscid;
-    // i k f goes into a scratch array that nobody reads again: the 1/(nx ny) of the inverse is folded into that pass and
-    // the inverse transform consumes the scratch directly (no intent(in) staging copy)
+    // i k f and the 1/(nx ny) of the inverse ride on the first load of the inverse y pass (fft2d.cu); on the cuFFT path they are the
+    // one pointwise pass that stages the intent(in) input
     const double nf2 = 1.0 / ((double)g->prm.nx * (double)g->prm.ny);
     auto dC = [&](int which, const double2* fhat, double* out) -> int {
         if (!out) return 0;
-        IG(spectral_mtimes(C, which, fhat, g->yC[0], st, nf2));
-        return fft3d_backward_yx_scratch(C->ft, g->yC[0], out, st);
+        return fft3d_backward_yx_mul(C->ft, fhat, which, which == 1 ? C->k1y : C->k2, nf2, false, out, st);
     };
     auto dE = [&](int which, const double2* fhat, double* out) -> int {
         if (!out) return 0;
-        IG(spectral_mtimes(E, which, fhat, g->yE[0], st, nf2));
-        return fft3d_backward_yx_scratch(E->ft, g->yE[0], out, st);
+        return fft3d_backward_yx_mul(E->ft, fhat, which, which == 1 ? E->k1y : E->k2, nf2, false, out, st);
     };
     IG(dC(1, g->cur[0], g->gradC[0])); IG(dE(1, g->uEhat, g->gradE[0]));
     IG(dC(2, g->cur[0], g->gradC[1])); IG(dE(2, g->uEhat, g->gradE[1]));
@@ -334,97 +338,81 @@ int ig_compute_duidxj(pdo_igrid_s* g, cudaStream_t st) {
     return 0;
 }
 
-// ---- igrid.F90:1572-1679 into (ru, rv, rw)
-int ig_nonlinear_skew(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStream_t st) {
-    pdo_spectral_s *C = g->spC, *E = g->spE;
-    double *T1C = g->rbC[0], *T1E = g->rbE[0];
-    double2 *fT1C = g->yC[0], *fT1E = g->yE[0], *fT2E = g->yE[1];
+// ---- igrid.F90:1572-1679: the terms of (ru, rv, rw), left in TC / TE with the assembly recipes in g->asmd
+int ig_nonlinear_skew(pdo_igrid_s* g, cudaStream_t st) {
+    double2 *fT1C = g->yC[0], *fT1E = g->yE[0];
+    double2 **TC = g->TC, **TE = g->TE;
     double **GC = g->gradC, **GE = g->gradE;
     const double2* z = nullptr;
     double2* t = nullptr;
     // u_rhs = interp_E2C(fft(dudz w)) + fft(dudx u + dudy v); same for v
     for (int c = 0; c < 2; ++c) {
-        double2* r = c == 0 ? ru : rv;
-        IG(mul2(T1C, GC[3 * c + 0], g->u, GC[3 * c + 1], g->v, g->nRC, st));
-        IG(mul2(T1E, GE[3 * c + 2], g->w, nullptr, nullptr, g->nRE, st));
-        IG(fftC(g, T1C, fT1C, st));
-        IG(fftE(g, T1E, fT1E, st));
+        IG(fft_mul2(g, false, TC[4 * c + 1], GC[3 * c + 0], g->u, GC[3 * c + 1], g->v, st));
+        IG(fft_mul2(g, true, fT1E, GE[3 * c + 2], g->w, nullptr, nullptr, st));
         IG(zviewE(g, fT1E, g->zE[0], &z, st));
-        t = ztarget(g, r, g->zC[0]);
+        t = ztarget(g, TC[4 * c + 0], g->zC[0]);
         ZOPB(pdo_pade6stagg_interpz_E2C, z, t, c == 0 ? BC_WdUdz : BC_WdVdz);
-        IG(zcommitC(g, t, r, st));
-        IG(cadd(r, fT1C, g->nYC, st));
+        IG(zcommitC(g, t, TC[4 * c + 0], st));
     }
     // w_rhs = interp_C2E(fft(dwdz wC)) + fft(dwdx uE + dwdy vE)
-    IG(mul2(T1E, GE[6], g->uE, GE[7], g->vE, g->nRE, st));
-    IG(fftE(g, T1E, fT2E, st));
-    IG(mul2(T1C, GC[8], g->wC, nullptr, nullptr, g->nRC, st));
-    IG(fftC(g, T1C, fT1C, st));
+    IG(fft_mul2(g, true, TE[1], GE[6], g->uE, GE[7], g->vE, st));
+    IG(fft_mul2(g, false, fT1C, GC[8], g->wC, nullptr, nullptr, st));
     IG(zviewC(g, fT1C, g->zC[0], &z, st));
-    t = ztarget(g, rw, g->zE[0]);
+    t = ztarget(g, TE[0], g->zE[0]);
     ZOPB(pdo_pade6stagg_interpz_C2E, z, t, BC_WdWdz);
-    IG(zcommitE(g, t, rw, st));
-    IG(cadd(rw, fT2E, g->nYE, st));
+    IG(zcommitE(g, t, TE[0], st));
     // conservative half: d(uu)/dx, d(vv)/dy, d(wC wC)/dz, d(uv)/dy & /dx, d(uE w)/dz & /dx, d(vE w)/dz & /dy
-    IG(mul2(T1C, g->u, g->u, nullptr, nullptr, g->nRC, st));
-    IG(fftC(g, T1C, fT1C, st));
-    IG(cadd_ik(C, 1, ru, fT1C, st));
-    IG(mul2(T1C, g->v, g->v, nullptr, nullptr, g->nRC, st));
-    IG(fftC(g, T1C, fT1C, st));
-    IG(cadd_ik(C, 2, rv, fT1C, st));
-    IG(mul2(T1C, g->wC, g->wC, nullptr, nullptr, g->nRC, st));
-    IG(fftC(g, T1C, fT1C, st));
+    IG(fft_mul2(g, false, TC[2], g->u, g->u, nullptr, nullptr, st));
+    IG(fft_mul2(g, false, TC[6], g->v, g->v, nullptr, nullptr, st));
+    IG(fft_mul2(g, false, fT1C, g->wC, g->wC, nullptr, nullptr, st));
     IG(zviewC(g, fT1C, g->zC[0], &z, st));
-    t = ztarget(g, fT1E, g->zE[0]);
+    t = ztarget(g, TE[2], g->zE[0]);
     ZOPB(pdo_pade6stagg_ddz_C2E, z, t, BC_WW);
-    IG(zcommitE(g, t, fT1E, st));
-    IG(cadd(rw, fT1E, g->nYE, st));
-    IG(mul2(T1C, g->u, g->v, nullptr, nullptr, g->nRC, st));
-    IG(fftC(g, T1C, fT1C, st));
-    IG(cadd_ik(C, 2, ru, fT1C, st));
-    IG(cadd_ik(C, 1, rv, fT1C, st));
+    IG(zcommitE(g, t, TE[2], st));
+    IG(fft_mul2(g, false, TC[8], g->u, g->v, nullptr, nullptr, st));
     for (int c = 0; c < 2; ++c) {
-        IG(mul2(T1E, c == 0 ? g->uE : g->vE, g->w, nullptr, nullptr, g->nRE, st));
-        IG(fftE(g, T1E, fT1E, st));
-        IG(zviewE(g, fT1E, g->zE[0], &z, st));
-        t = ztarget(g, fT1C, g->zC[0]);
+        IG(fft_mul2(g, true, TE[3 + c], c == 0 ? g->uE : g->vE, g->w, nullptr, nullptr, st));
+        IG(zviewE(g, TE[3 + c], g->zE[0], &z, st));
+        t = ztarget(g, TC[4 * c + 3], g->zC[0]);
         ZOPB(pdo_pade6stagg_ddz_E2C, z, t, c == 0 ? BC_UW : BC_VW);
-        IG(zcommitC(g, t, fT1C, st));
-        IG(cadd(c == 0 ? ru : rv, fT1C, g->nYC, st));
-        IG(cadd_ik(E, c == 0 ? 1 : 2, rw, fT1E, st));
+        IG(zcommitC(g, t, TC[4 * c + 3], st));
     }
+    // the order of the sums is the reference's order of in-place adds
+    g->asmd[0] = {{{TC[0], 0}, {TC[1], 0}, {TC[2], 1}, {TC[8], 2}, {TC[3], 0}}, 5};
+    g->asmd[1] = {{{TC[4], 0}, {TC[5], 0}, {TC[6], 2}, {TC[8], 1}, {TC[7], 0}}, 5};
+    g->asmd[2] = {{{TE[0], 0}, {TE[1], 0}, {TE[2], 0}, {TE[3], 1}, {TE[4], 2}}, 5};
     return 0;
 }
 
-// ---- igrid.F90:1527-1555 into (ru, rv, rw): u x omega; the products with w live on the edge grid and come back through
-// interpz_E2C.  Gradient slots: C 1 dudy, 3 dvdx; E 2 dudz, 5 dvdz, 6 dwdx, 7 dwdy.
-int ig_nonlinear_rot(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStream_t st) {
-    double *T1C = g->rbC[0], *T1E = g->rbE[0];
-    double2 *fT1C = g->yC[0], *fT1E = g->yE[0];
+// ---- igrid.F90:1527-1555: u x omega; the products with w live on the edge grid and come back through interpz_E2C.
+// Gradient slots: C 1 dudy, 3 dvdx; E 2 dudz, 5 dvdz, 6 dwdx, 7 dwdy.
+int ig_nonlinear_rot(pdo_igrid_s* g, cudaStream_t st) {
+    double2* fT1E = g->yE[0];
+    double2 **TC = g->TC, **TE = g->TE;
     double **GC = g->gradC, **GE = g->gradE;
     const double2* z = nullptr;
     double2* t = nullptr;
     for (int c = 0; c < 2; ++c) {
-        double2* r = c == 0 ? ru : rv;
         // c = 0: (dvdx - dudy) v and (dwdx - dudz) w;   c = 1: (dudy - dvdx) u and (dwdy - dvdz) w
-        if (c == 0) IG(muldiff(T1C, GC[3], GC[1], g->v, nullptr, nullptr, nullptr, g->nRC, st));
-        else IG(muldiff(T1C, GC[1], GC[3], g->u, nullptr, nullptr, nullptr, g->nRC, st));
-        IG(fftC(g, T1C, fT1C, st));
-        if (c == 0) IG(muldiff(T1E, GE[6], GE[2], g->w, nullptr, nullptr, nullptr, g->nRE, st));
-        else IG(muldiff(T1E, GE[7], GE[5], g->w, nullptr, nullptr, nullptr, g->nRE, st));
-        IG(fftE(g, T1E, fT1E, st));
+        if (c == 0) IG(fft_muldiff(g, false, TC[1], GC[3], GC[1], g->v, nullptr, nullptr, nullptr, st));
+        else IG(fft_muldiff(g, false, TC[5], GC[1], GC[3], g->u, nullptr, nullptr, nullptr, st));
+        if (c == 0) IG(fft_muldiff(g, true, fT1E, GE[6], GE[2], g->w, nullptr, nullptr, nullptr, st));
+        else IG(fft_muldiff(g, true, fT1E, GE[7], GE[5], g->w, nullptr, nullptr, nullptr, st));
         IG(zviewE(g, fT1E, g->zE[0], &z, st));
-        t = ztarget(g, r, g->zC[0]);
+        t = ztarget(g, TC[4 * c + 0], g->zC[0]);
         ZOP(pdo_pade6stagg_interpz_E2C, z, t);
-        IG(zcommitC(g, t, r, st));
-        IG(cadd(r, fT1C, g->nYC, st));
+        IG(zcommitC(g, t, TC[4 * c + 0], st));
     }
     // w_rhs = fft((dudz - dwdx) uE + (dvdz - dwdy) vE)
-    IG(muldiff(T1E, GE[2], GE[6], g->uE, GE[5], GE[7], g->vE, g->nRE, st));
-    return fftE(g, T1E, rw, st);
+    IG(fft_muldiff(g, true, TE[1], GE[2], GE[6], g->uE, GE[5], GE[7], g->vE, st));
+    g->asmd[0] = {{{TC[0], 0}, {TC[1], 0}}, 2};
+    g->asmd[1] = {{{TC[4], 0}, {TC[5], 0}}, 2};
+    g->asmd[2] = {{{TE[1], 0}}, 1};
+    return 0;
 }
 
-// rhs = -half*rhs (skew-symmetric form only), then addViscousTerm (igrid.F90:1663-1665, 1914-1941), one pass per component
+// rhs = -half * (sum of the terms) (skew-symmetric form; +1 for the rotational one), then addViscousTerm (igrid.F90:1663-1665,
+// 1914-1941): ONE pass per component over its terms
 int ig_finish_rhs(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStream_t st) {
     const bool visc = !g->prm.is_inviscid;
     const double scale = g->prm.rotational_advection ? 1.0 : -0.5;
@@ -436,11 +424,23 @@ int ig_finish_rhs(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStr
         const double2* d2 = c == 0 ? g->d2u : (c == 1 ? g->d2v : g->d2w);
         const int n1 = s->si.ysz[0], n2 = s->si.ysz[1];
         const double *k1 = s->k1y, *k2 = s->k2;
+        const pdo_igrid_s::AsmDesc D = g->asmd[c];
         IG(launch_ew(vol(s->si.ysz), st, [=] __device__(long long i) {
-            double2 a = r[i];
+            const double ka = k1[(int)(i % n1)], kb = k2[(int)((i / n1) % n2)];
+            double2 a = D.t[0].p[i];
+#pragma unroll
+            for (int t = 1; t < 5; ++t) {
+                if (t < D.n) {
+                    const double2 q = D.t[t].p[i];
+                    if (D.t[t].kind == 0) { a.x += q.x; a.y += q.y; }
+                    else {
+                        const double kv = D.t[t].kind == 1 ? ka : kb;
+                        a.x += -kv * q.y; a.y += kv * q.x;
+                    }
+                }
+            }
             a.x = scale * a.x; a.y = scale * a.y;
             if (visc) {
-                const double ka = k1[(int)(i % n1)], kb = k2[(int)((i / n1) % n2)];
                 const double ksq = ka * ka + kb * kb;  // kabs_sq = k1**2 + k2**2 (spectral.F90:1093-1099)
                 const double2 q = f[i], dd = d2[i];
                 a.x += oneByRe * (-ksq * q.x + dd.x);
@@ -455,8 +455,8 @@ int ig_finish_rhs(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStr
 #include "ig_sgs.inc.cuh"
 
 int ig_populate_rhs(pdo_igrid_s* g, double2** r, cudaStream_t st) {
-    if (g->prm.rotational_advection) IG(ig_nonlinear_rot(g, r[0], r[1], r[2], st));
-    else IG(ig_nonlinear_skew(g, r[0], r[1], r[2], st));
+    if (g->prm.rotational_advection) IG(ig_nonlinear_rot(g, st));
+    else IG(ig_nonlinear_skew(g, st));
     IG(ig_finish_rhs(g, r[0], r[1], r[2], st));
     if (g->sgs_on) IG(ig_sgs_rhs(g, r[0], r[1], r[2], st));   // Step 6 (igrid.F90:1866-1871)
     if (g->hit)   // Step 8 (igrid.F90:1907-1910)
@@ -664,6 +664,13 @@ int pdo_igrid_init(pdo_igrid_t* h, const pdo_igrid_params* p, const double* u, c
         for (int c = 0; c < 3; ++c) { g->S[s][c] = nullptr; if (s < nslots) AL(g->S[s][c], c < 2 ? g->nYC : g->nYE); }
     for (int c = 0; c < 3; ++c) { AL(g->R[c], c < 2 ? g->nYC : g->nYE); g->RX[c] = nullptr; if (p->time_stepping_scheme == 2) AL(g->RX[c], c < 2 ? g->nYC : g->nYE); }
     AL(g->whatC, g->nYC); AL(g->uEhat, g->nYE); AL(g->vEhat, g->nYE);
+    {   // right-hand-side terms (see TC / TE): the rotational form has two per horizontal component and one for w
+        const bool rot = p->rotational_advection != 0;
+        const bool needTC[9] = {true, true, !rot, !rot, true, true, !rot, !rot, !rot};
+        const bool needTE[5] = {!rot, true, !rot, !rot, !rot};
+        for (int i = 0; i < 9; ++i) if (needTC[i]) AL(g->TC[i], g->nYC);
+        for (int i = 0; i < 5; ++i) if (needTE[i]) AL(g->TE[i], g->nYE);
+    }
     g->d2u = g->d2v = g->d2w = nullptr;
     if (visc) { AL(g->d2u, g->nYC); AL(g->d2v, g->nYC); AL(g->d2w, g->nYE); }
 #undef AL

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fft2d.cuh"
 
 using namespace pdo;
 
@@ -37,14 +38,35 @@ __global__ void scale_kernel(double* __restrict__ a, long long n, double s) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] *= s;
 }
 
-// out = in * s, optionally zeroing the x-Nyquist column i == inyq (complex array with first extent n1)
-__global__ void copy_scale_oddball_kernel(const double2* __restrict__ in, double2* __restrict__ out, long long n, int n1,
-                                          int inyq, double s) {
+// out = in * s (* i k when ktab: k along index 1 (which == 1) or 2 of a complex array with extents n1, n2, ...), optionally zeroing
+// the x-Nyquist column i == inyq
+__global__ void copy_scale_oddball_kernel(const double2* __restrict__ in, double2* __restrict__ out, long long n, int n1, int n2,
+                                          int inyq, double s, int which, const double* __restrict__ ktab) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         double2 v = in[i];
-        if (inyq >= 0 && (int)(i % n1) == inyq) { v.x = 0.0; v.y = 0.0; }
-        else { v.x *= s; v.y *= s; }
+        const int i1 = (int)(i % n1);
+        if (inyq >= 0 && i1 == inyq) { v.x = 0.0; v.y = 0.0; }
+        else if (which) {
+            const double kv = (which == 1 ? ktab[i1] : ktab[(int)((i / n1) % n2)]) * s;
+            v = make_double2(-kv * v.y, kv * v.x);
+        } else { v.x *= s; v.y *= s; }
         out[i] = v;
+    }
+}
+
+// the products of fft2d.cuh's RealPro as a stand-alone pass (cuFFT path)
+__global__ void real_pro_kernel(RealPro pro, double* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double a = pro.p[0][i];
+        double r = a;
+        switch (pro.mode) {
+            case 1: r = a * pro.p[1][i]; break;
+            case 2: r = a * pro.p[1][i] + pro.p[2][i] * pro.p[3][i]; break;
+            case 3: r = (a - pro.p[1][i]) * pro.p[2][i]; break;
+            case 4: { const double t1 = (a - pro.p[1][i]) * pro.p[2][i]; const double t2 = (pro.p[3][i] - pro.p[4][i]) * pro.p[5][i]; r = t1 + t2; break; }
+            default: break;
+        }
+        out[i] = r;
     }
 }
 
@@ -97,7 +119,10 @@ struct pdo_fft3d_s {
     cufftHandle plan2d_f = 0, plan2d_b = 0, planx_f = 0, planx_b = 0, plany = 0, planz = 0;
     bool has2d = false, hasx = false, hasy = false, hasz = false;
     double2 *bufX = nullptr, *bufY = nullptr, *bufZ = nullptr;
+    double* rtmp = nullptr;   // real x-pencil scratch of the cuFFT path's product pass (allocated on first use)
     double normfactor, normfactor2d;
+    // hand-written passes (fft2d.cu): slab grids with power-of-two extents; cuFFT otherwise
+    bool own_xy = false, own_z = false;
 };
 
 namespace {
@@ -115,7 +140,18 @@ int y_pass(pdo_fft3d_s* f, double2* a, int dir, cudaStream_t st) {  // per-plane
 }
 
 // real x-pencil → complex y-pencil (spectral decomp), written to `outY`
+int own_y_pass(pdo_fft3d_s* f, const double2* in, double2* out, int dir, const FftPro& pro, cudaStream_t st) {
+    const long long nxh = f->si.ysz[0], ny = f->si.ysz[1];
+    return fft2d_cols((int)ny, nxh, f->si.ysz[2], nxh, nxh * ny, in, out, dir, pro, st);
+}
+
 int forward_xy(pdo_fft3d_s* f, const double* in, double2* outY, cudaStream_t st) {
+    if (f->own_xy) {
+        RealPro rp;
+        rp.p[0] = in;
+        if (int rc = fft2d_r2c_lines(f->nx, (long long)f->pi.xsz[1] * f->pi.xsz[2], rp, outY, st)) return rc;
+        return own_y_pass(f, outY, outY, -1, FftPro(), st);
+    }
     if (f->slab2d) {
         PDO_CUFFT(cufftSetStream(f->plan2d_f, st));
         PDO_CUFFT(cufftExecD2Z(f->plan2d_f, (cufftDoubleReal*)in, (cufftDoubleComplex*)outY));
@@ -131,6 +167,10 @@ int forward_xy(pdo_fft3d_s* f, const double* in, double2* outY, cudaStream_t st)
 
 // complex y-pencil in `Y` (destroyed) → real x-pencil
 int backward_yx(pdo_fft3d_s* f, double2* Y, double* out, cudaStream_t st) {
+    if (f->own_xy) {
+        if (int rc = own_y_pass(f, Y, Y, +1, FftPro(), st)) return rc;
+        return fft2d_c2r_lines(f->nx, (long long)f->pi.xsz[1] * f->pi.xsz[2], Y, out, st);
+    }
     if (f->slab2d) {
         PDO_CUFFT(cufftSetStream(f->plan2d_b, st));
         PDO_CUFFT(cufftExecZ2D(f->plan2d_b, (cufftDoubleComplex*)Y, (cufftDoubleReal*)out));
@@ -145,8 +185,18 @@ int backward_yx(pdo_fft3d_s* f, double2* Y, double* out, cudaStream_t st) {
     return 0;
 }
 
+int own_z_pass(pdo_fft3d_s* f, const double2* in, double2* out, int dir, const FftPro& pro, cudaStream_t st) {
+    const long long cols = (long long)f->si.zsz[0] * f->si.zsz[1];
+    return fft2d_cols(f->nz, cols, 1, cols, 0, in, out, dir, pro, st);
+}
+
 int fft3_x2z_dev(pdo_fft3d_s* f, const double* in, double2* out, cudaStream_t st) {
     if (int rc = forward_xy(f, in, f->bufY, st)) return rc;
+    if (f->own_z) {
+        if (f->p_col == 1) return own_z_pass(f, f->bufY, out, -1, FftPro(), st);
+        if (int rc = decomp_transpose_device(f->spec, 2, (const double*)f->bufY, (double*)out, 2, st)) return rc;
+        return own_z_pass(f, out, out, -1, FftPro(), st);
+    }
     PDO_CUFFT(cufftSetStream(f->planz, st));
     if (f->p_col == 1) {  // y- and z-pencils coincide: the out-of-place z pass is the "transpose"
         PDO_CUFFT(cufftExecZ2Z(f->planz, (cufftDoubleComplex*)f->bufY, (cufftDoubleComplex*)out, CUFFT_FORWARD));
@@ -160,6 +210,17 @@ int fft3_x2z_dev(pdo_fft3d_s* f, const double* in, double2* out, cudaStream_t st
 
 // scale == 0 → caller already folded the normalisation in
 int ifft3_z2x_dev(pdo_fft3d_s* f, const double2* in, double* out, bool do_scale, cudaStream_t st) {
+    if (f->own_z) {
+        FftPro pro;
+        if (do_scale) { pro.active = 1; pro.scale = f->normfactor; }   // linear: the normalisation rides on the first load
+        if (f->p_col == 1) {
+            if (int rc = own_z_pass(f, in, f->bufY, +1, pro, st)) return rc;
+        } else {
+            if (int rc = own_z_pass(f, in, f->bufZ, +1, pro, st)) return rc;
+            if (int rc = decomp_transpose_device(f->spec, 3, (const double*)f->bufZ, (double*)f->bufY, 2, st)) return rc;
+        }
+        return backward_yx(f, f->bufY, out, st);
+    }
     PDO_CUFFT(cufftSetStream(f->planz, st));
     if (f->p_col == 1) {
         PDO_CUFFT(cufftExecZ2Z(f->planz, (cufftDoubleComplex*)in, (cufftDoubleComplex*)f->bufY, CUFFT_INVERSE));
@@ -188,17 +249,59 @@ int fft3d_forward_xy(pdo_fft3d_t f, const double* in_real_x, double2* out_cplx_y
 // ifft2_y2x: the input is intent(in) — it is staged into bufY, folding in 1/(nx ny) and the oddball zeroing
 // (fft_3d.F90:633-641; zeroing the x-Nyquist column commutes with the y pass).
 int fft3d_backward_yx(pdo_fft3d_t f, const double2* in_cplx_y, double* out_real_x, bool set_oddball, cudaStream_t st) {
+    return fft3d_backward_yx_mul(f, in_cplx_y, 0, nullptr, f->normfactor2d, set_oddball, out_real_x, st);
+}
+// out = ifft2(in * scale * (i k)): which = 0 no wavenumber, 1 k along index 1 (ktab = the LOCAL slice of k1), 2 along index 2.
+// `in` is left untouched: the hand-written y pass reads it with the factor on its first load and writes the scratch pencil; on
+// the cuFFT path one pointwise pass stages it.
+int fft3d_backward_yx_mul(pdo_fft3d_t f, const double2* in_cplx_y, int which, const double* ktab, double scale, bool set_oddball,
+                          double* out_real_x, cudaStream_t st) {
     const long long n = cvol(f->si.ysz);
     int inyq = -1;
     if (set_oddball) {
         const int g = f->nx / 2;  // 0-based global index of mode nx/2+1
         if (g >= f->si.yst[0] - 1 && g <= f->si.yen[0] - 1) inyq = g - (f->si.yst[0] - 1);
     }
-    copy_scale_oddball_kernel<<<grid_for(n, 256), 256, 0, st>>>(in_cplx_y, f->bufY, n, f->si.ysz[0], inyq, f->normfactor2d);
+    if (f->own_xy) {
+        FftPro pro;
+        pro.active = 1;
+        pro.scale = scale;
+        pro.n1 = f->si.ysz[0];
+        pro.nyq = inyq;
+        if (which == 1) { pro.A = ktab; pro.times_i = 1; }
+        if (which == 2) { pro.C = ktab; pro.times_i = 1; }
+        if (int rc = own_y_pass(f, in_cplx_y, f->bufY, +1, pro, st)) return rc;
+        return fft2d_c2r_lines(f->nx, (long long)f->pi.xsz[1] * f->pi.xsz[2], f->bufY, out_real_x, st);
+    }
+    copy_scale_oddball_kernel<<<grid_for(n, 256), 256, 0, st>>>(in_cplx_y, f->bufY, n, f->si.ysz[0], f->si.ysz[1], inyq, scale, which, ktab);
     PDO_CUDA(cudaGetLastError());
     g_launches += 1;
     return backward_yx(f, f->bufY, out_real_x, st);
 }
+// fft2 of a pointwise combination of real x-pencil arrays (RealPro): the hand-written x pass forms it on its first load
+int fft3d_forward_xy_pro(pdo_fft3d_t f, const RealPro& pro, double2* out_cplx_y, cudaStream_t st) {
+    if (f->own_xy) {
+        if (int rc = fft2d_r2c_lines(f->nx, (long long)f->pi.xsz[1] * f->pi.xsz[2], pro, out_cplx_y, st)) return rc;
+        return own_y_pass(f, out_cplx_y, out_cplx_y, -1, FftPro(), st);
+    }
+    if (pro.mode == 0) return forward_xy(f, pro.p[0], out_cplx_y, st);
+    const long long n = cvol(f->pi.xsz);
+    if (!f->rtmp) PDO_CUDA(cudaMalloc(&f->rtmp, sizeof(double) * (size_t)n));
+    real_pro_kernel<<<grid_for(n, 256), 256, 0, st>>>(pro, f->rtmp, n);
+    PDO_CUDA(cudaGetLastError());
+    g_launches += 1;
+    return forward_xy(f, f->rtmp, out_cplx_y, st);
+}
+// c2c along z on a z-pencil array with a factor table on the first load: v *= scale * gx(i) gy(j) gz(k) (null = 1)
+int fft3d_z_pro(pdo_fft3d_t f, const double2* in, double2* out, int dir, const double* gx, const double* gy, const double* gz, double scale,
+                cudaStream_t st) {
+    if (!f->own_z) return fail(PDO_E_UNSUPPORTED, "fft3d_z_pro needs the hand-written z pass");
+    FftPro pro;
+    pro.active = 1; pro.scale = scale; pro.n1 = f->si.zsz[0]; pro.A = gx; pro.B = gy; pro.C = gz;
+    return own_z_pass(f, in, out, dir, pro, st);
+}
+bool fft3d_own_z(pdo_fft3d_t f) { return f->own_z; }
+bool fft3d_own_xy(pdo_fft3d_t f) { return f->own_xy; }
 // Same inverse for a caller-owned scratch array that already carries the 1/(nx ny) factor: it is consumed in place
 // (no staging copy).
 int fft3d_backward_yx_scratch(pdo_fft3d_t f, double2* scratch_cplx_y, double* out_real_x, cudaStream_t st) {
@@ -207,6 +310,7 @@ int fft3d_backward_yx_scratch(pdo_fft3d_t f, double2* scratch_cplx_y, double* ou
 // c2c along z, in place, on a z-pencil array of the spectral decomposition (or on the first nz planes of an edge
 // field, which has the same zsz(1:2)); dir = -1 forward, +1 backward, unnormalised like FFTW.
 int fft3d_z_inplace(pdo_fft3d_t f, double2* a_cplx_z, int dir, cudaStream_t st) {
+    if (f->own_z) return own_z_pass(f, a_cplx_z, a_cplx_z, dir, FftPro(), st);
     PDO_CUFFT(cufftSetStream(f->planz, st));
     PDO_CUFFT(cufftExecZ2Z(f->planz, (cufftDoubleComplex*)a_cplx_z, (cufftDoubleComplex*)a_cplx_z, dir < 0 ? CUFFT_FORWARD : CUFFT_INVERSE));
     g_launches += 1;
@@ -264,6 +368,8 @@ int pdo_fft3d_init(pdo_fft3d_t* h, int nx, int ny, int nz, double dx, double dy,
     f->normfactor = 1.0 / ((double)nx * (double)ny * (double)nz);  // in floating point: 2048^3 overflows int
     f->normfactor2d = 1.0 / ((double)nx * (double)ny);
     f->slab2d = (p_row == 1);
+    f->own_xy = f->slab2d && fft2d_enabled() && fft2d_x_ok(nx) && fft2d_cols_ok(ny);
+    f->own_z = fft2d_enabled() && fft2d_cols_ok(nz);
     const long long ny_c = cvol(f->si.ysz), nz_c = cvol(f->si.zsz), nx_c = cvol(f->si.xsz);
     // scratch pencils are transpose destinations: peer-writable for the fused NVLink path (collective, same order everywhere)
     rc = pdo::comm_shared_malloc((void**)&f->bufY, sizeof(double2) * (size_t)ny_c);
@@ -271,7 +377,9 @@ int pdo_fft3d_init(pdo_fft3d_t* h, int nx, int ny, int nz, double dx, double dy,
     if (!rc && !f->slab2d) rc = pdo::comm_shared_malloc((void**)&f->bufX, sizeof(double2) * (size_t)nx_c);
     if (rc) { pdo_fft3d_destroy(f); return rc; }
     cufftResult r = CUFFT_SUCCESS;
-    if (f->slab2d) {
+    if (f->own_xy) {
+        // no cuFFT plans (and none of their work areas) for passes that never run
+    } else if (f->slab2d) {
         int n2[2] = {ny, nx};
         int inembed[2] = {ny, nx}, onembed[2] = {ny, f->nxh};
         const int batch = f->pi.xsz[2];
@@ -293,7 +401,7 @@ int pdo_fft3d_init(pdo_fft3d_t* h, int nx, int ny, int nz, double dx, double dy,
             f->hasy = (r == CUFFT_SUCCESS);
         }
     }
-    if (r == CUFFT_SUCCESS) {
+    if (r == CUFFT_SUCCESS && !f->own_z) {
         int nz1[1] = {nz};
         int emb[1] = {nz};
         const int zs = f->si.zsz[0] * f->si.zsz[1];
@@ -315,6 +423,7 @@ int pdo_fft3d_destroy(pdo_fft3d_t f) {
     pdo::comm_shared_free(f->bufY);     // same order as the allocation on every rank
     pdo::comm_shared_free(f->bufZ);
     pdo::comm_shared_free(f->bufX);
+    if (f->rtmp) cudaFree(f->rtmp);
     pdo_decomp_destroy(f->phys);
     pdo_decomp_destroy(f->spec);
     delete f;

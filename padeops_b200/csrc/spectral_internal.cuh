@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/padeops_b200.h"
+#include "fft2d.cuh"
 
 namespace pdo {
 // dir: 0 x->y, 1 y->x, 2 y->z, 3 z->y; w = doubles per element (1 real, 2 complex)
@@ -25,6 +26,14 @@ int fft3d_forward_xy(pdo_fft3d_t f, const double* in_real_x, double2* out_cplx_y
 int fft3d_backward_yx(pdo_fft3d_t f, const double2* in_cplx_y, double* out_real_x, bool set_oddball, cudaStream_t st);
 int fft3d_backward_yx_scratch(pdo_fft3d_t f, double2* prescaled_scratch_cplx_y, double* out_real_x, cudaStream_t st);
 int fft3d_z_inplace(pdo_fft3d_t f, double2* a_cplx_z, int dir, cudaStream_t st);
+// fused forms (hand-written passes when the shape allows, pointwise pass + cuFFT otherwise; see spectral.cu)
+int fft3d_backward_yx_mul(pdo_fft3d_t f, const double2* in_cplx_y, int which, const double* ktab, double scale, bool set_oddball,
+                          double* out_real_x, cudaStream_t st);
+int fft3d_forward_xy_pro(pdo_fft3d_t f, const RealPro& pro, double2* out_cplx_y, cudaStream_t st);
+int fft3d_z_pro(pdo_fft3d_t f, const double2* in, double2* out, int dir, const double* gx, const double* gy, const double* gz, double scale,
+                cudaStream_t st);
+bool fft3d_own_z(pdo_fft3d_t f);
+bool fft3d_own_xy(pdo_fft3d_t f);
 // c2c along the slowest index of an array (nz, cols) with ANY column count (the real z-Fourier procedures transform pairs of
 // real columns as one complex column); the plan is cached in `p` and rebuilt when the shape changes.
 struct ZColsPlan { int plan = -1; long long cols = 0; int nz = 0; };

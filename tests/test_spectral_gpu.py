@@ -77,6 +77,45 @@ def test_fft3d_passes_match_numpy(pdo, comm, shape):
         assert _relerr(ft.ifft2_y2x(got2, setOddBall=True).cpu().numpy(), refo) < TOL
 
 
+# Power-of-two extents on a slab grid take the hand-written passes of csrc/fft2d.cu (Stockham radix-8 kernels; every other shape
+# goes to cuFFT): one case per compiled transform length of the contiguous pass (nx = 16 ... 2048), of the strided pass as y
+# (16 ... 1024) and as z (16 ... 1024), with plane / line counts that leave partial tiles.
+_HW_SHAPES = ([(3, 16, nx) for nx in (16, 32, 64, 128, 256, 512, 1024, 2048)] + [(3, ny, 16 + 16 * (i % 2)) for i, ny in enumerate((32, 64, 128, 256, 512, 1024))]
+              + [(nz, 16, 16) for nz in (16, 32, 64, 128, 256, 512, 1024)] + [(7, 64, 64), (5, 32, 512), (64, 128, 256)])
+
+
+@pytest.mark.parametrize("shape", _HW_SHAPES)
+def test_handwritten_fft_passes_match_numpy(pdo, comm, shape):
+    if comm.nproc != 1:
+        pytest.skip("single-rank test")
+    nz, ny, nx = shape
+    f = broadband(shape, seed=nx + ny)
+    ft = pdo.fft_3d()
+    assert ft.init(nx, ny, nz, "x", 0.1, 0.1, 0.1) == 0
+    fd = _dev(f)
+    ref2 = np.fft.fft(np.fft.rfft(f, axis=2), axis=1)
+    got2 = ft.fft2_x2y(fd)
+    assert _relerr(got2.cpu().numpy(), ref2) < TOL
+    assert np.array_equal(fd.cpu().numpy(), f)
+    back2 = ft.ifft2_y2x(got2)
+    assert _relerr(back2.cpu().numpy(), f) < TOL
+    assert _relerr(got2.cpu().numpy(), ref2) < TOL           # intent(in)
+    # c2r ignores the imaginary parts of the x modes 0 and nx/2 after the y pass, as FFTW's c2r does; a non-Hermitian input pins that
+    rng = np.random.default_rng(nx)
+    g = ref2 + 0.1 * (rng.standard_normal(ref2.shape) + 1j * rng.standard_normal(ref2.shape))
+    refg = np.fft.irfft(np.fft.ifft(g, axis=1), n=nx, axis=2)
+    assert _relerr(ft.ifft2_y2x(_dev(g)).cpu().numpy(), refg) < TOL
+    r2 = g.copy()
+    r2[:, :, nx // 2] = 0
+    refo = np.fft.irfft(np.fft.ifft(r2, axis=1), n=nx, axis=2)
+    assert _relerr(ft.ifft2_y2x(_dev(g), setOddBall=True).cpu().numpy(), refo) < TOL
+    ref3 = np.fft.fft(ref2, axis=0)
+    got3 = ft.fft3_x2z(fd)
+    assert _relerr(got3.cpu().numpy(), ref3) < TOL
+    assert _relerr(ft.ifft3_z2x(got3).cpu().numpy(), f) < TOL
+    assert _relerr(got3.cpu().numpy(), ref3) < TOL
+
+
 def test_poisson_manufactured_solution(pdo, oracle, comm):
     # tests/test_PoissonPeriodic.F90:109-118: 64 x 32 x 16, (l,m,n) = (6,3,1)
     if comm.nproc != 1:
