@@ -33,6 +33,10 @@ struct Plan {
     static constexpr int T = N / 8;                              // threads per transform
     __host__ __device__ static constexpr int radix(int i) { return i == 0 ? R0 : 8; }
     __host__ __device__ static constexpr int stride(int i) { return i == 0 ? 1 : (R0 << (3 * (i - 1))); }
+    // stage twiddles, one table per stage laid out [k - 1][p] (p = b / s, N / (R s) distinct values): lanes of a warp read
+    // consecutive (or equal) entries instead of gathering w^{s p k} from a flat table
+    __host__ __device__ static constexpr int npts(int i) { return N / (radix(i) * stride(i)); }
+    __host__ __device__ static constexpr int toff(int i) { return i == 0 ? 0 : toff(i - 1) + (radix(i - 1) - 1) * npts(i - 1); }
 };
 
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -72,10 +76,11 @@ __device__ __forceinline__ void bfly(double2* a) {
     }
 }
 
-// Stage I of the N-point transform, thread t of its T: load through ld(position), butterflies, twiddles.  W = exp(-2 pi i j / Nw)
-// with Nw = wmul * N.
-template <int LOG2N, int I, int SGN, class LD>
-__device__ __forceinline__ void stage_compute(int t, double2 (&v)[8], const double2* __restrict__ W, int wmul, LD ld) {
+// Stage I of the N-point transform, thread t of its T: raw loads through ld(position) — all of them issued before anything
+// depends on one — then fix(position, value) (the caller's pointwise work on the first stage), butterflies, twiddles from the
+// stage tables TW.
+template <int LOG2N, int I, int SGN, class LD, class FX>
+__device__ __forceinline__ void stage_compute(int t, double2 (&v)[8], const double2* __restrict__ TW, LD ld, FX fix) {
     using P = Plan<LOG2N>;
     constexpr int N = P::N, R = P::radix(I), s = P::stride(I), T = P::T, NB = 8 / R;
 #pragma unroll
@@ -85,21 +90,29 @@ __device__ __forceinline__ void stage_compute(int t, double2 (&v)[8], const doub
         for (int r = 0; r < R; ++r) v[u * R + r] = ld(b + (N / R) * r);
     }
 #pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        const int b = t + T * u;
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[u * R + r] = fix(b + (N / R) * r, v[u * R + r]);
+    }
+#pragma unroll
     for (int u = 0; u < NB; ++u) bfly<R, SGN>(&v[u * R]);
     if (I < P::NS - 1) {
+        constexpr int NP = P::npts(I);
+        const double2* tw = TW + P::toff(I);
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
-            const int b = t + T * u;
-            const int e = (b / s) * s * wmul;   // s p
+            const int p = (t + T * u) / s;
 #pragma unroll
             for (int k = 1; k < R; ++k) {
-                double2 w = __ldg(W + e * k);
+                double2 w = __ldg(tw + (k - 1) * NP + p);
                 if (SGN > 0) w.y = -w.y;
                 v[u * R + k] = cmul(v[u * R + k], w);
             }
         }
     }
 }
+struct NoFix { __device__ __forceinline__ double2 operator()(int, double2 x) const { return x; } };
 template <int LOG2N, int I, class ST>
 __device__ __forceinline__ void stage_store(int t, double2 (&v)[8], ST stf) {
     using P = Plan<LOG2N>;
@@ -113,37 +126,38 @@ __device__ __forceinline__ void stage_store(int t, double2 (&v)[8], ST stf) {
     }
 }
 
-// All stages of one transform.  ld0 feeds the first stage, stl takes the last stage's output, exchanges go through (lds, sts);
-// sync() separates a stage's shared reads from its shared writes and the writes from the next stage's reads.  FIRST_SM / LAST_SM say
-// that ld0 / stl are shared-memory accessors themselves, i.e. that the first / last stage needs the separating sync as well.
-template <int LOG2N, int SGN, bool FIRST_SM, bool LAST_SM, class LD0, class STL, class LDS, class STS, class SYNC>
-__device__ __forceinline__ void transform(int t, const double2* __restrict__ W, int wmul, LD0 ld0, STL stl, LDS lds, STS sts, SYNC sync) {
+// All stages of one transform.  ld0 (+ fix0) feeds the first stage, stl takes the last stage's output, exchanges go through
+// (lds, sts); sync() separates a stage's shared reads from its shared writes and the writes from the next stage's reads.
+// FIRST_SM / LAST_SM say that ld0 / stl are shared-memory accessors themselves, i.e. that the first / last stage needs the
+// separating sync as well.
+template <int LOG2N, int SGN, bool FIRST_SM, bool LAST_SM, class LD0, class FX0, class STL, class LDS, class STS, class SYNC>
+__device__ __forceinline__ void transform(int t, const double2* __restrict__ TW, LD0 ld0, FX0 fix0, STL stl, LDS lds, STS sts, SYNC sync) {
     using P = Plan<LOG2N>;
     constexpr int NS = P::NS;
     double2 v[8];
     if constexpr (NS == 1) {
-        stage_compute<LOG2N, 0, SGN>(t, v, W, wmul, ld0);
+        stage_compute<LOG2N, 0, SGN>(t, v, TW, ld0, fix0);
         if (FIRST_SM && LAST_SM) sync();
         stage_store<LOG2N, 0>(t, v, stl);
         return;
     }
-    stage_compute<LOG2N, 0, SGN>(t, v, W, wmul, ld0);
+    stage_compute<LOG2N, 0, SGN>(t, v, TW, ld0, fix0);
     if (FIRST_SM) sync();
     stage_store<LOG2N, 0>(t, v, sts);
     sync();
     if constexpr (NS >= 3) {
-        stage_compute<LOG2N, 1, SGN>(t, v, W, wmul, lds);
+        stage_compute<LOG2N, 1, SGN>(t, v, TW, lds, NoFix());
         sync();
         stage_store<LOG2N, 1>(t, v, sts);
         sync();
     }
     if constexpr (NS >= 4) {
-        stage_compute<LOG2N, 2, SGN>(t, v, W, wmul, lds);
+        stage_compute<LOG2N, 2, SGN>(t, v, TW, lds, NoFix());
         sync();
         stage_store<LOG2N, 2>(t, v, sts);
         sync();
     }
-    stage_compute<LOG2N, NS - 1, SGN>(t, v, W, wmul, lds);
+    stage_compute<LOG2N, NS - 1, SGN>(t, v, TW, lds, NoFix());
     if (LAST_SM) sync();
     stage_store<LOG2N, NS - 1>(t, v, stl);
 }
@@ -160,31 +174,29 @@ template <int LOG2N> struct ColsCfg {
 
 template <int LOG2N, int SGN>
 __global__ void __launch_bounds__(ColsCfg<LOG2N>::THREADS, ColsCfg<LOG2N>::MINB)
-fft_cols_kernel(const double2* __restrict__ in, double2* __restrict__ out, long long ncols, long long nplanes, long long row_stride,
-                long long plane_stride, FftPro pro, const double2* __restrict__ W) {
+fft_cols_kernel(const double2* __restrict__ in, double2* __restrict__ out, int ncols, int nplanes, long long row_stride,
+                long long plane_stride, FftPro pro, const double2* __restrict__ TW) {
     constexpr int XT = ColsCfg<LOG2N>::XT;
     extern __shared__ double2 sm[];
     const int c = threadIdx.x % XT, t = threadIdx.x / XT;
-    const long long cblocks = (ncols + XT - 1) / XT;
-    const long long ntiles = cblocks * nplanes;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long pl = tile / cblocks, cb = tile - pl * cblocks;
-        const long long col = cb * XT + c;
+    const int cblocks = (ncols + XT - 1) / XT;
+    const int ntiles = cblocks * nplanes;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int pl = tile / cblocks, cb = tile - pl * cblocks;
+        const int col = cb * XT + c;
         const bool ok = col < ncols;
         const double2* src = in + pl * plane_stride + col;
         double2* dst = out + pl * plane_stride + col;
         double colf = pro.scale;
         bool zero = false;
         if (pro.active && ok) {
-            const long long c1 = col / pro.n1;
-            const int c0 = (int)(col - c1 * pro.n1);
+            const int c1 = col / pro.n1, c0 = col - c1 * pro.n1;
             if (pro.A) colf *= __ldg(pro.A + c0);
             if (pro.B) colf *= __ldg(pro.B + c1);
             zero = (c0 == pro.nyq);
         }
-        auto ldg = [&](int row) -> double2 {
-            if (!ok) return make_double2(0.0, 0.0);
-            double2 x = src[(long long)row * row_stride];
+        auto ldg = [&](int row) -> double2 { return ok ? src[(long long)row * row_stride] : make_double2(0.0, 0.0); };
+        auto fix = [&](int row, double2 x) -> double2 {
             if (pro.active) {
                 double m = colf;
                 if (pro.C) m *= __ldg(pro.C + row);
@@ -198,9 +210,188 @@ fft_cols_kernel(const double2* __restrict__ in, double2* __restrict__ out, long 
         auto lds = [&](int pos) -> double2 { return sm[pos * XT + c]; };
         auto sts = [&](int pos, double2 x) { sm[pos * XT + c] = x; };
         auto sync = [] { __syncthreads(); };
-        transform<LOG2N, SGN, false, false>(t, W, 1, ldg, stg, lds, sts, sync);
+        transform<LOG2N, SGN, false, false>(t, TW, ldg, fix, stg, lds, sts, sync);
         if (Plan<LOG2N>::NS > 1) __syncthreads();   // the last stage's shared reads before the next tile's first writes
     }
+}
+
+// ---- pipelined form of the strided pass (N = 128, 256, 512) ----
+// Persistent CTAs, three tile buffers: every thread copies the eight points ITS first stage will read with cp.async (16 B each,
+// no registers held) two tiles ahead, so two tiles' worth of loads are in flight per CTA while a third is transformed.  The
+// stages run in place (decimation in frequency, same butterflies and the same stage tables as above: butterfly b = hi S + lo
+// touches hi R S + r S + lo, output k is scaled by w_N^{lo P k}); a thread's stage reads and writes hit the same slots, so one
+// barrier per exchange is enough, and the first stage needs none (it reads only what the thread copied itself).  Results leave
+// in digit-reversed slot order, which costs nothing here: every row of a tile is its own contiguous segment.
+template <int LOG2N> struct PipeCfg {
+    static constexpr int XT = 8, NBUF = 3, N = 1 << LOG2N;
+    static constexpr int THREADS = XT * N / 8;
+    static constexpr int TILE = XT * N;                         // complex numbers per buffer
+    static constexpr size_t SMEM = sizeof(double2) * NBUF * (size_t)TILE;
+    static constexpr int MINB = LOG2N >= 9 ? 1 : (LOG2N == 8 ? 2 : 4);
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+// in-place stage I: slots of butterfly (t, u)
+template <int LOG2N, int I>
+__device__ __forceinline__ void ip_slots(int t, int u, int& base, int& lo) {
+    using P = Plan<LOG2N>;
+    constexpr int R = P::radix(I), S = P::npts(I), T = P::T;
+    const int b = t + T * u, hi = b / S;
+    lo = b - hi * S;
+    base = hi * R * S + lo;
+}
+template <int LOG2N, int I, int SGN, class FX>
+__device__ __forceinline__ void ip_stage(int t, double2 (&v)[8], const double2* __restrict__ TW, const double2* buf, int c, FX fix) {
+    using P = Plan<LOG2N>;
+    constexpr int R = P::radix(I), S = P::npts(I), NB = 8 / R, XT = PipeCfg<LOG2N>::XT;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        int base, lo;
+        ip_slots<LOG2N, I>(t, u, base, lo);
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[u * R + r] = buf[(base + r * S) * XT + c];
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        int base, lo;
+        ip_slots<LOG2N, I>(t, u, base, lo);
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[u * R + r] = fix(base + r * S, v[u * R + r]);
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) bfly<R, SGN>(&v[u * R]);
+    if (I < P::NS - 1) {
+        const double2* tw = TW + P::toff(I);
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            int base, lo;
+            ip_slots<LOG2N, I>(t, u, base, lo);
+#pragma unroll
+            for (int k = 1; k < R; ++k) {
+                double2 w = __ldg(tw + (k - 1) * S + lo);
+                if (SGN > 0) w.y = -w.y;
+                v[u * R + k] = cmul(v[u * R + k], w);
+            }
+        }
+    }
+}
+template <int LOG2N, int I>
+__device__ __forceinline__ void ip_store(int t, double2 (&v)[8], double2* buf, int c) {
+    using P = Plan<LOG2N>;
+    constexpr int R = P::radix(I), S = P::npts(I), NB = 8 / R, XT = PipeCfg<LOG2N>::XT;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        int base, lo;
+        ip_slots<LOG2N, I>(t, u, base, lo);
+#pragma unroll
+        for (int k = 0; k < R; ++k) buf[(base + k * S) * XT + c] = v[u * R + k];
+    }
+}
+// output index held by slot `pos` after the last in-place stage
+template <int LOG2N>
+__device__ __forceinline__ int ip_freq_of(int pos) {
+    using P = Plan<LOG2N>;
+    int rem = pos, f = 0;
+#pragma unroll
+    for (int i = 0; i < P::NS; ++i) {
+        const int S = P::npts(i), d = rem / S;
+        rem -= d * S;
+        f += d * P::stride(i);
+    }
+    return f;
+}
+
+template <int LOG2N, int SGN>
+__global__ void __launch_bounds__(PipeCfg<LOG2N>::THREADS, PipeCfg<LOG2N>::MINB)
+fft_cols_pipe_kernel(const double2* __restrict__ in, double2* __restrict__ out, int ncols, int nplanes, long long row_stride,
+                     long long plane_stride, FftPro pro, const double2* __restrict__ TW) {
+    using P = Plan<LOG2N>;
+    using Cc = PipeCfg<LOG2N>;
+    constexpr int XT = Cc::XT, N = P::N, NS = P::NS, R0 = P::R0, T = P::T;
+    static_assert(NS >= 2 && NS <= 4, "pipelined strided pass: 16 <= N <= 2048");
+    extern __shared__ double2 sm[];
+    const int c = threadIdx.x % XT, t = threadIdx.x / XT;
+    const int cblocks = (ncols + XT - 1) / XT;
+    const int ntiles = cblocks * nplanes;
+    const int G = gridDim.x;
+    const int f0 = ip_freq_of<LOG2N>(8 * t);   // last stage: butterfly t owns slots 8 t + k, outputs f0 + (N / 8) k
+
+    auto prefetch = [&](int tile, double2* buf) {
+        if (tile < ntiles) {
+            const int pl = tile / cblocks, cb = tile - pl * cblocks, col = cb * XT + c;
+            if (col < ncols) {
+                const double2* src = in + pl * plane_stride + col;
+#pragma unroll
+                for (int u = 0; u < 8 / R0; ++u)
+#pragma unroll
+                    for (int r = 0; r < R0; ++r) {
+                        const int row = t + T * u + (N / R0) * r;   // first stage: hi = 0, lo = b
+                        cp_async16(buf + row * XT + c, src + (long long)row * row_stride);
+                    }
+            }
+        }
+        cp_async_commit();
+    };
+
+    prefetch(blockIdx.x, sm);
+    prefetch(blockIdx.x + G, sm + Cc::TILE);
+    int slot = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += G) {
+        double2* buf = sm + slot * Cc::TILE;
+        const int pl = tile / cblocks, cb = tile - pl * cblocks, col = cb * XT + c;
+        const bool ok = col < ncols;
+        double2* dst = out + pl * plane_stride + col;
+        double colf = pro.scale;
+        bool zero = false;
+        if (pro.active && ok) {
+            const int c1 = col / pro.n1, c0 = col - c1 * pro.n1;
+            if (pro.A) colf *= __ldg(pro.A + c0);
+            if (pro.B) colf *= __ldg(pro.B + c1);
+            zero = (c0 == pro.nyq);
+        }
+        auto fix = [&](int row, double2 x) -> double2 {
+            if (pro.active) {
+                double m = colf;
+                if (pro.C) m *= __ldg(pro.C + row);
+                x.x *= m; x.y *= m;
+                if (pro.times_i) x = make_double2(-x.y, x.x);
+                if (zero) x = make_double2(0.0, 0.0);
+            }
+            return x;
+        };
+        double2 v[8];
+        cp_async_wait<1>();   // this tile's copies (mine) have landed; the next tile's may still be in flight
+        ip_stage<LOG2N, 0, SGN>(t, v, TW, buf, c, fix);
+        ip_store<LOG2N, 0>(t, v, buf, c);
+        __syncthreads();
+        // everybody is past the previous tile's last reads: its buffer takes the tile after next
+        const int nslot = slot == 0 ? 2 : slot - 1;
+        prefetch(tile + 2 * G, sm + nslot * Cc::TILE);
+        if constexpr (NS >= 3) {
+            ip_stage<LOG2N, 1, SGN>(t, v, TW, buf, c, NoFix());
+            ip_store<LOG2N, 1>(t, v, buf, c);
+            __syncthreads();
+        }
+        if constexpr (NS >= 4) {
+            ip_stage<LOG2N, 2, SGN>(t, v, TW, buf, c, NoFix());
+            ip_store<LOG2N, 2>(t, v, buf, c);
+            __syncthreads();
+        }
+        ip_stage<LOG2N, NS - 1, SGN>(t, v, TW, buf, c, NoFix());
+        if (ok) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dst[(long long)(f0 + (N / 8) * k) * row_stride] = v[k];
+        }
+        slot = slot == 2 ? 0 : slot + 1;
+    }
+    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -239,7 +430,8 @@ __device__ __forceinline__ double2 real_pro_load(const RealPro& pro, long long i
 }
 
 template <int LOG2M>
-__global__ void __launch_bounds__(256, 4) fft_r2c_kernel(RealPro pro, double2* __restrict__ out, long long nlines, const double2* __restrict__ W) {
+__global__ void __launch_bounds__(256, 4) fft_r2c_kernel(RealPro pro, double2* __restrict__ out, long long nlines, const double2* __restrict__ TW,
+                                                         const double2* __restrict__ W) {
     using C = LineCfg<LOG2M>;
     constexpr int M = C::M, T = C::T, LPB = C::LPB, LS = C::LS;
     __shared__ double2 sm[LPB * LS];
@@ -255,7 +447,7 @@ __global__ void __launch_bounds__(256, 4) fft_r2c_kernel(RealPro pro, double2* _
         auto lds = [&](int p) -> double2 { return z[padx(p)]; };
         auto sts = [&](int p, double2 x) { z[padx(p)] = x; };
         auto sync = [] { if (C::WARP) __syncwarp(); else __syncthreads(); };
-        transform<LOG2M, -1, false, true>(t, W, 2, ldg, sts, lds, sts, sync);
+        transform<LOG2M, -1, false, true>(t, TW, ldg, NoFix(), sts, lds, sts, sync);
         sync();
         // merge: X_k = E_k + w^k O_k, X_{M-k} = conj(E_k - w^k O_k), E = (Z_k + conj Z_{M-k})/2, O = -i (Z_k - conj Z_{M-k})/2
 #pragma unroll
@@ -278,7 +470,8 @@ __global__ void __launch_bounds__(256, 4) fft_r2c_kernel(RealPro pro, double2* _
 }
 
 template <int LOG2M>
-__global__ void __launch_bounds__(256, 4) fft_c2r_kernel(const double2* __restrict__ in, double* __restrict__ out, long long nlines, const double2* __restrict__ W) {
+__global__ void __launch_bounds__(256, 4) fft_c2r_kernel(const double2* __restrict__ in, double* __restrict__ out, long long nlines,
+                                                         const double2* __restrict__ TW, const double2* __restrict__ W) {
     using C = LineCfg<LOG2M>;
     constexpr int M = C::M, T = C::T, LPB = C::LPB, LS = C::LS;
     __shared__ double2 sm[LPB * LS];
@@ -292,28 +485,37 @@ __global__ void __launch_bounds__(256, 4) fft_c2r_kernel(const double2* __restri
         double* dst = out + line * (2LL * M);
         auto sync = [] { if (C::WARP) __syncwarp(); else __syncthreads(); };
         // split: Z_k = (X_k + conj X_{M-k}) + i conj(w)^k (X_k - conj X_{M-k}),  Z_{M-k} = conj(X_k + conj X_{M-k}) + i conj(G)
+        {
+            const double2 zz = make_double2(0.0, 0.0);
+            double2 A[4], B[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int k = t + T * u;   // 4 T = M / 2 values
-            if (k == 0) {
-                const double2 x0 = ok ? src[0] : make_double2(0.0, 0.0), xm = ok ? src[M] : make_double2(0.0, 0.0);
-                z[0] = make_double2(x0.x + xm.x, x0.x - xm.x);
-            } else {
-                const double2 A = ok ? src[k] : make_double2(0.0, 0.0), B = ok ? src[M - k] : make_double2(0.0, 0.0);
-                const double2 Ze = make_double2(A.x + B.x, A.y - B.y), D = make_double2(A.x - B.x, A.y + B.y);
-                double2 w = __ldg(W + k);
-                w.y = -w.y;
-                const double2 G = cmul(D, w);
-                z[padx(k)] = make_double2(Ze.x - G.y, Ze.y + G.x);
-                z[padx(M - k)] = make_double2(Ze.x + G.y, -Ze.y + G.x);
+            for (int u = 0; u < 4; ++u) {   // k = t + T u, 4 T = M / 2 values; k = 0 pairs modes 0 and M
+                const int k = t + T * u;
+                A[u] = ok ? src[k] : zz;
+                B[u] = ok ? src[M - k] : zz;
             }
+            const double2 Ah = (t == 0 && ok) ? src[M / 2] : zz;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = t + T * u;
+                if (k == 0) {
+                    z[0] = make_double2(A[u].x + B[u].x, A[u].x - B[u].x);
+                } else {
+                    const double2 Ze = make_double2(A[u].x + B[u].x, A[u].y - B[u].y), D = make_double2(A[u].x - B[u].x, A[u].y + B[u].y);
+                    double2 w = __ldg(W + k);
+                    w.y = -w.y;
+                    const double2 G = cmul(D, w);
+                    z[padx(k)] = make_double2(Ze.x - G.y, Ze.y + G.x);
+                    z[padx(M - k)] = make_double2(Ze.x + G.y, -Ze.y + G.x);
+                }
+            }
+            if (t == 0) z[padx(M / 2)] = make_double2(2.0 * Ah.x, -2.0 * Ah.y);
         }
-        if (t == 0) { const double2 A = ok ? src[M / 2] : make_double2(0.0, 0.0); z[padx(M / 2)] = make_double2(2.0 * A.x, -2.0 * A.y); }
         sync();
         auto lds = [&](int p) -> double2 { return z[padx(p)]; };
         auto sts = [&](int p, double2 x) { z[padx(p)] = x; };
         auto stg = [&](int p, double2 x) { if (ok) *reinterpret_cast<double2*>(dst + 2 * p) = x; };
-        transform<LOG2M, +1, true, false>(t, W, 2, lds, stg, lds, sts, sync);
+        transform<LOG2M, +1, true, false>(t, TW, lds, NoFix(), stg, lds, sts, sync);
         sync();   // last stage's shared reads before the next group's split writes
     }
 }
@@ -360,6 +562,48 @@ int twiddles(int n, const double2** out) {
     return 0;
 }
 
+// the stage tables of Plan<log2 n> (see Plan::toff / npts), built from the flat table
+template <int LOG2N>
+void fill_stage_tables(const std::vector<double2>& flat, std::vector<double2>& out) {
+    using P = Plan<LOG2N>;
+    out.assign((size_t)(P::toff(P::NS - 1) > 0 ? P::toff(P::NS - 1) : 1), make_double2(1.0, 0.0));
+    for (int i = 0; i + 1 < P::NS; ++i) {
+        const int R = P::radix(i), s = P::stride(i), NP = P::npts(i);
+        for (int k = 1; k < R; ++k)
+            for (int p = 0; p < NP; ++p) out[(size_t)P::toff(i) + (size_t)(k - 1) * NP + p] = flat[(size_t)((long long)s * p * k) % P::N];
+    }
+}
+std::map<int, double2*> g_stw;
+int stage_twiddles(int n, const double2** out) {
+    {
+        std::lock_guard<std::mutex> lk(g_tw_mutex);
+        auto it = g_stw.find(n);
+        if (it != g_stw.end()) { *out = it->second; return 0; }
+    }
+    const double2* flat_dev = nullptr;
+    if (int rc = twiddles(n, &flat_dev)) return rc;
+    std::vector<double2> flat((size_t)n), tab;
+    PDO_CUDA(cudaMemcpy(flat.data(), flat_dev, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost));
+    switch (n) {
+        case 8: fill_stage_tables<3>(flat, tab); break;
+        case 16: fill_stage_tables<4>(flat, tab); break;
+        case 32: fill_stage_tables<5>(flat, tab); break;
+        case 64: fill_stage_tables<6>(flat, tab); break;
+        case 128: fill_stage_tables<7>(flat, tab); break;
+        case 256: fill_stage_tables<8>(flat, tab); break;
+        case 512: fill_stage_tables<9>(flat, tab); break;
+        case 1024: fill_stage_tables<10>(flat, tab); break;
+        default: return fail(PDO_E_BADARG, "stage_twiddles: n = %d", n);
+    }
+    double2* d = nullptr;
+    PDO_CUDA(cudaMalloc(&d, sizeof(double2) * tab.size()));
+    PDO_CUDA(cudaMemcpy(d, tab.data(), sizeof(double2) * tab.size(), cudaMemcpyHostToDevice));
+    std::lock_guard<std::mutex> lk(g_tw_mutex);
+    g_stw[n] = d;
+    *out = d;
+    return 0;
+}
+
 int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 bool pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
@@ -376,7 +620,7 @@ int sm_count() {
 
 template <int LOG2N, int SGN>
 int launch_cols(long long ncols, long long nplanes, long long row_stride, long long plane_stride, const double2* in, double2* out,
-                const FftPro& pro, const double2* W, cudaStream_t st) {
+                const FftPro& pro, const double2* TW, cudaStream_t st) {
     using Cc = ColsCfg<LOG2N>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -386,30 +630,58 @@ int launch_cols(long long ncols, long long nplanes, long long row_stride, long l
     const long long ntiles = ((ncols + Cc::XT - 1) / Cc::XT) * nplanes;
     long long grid = (long long)sm_count() * Cc::MINB;
     if (grid > ntiles) grid = ntiles;
-    fft_cols_kernel<LOG2N, SGN><<<(unsigned)grid, Cc::THREADS, Cc::SMEM, st>>>(in, out, ncols, nplanes, row_stride, plane_stride, pro, W);
+    if (ncols > 0x7fffffffLL || ntiles > 0x7fffffffLL) return fail(PDO_E_BADARG, "fft2d_cols: too many columns");
+    fft_cols_kernel<LOG2N, SGN><<<(unsigned)grid, Cc::THREADS, Cc::SMEM, st>>>(in, out, (int)ncols, (int)nplanes, row_stride, plane_stride, pro, TW);
+    PDO_CUDA(cudaGetLastError());
+    g_launches += 1;
+    return 0;
+}
+
+bool cols_pipe_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = std::getenv("PDO_FFT_COLS");
+        on = (e && std::strcmp(e, "simple") == 0) ? 0 : 1;
+    }
+    return on == 1;
+}
+template <int LOG2N, int SGN>
+int launch_cols_pipe(long long ncols, long long nplanes, long long row_stride, long long plane_stride, const double2* in, double2* out,
+                     const FftPro& pro, const double2* TW, cudaStream_t st) {
+    using Cc = PipeCfg<LOG2N>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        PDO_CUDA(cudaFuncSetAttribute(fft_cols_pipe_kernel<LOG2N, SGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cc::SMEM));
+        attr_done = true;
+    }
+    const long long ntiles = ((ncols + Cc::XT - 1) / Cc::XT) * nplanes;
+    if (ncols > 0x7fffffffLL || ntiles > 0x3fffffffLL) return fail(PDO_E_BADARG, "fft2d_cols: too many columns");
+    long long grid = (long long)sm_count() * Cc::MINB;
+    if (grid > ntiles) grid = ntiles;
+    fft_cols_pipe_kernel<LOG2N, SGN><<<(unsigned)grid, Cc::THREADS, Cc::SMEM, st>>>(in, out, (int)ncols, (int)nplanes, row_stride, plane_stride, pro, TW);
     PDO_CUDA(cudaGetLastError());
     g_launches += 1;
     return 0;
 }
 
 template <int LOG2M>
-int launch_r2c(long long nlines, const RealPro& pro, double2* out, const double2* W, cudaStream_t st) {
+int launch_r2c(long long nlines, const RealPro& pro, double2* out, const double2* TW, const double2* W, cudaStream_t st) {
     using C = LineCfg<LOG2M>;
     const long long ngroups = (nlines + C::LPB - 1) / C::LPB;
     long long grid = (long long)sm_count() * 4;
     if (grid > ngroups) grid = ngroups;
-    fft_r2c_kernel<LOG2M><<<(unsigned)grid, 256, 0, st>>>(pro, out, nlines, W);
+    fft_r2c_kernel<LOG2M><<<(unsigned)grid, 256, 0, st>>>(pro, out, nlines, TW, W);
     PDO_CUDA(cudaGetLastError());
     g_launches += 1;
     return 0;
 }
 template <int LOG2M>
-int launch_c2r(long long nlines, const double2* in, double* out, const double2* W, cudaStream_t st) {
+int launch_c2r(long long nlines, const double2* in, double* out, const double2* TW, const double2* W, cudaStream_t st) {
     using C = LineCfg<LOG2M>;
     const long long ngroups = (nlines + C::LPB - 1) / C::LPB;
     long long grid = (long long)sm_count() * 4;
     if (grid > ngroups) grid = ngroups;
-    fft_c2r_kernel<LOG2M><<<(unsigned)grid, 256, 0, st>>>(in, out, nlines, W);
+    fft_c2r_kernel<LOG2M><<<(unsigned)grid, 256, 0, st>>>(in, out, nlines, TW, W);
     PDO_CUDA(cudaGetLastError());
     g_launches += 1;
     return 0;
@@ -433,11 +705,19 @@ int fft2d_cols(int n, long long ncols, long long nplanes, long long row_stride, 
     if (!fft2d_cols_ok(n)) return fail(PDO_E_BADARG, "fft2d_cols: n = %d is not covered", n);
     if (ncols <= 0 || nplanes <= 0) return 0;
     const double2* W = nullptr;
-    if (int rc = twiddles(n, &W)) return rc;
+    if (int rc = stage_twiddles(n, &W)) return rc;
 #define PDO_COLS_CASE(L)                                                                                                         \
     case L:                                                                                                                      \
         return dir < 0 ? launch_cols<L, -1>(ncols, nplanes, row_stride, plane_stride, in, out, pro, W, st)                       \
                        : launch_cols<L, +1>(ncols, nplanes, row_stride, plane_stride, in, out, pro, W, st);
+#define PDO_PIPE_CASE(L)                                                                                                         \
+    case L:                                                                                                                      \
+        return dir < 0 ? launch_cols_pipe<L, -1>(ncols, nplanes, row_stride, plane_stride, in, out, pro, W, st)                  \
+                       : launch_cols_pipe<L, +1>(ncols, nplanes, row_stride, plane_stride, in, out, pro, W, st);
+    if (cols_pipe_enabled()) {
+        switch (ilog2(n)) { PDO_PIPE_CASE(7) PDO_PIPE_CASE(8) PDO_PIPE_CASE(9) default: break; }
+    }
+#undef PDO_PIPE_CASE
     switch (ilog2(n)) {
         PDO_COLS_CASE(4) PDO_COLS_CASE(5) PDO_COLS_CASE(6) PDO_COLS_CASE(7) PDO_COLS_CASE(8) PDO_COLS_CASE(9) PDO_COLS_CASE(10)
     }
@@ -448,17 +728,18 @@ int fft2d_cols(int n, long long ncols, long long nplanes, long long row_stride, 
 int fft2d_r2c_lines(int nx, long long nlines, const RealPro& pro, double2* out, cudaStream_t st) {
     if (!fft2d_x_ok(nx)) return fail(PDO_E_BADARG, "fft2d_r2c: nx = %d is not covered", nx);
     if (nlines <= 0) return 0;
-    const double2* W = nullptr;
+    const double2 *W = nullptr, *TW = nullptr;
     if (int rc = twiddles(nx, &W)) return rc;
+    if (int rc = stage_twiddles(nx / 2, &TW)) return rc;
     switch (ilog2(nx / 2)) {
-        case 3: return launch_r2c<3>(nlines, pro, out, W, st);
-        case 4: return launch_r2c<4>(nlines, pro, out, W, st);
-        case 5: return launch_r2c<5>(nlines, pro, out, W, st);
-        case 6: return launch_r2c<6>(nlines, pro, out, W, st);
-        case 7: return launch_r2c<7>(nlines, pro, out, W, st);
-        case 8: return launch_r2c<8>(nlines, pro, out, W, st);
-        case 9: return launch_r2c<9>(nlines, pro, out, W, st);
-        case 10: return launch_r2c<10>(nlines, pro, out, W, st);
+        case 3: return launch_r2c<3>(nlines, pro, out, TW, W, st);
+        case 4: return launch_r2c<4>(nlines, pro, out, TW, W, st);
+        case 5: return launch_r2c<5>(nlines, pro, out, TW, W, st);
+        case 6: return launch_r2c<6>(nlines, pro, out, TW, W, st);
+        case 7: return launch_r2c<7>(nlines, pro, out, TW, W, st);
+        case 8: return launch_r2c<8>(nlines, pro, out, TW, W, st);
+        case 9: return launch_r2c<9>(nlines, pro, out, TW, W, st);
+        case 10: return launch_r2c<10>(nlines, pro, out, TW, W, st);
     }
     return fail(PDO_E_BADARG, "fft2d_r2c: nx = %d", nx);
 }
@@ -466,17 +747,18 @@ int fft2d_r2c_lines(int nx, long long nlines, const RealPro& pro, double2* out, 
 int fft2d_c2r_lines(int nx, long long nlines, const double2* in, double* out, cudaStream_t st) {
     if (!fft2d_x_ok(nx)) return fail(PDO_E_BADARG, "fft2d_c2r: nx = %d is not covered", nx);
     if (nlines <= 0) return 0;
-    const double2* W = nullptr;
+    const double2 *W = nullptr, *TW = nullptr;
     if (int rc = twiddles(nx, &W)) return rc;
+    if (int rc = stage_twiddles(nx / 2, &TW)) return rc;
     switch (ilog2(nx / 2)) {
-        case 3: return launch_c2r<3>(nlines, in, out, W, st);
-        case 4: return launch_c2r<4>(nlines, in, out, W, st);
-        case 5: return launch_c2r<5>(nlines, in, out, W, st);
-        case 6: return launch_c2r<6>(nlines, in, out, W, st);
-        case 7: return launch_c2r<7>(nlines, in, out, W, st);
-        case 8: return launch_c2r<8>(nlines, in, out, W, st);
-        case 9: return launch_c2r<9>(nlines, in, out, W, st);
-        case 10: return launch_c2r<10>(nlines, in, out, W, st);
+        case 3: return launch_c2r<3>(nlines, in, out, TW, W, st);
+        case 4: return launch_c2r<4>(nlines, in, out, TW, W, st);
+        case 5: return launch_c2r<5>(nlines, in, out, TW, W, st);
+        case 6: return launch_c2r<6>(nlines, in, out, TW, W, st);
+        case 7: return launch_c2r<7>(nlines, in, out, TW, W, st);
+        case 8: return launch_c2r<8>(nlines, in, out, TW, W, st);
+        case 9: return launch_c2r<9>(nlines, in, out, TW, W, st);
+        case 10: return launch_c2r<10>(nlines, in, out, TW, W, st);
     }
     return fail(PDO_E_BADARG, "fft2d_c2r: nx = %d", nx);
 }
