@@ -165,6 +165,50 @@ __device__ __forceinline__ void transform(int t, const double2* __restrict__ TW,
 // ---------------------------------------------------------------------------------------------------------------------------
 // strided pass
 // ---------------------------------------------------------------------------------------------------------------------------
+// the first-load work of a strided pass (FftPro) for one thread's column
+struct ColFix {
+    const FftPro& pro;
+    double colf = 1.0, b1 = 0.0, ku = 0.0, kv = 0.0;
+    bool zero = false;
+    __device__ __forceinline__ explicit ColFix(const FftPro& p) : pro(p) {}
+    __device__ __forceinline__ void setup(int col, bool ok) {
+        colf = pro.scale;
+        zero = false;
+        if (pro.active && ok) {
+            const int c1 = col / pro.n1, c0 = col - c1 * pro.n1;
+            if (pro.poisson) { colf = __ldg(pro.A + c0); b1 = __ldg(pro.B + c1); }
+            else {
+                if (pro.A) colf *= __ldg(pro.A + c0);
+                if (pro.B) colf *= __ldg(pro.B + c1);
+            }
+            if (pro.U) { ku = __ldg(pro.KU + c0); kv = __ldg(pro.KV + c1); }
+            zero = (c0 == pro.nyq);
+        }
+    }
+    // idx: element index of (col, row, plane) in the input's layout
+    __device__ __forceinline__ double2 operator()(int row, double2 x, long long idx) const {
+        if (pro.active) {
+            if (pro.U) {
+                const double2 uu = pro.U[idx], vv = pro.V[idx];
+                const double re = ku * uu.x + kv * vv.x, im = ku * uu.y + kv * vv.y;
+                x.x += -im; x.y += re;
+            }
+            if (pro.poisson) {
+                const double kradsq = colf + b1 + __ldg(pro.C + row);
+                const double m = (kradsq <= 1.e-14) ? 0.0 : -(1.0 / kradsq) * pro.scale;
+                x.x *= m; x.y *= m;
+            } else {
+                double m = colf;
+                if (pro.C) m *= __ldg(pro.C + row);
+                x.x *= m; x.y *= m;
+            }
+            if (pro.times_i) x = make_double2(-x.y, x.x);
+            if (zero) x = make_double2(0.0, 0.0);
+        }
+        return x;
+    }
+};
+
 template <int LOG2N> struct ColsCfg {
     static constexpr int XT = LOG2N <= 5 ? 32 : (LOG2N <= 7 ? 16 : 8);
     static constexpr int THREADS = XT * (1 << LOG2N) / 8;
@@ -187,25 +231,11 @@ fft_cols_kernel(const double2* __restrict__ in, double2* __restrict__ out, int n
         const bool ok = col < ncols;
         const double2* src = in + pl * plane_stride + col;
         double2* dst = out + pl * plane_stride + col;
-        double colf = pro.scale;
-        bool zero = false;
-        if (pro.active && ok) {
-            const int c1 = col / pro.n1, c0 = col - c1 * pro.n1;
-            if (pro.A) colf *= __ldg(pro.A + c0);
-            if (pro.B) colf *= __ldg(pro.B + c1);
-            zero = (c0 == pro.nyq);
-        }
+        ColFix cf(pro);
+        cf.setup(col, ok);
+        const long long ebase = pl * plane_stride + col;
         auto ldg = [&](int row) -> double2 { return ok ? src[(long long)row * row_stride] : make_double2(0.0, 0.0); };
-        auto fix = [&](int row, double2 x) -> double2 {
-            if (pro.active) {
-                double m = colf;
-                if (pro.C) m *= __ldg(pro.C + row);
-                x.x *= m; x.y *= m;
-                if (pro.times_i) x = make_double2(-x.y, x.x);
-                if (zero) x = make_double2(0.0, 0.0);
-            }
-            return x;
-        };
+        auto fix = [&](int row, double2 x) -> double2 { return ok ? cf(row, x, ebase + (long long)row * row_stride) : x; };
         auto stg = [&](int row, double2 x) { if (ok) dst[(long long)row * row_stride] = x; };
         auto lds = [&](int pos) -> double2 { return sm[pos * XT + c]; };
         auto sts = [&](int pos, double2 x) { sm[pos * XT + c] = x; };
@@ -348,24 +378,10 @@ fft_cols_pipe_kernel(const double2* __restrict__ in, double2* __restrict__ out, 
         const int pl = tile / cblocks, cb = tile - pl * cblocks, col = cb * XT + c;
         const bool ok = col < ncols;
         double2* dst = out + pl * plane_stride + col;
-        double colf = pro.scale;
-        bool zero = false;
-        if (pro.active && ok) {
-            const int c1 = col / pro.n1, c0 = col - c1 * pro.n1;
-            if (pro.A) colf *= __ldg(pro.A + c0);
-            if (pro.B) colf *= __ldg(pro.B + c1);
-            zero = (c0 == pro.nyq);
-        }
-        auto fix = [&](int row, double2 x) -> double2 {
-            if (pro.active) {
-                double m = colf;
-                if (pro.C) m *= __ldg(pro.C + row);
-                x.x *= m; x.y *= m;
-                if (pro.times_i) x = make_double2(-x.y, x.x);
-                if (zero) x = make_double2(0.0, 0.0);
-            }
-            return x;
-        };
+        ColFix cf(pro);
+        cf.setup(col, ok);
+        const long long ebase = pl * plane_stride + col;
+        auto fix = [&](int row, double2 x) -> double2 { return ok ? cf(row, x, ebase + (long long)row * row_stride) : x; };
         double2 v[8];
         cp_async_wait<1>();   // this tile's copies (mine) have landed; the next tile's may still be in flight
         ip_stage<LOG2N, 0, SGN>(t, v, TW, buf, c, fix);

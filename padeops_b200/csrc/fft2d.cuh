@@ -10,16 +10,24 @@
 
 namespace pdo {
 
-// First load of a strided c2c pass: v(col, row) *= scale * A[col % n1] * B[col / n1] * C[row]  (null table = 1), then * i when
-// times_i, then the column with col % n1 == nyq is zeroed (nyq < 0: none).
+// First load of a strided c2c pass, with c0 = col % n1, c1 = col / n1:
+//   U, V:      v += i (KU[c0] U + KV[c1] V)        (U, V: arrays of the input's shape; the divergence of PadePoisson.F90:392-401)
+//   poisson:   v *= (s <= 1e-14 ? 0 : -scale / s), s = A[c0] + B[c1] + C[row]   (kradsq_inv and mfact, PadePoisson.F90:103-108, 413-415)
+//   otherwise: v *= scale * A[c0] * B[c1] * C[row]  (null table = 1)
+// then * i when times_i, then the column with c0 == nyq is zeroed (nyq < 0: none).
 struct FftPro {
     const double* A = nullptr;
     const double* B = nullptr;
     const double* C = nullptr;
+    const double2* U = nullptr;
+    const double2* V = nullptr;
+    const double* KU = nullptr;
+    const double* KV = nullptr;
     double scale = 1.0;
     int n1 = 1;
     int times_i = 0;
     int nyq = -1;
+    int poisson = 0;
     int active = 0;   // 0: plain load
 };
 

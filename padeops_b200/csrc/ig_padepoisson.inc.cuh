@@ -45,6 +45,17 @@ int poiss_div_xy(pdo_padepoisson_s* p, const double2* u, const double2* v, doubl
 
 // steps shared by PeriodicProjection / Periodic_getPressure*: leaves phat in f2d (z-pencil) and what in w2 (z-pencil)
 int poiss_solve(pdo_padepoisson_s* p, const double2* uhat, const double2* vhat, const double2* what, cudaStream_t st) {
+    if (p->alias && fft3d_own_z(p->sp->ft)) {
+        // one GPU column: y- and z-pencils coincide and the hand-written z pass takes the pointwise work on its first load —
+        // "+ i (k1 u + k2 v)" on the way into the forward transform, "-kradsq_inv mfact" on the way into the backward one
+        if (int rc = pdo_pade6stagg_ddz_E2C(p->derivZ, (const double*)what, (double*)p->f2d, 1, 0, 0, st)) return rc;
+        FftPro div;
+        div.U = uhat; div.V = vhat; div.KU = p->sp->k1y; div.KV = p->sp->k2;
+        if (int rc = fft3d_z_fused(p->sp->ft, p->f2d, p->f2d, -1, div, st)) return rc;
+        FftPro inv;
+        inv.poisson = 1; inv.A = p->k1sq; inv.B = p->k2sq; inv.C = p->k3sq; inv.scale = p->mfact;
+        return fft3d_z_fused(p->sp->ft, p->f2d, p->f2d, +1, inv, st);
+    }
     if (int rc = poiss_div_xy(p, uhat, vhat, p->f2dy, st)) return rc;
     const double2 *uz = p->f2dy, *wz = what;
     if (!p->alias) {

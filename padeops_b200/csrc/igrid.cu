@@ -209,25 +209,6 @@ int fft_muldiff(pdo_igrid_s* g, bool edge, double2* out, const double* a, const 
     rp.mode = d ? 4 : 3;
     return fft3d_forward_xy_pro(edge ? g->spE->ft : g->spC->ft, rp, out, st);
 }
-// dst += src (complex arrays viewed as doubles)
-int cadd(double2* dst, const double2* src, long long n, cudaStream_t st) {
-    double* d = (double*)dst;
-    const double* s = (const double*)src;
-    return launch_ew(2 * n, st, [=] __device__(long long i) { d[i] += s[i]; });
-}
-// dst += i k f  with k along index 1 (which = 1) or 2 (which = 2) of a y-pencil (mTimes_ik*_ip followed by the add)
-int cadd_ik(pdo_spectral_s* s, int which, double2* dst, const double2* f, cudaStream_t st) {
-    const int n1 = s->si.ysz[0], n2 = s->si.ysz[1];
-    const double* k = which == 1 ? s->k1y : s->k2;
-    const int w = which;
-    return launch_ew(vol(s->si.ysz), st, [=] __device__(long long i) {
-        const double kv = (w == 1) ? k[(int)(i % n1)] : k[(int)((i / n1) % n2)];
-        const double2 q = f[i];
-        double2 a = dst[i];
-        a.x += -kv * q.y; a.y += kv * q.x;
-        dst[i] = a;
-    });
-}
 // out = sum_i c_i x_i over complex arrays (as doubles); up to five terms, out may alias any x_i
 struct Lin5 { double c[5]; const double* x[5]; int n; };
 int lincomb(double2* out, const Lin5& L, long long ncplx, cudaStream_t st) {
@@ -413,7 +394,10 @@ int ig_nonlinear_rot(pdo_igrid_s* g, cudaStream_t st) {
 
 // rhs = -half * (sum of the terms) (skew-symmetric form; +1 for the rotational one), then addViscousTerm (igrid.F90:1663-1665,
 // 1914-1941): ONE pass per component over its terms
-int ig_finish_rhs(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStream_t st) {
+// With `upd` the stage update that consumes the right-hand side runs in the same pass (S_dst = sum_t c_t x_t, the term x_t == r
+// taken from the register; same order of operations as the stand-alone pass); the right-hand side itself is stored only if keep_r.
+struct StageUpd { double c[5]; const double2* x[5]; int n; int ridx; double2* dst; };
+int ig_finish_rhs(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStream_t st, const StageUpd* upd = nullptr, bool keep_r = true) {
     const bool visc = !g->prm.is_inviscid;
     const double scale = g->prm.rotational_advection ? 1.0 : -0.5;
     const double oneByRe = visc ? 1.0 / g->prm.Re : 0.0;
@@ -425,6 +409,10 @@ int ig_finish_rhs(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStr
         const int n1 = s->si.ysz[0], n2 = s->si.ysz[1];
         const double *k1 = s->k1y, *k2 = s->k2;
         const pdo_igrid_s::AsmDesc D = g->asmd[c];
+        StageUpd U{};
+        const bool fuse = upd != nullptr;
+        if (fuse) U = upd[c];
+        const bool keep = keep_r || !fuse;
         IG(launch_ew(vol(s->si.ysz), st, [=] __device__(long long i) {
             const double ka = k1[(int)(i % n1)], kb = k2[(int)((i / n1) % n2)];
             double2 a = D.t[0].p[i];
@@ -446,7 +434,19 @@ int ig_finish_rhs(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStr
                 a.x += oneByRe * (-ksq * q.x + dd.x);
                 a.y += oneByRe * (-ksq * q.y + dd.y);
             }
-            r[i] = a;
+            if (keep) r[i] = a;
+            if (fuse) {
+                double2 x0 = U.ridx == 0 ? a : U.x[0][i];
+                double2 acc = make_double2(U.c[0] * x0.x, U.c[0] * x0.y);
+#pragma unroll
+                for (int t = 1; t < 5; ++t) {
+                    if (t < U.n) {
+                        const double2 xt = U.ridx == t ? a : U.x[t][i];
+                        acc.x += U.c[t] * xt.x; acc.y += U.c[t] * xt.y;
+                    }
+                }
+                U.dst[i] = acc;
+            }
         }));
     }
     return 0;
@@ -454,15 +454,33 @@ int ig_finish_rhs(pdo_igrid_s* g, double2* ru, double2* rv, double2* rw, cudaStr
 
 #include "ig_sgs.inc.cuh"
 
-int ig_populate_rhs(pdo_igrid_s* g, double2** r, cudaStream_t st) {
+// PopulateRHS (igrid.F90:1793-1911) followed by the Runge-Kutta stage update that consumes it:
+// S[dst_slot] = sum_t coef_t terms_t, with r among the terms.
+int ig_stage_update(pdo_igrid_s* g, int dst_slot, int nterms, const double* coef, double2* const (*terms)[3], cudaStream_t st);
+int ig_rhs_and_update(pdo_igrid_s* g, double2** r, int dst_slot, int nterms, const double* coef, double2* const (*terms)[3], bool keep_r,
+                      cudaStream_t st) {
     if (g->prm.rotational_advection) IG(ig_nonlinear_rot(g, st));
     else IG(ig_nonlinear_skew(g, st));
+    if (!g->sgs_on && !g->hit) {   // nothing else touches the right-hand side: assemble it and update the stage in one pass
+        StageUpd U[3];
+        for (int c = 0; c < 3; ++c) {
+            U[c].n = nterms; U[c].ridx = -1; U[c].dst = g->S[dst_slot][c];
+            for (int t = 0; t < nterms; ++t) {
+                U[c].c[t] = coef[t]; U[c].x[t] = terms[t][c];
+                if (terms[t][c] == r[c]) U[c].ridx = t;
+            }
+        }
+        IG(ig_finish_rhs(g, r[0], r[1], r[2], st, U, keep_r));
+        for (int c = 0; c < 3; ++c) g->cur[c] = g->S[dst_slot][c];
+        g->new_timestep = false;
+        return 0;
+    }
     IG(ig_finish_rhs(g, r[0], r[1], r[2], st));
     if (g->sgs_on) IG(ig_sgs_rhs(g, r[0], r[1], r[2], st));   // Step 6 (igrid.F90:1866-1871)
     if (g->hit)   // Step 8 (igrid.F90:1907-1910)
         IG(hit_get_rhs_dev(g->hit, r[0], r[1], r[2], g->cur[0], g->cur[1], g->cur[2], g->new_timestep, st));
     g->new_timestep = false;
-    return 0;
+    return ig_stage_update(g, dst_slot, nterms, coef, terms, st);
 }
 
 // ---- igrid.F90:1961-1990
@@ -493,19 +511,14 @@ int ig_stage_update(pdo_igrid_s* g, int dst_slot, int nterms, const double* coef
 
 // ---- igrid.F90:1105-1173
 int ig_tvd_rk3(pdo_igrid_s* g, double dt, cudaStream_t st) {
-    IG(ig_populate_rhs(g, g->R, st));
     { double c[2] = {1.0, dt}; double2* const t[2][3] = {{g->S[0][0], g->S[0][1], g->S[0][2]}, {g->R[0], g->R[1], g->R[2]}};
-      IG(ig_stage_update(g, 1, 2, c, t, st)); }
+      IG(ig_rhs_and_update(g, g->R, 1, 2, c, t, false, st)); }
     IG(ig_project_and_prep(g, false, st));
-    IG(ig_populate_rhs(g, g->R, st));
-    { double c[3] = {3.0 / 4.0, 1.0 / 4.0, (1.0 / 4.0) * dt};
-      double2* const t[3][3] = {{g->S[0][0], g->S[0][1], g->S[0][2]}, {g->S[1][0], g->S[1][1], g->S[1][2]}, {g->R[0], g->R[1], g->R[2]}};
-      IG(ig_stage_update(g, 1, 3, c, t, st)); }
+    { double c[3] = {3.0 / 4.0, 1.0 / 4.0, (1.0 / 4.0) * dt}; double2* const t[3][3] = {{g->S[0][0], g->S[0][1], g->S[0][2]}, {g->S[1][0], g->S[1][1], g->S[1][2]}, {g->R[0], g->R[1], g->R[2]}};
+      IG(ig_rhs_and_update(g, g->R, 1, 3, c, t, false, st)); }
     IG(ig_project_and_prep(g, false, st));
-    IG(ig_populate_rhs(g, g->R, st));
-    { double c[3] = {1.0 / 3.0, 2.0 / 3.0, (2.0 / 3.0) * dt};
-      double2* const t[3][3] = {{g->S[0][0], g->S[0][1], g->S[0][2]}, {g->S[1][0], g->S[1][1], g->S[1][2]}, {g->R[0], g->R[1], g->R[2]}};
-      IG(ig_stage_update(g, 0, 3, c, t, st)); }
+    { double c[3] = {1.0 / 3.0, 2.0 / 3.0, (2.0 / 3.0) * dt}; double2* const t[3][3] = {{g->S[0][0], g->S[0][1], g->S[0][2]}, {g->S[1][0], g->S[1][1], g->S[1][2]}, {g->R[0], g->R[1], g->R[2]}};
+      IG(ig_rhs_and_update(g, g->R, 0, 3, c, t, false, st)); }
     return ig_project_and_prep(g, false, st);
 }
 
@@ -520,21 +533,20 @@ int ig_ssp_rk45(pdo_igrid_s* g, double dt, cudaStream_t st) {
 #define SL(s) {g->S[s][0], g->S[s][1], g->S[s][2]}
 #define RR {g->R[0], g->R[1], g->R[2]}
 #define RXX {g->RX[0], g->RX[1], g->RX[2]}
-    IG(ig_populate_rhs(g, g->R, st));
-    { double c[2] = {1.0, b01 * dt}; double2* const t[2][3] = {SL(0), RR}; IG(ig_stage_update(g, 1, 2, c, t, st)); }
+    { double c[2] = {1.0, b01 * dt}; double2* const t[2][3] = {SL(0), RR};
+      IG(ig_rhs_and_update(g, g->R, 1, 2, c, t, false, st)); }
     IG(ig_project_and_prep(g, false, st));
-    IG(ig_populate_rhs(g, g->R, st));
-    { double c[3] = {a20, a21, b12 * dt}; double2* const t[3][3] = {SL(0), SL(1), RR}; IG(ig_stage_update(g, 2, 3, c, t, st)); }
+    { double c[3] = {a20, a21, b12 * dt}; double2* const t[3][3] = {SL(0), SL(1), RR};
+      IG(ig_rhs_and_update(g, g->R, 2, 3, c, t, false, st)); }
     IG(ig_project_and_prep(g, false, st));
-    IG(ig_populate_rhs(g, g->R, st));
-    { double c[3] = {a30, a32, b23 * dt}; double2* const t[3][3] = {SL(0), SL(2), RR}; IG(ig_stage_update(g, 3, 3, c, t, st)); }
+    { double c[3] = {a30, a32, b23 * dt}; double2* const t[3][3] = {SL(0), SL(2), RR};
+      IG(ig_rhs_and_update(g, g->R, 3, 3, c, t, false, st)); }
     IG(ig_project_and_prep(g, false, st));
-    IG(ig_populate_rhs(g, g->R, st));
-    { double c[3] = {a40, a43, b34 * dt}; double2* const t[3][3] = {SL(0), SL(3), RR}; IG(ig_stage_update(g, 0, 3, c, t, st)); }
+    { double c[3] = {a40, a43, b34 * dt}; double2* const t[3][3] = {SL(0), SL(3), RR};
+      IG(ig_rhs_and_update(g, g->R, 0, 3, c, t, true, st)); }   // this right-hand side enters the last stage as well
     IG(ig_project_and_prep(g, false, st));
-    IG(ig_populate_rhs(g, g->RX, st));
     { double c[5] = {a52, a53, b35 * dt, a54, b45 * dt}; double2* const t[5][3] = {SL(2), SL(3), RR, SL(0), RXX};
-      IG(ig_stage_update(g, 0, 5, c, t, st)); }
+      IG(ig_rhs_and_update(g, g->RX, 0, 5, c, t, false, st)); }
 #undef SL
 #undef RR
 #undef RXX

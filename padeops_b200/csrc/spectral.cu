@@ -300,6 +300,13 @@ int fft3d_z_pro(pdo_fft3d_t f, const double2* in, double2* out, int dir, const d
     pro.active = 1; pro.scale = scale; pro.n1 = f->si.zsz[0]; pro.A = gx; pro.B = gy; pro.C = gz;
     return own_z_pass(f, in, out, dir, pro, st);
 }
+// the same with a caller-built first-load recipe (n1 and active are filled in here)
+int fft3d_z_fused(pdo_fft3d_t f, const double2* in, double2* out, int dir, FftPro pro, cudaStream_t st) {
+    if (!f->own_z) return fail(PDO_E_UNSUPPORTED, "fft3d_z_fused needs the hand-written z pass");
+    pro.active = 1;
+    pro.n1 = f->si.zsz[0];
+    return own_z_pass(f, in, out, dir, pro, st);
+}
 bool fft3d_own_z(pdo_fft3d_t f) { return f->own_z; }
 bool fft3d_own_xy(pdo_fft3d_t f) { return f->own_xy; }
 // Same inverse for a caller-owned scratch array that already carries the 1/(nx ny) factor: it is consumed in place

@@ -32,6 +32,7 @@ int fft3d_backward_yx_mul(pdo_fft3d_t f, const double2* in_cplx_y, int which, co
 int fft3d_forward_xy_pro(pdo_fft3d_t f, const RealPro& pro, double2* out_cplx_y, cudaStream_t st);
 int fft3d_z_pro(pdo_fft3d_t f, const double2* in, double2* out, int dir, const double* gx, const double* gy, const double* gz, double scale,
                 cudaStream_t st);
+int fft3d_z_fused(pdo_fft3d_t f, const double2* in, double2* out, int dir, FftPro pro, cudaStream_t st);
 bool fft3d_own_z(pdo_fft3d_t f);
 bool fft3d_own_xy(pdo_fft3d_t f);
 // c2c along the slowest index of an array (nz, cols) with ANY column count (the real z-Fourier procedures transform pairs of
