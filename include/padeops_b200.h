@@ -336,8 +336,10 @@ int pdo_padepoisson_init(pdo_padepoisson_t* h, double dx, double dy, double dz, 
 /* the same with the reference's PeriodicInZ argument.  PeriodicInZ = .false., computeStokesPressure = .false. (:180-230, 459-623):
    walls at both ends of z — PressureProjection extends the horizontal divergence evenly and w oddly to 2 nz planes, solves in
    z-Fourier space with the z scheme's modified wavenumber and the half-cell shifts, and leaves w = 0 on both walls;
-   DivergenceCheck uses derivZ%ddz_E2C(-1, -1).  derivZ must have been initialised with the same periodicity; computeStokesPressure: init3; the pressure getters
-   are periodic-only (PDO_E_UNSUPPORTED otherwise). */
+   DivergenceCheck uses derivZ%ddz_E2C(-1, -1).  derivZ must have been initialised with the same periodicity; computeStokesPressure: init3.  The pressure
+   getters run with walls too (:762-896, 963-1160): getPressure projects copies of its intent(in) arguments and returns
+   phat (+ phat_z1 + phat_z2 with computeStokesPressure, the pieces GetStokesPressure :641-714 keeps); getPressureAndUpdateRHS
+   projects in place and, as in the reference, adds the Stokes pieces of the LAST getPressure call (:1146-1156; zero before any). */
 int pdo_padepoisson_init2(pdo_padepoisson_t* h, double dx, double dy, double dz, pdo_spectral_t sp, pdo_spectral_t spE,
                           pdo_pade6stagg_t derivZ, int periodic_in_z);
 /* ... and with computeStokesPressure and Lz (:232-296, 320-384, 444-458, 597-609; walls only): before the projection the harmonic

@@ -295,31 +295,37 @@ class PadePoisson:
         f2d = f2d * self.mfact
         return f2d, w2
 
-    def ProjectStokesPressure(self, uhat, vhat, what):
+    def ProjectStokesPressure(self, uhat, vhat, what, store=False):
         """PadePoisson.F90:320-384: the harmonic (Stokes) pressure that cancels w on the two walls, bottom first, then top with the
-        already corrected top plane; returns (uhatInZ, vhatInZ, w2)."""
+        already corrected top plane; returns (uhatInZ, vhatInZ, w2).  store = True is GetStokesPressure (:641-714): the same
+        arithmetic, and the two pressure pieces are kept in phat_z1 / phat_z2."""
         nz = self.sp.nz
         u, v, w2 = np.array(uhat, dtype=complex), np.array(vhat, dtype=complex), np.array(what, dtype=complex)
         chat = -w2[0] * self.denFact
         phat = imi * chat[None] * self.cosh_bot
+        if store:
+            self.phat_z1 = phat.copy()
         u = u - self.k1inZ[None] * phat
         v = v - self.k2inZ[None] * phat
         w2[0] = 0.0
         w2[1:] = w2[1:] - chat[None] * self.sinh_bot[1:]
         chat = w2[nz] * self.denFact
         phat = imi * chat[None] * self.cosh_top
+        if store:
+            self.phat_z2 = phat.copy()
         u = u - self.k1inZ[None] * phat
         v = v - self.k2inZ[None] * phat
         w2[:nz] = w2[:nz] - chat[None] * self.sinh_top[:nz]
         w2[nz] = 0.0
         return u, v, w2
 
-    def _wall_projection(self, uhat, vhat, what):
-        """PadePoisson.F90:444-623"""
+    def _wall_projection(self, uhat, vhat, what, want_pressure=False, store_stokes=False):
+        """PadePoisson.F90:444-623 (PressureProjection), :762-896 (getPressure), :963-1160 (getPressureAndUpdateRHS): the three
+        share Steps 0-7.  want_pressure: also return phat (z-pencil, before the Stokes terms are added)."""
         sp = self.sp
         nz = sp.nz
         if self.computeStokesPressure:
-            uZ, vZ, w2 = self.ProjectStokesPressure(uhat, vhat, what)
+            uZ, vZ, w2 = self.ProjectStokesPressure(uhat, vhat, what, store=store_stokes)
             f2d = self.k1inZ[None] * uZ
             f2d = f2d + self.k2inZ[None] * vZ
             f2d = -f2d.imag + 1j * f2d.real
@@ -345,8 +351,10 @@ class PadePoisson:
         w2[nz] = 0.0
         if self.computeStokesPressure:                                         # :597-609
             g = -f2d.imag + 1j * f2d.real
-            return uZ - g * self.k1inZ[None], vZ - g * self.k2inZ[None], w2
-        return uhat - imi * sp.k1 * f2d, vhat - imi * sp.k2 * f2d, w2
+            out = (uZ - g * self.k1inZ[None], vZ - g * self.k2inZ[None], w2)
+        else:
+            out = (uhat - imi * sp.k1 * f2d, vhat - imi * sp.k2 * f2d, w2)
+        return out + (f2d,) if want_pressure else out
 
     def PressureProjection(self, uhat, vhat, what):
         if not self.PeriodicInZ:
@@ -360,11 +368,27 @@ class PadePoisson:
         return uhat_new, vhat_new, what_new
 
     def getPressure(self, uhat, vhat, what):
+        if not self.PeriodicInZ:                                               # :762-896
+            f2d = self._wall_projection(uhat, vhat, what, want_pressure=True, store_stokes=True)[3]
+            if self.computeStokesPressure:
+                f2d = f2d + self.phat_z1 + self.phat_z2
+            return self.sp.ifft(f2d)
         f2d, _ = self._solve(uhat, vhat, what)
         return self.sp.ifft(f2d)
 
     def getPressureAndUpdateRHS(self, uhat, vhat, what):
         sp = self.sp
+        if not self.PeriodicInZ:
+            # :963-1160.  With computeStokesPressure this routine calls ProjectStokesPressure, which does NOT refresh phat_z1 /
+            # phat_z2, and then adds them (:1146-1156): the pressure it returns carries the Stokes pieces of the LAST getPressure
+            # call (zero here before any; unallocated-array garbage in the reference).  The updated right-hand sides do not depend
+            # on that.
+            u, v, w, f2d = self._wall_projection(uhat, vhat, what, want_pressure=True, store_stokes=False)
+            if self.computeStokesPressure:
+                z1 = getattr(self, "phat_z1", None)
+                if z1 is not None:
+                    f2d = f2d + self.phat_z1 + self.phat_z2
+            return u, v, w, sp.ifft(f2d)
         f2d, w2 = self._solve(uhat, vhat, what)
         dwdz = self.derivZ.ddz_C2E(f2d)
         return uhat - imi * sp.k1 * f2d, vhat - imi * sp.k2 * f2d, w2 - dwdz, sp.ifft(f2d)

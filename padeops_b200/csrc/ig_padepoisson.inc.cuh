@@ -26,6 +26,9 @@ struct pdo_padepoisson_s {
     double Lz = 0.0;
     double *k1z = nullptr, *k2z = nullptr, *denfact = nullptr;
     double2* vhatInZ = nullptr;
+    // GetStokesPressure (:641-714) keeps the two harmonic pressure pieces for getPressure; getPressureAndUpdateRHS adds whatever
+    // the LAST getPressure left there (:1146-1156 — it runs ProjectStokesPressure, which does not refresh them); allocated zeroed
+    double2 *phat_z1 = nullptr, *phat_z2 = nullptr;
 };
 
 namespace {
@@ -110,6 +113,61 @@ int poiss_correct(pdo_padepoisson_s* p, double2* uhat, double2* vhat, double2* w
     });
 }
 
+// PeriodicProjection (PadePoisson.F90:386-432) on z-PENCIL copies of (uhat, vhat, what), in place: the pointwise steps do not care
+// which pencil they run in, so a caller that already holds the three fields in the z-pencil (igrid, after dealiasing there) skips
+// the four transposes of the y-pencil entry point.  Same operations per element, same results.  phat stays in f2d (z-pencil).
+int poiss_projection_z(pdo_padepoisson_s* p, double2* zu, double2* zv, double2* zw, cudaStream_t st) {
+    const pdo_spectral_s* s = p->sp;
+    const int n1 = p->sC.zsz[0], n2 = p->sC.zsz[1];
+    const long long n = vol(p->sC.zsz);
+    const double *k1 = s->k1y, *k2 = s->k2z;
+    double2* f2d = p->f2d;
+    if (int rc = pdo_pade6stagg_ddz_E2C(p->derivZ, (const double*)zw, (double*)f2d, 1, 0, 0, st)) return rc;
+    const double *k1sq = p->k1sq, *k2sq = p->k2sq, *k3sq = p->k3sq;
+    const double mfact = p->mfact;
+    if (fft3d_own_z(s->ft)) {
+        FftPro div;
+        div.U = zu; div.V = zv; div.KU = k1; div.KV = k2;
+        if (int rc = fft3d_z_fused(s->ft, f2d, f2d, -1, div, st)) return rc;
+        FftPro inv;
+        inv.poisson = 1; inv.A = k1sq; inv.B = k2sq; inv.C = k3sq; inv.scale = mfact;
+        if (int rc = fft3d_z_fused(s->ft, f2d, f2d, +1, inv, st)) return rc;
+    } else {
+        if (int rc = launch_ew(n, st, [=] __device__(long long i) {   // f2d += i (k1 u + k2 v)
+                const double a = k1[(int)(i % n1)], b = k2[(int)((i / n1) % n2)];
+                const double2 uu = zu[i], vv = zv[i];
+                const double re = a * uu.x + b * vv.x, im = a * uu.y + b * vv.y;
+                double2 q = f2d[i];
+                q.x += -im; q.y += re;
+                f2d[i] = q;
+            })) return rc;
+        if (int rc = fft3d_z_inplace(s->ft, f2d, -1, st)) return rc;
+        if (int rc = launch_ew(n, st, [=] __device__(long long i) {
+                const int ii = (int)(i % n1);
+                const long long t = i / n1;
+                const int jj = (int)(t % n2), kk = (int)(t / n2);
+                const double kradsq = k1sq[ii] + k2sq[jj] + k3sq[kk];
+                const double m = (kradsq <= 1.e-14) ? 0.0 : -(1.0 / kradsq) * mfact;
+                double2 a = f2d[i];
+                a.x *= m; a.y *= m;
+                f2d[i] = a;
+            })) return rc;
+        if (int rc = fft3d_z_inplace(s->ft, f2d, +1, st)) return rc;
+    }
+    if (int rc = pdo_pade6stagg_ddz_C2E(p->derivZ, (const double*)f2d, (double*)p->dwdz, 1, 0, 0, st)) return rc;
+    const double2* dw = p->dwdz;
+    if (int rc = launch_ew(vol(p->sE.zsz), st, [=] __device__(long long i) { double2 a = zw[i]; const double2 b = dw[i]; a.x -= b.x; a.y -= b.y; zw[i] = a; })) return rc;
+    p->phat_y = nullptr;   // the pressure was not taken to the y-pencil
+    return launch_ew(n, st, [=] __device__(long long i) {
+        const double a = k1[(int)(i % n1)], b = k2[(int)((i / n1) % n2)];
+        const double2 q = f2d[i];
+        double2 uu = zu[i], vv = zv[i];
+        uu.x += a * q.y; uu.y -= a * q.x;  // u - i k1 p
+        vv.x += b * q.y; vv.y -= b * q.x;
+        zu[i] = uu; zv[i] = vv;
+    });
+}
+
 int poiss_divergence(pdo_padepoisson_s* p, const double2* uhat, const double2* vhat, const double2* what, double* div, cudaStream_t st) {
     const double2* wz = what;
     if (!p->alias) {
@@ -156,7 +214,7 @@ int global_max(pdo_spectral_s* s, const double* a, long long n, int use_abs, dou
 // 1e13 / -4e13 / 4e13) instead of being read from four 3-D tables.
 __global__ void __launch_bounds__(128) stokes_kernel(double2* __restrict__ u, double2* __restrict__ v, double2* __restrict__ w2, long long cols,
                                                      int n1, int nz, double Lz, const double* __restrict__ k1z, const double* __restrict__ k2z,
-                                                     const double* __restrict__ denfact) {
+                                                     const double* __restrict__ denfact, double2* __restrict__ pz1, double2* __restrict__ pz2) {
     const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (c >= cols) return;
     const double k1 = k1z[(int)(c % n1)], k2 = k2z[(int)(c / n1)];
@@ -169,6 +227,7 @@ __global__ void __launch_bounds__(128) stokes_kernel(double2* __restrict__ u, do
         const double t = lam * (Lz - zc);
         const double cb = t < 32.0 ? cosh(t) : 4.0e13;
         const double2 ph = make_double2(-ch.y * cb, ch.x * cb);      // imi * chat * cosh_bot
+        if (pz1) pz1[c + cols * k] = ph;
         double2 a = u[c + cols * k]; a.x -= k1 * ph.x; a.y -= k1 * ph.y; u[c + cols * k] = a;
         double2 b = v[c + cols * k]; b.x -= k2 * ph.x; b.y -= k2 * ph.y; v[c + cols * k] = b;
     }
@@ -186,6 +245,7 @@ __global__ void __launch_bounds__(128) stokes_kernel(double2* __restrict__ u, do
         double t = lam * zc;
         const double ct = t < 32.0 ? cosh(t) : 1.0e13;
         const double2 ph = make_double2(-ch.y * ct, ch.x * ct);
+        if (pz2) pz2[c + cols * k] = ph;
         double2 a = u[c + cols * k]; a.x -= k1 * ph.x; a.y -= k1 * ph.y; u[c + cols * k] = a;
         double2 b = v[c + cols * k]; b.x -= k2 * ph.x; b.y -= k2 * ph.y; v[c + cols * k] = b;
         t = lam * ((double)k * dzl);
@@ -198,7 +258,7 @@ __global__ void __launch_bounds__(128) stokes_kernel(double2* __restrict__ u, do
 // PressureProjection with walls (PadePoisson.F90:444-623): the horizontal divergence is extended
 // evenly and w oddly about both walls to 2 nz planes, one c2c-z pair solves and projects (the half-cell shifts ride on
 // k3modcm / k3modcp), the upper halves come back and w is zero on both walls.
-int poiss_wall_projection(pdo_padepoisson_s* p, double2* uhat, double2* vhat, double2* what, cudaStream_t st) {
+int poiss_wall_projection(pdo_padepoisson_s* p, double2* uhat, double2* vhat, double2* what, cudaStream_t st, bool store_stokes = false) {
     const int nz = p->sp->nz, n1 = p->sC.zsz[0], n2 = p->sC.zsz[1];
     const long long cols = (long long)n1 * n2, next = cols * 2 * nz;
     const double2 *uz = nullptr, *wz = what;
@@ -211,7 +271,8 @@ int poiss_wall_projection(pdo_padepoisson_s* p, double2* uhat, double2* vhat, do
             if (int rc = decomp_transpose_device(p->dE, 2, (const double*)what, (double*)p->w2, 2, st)) return rc;
             uZ = p->uhatInZ; vZ = p->vhatInZ; w2 = p->w2;
         }
-        stokes_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(uZ, vZ, w2, cols, n1, nz, p->Lz, p->k1z, p->k2z, p->denfact);
+        stokes_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(uZ, vZ, w2, cols, n1, nz, p->Lz, p->k1z, p->k2z, p->denfact,
+                                                                      store_stokes ? p->phat_z1 : nullptr, store_stokes ? p->phat_z2 : nullptr);
         PDO_CUDA(cudaGetLastError());
         g_launches += 1;
         const double *k1z = p->k1z, *k2z = p->k2z;
@@ -309,6 +370,43 @@ int poiss_wall_projection(pdo_padepoisson_s* p, double2* uhat, double2* vhat, do
         vv.x += b * q.y; vv.y -= b * q.x;
         uhat[i] = uu; vhat[i] = vv;
     });
+}
+
+// the pressure of the wall-bounded solver after poiss_wall_projection (getPressure :880-896, getPressureAndUpdateRHS :1144-1160):
+// phat = f2d (+ phat_z1 + phat_z2 with computeStokesPressure), taken to the y-pencil and to physical space
+int poiss_wall_pressure_out(pdo_padepoisson_s* p, double* pressure, cudaStream_t st) {
+    const double2* ph = p->phat_y;
+    if (p->stokes) {
+        double2* f2d = p->f2d;
+        const double2 *z1 = p->phat_z1, *z2 = p->phat_z2;
+        if (z1) {
+            if (int rc = launch_ew(vol(p->sC.zsz), st, [=] __device__(long long i) {
+                    double2 a = f2d[i];
+                    const double2 b = z1[i], c = z2[i];
+                    a.x += b.x; a.y += b.y;
+                    a.x += c.x; a.y += c.y;
+                    f2d[i] = a;
+                })) return rc;
+        }
+        ph = p->f2d;
+        if (!p->alias) {
+            if (int rc = decomp_transpose_device(p->dC, 3, (const double*)p->f2d, (double*)p->f2dy, 2, st)) return rc;
+            ph = p->f2dy;
+        }
+    }
+    const size_t bytes = sizeof(double) * (size_t)vol(p->sp->pi.xsz);
+    return with_device_views(pressure, 0, pressure, bytes, st, [&](const void*, void* d_o) {
+        return fft3d_backward_yx(p->sp->ft, ph, (double*)d_o, false, st);
+    });
+}
+int poiss_alloc_stokes_pieces(pdo_padepoisson_s* p) {
+    if (p->phat_z1) return 0;
+    const size_t bytes = sizeof(double2) * (size_t)vol(p->sC.zsz);
+    PDO_CUDA(cudaMalloc(&p->phat_z1, bytes));
+    PDO_CUDA(cudaMalloc(&p->phat_z2, bytes));
+    PDO_CUDA(cudaMemset(p->phat_z1, 0, bytes));
+    PDO_CUDA(cudaMemset(p->phat_z2, 0, bytes));
+    return 0;
 }
 
 int poiss_projection(pdo_padepoisson_s* p, double2* u, double2* v, double2* w, cudaStream_t st) {
@@ -495,8 +593,28 @@ int pdo_padepoisson_pressure_projection(pdo_padepoisson_t p, double* uhat, doubl
 int pdo_padepoisson_get_pressure(pdo_padepoisson_t p, const double* uhat, const double* vhat, const double* what, double* pressure,
                                  void* stream) {
     if (!p || !uhat || !vhat || !what || !pressure) return fail(PDO_E_BADARG, "null argument");
-    if (!p->periodic_in_z) return fail(PDO_E_UNSUPPORTED, "padepoisson getPressure: only PressureProjection and DivergenceCheck are built for PeriodicInZ = .false.");
     cudaStream_t st = (cudaStream_t)stream;
+    if (!p->periodic_in_z) {
+        // walls (:762-896): the projection's Steps 0-7 on COPIES of the intent(in) right-hand sides, GetStokesPressure's two
+        // pressure pieces kept, phat = f2d + phat_z1 + phat_z2
+        if (p->stokes) { if (int rc = poiss_alloc_stokes_pieces(p)) return rc; }
+        return with_uvw(p, uhat, vhat, what, false, st, [&](double2* u, double2* v, double2* w) -> int {
+            const size_t bC = sizeof(double2) * (size_t)vol(p->sp->si.ysz), bE = sizeof(double2) * (size_t)vol(p->spE->si.ysz);
+            double2* cp[3] = {nullptr, nullptr, nullptr};
+            const double2* src[3] = {u, v, w};
+            const size_t nb[3] = {bC, bC, bE};
+            int rc = 0;
+            for (int i = 0; i < 3 && !rc; ++i) {
+                if (cudaMalloc(&cp[i], nb[i]) != cudaSuccess) { cudaGetLastError(); rc = fail(PDO_E_CUDA, "getPressure: out of device memory"); break; }
+                if (cudaMemcpyAsync(cp[i], src[i], nb[i], cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = fail(PDO_E_CUDA, "getPressure: copy failed");
+            }
+            if (!rc) rc = poiss_wall_projection(p, cp[0], cp[1], cp[2], st, true);
+            if (!rc) rc = poiss_wall_pressure_out(p, pressure, st);
+            cudaStreamSynchronize(st);
+            for (int i = 0; i < 3; ++i) if (cp[i]) cudaFree(cp[i]);
+            return rc;
+        });
+    }
     return with_uvw(p, uhat, vhat, what, false, st, [&](double2* u, double2* v, double2* w) -> int {
         if (int rc = poiss_solve(p, u, v, w, st)) return rc;
         const double2* ph = p->f2d;
@@ -514,8 +632,12 @@ int pdo_padepoisson_get_pressure(pdo_padepoisson_t p, const double* uhat, const 
 int pdo_padepoisson_get_pressure_and_update_rhs(pdo_padepoisson_t p, double* uhat, double* vhat, double* what, double* pressure,
                                                 void* stream) {
     if (!p || !uhat || !vhat || !what || !pressure) return fail(PDO_E_BADARG, "null argument");
-    if (!p->periodic_in_z) return fail(PDO_E_UNSUPPORTED, "padepoisson getPressureAndUpdateRHS: only PressureProjection and DivergenceCheck are built for PeriodicInZ = .false.");
     cudaStream_t st = (cudaStream_t)stream;
+    if (!p->periodic_in_z)   // walls (:963-1160): the projection in place, then its pressure (with the Stokes pieces of the last getPressure)
+        return with_uvw(p, uhat, vhat, what, true, st, [&](double2* u, double2* v, double2* w) -> int {
+            if (int rc = poiss_wall_projection(p, u, v, w, st, false)) return rc;
+            return poiss_wall_pressure_out(p, pressure, st);
+        });
     return with_uvw(p, uhat, vhat, what, true, st, [&](double2* u, double2* v, double2* w) -> int {
         if (int rc = poiss_projection(p, u, v, w, st)) return rc;  // leaves phat at phat_y
         const size_t bytes = sizeof(double) * (size_t)vol(p->sp->pi.xsz);

@@ -14,6 +14,7 @@ struct pdo_spectral_s {
     double normfactz = 1.0;
     std::vector<double> h_k1, h_k2, h_gx, h_gy, h_gz;  // global 1-D tables (nxh, ny, nxh, ny, nz)
     double *k1y = nullptr, *k2 = nullptr;               // local slice of k1 (ysz0 == zsz0 entries), full k2
+    double* k2z = nullptr;                              // y slice of k2 owned by the z-pencil
     double *gx = nullptr, *gy = nullptr, *gyz = nullptr, *gz = nullptr;  // dealias masks: x slice, y full, y slice of the z-pencil, z
     double2* ctmpz = nullptr;
     double* partial = nullptr;  // reduction scratch
@@ -136,6 +137,14 @@ int spectral_mask_z(pdo_spectral_s* s, double2* a, double scale, cudaStream_t st
     });
 }
 
+// the z-pencil part of dealias (spectral.F90:343-363) on a z-pencil array of the spectral decomposition, in place
+int spectral_dealias_zwork(pdo_spectral_s* s, double2* work, cudaStream_t st) {
+    if (int rc = fft3d_z_inplace(s->ft, work, -1, st)) return rc;
+    if (fft3d_own_z(s->ft)) return fft3d_z_pro(s->ft, work, work, +1, s->gx, s->gyz, s->gz, s->normfactz, st);   // mask and 1/nz on the first load
+    if (int rc = spectral_mask_z(s, work, s->normfactz, st)) return rc;
+    return fft3d_z_inplace(s->ft, work, +1, st);  // take_ifftz
+}
+
 int spectral_dealias(pdo_spectral_s* s, double2* fhat, cudaStream_t st) {
     if (!s->periodicInZ) {  // 2-D mask (spectral.F90:329-338 with the table of :1147-1159)
         const int n1 = s->si.ysz[0], n2 = s->si.ysz[1];
@@ -153,26 +162,14 @@ int spectral_dealias(pdo_spectral_s* s, double2* fhat, cudaStream_t st) {
         work = s->ctmpz;
         if (int rc = decomp_transpose_device(spec, 2, (const double*)fhat, (double*)work, 2, st)) return rc;  // take_fftz
     }
-    if (int rc = fft3d_z_inplace(s->ft, work, -1, st)) return rc;
-    if (fft3d_own_z(s->ft)) {   // the mask and 1/nz ride on the first load of the inverse pass
-        if (int rc = fft3d_z_pro(s->ft, work, work, +1, s->gx, s->gyz, s->gz, s->normfactz, st)) return rc;
-    } else {
-        if (int rc = spectral_mask_z(s, work, s->normfactz, st)) return rc;
-        if (int rc = fft3d_z_inplace(s->ft, work, +1, st)) return rc;  // take_ifftz
-    }
+    if (int rc = spectral_dealias_zwork(s, work, st)) return rc;
     if (s->p_col > 1) return decomp_transpose_device(spec, 3, (const double*)work, (double*)fhat, 2, st);
     return 0;
 }
 
 int spectral_dealias_edge(pdo_spectral_s* s, double2* fE, cudaStream_t st) {
     if (!s->periodicInZ) return 0;  // the reference does nothing on this branch (spectral.F90:348)
-    if (int rc = fft3d_z_inplace(s->ft, fE, -1, st)) return rc;
-    if (fft3d_own_z(s->ft)) {
-        if (int rc = fft3d_z_pro(s->ft, fE, fE, +1, s->gx, s->gyz, s->gz, s->normfactz, st)) return rc;
-    } else {
-        if (int rc = spectral_mask_z(s, fE, s->normfactz, st)) return rc;
-        if (int rc = fft3d_z_inplace(s->ft, fE, +1, st)) return rc;
-    }
+    if (int rc = spectral_dealias_zwork(s, fE, st)) return rc;
     const size_t plane = (size_t)s->si.zsz[0] * s->si.zsz[1];
     PDO_CUDA(cudaMemcpyAsync(fE + plane * s->nz, fE, sizeof(double2) * plane, cudaMemcpyDeviceToDevice, st));  // :361
     return 0;
@@ -225,6 +222,7 @@ int pdo_spectral_init(pdo_spectral_t* h, int nx, int ny, int nz, double dx, doub
     if (!rc) rc = upload(&s->gx, s->h_gx, i0, ni);
     if (!rc) rc = upload(&s->gy, s->h_gy, 0, ny);
     if (!rc) rc = upload(&s->gyz, s->h_gy, s->si.zst[1] - 1, s->si.zsz[1]);
+    if (!rc) rc = upload(&s->k2z, s->h_k2, s->si.zst[1] - 1, s->si.zsz[1]);
     if (!rc) rc = upload(&s->gz, s->h_gz, 0, nz);
     if (!rc && s->periodicInZ && p_col > 1) {
         rc = comm_shared_malloc((void**)&s->ctmpz, sizeof(double2) * (size_t)vol(s->si.zsz));
@@ -240,7 +238,7 @@ int pdo_spectral_init(pdo_spectral_t* h, int nx, int ny, int nz, double dx, doub
 
 int pdo_spectral_destroy(pdo_spectral_t s) {
     if (!s) return 0;
-    double* ptrs[] = {s->k1y, s->k2, s->gx, s->gy, s->gyz, s->gz, s->partial};
+    double* ptrs[] = {s->k1y, s->k2, s->k2z, s->gx, s->gy, s->gyz, s->gz, s->partial};
     for (double* p : ptrs) if (p) cudaFree(p);
     comm_shared_free(s->ctmpz);
     if (s->ztab) cudaFree(s->ztab);

@@ -26,6 +26,7 @@
 // This file keeps the helpers and the igrid handle itself (state, RK stages, right-hand side, restart files).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -137,6 +138,11 @@ struct pdo_igrid_s {
     double2 *cur[3];
     double2 *whatC, *uEhat, *vEhat, *d2u, *d2v, *d2w;
     double2 *yC[2], *yE[2], *zC[2], *zE[2];
+    // decomposed column communicator (not alias), periodic in z: z-pencil copies of cur[0..2].  project_and_prep takes the three
+    // fields to the z-pencil ONCE, dealiases and projects them there and brings them back once; the interpolations and the
+    // z-derivatives that follow read these copies instead of transposing the same arrays again (16 -> 6 transposes)
+    double2 *zU = nullptr, *zV = nullptr, *zW = nullptr;
+    bool zviews_valid = false;
     // terms of the advection right-hand side, each in its own y-pencil array until ONE assembly pass per component sums them,
     // applies the -1/2 and adds the viscous term (replaces the reference's chain of in-place adds, igrid.F90:1572-1679, 1914-1941).
     // cell: 0 A_u 1 P_u 2 F_uu 3 B_u 4 A_v 5 P_v 6 F_vv 7 B_v 8 F_uv; edge: 0 A_w 1 P_w 2 B_w 3 F_uEw 4 F_vEw
@@ -235,14 +241,16 @@ int ig_dealias_fields(pdo_igrid_s* g, cudaStream_t st) {
 // ---- igrid.F90:1423-1447
 int ig_interp_primitive(pdo_igrid_s* g, cudaStream_t st) {
     const double2* z = nullptr;
-    IG(zviewE(g, g->cur[2], g->zE[0], &z, st));
+    if (g->zviews_valid) z = g->zW;
+    else IG(zviewE(g, g->cur[2], g->zE[0], &z, st));
     double2* t = ztarget(g, g->whatC, g->zC[0]);
     ZOPB(pdo_pade6stagg_interpz_E2C, z, t, BC_W);
     IG(zcommitC(g, t, g->whatC, st));
     IG(ifftC(g, g->whatC, g->wC, st));
     for (int c = 0; c < 2; ++c) {
         double2* eh = c == 0 ? g->uEhat : g->vEhat;
-        IG(zviewC(g, g->cur[c], g->zC[0], &z, st));
+        if (g->zviews_valid) z = c == 0 ? g->zU : g->zV;
+        else IG(zviewC(g, g->cur[c], g->zC[0], &z, st));
         t = ztarget(g, eh, g->zE[0]);
         ZOPB(pdo_pade6stagg_interpz_C2E, z, t, c == 0 ? BC_U : BC_V);
         IG(zcommitE(g, t, eh, st));
@@ -274,7 +282,8 @@ int ig_compute_duidxj(pdo_igrid_s* g, cudaStream_t st) {
     IG(dC(2, g->whatC, g->gradC[7])); IG(dE(2, g->cur[2], g->gradE[7]));
     // dwdz (and its edge interpolant), d2wdz2
     const double2* wz = nullptr;
-    IG(zviewE(g, g->cur[2], g->zE[0], &wz, st));
+    if (g->zviews_valid) wz = g->zW;
+    else IG(zviewE(g, g->cur[2], g->zE[0], &wz, st));
     double2* dwz = ztarget(g, g->yC[0], g->zC[0]);
     ZOPB(pdo_pade6stagg_ddz_E2C, wz, dwz, BC_W);
     IG(zcommitC(g, dwz, g->yC[0], st));
@@ -293,7 +302,8 @@ int ig_compute_duidxj(pdo_igrid_s* g, cudaStream_t st) {
     // dudz / dvdz on edges, their cell interpolants, and the viscous second derivatives
     for (int c = 0; c < 2; ++c) {
         const double2* fz = nullptr;
-        IG(zviewC(g, g->cur[c], g->zC[0], &fz, st));
+        if (g->zviews_valid) fz = c == 0 ? g->zU : g->zV;
+        else IG(zviewC(g, g->cur[c], g->zC[0], &fz, st));
         double2* te = ztarget(g, g->yE[0], g->zE[0]);
         ZOPB(pdo_pade6stagg_ddz_C2E, fz, te, c == 0 ? BC_U : BC_V);
         IG(zcommitE(g, te, g->yE[0], st));
@@ -485,6 +495,29 @@ int ig_rhs_and_update(pdo_igrid_s* g, double2** r, int dst_slot, int nterms, con
 
 // ---- igrid.F90:1961-1990
 int ig_project_and_prep(pdo_igrid_s* g, bool already_projected, cudaStream_t st) {
+    g->zviews_valid = false;
+    const bool check_now = g->prm.t_divergence_check > 0 && g->step % g->prm.t_divergence_check == 0;
+    if (g->zU && !already_projected && !check_now) {
+        // z-resident form: to the z-pencil once, dealias (spectral.F90:343-363) and project (PadePoisson.F90:386-432) there, back once
+        IG(y2zC(g, g->cur[0], g->zU, st));
+        IG(y2zC(g, g->cur[1], g->zV, st));
+        IG(y2zE(g, g->cur[2], g->zW, st));
+        IG(spectral_dealias_zwork(g->spC, g->zU, st));
+        IG(spectral_dealias_zwork(g->spC, g->zV, st));
+        IG(spectral_dealias_edge(g->spC, g->zW, st));
+        IG(poiss_projection_z(g->poiss, g->zU, g->zV, g->zW, st));
+        IG(z2yC(g, g->zU, g->cur[0], st));
+        IG(z2yC(g, g->zV, g->cur[1], st));
+        IG(z2yE(g, g->zW, g->cur[2], st));
+        g->zviews_valid = true;
+        IG(ifftC(g, g->cur[0], g->u, st));
+        IG(ifftC(g, g->cur[1], g->v, st));
+        IG(ifftE(g, g->cur[2], g->w, st));
+        IG(ig_interp_primitive(g, st));
+        const int rc = ig_compute_duidxj(g, st);
+        g->zviews_valid = false;   // the next stage update overwrites cur
+        return rc;
+    }
     IG(ig_dealias_fields(g, st));
     if (!already_projected) {
         IG(poiss_projection(g->poiss, g->cur[0], g->cur[1], g->cur[2], st));
@@ -660,6 +693,11 @@ int pdo_igrid_init(pdo_igrid_t* h, const pdo_igrid_params* p, const double* u, c
     if (rc) { pdo_igrid_destroy(g); return rc; }
     g->dC = fft3d_spec_decomp(g->spC->ft); g->dE = fft3d_spec_decomp(g->spE->ft);
     g->alias = (g->spC->p_col == 1);
+    if (const char* e = std::getenv("PDO_IG_FORCE_TRANSPOSES")) {
+        // test switch: run the decomposed-grid code path (explicit y <-> z transposes, z-resident projection) on one rank,
+        // where every transpose is a device copy
+        if (e[0] == '1') g->alias = false;
+    }
     g->nRC = vol(g->gC.xsz); g->nRE = vol(g->gE.xsz);
     g->nYC = vol(g->sC.ysz); g->nYE = vol(g->sE.ysz);
     g->nZC = vol(g->sC.zsz); g->nZE = vol(g->sE.zsz);
@@ -676,6 +714,7 @@ int pdo_igrid_init(pdo_igrid_t* h, const pdo_igrid_params* p, const double* u, c
         for (int c = 0; c < 3; ++c) { g->S[s][c] = nullptr; if (s < nslots) AL(g->S[s][c], c < 2 ? g->nYC : g->nYE); }
     for (int c = 0; c < 3; ++c) { AL(g->R[c], c < 2 ? g->nYC : g->nYE); g->RX[c] = nullptr; if (p->time_stepping_scheme == 2) AL(g->RX[c], c < 2 ? g->nYC : g->nYE); }
     AL(g->whatC, g->nYC); AL(g->uEhat, g->nYE); AL(g->vEhat, g->nYE);
+    if (!g->alias && !p->wall_bounded) { AL(g->zU, g->nZC); AL(g->zV, g->nZC); AL(g->zW, g->nZE); }
     {   // right-hand-side terms (see TC / TE): the rotational form has two per horizontal component and one for w
         const bool rot = p->rotational_advection != 0;
         const bool needTC[9] = {true, true, !rot, !rot, true, true, !rot, !rot, !rot};

@@ -162,6 +162,36 @@ def test_igrid_substep_matches_oracle_broadband(pdo, IG, scheme, inviscid, shape
     assert g.maxDivergence() < 1e-11 * scale
 
 
+@pytest.mark.parametrize("shape", [(24, 16, 32), (16, 32, 32)])
+@pytest.mark.parametrize("scheme,adv,vert", [(1, 1, 1), (2, 0, 1), (1, 1, 2)])
+def test_igrid_decomposed_code_path_on_one_gpu(pdo, IG, monkeypatch, shape, scheme, adv, vert):
+    """PDO_IG_FORCE_TRANSPOSES=1 runs what a decomposed column communicator runs — explicit y <-> z transposes (device copies on one
+    rank) and the z-resident dealias + projection of project_and_prep — on a single GPU: against the oracle, and bit for bit against
+    the default single-GPU path (the same operations per element in another order of passes)."""
+    nx, ny, nz = shape
+    L = (2 * np.pi, 2 * np.pi, 2 * np.pi)
+    u, v = broadband((nz, ny, nx), 11), broadband((nz, ny, nx), 12)
+    w = broadband((nz + 1, ny, nx), 13)
+    w[nz] = w[0]
+    kw = dict(TimeSteppingScheme=scheme, AdvectionTerm=adv, NumericalSchemeVert=vert)
+    ref = IG.IGrid(nx, ny, nz, *L, 80.0, u, v, w, **kw)
+    ga = pdo.igrid()
+    ga.init(nx, ny, nz, *L, 80.0, u, v, w, **kw)
+    monkeypatch.setenv("PDO_IG_FORCE_TRANSPOSES", "1")
+    gt = pdo.igrid()
+    gt.init(nx, ny, nz, *L, 80.0, u, v, w, **kw)
+    monkeypatch.delenv("PDO_IG_FORCE_TRANSPOSES")
+    for it in range(2):
+        ref.timeAdvance(0.01)
+        ga.timeAdvance(0.01)
+        gt.timeAdvance(0.01)
+        for nm in ("u", "v", "w", "wC", "uhat", "vhat", "what"):
+            r = getattr(ref, nm)
+            assert np.abs(gt.get(nm) - r).max() < TOL * np.abs(r).max(), (it, nm)
+            assert np.array_equal(gt.get(nm), ga.get(nm)), (it, nm, "decomposed-path result differs from the single-GPU path")
+    assert gt.maxDivergence() < 1e-11 * max(np.abs(ref.u).max(), np.abs(ref.w).max())
+
+
 @pytest.mark.parametrize("direction", [1, 2])
 def test_igrid_taylor_green_decay_on_gpu(pdo, IG, direction):
     """problems/incompressible/TaylorGreenPeriodic: 32^3, Re = 100 — analytic decay exp(-2t/Re)."""

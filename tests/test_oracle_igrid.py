@@ -321,6 +321,45 @@ def test_no_slip_channel_stays_solenoidal_and_decays(walls):
         IG.IGrid(nx, ny, nz, L, L, Lz, 50.0, u, v, w, PeriodicInZ=False, botWall=3)
 
 
+@pytest.mark.parametrize("shape", [(16, 12, 16), (12, 16, 10)])
+def test_wall_pressure_getters_are_consistent_with_the_projection(shape):
+    """getPressure / getPressureAndUpdateRHS with walls (PadePoisson.F90:762-896, 963-1160).  Pins: (i) without the Stokes pressure
+    the projected right-hand sides ARE u - i k1 p, v - i k2 p for the pressure getPressure returns (every mode the c2r keeps);
+    (ii) getPressureAndUpdateRHS updates exactly as PressureProjection does; (iii) with computeStokesPressure the returned pressure
+    is phat + phat_z1 + phat_z2 with the pieces in the form the reference stores them (i chat cosh: its velocity correction is
+    u - k1 (phat_z1 + phat_z2), without another i — the pressure output keeps that factor, as the reference's does), and
+    getPressureAndUpdateRHS adds the pieces of the LAST getPressure call (:1146-1156)."""
+    nx, ny, nz = shape
+    L = 2 * np.pi
+    d = [L / nx, L / ny, L / nz]
+    spC, spE = IG.Spectral(nx, ny, nz, *d), IG.Spectral(nx, ny, nz + 1, *d)
+    ops = IG.Pade6stagg(nz, d[2], scheme=1, isPeriodic=False)
+    rng = np.random.default_rng(nx)
+    u, v, w = rng.standard_normal((nz, ny, nx)), rng.standard_normal((nz, ny, nx)), rng.standard_normal((nz + 1, ny, nx))
+    uh, vh, wh = spC.fft(u), spC.fft(v), spE.fft(w)
+    keep = np.ones((ny, nx // 2 + 1), bool)
+    keep[ny // 2, :] = False
+    keep[:, nx // 2] = False            # the oddball modes: ifft drops their imaginary parts
+    P = IG.PadePoisson(*d, spC, spE, ops, PeriodicInZ=False)
+    pr = P.getPressure(uh, vh, wh)
+    un, vn, wn = P.PressureProjection(uh, vh, wh)
+    ph = spC.fft(pr)
+    assert np.abs((un - (uh - 1j * spC.k1 * ph))[:, keep]).max() < 1e-13 * np.abs(un).max()
+    assert np.abs((vn - (vh - 1j * spC.k2 * ph))[:, keep]).max() < 1e-13 * np.abs(vn).max()
+    u2, v2, w2, p2 = P.getPressureAndUpdateRHS(uh, vh, wh)
+    assert np.array_equal(u2, un) and np.array_equal(v2, vn) and np.array_equal(w2, wn) and np.array_equal(p2, pr)
+    S = IG.PadePoisson(*d, spC, spE, ops, PeriodicInZ=False, computeStokesPressure=True, Lz=L)
+    u3, v3, w3, p3 = S.getPressureAndUpdateRHS(uh, vh, wh)          # no getPressure yet: no Stokes pieces in the pressure
+    us, vs, ws = S.PressureProjection(uh, vh, wh)
+    assert np.array_equal(u3, us) and np.array_equal(w3, ws)
+    prs = S.getPressure(uh, vh, wh)
+    pieces = S.phat_z1 + S.phat_z2
+    assert np.abs(prs - p3 - spC.ifft(pieces)).max() < 1e-12 * np.abs(prs).max()
+    f2d = spC.fft(p3)
+    assert np.abs((us - (uh - spC.k1 * pieces - 1j * spC.k1 * f2d))[:, keep]).max() < 1e-12 * np.abs(us).max()
+    assert np.array_equal(S.getPressureAndUpdateRHS(uh, vh, wh)[3], prs)
+
+
 def test_wall_projection_kernels_index_arithmetic():
     """csrc/igrid.cu poiss_wall_projection re-enacted in numpy with the kernels' own flat-index expressions (extension, fused
     solve + project with the complex products written out in components, extraction) against the oracle's array formulation."""

@@ -117,8 +117,19 @@ def test_wall_bounded_projection(pdo, oracle, shape):
         assert _rel(got.cpu().numpy(), ref) < TOL
     div, _ = po.DivergenceCheck(du, dv, dw)
     assert np.abs(div.cpu().numpy()).max() < 1e-11 * np.abs(rP.divergence(uh, vh, wh)).max()
-    with pytest.raises(pdo.PadeOpsError):
-        po.getPressure(du, dv, dw)                                               # periodic-only
+    # getPressure / getPressureAndUpdateRHS with walls (PadePoisson.F90:762-896, 963-1160): the inputs of getPressure are intent(in)
+    a, b, c = _dev(uh), _dev(vh), _dev(wh)
+    pr = po.getPressure(a, b, c).cpu().numpy()
+    assert _rel(pr, rP.getPressure(uh, vh, wh)) < TOL
+    assert np.array_equal(a.cpu().numpy(), uh) and np.array_equal(c.cpu().numpy(), wh)
+    pr2 = po.getPressureAndUpdateRHS(a, b, c).cpu().numpy()
+    wu, wv, ww, wp = rP.getPressureAndUpdateRHS(uh, vh, wh)
+    assert _rel(pr2, wp) < TOL
+    for got, ref in zip((a, b, c), (wu, wv, ww)):
+        assert _rel(got.cpu().numpy(), ref) < TOL
+    pr_host = np.empty_like(pr)
+    po.getPressure(uh.copy(), vh.copy(), wh.copy(), pr_host)                     # host-pointer (drop-in) path
+    assert _rel(pr_host, rP.getPressure(uh, vh, wh)) < TOL
     with pytest.raises(pdo.PadeOpsError):
         pdo.padepoisson().init(*d, spC, spE, derivZ=der, PeriodicInZ=True)      # periodicity of derivZ and the solver must agree
     # computeStokesPressure = .true. (:320-384): w* nonzero on the walls on input
@@ -134,3 +145,18 @@ def test_wall_bounded_projection(pdo, oracle, shape):
         assert _rel(got.cpu().numpy(), ref) < TOL
     div, _ = ps.DivergenceCheck(du, dv, dw)
     assert np.abs(div.cpu().numpy()).max() < 1e-11 * np.abs(rS.divergence(uhd, vhd, whs)).max()
+    # pressure getters with the Stokes pressure.  Reference quirk kept: getPressureAndUpdateRHS adds the Stokes pieces of the LAST
+    # getPressure call (it runs ProjectStokesPressure, which does not refresh phat_z1 / phat_z2; :1146-1156) — zero before any
+    a, b, c = _dev(uhd), _dev(vhd), _dev(whs)
+    p0 = ps.getPressureAndUpdateRHS(a, b, c).cpu().numpy()
+    wu, wv, ww, wp0 = rS.getPressureAndUpdateRHS(uhd, vhd, whs)
+    assert _rel(p0, wp0) < TOL
+    for got, ref in zip((a, b, c), (wu, wv, ww)):
+        assert _rel(got.cpu().numpy(), ref) < TOL
+    a, b, c = _dev(uhd), _dev(vhd), _dev(whs)
+    pr = ps.getPressure(a, b, c).cpu().numpy()
+    assert _rel(pr, rS.getPressure(uhd, vhd, whs)) < TOL
+    assert np.array_equal(a.cpu().numpy(), uhd) and np.array_equal(c.cpu().numpy(), whs)
+    p1 = ps.getPressureAndUpdateRHS(a, b, c).cpu().numpy()                       # now carries the pieces getPressure stored
+    assert _rel(p1, rS.getPressureAndUpdateRHS(uhd, vhd, whs)[3]) < TOL
+    assert np.abs(p1 - p0).max() > 1e-6 * np.abs(p1).max()
