@@ -768,6 +768,22 @@ bool fft2d_enabled() {
     return on == 1;
 }
 
+// Tables are built (device allocation + synchronous copy) here, at plan time, so that the passes themselves only launch kernels:
+// stream-ordered from the first call on and safe under stream capture.
+int fft2d_prepare_x(int nx) {
+    if (!fft2d_x_ok(nx)) return 0;
+    const double2* t = nullptr;
+    if (int rc = twiddles(nx, &t)) return rc;
+    if (int rc = stage_twiddles(nx / 2, &t)) return rc;
+    if (nx == 256 || nx == 512) return stage_twiddles(nx / 2, &t, 4);
+    return 0;
+}
+int fft2d_prepare_cols(int n) {
+    if (!fft2d_cols_ok(n)) return 0;
+    const double2* t = nullptr;
+    return stage_twiddles(n, &t);
+}
+
 int fft2d_cols(int n, long long ncols, long long nplanes, long long row_stride, long long plane_stride, const double2* in, double2* out,
                int dir, const FftPro& pro, cudaStream_t st) {
     if (!fft2d_cols_ok(n)) return fail(PDO_E_BADARG, "fft2d_cols: n = %d is not covered", n);

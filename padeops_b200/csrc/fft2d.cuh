@@ -41,7 +41,10 @@ struct RealPro {
 // extents the kernels cover: powers of two, 16 <= nx <= 2048 (x pass), 16 <= n <= 1024 (strided pass)
 bool fft2d_x_ok(int nx);
 bool fft2d_cols_ok(int n);
-bool fft2d_enabled();   // PDO_FFT=cufft turns the hand-written passes off (A/B measurements)
+bool fft2d_enabled();
+// build the twiddle tables of a transform length ahead of the first pass (plan time; the passes then only launch kernels)
+int fft2d_prepare_x(int nx);
+int fft2d_prepare_cols(int n);   // PDO_FFT=cufft turns the hand-written passes off (A/B measurements)
 
 // c2c along a strided axis: element (col, row, plane) at plane*plane_stride + row*row_stride + col, col < ncols, row < n.
 // dir = -1 forward (e^{-i}), +1 backward (unnormalised).  in == out is allowed (a tile of whole columns is read before it is written).

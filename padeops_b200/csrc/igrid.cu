@@ -714,7 +714,10 @@ int pdo_igrid_init(pdo_igrid_t* h, const pdo_igrid_params* p, const double* u, c
         for (int c = 0; c < 3; ++c) { g->S[s][c] = nullptr; if (s < nslots) AL(g->S[s][c], c < 2 ? g->nYC : g->nYE); }
     for (int c = 0; c < 3; ++c) { AL(g->R[c], c < 2 ? g->nYC : g->nYE); g->RX[c] = nullptr; if (p->time_stepping_scheme == 2) AL(g->RX[c], c < 2 ? g->nYC : g->nYE); }
     AL(g->whatC, g->nYC); AL(g->uEhat, g->nYE); AL(g->vEhat, g->nYE);
-    if (!g->alias && !p->wall_bounded) { AL(g->zU, g->nZC); AL(g->zV, g->nZC); AL(g->zW, g->nZE); }
+    {
+        const char* e = std::getenv("PDO_IG_ZRESIDENT");   // "0": the reference's pass structure (A/B measurements)
+        if (!g->alias && !p->wall_bounded && !(e && e[0] == '0')) { AL(g->zU, g->nZC); AL(g->zV, g->nZC); AL(g->zW, g->nZE); }
+    }
     {   // right-hand-side terms (see TC / TE): the rotational form has two per horizontal component and one for w
         const bool rot = p->rotational_advection != 0;
         const bool needTC[9] = {true, true, !rot, !rot, true, true, !rot, !rot, !rot};

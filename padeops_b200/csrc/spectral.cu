@@ -377,6 +377,9 @@ int pdo_fft3d_init(pdo_fft3d_t* h, int nx, int ny, int nz, double dx, double dy,
     f->slab2d = (p_row == 1);
     f->own_xy = f->slab2d && fft2d_enabled() && fft2d_x_ok(nx) && fft2d_cols_ok(ny);
     f->own_z = fft2d_enabled() && fft2d_cols_ok(nz);
+    if (f->own_xy) { rc = fft2d_prepare_x(nx); if (!rc) rc = fft2d_prepare_cols(ny); }
+    if (!rc && f->own_z) rc = fft2d_prepare_cols(nz);
+    if (rc) { pdo_fft3d_destroy(f); return rc; }
     const long long ny_c = cvol(f->si.ysz), nz_c = cvol(f->si.zsz), nx_c = cvol(f->si.xsz);
     // scratch pencils are transpose destinations: peer-writable for the fused NVLink path (collective, same order everywhere)
     rc = pdo::comm_shared_malloc((void**)&f->bufY, sizeof(double2) * (size_t)ny_c);
