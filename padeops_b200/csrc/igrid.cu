@@ -143,6 +143,7 @@ struct pdo_igrid_s {
     // z-derivatives that follow read these copies instead of transposing the same arrays again (16 -> 6 transposes)
     double2 *zU = nullptr, *zV = nullptr, *zW = nullptr;
     bool zviews_valid = false;
+    double2* zAcc[3] = {nullptr, nullptr, nullptr};   // z-pencil sums of the two z-operator terms of ru, rv (cell), rw (edge)
     // terms of the advection right-hand side, each in its own y-pencil array until ONE assembly pass per component sums them,
     // applies the -1/2 and adds the viscous term (replaces the reference's chain of in-place adds, igrid.F90:1572-1679, 1914-1941).
     // cell: 0 A_u 1 P_u 2 F_uu 3 B_u 4 A_v 5 P_v 6 F_vv 7 B_v 8 F_uv; edge: 0 A_w 1 P_w 2 B_w 3 F_uEw 4 F_vEw
@@ -329,11 +330,22 @@ int ig_compute_duidxj(pdo_igrid_s* g, cudaStream_t st) {
     return 0;
 }
 
-// ---- igrid.F90:1572-1679: the terms of (ru, rv, rw), left in TC / TE with the assembly recipes in g->asmd
+// dst += src on z-pencil arrays (complex viewed as doubles)
+int zadd(double2* dst, const double2* src, long long n, cudaStream_t st) {
+    double* d = (double*)dst;
+    const double* q = (const double*)src;
+    return launch_ew(2 * n, st, [=] __device__(long long i) { d[i] += q[i]; });
+}
+
+// ---- igrid.F90:1572-1679: the terms of (ru, rv, rw), left in TC / TE with the assembly recipes in g->asmd.
+// Each component has TWO terms that come out of a staggered z-operator (A = interp(fft(d./dz w)), B = ddz(fft(. w))); they are summed
+// first.  On a decomposed column communicator that sum is formed in the z-pencil (g->zAcc) and travels back as ONE array: three
+// transposes less per substep; on one column the assembly pass forms the same sum (same operations, bit-identical results).
 int ig_nonlinear_skew(pdo_igrid_s* g, cudaStream_t st) {
     double2 *fT1C = g->yC[0], *fT1E = g->yE[0];
     double2 **TC = g->TC, **TE = g->TE;
     double **GC = g->gradC, **GE = g->gradE;
+    const bool zsum = !g->alias && g->zAcc[0];
     const double2* z = nullptr;
     double2* t = nullptr;
     // u_rhs = interp_E2C(fft(dudz w)) + fft(dudx u + dudy v); same for v
@@ -341,17 +353,17 @@ int ig_nonlinear_skew(pdo_igrid_s* g, cudaStream_t st) {
         IG(fft_mul2(g, false, TC[4 * c + 1], GC[3 * c + 0], g->u, GC[3 * c + 1], g->v, st));
         IG(fft_mul2(g, true, fT1E, GE[3 * c + 2], g->w, nullptr, nullptr, st));
         IG(zviewE(g, fT1E, g->zE[0], &z, st));
-        t = ztarget(g, TC[4 * c + 0], g->zC[0]);
+        t = zsum ? g->zAcc[c] : ztarget(g, TC[4 * c + 0], g->zC[0]);
         ZOPB(pdo_pade6stagg_interpz_E2C, z, t, c == 0 ? BC_WdUdz : BC_WdVdz);
-        IG(zcommitC(g, t, TC[4 * c + 0], st));
+        if (!zsum) IG(zcommitC(g, t, TC[4 * c + 0], st));
     }
     // w_rhs = interp_C2E(fft(dwdz wC)) + fft(dwdx uE + dwdy vE)
     IG(fft_mul2(g, true, TE[1], GE[6], g->uE, GE[7], g->vE, st));
     IG(fft_mul2(g, false, fT1C, GC[8], g->wC, nullptr, nullptr, st));
     IG(zviewC(g, fT1C, g->zC[0], &z, st));
-    t = ztarget(g, TE[0], g->zE[0]);
+    t = zsum ? g->zAcc[2] : ztarget(g, TE[0], g->zE[0]);
     ZOPB(pdo_pade6stagg_interpz_C2E, z, t, BC_WdWdz);
-    IG(zcommitE(g, t, TE[0], st));
+    if (!zsum) IG(zcommitE(g, t, TE[0], st));
     // conservative half: d(uu)/dx, d(vv)/dy, d(wC wC)/dz, d(uv)/dy & /dx, d(uE w)/dz & /dx, d(vE w)/dz & /dy
     IG(fft_mul2(g, false, TC[2], g->u, g->u, nullptr, nullptr, st));
     IG(fft_mul2(g, false, TC[6], g->v, g->v, nullptr, nullptr, st));
@@ -359,19 +371,30 @@ int ig_nonlinear_skew(pdo_igrid_s* g, cudaStream_t st) {
     IG(zviewC(g, fT1C, g->zC[0], &z, st));
     t = ztarget(g, TE[2], g->zE[0]);
     ZOPB(pdo_pade6stagg_ddz_C2E, z, t, BC_WW);
-    IG(zcommitE(g, t, TE[2], st));
+    if (zsum) {
+        IG(zadd(g->zAcc[2], t, g->nZE, st));
+        IG(z2yE(g, g->zAcc[2], TE[0], st));
+    } else IG(zcommitE(g, t, TE[2], st));
     IG(fft_mul2(g, false, TC[8], g->u, g->v, nullptr, nullptr, st));
     for (int c = 0; c < 2; ++c) {
         IG(fft_mul2(g, true, TE[3 + c], c == 0 ? g->uE : g->vE, g->w, nullptr, nullptr, st));
         IG(zviewE(g, TE[3 + c], g->zE[0], &z, st));
         t = ztarget(g, TC[4 * c + 3], g->zC[0]);
         ZOPB(pdo_pade6stagg_ddz_E2C, z, t, c == 0 ? BC_UW : BC_VW);
-        IG(zcommitC(g, t, TC[4 * c + 3], st));
+        if (zsum) {
+            IG(zadd(g->zAcc[c], t, g->nZC, st));
+            IG(z2yC(g, g->zAcc[c], TC[4 * c + 0], st));
+        } else IG(zcommitC(g, t, TC[4 * c + 3], st));
     }
-    // the order of the sums is the reference's order of in-place adds
-    g->asmd[0] = {{{TC[0], 0}, {TC[1], 0}, {TC[2], 1}, {TC[8], 2}, {TC[3], 0}}, 5};
-    g->asmd[1] = {{{TC[4], 0}, {TC[5], 0}, {TC[6], 2}, {TC[8], 1}, {TC[7], 0}}, 5};
-    g->asmd[2] = {{{TE[0], 0}, {TE[1], 0}, {TE[2], 0}, {TE[3], 1}, {TE[4], 2}}, 5};
+    if (zsum) {
+        g->asmd[0] = {{{TC[0], 0}, {TC[1], 0}, {TC[2], 1}, {TC[8], 2}}, 4};
+        g->asmd[1] = {{{TC[4], 0}, {TC[5], 0}, {TC[6], 2}, {TC[8], 1}}, 4};
+        g->asmd[2] = {{{TE[0], 0}, {TE[1], 0}, {TE[3], 1}, {TE[4], 2}}, 4};
+    } else {
+        g->asmd[0] = {{{TC[0], 0}, {TC[3], 0}, {TC[1], 0}, {TC[2], 1}, {TC[8], 2}}, 5};
+        g->asmd[1] = {{{TC[4], 0}, {TC[7], 0}, {TC[5], 0}, {TC[6], 2}, {TC[8], 1}}, 5};
+        g->asmd[2] = {{{TE[0], 0}, {TE[2], 0}, {TE[1], 0}, {TE[3], 1}, {TE[4], 2}}, 5};
+    }
     return 0;
 }
 
@@ -717,6 +740,7 @@ int pdo_igrid_init(pdo_igrid_t* h, const pdo_igrid_params* p, const double* u, c
     {
         const char* e = std::getenv("PDO_IG_ZRESIDENT");   // "0": the reference's pass structure (A/B measurements)
         if (!g->alias && !p->wall_bounded && !(e && e[0] == '0')) { AL(g->zU, g->nZC); AL(g->zV, g->nZC); AL(g->zW, g->nZE); }
+        if (!g->alias && !p->rotational_advection && !(e && e[0] == '0')) { AL(g->zAcc[0], g->nZC); AL(g->zAcc[1], g->nZC); AL(g->zAcc[2], g->nZE); }
     }
     {   // right-hand-side terms (see TC / TE): the rotational form has two per horizontal component and one for w
         const bool rot = p->rotational_advection != 0;
