@@ -133,6 +133,8 @@ _PROTOS.update({
     "pdo_spectral_take_fft1d_z2z_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "pdo_spectral_take_ifft1d_z2z_ip": (C.c_int, [C.c_void_p, c_dp, C.c_void_p]),
     "pdo_debug_ztables": (C.c_int, [C.c_int, C.c_double, c_dp]),
+    "pdo_debug_fft_plan": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "pdo_debug_fft_tables": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "pdo_lstsq_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "pdo_lstsq_destroy": (C.c_int, [C.c_void_p]),
     "pdo_lstsq_filter1": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_int, C.c_void_p]),

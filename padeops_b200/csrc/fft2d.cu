@@ -576,12 +576,9 @@ fft_c2r_kernel(const double2* __restrict__ in, double* __restrict__ out, long lo
 std::mutex g_tw_mutex;
 std::map<int, double2*> g_tw;
 
-// exp(-2 pi i j / n), j < n, from long double sines of the first octant
-int twiddles(int n, const double2** out) {
-    std::lock_guard<std::mutex> lk(g_tw_mutex);
-    auto it = g_tw.find(n);
-    if (it != g_tw.end()) { *out = it->second; return 0; }
-    std::vector<double2> h((size_t)n);
+// exp(-2 pi i j / n), j < n, from long double sines of the first octant (host)
+void twiddles_host(int n, std::vector<double2>& h) {
+    h.resize((size_t)n);
     const long double two_pi = 6.283185307179586476925286766559005768L;
     for (int j = 0; j < n; ++j) {
         // reduce to the first octant so that symmetric entries are exact mirror images
@@ -604,6 +601,13 @@ int twiddles(int n, const double2** out) {
         }
         h[(size_t)j] = make_double2((double)c, (double)(-s));
     }
+}
+int twiddles(int n, const double2** out) {
+    std::lock_guard<std::mutex> lk(g_tw_mutex);
+    auto it = g_tw.find(n);
+    if (it != g_tw.end()) { *out = it->second; return 0; }
+    std::vector<double2> h;
+    twiddles_host(n, h);
     double2* d = nullptr;
     PDO_CUDA(cudaMalloc(&d, sizeof(double2) * (size_t)n));
     PDO_CUDA(cudaMemcpy(d, h.data(), sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice));
@@ -623,23 +627,14 @@ void fill_stage_tables(const std::vector<double2>& flat, std::vector<double2>& o
             for (int p = 0; p < NP; ++p) out[(size_t)P::toff(i) + (size_t)(k - 1) * NP + p] = flat[(size_t)((long long)s * p * k) % P::N];
     }
 }
-std::map<int, double2*> g_stw;
-int stage_twiddles(int n, const double2** out, int loge = 3) {
-    const int key = n * 8 + loge;
-    {
-        std::lock_guard<std::mutex> lk(g_tw_mutex);
-        auto it = g_stw.find(key);
-        if (it != g_stw.end()) { *out = it->second; return 0; }
-    }
-    const double2* flat_dev = nullptr;
-    if (int rc = twiddles(n, &flat_dev)) return rc;
-    std::vector<double2> flat((size_t)n), tab;
-    PDO_CUDA(cudaMemcpy(flat.data(), flat_dev, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost));
+// host: the stage tables of the plan (n, points per thread 2^loge); false when no such plan is compiled
+bool stage_tables_host(int n, int loge, const std::vector<double2>& flat, std::vector<double2>& tab) {
     if (loge == 4) {
         if (n == 128) fill_stage_tables<7, 4>(flat, tab);
         else if (n == 256) fill_stage_tables<8, 4>(flat, tab);
-        else return fail(PDO_E_BADARG, "stage_twiddles: no radix-16 plan for n = %d", n);
-    } else
+        else return false;
+        return true;
+    }
     switch (n) {
         case 8: fill_stage_tables<3>(flat, tab); break;
         case 16: fill_stage_tables<4>(flat, tab); break;
@@ -649,8 +644,21 @@ int stage_twiddles(int n, const double2** out, int loge = 3) {
         case 256: fill_stage_tables<8>(flat, tab); break;
         case 512: fill_stage_tables<9>(flat, tab); break;
         case 1024: fill_stage_tables<10>(flat, tab); break;
-        default: return fail(PDO_E_BADARG, "stage_twiddles: n = %d", n);
+        default: return false;
     }
+    return true;
+}
+std::map<int, double2*> g_stw;
+int stage_twiddles(int n, const double2** out, int loge = 3) {
+    const int key = n * 8 + loge;
+    {
+        std::lock_guard<std::mutex> lk(g_tw_mutex);
+        auto it = g_stw.find(key);
+        if (it != g_stw.end()) { *out = it->second; return 0; }
+    }
+    std::vector<double2> flat, tab;
+    twiddles_host(n, flat);
+    if (!stage_tables_host(n, loge, flat, tab)) return fail(PDO_E_BADARG, "stage_twiddles: no plan for n = %d, %d points per thread", n, 1 << loge);
     double2* d = nullptr;
     PDO_CUDA(cudaMalloc(&d, sizeof(double2) * tab.size()));
     PDO_CUDA(cudaMemcpy(d, tab.data(), sizeof(double2) * tab.size(), cudaMemcpyHostToDevice));
@@ -658,6 +666,19 @@ int stage_twiddles(int n, const double2** out, int loge = 3) {
     g_stw[key] = d;
     *out = d;
     return 0;
+}
+
+// host: the plan constants a kernel instance is compiled with
+template <int LOG2N, int LOGE>
+void plan_constants(int* out) {
+    using P = Plan<LOG2N, LOGE>;
+    out[0] = P::NS; out[1] = P::R0; out[2] = P::T; out[3] = P::E;
+    for (int i = 0; i < 4; ++i) {
+        out[4 + i] = i < P::NS ? P::radix(i) : 0;
+        out[8 + i] = i < P::NS ? P::stride(i) : 0;
+        out[12 + i] = i < P::NS ? P::npts(i) : 0;
+        out[16 + i] = i < P::NS ? P::toff(i) : 0;
+    }
 }
 
 int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
@@ -855,4 +876,38 @@ int fft2d_c2r_lines(int nx, long long nlines, const double2* in, double* out, cu
     return fail(PDO_E_BADARG, "fft2d_c2r: nx = %d", nx);
 }
 
+// test hooks (host only): the plan a transform length is compiled with, its stage tables and the flat twiddle table, so that the
+// CPU tests can re-enact the kernels' index algebra with the product's own constants (tests/test_fft_plan_cpu.py)
+namespace hooks {
+int fft_plan(int log2n, int loge, int* out20) {
+    if (!out20) return fail(PDO_E_BADARG, "null argument");
+    if (loge == 4) {
+        if (log2n == 7) { plan_constants<7, 4>(out20); return 0; }
+        if (log2n == 8) { plan_constants<8, 4>(out20); return 0; }
+        return fail(PDO_E_BADARG, "no radix-16 plan for 2^%d points", log2n);
+    }
+    switch (log2n) {
+        case 3: plan_constants<3, 3>(out20); return 0;
+        case 4: plan_constants<4, 3>(out20); return 0;
+        case 5: plan_constants<5, 3>(out20); return 0;
+        case 6: plan_constants<6, 3>(out20); return 0;
+        case 7: plan_constants<7, 3>(out20); return 0;
+        case 8: plan_constants<8, 3>(out20); return 0;
+        case 9: plan_constants<9, 3>(out20); return 0;
+        case 10: plan_constants<10, 3>(out20); return 0;
+    }
+    return fail(PDO_E_BADARG, "no plan for 2^%d points", log2n);
+}
+// out: n flat twiddles then the stage tables (complex as pairs of doubles); returns the number of complex entries written
+int fft_tables(int n, int loge, double* out, int capacity) {
+    std::vector<double2> flat, tab;
+    twiddles_host(n, flat);
+    if (!stage_tables_host(n, loge, flat, tab)) return fail(PDO_E_BADARG, "no plan for n = %d", n);
+    const int total = (int)(flat.size() + tab.size());
+    if (!out || capacity < total) return fail(PDO_E_BADARG, "capacity %d < %d", capacity, total);
+    std::memcpy(out, flat.data(), sizeof(double2) * flat.size());
+    std::memcpy(out + 2 * flat.size(), tab.data(), sizeof(double2) * tab.size());
+    return total;
+}
+}  // namespace hooks
 }  // namespace pdo

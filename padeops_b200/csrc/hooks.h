@@ -21,5 +21,7 @@ int zslab_emulate(void* handle, int which, const double* f, double* out, long lo
 int hit_draw(double kmin, double kmax, int nwaves, int tid_start, int rand_seed_to_add, int updates, long long seeds[4], int* wx, int* wy, int* wz);
 int ztables(int nz, double dz, double* out);
 int igrid_bcs(int bot_wall, int top_wall, int* out24);
+int fft_plan(int log2n, int loge, int* out20);
+int fft_tables(int n, int loge, double* out, int capacity);
 int sgs_point(int mid, double cmodel, double cx, double cy, double cz, const double* d9, double* nu, double* S6);
 }}  // namespace pdo::hooks

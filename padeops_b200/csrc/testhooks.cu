@@ -20,4 +20,6 @@ int pdo_debug_hit_draw(double kmin, double kmax, int nwaves, int tid_start, int 
 int pdo_debug_ztables(int nz, double dz, double* out) { return pdo::hooks::ztables(nz, dz, out); }
 int pdo_debug_igrid_bcs(int bot_wall, int top_wall, int* out24) { return pdo::hooks::igrid_bcs(bot_wall, top_wall, out24); }
 int pdo_debug_sgs_point(int mid, double cmodel, double cx, double cy, double cz, const double* d9, double* nu, double* S6) { return pdo::hooks::sgs_point(mid, cmodel, cx, cy, cz, d9, nu, S6); }
+int pdo_debug_fft_plan(int log2n, int loge, int* out20) { return pdo::hooks::fft_plan(log2n, loge, out20); }
+int pdo_debug_fft_tables(int n, int loge, double* out, int capacity) { return pdo::hooks::fft_tables(n, loge, out, capacity); }
 }  // extern "C"
