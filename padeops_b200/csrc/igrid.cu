@@ -520,15 +520,20 @@ int ig_rhs_and_update(pdo_igrid_s* g, double2** r, int dst_slot, int nterms, con
 int ig_project_and_prep(pdo_igrid_s* g, bool already_projected, cudaStream_t st) {
     g->zviews_valid = false;
     const bool check_now = g->prm.t_divergence_check > 0 && g->step % g->prm.t_divergence_check == 0;
+    static const bool kz_on = [] { const char* e = std::getenv("PDO_IG_KZ"); return !(e && e[0] == '0'); }();
+    const bool kz = kz_on && g->poiss->symE2C && !g->prm.wall_bounded;   // dealias + project in kz-space (poiss_dealias_project_kz)
     if (g->zU && !already_projected && !check_now) {
         // z-resident form: to the z-pencil once, dealias (spectral.F90:343-363) and project (PadePoisson.F90:386-432) there, back once
         IG(y2zC(g, g->cur[0], g->zU, st));
         IG(y2zC(g, g->cur[1], g->zV, st));
         IG(y2zE(g, g->cur[2], g->zW, st));
-        IG(spectral_dealias_zwork(g->spC, g->zU, st));
-        IG(spectral_dealias_zwork(g->spC, g->zV, st));
-        IG(spectral_dealias_edge(g->spC, g->zW, st));
-        IG(poiss_projection_z(g->poiss, g->zU, g->zV, g->zW, st));
+        if (kz) IG(poiss_dealias_project_kz(g->poiss, g->zU, g->zV, g->zW, st));
+        else {
+            IG(spectral_dealias_zwork(g->spC, g->zU, st));
+            IG(spectral_dealias_zwork(g->spC, g->zV, st));
+            IG(spectral_dealias_edge(g->spC, g->zW, st));
+            IG(poiss_projection_z(g->poiss, g->zU, g->zV, g->zW, st));
+        }
         IG(z2yC(g, g->zU, g->cur[0], st));
         IG(z2yC(g, g->zV, g->cur[1], st));
         IG(z2yE(g, g->zW, g->cur[2], st));
@@ -540,6 +545,15 @@ int ig_project_and_prep(pdo_igrid_s* g, bool already_projected, cudaStream_t st)
         const int rc = ig_compute_duidxj(g, st);
         g->zviews_valid = false;   // the next stage update overwrites cur
         return rc;
+    }
+    if (g->alias && kz && !already_projected && !check_now) {
+        // one column: y- and z-pencils coincide, the same pass works on the stage arrays directly
+        IG(poiss_dealias_project_kz(g->poiss, g->cur[0], g->cur[1], g->cur[2], st));
+        IG(ifftC(g, g->cur[0], g->u, st));
+        IG(ifftC(g, g->cur[1], g->v, st));
+        IG(ifftE(g, g->cur[2], g->w, st));
+        IG(ig_interp_primitive(g, st));
+        return ig_compute_duidxj(g, st);
     }
     IG(ig_dealias_fields(g, st));
     if (!already_projected) {

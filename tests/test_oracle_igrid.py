@@ -360,6 +360,41 @@ def test_wall_pressure_getters_are_consistent_with_the_projection(shape):
     assert np.array_equal(S.getPressureAndUpdateRHS(uh, vh, wh)[3], prs)
 
 
+@pytest.mark.parametrize("scheme", [1, 2])
+@pytest.mark.parametrize("shape", [(16, 12, 16), (8, 8, 32)])
+def test_dealias_and_projection_in_kz_space_equal_the_reference_sequence(scheme, shape):
+    """What csrc/ig_padepoisson.inc.cuh: poiss_dealias_project_kz does, in numpy: the periodic z-operators are circulant, so with their
+    symbols (the transform of the response to a unit pulse — whatever the scheme) dealias (spectral.F90:343-363) followed by
+    PeriodicProjection (PadePoisson.F90:386-432) is ONE pointwise pass between a forward and a backward z transform per field.  It
+    must reproduce the statement-by-statement sequence to rounding."""
+    nx, ny, nz = shape
+    L = 2 * np.pi
+    d = [L / nx, L / ny, L / nz]
+    spC, spE = IG.Spectral(nx, ny, nz, *d, init_periodicInZ=True), IG.Spectral(nx, ny, nz + 1, *d)
+    ops = IG.Pade6stagg(nz, d[2], scheme=scheme)
+    P = IG.PadePoisson(*d, spC, spE, ops)
+    rng = np.random.default_rng(nz)
+    u, v, w = rng.standard_normal((nz, ny, nx)), rng.standard_normal((nz, ny, nx)), rng.standard_normal((nz + 1, ny, nx))
+    w[nz] = w[0]
+    uh, vh, wh = spC.fft(u), spC.fft(v), spE.fft(w)
+    want = P.PressureProjection(spC.dealias(uh), spC.dealias(vh), spC.dealias_edgeField(wh))
+    pulseE = np.zeros((nz + 1, 1, 1), complex)
+    pulseE[0] = pulseE[nz] = 1.0
+    pulseC = np.zeros((nz, 1, 1), complex)
+    pulseC[0] = 1.0
+    dE2C = np.fft.fft(ops.ddz_E2C(pulseE)[:, 0, 0])[:, None, None]
+    dC2E = np.fft.fft(ops.ddz_C2E(pulseC)[:nz, 0, 0])[:, None, None]
+    U, V, W = (spC.Gdealias * np.fft.fft(a, axis=0) for a in (uh, vh, wh[:nz]))
+    f = dE2C * W + 1j * spC.k1 * U + 1j * spC.k2 * V
+    p = -P.kradsq_inv * f
+    got_u = np.fft.ifft(U - 1j * spC.k1 * p, axis=0)
+    got_v = np.fft.ifft(V - 1j * spC.k2 * p, axis=0)
+    got_w = np.fft.ifft(W - dC2E * p, axis=0)
+    got_w = np.concatenate([got_w, got_w[:1]], axis=0)
+    for got, ref in zip((got_u, got_v, got_w), want):
+        assert np.abs(got - ref).max() < 1e-13 * np.abs(ref).max()
+
+
 def test_wall_projection_kernels_index_arithmetic():
     """csrc/igrid.cu poiss_wall_projection re-enacted in numpy with the kernels' own flat-index expressions (extension, fused
     solve + project with the complex products written out in components, extraction) against the oracle's array formulation."""
